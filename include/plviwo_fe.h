@@ -1,0 +1,212 @@
+/*
+ * plviwo_fe.h — C ABI of the B200-native PL-VIWO visual front end.
+ *
+ * One FeHandle = one camera stream (one ov_core::TrackKLT + one viw::TrackLSD for the same camera) bound to one
+ * CUDA device and its own CUDA streams.  The entry points are what a binding of the reference's tracker API
+ * would call (see INTEGRATION.md for the header-only ov_core adaptor):
+ *
+ *   reference interface                                               file:line                      replaced by
+ *   ----------------------------------------------------------------  -----------------------------  -------------------------
+ *   TrackKLT::TrackKLT(cameras, numfeats, numaruco, stereo, hist,     ov_core/src/track/TrackKLT.h:54-57,       plviwo_fe_create
+ *       fast_threshold, gridx, gridy, minpxdist)                      TrackBase.cpp:30-41
+ *   viw::TrackLSD::TrackLSD(cameras, stereo, hist, trackFEATS)        PL-VIWO/src/update/cam/TrackLSD.cpp:30-37  plviwo_fe_create (use_lines)
+ *   CamBase::set_value(calib) on the shared camera object             ov_core/src/cam/CamBase.h:56-82            plviwo_fe_set_calib
+ *   TrackKLT::feed_new_camera(const CameraData&)                      ov_core/src/track/TrackKLT.cpp:34-94       plviwo_fe_feed
+ *   TrackLSD::feed_new_camera(const CameraData&, vanishing_points)    PL-VIWO/src/update/cam/TrackLSD.cpp:39-68  plviwo_fe_feed (vp != NULL)
+ *   FeatureDatabase::update_feature(id,t,cam,u,v,un,vn) rows          ov_core/src/feat/FeatureDatabase.cpp:60-85 plviwo_fe_get_point_rows
+ *   TrackBase::get_last_obs() / get_last_ids()                        ov_core/src/track/TrackBase.h:137-146      plviwo_fe_get_last_obs
+ *   LineFeatureDatabase::update_feature(id,t,cam,line,line_n,...)     linefeat/LineFeatureDatabase.cpp:40-76     plviwo_fe_get_line_rows (+ _line_points)
+ *   TrackBase::set_num_features / change_feat_id                      ov_core/src/track/TrackBase.cpp:267-285    plviwo_fe_set_num_features / _change_feat_id
+ *   tracker members pts_last/ids_last/currid, lines_last/...          TrackBase.h:173-192, TrackLSD.h:248-279    plviwo_fe_get_state / _set_state
+ *
+ * No C++ types, no exceptions, no exit() cross this boundary: malformed input is FE_BAD_ARG where the reference
+ * calls std::exit(EXIT_FAILURE) (TrackKLT.cpp:37-43).  All pixel work runs in hand-written CUDA kernels for
+ * sm_100a; there is no CPU fallback — every entry point fails with FE_NO_DEVICE / FE_CUDA_ERROR instead.
+ *
+ * Threading (TrackBase.h:58-65): a handle is not re-entrant; distinct handles are independent and may be
+ * driven from different host threads and live on different GPUs (streams never exchange data).
+ */
+#ifndef PLVIWO_FE_H
+#define PLVIWO_FE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLVIWO_FE_ABI_VERSION 1
+
+typedef struct FeHandle FeHandle;
+
+enum FeStatus {
+  FE_OK = 0,
+  FE_BAD_ARG = 1,        /* malformed message / sizes do not match the handle          */
+  FE_NO_DEVICE = 2,      /* no usable CUDA device (never falls back to the CPU)        */
+  FE_CUDA_ERROR = 3,     /* a CUDA call failed; see plviwo_fe_last_error               */
+  FE_OVERFLOW = 4,       /* caller-provided output array too small (n_out = required)  */
+  FE_INTERNAL = 5
+};
+
+enum FeHistogramMethod { FE_HIST_NONE = 0, FE_HIST_HISTOGRAM = 1, FE_HIST_CLAHE = 2 }; /* TrackBase.h:78 */
+
+/* Every front-end knob: options/OptionsCamera.h:77-108 plus the constants the reference hard-codes
+ * (TrackKLT.h:143-144 pyr_levels/win_size, TrackLSD.h:269-273 FLD parameters, TrackLSD.cpp:231 length). */
+typedef struct FeConfig {
+  int32_t width, height;        /* image size; fixed for the lifetime of the handle                     */
+  int32_t num_features;         /* n_pts                                                                */
+  int32_t fast_threshold;
+  int32_t grid_x, grid_y;
+  int32_t min_px_dist;
+  int32_t pyr_levels;           /* OpenCV maxLevel (reference: 5) => pyr_levels + 1 images              */
+  int32_t win_size;             /* LK window (reference: 15); odd, <= 31                                */
+  int32_t histogram_method;     /* FeHistogramMethod; FE_HIST_CLAHE is not implemented (FE_BAD_ARG)     */
+  int32_t numaruco;             /* first point id = 4 * numaruco + 2 (TrackBase.cpp:34)                 */
+  int32_t use_lines;            /* OptionsCamera.h:108                                                  */
+  int32_t fld_length_threshold; /* 20                                                                   */
+  float fld_distance_threshold; /* 1.414213562f                                                         */
+  float canny_th1, canny_th2;   /* 50, 50 (aperture 3, L1 gradient)                                     */
+  float line_min_length;        /* 40 (TrackLSD.cpp:231)                                                */
+  int32_t line_samples;         /* extension (not in the reference): LK over this many points sampled   */
+                                /* along each of last frame's segments; 0 = off                         */
+  int32_t lookahead;            /* frames that plviwo_fe_submit may run ahead of plviwo_fe_collect      */
+  double K[4];                  /* fx fy cx cy                                                          */
+  double D[4];                  /* radtan k1 k2 p1 p2                                                   */
+} FeConfig;
+
+/* One FeatureDatabase::update_feature call (TrackKLT.cpp:176-179). */
+typedef struct FePointRow {
+  uint64_t id;
+  float u, v;     /* raw pixel                     */
+  float un, vn;   /* undistorted normalised coords */
+} FePointRow;
+
+/* One LineFeatureDatabase::update_feature call (TrackLSD.cpp:163-167).  The points attached to the line
+ * (point_on_lines map in ascending point id, and point_position in detection order) are stored contiguously;
+ * fetch them with plviwo_fe_get_line_points using [pt_offset, pt_offset + n_pts). */
+typedef struct FeLineRow {
+  uint64_t id;
+  float line[4];    /* x1 y1 x2 y2, full-resolution pixels */
+  float line_n[4];  /* undistorted normalised endpoints    */
+  int32_t D;        /* LineClassification: 3 z, 2 y, 1 x, 0 none */
+  int32_t n_pts;
+  int32_t pt_offset;
+  int32_t matched;  /* 1 if the id was inherited from last frame's line (LineMatch) */
+} FeLineRow;
+
+typedef struct FeLinePoint {
+  int32_t pid;      /* key of point_on_lines (ascending within a line)          */
+  float dist;       /* value of point_on_lines: point-to-segment distance       */
+  float u, v;       /* point_position entry k of the same line (detection order)*/
+} FeLinePoint;
+
+/* Per-frame outcome flags / counters (the reference only prints these). */
+typedef struct FeFrameInfo {
+  double timestamp;
+  int32_t n_point_rows;
+  int32_t n_line_rows;
+  int32_t n_last_obs;       /* size of pts_last after the frame                          */
+  int32_t reset;            /* 1: tracker cleared itself (TrackKLT.cpp:143-152)          */
+  int32_t first_frame;      /* 1: detection-only frame (TrackKLT.cpp:110-123)            */
+  int32_t n_detected;       /* points added by the top-off detection                    */
+  int32_t n_lk_in, n_klt_ok, n_ransac_ok;
+  int32_t n_lines_detected; /* segments longer than line_min_length                      */
+  int32_t n_line_matches;
+  int32_t detection_ran;
+  int32_t reserved;
+} FeFrameInfo;
+
+/* Stage timings accumulated with CUDA events on the handle's own streams (ms, and launch counts). */
+enum FeStage {
+  FE_STAGE_H2D = 0, FE_STAGE_HIST, FE_STAGE_EQ_PYR, FE_STAGE_PYR_REST, FE_STAGE_FAST, FE_STAGE_SUBPIX, FE_STAGE_LK,
+  FE_STAGE_CANNY, FE_STAGE_FLD, FE_STAGE_COUNT
+};
+typedef struct FeStageTimes {
+  double ms[16];
+  uint64_t launches[16];
+  uint64_t frames;
+  uint64_t kernel_launches_total;
+} FeStageTimes;
+
+/* ---- lifetime ----------------------------------------------------------------------------------------- */
+int plviwo_fe_abi_version(void);
+void plviwo_fe_default_config(FeConfig *cfg);                 /* reference defaults, KAIST cam0 calibration */
+int plviwo_fe_device_count(int *n);
+int plviwo_fe_create(const FeConfig *cfg, int device, FeHandle **out);
+int plviwo_fe_destroy(FeHandle *h);
+const char *plviwo_fe_last_error(const FeHandle *h);          /* h may be NULL: last create() error         */
+
+/* ---- per-frame ---------------------------------------------------------------------------------------- */
+/* Intrinsics are refined online by the estimator (StateHelper.cpp:166): call before feed whenever they change. */
+int plviwo_fe_set_calib(FeHandle *h, const double K[4], const double D[4]);
+int plviwo_fe_set_num_features(FeHandle *h, int num_features);
+int plviwo_fe_change_feat_id(FeHandle *h, uint64_t id_old, uint64_t id_new);
+
+/* Synchronous drop-in for feed_new_camera: image and mask are HOST buffers (8UC1, borrowed for the call);
+ * mask may be NULL (all zero); vp = 3 vanishing points (x0 y0 x1 y1 x2 y2) or NULL to skip the line tracker. */
+int plviwo_fe_feed(FeHandle *h, double timestamp, const uint8_t *image, int width, int height, int stride,
+                   const uint8_t *mask, int mask_stride, const double vp[6], FeFrameInfo *info);
+
+/* Same, with the image already resident in this handle's device memory (device pointer, pitch in bytes). */
+int plviwo_fe_feed_device(FeHandle *h, double timestamp, const void *d_image, int width, int height, int pitch,
+                          const uint8_t *mask, int mask_stride, const double vp[6], FeFrameInfo *info);
+
+/* Pipelined form for offline playback (run_bag.cpp indexes the whole bag first): submit() enqueues the
+ * state-independent work of a frame (copy, equalisation, pyramid, edge map, segment extraction) up to
+ * cfg.lookahead frames ahead; collect() finishes the oldest submitted frame in order and exposes its rows.
+ * Results are identical to calling plviwo_fe_feed frame by frame. */
+int plviwo_fe_submit(FeHandle *h, double timestamp, const uint8_t *image, int stride, int on_device,
+                     const uint8_t *mask, int mask_stride, const double vp[6]);
+int plviwo_fe_collect(FeHandle *h, FeFrameInfo *info);
+
+/* ---- results of the last completed frame -------------------------------------------------------------- */
+int plviwo_fe_get_point_rows(FeHandle *h, FePointRow *out, int cap, int *n_out);
+int plviwo_fe_get_last_obs(FeHandle *h, uint64_t *ids, float *uv /* 2 per point */, int cap, int *n_out);
+int plviwo_fe_get_line_rows(FeHandle *h, FeLineRow *out, int cap, int *n_out);
+int plviwo_fe_get_line_points(FeHandle *h, FeLinePoint *out, int cap, int *n_out);
+/* extension: LK-tracked samples of last frame's segments: per sample (line row index in the PREVIOUS frame,
+ * u0 v0 u1 v1, status) */
+int plviwo_fe_get_line_samples(FeHandle *h, float *uv01 /* 4 per sample */, uint8_t *status, int cap, int *n_out);
+
+/* ---- tracker state: teacher-forced parity tests, checkpoint / resume ---------------------------------- */
+/* Serialised into a caller buffer; *n_bytes returns the size needed / written.  Includes the previous frame's
+ * equalised image (the pyramid is rebuilt on set_state). */
+int plviwo_fe_get_state(FeHandle *h, void *buf, size_t cap, size_t *n_bytes);
+int plviwo_fe_set_state(FeHandle *h, const void *buf, size_t n_bytes);
+
+/* ---- debug / test taps (device results copied to host) ------------------------------------------------ */
+enum FeTap {
+  FE_TAP_PYR_LEVEL0 = 0,   /* .. FE_TAP_PYR_LEVEL0 + level : current pyramid images (8U, tight rows)          */
+  FE_TAP_HALF = 32,        /* half-resolution equalised image fed to the line detector                        */
+  FE_TAP_EDGES = 33,       /* Canny edge map, one byte per pixel (0 / 255), half resolution                   */
+  FE_TAP_FAST_LAST = 34,   /* last detection: int32 records (cell_x, cell_y, x, y, score) in reference order  */
+  FE_TAP_LK_LAST = 35,     /* last LK: float records (x0, y0, x1, y1, status_klt, status_ransac)              */
+  FE_TAP_SUBPIX_LAST = 36, /* last detection: float records (x_sel, y_sel, x_ref, y_ref)                      */
+  FE_TAP_FLD_LAST = 37     /* last line detection: float records (x1, y1, x2, y2) at half resolution          */
+};
+int plviwo_fe_tap(FeHandle *h, int what, void *buf, size_t cap, size_t *n_bytes);
+
+/* ---- measurement -------------------------------------------------------------------------------------- */
+int plviwo_fe_enable_timing(FeHandle *h, int on);   /* CUDA-event stage timing (adds event records only)   */
+int plviwo_fe_get_stage_times(FeHandle *h, FeStageTimes *out, int reset);
+
+/* ---- stand-alone kernels (tests / micro-benchmarks; all pointers are HOST buffers) --------------------- */
+int plviwo_op_equalize_pyramid(int device, const uint8_t *img, int w, int h, int levels /* maxLevel */,
+                               uint8_t *out_levels /* concatenated tight levels 0..maxLevel */, uint8_t *out_half);
+int plviwo_op_fast_cell(int device, const uint8_t *img, int w, int h, int threshold, int32_t *xys /* x y score */,
+                        int cap, int *n_out);
+int plviwo_op_corner_subpix(int device, const uint8_t *img, int w, int h, float *pts /* in/out 2 per point */, int n);
+int plviwo_op_lk(int device, const uint8_t *img0, const uint8_t *img1, int w, int h, int win, int max_level,
+                 const float *pts0, float *pts1 /* in: initial flow, out */, uint8_t *status, int n);
+int plviwo_op_undistort(int device, const float *pts, int n, const double K[4], const double D[4], float *out);
+int plviwo_op_canny_half(int device, const uint8_t *img, int w, int h, float th, uint8_t *edges /* w*h bytes */);
+int plviwo_op_fld(int device, const uint8_t *img, int w, int h, int length_threshold, float distance_threshold,
+                  float canny_th, float *lines /* 4 per segment */, int cap, int *n_out);
+int plviwo_op_ransac_fundamental(const float *p0n, const float *p1n, int n, double threshold, double confidence,
+                                 uint8_t *mask, int *n_inliers); /* host-side sequential step (K9) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLVIWO_FE_H */

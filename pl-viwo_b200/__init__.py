@@ -1,0 +1,476 @@
+"""plviwo_b200 — Python binding (ctypes) of the B200-native PL-VIWO visual front end.
+
+The product is ``libplviwo_fe.so`` (hand-written sm_100a kernels + C++ host trackers behind the C ABI in
+``include/plviwo_fe.h``).  This module only marshals NumPy arrays across that ABI for tests and benchmarks and
+mirrors the reference's tracker interface (``feed_new_camera``, ``get_last_obs``, ``get_last_ids``,
+``get_feature_database`` — ov_core/src/track/TrackBase.h:72-196, PL-VIWO/src/update/cam/TrackLSD.h:84-99).
+There is no CPU implementation behind it: if the library is missing or no GPU is present every compute call
+raises ``FrontEndError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libplviwo_fe.so")
+
+FE_OK, FE_BAD_ARG, FE_NO_DEVICE, FE_CUDA_ERROR, FE_OVERFLOW, FE_INTERNAL = range(6)
+HIST_NONE, HIST_HISTOGRAM, HIST_CLAHE = 0, 1, 2
+_STATUS = {0: "FE_OK", 1: "FE_BAD_ARG", 2: "FE_NO_DEVICE", 3: "FE_CUDA_ERROR", 4: "FE_OVERFLOW", 5: "FE_INTERNAL"}
+STAGES = ["h2d", "hist", "eq_pyr1", "pyr_rest", "fast", "subpix", "lk", "canny", "fld"]
+TAP_PYR_LEVEL0, TAP_HALF, TAP_EDGES, TAP_FAST_LAST, TAP_LK_LAST, TAP_SUBPIX_LAST, TAP_FLD_LAST = 0, 32, 33, 34, 35, 36, 37
+
+
+class FrontEndError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("%s: %s" % (_STATUS.get(code, code), msg))
+        self.code = code
+
+
+class FeConfig(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("num_features", C.c_int32), ("fast_threshold", C.c_int32),
+        ("grid_x", C.c_int32), ("grid_y", C.c_int32), ("min_px_dist", C.c_int32), ("pyr_levels", C.c_int32),
+        ("win_size", C.c_int32), ("histogram_method", C.c_int32), ("numaruco", C.c_int32), ("use_lines", C.c_int32),
+        ("fld_length_threshold", C.c_int32), ("fld_distance_threshold", C.c_float), ("canny_th1", C.c_float),
+        ("canny_th2", C.c_float), ("line_min_length", C.c_float), ("line_samples", C.c_int32), ("lookahead", C.c_int32),
+        ("K", C.c_double * 4), ("D", C.c_double * 4),
+    ]
+
+
+class FePointRow(C.Structure):
+    _fields_ = [("id", C.c_uint64), ("u", C.c_float), ("v", C.c_float), ("un", C.c_float), ("vn", C.c_float)]
+
+
+class FeLineRow(C.Structure):
+    _fields_ = [("id", C.c_uint64), ("line", C.c_float * 4), ("line_n", C.c_float * 4), ("D", C.c_int32),
+                ("n_pts", C.c_int32), ("pt_offset", C.c_int32), ("matched", C.c_int32)]
+
+
+class FeLinePoint(C.Structure):
+    _fields_ = [("pid", C.c_int32), ("dist", C.c_float), ("u", C.c_float), ("v", C.c_float)]
+
+
+class FeFrameInfo(C.Structure):
+    _fields_ = [("timestamp", C.c_double), ("n_point_rows", C.c_int32), ("n_line_rows", C.c_int32),
+                ("n_last_obs", C.c_int32), ("reset", C.c_int32), ("first_frame", C.c_int32), ("n_detected", C.c_int32),
+                ("n_lk_in", C.c_int32), ("n_klt_ok", C.c_int32), ("n_ransac_ok", C.c_int32),
+                ("n_lines_detected", C.c_int32), ("n_line_matches", C.c_int32), ("detection_ran", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class FeStageTimes(C.Structure):
+    _fields_ = [("ms", C.c_double * 16), ("launches", C.c_uint64 * 16), ("frames", C.c_uint64),
+                ("kernel_launches_total", C.c_uint64)]
+
+
+POINT_ROW_DTYPE = np.dtype([("id", "<u8"), ("u", "<f4"), ("v", "<f4"), ("un", "<f4"), ("vn", "<f4")])
+LINE_ROW_DTYPE = np.dtype([("id", "<u8"), ("line", "<f4", (4,)), ("line_n", "<f4", (4,)), ("D", "<i4"), ("n_pts", "<i4"),
+                           ("pt_offset", "<i4"), ("matched", "<i4")])
+LINE_POINT_DTYPE = np.dtype([("pid", "<i4"), ("dist", "<f4"), ("u", "<f4"), ("v", "<f4")])
+
+_lib = None
+
+# every symbol include/plviwo_fe.h declares (tests/test_abi.py checks the header against this list and the .so)
+EXPORTS = [
+    "plviwo_fe_abi_version", "plviwo_fe_default_config", "plviwo_fe_device_count", "plviwo_fe_create", "plviwo_fe_destroy",
+    "plviwo_fe_last_error", "plviwo_fe_set_calib", "plviwo_fe_set_num_features", "plviwo_fe_change_feat_id", "plviwo_fe_feed",
+    "plviwo_fe_feed_device", "plviwo_fe_submit", "plviwo_fe_collect", "plviwo_fe_get_point_rows", "plviwo_fe_get_last_obs",
+    "plviwo_fe_get_line_rows", "plviwo_fe_get_line_points", "plviwo_fe_get_line_samples", "plviwo_fe_get_state",
+    "plviwo_fe_set_state", "plviwo_fe_tap", "plviwo_fe_enable_timing", "plviwo_fe_get_stage_times",
+    "plviwo_op_equalize_pyramid", "plviwo_op_fast_cell", "plviwo_op_corner_subpix", "plviwo_op_lk", "plviwo_op_undistort",
+    "plviwo_op_canny_half", "plviwo_op_fld", "plviwo_op_ransac_fundamental",
+]
+
+
+def lib() -> C.CDLL:
+    """Loads libplviwo_fe.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FrontEndError(FE_INTERNAL, "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                             "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.plviwo_fe_last_error.restype = C.c_char_p
+        L.plviwo_fe_last_error.argtypes = [C.c_void_p]
+        L.plviwo_fe_create.argtypes = [C.POINTER(FeConfig), C.c_int, C.POINTER(C.c_void_p)]
+        L.plviwo_fe_destroy.argtypes = [C.c_void_p]
+        L.plviwo_fe_set_calib.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.plviwo_fe_set_num_features.argtypes = [C.c_void_p, C.c_int]
+        L.plviwo_fe_change_feat_id.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+        L.plviwo_fe_feed.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                     C.c_void_p, C.POINTER(FeFrameInfo)]
+        L.plviwo_fe_feed_device.argtypes = L.plviwo_fe_feed.argtypes
+        L.plviwo_fe_submit.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.plviwo_fe_collect.argtypes = [C.c_void_p, C.POINTER(FeFrameInfo)]
+        for name in ("plviwo_fe_get_point_rows", "plviwo_fe_get_line_rows", "plviwo_fe_get_line_points"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.plviwo_fe_get_last_obs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.plviwo_fe_get_line_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.plviwo_fe_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.plviwo_fe_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.plviwo_fe_tap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.plviwo_fe_enable_timing.argtypes = [C.c_void_p, C.c_int]
+        L.plviwo_fe_get_stage_times.argtypes = [C.c_void_p, C.POINTER(FeStageTimes), C.c_int]
+        L.plviwo_fe_default_config.argtypes = [C.POINTER(FeConfig)]
+        L.plviwo_fe_default_config.restype = None
+        L.plviwo_fe_device_count.argtypes = [C.POINTER(C.c_int)]
+        L.plviwo_op_equalize_pyramid.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.plviwo_op_fast_cell.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.plviwo_op_corner_subpix.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.plviwo_op_lk.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int]
+        L.plviwo_op_undistort.argtypes = [C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]
+        L.plviwo_op_canny_half.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
+        L.plviwo_op_fld.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_int,
+                                    C.POINTER(C.c_int)]
+        L.plviwo_op_ransac_fundamental.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p,
+                                                   C.POINTER(C.c_int)]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, handle=None):
+    if rc != FE_OK:
+        msg = lib().plviwo_fe_last_error(handle)
+        raise FrontEndError(rc, msg.decode() if msg else "")
+
+
+def default_config(**kw) -> FeConfig:
+    cfg = FeConfig()
+    lib().plviwo_fe_default_config(C.byref(cfg))
+    for k, v in kw.items():
+        if k in ("K", "D"):
+            for i in range(4):
+                getattr(cfg, k)[i] = float(v[i])
+        else:
+            if not hasattr(cfg, k):
+                raise AttributeError(k)
+            setattr(cfg, k, v)
+    return cfg
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    lib().plviwo_fe_device_count(C.byref(n))
+    return n.value
+
+
+# ------------------------------------------------------------------------------------------- databases
+class Feature:
+    """ov_core::Feature (feat/Feature.h): per-id track container, one camera."""
+
+    def __init__(self, featid: int):
+        self.featid = featid
+        self.uvs: List[Tuple[float, float]] = []
+        self.uvs_norm: List[Tuple[float, float]] = []
+        self.timestamps: List[float] = []
+
+
+class FeatureDatabase:
+    """ov_core::FeatureDatabase::update_feature (feat/FeatureDatabase.cpp:60-85): the sink of the point tracker."""
+
+    def __init__(self):
+        self.features_idlookup: Dict[int, Feature] = {}
+
+    def update_feature(self, fid: int, timestamp: float, cam_id: int, u: float, v: float, u_n: float, v_n: float):
+        feat = self.features_idlookup.get(fid)
+        if feat is None:
+            feat = self.features_idlookup[fid] = Feature(fid)
+        feat.uvs.append((u, v))
+        feat.uvs_norm.append((u_n, v_n))
+        feat.timestamps.append(timestamp)
+
+    def get_internal_data(self):
+        return self.features_idlookup
+
+
+class LineFeature:
+    def __init__(self, featid: int, D: int):
+        self.featid = featid
+        self.D = D
+        self.line_uvs: List[np.ndarray] = []
+        self.line_uvs_norm: List[np.ndarray] = []
+        self.timestamps: List[float] = []
+        self.points: List[int] = []
+        self.point_uvs: Dict[float, np.ndarray] = {}
+
+
+class LineFeatureDatabase:
+    """viw::LineFeatureDatabase::update_feature (linefeat/LineFeatureDatabase.cpp:40-76): D is set on creation only."""
+
+    def __init__(self):
+        self.features_idlookup: Dict[int, LineFeature] = {}
+
+    def update_feature(self, fid, timestamp, cam_id, line, line_n, points_line: Dict[int, float], points, D):
+        feat = self.features_idlookup.get(fid)
+        if feat is None:
+            feat = self.features_idlookup[fid] = LineFeature(fid, D)
+        feat.line_uvs.append(np.asarray(line, np.float32))
+        feat.line_uvs_norm.append(np.asarray(line_n, np.float32))
+        feat.timestamps.append(timestamp)
+        feat.points.extend(points_line.keys())
+        feat.point_uvs[timestamp] = np.asarray(points, np.float32)
+
+
+# ------------------------------------------------------------------------------------------- front end
+class FrontEnd:
+    """One camera stream: TrackKLT + TrackLSD behind one FeHandle."""
+
+    def __init__(self, cfg: Optional[FeConfig] = None, device: int = 0, **kw):
+        self.cfg = cfg if cfg is not None else default_config(**kw)
+        self._h = C.c_void_p()
+        self._lib = lib()
+        _check(self._lib.plviwo_fe_create(C.byref(self.cfg), device, C.byref(self._h)))
+        self.database = FeatureDatabase()
+        self.line_database = LineFeatureDatabase()
+        self.cam_id = 0
+        self.info = FeFrameInfo()
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.plviwo_fe_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- reference-shaped calls
+    def set_calib(self, K: Sequence[float], D: Sequence[float]):
+        _check(self._lib.plviwo_fe_set_calib(self._h, (C.c_double * 4)(*K), (C.c_double * 4)(*D)), self._h)
+
+    def set_num_features(self, n: int):
+        _check(self._lib.plviwo_fe_set_num_features(self._h, n), self._h)
+
+    def change_feat_id(self, id_old: int, id_new: int):
+        _check(self._lib.plviwo_fe_change_feat_id(self._h, id_old, id_new), self._h)
+
+    def feed_new_camera(self, timestamp: float, image: np.ndarray, mask: Optional[np.ndarray] = None,
+                        vanishing_points=None, update_db: bool = True) -> FeFrameInfo:
+        """TrackKLT::feed_new_camera followed (when vanishing points are given) by TrackLSD::feed_new_camera, as
+        UpdaterCamera::feed_measurement does (UpdaterCamera.cpp:105-110)."""
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise FrontEndError(FE_BAD_ARG, "image must be a 2-D uint8 array")
+        image = image if image.strides[1] == 1 else np.ascontiguousarray(image)
+        mptr, mstride = None, 0
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, np.uint8)
+            mptr, mstride = mask.ctypes.data, mask.strides[0]
+        vp = None
+        if vanishing_points is not None:
+            vp = (C.c_double * 6)(*[float(v) for p in vanishing_points for v in p])
+        _check(self._lib.plviwo_fe_feed(self._h, float(timestamp), image.ctypes.data, image.shape[1], image.shape[0],
+                                        image.strides[0], mptr, mstride, vp, C.byref(self.info)), self._h)
+        if update_db:
+            self._push_rows(timestamp)
+        return self.info
+
+    def feed_device(self, timestamp: float, d_ptr: int, width: int, height: int, pitch: int, vanishing_points=None):
+        vp = None
+        if vanishing_points is not None:
+            vp = (C.c_double * 6)(*[float(v) for p in vanishing_points for v in p])
+        _check(self._lib.plviwo_fe_feed_device(self._h, float(timestamp), d_ptr, width, height, pitch, None, 0, vp,
+                                               C.byref(self.info)), self._h)
+        return self.info
+
+    def submit(self, timestamp: float, image, stride: int = 0, on_device: bool = False, vanishing_points=None):
+        vp = None
+        if vanishing_points is not None:
+            vp = (C.c_double * 6)(*[float(v) for p in vanishing_points for v in p])
+        if on_device:
+            ptr = int(image)
+        else:
+            ptr, stride = image.ctypes.data, image.strides[0]
+        _check(self._lib.plviwo_fe_submit(self._h, float(timestamp), ptr, stride, 1 if on_device else 0, None, 0, vp), self._h)
+
+    def collect(self) -> FeFrameInfo:
+        _check(self._lib.plviwo_fe_collect(self._h, C.byref(self.info)), self._h)
+        return self.info
+
+    def _push_rows(self, timestamp):
+        for r in self.point_rows():
+            self.database.update_feature(int(r["id"]), timestamp, self.cam_id, float(r["u"]), float(r["v"]),
+                                         float(r["un"]), float(r["vn"]))
+        lrows, lpts = self.line_rows()
+        for r in lrows:
+            pts = lpts[r["pt_offset"]:r["pt_offset"] + r["n_pts"]]
+            self.line_database.update_feature(int(r["id"]), timestamp, self.cam_id, r["line"], r["line_n"],
+                                              {int(p["pid"]): float(p["dist"]) for p in pts},
+                                              np.stack([pts["u"], pts["v"]], 1) if len(pts) else np.zeros((0, 2)), int(r["D"]))
+
+    # -- results
+    def point_rows(self) -> np.ndarray:
+        n = C.c_int(0)
+        _check(self._lib.plviwo_fe_get_point_rows(self._h, None, 0, C.byref(n)), self._h)
+        out = np.zeros((n.value,), POINT_ROW_DTYPE)
+        if n.value:
+            _check(self._lib.plviwo_fe_get_point_rows(self._h, out.ctypes.data, n.value, C.byref(n)), self._h)
+        return out
+
+    def line_rows(self):
+        n = C.c_int(0)
+        _check(self._lib.plviwo_fe_get_line_rows(self._h, None, 0, C.byref(n)), self._h)
+        rows = np.zeros((n.value,), LINE_ROW_DTYPE)
+        if n.value:
+            _check(self._lib.plviwo_fe_get_line_rows(self._h, rows.ctypes.data, n.value, C.byref(n)), self._h)
+        m = C.c_int(0)
+        _check(self._lib.plviwo_fe_get_line_points(self._h, None, 0, C.byref(m)), self._h)
+        pts = np.zeros((m.value,), LINE_POINT_DTYPE)
+        if m.value:
+            _check(self._lib.plviwo_fe_get_line_points(self._h, pts.ctypes.data, m.value, C.byref(m)), self._h)
+        return rows, pts
+
+    def line_samples(self):
+        n = C.c_int(0)
+        _check(self._lib.plviwo_fe_get_line_samples(self._h, None, None, 0, C.byref(n)), self._h)
+        uv = np.zeros((n.value, 4), np.float32)
+        st = np.zeros((n.value,), np.uint8)
+        if n.value:
+            _check(self._lib.plviwo_fe_get_line_samples(self._h, uv.ctypes.data, st.ctypes.data, n.value, C.byref(n)), self._h)
+        return uv, st
+
+    def get_last_obs(self) -> np.ndarray:
+        return self._last()[1]
+
+    def get_last_ids(self) -> np.ndarray:
+        return self._last()[0]
+
+    def _last(self):
+        n = C.c_int(0)
+        _check(self._lib.plviwo_fe_get_last_obs(self._h, None, None, 0, C.byref(n)), self._h)
+        ids = np.zeros((n.value,), np.uint64)
+        uv = np.zeros((n.value, 2), np.float32)
+        if n.value:
+            _check(self._lib.plviwo_fe_get_last_obs(self._h, ids.ctypes.data, uv.ctypes.data, n.value, C.byref(n)), self._h)
+        return ids, uv
+
+    def get_feature_database(self) -> FeatureDatabase:
+        return self.database
+
+    def get_line_feature_database(self) -> LineFeatureDatabase:
+        return self.line_database
+
+    # -- state, taps, timing
+    def get_state(self) -> bytes:
+        n = C.c_size_t(0)
+        _check(self._lib.plviwo_fe_get_state(self._h, None, 0, C.byref(n)), self._h)
+        buf = C.create_string_buffer(n.value)
+        _check(self._lib.plviwo_fe_get_state(self._h, buf, n.value, C.byref(n)), self._h)
+        return buf.raw[:n.value]
+
+    def set_state(self, blob: bytes):
+        _check(self._lib.plviwo_fe_set_state(self._h, blob, len(blob)), self._h)
+
+    def tap(self, what: int, dtype=np.uint8) -> np.ndarray:
+        n = C.c_size_t(0)
+        _check(self._lib.plviwo_fe_tap(self._h, what, None, 0, C.byref(n)), self._h)
+        out = np.zeros((n.value // np.dtype(dtype).itemsize,), dtype)
+        if n.value:
+            _check(self._lib.plviwo_fe_tap(self._h, what, out.ctypes.data, n.value, C.byref(n)), self._h)
+        return out
+
+    def enable_timing(self, on: bool = True):
+        _check(self._lib.plviwo_fe_enable_timing(self._h, 1 if on else 0), self._h)
+
+    def stage_times(self, reset: bool = False) -> Dict[str, object]:
+        t = FeStageTimes()
+        _check(self._lib.plviwo_fe_get_stage_times(self._h, C.byref(t), 1 if reset else 0), self._h)
+        return {"ms": {s: t.ms[i] for i, s in enumerate(STAGES)}, "launches": {s: int(t.launches[i]) for i, s in enumerate(STAGES)},
+                "frames": int(t.frames), "kernel_launches_total": int(t.kernel_launches_total)}
+
+
+# ------------------------------------------------------------------------------------------- stand-alone ops
+def pyramid_level_sizes(w: int, h: int, levels: int):
+    out = []
+    for _ in range(levels + 1):
+        out.append((w, h))
+        w, h = (w + 1) // 2, (h + 1) // 2
+        if w < 2 or h < 2:
+            break
+    return out
+
+
+def op_equalize_pyramid(img: np.ndarray, levels: int, device: int = 0):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    sizes = pyramid_level_sizes(w, h, levels)
+    out = np.zeros((sum(a * b for a, b in sizes),), np.uint8)
+    half = np.zeros((h // 2, w // 2), np.uint8)
+    _check(lib().plviwo_op_equalize_pyramid(device, img.ctypes.data, w, h, levels, out.ctypes.data, half.ctypes.data))
+    lv, o = [], 0
+    for (lw, lh) in sizes:
+        lv.append(out[o:o + lw * lh].reshape(lh, lw))
+        o += lw * lh
+    return lv, half
+
+
+def op_fast_cell(img: np.ndarray, threshold: int, device: int = 0) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = w * h // 4 + 16
+    out = np.zeros((cap, 3), np.int32)
+    n = C.c_int(0)
+    _check(lib().plviwo_op_fast_cell(device, img.ctypes.data, w, h, threshold, out.ctypes.data, cap, C.byref(n)))
+    return out[:n.value].copy()
+
+
+def op_corner_subpix(img: np.ndarray, pts: np.ndarray, device: int = 0) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    p = np.ascontiguousarray(pts, np.float32).reshape(-1, 2).copy()
+    _check(lib().plviwo_op_corner_subpix(device, img.ctypes.data, img.shape[1], img.shape[0], p.ctypes.data, len(p)))
+    return p
+
+
+def op_lk(img0, img1, pts0, pts1_init, win: int = 15, max_level: int = 5, device: int = 0):
+    img0 = np.ascontiguousarray(img0, np.uint8)
+    img1 = np.ascontiguousarray(img1, np.uint8)
+    p0 = np.ascontiguousarray(pts0, np.float32).reshape(-1, 2)
+    p1 = np.ascontiguousarray(pts1_init, np.float32).reshape(-1, 2).copy()
+    st = np.zeros((len(p0),), np.uint8)
+    _check(lib().plviwo_op_lk(device, img0.ctypes.data, img1.ctypes.data, img0.shape[1], img0.shape[0], win, max_level,
+                              p0.ctypes.data, p1.ctypes.data, st.ctypes.data, len(p0)))
+    return p1, st
+
+
+def op_undistort(pts, K, D, device: int = 0) -> np.ndarray:
+    p = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    out = np.zeros_like(p)
+    _check(lib().plviwo_op_undistort(device, p.ctypes.data, len(p), (C.c_double * 4)(*K), (C.c_double * 4)(*D), out.ctypes.data))
+    return out
+
+
+def op_canny(img: np.ndarray, th: float = 50.0, device: int = 0) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros_like(img)
+    _check(lib().plviwo_op_canny_half(device, img.ctypes.data, img.shape[1], img.shape[0], th, out.ctypes.data))
+    return out
+
+
+def op_fld(img: np.ndarray, length_threshold: int = 20, distance_threshold: float = 1.414213562, canny_th: float = 50.0,
+           device: int = 0) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = 8192
+    out = np.zeros((cap, 4), np.float32)
+    n = C.c_int(0)
+    _check(lib().plviwo_op_fld(device, img.ctypes.data, img.shape[1], img.shape[0], length_threshold, distance_threshold,
+                               canny_th, out.ctypes.data, cap, C.byref(n)))
+    return out[:n.value].copy()
+
+
+def op_ransac_fundamental(p0n, p1n, threshold: float, confidence: float = 0.999):
+    """Host-side sequential step (no GPU needed): returns (mask uint8, n_inliers or -1 when OpenCV returns no mask)."""
+    a = np.ascontiguousarray(p0n, np.float32).reshape(-1, 2)
+    b = np.ascontiguousarray(p1n, np.float32).reshape(-1, 2)
+    mask = np.zeros((len(a),), np.uint8)
+    n = C.c_int(0)
+    _check(lib().plviwo_op_ransac_fundamental(a.ctypes.data, b.ctypes.data, len(a), threshold, confidence, mask.ctypes.data,
+                                              C.byref(n)))
+    return mask, n.value

@@ -1,0 +1,514 @@
+// extern "C" surface declared in include/plviwo_fe.h.  Thin: argument checks, exception firewall, and the
+// stand-alone kernel entry points used by the parity tests and micro-benchmarks.
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "fe_context.h"
+
+using namespace plviwo;
+
+struct FeHandle {
+  FeContext *ctx;
+};
+
+static thread_local std::string g_create_error;
+
+#define API_BEGIN try {
+#define API_END                                   \
+  }                                               \
+  catch (const std::bad_alloc &) {                \
+    return FE_INTERNAL;                           \
+  }                                               \
+  catch (...) {                                   \
+    return FE_INTERNAL;                           \
+  }
+
+extern "C" {
+
+int plviwo_fe_abi_version(void) { return PLVIWO_FE_ABI_VERSION; }
+
+void plviwo_fe_default_config(FeConfig *cfg) {
+  if (!cfg) return;
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->width = 1280;
+  cfg->height = 560;
+  cfg->num_features = 150;      // OptionsCamera.h:77-89
+  cfg->fast_threshold = 20;
+  cfg->grid_x = 5;
+  cfg->grid_y = 5;
+  cfg->min_px_dist = 10;
+  cfg->pyr_levels = 5;          // TrackKLT.h:143
+  cfg->win_size = 15;           // TrackKLT.h:144
+  cfg->histogram_method = FE_HIST_HISTOGRAM;
+  cfg->numaruco = 0;
+  cfg->use_lines = 1;           // OptionsCamera.h:108
+  cfg->fld_length_threshold = 20;
+  cfg->fld_distance_threshold = 1.414213562f;
+  cfg->canny_th1 = 50.f;
+  cfg->canny_th2 = 50.f;
+  cfg->line_min_length = 40.f;
+  cfg->line_samples = 0;
+  cfg->lookahead = 0;
+  const double K[4] = {8.1690378992770002e+02, 8.1156803828490001e+02, 6.0850726281690004e+02, 2.6347599764440002e+02};
+  const double D[4] = {-5.6143027800000002e-02, 1.3952563200000001e-01, -1.2155906999999999e-03, -9.7281389999999998e-04};
+  for (int i = 0; i < 4; i++) {
+    cfg->K[i] = K[i];
+    cfg->D[i] = D[i];
+  }
+}
+
+int plviwo_fe_device_count(int *n) {
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (n) *n = e == cudaSuccess ? c : 0;
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return FE_NO_DEVICE;
+  }
+  return c > 0 ? FE_OK : FE_NO_DEVICE;
+}
+
+int plviwo_fe_create(const FeConfig *cfg, int device, FeHandle **out) {
+  API_BEGIN
+  if (!cfg || !out) return FE_BAD_ARG;
+  *out = nullptr;
+  auto bad = [&](const char *why) {
+    g_create_error = why;
+    return FE_BAD_ARG;
+  };
+  if (cfg->width < 64 || cfg->height < 64 || cfg->width > 4095 || cfg->height > 4095) return bad("image size must be in [64, 4095]");
+  if (cfg->win_size < 3 || cfg->win_size > kMaxWin || (cfg->win_size & 1) == 0) return bad("win_size must be odd and in [3, 31]");
+  if (cfg->pyr_levels < 0 || cfg->pyr_levels >= kMaxLevels) return bad("pyr_levels must be in [0, 7]");
+  if (cfg->grid_x < 1 || cfg->grid_y < 1 || cfg->min_px_dist < 1 || cfg->num_features < 1) return bad("bad grid / distance / feature count");
+  if (cfg->histogram_method == FE_HIST_CLAHE) return bad("FE_HIST_CLAHE is not implemented");
+  if (cfg->histogram_method != FE_HIST_NONE && cfg->histogram_method != FE_HIST_HISTOGRAM) return bad("bad histogram_method");
+  if (cfg->use_lines) {
+    if ((cfg->width & 1) || (cfg->height & 1)) return bad("line tracker needs even image dimensions (exact 2x decimation)");
+    if (cfg->canny_th1 != cfg->canny_th2) return bad("canny_th1 != canny_th2: hysteresis pass is not implemented");
+    if (cfg->fld_length_threshold < 2) return bad("bad fld_length_threshold");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    g_create_error = "no CUDA device: this front end has no CPU fallback";
+    return FE_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) return bad("device index out of range");
+  FeContext *ctx = new FeContext(*cfg, device);
+  int rc = ctx->init();
+  if (rc != FE_OK) {
+    g_create_error = ctx->last_error;
+    delete ctx;
+    return rc;
+  }
+  FeHandle *h = new FeHandle{ctx};
+  *out = h;
+  return FE_OK;
+  API_END
+}
+
+int plviwo_fe_destroy(FeHandle *h) {
+  API_BEGIN
+  if (!h) return FE_BAD_ARG;
+  delete h->ctx;
+  delete h;
+  return FE_OK;
+  API_END
+}
+
+const char *plviwo_fe_last_error(const FeHandle *h) { return h ? h->ctx->last_error.c_str() : g_create_error.c_str(); }
+
+int plviwo_fe_set_calib(FeHandle *h, const double K[4], const double D[4]) {
+  if (!h || !K || !D) return FE_BAD_ARG;
+  return h->ctx->set_calib(K, D);
+}
+int plviwo_fe_set_num_features(FeHandle *h, int n) {
+  if (!h || n < 1) return FE_BAD_ARG;
+  h->ctx->set_num_features(n);
+  return FE_OK;
+}
+int plviwo_fe_change_feat_id(FeHandle *h, uint64_t id_old, uint64_t id_new) {
+  if (!h) return FE_BAD_ARG;
+  h->ctx->change_feat_id(id_old, id_new);
+  return FE_OK;
+}
+
+int plviwo_fe_feed(FeHandle *h, double timestamp, const uint8_t *image, int width, int height, int stride,
+                   const uint8_t *mask, int mask_stride, const double vp[6], FeFrameInfo *info) {
+  API_BEGIN
+  if (!h) return FE_BAD_ARG;
+  return h->ctx->feed(timestamp, image, width, height, stride, false, mask, mask_stride, vp, info);
+  API_END
+}
+int plviwo_fe_feed_device(FeHandle *h, double timestamp, const void *d_image, int width, int height, int pitch,
+                          const uint8_t *mask, int mask_stride, const double vp[6], FeFrameInfo *info) {
+  API_BEGIN
+  if (!h) return FE_BAD_ARG;
+  return h->ctx->feed(timestamp, static_cast<const uint8_t *>(d_image), width, height, pitch, true, mask, mask_stride, vp, info);
+  API_END
+}
+int plviwo_fe_submit(FeHandle *h, double timestamp, const uint8_t *image, int stride, int on_device, const uint8_t *mask,
+                     int mask_stride, const double vp[6]) {
+  API_BEGIN
+  if (!h || !image || stride < h->ctx->cfg().width || (mask && mask_stride < h->ctx->cfg().width)) return FE_BAD_ARG;
+  return h->ctx->submit(timestamp, image, stride, on_device != 0, mask, mask_stride, vp);
+  API_END
+}
+int plviwo_fe_collect(FeHandle *h, FeFrameInfo *info) {
+  API_BEGIN
+  if (!h) return FE_BAD_ARG;
+  return h->ctx->collect(info);
+  API_END
+}
+
+}  // extern "C"
+template <class T>
+static int copy_out(const std::vector<T> &v, T *out, int cap, int *n_out) {
+  if (n_out) *n_out = (int)v.size();
+  if (!out) return FE_OK;
+  if (cap < (int)v.size()) return FE_OVERFLOW;
+  if (!v.empty()) std::memcpy(out, v.data(), v.size() * sizeof(T));
+  return FE_OK;
+}
+extern "C" {
+
+int plviwo_fe_get_point_rows(FeHandle *h, FePointRow *out, int cap, int *n_out) {
+  if (!h) return FE_BAD_ARG;
+  return copy_out(h->ctx->point_rows, out, cap, n_out);
+}
+int plviwo_fe_get_last_obs(FeHandle *h, uint64_t *ids, float *uv, int cap, int *n_out) {
+  if (!h) return FE_BAD_ARG;
+  const auto &p = h->ctx->get_last_obs();
+  const auto &id = h->ctx->get_last_ids();
+  if (n_out) *n_out = (int)p.size();
+  if (!ids && !uv) return FE_OK;
+  if (cap < (int)p.size()) return FE_OVERFLOW;
+  for (size_t i = 0; i < p.size(); i++) {
+    if (ids) ids[i] = id[i];
+    if (uv) {
+      uv[2 * i] = p[i].x;
+      uv[2 * i + 1] = p[i].y;
+    }
+  }
+  return FE_OK;
+}
+int plviwo_fe_get_line_rows(FeHandle *h, FeLineRow *out, int cap, int *n_out) {
+  if (!h) return FE_BAD_ARG;
+  return copy_out(h->ctx->line_rows, out, cap, n_out);
+}
+int plviwo_fe_get_line_points(FeHandle *h, FeLinePoint *out, int cap, int *n_out) {
+  if (!h) return FE_BAD_ARG;
+  return copy_out(h->ctx->line_points, out, cap, n_out);
+}
+int plviwo_fe_get_line_samples(FeHandle *h, float *uv01, uint8_t *status, int cap, int *n_out) {
+  if (!h) return FE_BAD_ARG;
+  const auto &s = h->ctx->sample_status;
+  if (n_out) *n_out = (int)s.size();
+  if (!uv01 && !status) return FE_OK;
+  if (cap < (int)s.size()) return FE_OVERFLOW;
+  if (uv01 && !s.empty()) std::memcpy(uv01, h->ctx->sample_uv.data(), s.size() * 4 * sizeof(float));
+  if (status && !s.empty()) std::memcpy(status, s.data(), s.size());
+  return FE_OK;
+}
+
+int plviwo_fe_get_state(FeHandle *h, void *buf, size_t cap, size_t *n_bytes) {
+  API_BEGIN
+  if (!h) return FE_BAD_ARG;
+  return h->ctx->get_state(buf, cap, n_bytes);
+  API_END
+}
+int plviwo_fe_set_state(FeHandle *h, const void *buf, size_t n_bytes) {
+  API_BEGIN
+  if (!h) return FE_BAD_ARG;
+  return h->ctx->set_state(buf, n_bytes);
+  API_END
+}
+int plviwo_fe_tap(FeHandle *h, int what, void *buf, size_t cap, size_t *n_bytes) {
+  API_BEGIN
+  if (!h) return FE_BAD_ARG;
+  return h->ctx->tap(what, buf, cap, n_bytes);
+  API_END
+}
+int plviwo_fe_enable_timing(FeHandle *h, int on) {
+  if (!h) return FE_BAD_ARG;
+  h->ctx->timing = on != 0;
+  return FE_OK;
+}
+int plviwo_fe_get_stage_times(FeHandle *h, FeStageTimes *out, int reset) {
+  if (!h || !out) return FE_BAD_ARG;
+  *out = h->ctx->times;
+  if (reset) std::memset(&h->ctx->times, 0, sizeof(h->ctx->times));
+  return FE_OK;
+}
+
+// --------------------------------------------------------------------------------- stand-alone kernels
+#define OP_CUDA(call)                              \
+  do {                                             \
+    cudaError_t e__ = (call);                      \
+    if (e__ != cudaSuccess) {                      \
+      g_create_error = std::string(#call) + ": " + cudaGetErrorString(e__); \
+      return e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver ? FE_NO_DEVICE : FE_CUDA_ERROR; \
+    }                                              \
+  } while (0)
+
+}  // extern "C"
+namespace {
+struct TmpImage {
+  DevImage im;
+  ~TmpImage() { cudaFree(im.p); }
+  int alloc(int w, int h) {
+    im.w = w;
+    im.h = h;
+    im.pitch = (w + 255) / 256 * 256;
+    return cudaMalloc(&im.p, (size_t)im.pitch * h + 256) == cudaSuccess ? 0 : 1;
+  }
+  int upload(const uint8_t *src) {
+    return cudaMemcpy2D(im.p, im.pitch, src, im.w, im.w, im.h, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : 1;
+  }
+};
+struct TmpPyr {
+  Pyramid pyr;
+  ~TmpPyr() {
+    for (int l = 0; l < pyr.n; l++) cudaFree(pyr.lvl[l].p);
+  }
+  int alloc(int w, int h, int levels, int win) {
+    pyr.n = 0;
+    for (int l = 0; l <= levels && l < kMaxLevels; l++) {
+      DevImage &im = pyr.lvl[l];
+      im.w = w;
+      im.h = h;
+      im.pitch = (w + 255) / 256 * 256;
+      if (cudaMalloc(&im.p, (size_t)im.pitch * h + 256) != cudaSuccess) return 1;
+      pyr.n = l + 1;
+      w = (w + 1) / 2;
+      h = (h + 1) / 2;
+      if (win > 0 && (w <= win || h <= win)) break;
+      if (w < 2 || h < 2) break;
+    }
+    return 0;
+  }
+};
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+  int alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) == cudaSuccess ? 0 : 1; }
+};
+int build_pyramid(const uint8_t *img, int w, int h, int levels, int win, int equalize, TmpImage &raw, TmpPyr &pyr,
+                  TmpImage *half) {
+  if (raw.alloc(w, h) || raw.upload(img) || pyr.alloc(w, h, levels, win)) return 1;
+  DevBuf<unsigned> hist, counters;
+  if (hist.alloc(256) || counters.alloc(4)) return 1;
+  cudaMemset(hist.p, 0, 256 * sizeof(unsigned));
+  cudaMemset(counters.p, 0, 4 * sizeof(unsigned));
+  if (equalize) launch_hist(raw.im, hist.p, 0);
+  DevImage l1 = pyr.pyr.n > 1 ? pyr.pyr.lvl[1] : DevImage();
+  launch_eq_pyr1(raw.im, hist.p, counters.p, equalize, pyr.pyr.lvl[0], l1, half ? half->im : DevImage(), 0);
+  launch_pyr_rest(pyr.pyr, counters.p + 1, 0);
+  return cudaDeviceSynchronize() == cudaSuccess ? 0 : 1;
+}
+}  // namespace
+extern "C" {
+
+int plviwo_op_equalize_pyramid(int device, const uint8_t *img, int w, int h, int levels, uint8_t *out_levels, uint8_t *out_half) {
+  API_BEGIN
+  if (!img || !out_levels || w < 8 || h < 8 || levels < 1 || levels >= kMaxLevels) return FE_BAD_ARG;
+  OP_CUDA(cudaSetDevice(device));
+  TmpImage raw, half;
+  TmpPyr pyr;
+  if (out_half && half.alloc(w / 2, h / 2)) return FE_CUDA_ERROR;
+  if (build_pyramid(img, w, h, levels, 0, 1, raw, pyr, out_half ? &half : nullptr)) {
+    g_create_error = cudaGetErrorString(cudaGetLastError());
+    return FE_CUDA_ERROR;
+  }
+  uint8_t *o = out_levels;
+  for (int l = 0; l < pyr.pyr.n; l++) {
+    const DevImage &im = pyr.pyr.lvl[l];
+    OP_CUDA(cudaMemcpy2D(o, im.w, im.p, im.pitch, im.w, im.h, cudaMemcpyDeviceToHost));
+    o += (size_t)im.w * im.h;
+  }
+  if (out_half) OP_CUDA(cudaMemcpy2D(out_half, half.im.w, half.im.p, half.im.pitch, half.im.w, half.im.h, cudaMemcpyDeviceToHost));
+  return FE_OK;
+  API_END
+}
+
+int plviwo_op_fast_cell(int device, const uint8_t *img, int w, int h, int threshold, int32_t *xys, int cap, int *n_out) {
+  API_BEGIN
+  if (!img || !n_out || w < 7 || h < 7 || w > 4095 || h > 4095) return FE_BAD_ARG;
+  OP_CUDA(cudaSetDevice(device));
+  TmpImage raw;
+  if (raw.alloc(w, h) || raw.upload(img)) return FE_CUDA_ERROR;
+  const int nb = (h + kFastBandRows - 1) / kFastBandRows;
+  const int kcap = w * h / 4 + 1024;
+  DevBuf<FastCell> cells;
+  DevBuf<unsigned> total, kps;
+  DevBuf<int> off, cnt;
+  if (cells.alloc(1) || total.alloc(1) || kps.alloc(kcap) || off.alloc(nb) || cnt.alloc(nb)) return FE_CUDA_ERROR;
+  FastCell c{0, 0, w, h};
+  OP_CUDA(cudaMemcpy(cells.p, &c, sizeof(c), cudaMemcpyHostToDevice));
+  OP_CUDA(cudaMemset(total.p, 0, sizeof(unsigned)));
+  launch_fast(raw.im, cells.p, 1, nb, w, threshold, total.p, off.p, cnt.p, kps.p, kcap, 0);
+  OP_CUDA(cudaDeviceSynchronize());
+  std::vector<int> hoff(nb), hcnt(nb);
+  unsigned htotal = 0;
+  OP_CUDA(cudaMemcpy(&htotal, total.p, sizeof(unsigned), cudaMemcpyDeviceToHost));
+  OP_CUDA(cudaMemcpy(hoff.data(), off.p, nb * sizeof(int), cudaMemcpyDeviceToHost));
+  OP_CUDA(cudaMemcpy(hcnt.data(), cnt.p, nb * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<unsigned> hk(std::min<unsigned>(htotal, kcap));
+  if (!hk.empty()) OP_CUDA(cudaMemcpy(hk.data(), kps.p, hk.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  int n = 0;
+  for (int b = 0; b < nb; b++)
+    for (int k = 0; k < hcnt[b]; k++, n++) {
+      if (xys && n < cap) {
+        unsigned v = hk[hoff[b] + k];
+        xys[3 * n] = v & 0xfff;
+        xys[3 * n + 1] = (v >> 12) & 0xfff;
+        xys[3 * n + 2] = v >> 24;
+      }
+    }
+  *n_out = n;
+  return (xys && n > cap) ? FE_OVERFLOW : FE_OK;
+  API_END
+}
+
+int plviwo_op_corner_subpix(int device, const uint8_t *img, int w, int h, float *pts, int n) {
+  API_BEGIN
+  if (!img || !pts || n < 0) return FE_BAD_ARG;
+  OP_CUDA(cudaSetDevice(device));
+  TmpImage raw;
+  DevBuf<float2> d;
+  if (raw.alloc(w, h) || raw.upload(img) || d.alloc(n)) return FE_CUDA_ERROR;
+  OP_CUDA(cudaMemcpy(d.p, pts, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice));
+  launch_corner_subpix(raw.im, d.p, n, 0);
+  OP_CUDA(cudaDeviceSynchronize());
+  OP_CUDA(cudaMemcpy(pts, d.p, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost));
+  return FE_OK;
+  API_END
+}
+
+int plviwo_op_lk(int device, const uint8_t *img0, const uint8_t *img1, int w, int h, int win, int max_level,
+                 const float *pts0, float *pts1, uint8_t *status, int n) {
+  API_BEGIN
+  if (!img0 || !img1 || !pts0 || !pts1 || !status || n < 0 || win < 3 || win > kMaxWin || !(win & 1) || max_level < 0 ||
+      max_level >= kMaxLevels)
+    return FE_BAD_ARG;
+  OP_CUDA(cudaSetDevice(device));
+  TmpImage r0, r1;
+  TmpPyr p0, p1;
+  if (build_pyramid(img0, w, h, max_level, win, 0, r0, p0, nullptr) || build_pyramid(img1, w, h, max_level, win, 0, r1, p1, nullptr)) {
+    g_create_error = cudaGetErrorString(cudaGetLastError());
+    return FE_CUDA_ERROR;
+  }
+  DevBuf<float2> d0, d1, dn0, dn1;
+  DevBuf<uint8_t> ds;
+  if (d0.alloc(n) || d1.alloc(n) || dn0.alloc(n) || dn1.alloc(n) || ds.alloc(n)) return FE_CUDA_ERROR;
+  OP_CUDA(cudaMemcpy(d0.p, pts0, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice));
+  OP_CUDA(cudaMemcpy(d1.p, pts1, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice));
+  LkParams prm;
+  prm.win = win;
+  prm.max_level = max_level;
+  prm.max_count = 30;
+  prm.eps_sq = 0.01f * 0.01f;
+  prm.min_eig = 1e-4f;
+  prm.undistort = 0;
+  for (int i = 0; i < 4; i++) prm.K[i] = prm.D[i] = 0;
+  launch_lk(p0.pyr, p1.pyr, d0.p, d1.p, ds.p, dn0.p, dn1.p, n, prm, 0);
+  OP_CUDA(cudaDeviceSynchronize());
+  OP_CUDA(cudaMemcpy(pts1, d1.p, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost));
+  OP_CUDA(cudaMemcpy(status, ds.p, (size_t)n, cudaMemcpyDeviceToHost));
+  return FE_OK;
+  API_END
+}
+
+int plviwo_op_undistort(int device, const float *pts, int n, const double K[4], const double D[4], float *out) {
+  API_BEGIN
+  if (!pts || !out || !K || !D || n < 0) return FE_BAD_ARG;
+  OP_CUDA(cudaSetDevice(device));
+  DevBuf<float2> a, b;
+  if (a.alloc(n) || b.alloc(n)) return FE_CUDA_ERROR;
+  OP_CUDA(cudaMemcpy(a.p, pts, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice));
+  launch_undistort(a.p, b.p, n, K, D, 0);
+  OP_CUDA(cudaDeviceSynchronize());
+  OP_CUDA(cudaMemcpy(out, b.p, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost));
+  return FE_OK;
+  API_END
+}
+
+namespace {
+struct TmpFld {
+  FldBuffers fb;
+  ~TmpFld() {
+    cudaFree(fb.edges); cudaFree(fb.chain_pts); cudaFree(fb.chain_off); cudaFree(fb.n_chains);
+    cudaFree(fb.segs); cudaFree(fb.seg_cnt); cudaFree(fb.out);
+  }
+  int alloc(int w, int h, int T, int out_cap) {
+    fb.words_per_row = (w + 31) / 32;
+    fb.max_chains = w * h / (T + 1) + 1;
+    fb.out_cap = out_cap;
+    if (cudaMalloc(&fb.edges, (size_t)fb.words_per_row * h * sizeof(unsigned)) != cudaSuccess) return 1;
+    if (cudaMalloc(&fb.chain_pts, (size_t)w * h * sizeof(int2)) != cudaSuccess) return 1;
+    if (cudaMalloc(&fb.chain_off, (size_t)(fb.max_chains + 1) * sizeof(int)) != cudaSuccess) return 1;
+    if (cudaMalloc(&fb.n_chains, 2 * sizeof(int)) != cudaSuccess) return 1;
+    if (cudaMalloc(&fb.segs, (size_t)(w * h / kSegsPerChainDiv + fb.max_chains + 2) * sizeof(float4)) != cudaSuccess) return 1;
+    if (cudaMalloc(&fb.seg_cnt, (size_t)2 * fb.max_chains * sizeof(int)) != cudaSuccess) return 1;
+    if (cudaMalloc(&fb.out, (size_t)out_cap * sizeof(float4)) != cudaSuccess) return 1;
+    cudaMemset(fb.n_chains, 0, 2 * sizeof(int));
+    return 0;
+  }
+};
+}  // namespace
+
+int plviwo_op_canny_half(int device, const uint8_t *img, int w, int h, float th, uint8_t *edges) {
+  API_BEGIN
+  if (!img || !edges || w < 8 || h < 8) return FE_BAD_ARG;
+  OP_CUDA(cudaSetDevice(device));
+  TmpImage raw;
+  TmpFld f;
+  DevBuf<uint8_t> out;
+  if (raw.alloc(w, h) || raw.upload(img) || f.alloc(w, h, 20, 16) || out.alloc((size_t)w * h)) return FE_CUDA_ERROR;
+  launch_canny(raw.im, th, th, f.fb, 0);
+  launch_unpack_edges(f.fb, w, h, out.p, 0);
+  OP_CUDA(cudaDeviceSynchronize());
+  OP_CUDA(cudaMemcpy(edges, out.p, (size_t)w * h, cudaMemcpyDeviceToHost));
+  return FE_OK;
+  API_END
+}
+
+int plviwo_op_fld(int device, const uint8_t *img, int w, int h, int length_threshold, float distance_threshold,
+                  float canny_th, float *lines, int cap, int *n_out) {
+  API_BEGIN
+  if (!img || !n_out || w < 16 || h < 16 || length_threshold < 2) return FE_BAD_ARG;
+  OP_CUDA(cudaSetDevice(device));
+  TmpImage raw;
+  TmpFld f;
+  const int out_cap = 8192;
+  if (raw.alloc(w, h) || raw.upload(img) || f.alloc(w, h, length_threshold, out_cap)) return FE_CUDA_ERROR;
+  launch_canny(raw.im, canny_th, canny_th, f.fb, 0);
+  launch_fld(raw.im, length_threshold, distance_threshold, f.fb, 0);
+  OP_CUDA(cudaDeviceSynchronize());
+  int counts[2] = {0, 0};
+  OP_CUDA(cudaMemcpy(counts, f.fb.n_chains, sizeof(counts), cudaMemcpyDeviceToHost));
+  int n = std::min(counts[1], out_cap);
+  *n_out = n;
+  if (lines) {
+    if (n > cap) return FE_OVERFLOW;
+    if (n) OP_CUDA(cudaMemcpy(lines, f.fb.out, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
+  }
+  return FE_OK;
+  API_END
+}
+
+int plviwo_op_ransac_fundamental(const float *p0n, const float *p1n, int n, double threshold, double confidence,
+                                 uint8_t *mask, int *n_inliers) {
+  API_BEGIN
+  if (!p0n || !p1n || !mask || n < 0) return FE_BAD_ARG;
+  int valid = 0;
+  int good = ransac_fundamental(p0n, p1n, n, threshold, confidence, mask, &valid);
+  if (n_inliers) *n_inliers = valid ? good : -1;
+  return FE_OK;
+  API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,972 @@
+// Host-side trackers of the B200 front end.  Line-by-line counterparts of the reference's glue, with every
+// OpenCV call replaced by a kernel launch (fe_kernels.h):
+//   ov_core::TrackKLT::feed_new_camera / feed_monocular      open_vins/ov_core/src/track/TrackKLT.cpp:34-200
+//   TrackKLT::perform_detection_monocular                    TrackKLT.cpp:395-528
+//   Grider_GRID::perform_griding                             open_vins/ov_core/src/track/Grider_GRID.h:74-180
+//   TrackKLT::perform_matching                               TrackKLT.cpp:829-886
+//   viw::TrackLSD::feed_monocular and helpers                PL-VIWO/src/update/cam/TrackLSD.cpp:70-236, 318-448, 744-830
+// The frame-independent work of a frame (copy, equalise, pyramid, edge map, segment extraction) is enqueued at
+// submit() on its own streams; collect() runs the state-dependent chain (top-off detection on the previous
+// image, LK, RANSAC gate, line association) in frame order.
+#include "fe_context.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace plviwo {
+
+#define FE_CUDA(call)                                  \
+  do {                                                 \
+    cudaError_t e__ = (call);                          \
+    if (e__ != cudaSuccess) return fail(e__, #call);   \
+  } while (0)
+
+static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+FeContext::FeContext(const FeConfig &cfg, int device) : cfg_(cfg), device_(device), W_(cfg.width), H_(cfg.height) {
+  currid_ = 4 * (uint64_t)cfg.numaruco + 1;  // TrackBase.cpp:34
+  line_currid_ = 1;                          // TrackLSD.cpp:32
+}
+
+int FeContext::fail(cudaError_t e, const char *what) {
+  last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return FE_CUDA_ERROR;
+}
+
+int FeContext::alloc_image(DevImage &im, int w, int h) {
+  im.w = w;
+  im.h = h;
+  im.pitch = align_up(w, 256);
+  FE_CUDA(cudaMalloc(&im.p, (size_t)im.pitch * h + 256));
+  FE_CUDA(cudaMemset(im.p, 0, (size_t)im.pitch * h + 256));
+  return FE_OK;
+}
+
+int FeContext::init() {
+  FE_CUDA(cudaSetDevice(device_));
+  int lo = 0, hi = 0;
+  FE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  FE_CUDA(cudaStreamCreateWithPriority(&s_img_, cudaStreamNonBlocking, lo));
+  FE_CUDA(cudaStreamCreateWithPriority(&s_pt_, cudaStreamNonBlocking, hi));
+  FE_CUDA(cudaStreamCreateWithPriority(&s_line_, cudaStreamNonBlocking, lo));
+  FE_CUDA(cudaMalloc(&d_hist_, 256 * sizeof(unsigned)));
+  FE_CUDA(cudaMemset(d_hist_, 0, 256 * sizeof(unsigned)));
+  FE_CUDA(cudaMalloc(&d_counters_, 4 * sizeof(unsigned)));
+  FE_CUDA(cudaMemset(d_counters_, 0, 4 * sizeof(unsigned)));
+
+  const int nslots = std::max(cfg_.lookahead, 0) + 2;
+  slots_.resize(nslots);
+  for (FrameSlot &s : slots_) {
+    int rc = alloc_image(s.raw, W_, H_);
+    if (rc) return rc;
+    // cv::buildOpticalFlowPyramid: a level is kept while both sides stay > winSize
+    int w = W_, h = H_;
+    s.pyr.n = 0;
+    for (int l = 0; l <= cfg_.pyr_levels && l < kMaxLevels; l++) {
+      rc = alloc_image(s.pyr.lvl[l], w, h);
+      if (rc) return rc;
+      s.pyr.n = l + 1;
+      w = (w + 1) / 2;
+      h = (h + 1) / 2;
+      if (w <= cfg_.win_size || h <= cfg_.win_size) break;
+    }
+    if (cfg_.use_lines) {
+      rc = alloc_image(s.half, W_ / 2, H_ / 2);
+      if (rc) return rc;
+      FldBuffers &fb = s.fld;
+      const int hw = W_ / 2, hh = H_ / 2;
+      fb.words_per_row = (hw + 31) / 32;
+      fb.max_chains = hw * hh / (cfg_.fld_length_threshold + 1) + 1;
+      fb.out_cap = 4096;
+      FE_CUDA(cudaMalloc(&fb.edges, (size_t)fb.words_per_row * hh * sizeof(unsigned)));
+      FE_CUDA(cudaMalloc(&fb.chain_pts, (size_t)hw * hh * sizeof(int2)));
+      FE_CUDA(cudaMalloc(&fb.chain_off, (size_t)(fb.max_chains + 1) * sizeof(int)));
+      FE_CUDA(cudaMalloc(&fb.n_chains, 2 * sizeof(int)));
+      FE_CUDA(cudaMemset(fb.n_chains, 0, 2 * sizeof(int)));
+      FE_CUDA(cudaMalloc(&fb.segs, (size_t)(hw * hh / kSegsPerChainDiv + fb.max_chains + 2) * sizeof(float4)));
+      FE_CUDA(cudaMalloc(&fb.seg_cnt, (size_t)2 * fb.max_chains * sizeof(int)));
+      FE_CUDA(cudaMalloc(&fb.out, (size_t)fb.out_cap * sizeof(float4)));
+      FE_CUDA(cudaMallocHost(&s.h_segs, (size_t)fb.out_cap * sizeof(float4)));
+      FE_CUDA(cudaMallocHost(&s.h_fld_counts, 2 * sizeof(int)));
+    }
+    FE_CUDA(cudaMallocHost(&s.h_raw, (size_t)W_ * H_));
+    FE_CUDA(cudaEventCreateWithFlags(&s.ev_pyr, cudaEventDisableTiming));
+    FE_CUDA(cudaEventCreateWithFlags(&s.ev_lines, cudaEventDisableTiming));
+    for (auto &e : s.ev_t) FE_CUDA(cudaEventCreate(&e));
+  }
+  for (auto &e : ev_pt_) FE_CUDA(cudaEventCreate(&e));
+
+  // detection scratch (Grider_GRID may shrink the grid when num_features < grid_x * grid_y; cells never get larger
+  // than the image, so size for the worst case)
+  max_cells_ = std::max(cfg_.grid_x * cfg_.grid_y, 1);
+  max_bands_ = (H_ + kFastBandRows - 1) / kFastBandRows;
+  kps_cap_ = W_ * H_ / 4 + 1024;
+  FE_CUDA(cudaMalloc(&d_cells_, (size_t)max_cells_ * sizeof(FastCell)));
+  FE_CUDA(cudaMallocHost(&h_cells_, (size_t)max_cells_ * sizeof(FastCell)));
+  FE_CUDA(cudaMalloc(&d_fast_total_, sizeof(unsigned)));
+  FE_CUDA(cudaMalloc(&d_kps_, (size_t)kps_cap_ * sizeof(unsigned)));
+  FE_CUDA(cudaMallocHost(&h_kps_, (size_t)kps_cap_ * sizeof(unsigned)));
+  FE_CUDA(cudaMalloc(&d_band_off_, (size_t)max_cells_ * max_bands_ * sizeof(int)));
+  FE_CUDA(cudaMalloc(&d_band_cnt_, (size_t)max_cells_ * max_bands_ * sizeof(int)));
+  FE_CUDA(cudaMallocHost(&h_band_, (size_t)(1 + 2 * max_cells_ * max_bands_) * sizeof(int)));
+  occ_bits_.assign((size_t)((W_ + 63) / 64) * H_, 0);
+
+  max_pts_ = std::max(4096, 8 * cfg_.num_features) + 4096 * (cfg_.line_samples > 0 ? 8 : 0);
+  FE_CUDA(cudaMalloc(&d_pts0_, (size_t)max_pts_ * sizeof(float2)));
+  FE_CUDA(cudaMalloc(&d_pts1_, (size_t)max_pts_ * sizeof(float2)));
+  FE_CUDA(cudaMalloc(&d_p0n_, (size_t)max_pts_ * sizeof(float2)));
+  FE_CUDA(cudaMalloc(&d_p1n_, (size_t)max_pts_ * sizeof(float2)));
+  FE_CUDA(cudaMalloc(&d_status_, (size_t)max_pts_));
+  FE_CUDA(cudaMallocHost(&h_pts0_, (size_t)max_pts_ * sizeof(float2)));
+  FE_CUDA(cudaMallocHost(&h_pts1_, (size_t)max_pts_ * sizeof(float2)));
+  FE_CUDA(cudaMallocHost(&h_p0n_, (size_t)max_pts_ * sizeof(float2)));
+  FE_CUDA(cudaMallocHost(&h_p1n_, (size_t)max_pts_ * sizeof(float2)));
+  FE_CUDA(cudaMallocHost(&h_status_, (size_t)max_pts_));
+  FE_CUDA(cudaDeviceSynchronize());
+  return FE_OK;
+}
+
+FeContext::~FeContext() {
+  cudaSetDevice(device_);
+  cudaDeviceSynchronize();
+  for (FrameSlot &s : slots_) {
+    cudaFree(s.raw.p);
+    for (int l = 0; l < s.pyr.n; l++) cudaFree(s.pyr.lvl[l].p);
+    cudaFree(s.half.p);
+    cudaFree(s.fld.edges); cudaFree(s.fld.chain_pts); cudaFree(s.fld.chain_off); cudaFree(s.fld.n_chains);
+    cudaFree(s.fld.segs); cudaFree(s.fld.seg_cnt); cudaFree(s.fld.out);
+    cudaFreeHost(s.h_segs); cudaFreeHost(s.h_fld_counts); cudaFreeHost(s.h_raw);
+    if (s.ev_pyr) cudaEventDestroy(s.ev_pyr);
+    if (s.ev_lines) cudaEventDestroy(s.ev_lines);
+    for (auto &e : s.ev_t) if (e) cudaEventDestroy(e);
+  }
+  for (auto &e : ev_pt_) if (e) cudaEventDestroy(e);
+  cudaFree(d_hist_); cudaFree(d_counters_);
+  cudaFree(d_cells_); cudaFreeHost(h_cells_); cudaFree(d_fast_total_); cudaFree(d_kps_); cudaFreeHost(h_kps_);
+  cudaFree(d_band_off_); cudaFree(d_band_cnt_); cudaFreeHost(h_band_);
+  cudaFree(d_pts0_); cudaFree(d_pts1_); cudaFree(d_p0n_); cudaFree(d_p1n_); cudaFree(d_status_);
+  cudaFreeHost(h_pts0_); cudaFreeHost(h_pts1_); cudaFreeHost(h_p0n_); cudaFreeHost(h_p1n_); cudaFreeHost(h_status_);
+  if (s_img_) cudaStreamDestroy(s_img_);
+  if (s_pt_) cudaStreamDestroy(s_pt_);
+  if (s_line_) cudaStreamDestroy(s_line_);
+}
+
+int FeContext::set_calib(const double K[4], const double D[4]) {
+  for (int i = 0; i < 4; i++) {
+    cfg_.K[i] = K[i];
+    cfg_.D[i] = D[i];
+  }
+  return FE_OK;
+}
+
+void FeContext::change_feat_id(uint64_t id_old, uint64_t id_new) {  // TrackBase.cpp:267-285 (tracker side)
+  for (uint64_t &id : ids_last_)
+    if (id == id_old) id = id_new;
+}
+
+// cv::undistortPoints on one point (Appendix A6) — only for the two endpoints of each line row
+void FeContext::undistort_host(float u, float v, float &un, float &vn) const {
+  const double *K = cfg_.K, *D = cfg_.D;
+  double x0 = ((double)u - K[2]) / K[0], y0 = ((double)v - K[3]) / K[1];
+  double x = x0, y = y0;
+  for (int j = 0; j < 5; j++) {
+    double r2 = x * x + y * y;
+    double icdist = 1.0 / (1.0 + (D[1] * r2 + D[0]) * r2);
+    double dx = 2 * D[2] * x * y + D[3] * (r2 + 2 * x * x);
+    double dy = D[2] * (r2 + 2 * y * y) + 2 * D[3] * x * y;
+    x = (x0 - dx) * icdist;
+    y = (y0 - dy) * icdist;
+  }
+  un = (float)x;
+  vn = (float)y;
+}
+
+// ------------------------------------------------------------------------------------------------ submit
+int FeContext::enqueue_frame_independent(FrameSlot &s) {
+  const bool tm = timing;
+  s.timed = tm;
+  if (cfg_.histogram_method == FE_HIST_HISTOGRAM) {
+    launch_hist(s.raw, d_hist_, s_img_);
+    times.kernel_launches_total++;
+  }
+  if (tm) cudaEventRecord(s.ev_t[2], s_img_);
+  DevImage half = cfg_.use_lines ? s.half : DevImage();
+  launch_eq_pyr1(s.raw, d_hist_, d_counters_, cfg_.histogram_method == FE_HIST_HISTOGRAM ? 1 : 0, s.pyr.lvl[0],
+                 s.pyr.n > 1 ? s.pyr.lvl[1] : DevImage(), half, s_img_);
+  times.kernel_launches_total++;
+  if (tm) cudaEventRecord(s.ev_t[3], s_img_);
+  FE_CUDA(cudaEventRecord(s.ev_lines, s_img_));  // reused as "half image ready" until the line stream re-records it
+  if (s.pyr.n > 2) {
+    launch_pyr_rest(s.pyr, d_counters_ + 1, s_img_);
+    times.kernel_launches_total++;
+  }
+  if (tm) cudaEventRecord(s.ev_t[4], s_img_);
+  FE_CUDA(cudaEventRecord(s.ev_pyr, s_img_));
+  if (cfg_.use_lines && s.has_vp) {
+    FE_CUDA(cudaStreamWaitEvent(s_line_, s.ev_lines, 0));
+    if (tm) cudaEventRecord(s.ev_t[5], s_line_);
+    launch_canny(s.half, cfg_.canny_th1, cfg_.canny_th2, s.fld, s_line_);
+    if (tm) cudaEventRecord(s.ev_t[6], s_line_);
+    launch_fld(s.half, cfg_.fld_length_threshold, cfg_.fld_distance_threshold, s.fld, s_line_);
+    times.kernel_launches_total += 4;
+    if (tm) cudaEventRecord(s.ev_t[7], s_line_);
+    FE_CUDA(cudaMemcpyAsync(s.h_fld_counts, s.fld.n_chains, 2 * sizeof(int), cudaMemcpyDeviceToHost, s_line_));
+    FE_CUDA(cudaMemcpyAsync(s.h_segs, s.fld.out, 1024 * sizeof(float4), cudaMemcpyDeviceToHost, s_line_));
+    FE_CUDA(cudaEventRecord(s.ev_lines, s_line_));
+  }
+  FE_CUDA(cudaGetLastError());
+  return FE_OK;
+}
+
+int FeContext::submit(double t, const uint8_t *image, int stride, bool on_device, const uint8_t *mask, int mask_stride,
+                      const double vp[6]) {
+  FE_CUDA(cudaSetDevice(device_));
+  int si = -1;
+  for (int i = 0; i < (int)slots_.size(); i++)
+    if (!slots_[i].busy && i != last_slot_) { si = i; break; }
+  if (si < 0) {
+    last_error = "submit: lookahead window full (collect a frame first)";
+    return FE_BAD_ARG;
+  }
+  FrameSlot &s = slots_[si];
+  s.busy = true;
+  s.timestamp = t;
+  s.has_vp = vp != nullptr;
+  if (vp) std::memcpy(s.vp, vp, sizeof(s.vp));
+  if (mask) {
+    s.mask.resize((size_t)W_ * H_);
+    for (int y = 0; y < H_; y++) std::memcpy(&s.mask[(size_t)y * W_], mask + (size_t)y * mask_stride, W_);
+  } else {
+    s.mask.clear();
+  }
+  if (timing) cudaEventRecord(s.ev_t[0], s_img_);
+  if (on_device) {
+    FE_CUDA(cudaMemcpy2DAsync(s.raw.p, s.raw.pitch, image, stride, W_, H_, cudaMemcpyDeviceToDevice, s_img_));
+  } else {
+    cudaPointerAttributes attr;
+    bool pinned = cudaPointerGetAttributes(&attr, image) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const uint8_t *src = image;
+    int sstride = stride;
+    if (!pinned) {  // pageable caller memory: stage through the slot's pinned buffer
+      for (int y = 0; y < H_; y++) std::memcpy(s.h_raw + (size_t)y * W_, image + (size_t)y * stride, W_);
+      src = s.h_raw;
+      sstride = W_;
+    }
+    FE_CUDA(cudaMemcpy2DAsync(s.raw.p, s.raw.pitch, src, sstride, W_, H_, cudaMemcpyHostToDevice, s_img_));
+  }
+  if (timing) cudaEventRecord(s.ev_t[1], s_img_);
+  int rc = enqueue_frame_independent(s);
+  if (rc) return rc;
+  queue_.push_back(si);
+  return FE_OK;
+}
+
+static void acc_time(FeStageTimes &t, int stage, cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) {
+    t.ms[stage] += ms;
+    t.launches[stage]++;
+  } else {
+    cudaGetLastError();
+  }
+}
+
+int FeContext::collect(FeFrameInfo *info) {
+  FE_CUDA(cudaSetDevice(device_));
+  if (queue_.empty()) {
+    last_error = "collect: nothing submitted";
+    return FE_BAD_ARG;
+  }
+  const int si = queue_.front();
+  queue_.erase(queue_.begin());
+  FrameSlot &cur = slots_[si];
+  cur_slot_ = si;
+  FeFrameInfo local;
+  std::memset(&local, 0, sizeof(local));
+  local.timestamp = cur.timestamp;
+  point_rows.clear();
+  line_rows.clear();
+  line_points.clear();
+  sample_uv.clear();
+  sample_status.clear();
+
+  FE_CUDA(cudaStreamWaitEvent(s_pt_, cur.ev_pyr, 0));
+  int rc = klt_feed(cur, &local);
+  if (rc) return rc;
+  if (cfg_.use_lines && cur.has_vp) {
+    rc = lsd_feed(cur, &local);
+    if (rc) return rc;
+  }
+  if (cur.timed) {
+    FE_CUDA(cudaEventSynchronize(cur.ev_pyr));
+    acc_time(times, FE_STAGE_H2D, cur.ev_t[0], cur.ev_t[1]);
+    if (cfg_.histogram_method == FE_HIST_HISTOGRAM) acc_time(times, FE_STAGE_HIST, cur.ev_t[1], cur.ev_t[2]);
+    acc_time(times, FE_STAGE_EQ_PYR, cur.ev_t[2], cur.ev_t[3]);
+    acc_time(times, FE_STAGE_PYR_REST, cur.ev_t[3], cur.ev_t[4]);
+    if (cfg_.use_lines && cur.has_vp) {
+      acc_time(times, FE_STAGE_CANNY, cur.ev_t[5], cur.ev_t[6]);
+      acc_time(times, FE_STAGE_FLD, cur.ev_t[6], cur.ev_t[7]);
+    }
+  }
+  times.frames++;
+  // move forward in time (TrackKLT.cpp:182-189): the previous "last" slot becomes free
+  if (last_slot_ >= 0) slots_[last_slot_].busy = false;
+  last_slot_ = si;
+  local.n_point_rows = (int)point_rows.size();
+  local.n_line_rows = (int)line_rows.size();
+  local.n_last_obs = (int)pts_last_.size();
+  if (info) *info = local;
+  return FE_OK;
+}
+
+int FeContext::feed(double t, const uint8_t *image, int w, int h, int stride, bool on_device, const uint8_t *mask,
+                    int mask_stride, const double vp[6], FeFrameInfo *info) {
+  if (!image || w != W_ || h != H_ || stride < w || (mask && mask_stride < w)) {
+    last_error = "feed: image/mask size does not match the handle";   // TrackKLT.cpp:37-43 exits here
+    return FE_BAD_ARG;
+  }
+  if (!queue_.empty()) {
+    last_error = "feed: frames submitted with plviwo_fe_submit are still pending";
+    return FE_BAD_ARG;
+  }
+  int rc = submit(t, image, stride, on_device, mask, mask_stride, vp);
+  if (rc) return rc;
+  return collect(info);
+}
+
+// -------------------------------------------------------------------------------------------- TrackKLT
+static inline bool mask_hit(const FrameSlot &s, int W, int y, int x) { return !s.mask.empty() && s.mask[(size_t)y * W + x] > 127; }
+
+int FeContext::klt_feed(FrameSlot &cur, FeFrameInfo *info) {
+  // TrackKLT.cpp:110-123 — nothing tracked last time: detect on the CURRENT image only
+  if (pts_last_.empty() || last_slot_ < 0) {
+    std::vector<Pt> good;
+    std::vector<uint64_t> good_ids;
+    int rc = perform_detection(cur, good, good_ids, info);
+    if (rc) return rc;
+    pts_last_ = good;
+    ids_last_ = good_ids;
+    info->first_frame = 1;
+    return FE_OK;
+  }
+  FrameSlot &last = slots_[last_slot_];
+  // top-off on the PREVIOUS image with the previous points (:127-130)
+  std::vector<Pt> pts_old = pts_last_;
+  std::vector<uint64_t> ids_old = ids_last_;
+  int rc = perform_detection(last, pts_old, ids_old, info);
+  if (rc) return rc;
+  std::vector<Pt> pts_new = pts_old;
+  std::vector<uint8_t> mask_ll;
+  bool mask_empty = true;
+  rc = perform_matching(last, cur, pts_old, pts_new, mask_ll, mask_empty, info);
+  if (rc) return rc;
+  if (mask_empty) {  // :143-152
+    pts_last_.clear();
+    ids_last_.clear();
+    info->reset = 1;
+    return FE_OK;
+  }
+  std::vector<Pt> good;
+  std::vector<uint64_t> good_ids;
+  good.reserve(pts_new.size());
+  good_ids.reserve(pts_new.size());
+  for (size_t i = 0; i < pts_new.size(); i++) {  // :159-173
+    const Pt &p = pts_new[i];
+    if (p.x < 0 || p.y < 0 || (int)p.x >= W_ || (int)p.y >= H_) continue;
+    if (mask_hit(cur, W_, (int)p.y, (int)p.x)) continue;
+    if (mask_ll[i]) {
+      good.push_back(p);
+      good_ids.push_back(ids_old[i]);
+      // :176-179 — undistort_cv(pt) of the tracked point is exactly the p1n the LK epilogue produced
+      FePointRow r;
+      r.id = ids_old[i];
+      r.u = p.x;
+      r.v = p.y;
+      r.un = h_p1n_[i].x;
+      r.vn = h_p1n_[i].y;
+      point_rows.push_back(r);
+    }
+  }
+  pts_last_ = good;
+  ids_last_ = good_ids;
+  return FE_OK;
+}
+
+namespace {
+struct KpSort {  // same footprint as cv::KeyPoint; sorted with the reference's by-value comparator
+  float x, y, size, angle, response;
+  int octave, class_id;
+};
+bool compare_response(KpSort first, KpSort second) { return first.response > second.response; }  // Grider_FAST.h:57
+}  // namespace
+
+int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, std::vector<uint64_t> &ids0, FeFrameInfo *info) {
+  const int d = cfg_.min_px_dist;
+  const int cols = W_, rows = H_;
+  const int close_w = (int)((float)cols / (float)d), close_h = (int)((float)rows / (float)d);
+  std::vector<uint8_t> grid_close((size_t)close_w * close_h, 0);
+  const float size_x = (float)cols / (float)cfg_.grid_x, size_y = (float)rows / (float)cfg_.grid_y;
+  const int gx = cfg_.grid_x, gy = cfg_.grid_y;
+  std::vector<uint8_t> grid_grid((size_t)gx * gy, 0);
+  // mask0_updated = mask0.clone() plus filled squares: kept as a bit mask, only built if detection really runs
+  const int bw = (cols + 63) / 64;
+  std::vector<std::pair<int, int>> rects;
+  {
+    size_t keep = 0;
+    for (size_t k = 0; k < pts0.size(); k++) {  // TrackKLT.cpp:411-464
+      const Pt kp = pts0[k];
+      int x = (int)kp.x, y = (int)kp.y;
+      const int edge = 10;
+      if (x < edge || x >= cols - edge || y < edge || y >= rows - edge) continue;
+      int x_close = (int)(kp.x / (float)d), y_close = (int)(kp.y / (float)d);
+      if (x_close < 0 || x_close >= close_w || y_close < 0 || y_close >= close_h) continue;
+      int x_grid = (int)std::floor(kp.x / size_x), y_grid = (int)std::floor(kp.y / size_y);
+      if (x_grid < 0 || x_grid >= gx || y_grid < 0 || y_grid >= gy) continue;
+      if (grid_close[(size_t)y_close * close_w + x_close] > 127) continue;
+      if (mask_hit(img, cols, y, x)) continue;
+      grid_close[(size_t)y_close * close_w + x_close] = 255;
+      uint8_t &g = grid_grid[(size_t)y_grid * gx + x_grid];
+      if (g < 255) g += 1;
+      if (x - d >= 0 && x + d < cols && y - d >= 0 && y + d < rows) rects.emplace_back(x, y);
+      pts0[keep] = kp;
+      ids0[keep] = ids0[k];
+      keep++;
+    }
+    pts0.resize(keep);
+    ids0.resize(keep);
+  }
+  const double min_feat_percent = 0.50;
+  int num_featsneeded = cfg_.num_features - (int)pts0.size();
+  if (num_featsneeded < std::min(20, (int)(min_feat_percent * cfg_.num_features))) return FE_OK;  // :468-471
+  info->detection_ran = 1;
+
+  // mask0_grid = resize(mask0, grid, INTER_NEAREST) (:479-480)
+  std::vector<uint8_t> mask_grid((size_t)gx * gy, 0);
+  if (!img.mask.empty()) {
+    const double ifx = 1.0 / ((double)gx / (double)cols), ify = 1.0 / ((double)gy / (double)rows);
+    for (int y = 0; y < gy; y++) {
+      int sy = std::min((int)std::floor(y * ify), rows - 1);
+      for (int x = 0; x < gx; x++) {
+        int sx = std::min((int)std::floor(x * ifx), cols - 1);
+        mask_grid[(size_t)y * gx + x] = img.mask[(size_t)sy * cols + sx];
+      }
+    }
+  }
+  int num_features_grid = (int)((double)cfg_.num_features / (double)(gx * gy)) + 1;
+  int num_features_grid_req = std::max(1, (int)(min_feat_percent * num_features_grid));
+  std::vector<std::pair<int, int>> valid_locs;
+  for (int x = 0; x < gx; x++)        // x-major order (:486-492)
+    for (int y = 0; y < gy; y++)
+      if ((int)grid_grid[(size_t)y * gx + x] < num_features_grid_req && (int)mask_grid[(size_t)y * gx + x] != 255)
+        valid_locs.emplace_back(x, y);
+
+  // ---- Grider_GRID::perform_griding (Grider_GRID.h:74-180)
+  std::vector<Pt> ext;  // pts0_ext after sub-pixel refinement
+  tap_fast_.clear();
+  tap_subpix_.clear();
+  if (!valid_locs.empty()) {
+    int ggx = gx, ggy = gy;
+    if (cfg_.num_features < ggx * ggy) {  // :88-92
+      double ratio = (double)ggx / (double)ggy;
+      ggy = (int)std::ceil(std::sqrt(cfg_.num_features / ratio));
+      ggx = (int)std::ceil(ggy * ratio);
+    }
+    const int nfg = (int)((double)cfg_.num_features / (double)(ggx * ggy)) + 1;
+    const int csx = cols / ggx, csy = rows / ggy;
+    if (csx <= 0 || csy <= 0) {
+      last_error = "perform_griding: zero cell size";
+      return FE_BAD_ARG;
+    }
+    // cells in valid_locs order; out-of-image cells are skipped (:117-118)
+    std::vector<int> cell_of_loc(valid_locs.size(), -1);
+    int ncell = 0;
+    for (size_t r = 0; r < valid_locs.size(); r++) {
+      int x = valid_locs[r].first * csx, y = valid_locs[r].second * csy;
+      if (x + csx > cols || y + csy > rows) continue;
+      if (ncell >= max_cells_) break;
+      h_cells_[ncell] = FastCell{x, y, csx, csy};
+      cell_of_loc[r] = ncell++;
+    }
+    if (ncell > 0) {
+      const int nb = (csy + kFastBandRows - 1) / kFastBandRows;
+      FE_CUDA(cudaMemcpyAsync(d_cells_, h_cells_, (size_t)ncell * sizeof(FastCell), cudaMemcpyHostToDevice, s_pt_));
+      FE_CUDA(cudaMemsetAsync(d_fast_total_, 0, sizeof(unsigned), s_pt_));
+      if (timing) cudaEventRecord(ev_pt_[0], s_pt_);
+      launch_fast(img.pyr.lvl[0], d_cells_, ncell, nb, csx, cfg_.fast_threshold, d_fast_total_, d_band_off_, d_band_cnt_,
+                  d_kps_, kps_cap_, s_pt_);
+      times.kernel_launches_total++;
+      if (timing) cudaEventRecord(ev_pt_[1], s_pt_);
+      const int ntab = ncell * nb;
+      const int spec = 8192;  // speculative first chunk of the compact keypoint list
+      FE_CUDA(cudaMemcpyAsync(h_band_, d_fast_total_, sizeof(unsigned), cudaMemcpyDeviceToHost, s_pt_));
+      FE_CUDA(cudaMemcpyAsync(h_band_ + 1, d_band_off_, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, s_pt_));
+      FE_CUDA(cudaMemcpyAsync(h_band_ + 1 + ntab, d_band_cnt_, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, s_pt_));
+      FE_CUDA(cudaMemcpyAsync(h_kps_, d_kps_, (size_t)std::min(spec, kps_cap_) * sizeof(unsigned), cudaMemcpyDeviceToHost, s_pt_));
+      FE_CUDA(cudaStreamSynchronize(s_pt_));
+      if (timing) acc_time(times, FE_STAGE_FAST, ev_pt_[0], ev_pt_[1]);
+      int total = std::min(h_band_[0], kps_cap_);
+      if (total > spec) {
+        FE_CUDA(cudaMemcpyAsync(h_kps_ + spec, d_kps_ + spec, (size_t)(total - spec) * sizeof(unsigned), cudaMemcpyDeviceToHost, s_pt_));
+        FE_CUDA(cudaStreamSynchronize(s_pt_));
+      }
+      // mask0_updated as a bit mask: caller mask > 127 or inside a (2d+1)^2 square of a kept point (:457-461)
+      std::fill(occ_bits_.begin(), occ_bits_.end(), 0);
+      if (!img.mask.empty())
+        for (int y = 0; y < rows; y++)
+          for (int x = 0; x < cols; x++)
+            if (img.mask[(size_t)y * cols + x] > 127) occ_bits_[(size_t)y * bw + (x >> 6)] |= 1ull << (x & 63);
+      for (auto &rc : rects) {
+        int x0 = rc.first - d, x1 = rc.first + d;
+        for (int y = rc.second - d; y <= rc.second + d; y++) {
+          uint64_t *row = &occ_bits_[(size_t)y * bw];
+          int w0 = x0 >> 6, w1 = x1 >> 6;
+          uint64_t m0 = ~0ull << (x0 & 63), m1 = (x1 & 63) == 63 ? ~0ull : ((1ull << ((x1 & 63) + 1)) - 1);
+          if (w0 == w1) {
+            row[w0] |= m0 & m1;
+          } else {
+            row[w0] |= m0;
+            for (int w = w0 + 1; w < w1; w++) row[w] = ~0ull;
+            row[w1] |= m1;
+          }
+        }
+      }
+      const int *band_off = h_band_ + 1, *band_cnt = h_band_ + 1 + ntab;
+      std::vector<KpSort> kps;
+      std::vector<Pt> selected;
+      for (size_t r = 0; r < valid_locs.size(); r++) {
+        int c = cell_of_loc[r];
+        if (c < 0) continue;
+        kps.clear();
+        for (int b = 0; b < nb; b++) {
+          int off = band_off[c * nb + b], cnt = band_cnt[c * nb + b];
+          for (int k = 0; k < cnt && off + k < total; k++) {
+            unsigned v = h_kps_[off + k];
+            KpSort kp{(float)(v & 0xfff), (float)((v >> 12) & 0xfff), 7.f, -1.f, (float)(v >> 24), 0, -1};
+            kps.push_back(kp);
+            tap_fast_.insert(tap_fast_.end(), {valid_locs[r].first, valid_locs[r].second, (int)(v & 0xfff), (int)((v >> 12) & 0xfff), (int)(v >> 24)});
+          }
+        }
+        std::sort(kps.begin(), kps.end(), compare_response);  // Grider_GRID.h:128 (unstable, ties!)
+        const int x0 = h_cells_[c].x, y0 = h_cells_[c].y;
+        for (size_t i = 0; i < (size_t)nfg && i < kps.size(); i++) {  // :133-149
+          Pt p{kps[i].x + (float)x0, kps[i].y + (float)y0};
+          if ((int)p.x < 0 || (int)p.x > cols || (int)p.y < 0 || (int)p.y > rows) continue;
+          int ix = (int)p.x, iy = (int)p.y;
+          if (iy >= rows || ix >= cols) continue;  // the reference would read out of bounds here; cannot happen
+          if ((occ_bits_[(size_t)iy * bw + (ix >> 6)] >> (ix & 63)) & 1ull) continue;
+          selected.push_back(p);
+        }
+      }
+      // cv::cornerSubPix on every selected point (:163-179)
+      int ns = std::min((int)selected.size(), max_pts_);
+      if (ns > 0) {
+        for (int i = 0; i < ns; i++) h_pts0_[i] = make_float2(selected[i].x, selected[i].y);
+        FE_CUDA(cudaMemcpyAsync(d_pts0_, h_pts0_, (size_t)ns * sizeof(float2), cudaMemcpyHostToDevice, s_pt_));
+        if (timing) cudaEventRecord(ev_pt_[2], s_pt_);
+        launch_corner_subpix(img.pyr.lvl[0], d_pts0_, ns, s_pt_);
+        times.kernel_launches_total++;
+        if (timing) cudaEventRecord(ev_pt_[3], s_pt_);
+        FE_CUDA(cudaMemcpyAsync(h_pts1_, d_pts0_, (size_t)ns * sizeof(float2), cudaMemcpyDeviceToHost, s_pt_));
+        FE_CUDA(cudaStreamSynchronize(s_pt_));
+        if (timing) acc_time(times, FE_STAGE_SUBPIX, ev_pt_[2], ev_pt_[3]);
+        ext.resize(ns);
+        for (int i = 0; i < ns; i++) {
+          ext[i] = Pt{h_pts1_[i].x, h_pts1_[i].y};
+          tap_subpix_.insert(tap_subpix_.end(), {selected[i].x, selected[i].y, ext[i].x, ext[i].y});
+        }
+      }
+    }
+  }
+  // reject new points that are close to an existing one (:497-512), then hand out ids (:519-527)
+  int added = 0;
+  for (const Pt &kp : ext) {
+    int x_grid = (int)(kp.x / (float)d), y_grid = (int)(kp.y / (float)d);
+    if (x_grid < 0 || x_grid >= close_w || y_grid < 0 || y_grid >= close_h) continue;
+    if (grid_close[(size_t)y_grid * close_w + x_grid] > 127) continue;
+    grid_close[(size_t)y_grid * close_w + x_grid] = 255;
+    pts0.push_back(kp);
+    ids0.push_back(++currid_);
+    added++;
+  }
+  info->n_detected += added;
+  return FE_OK;
+}
+
+int FeContext::perform_matching(const FrameSlot &f0, const FrameSlot &f1, std::vector<Pt> &pts0, std::vector<Pt> &pts1,
+                                std::vector<uint8_t> &mask_out, bool &mask_empty, FeFrameInfo *info) {
+  mask_out.clear();
+  mask_empty = true;
+  const int n = (int)pts0.size();
+  if (n == 0) return FE_OK;                  // :836-837 (mask stays empty => caller resets)
+  mask_empty = false;
+  if (n < 10) {                              // :848-852
+    mask_out.assign(n, 0);
+    return FE_OK;
+  }
+  // extension: samples along last frame's segments ride in the same LK launch (not part of the RANSAC gate)
+  int ns = 0;
+  if (cfg_.line_samples > 0 && !lines_last_.empty()) {
+    const int S = cfg_.line_samples;
+    for (const float4 &l : lines_last_) {
+      for (int k = 0; k < S && n + ns < max_pts_; k++) {
+        float a = S > 1 ? (float)k / (float)(S - 1) : 0.5f;
+        h_pts0_[n + ns] = make_float2(l.x + (l.z - l.x) * a, l.y + (l.w - l.y) * a);
+        ns++;
+      }
+    }
+  }
+  const int nt = std::min(n, max_pts_) + ns;
+  for (int i = 0; i < n && i < max_pts_; i++) h_pts0_[i] = make_float2(pts0[i].x, pts0[i].y);
+  FE_CUDA(cudaMemcpyAsync(d_pts0_, h_pts0_, (size_t)nt * sizeof(float2), cudaMemcpyHostToDevice, s_pt_));
+  FE_CUDA(cudaMemcpyAsync(d_pts1_, d_pts0_, (size_t)nt * sizeof(float2), cudaMemcpyDeviceToDevice, s_pt_));
+  LkParams prm;
+  prm.win = cfg_.win_size;
+  prm.max_level = cfg_.pyr_levels;
+  prm.max_count = 30;
+  prm.eps_sq = 0.01f * 0.01f;
+  prm.min_eig = 1e-4f;
+  prm.undistort = 1;
+  for (int i = 0; i < 4; i++) { prm.K[i] = cfg_.K[i]; prm.D[i] = cfg_.D[i]; }
+  if (timing) cudaEventRecord(ev_pt_[4], s_pt_);
+  launch_lk(f0.pyr, f1.pyr, d_pts0_, d_pts1_, d_status_, d_p0n_, d_p1n_, nt, prm, s_pt_);
+  times.kernel_launches_total++;
+  if (timing) cudaEventRecord(ev_pt_[5], s_pt_);
+  FE_CUDA(cudaMemcpyAsync(h_pts1_, d_pts1_, (size_t)nt * sizeof(float2), cudaMemcpyDeviceToHost, s_pt_));
+  FE_CUDA(cudaMemcpyAsync(h_status_, d_status_, (size_t)nt, cudaMemcpyDeviceToHost, s_pt_));
+  FE_CUDA(cudaMemcpyAsync(h_p0n_, d_p0n_, (size_t)nt * sizeof(float2), cudaMemcpyDeviceToHost, s_pt_));
+  FE_CUDA(cudaMemcpyAsync(h_p1n_, d_p1n_, (size_t)nt * sizeof(float2), cudaMemcpyDeviceToHost, s_pt_));
+  FE_CUDA(cudaStreamSynchronize(s_pt_));
+  if (timing) acc_time(times, FE_STAGE_LK, ev_pt_[4], ev_pt_[5]);
+
+  // RANSAC gate on the normalised coordinates (:869-873)
+  const double max_focal = std::max(cfg_.K[0], cfg_.K[1]);
+  std::vector<uint8_t> mask_rsc(n, 0);
+  int mask_valid = 0;
+  int n_in = ransac_fundamental(reinterpret_cast<const float *>(h_p0n_), reinterpret_cast<const float *>(h_p1n_), n,
+                                2.0 / max_focal, 0.999, mask_rsc.data(), &mask_valid);
+  mask_out.resize(n);
+  int n_klt = 0;
+  tap_lk_.clear();
+  for (int i = 0; i < n; i++) {  // :876-885
+    mask_out[i] = (h_status_[i] && mask_valid && mask_rsc[i]) ? 1 : 0;
+    n_klt += h_status_[i] ? 1 : 0;
+    pts1[i] = Pt{h_pts1_[i].x, h_pts1_[i].y};
+    tap_lk_.insert(tap_lk_.end(), {pts0[i].x, pts0[i].y, pts1[i].x, pts1[i].y, (float)h_status_[i], (float)(mask_valid && mask_rsc[i])});
+  }
+  for (int k = 0; k < ns; k++) {
+    sample_uv.insert(sample_uv.end(), {h_pts0_[n + k].x, h_pts0_[n + k].y, h_pts1_[n + k].x, h_pts1_[n + k].y});
+    sample_status.push_back(h_status_[n + k]);
+  }
+  info->n_lk_in = n;
+  info->n_klt_ok = n_klt;
+  info->n_ransac_ok = n_in;
+  return FE_OK;
+}
+
+// -------------------------------------------------------------------------------------------- TrackLSD
+namespace {
+// TrackLSD::PointLineDistance (TrackLSD.cpp:794-814): float arithmetic, std::pow(float,int) promotes to double
+float point_line_distance(const float4 &line, float x0, float y0) {
+  float x1 = line.x, y1 = line.y, x2 = line.z, y2 = line.w;
+  float cross = (x2 - x1) * (x0 - x1) + (y2 - y1) * (y0 - y1);
+  if (cross <= 0) return std::sqrt((x0 - x1) * (x0 - x1) + (y0 - y1) * (y0 - y1));
+  float d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1);
+  if (cross > d) return std::sqrt((x0 - x2) * (x0 - x2) + (y0 - y2) * (y0 - y2));
+  return (float)std::abs(std::fabs((y2 - y1) * x0 + (x1 - x2) * y0 + ((x2 * y1) - (x1 * y2))) /
+                         (std::sqrt(std::pow((double)(y2 - y1), 2) + std::pow((double)(x1 - x2), 2))));
+}
+// TrackLSD::LineSimilar (:816-830)
+bool line_similar(const float4 &line2, const float4 &line1) {
+  float mx = (line1.x + line1.z) / 2, my = (line1.y + line1.w) / 2;
+  return point_line_distance(line2, mx, my) <= 6;
+}
+// TrackLSD::LineClass (:335-366), including atan(dy) / dx at :350-351
+bool line_class(const float4 &line, double vx, double vy) {
+  double s[3] = {line.x, line.y, 1}, e[3] = {line.z, line.w, 1};
+  double mid[3] = {(s[0] + e[0]) / 2, (s[1] + e[1]) / 2, (s[2] + e[2]) / 2};
+  double v3[3] = {vx, vy, 1};
+  double ln[3] = {mid[1] * v3[2] - mid[2] * v3[1], mid[2] * v3[0] - mid[0] * v3[2], mid[0] * v3[1] - mid[1] * v3[0]};
+  double dis_error = (std::abs(ln[0] * s[0] + ln[1] * s[1] + ln[2] * s[2]) + std::abs(ln[0] * e[0] + ln[1] * e[1] + ln[2] * e[2])) /
+                     (2 * std::sqrt(ln[0] * ln[0] + ln[1] * ln[1]));
+  dis_error = std::abs(dis_error);
+  double angle1 = std::atan(line.y - line.w) / (line.x - line.z);   // float arithmetic, as written in the reference
+  double angle2 = std::atan(mid[1] - vy) / (mid[0] - vx);
+  double angle_error = std::abs(angle1 - angle2);
+  return dis_error <= 5.0 && angle_error <= 0.35;
+}
+int line_classification(const float4 &line, const double vp[6]) {  // :318-333
+  if (line_class(line, vp[4], vp[5])) return 3;
+  if (line_class(line, vp[2], vp[3])) return 2;
+  if (line_class(line, vp[0], vp[1])) return 1;
+  return 0;
+}
+}  // namespace
+
+int FeContext::lsd_feed(FrameSlot &cur, FeFrameInfo *info) {
+  FE_CUDA(cudaEventSynchronize(cur.ev_lines));
+  int nseg = std::min(cur.h_fld_counts[1], cur.fld.out_cap);
+  if (nseg > 1024) {
+    FE_CUDA(cudaMemcpyAsync(cur.h_segs + 1024, cur.fld.out + 1024, (size_t)(nseg - 1024) * sizeof(float4), cudaMemcpyDeviceToHost, s_line_));
+    FE_CUDA(cudaStreamSynchronize(s_line_));
+  }
+  tap_fld_.assign(reinterpret_cast<float *>(cur.h_segs), reinterpret_cast<float *>(cur.h_segs) + 4 * (size_t)nseg);
+  // perform_detection_monocular (:194-236): x2, FilterShortLines(40), a fresh id for EVERY detected line
+  std::vector<float4> lines_new;
+  std::vector<uint64_t> ids_new;
+  const float thr_sq = cfg_.line_min_length * cfg_.line_min_length;
+  for (int i = 0; i < nseg; i++) {
+    float4 l = cur.h_segs[i];
+    l.x *= 2; l.y *= 2; l.z *= 2; l.w *= 2;
+    float lsq = (l.z - l.x) * (l.z - l.x) + (l.w - l.y) * (l.w - l.y);
+    if (lsq > thr_sq) lines_new.push_back(l);
+  }
+  for (size_t i = 0; i < lines_new.size(); i++) ids_new.push_back(++line_currid_);
+  info->n_lines_detected = (int)lines_new.size();
+
+  // AssignPointToLines (:744-792) against the CURRENT points of the point tracker (:127-129)
+  const std::vector<Pt> &points = pts_last_;
+  const std::vector<uint64_t> &pids = ids_last_;
+  std::vector<std::map<int, double>> pol_new;
+  std::vector<std::vector<Pt>> positions;
+  std::vector<float4> filt_lines;
+  std::vector<uint64_t> filt_ids;
+  for (size_t i = 0; i < lines_new.size(); i++) {
+    const float4 &l = lines_new[i];
+    double lx1 = l.x, lx2 = l.y, ly1 = l.z, ly2 = l.w;  // index mix-up reproduced (:754-757)
+    double min_lx = lx1, max_lx = lx2, min_ly = ly1, max_ly = ly2;
+    if (lx1 > lx2) std::swap(min_lx, max_lx);
+    if (ly1 > ly2) std::swap(min_ly, max_ly);
+    std::map<int, double> pol;
+    std::vector<Pt> feats;
+    bool find_point = false;
+    for (size_t j = 0; j < points.size(); j++) {
+      float x = points[j].x, y = points[j].y;
+      if (x < min_lx || x > max_lx || y < min_ly || y > max_ly) continue;
+      float dist = point_line_distance(l, x, y);
+      if (dist > 5) continue;
+      pol[(int)pids[j]] = dist;
+      feats.push_back(points[j]);
+      find_point = true;
+    }
+    if (find_point) {
+      pol_new.push_back(pol);
+      filt_lines.push_back(l);
+      filt_ids.push_back(ids_new[i]);
+      positions.push_back(feats);
+    }
+  }
+  if (lines_last_.empty()) {  // first frame / lost (:95-115): no database rows
+    lines_last_ = filt_lines;
+    line_ids_last_ = filt_ids;
+    pol_last_ = pol_new;
+    return FE_OK;
+  }
+  // LineMatch (:368-407): i over new lines, j over last lines, the LAST satisfying j wins
+  std::map<int, int> matches;
+  const size_t n0 = pol_last_.size(), n1 = pol_new.size();
+  if (n0 != 0 && n1 != 0) {
+    for (size_t i = 0; i < n1; i++) {
+      if (pol_new[i].size() < 1) continue;
+      for (size_t j = 0; j < n0; j++) {
+        if (pol_last_[j].size() < 1) continue;
+        int m = 0;
+        for (auto &pt : pol_last_[j]) {
+          if (pol_new[i].find(pt.first) == pol_new[i].end()) continue;
+          m += 1;
+          if (m >= 2) {
+            matches[(int)i] = (int)j;
+            break;
+          } else if (m == 1 && line_similar(filt_lines[i], lines_last_[j])) {
+            matches[(int)i] = (int)j;
+            break;
+          }
+        }
+      }
+    }
+  }
+  info->n_line_matches = (int)matches.size();
+  std::vector<uint64_t> good_ids(filt_lines.size());
+  for (size_t i = 0; i < filt_lines.size(); i++) {  // :146-158
+    auto it = matches.find((int)i);
+    int id = it != matches.end() ? (int)line_ids_last_[it->second] : (int)filt_ids[i];
+    good_ids[i] = (uint64_t)(size_t)id;
+  }
+  for (size_t i = 0; i < filt_lines.size(); i++) {  // :163-167
+    FeLineRow r;
+    std::memset(&r, 0, sizeof(r));
+    r.id = good_ids[i];
+    const float4 &l = filt_lines[i];
+    r.line[0] = l.x; r.line[1] = l.y; r.line[2] = l.z; r.line[3] = l.w;
+    undistort_host(l.x, l.y, r.line_n[0], r.line_n[1]);
+    undistort_host(l.z, l.w, r.line_n[2], r.line_n[3]);
+    r.D = line_classification(l, cur.vp);
+    r.n_pts = (int)pol_new[i].size();
+    r.pt_offset = (int)line_points.size();
+    r.matched = matches.count((int)i) ? 1 : 0;
+    size_t k = 0;
+    for (auto &pt : pol_new[i]) {
+      FeLinePoint lp;
+      lp.pid = pt.first;
+      lp.dist = (float)pt.second;
+      lp.u = positions[i][k].x;
+      lp.v = positions[i][k].y;
+      line_points.push_back(lp);
+      k++;
+    }
+    line_rows.push_back(r);
+  }
+  lines_last_ = filt_lines;  // :175-182
+  line_ids_last_ = good_ids;
+  pol_last_ = pol_new;
+  return FE_OK;
+}
+
+// ------------------------------------------------------------------------------------------ state / taps
+namespace {
+struct StateHeader {
+  uint32_t magic, version;
+  int32_t w, h;
+  uint64_t currid, line_currid;
+  int32_t n_pts, n_lines, has_image, has_mask;
+  int32_t n_pol_entries, reserved;
+};
+}  // namespace
+
+int FeContext::get_state(void *buf, size_t cap, size_t *n_bytes) {
+  FE_CUDA(cudaSetDevice(device_));
+  StateHeader hd;
+  std::memset(&hd, 0, sizeof(hd));
+  hd.magic = 0x504c5657u;
+  hd.version = 1;
+  hd.w = W_;
+  hd.h = H_;
+  hd.currid = currid_;
+  hd.line_currid = line_currid_;
+  hd.n_pts = (int)pts_last_.size();
+  hd.n_lines = (int)lines_last_.size();
+  hd.has_image = last_slot_ >= 0 ? 1 : 0;
+  hd.has_mask = (last_slot_ >= 0 && !slots_[last_slot_].mask.empty()) ? 1 : 0;
+  int npol = 0;
+  for (auto &m : pol_last_) npol += (int)m.size();
+  hd.n_pol_entries = npol;
+  size_t need = sizeof(hd) + (size_t)hd.n_pts * (sizeof(Pt) + sizeof(uint64_t)) +
+                (size_t)hd.n_lines * (sizeof(float4) + sizeof(uint64_t) + sizeof(int32_t)) +
+                (size_t)npol * (sizeof(int32_t) + sizeof(double)) + (hd.has_image ? (size_t)W_ * H_ : 0) +
+                (hd.has_mask ? (size_t)W_ * H_ : 0);
+  if (n_bytes) *n_bytes = need;
+  if (!buf || cap < need) return buf ? FE_OVERFLOW : FE_OK;
+  uint8_t *p = static_cast<uint8_t *>(buf);
+  auto put = [&](const void *src, size_t n) { std::memcpy(p, src, n); p += n; };
+  put(&hd, sizeof(hd));
+  put(pts_last_.data(), pts_last_.size() * sizeof(Pt));
+  put(ids_last_.data(), ids_last_.size() * sizeof(uint64_t));
+  put(lines_last_.data(), lines_last_.size() * sizeof(float4));
+  put(line_ids_last_.data(), line_ids_last_.size() * sizeof(uint64_t));
+  for (auto &m : pol_last_) { int32_t k = (int32_t)m.size(); put(&k, sizeof(k)); }
+  for (auto &m : pol_last_)
+    for (auto &kv : m) { int32_t k = kv.first; put(&k, sizeof(k)); put(&kv.second, sizeof(double)); }
+  if (hd.has_image) {
+    const DevImage &l0 = slots_[last_slot_].pyr.lvl[0];
+    FE_CUDA(cudaMemcpy2D(p, W_, l0.p, l0.pitch, W_, H_, cudaMemcpyDeviceToHost));
+    p += (size_t)W_ * H_;
+  }
+  if (hd.has_mask) put(slots_[last_slot_].mask.data(), (size_t)W_ * H_);
+  return FE_OK;
+}
+
+int FeContext::set_state(const void *buf, size_t n_bytes) {
+  FE_CUDA(cudaSetDevice(device_));
+  if (!buf || n_bytes < sizeof(StateHeader) || !queue_.empty()) return FE_BAD_ARG;
+  const uint8_t *p = static_cast<const uint8_t *>(buf);
+  StateHeader hd;
+  std::memcpy(&hd, p, sizeof(hd));
+  p += sizeof(hd);
+  if (hd.magic != 0x504c5657u || hd.w != W_ || hd.h != H_) return FE_BAD_ARG;
+  auto get = [&](void *dst, size_t n) { std::memcpy(dst, p, n); p += n; };
+  currid_ = hd.currid;
+  line_currid_ = hd.line_currid;
+  pts_last_.resize(hd.n_pts);
+  ids_last_.resize(hd.n_pts);
+  get(pts_last_.data(), (size_t)hd.n_pts * sizeof(Pt));
+  get(ids_last_.data(), (size_t)hd.n_pts * sizeof(uint64_t));
+  lines_last_.resize(hd.n_lines);
+  line_ids_last_.resize(hd.n_lines);
+  get(lines_last_.data(), (size_t)hd.n_lines * sizeof(float4));
+  get(line_ids_last_.data(), (size_t)hd.n_lines * sizeof(uint64_t));
+  std::vector<int32_t> sizes(hd.n_lines);
+  get(sizes.data(), (size_t)hd.n_lines * sizeof(int32_t));
+  pol_last_.assign(hd.n_lines, {});
+  for (int i = 0; i < hd.n_lines; i++)
+    for (int k = 0; k < sizes[i]; k++) {
+      int32_t key;
+      double val;
+      get(&key, sizeof(key));
+      get(&val, sizeof(val));
+      pol_last_[i][key] = val;
+    }
+  for (FrameSlot &s : slots_) s.busy = false;
+  last_slot_ = -1;
+  if (hd.has_image) {
+    FrameSlot &s = slots_[0];
+    s.busy = true;
+    FE_CUDA(cudaMemcpy2DAsync(s.raw.p, s.raw.pitch, p, W_, W_, H_, cudaMemcpyHostToDevice, s_img_));
+    p += (size_t)W_ * H_;
+    // the stored image is already equalised: rebuild the pyramid from it without a LUT
+    launch_eq_pyr1(s.raw, d_hist_, d_counters_, 0, s.pyr.lvl[0], s.pyr.n > 1 ? s.pyr.lvl[1] : DevImage(),
+                   cfg_.use_lines ? s.half : DevImage(), s_img_);
+    if (s.pyr.n > 2) launch_pyr_rest(s.pyr, d_counters_ + 1, s_img_);
+    FE_CUDA(cudaStreamSynchronize(s_img_));
+    if (hd.has_mask) {
+      s.mask.resize((size_t)W_ * H_);
+      get(s.mask.data(), (size_t)W_ * H_);
+    } else {
+      s.mask.clear();
+    }
+    last_slot_ = 0;
+  }
+  return FE_OK;
+}
+
+int FeContext::tap(int what, void *buf, size_t cap, size_t *n_bytes) {
+  FE_CUDA(cudaSetDevice(device_));
+  const int si = cur_slot_ >= 0 ? cur_slot_ : last_slot_;
+  auto copy_vec = [&](const void *src, size_t n) -> int {
+    if (n_bytes) *n_bytes = n;
+    if (!buf) return FE_OK;
+    if (cap < n) return FE_OVERFLOW;
+    std::memcpy(buf, src, n);
+    return FE_OK;
+  };
+  if (what == FE_TAP_FAST_LAST) return copy_vec(tap_fast_.data(), tap_fast_.size() * sizeof(int32_t));
+  if (what == FE_TAP_LK_LAST) return copy_vec(tap_lk_.data(), tap_lk_.size() * sizeof(float));
+  if (what == FE_TAP_SUBPIX_LAST) return copy_vec(tap_subpix_.data(), tap_subpix_.size() * sizeof(float));
+  if (what == FE_TAP_FLD_LAST) return copy_vec(tap_fld_.data(), tap_fld_.size() * sizeof(float));
+  if (si < 0) return FE_BAD_ARG;
+  FrameSlot &s = slots_[si];
+  FE_CUDA(cudaDeviceSynchronize());
+  if (what >= FE_TAP_PYR_LEVEL0 && what < FE_TAP_PYR_LEVEL0 + kMaxLevels) {
+    int l = what - FE_TAP_PYR_LEVEL0;
+    if (l >= s.pyr.n) return FE_BAD_ARG;
+    const DevImage &im = s.pyr.lvl[l];
+    size_t n = (size_t)im.w * im.h;
+    if (n_bytes) *n_bytes = n;
+    if (!buf) return FE_OK;
+    if (cap < n) return FE_OVERFLOW;
+    FE_CUDA(cudaMemcpy2D(buf, im.w, im.p, im.pitch, im.w, im.h, cudaMemcpyDeviceToHost));
+    return FE_OK;
+  }
+  if (what == FE_TAP_HALF && cfg_.use_lines) {
+    const DevImage &im = s.half;
+    size_t n = (size_t)im.w * im.h;
+    if (n_bytes) *n_bytes = n;
+    if (!buf) return FE_OK;
+    if (cap < n) return FE_OVERFLOW;
+    FE_CUDA(cudaMemcpy2D(buf, im.w, im.p, im.pitch, im.w, im.h, cudaMemcpyDeviceToHost));
+    return FE_OK;
+  }
+  return FE_BAD_ARG;
+}
+
+}  // namespace plviwo

@@ -1,0 +1,76 @@
+// Internal C++ interface between the host-side trackers and the sm_100a kernels (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace plviwo {
+
+struct DevImage {
+  uint8_t *p = nullptr;
+  int w = 0, h = 0, pitch = 0;
+};
+
+constexpr int kMaxLevels = 8;       // pyramid images (maxLevel + 1)
+constexpr int kFastBandRows = 16;   // rows per FAST CTA band
+constexpr int kMaxWin = 31;
+
+struct Pyramid {
+  DevImage lvl[kMaxLevels];
+  int n = 0;  // number of images actually built (maxLevel + 1, fewer if a level gets <= win)
+};
+
+// ---- image kernels (kernels_image.cu) -------------------------------------------------------------------
+// hist[256] must be zero on entry (the equalise kernel re-zeroes it when it is done with it).
+void launch_hist(const DevImage &src, unsigned *d_hist, cudaStream_t s);
+// LUT from hist (cv::equalizeHist), level 0 = lut[src] (or a plain copy when equalize == 0), level 1 = pyrDown,
+// half = exact 2x2 INTER_AREA of level 0 (may be null).  d_hist is cleared for the next frame by the last CTA.
+void launch_eq_pyr1(const DevImage &src, unsigned *d_hist, unsigned *d_counter, int equalize, const DevImage &l0,
+                    const DevImage &l1, const DevImage &half, cudaStream_t s);
+// levels 2..n-1 in ONE launch: level 2 by all CTAs, the remaining (tiny) levels by the last CTA to finish.
+void launch_pyr_rest(const Pyramid &pyr, unsigned *d_counter, cudaStream_t s);
+
+// ---- FAST (kernels_fast.cu) ------------------------------------------------------------------------------
+struct FastCell {
+  int x, y, w, h;  // ROI in level-0 pixels
+};
+// Output: d_total (1 counter, must be 0 on entry), per (cell, band) offset/count tables and packed keypoints
+// (x | y << 12 | score << 24, cell-local coordinates) written compactly at [offset, offset + count).
+void launch_fast(const DevImage &img, const FastCell *d_cells, int n_cells, int max_bands, int max_cell_w, int threshold,
+                 unsigned *d_total, int *d_band_off, int *d_band_cnt, unsigned *d_kps, int kps_cap, cudaStream_t s);
+
+// ---- cornerSubPix (kernels_track.cu) ----------------------------------------------------------------------
+void launch_corner_subpix(const DevImage &img, float2 *d_pts, int n, cudaStream_t s);
+
+// ---- pyramidal LK + undistort (kernels_track.cu) ----------------------------------------------------------
+struct LkParams {
+  int win;         // odd
+  int max_level;   // pyramid images - 1
+  int max_count;   // 30
+  float eps_sq;    // 0.01^2
+  float min_eig;   // 1e-4
+  double K[4], D[4];
+  int undistort;   // also write normalised coordinates of pts0 / pts1
+};
+void launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *d_pts0, float2 *d_pts1, uint8_t *d_status,
+               float2 *d_p0n, float2 *d_p1n, int n, const LkParams &prm, cudaStream_t s);
+void launch_undistort(const float2 *d_pts, float2 *d_out, int n, const double K[4], const double D[4], cudaStream_t s);
+
+// ---- lines (kernels_lines.cu) -------------------------------------------------------------------------------
+struct FldBuffers {
+  unsigned *edges = nullptr;      // bit-packed edge map, words_per_row * h
+  int words_per_row = 0;
+  int2 *chain_pts = nullptr;      // all chain points, chain after chain (capacity = w * h)
+  int *chain_off = nullptr;       // chain start offsets (capacity max_chains + 1)
+  int *n_chains = nullptr;        // [0] = number of chains kept, [1] = number of segments
+  int max_chains = 0;
+  float4 *segs = nullptr;         // per-chain segment slots: chain c owns [c * kSegsPerChain ...)
+  int *seg_cnt = nullptr;         // segments found in chain c
+  float4 *out = nullptr;          // compacted, ordered segments
+  int out_cap = 0;
+};
+constexpr int kSegsPerChainDiv = 21;  // a chain of n points yields at most n / 21 + 1 segments
+void launch_canny(const DevImage &half, float th_low, float th_high, FldBuffers &fb, cudaStream_t s);
+void launch_fld(const DevImage &half, int length_threshold, float distance_threshold, FldBuffers &fb, cudaStream_t s);
+void launch_unpack_edges(const FldBuffers &fb, int w, int h, uint8_t *d_out, cudaStream_t s);
+
+}  // namespace plviwo

@@ -1,0 +1,174 @@
+// Grid-bucketed FAST-9/16 with 3x3 non-max suppression, per cell ROI (sm_100a).
+//
+// Replaces cv::FAST(img(roi), pts, threshold, true) as called per valid grid cell at Grider_GRID.h:121-125.
+// Arithmetic per SURVEY.md Appendix A4: the ROI is treated as a whole image, so only 3 <= x < cols-3,
+// 3 <= y < rows-3 are tested (a 3 px band along every cell edge is never a corner), score = max over the 16
+// contiguous 9-arcs of min(d) / of -max(d) minus 1, strict 3x3 NMS against the 8 neighbours' scores, output in
+// row-major order — the order matters because the unstable std::sort at Grider_GRID.h:128 permutes ties.
+//
+// One CTA handles one band of kFastBandRows rows of one cell: the pixels are staged in shared memory with a
+// halo that is CLAMPED TO THE CELL (rows outside the cell simply do not exist), scores go to a second shared
+// plane, and survivors are emitted with an ordered block-wide compaction.  Bands of a cell reserve their slice
+// of the compact output with one atomic; the host (or the selection kernel) walks bands in order.
+#include "fe_kernels.h"
+
+namespace plviwo {
+
+constexpr int kFastThreads = 256;
+constexpr int kBH = kFastBandRows;
+
+__device__ __forceinline__ bool has_arc9(unsigned m16) {
+  // 9 contiguous set bits in a circular 16-bit mask
+  unsigned m = m16 | (m16 << 16);
+  unsigned r = m & (m >> 1);
+  r &= r >> 2;
+  r &= r >> 4;
+  r &= m >> 8;
+  return (r & 0xffffu) != 0;
+}
+
+__device__ __forceinline__ int fast_score(const uint8_t *__restrict__ px, int stride, int threshold) {
+  // ring offsets in OpenCV's order (Appendix A4)
+  const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+  const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+  int v = px[0];
+  int d[16];
+  unsigned bright = 0, dark = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    d[k] = v - (int)px[dy[k] * stride + dx[k]];
+    bright |= (d[k] > threshold ? 1u : 0u) << k;
+    dark |= (d[k] < -threshold ? 1u : 0u) << k;
+  }
+  if (!has_arc9(bright) && !has_arc9(dark)) return 0;
+  // a0 = max over arcs of min(d), b0 = min over arcs of max(d): sliding window of 9 over the circular ring
+  int mn2[16], mx2[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    mn2[k] = min(d[k], d[(k + 1) & 15]);
+    mx2[k] = max(d[k], d[(k + 1) & 15]);
+  }
+  int mn4[16], mx4[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    mn4[k] = min(mn2[k], mn2[(k + 2) & 15]);
+    mx4[k] = max(mx2[k], mx2[(k + 2) & 15]);
+  }
+  int a0 = -256, b0 = 256;
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
+    int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
+    a0 = max(a0, mn9);
+    b0 = min(b0, mx9);
+  }
+  return max(a0, -b0) - 1;
+}
+
+__global__ void __launch_bounds__(kFastThreads)
+    k_fast(const uint8_t *__restrict__ img, int pitch, const FastCell *__restrict__ cells, int max_bands, int threshold,
+           unsigned *__restrict__ total, int *__restrict__ band_off, int *__restrict__ band_cnt,
+           unsigned *__restrict__ kps, int kps_cap, int smem_w) {
+  extern __shared__ uint8_t smem[];
+  uint8_t *pix = smem;                               // (kBH + 8) rows x smem_w
+  uint8_t *sc = smem + (kBH + 8) * smem_w;           // (kBH + 2) rows x smem_w
+  __shared__ int warp_tot[kFastThreads / 32];
+  __shared__ int s_base;
+
+  const FastCell cell = cells[blockIdx.y];
+  const int band = blockIdx.x;
+  const int slot = blockIdx.y * max_bands + band;
+  const int y0 = band * kBH;
+  const int cw = cell.w, ch = cell.h;
+  if (y0 >= ch) {
+    if (threadIdx.x == 0) { band_off[slot] = 0; band_cnt[slot] = 0; }
+    return;
+  }
+  const int tid = threadIdx.x;
+  // ---- stage pixel rows y0-4 .. y0+kBH+3 (cell-local), clipped to the cell
+  const int py0 = y0 - 4;
+  for (int i = tid; i < (kBH + 8) * cw; i += kFastThreads) {
+    int r = i / cw, x = i - r * cw;
+    int y = py0 + r;
+    uint8_t v = 0;
+    if (y >= 0 && y < ch) v = img[(size_t)(cell.y + y) * pitch + cell.x + x];
+    pix[r * smem_w + x] = v;
+  }
+  __syncthreads();
+  // ---- scores for rows y0-1 .. y0+kBH
+  for (int i = tid; i < (kBH + 2) * cw; i += kFastThreads) {
+    int r = i / cw, x = i - r * cw;
+    int y = y0 - 1 + r;
+    int s = 0;
+    if (x >= 3 && x < cw - 3 && y >= 3 && y < ch - 3) s = fast_score(&pix[(r + 3) * smem_w + x], smem_w, threshold);
+    sc[r * smem_w + x] = (uint8_t)s;
+  }
+  __syncthreads();
+  // ---- NMS + ordered compaction: thread t owns positions [t*R, (t+1)*R) of the band in row-major order
+  const int rows = min(kBH, ch - y0);
+  const int npos = rows * cw;
+  const int R = (npos + kFastThreads - 1) / kFastThreads;
+  const int p0 = tid * R, p1 = min(p0 + R, npos);
+  int cnt = 0;
+  for (int p = p0; p < p1; p++) {
+    int r = p / cw, x = p - r * cw;
+    int s = sc[(r + 1) * smem_w + x];
+    if (s > 0 && x > 0 && x < cw - 1) {
+      const uint8_t *c = &sc[(r + 1) * smem_w + x];
+      bool keep = s > c[-1] && s > c[1] && s > c[-smem_w - 1] && s > c[-smem_w] && s > c[-smem_w + 1] &&
+                  s > c[smem_w - 1] && s > c[smem_w] && s > c[smem_w + 1];
+      cnt += keep ? 1 : 0;
+    }
+  }
+  // block exclusive scan of cnt
+  int v = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, d);
+    if ((tid & 31) >= d) v += t;
+  }
+  if ((tid & 31) == 31) warp_tot[tid >> 5] = v;
+  __syncthreads();
+  int base = 0;
+  for (int k = 0; k < (tid >> 5); k++) base += warp_tot[k];
+  int excl = base + v - cnt;
+  if (tid == kFastThreads - 1) {
+    int tot = base + v;
+    int off = tot ? (int)atomicAdd(total, (unsigned)tot) : 0;
+    s_base = off;
+    band_off[slot] = off;
+    band_cnt[slot] = tot;
+  }
+  __syncthreads();
+  int w = s_base + excl;
+  for (int p = p0; p < p1; p++) {
+    int r = p / cw, x = p - r * cw;
+    int s = sc[(r + 1) * smem_w + x];
+    if (s > 0 && x > 0 && x < cw - 1) {
+      const uint8_t *c = &sc[(r + 1) * smem_w + x];
+      bool keep = s > c[-1] && s > c[1] && s > c[-smem_w - 1] && s > c[-smem_w] && s > c[-smem_w + 1] &&
+                  s > c[smem_w - 1] && s > c[smem_w] && s > c[smem_w + 1];
+      if (keep) {
+        if (w < kps_cap) kps[w] = (unsigned)x | ((unsigned)(y0 + r) << 12) | ((unsigned)s << 24);
+        w++;
+      }
+    }
+  }
+}
+
+void launch_fast(const DevImage &img, const FastCell *d_cells, int n_cells, int max_bands, int max_cell_w, int threshold,
+                 unsigned *d_total, int *d_band_off, int *d_band_cnt, unsigned *d_kps, int kps_cap, cudaStream_t s) {
+  if (n_cells <= 0) return;
+  int smem_w = (max_cell_w + 15) & ~15;
+  size_t smem = (size_t)(2 * kBH + 10) * smem_w;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  dim3 grid(max_bands, n_cells);
+  k_fast<<<grid, kFastThreads, smem, s>>>(img.p, img.pitch, d_cells, max_bands, threshold, d_total, d_band_off, d_band_cnt,
+                                          d_kps, kps_cap, smem_w);
+}
+
+}  // namespace plviwo

@@ -1,0 +1,385 @@
+// Per-feature kernels (sm_100a): sub-pixel corner refinement, pyramidal Lucas-Kanade with on-the-fly Scharr
+// derivatives, and radtan undistortion.  One warp per feature; compiled with --fmad=false so that float
+// expressions round exactly where the reference's SSE build rounds.
+//
+// Reference ops replaced:
+//   cv::cornerSubPix(img, pts, (5,5), (-1,-1), {COUNT+EPS, 20, 0.001})             Grider_GRID.h:163-174
+//   cv::calcOpticalFlowPyrLK(.., win, maxLevel, {COUNT|EPS, 30, 0.01}, USE_INITIAL_FLOW)  TrackKLT.cpp:855-858
+//   CamRadtan::undistort_f -> cv::undistortPoints (one Mat per point)               cam/CamRadtan.h:99-120
+#include "fe_kernels.h"
+
+#include <cfloat>
+#include <cmath>
+
+namespace plviwo {
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  // BORDER_REFLECT_101; the final clamp only guards reads that the algorithm discards (far-outside halo)
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return min(max(i, 0), n - 1);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// ============================================================================================ cornerSubPix
+// win = (5,5): 11 x 11 window, 13 x 13 bilinear patch (cv::getRectSubPix, BORDER_REPLICATE at the image edge),
+// Gaussian-like mask exp(-x^2/25) exp(-y^2/25), double-precision normal equations, <= 20 iterations, eps 1e-3.
+constexpr int kSpWin = 5;
+constexpr int kSpW = 2 * kSpWin + 1;   // 11
+constexpr int kSpP = kSpW + 2;         // 13
+constexpr int kSpWarps = 4;
+
+__constant__ float c_subpix_mask[kSpW * kSpW];
+static bool g_subpix_mask_ready[64] = {false};
+
+__global__ void __launch_bounds__(kSpWarps * 32)
+    k_corner_subpix(const uint8_t *__restrict__ img, int w, int h, int pitch, float2 *__restrict__ pts, int n) {
+  __shared__ float patch_s[kSpWarps][kSpP * kSpP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pi = blockIdx.x * kSpWarps + warp;
+  if (pi >= n) return;
+  float *patch = patch_s[warp];
+  const float2 cT = pts[pi];
+  float2 cI = cT;
+  const double eps = 0.001 * 0.001;
+  int iter = 0;
+  double err = 0;
+  do {
+    // getRectSubPix(src, 13x13, cI): top-left = cI - 6, bilinear weights in float, replicate outside
+    float cx = cI.x - (kSpP - 1) * 0.5f, cy = cI.y - (kSpP - 1) * 0.5f;
+    int ipx = __float2int_rd(cx), ipy = __float2int_rd(cy);
+    float a = cx - ipx, b = cy - ipy;
+    float a11 = (1.f - a) * (1.f - b), a12 = a * (1.f - b), a21 = (1.f - a) * b, a22 = a * b;
+    for (int i = lane; i < kSpP * kSpP; i += 32) {
+      int r = i / kSpP, c = i - r * kSpP;
+      int x0 = min(max(ipx + c, 0), w - 1), x1 = min(max(ipx + c + 1, 0), w - 1);
+      int y0 = min(max(ipy + r, 0), h - 1), y1 = min(max(ipy + r + 1, 0), h - 1);
+      const uint8_t *r0 = img + (size_t)y0 * pitch, *r1 = img + (size_t)y1 * pitch;
+      patch[i] = r0[x0] * a11 + r0[x1] * a12 + r1[x0] * a21 + r1[x1] * a22;
+    }
+    __syncwarp();
+    double sa = 0, sb = 0, sc = 0, sbb1 = 0, sbb2 = 0;
+    for (int k = lane; k < kSpW * kSpW; k += 32) {
+      int i = k / kSpW, j = k - i * kSpW;
+      const float *sp = patch + (i + 1) * kSpP + (j + 1);
+      double m = c_subpix_mask[k];
+      double tgx = sp[1] - sp[-1];
+      double tgy = sp[kSpP] - sp[-kSpP];
+      double gxx = tgx * tgx * m, gxy = tgx * tgy * m, gyy = tgy * tgy * m;
+      double px = j - kSpWin, py = i - kSpWin;
+      sa += gxx; sb += gxy; sc += gyy;
+      sbb1 += gxx * px + gxy * py;
+      sbb2 += gxy * px + gyy * py;
+    }
+    sa = warp_sum(sa); sb = warp_sum(sb); sc = warp_sum(sc); sbb1 = warp_sum(sbb1); sbb2 = warp_sum(sbb2);
+    __syncwarp();
+    double det = sa * sc - sb * sb;
+    if (fabs(det) <= DBL_EPSILON * DBL_EPSILON) break;
+    double scale = 1.0 / det;
+    float2 cI2;
+    cI2.x = (float)(cI.x + sc * scale * sbb1 - sb * scale * sbb2);
+    cI2.y = (float)(cI.y - sb * scale * sbb1 + sa * scale * sbb2);
+    err = (double)((cI2.x - cI.x) * (cI2.x - cI.x) + (cI2.y - cI.y) * (cI2.y - cI.y));
+    cI = cI2;
+    if (cI.x < 0 || cI.x >= w || cI.y < 0 || cI.y >= h) break;
+  } while (++iter < 20 && err > eps);
+  if (fabsf(cI.x - cT.x) > kSpWin || fabsf(cI.y - cT.y) > kSpWin) cI = cT;
+  if (lane == 0) pts[pi] = cI;
+}
+
+void launch_corner_subpix(const DevImage &img, float2 *d_pts, int n, cudaStream_t s) {
+  if (n <= 0) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!g_subpix_mask_ready[dev & 63]) {
+    float m[kSpW * kSpW];
+    for (int i = 0; i < kSpW; i++) {
+      float y = (float)(i - kSpWin) / kSpWin;
+      float vy = std::exp(-y * y);
+      for (int j = 0; j < kSpW; j++) {
+        float x = (float)(j - kSpWin) / kSpWin;
+        m[i * kSpW + j] = (float)(vy * std::exp(-x * x));
+      }
+    }
+    cudaMemcpyToSymbol(c_subpix_mask, m, sizeof(m));
+    g_subpix_mask_ready[dev & 63] = true;
+  }
+  k_corner_subpix<<<(n + kSpWarps - 1) / kSpWarps, kSpWarps * 32, 0, s>>>(img.p, img.w, img.h, img.pitch, d_pts, n);
+}
+
+// ============================================================================================== undistort
+// cv::undistortPoints with a 4-coefficient radtan model: 5 fixed-point iterations in double (Appendix A6).
+__device__ __forceinline__ float2 undistort_radtan(float2 uv, const double *K, const double *D) {
+  double x0 = ((double)uv.x - K[2]) / K[0], y0 = ((double)uv.y - K[3]) / K[1];
+  double x = x0, y = y0;
+  const double k1 = D[0], k2 = D[1], p1 = D[2], p2 = D[3];
+#pragma unroll 1
+  for (int j = 0; j < 5; j++) {
+    double r2 = x * x + y * y;
+    double icdist = 1.0 / (1.0 + (k2 * r2 + k1) * r2);
+    double dx = 2 * p1 * x * y + p2 * (r2 + 2 * x * x);
+    double dy = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y;
+    x = (x0 - dx) * icdist;
+    y = (y0 - dy) * icdist;
+  }
+  return make_float2((float)x, (float)y);
+}
+
+struct CalibArgs {
+  double K[4], D[4];
+};
+
+__global__ void k_undistort(const float2 *__restrict__ pts, float2 *__restrict__ out, int n, CalibArgs c) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = undistort_radtan(pts[i], c.K, c.D);
+}
+
+void launch_undistort(const float2 *d_pts, float2 *d_out, int n, const double K[4], const double D[4], cudaStream_t s) {
+  if (n <= 0) return;
+  CalibArgs c;
+  for (int i = 0; i < 4; i++) { c.K[i] = K[i]; c.D[i] = D[i]; }
+  k_undistort<<<(n + 127) / 128, 128, 0, s>>>(d_pts, d_out, n, c);
+}
+
+// ===================================================================================================== LK
+// One warp per feature, every pyramid level in ONE launch.  Per level the warp
+//   1. loads the (win+3)^2 neighbourhood of the previous image (REFLECT_101 like OpenCV's padded pyramid),
+//   2. forms Scharr derivatives at the (win+1)^2 integer positions on the fly (zero outside the frame, exactly
+//      what the reference's zero-padded derivative planes hold),
+//   3. builds the fixed-point (W_BITS = 14) bilinear patches I, Ix, Iy (int16) and the 2x2 normal matrix,
+//   4. iterates <= 30 times: bilinear J patch, mismatch vector b (shuffle-reduced), 2x2 solve.
+// Nothing but the two 8-bit pyramids is read from HBM: no derivative planes, no padded copies.
+constexpr int kLkWarps = 4;
+constexpr int kLkMaxPatch = (kMaxWin + 3) * (kMaxWin + 3);
+
+struct LkArgs {
+  const uint8_t *p0[kMaxLevels];
+  const uint8_t *p1[kMaxLevels];
+  int w[kMaxLevels], h[kMaxLevels], pitch0[kMaxLevels], pitch1[kMaxLevels];
+  int win, max_level, max_count, undistort;
+  float eps_sq, min_eig;
+  CalibArgs calib;
+};
+
+__global__ void __launch_bounds__(kLkWarps * 32)
+    k_lk(LkArgs a, const float2 *__restrict__ pts0, float2 *__restrict__ pts1, uint8_t *__restrict__ status,
+         float2 *__restrict__ p0n, float2 *__restrict__ p1n, int n) {
+  extern __shared__ __align__(16) uint8_t lk_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pi = blockIdx.x * kLkWarps + warp;
+  if (pi >= n) return;
+  const int win = a.win;
+  const int np = win + 3;        // raw patch side
+  const int nd = win + 1;        // derivative grid side
+  const int nw = win * win;
+  // per-warp shared layout: raw[np*np] u8 | dx[nd*nd] s16 | dy[nd*nd] s16 | Iw[nw] s16 | Ix[nw] s16 | Iy[nw] s16
+  const int raw_bytes = (np * np + 15) & ~15;
+  const int d_bytes = (nd * nd * 2 + 15) & ~15;
+  const int w_bytes = (nw * 2 + 15) & ~15;
+  const int per_warp = raw_bytes + 2 * d_bytes + 3 * w_bytes;
+  uint8_t *base = lk_smem + warp * per_warp;
+  uint8_t *raw = base;
+  short *ddx = reinterpret_cast<short *>(base + raw_bytes);
+  short *ddy = reinterpret_cast<short *>(base + raw_bytes + d_bytes);
+  short *Iw = reinterpret_cast<short *>(base + raw_bytes + 2 * d_bytes);
+  short *Ixw = reinterpret_cast<short *>(base + raw_bytes + 2 * d_bytes + w_bytes);
+  short *Iyw = reinterpret_cast<short *>(base + raw_bytes + 2 * d_bytes + 2 * w_bytes);
+
+  const float2 prev_in = pts0[pi];
+  float2 next = pts1[pi];   // OPTFLOW_USE_INITIAL_FLOW
+  bool ok = true;
+  const float half = (win - 1) * 0.5f;
+  const float FLT_SCALE = 1.f / (1 << 20);
+
+  for (int level = a.max_level; level >= 0; level--) {
+    const int cols = a.w[level], rows = a.h[level];
+    const float lscale = 1.f / (float)(1 << level);
+    float2 prevPt = make_float2(prev_in.x * lscale, prev_in.y * lscale);
+    if (level == a.max_level) {
+      next.x = next.x * lscale;
+      next.y = next.y * lscale;
+    } else {
+      next.x = next.x * 2.f;
+      next.y = next.y * 2.f;
+    }
+    prevPt.x -= half;
+    prevPt.y -= half;
+    const int ipx = __float2int_rd(prevPt.x), ipy = __float2int_rd(prevPt.y);
+    if (ipx < -win || ipx >= cols || ipy < -win || ipy >= rows) {
+      if (level == 0) ok = false;
+      continue;
+    }
+    float fa = prevPt.x - ipx, fb = prevPt.y - ipy;
+    int iw00 = __float2int_rn((1.f - fa) * (1.f - fb) * 16384.f);
+    int iw01 = __float2int_rn(fa * (1.f - fb) * 16384.f);
+    int iw10 = __float2int_rn((1.f - fa) * fb * 16384.f);
+    int iw11 = 16384 - iw00 - iw01 - iw10;
+
+    // 1. raw neighbourhood, origin (ipx - 1, ipy - 1)
+    const uint8_t *I = a.p0[level];
+    const int pitchI = a.pitch0[level];
+    for (int i = lane; i < np * np; i += 32) {
+      int r = i / np, c = i - r * np;
+      int x = reflect101(ipx - 1 + c, cols), y = reflect101(ipy - 1 + r, rows);
+      raw[i] = I[(size_t)y * pitchI + x];
+    }
+    __syncwarp();
+    // 2. Scharr derivatives at (ipx + c, ipy + r), c, r in [0, win]; zero outside the frame
+    for (int i = lane; i < nd * nd; i += 32) {
+      int r = i / nd, c = i - r * nd;
+      int gx = ipx + c, gy = ipy + r;
+      int vx = 0, vy = 0;
+      if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
+        const uint8_t *q = raw + (r + 1) * np + (c + 1);
+        int tl = q[-np - 1], tc = q[-np], tr = q[-np + 1];
+        int ml = q[-1], mr = q[1];
+        int bl = q[np - 1], bc = q[np], br = q[np + 1];
+        vx = 3 * (tr + br) + 10 * mr - 3 * (tl + bl) - 10 * ml;
+        vy = 3 * (bl + br) + 10 * bc - 3 * (tl + tr) - 10 * tc;
+      }
+      ddx[i] = (short)vx;
+      ddy[i] = (short)vy;
+    }
+    __syncwarp();
+    // 3. interpolated patches + normal matrix
+    float A11 = 0, A12 = 0, A22 = 0;
+    for (int i = lane; i < nw; i += 32) {
+      int y = i / win, x = i - y * win;
+      const uint8_t *q = raw + (y + 1) * np + (x + 1);
+      int ival = (q[0] * iw00 + q[1] * iw01 + q[np] * iw10 + q[np + 1] * iw11 + (1 << 8)) >> 9;
+      int di = y * nd + x;
+      int ixval = (ddx[di] * iw00 + ddx[di + 1] * iw01 + ddx[di + nd] * iw10 + ddx[di + nd + 1] * iw11 + (1 << 13)) >> 14;
+      int iyval = (ddy[di] * iw00 + ddy[di + 1] * iw01 + ddy[di + nd] * iw10 + ddy[di + nd + 1] * iw11 + (1 << 13)) >> 14;
+      Iw[i] = (short)ival;
+      Ixw[i] = (short)ixval;
+      Iyw[i] = (short)iyval;
+      A11 += (float)(ixval * ixval);
+      A12 += (float)(ixval * iyval);
+      A22 += (float)(iyval * iyval);
+    }
+    A11 = warp_sum(A11) * FLT_SCALE;
+    A12 = warp_sum(A12) * FLT_SCALE;
+    A22 = warp_sum(A22) * FLT_SCALE;
+    __syncwarp();
+    float Dt = A11 * A22 - A12 * A12;
+    float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+    if (minEig < a.min_eig || Dt < FLT_EPSILON) {
+      if (level == 0) ok = false;
+      continue;
+    }
+    Dt = 1.f / Dt;
+    float2 result = next;   // nextPts[ptidx] as stored by OpenCV; only rewritten after an update step
+    next.x -= half;
+    next.y -= half;
+    float2 prevDelta = make_float2(0.f, 0.f);
+    const uint8_t *J = a.p1[level];
+    const int pitchJ = a.pitch1[level];
+    for (int j = 0; j < a.max_count; j++) {
+      const int inx = __float2int_rd(next.x), iny = __float2int_rd(next.y);
+      if (inx < -win || inx >= cols || iny < -win || iny >= rows) {
+        if (level == 0) ok = false;
+        break;
+      }
+      float ja = next.x - inx, jb = next.y - iny;
+      int jw00 = __float2int_rn((1.f - ja) * (1.f - jb) * 16384.f);
+      int jw01 = __float2int_rn(ja * (1.f - jb) * 16384.f);
+      int jw10 = __float2int_rn((1.f - ja) * jb * 16384.f);
+      int jw11 = 16384 - jw00 - jw01 - jw10;
+      float b1 = 0, b2 = 0;
+      const bool inside = inx >= 0 && iny >= 0 && inx + win < cols && iny + win < rows;
+      if (inside) {
+        const uint8_t *Jp = J + (size_t)iny * pitchJ + inx;
+        for (int i = lane; i < nw; i += 32) {
+          int y = i / win, x = i - y * win;
+          const uint8_t *q = Jp + (size_t)y * pitchJ + x;
+          int jv = (q[0] * jw00 + q[1] * jw01 + q[pitchJ] * jw10 + q[pitchJ + 1] * jw11 + (1 << 8)) >> 9;
+          int diff = jv - Iw[i];
+          b1 += (float)(diff * Ixw[i]);
+          b2 += (float)(diff * Iyw[i]);
+        }
+      } else {
+        for (int i = lane; i < nw; i += 32) {
+          int y = i / win, x = i - y * win;
+          int x0 = reflect101(inx + x, cols), x1 = reflect101(inx + x + 1, cols);
+          const uint8_t *r0 = J + (size_t)reflect101(iny + y, rows) * pitchJ;
+          const uint8_t *r1 = J + (size_t)reflect101(iny + y + 1, rows) * pitchJ;
+          int jv = (r0[x0] * jw00 + r0[x1] * jw01 + r1[x0] * jw10 + r1[x1] * jw11 + (1 << 8)) >> 9;
+          int diff = jv - Iw[i];
+          b1 += (float)(diff * Ixw[i]);
+          b2 += (float)(diff * Iyw[i]);
+        }
+      }
+      b1 = warp_sum(b1) * FLT_SCALE;
+      b2 = warp_sum(b2) * FLT_SCALE;
+      float2 delta = make_float2((A12 * b2 - A22 * b1) * Dt, (A12 * b1 - A11 * b2) * Dt);
+      next.x += delta.x;
+      next.y += delta.y;
+      result = make_float2(next.x + half, next.y + half);
+      if ((double)delta.x * (double)delta.x + (double)delta.y * (double)delta.y <= (double)a.eps_sq) break;
+      if (j > 0 && fabs((double)(delta.x + prevDelta.x)) < 0.01 && fabs((double)(delta.y + prevDelta.y)) < 0.01) {
+        result.x -= delta.x * 0.5f;
+        result.y -= delta.y * 0.5f;
+        break;
+      }
+      prevDelta = delta;
+    }
+    next = result;
+    if (level == 0 && ok) {
+      // the reference asks for the error vector, so OpenCV re-checks the final position (lkpyramid.cpp err block)
+      int fx = __float2int_rd(next.x - half), fy = __float2int_rd(next.y - half);
+      if (fx < -win || fx >= cols || fy < -win || fy >= rows) ok = false;
+    }
+  }
+  if (lane == 0) {
+    pts1[pi] = next;
+    status[pi] = ok ? 1 : 0;
+  }
+  if (a.undistort) {
+    if (lane == 0) p0n[pi] = undistort_radtan(prev_in, a.calib.K, a.calib.D);
+    if (lane == 1) p1n[pi] = undistort_radtan(next, a.calib.K, a.calib.D);
+  }
+}
+
+void launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *d_pts0, float2 *d_pts1, uint8_t *d_status,
+               float2 *d_p0n, float2 *d_p1n, int n, const LkParams &prm, cudaStream_t s) {
+  if (n <= 0) return;
+  LkArgs a;
+  int levels = prm.max_level + 1;
+  if (levels > prev.n) levels = prev.n;
+  for (int l = 0; l < levels; l++) {
+    a.p0[l] = prev.lvl[l].p;
+    a.p1[l] = next.lvl[l].p;
+    a.w[l] = prev.lvl[l].w;
+    a.h[l] = prev.lvl[l].h;
+    a.pitch0[l] = prev.lvl[l].pitch;
+    a.pitch1[l] = next.lvl[l].pitch;
+  }
+  a.win = prm.win;
+  a.max_level = levels - 1;
+  a.max_count = prm.max_count;
+  a.eps_sq = prm.eps_sq;
+  a.min_eig = prm.min_eig;
+  a.undistort = prm.undistort;
+  for (int i = 0; i < 4; i++) { a.calib.K[i] = prm.K[i]; a.calib.D[i] = prm.D[i]; }
+  const int win = prm.win, np = win + 3, nd = win + 1, nw = win * win;
+  const int per_warp = ((np * np + 15) & ~15) + 2 * ((nd * nd * 2 + 15) & ~15) + 3 * ((nw * 2 + 15) & ~15);
+  size_t smem = (size_t)per_warp * kLkWarps;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(k_lk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  k_lk<<<(n + kLkWarps - 1) / kLkWarps, kLkWarps * 32, smem, s>>>(a, d_pts0, d_pts1, d_status, d_p0n, d_p1n, n);
+}
+
+}  // namespace plviwo
