@@ -127,6 +127,7 @@ typedef struct FeStageTimes {
   uint64_t launches[16];
   uint64_t frames;
   uint64_t kernel_launches_total;
+  uint64_t h2d_bytes, d2h_bytes;   /* bytes moved by the handle's own cudaMemcpyAsync calls */
 } FeStageTimes;
 
 /* ---- lifetime ----------------------------------------------------------------------------------------- */

@@ -66,7 +66,7 @@ class FeFrameInfo(C.Structure):
 
 class FeStageTimes(C.Structure):
     _fields_ = [("ms", C.c_double * 16), ("launches", C.c_uint64 * 16), ("frames", C.c_uint64),
-                ("kernel_launches_total", C.c_uint64)]
+                ("kernel_launches_total", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 POINT_ROW_DTYPE = np.dtype([("id", "<u8"), ("u", "<f4"), ("v", "<f4"), ("un", "<f4"), ("vn", "<f4")])
@@ -384,7 +384,73 @@ class FrontEnd:
         t = FeStageTimes()
         _check(self._lib.plviwo_fe_get_stage_times(self._h, C.byref(t), 1 if reset else 0), self._h)
         return {"ms": {s: t.ms[i] for i, s in enumerate(STAGES)}, "launches": {s: int(t.launches[i]) for i, s in enumerate(STAGES)},
-                "frames": int(t.frames), "kernel_launches_total": int(t.kernel_launches_total)}
+                "frames": int(t.frames), "kernel_launches_total": int(t.kernel_launches_total),
+                "h2d_bytes": int(t.h2d_bytes), "d2h_bytes": int(t.d2h_bytes)}
+
+
+# ------------------------------------------------------------------------------------------- tracker state blob
+_STATE_MAGIC = 0x504C5657
+_STATE_HDR = np.dtype([("magic", "<u4"), ("version", "<u4"), ("w", "<i4"), ("h", "<i4"), ("currid", "<u8"),
+                       ("line_currid", "<u8"), ("n_pts", "<i4"), ("n_lines", "<i4"), ("has_image", "<i4"),
+                       ("has_mask", "<i4"), ("n_pol", "<i4"), ("reserved", "<i4")])
+
+
+def pack_state(width, height, currid, pts_last, ids_last, img_last_eq=None, mask_last=None, line_currid=1,
+               lines_last=None, line_ids_last=None, pol_last=None) -> bytes:
+    """Serialises tracker state in the layout plviwo_fe_set_state expects (teacher forcing / resume):
+    TrackBase members pts_last / ids_last / currid / img_last (equalised) / img_mask_last and TrackLSD members
+    lines_last / ids_last / point_on_lines_last / currid."""
+    pts = np.ascontiguousarray(pts_last, np.float32).reshape(-1, 2)
+    ids = np.ascontiguousarray(ids_last, np.uint64).reshape(-1)
+    lines = np.zeros((0, 4), np.float32) if lines_last is None else np.ascontiguousarray(lines_last, np.float32).reshape(-1, 4)
+    lids = np.zeros((0,), np.uint64) if line_ids_last is None else np.ascontiguousarray(line_ids_last, np.uint64).reshape(-1)
+    pol = [] if pol_last is None else pol_last
+    hdr = np.zeros((), _STATE_HDR)
+    hdr["magic"], hdr["version"], hdr["w"], hdr["h"] = _STATE_MAGIC, 1, width, height
+    hdr["currid"], hdr["line_currid"] = currid, line_currid
+    hdr["n_pts"], hdr["n_lines"] = len(pts), len(lines)
+    hdr["has_image"] = 0 if img_last_eq is None else 1
+    hdr["has_mask"] = 0 if (mask_last is None or img_last_eq is None or not np.any(mask_last)) else 1
+    hdr["n_pol"] = sum(len(m) for m in pol)
+    parts = [hdr.tobytes(), pts.tobytes(), ids.tobytes(), lines.tobytes(), lids.tobytes(),
+             np.array([len(m) for m in pol], np.int32).tobytes()]
+    ent = np.zeros((int(hdr["n_pol"]),), np.dtype([("k", "<i4"), ("v", "<f8")], align=False))
+    i = 0
+    for m in pol:
+        for k in sorted(m):
+            ent[i] = (k, m[k])
+            i += 1
+    parts.append(ent.tobytes())
+    if img_last_eq is not None:
+        parts.append(np.ascontiguousarray(img_last_eq, np.uint8).tobytes())
+        if hdr["has_mask"]:
+            parts.append(np.ascontiguousarray(mask_last, np.uint8).tobytes())
+    return b"".join(parts)
+
+
+def unpack_state(blob: bytes) -> Dict[str, object]:
+    hdr = np.frombuffer(blob, _STATE_HDR, 1)[0]
+    o = _STATE_HDR.itemsize
+    n, m = int(hdr["n_pts"]), int(hdr["n_lines"])
+    pts = np.frombuffer(blob, np.float32, 2 * n, o).reshape(-1, 2); o += 8 * n
+    ids = np.frombuffer(blob, np.uint64, n, o); o += 8 * n
+    lines = np.frombuffer(blob, np.float32, 4 * m, o).reshape(-1, 4); o += 16 * m
+    lids = np.frombuffer(blob, np.uint64, m, o); o += 8 * m
+    sizes = np.frombuffer(blob, np.int32, m, o); o += 4 * m
+    ent = np.frombuffer(blob, np.dtype([("k", "<i4"), ("v", "<f8")], align=False), int(hdr["n_pol"]), o)
+    o += 12 * int(hdr["n_pol"])
+    pol, e = [], 0
+    for sz in sizes:
+        pol.append({int(ent[e + j]["k"]): float(ent[e + j]["v"]) for j in range(sz)})
+        e += sz
+    w, h = int(hdr["w"]), int(hdr["h"])
+    img = mask = None
+    if hdr["has_image"]:
+        img = np.frombuffer(blob, np.uint8, w * h, o).reshape(h, w); o += w * h
+        if hdr["has_mask"]:
+            mask = np.frombuffer(blob, np.uint8, w * h, o).reshape(h, w)
+    return dict(currid=int(hdr["currid"]), line_currid=int(hdr["line_currid"]), pts_last=pts, ids_last=ids, lines_last=lines,
+                line_ids_last=lids, pol_last=pol, img_last=img, mask_last=mask)
 
 
 # ------------------------------------------------------------------------------------------- stand-alone ops

@@ -24,6 +24,15 @@ namespace plviwo {
 
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
+// cudaMemcpyAsync with byte accounting (FeStageTimes::h2d_bytes / d2h_bytes)
+#define FE_COPY(dst, src, bytes, kind, stream)                                   \
+  do {                                                                           \
+    size_t b__ = (bytes);                                                        \
+    if ((kind) == cudaMemcpyHostToDevice) times.h2d_bytes += b__;                \
+    if ((kind) == cudaMemcpyDeviceToHost) times.d2h_bytes += b__;                \
+    FE_CUDA(cudaMemcpyAsync((dst), (src), b__, (kind), (stream)));               \
+  } while (0)
+
 FeContext::FeContext(const FeConfig &cfg, int device) : cfg_(cfg), device_(device), W_(cfg.width), H_(cfg.height) {
   currid_ = 4 * (uint64_t)cfg.numaruco + 1;  // TrackBase.cpp:34
   line_currid_ = 1;                          // TrackLSD.cpp:32
@@ -211,8 +220,8 @@ int FeContext::enqueue_frame_independent(FrameSlot &s) {
     launch_fld(s.half, cfg_.fld_length_threshold, cfg_.fld_distance_threshold, s.fld, s_line_);
     times.kernel_launches_total += 4;
     if (tm) cudaEventRecord(s.ev_t[7], s_line_);
-    FE_CUDA(cudaMemcpyAsync(s.h_fld_counts, s.fld.n_chains, 2 * sizeof(int), cudaMemcpyDeviceToHost, s_line_));
-    FE_CUDA(cudaMemcpyAsync(s.h_segs, s.fld.out, 1024 * sizeof(float4), cudaMemcpyDeviceToHost, s_line_));
+    FE_COPY(s.h_fld_counts, s.fld.n_chains, 2 * sizeof(int), cudaMemcpyDeviceToHost, s_line_);
+    FE_COPY(s.h_segs, s.fld.out, 1024 * sizeof(float4), cudaMemcpyDeviceToHost, s_line_);
     FE_CUDA(cudaEventRecord(s.ev_lines, s_line_));
   }
   FE_CUDA(cudaGetLastError());
@@ -255,6 +264,7 @@ int FeContext::submit(double t, const uint8_t *image, int stride, bool on_device
       sstride = W_;
     }
     FE_CUDA(cudaMemcpy2DAsync(s.raw.p, s.raw.pitch, src, sstride, W_, H_, cudaMemcpyHostToDevice, s_img_));
+    times.h2d_bytes += (size_t)W_ * H_;
   }
   if (timing) cudaEventRecord(s.ev_t[1], s_img_);
   int rc = enqueue_frame_independent(s);
@@ -491,7 +501,7 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
     }
     if (ncell > 0) {
       const int nb = (csy + kFastBandRows - 1) / kFastBandRows;
-      FE_CUDA(cudaMemcpyAsync(d_cells_, h_cells_, (size_t)ncell * sizeof(FastCell), cudaMemcpyHostToDevice, s_pt_));
+      FE_COPY(d_cells_, h_cells_, (size_t)ncell * sizeof(FastCell), cudaMemcpyHostToDevice, s_pt_);
       FE_CUDA(cudaMemsetAsync(d_fast_total_, 0, sizeof(unsigned), s_pt_));
       if (timing) cudaEventRecord(ev_pt_[0], s_pt_);
       launch_fast(img.pyr.lvl[0], d_cells_, ncell, nb, csx, cfg_.fast_threshold, d_fast_total_, d_band_off_, d_band_cnt_,
@@ -500,15 +510,15 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
       if (timing) cudaEventRecord(ev_pt_[1], s_pt_);
       const int ntab = ncell * nb;
       const int spec = 8192;  // speculative first chunk of the compact keypoint list
-      FE_CUDA(cudaMemcpyAsync(h_band_, d_fast_total_, sizeof(unsigned), cudaMemcpyDeviceToHost, s_pt_));
-      FE_CUDA(cudaMemcpyAsync(h_band_ + 1, d_band_off_, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, s_pt_));
-      FE_CUDA(cudaMemcpyAsync(h_band_ + 1 + ntab, d_band_cnt_, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, s_pt_));
-      FE_CUDA(cudaMemcpyAsync(h_kps_, d_kps_, (size_t)std::min(spec, kps_cap_) * sizeof(unsigned), cudaMemcpyDeviceToHost, s_pt_));
+      FE_COPY(h_band_, d_fast_total_, sizeof(unsigned), cudaMemcpyDeviceToHost, s_pt_);
+      FE_COPY(h_band_ + 1, d_band_off_, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, s_pt_);
+      FE_COPY(h_band_ + 1 + ntab, d_band_cnt_, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, s_pt_);
+      FE_COPY(h_kps_, d_kps_, (size_t)std::min(spec, kps_cap_) * sizeof(unsigned), cudaMemcpyDeviceToHost, s_pt_);
       FE_CUDA(cudaStreamSynchronize(s_pt_));
       if (timing) acc_time(times, FE_STAGE_FAST, ev_pt_[0], ev_pt_[1]);
       int total = std::min(h_band_[0], kps_cap_);
       if (total > spec) {
-        FE_CUDA(cudaMemcpyAsync(h_kps_ + spec, d_kps_ + spec, (size_t)(total - spec) * sizeof(unsigned), cudaMemcpyDeviceToHost, s_pt_));
+        FE_COPY(h_kps_ + spec, d_kps_ + spec, (size_t)(total - spec) * sizeof(unsigned), cudaMemcpyDeviceToHost, s_pt_);
         FE_CUDA(cudaStreamSynchronize(s_pt_));
       }
       // mask0_updated as a bit mask: caller mask > 127 or inside a (2d+1)^2 square of a kept point (:457-461)
@@ -563,12 +573,12 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
       int ns = std::min((int)selected.size(), max_pts_);
       if (ns > 0) {
         for (int i = 0; i < ns; i++) h_pts0_[i] = make_float2(selected[i].x, selected[i].y);
-        FE_CUDA(cudaMemcpyAsync(d_pts0_, h_pts0_, (size_t)ns * sizeof(float2), cudaMemcpyHostToDevice, s_pt_));
+        FE_COPY(d_pts0_, h_pts0_, (size_t)ns * sizeof(float2), cudaMemcpyHostToDevice, s_pt_);
         if (timing) cudaEventRecord(ev_pt_[2], s_pt_);
         launch_corner_subpix(img.pyr.lvl[0], d_pts0_, ns, s_pt_);
         times.kernel_launches_total++;
         if (timing) cudaEventRecord(ev_pt_[3], s_pt_);
-        FE_CUDA(cudaMemcpyAsync(h_pts1_, d_pts0_, (size_t)ns * sizeof(float2), cudaMemcpyDeviceToHost, s_pt_));
+        FE_COPY(h_pts1_, d_pts0_, (size_t)ns * sizeof(float2), cudaMemcpyDeviceToHost, s_pt_);
         FE_CUDA(cudaStreamSynchronize(s_pt_));
         if (timing) acc_time(times, FE_STAGE_SUBPIX, ev_pt_[2], ev_pt_[3]);
         ext.resize(ns);
@@ -619,8 +629,8 @@ int FeContext::perform_matching(const FrameSlot &f0, const FrameSlot &f1, std::v
   }
   const int nt = std::min(n, max_pts_) + ns;
   for (int i = 0; i < n && i < max_pts_; i++) h_pts0_[i] = make_float2(pts0[i].x, pts0[i].y);
-  FE_CUDA(cudaMemcpyAsync(d_pts0_, h_pts0_, (size_t)nt * sizeof(float2), cudaMemcpyHostToDevice, s_pt_));
-  FE_CUDA(cudaMemcpyAsync(d_pts1_, d_pts0_, (size_t)nt * sizeof(float2), cudaMemcpyDeviceToDevice, s_pt_));
+  FE_COPY(d_pts0_, h_pts0_, (size_t)nt * sizeof(float2), cudaMemcpyHostToDevice, s_pt_);
+  FE_COPY(d_pts1_, d_pts0_, (size_t)nt * sizeof(float2), cudaMemcpyDeviceToDevice, s_pt_);
   LkParams prm;
   prm.win = cfg_.win_size;
   prm.max_level = cfg_.pyr_levels;
@@ -633,10 +643,10 @@ int FeContext::perform_matching(const FrameSlot &f0, const FrameSlot &f1, std::v
   launch_lk(f0.pyr, f1.pyr, d_pts0_, d_pts1_, d_status_, d_p0n_, d_p1n_, nt, prm, s_pt_);
   times.kernel_launches_total++;
   if (timing) cudaEventRecord(ev_pt_[5], s_pt_);
-  FE_CUDA(cudaMemcpyAsync(h_pts1_, d_pts1_, (size_t)nt * sizeof(float2), cudaMemcpyDeviceToHost, s_pt_));
-  FE_CUDA(cudaMemcpyAsync(h_status_, d_status_, (size_t)nt, cudaMemcpyDeviceToHost, s_pt_));
-  FE_CUDA(cudaMemcpyAsync(h_p0n_, d_p0n_, (size_t)nt * sizeof(float2), cudaMemcpyDeviceToHost, s_pt_));
-  FE_CUDA(cudaMemcpyAsync(h_p1n_, d_p1n_, (size_t)nt * sizeof(float2), cudaMemcpyDeviceToHost, s_pt_));
+  FE_COPY(h_pts1_, d_pts1_, (size_t)nt * sizeof(float2), cudaMemcpyDeviceToHost, s_pt_);
+  FE_COPY(h_status_, d_status_, (size_t)nt, cudaMemcpyDeviceToHost, s_pt_);
+  FE_COPY(h_p0n_, d_p0n_, (size_t)nt * sizeof(float2), cudaMemcpyDeviceToHost, s_pt_);
+  FE_COPY(h_p1n_, d_p1n_, (size_t)nt * sizeof(float2), cudaMemcpyDeviceToHost, s_pt_);
   FE_CUDA(cudaStreamSynchronize(s_pt_));
   if (timing) acc_time(times, FE_STAGE_LK, ev_pt_[4], ev_pt_[5]);
 
@@ -708,7 +718,7 @@ int FeContext::lsd_feed(FrameSlot &cur, FeFrameInfo *info) {
   FE_CUDA(cudaEventSynchronize(cur.ev_lines));
   int nseg = std::min(cur.h_fld_counts[1], cur.fld.out_cap);
   if (nseg > 1024) {
-    FE_CUDA(cudaMemcpyAsync(cur.h_segs + 1024, cur.fld.out + 1024, (size_t)(nseg - 1024) * sizeof(float4), cudaMemcpyDeviceToHost, s_line_));
+    FE_COPY(cur.h_segs + 1024, cur.fld.out + 1024, (size_t)(nseg - 1024) * sizeof(float4), cudaMemcpyDeviceToHost, s_line_);
     FE_CUDA(cudaStreamSynchronize(s_line_));
   }
   tap_fld_.assign(reinterpret_cast<float *>(cur.h_segs), reinterpret_cast<float *>(cur.h_segs) + 4 * (size_t)nseg);

@@ -1,0 +1,85 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol include/plviwo_fe.h
+declares, refuses to run without a GPU (no CPU fallback), and its host-side sequential step — the RANSAC gate —
+reproduces cv2.findFundamentalMat.  No kernel is launched here."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported(fe):
+    hdr = open(os.path.join(ROOT, "include", "plviwo_fe.h")).read()
+    declared = sorted(set(re.findall(r"\b(plviwo_(?:fe|op)_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(fe.EXPORTS), set(declared) ^ set(fe.EXPORTS)
+    lib = fe.lib()
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.plviwo_fe_abi_version() == 1
+
+
+def test_struct_layouts_match_header(fe):
+    import ctypes as C
+    assert C.sizeof(fe.FePointRow) == 24 and fe.POINT_ROW_DTYPE.itemsize == 24
+    assert C.sizeof(fe.FeLineRow) == 56 and fe.LINE_ROW_DTYPE.itemsize == 56
+    assert C.sizeof(fe.FeLinePoint) == 16 and fe.LINE_POINT_DTYPE.itemsize == 16
+    assert C.sizeof(fe.FeConfig) == 19 * 4 + 4 + 64
+    cfg = fe.default_config()
+    assert (cfg.width, cfg.height, cfg.num_features, cfg.pyr_levels, cfg.win_size) == (1280, 560, 150, 5, 15)
+    assert abs(cfg.K[0] - 816.90378992770002) < 1e-12 and cfg.fld_length_threshold == 20
+
+
+def test_no_cpu_fallback(fe):
+    if fe.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(fe.FrontEndError) as e:
+        fe.FrontEnd(fe.default_config())
+    assert e.value.code == fe.FE_NO_DEVICE
+    with pytest.raises(fe.FrontEndError):
+        fe.op_equalize_pyramid(np.zeros((64, 64), np.uint8), 2)
+
+
+def test_state_blob_pack_unpack(fe):
+    pts = np.random.default_rng(0).uniform(0, 500, (7, 2)).astype(np.float32)
+    blob = fe.pack_state(1280, 560, 99, pts, np.arange(7) + 5, None, None, 12, np.ones((2, 4), np.float32), [3, 4],
+                         [{5: 0.25, 7: 1.5}, {6: 2.0}])
+    st = fe.unpack_state(blob)
+    assert st["currid"] == 99 and st["line_currid"] == 12
+    assert np.array_equal(st["pts_last"], pts) and list(st["ids_last"]) == list(range(5, 12))
+    assert st["pol_last"] == [{5: 0.25, 7: 1.5}, {6: 2.0}] and st["img_last"] is None
+
+
+def test_ransac_host_matches_opencv(fe):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    exact = 0
+    for trial in range(40):
+        n = int(rng.integers(15, 600))
+        X = np.c_[rng.uniform(-3, 3, n), rng.uniform(-2, 2, n), rng.uniform(4, 12, n)]
+        R, _ = cv2.Rodrigues(rng.normal(0, 0.03, 3))
+        X2 = X @ R.T + rng.normal(0, 0.3, 3)
+        p0 = (X[:, :2] / X[:, 2:]).astype(np.float32)
+        p1 = (X2[:, :2] / X2[:, 2:]).astype(np.float32) + rng.normal(0, 0.5 / 800, (n, 2)).astype(np.float32)
+        out = rng.random(n) < 0.15
+        p1[out] += rng.normal(0, 0.05, (int(out.sum()), 2)).astype(np.float32)
+        thr = 2.0 / 816.9
+        _F, m = cv2.findFundamentalMat(p0, p1, cv2.FM_RANSAC, thr, 0.999)
+        ref = np.zeros(n, np.uint8) if m is None else m.reshape(-1)
+        mine, n_in = fe.op_ransac_fundamental(p0, p1, thr, 0.999)
+        exact += int(np.array_equal(ref, mine))
+        assert (ref != mine).mean() <= 0.005
+    assert exact >= 38, exact
+    # fewer than 7 points: OpenCV returns no mask at all (TrackKLT.cpp:877 then fails every point)
+    mine, n_in = fe.op_ransac_fundamental(p0[:5], p1[:5], thr, 0.999)
+    assert n_in == -1 and not mine.any()
+
+
+def test_synth_sequence_is_deterministic(synth):
+    a = synth.SynthSequence(seed=5, width=320, height=192, n_frames=5)
+    b = synth.SynthSequence(seed=5, width=320, height=192, n_frames=5)
+    assert np.array_equal(a.frame(3), b.frame(3)) and not np.array_equal(a.frame(3), a.frame(2))
+    assert a.frame(0).shape == (192, 320) and a.frame(0).dtype == np.uint8
+    m = synth.SynthSequence(seed=5, width=320, height=192, n_frames=5, moving_mask=True).mask(2)
+    assert m.max() == 255 and m.min() == 0
