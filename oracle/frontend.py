@@ -325,6 +325,21 @@ def point_line_distance(line: np.ndarray, x0, y0) -> np.float32:
     return f32(abs(float(num) / den))
 
 
+def point_line_distance_vec(line: np.ndarray, xs: np.ndarray, ys: np.ndarray) -> np.ndarray:
+    """point_line_distance over arrays of points: the same float32 operations, element-wise (speed only)."""
+    x0, y0 = xs.astype(f32), ys.astype(f32)
+    x1, y1, x2, y2 = f32(line[0]), f32(line[1]), f32(line[2]), f32(line[3])
+    cross = (x2 - x1) * (x0 - x1) + (y2 - y1) * (y0 - y1)
+    d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1)
+    d1 = np.sqrt((x0 - x1) * (x0 - x1) + (y0 - y1) * (y0 - y1)).astype(f32)
+    d2 = np.sqrt((x0 - x2) * (x0 - x2) + (y0 - y2) * (y0 - y2)).astype(f32)
+    num = np.abs((y2 - y1) * x0 + (x1 - x2) * y0 + ((x2 * y1) - (x1 * y2))).astype(f32)
+    den = math.sqrt(float(y2 - y1) ** 2 + float(x1 - x2) ** 2)
+    with np.errstate(all="ignore"):
+        d3 = np.abs(num.astype(np.float64) / den).astype(f32)
+    return np.where(cross <= 0, d1, np.where(cross > d, d2, d3)).astype(f32)
+
+
 def line_similar(line2: np.ndarray, line1: np.ndarray) -> bool:
     """TrackLSD::LineSimilar (TrackLSD.cpp:816-830)."""
     mx = (f32(line1[0]) + f32(line1[2])) / f32(2)
@@ -407,33 +422,40 @@ class TrackLSD:
     # -- TrackLSD.cpp:744-792 (bbox index mix-up reproduced)
     @staticmethod
     def assign_points_to_lines(lines, line_ids, points, pids):
+        """AssignPointToLines.  The double loop over (line, point) is evaluated as NumPy arrays — the same float32 /
+        float64 comparisons and PointLineDistance operations element-wise — so that the CPU baseline is not dominated
+        by interpreter overhead; the dictionaries are then filled in the reference's (line, point) order."""
         relation, positions, new_lines, new_ids = [], [], [], []
-        for i in range(len(lines)):
-            l = lines[i]
-            lx1, lx2, ly1, ly2 = float(l[0]), float(l[1]), float(l[2]), float(l[3])
-            min_lx, max_lx, min_ly, max_ly = lx1, lx2, ly1, ly2
-            if lx1 > lx2:
-                min_lx, max_lx = max_lx, min_lx
-            if ly1 > ly2:
-                min_ly, max_ly = max_ly, min_ly
-            pol: Dict[int, float] = {}
-            feats = []
-            found = False
-            for j in range(len(points)):
-                x, y = f32(points[j, 0]), f32(points[j, 1])
-                if float(x) < min_lx or float(x) > max_lx or float(y) < min_ly or float(y) > max_ly:
-                    continue
-                dist = point_line_distance(l, x, y)
-                if dist > 5:
-                    continue
-                pol[int(pids[j])] = float(dist)
-                feats.append((x, y))
-                found = True
-            if found:
-                relation.append(dict(sorted(pol.items())))
-                new_lines.append(l)
-                new_ids.append(line_ids[i])
-                positions.append(np.asarray(feats, f32).reshape(-1, 2))
+        lines = np.asarray(lines, f32).reshape(-1, 4)
+        points = np.asarray(points, f32).reshape(-1, 2)
+        if len(lines) == 0 or len(points) == 0:
+            return relation, positions, np.zeros((0, 4), f32), new_ids
+        L = lines.astype(np.float64)
+        lx1, lx2, ly1, ly2 = L[:, 0], L[:, 1], L[:, 2], L[:, 3]               # :754-757 (sic)
+        min_lx, max_lx = np.minimum(lx1, lx2)[:, None], np.maximum(lx1, lx2)[:, None]
+        min_ly, max_ly = np.minimum(ly1, ly2)[:, None], np.maximum(ly1, ly2)[:, None]
+        px, py = points[:, 0].astype(np.float64)[None, :], points[:, 1].astype(np.float64)[None, :]
+        inside = ~((px < min_lx) | (px > max_lx) | (py < min_ly) | (py > max_ly))   # :775
+        # PointLineDistance (:794-814) for every pair, float32 like the C++
+        x0, y0 = points[:, 0][None, :], points[:, 1][None, :]
+        x1, y1, x2, y2 = lines[:, 0][:, None], lines[:, 1][:, None], lines[:, 2][:, None], lines[:, 3][:, None]
+        cross = (x2 - x1) * (x0 - x1) + (y2 - y1) * (y0 - y1)
+        d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1)
+        d1 = np.sqrt((x0 - x1) * (x0 - x1) + (y0 - y1) * (y0 - y1))
+        d2 = np.sqrt((x0 - x2) * (x0 - x2) + (y0 - y2) * (y0 - y2))
+        num = np.abs((y2 - y1) * x0 + (x1 - x2) * y0 + ((x2 * y1) - (x1 * y2)))
+        den = np.sqrt((y2 - y1).astype(np.float64) ** 2 + (x1 - x2).astype(np.float64) ** 2)
+        with np.errstate(all="ignore"):
+            d3 = np.abs(num.astype(np.float64) / den).astype(f32)
+        dist = np.where(cross <= 0, d1, np.where(cross > d, d2, d3)).astype(f32)
+        hit = inside & ~(dist > 5)                                            # :780
+        for i in np.nonzero(hit.any(1))[0]:
+            js = np.nonzero(hit[i])[0]
+            pol = {int(pids[j]): float(dist[i, j]) for j in js}
+            relation.append(dict(sorted(pol.items())))
+            new_lines.append(lines[i])
+            new_ids.append(line_ids[i])
+            positions.append(points[js].copy())
         return relation, positions, np.asarray(new_lines, f32).reshape(-1, 4), new_ids
 
     # -- TrackLSD.cpp:368-407

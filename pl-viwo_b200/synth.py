@@ -28,7 +28,7 @@ class SynthSequence:
         self.line_heavy = bool(line_heavy)
         self.moving_mask = bool(moving_mask)
         self.hard = bool(hard)
-        self.noise_sigma = 0.6 if line_heavy else 2.0
+        self.noise_sigma = 0.6 if line_heavy else 1.2
         sc = self.W / 1280.0
         self.sc = sc
         # intrinsics scale with resolution (config 4 uses x1.5)
@@ -51,12 +51,16 @@ class SynthSequence:
             n /= n.std() + 1e-6
             acc += amp * n
         acc /= acc.std() + 1e-6
-        img = 120.0 + (3.0 if self.line_heavy else 24.0) * acc
-        if self.line_heavy:
-            # broad large-scale shading: keeps the histogram wide so equalisation does not amplify the fine texture
-            shade = cv2.GaussianBlur(rng.standard_normal((ch // 8 + 1, cw // 8 + 1)).astype(np.float32), (0, 0), 10)
-            shade = cv2.resize(shade, (cw, ch), interpolation=cv2.INTER_CUBIC)
-            img += 38.0 * shade / (shade.std() + 1e-6)
+        # texture strength varies over the scene (road / sky are smooth, vegetation / facades are busy), like a real
+        # urban frame: about a third of the canvas is strongly textured
+        amp = cv2.GaussianBlur(rng.standard_normal((ch // 8 + 1, cw // 8 + 1)).astype(np.float32), (0, 0), 6)
+        amp = cv2.resize(amp / (amp.std() + 1e-6), (cw, ch), interpolation=cv2.INTER_CUBIC)
+        amp = 1.0 / (1.0 + np.exp(-(amp - 0.9) * 4.0))
+        img = 120.0 + (3.0 if self.line_heavy else 26.0 * amp + 1.5) * acc
+        # broad large-scale shading: keeps the histogram wide so equalisation does not amplify noise in flat regions
+        shade = cv2.GaussianBlur(rng.standard_normal((ch // 8 + 1, cw // 8 + 1)).astype(np.float32), (0, 0), 10)
+        shade = cv2.resize(shade, (cw, ch), interpolation=cv2.INTER_CUBIC)
+        img += (38.0 if self.line_heavy else 30.0) * shade / (shade.std() + 1e-6)
         # piecewise-constant regions ("buildings", "road") give long crisp edges
         n_rect = 36 if self.line_heavy else 28
         for _ in range(n_rect):
@@ -147,8 +151,8 @@ class SynthSequence:
                 img[ya:yb, xa:xb] = tex[ya - y:yb - y, xa - x:xb - x]
         rng = np.random.default_rng(self.seed * 100003 + t)
         noise = rng.standard_normal(img.shape).astype(np.float32)
-        if self.line_heavy:  # correlated (demosaic-like) low noise keeps Canny(50,50) after equalisation readable
-            noise = cv2.GaussianBlur(noise, (0, 0), 1.2)
+        # correlated (demosaic-like) noise keeps Canny(50,50) after equalisation readable
+        noise = cv2.GaussianBlur(noise, (0, 0), 1.2 if self.line_heavy else 0.8) * (1.0 if self.line_heavy else 1.6)
         img = self.gain[t] * img + self.offset[t] + self.noise_sigma * noise
         return np.clip(np.rint(img), 0, 255).astype(np.uint8)
 
