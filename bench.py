@@ -36,7 +36,7 @@ WORKLOAD = dict(width=1280, height=560, num_features=400, fast_threshold=20, gri
                 pyr_levels=4, win_size=15)
 WORKLOAD_NAME = "BASELINE.json configs[1]: synthetic KAIST-shaped 1280x560 mono, point+line front end, 400 pts, 5x5 grid, maxLevel 4, win 15"
 SEQ_FRAMES = 300
-LOOKAHEAD = 6
+LOOKAHEAD = 12
 METRIC = "front-end frames/sec @1280x560"
 
 
@@ -298,6 +298,7 @@ def main():
                 "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ab[dom], "avg_launch_ms": avg_ms,
                 "stage_ms_per_frame": {k: v / nfr for k, v in st["ms"].items()},
+                "host_ms_per_frame": {k: v / nfr for k, v in st["host_ms"].items()},
                 "whole_frame": {"algorithmic_bytes": ab["frame_total"],
                                 "achieved_GBps": ab["frame_total"] * (total_frames / (ms * 1e-3)) / 1e9 / world}}
     cpu = None

@@ -128,6 +128,8 @@ typedef struct FeStageTimes {
   uint64_t frames;
   uint64_t kernel_launches_total;
   uint64_t h2d_bytes, d2h_bytes;   /* bytes moved by the handle's own cudaMemcpyAsync calls */
+  double host_ms[16];              /* host wall time: submit, detection, matching, ransac, lines, collect, line wait,
+                                      pre-detection wait; worker thread: total, FAST wait, sort, sub-pixel round trip */
 } FeStageTimes;
 
 /* ---- lifetime ----------------------------------------------------------------------------------------- */
@@ -186,6 +188,7 @@ enum FeTap {
   FE_TAP_SUBPIX_LAST = 36, /* last detection: float records (x_sel, y_sel, x_ref, y_ref)                      */
   FE_TAP_FLD_LAST = 37     /* last line detection: float records (x1, y1, x2, y2) at half resolution          */
 };
+int plviwo_fe_enable_taps(FeHandle *h, int on);   /* taps cost host time: off by default, enable BEFORE feeding */
 int plviwo_fe_tap(FeHandle *h, int what, void *buf, size_t cap, size_t *n_bytes);
 
 /* ---- measurement -------------------------------------------------------------------------------------- */

@@ -22,6 +22,8 @@ LIB_PATH = os.path.join(_HERE, "libplviwo_fe.so")
 FE_OK, FE_BAD_ARG, FE_NO_DEVICE, FE_CUDA_ERROR, FE_OVERFLOW, FE_INTERNAL = range(6)
 HIST_NONE, HIST_HISTOGRAM, HIST_CLAHE = 0, 1, 2
 _STATUS = {0: "FE_OK", 1: "FE_BAD_ARG", 2: "FE_NO_DEVICE", 3: "FE_CUDA_ERROR", 4: "FE_OVERFLOW", 5: "FE_INTERNAL"}
+HOST_STAGES = ["submit", "detection", "matching", "ransac", "lines", "collect", "line_wait", "predet_wait",
+               "worker_total", "worker_fast_wait", "worker_sort", "worker_subpix"]
 STAGES = ["h2d", "hist", "eq_pyr1", "pyr_rest", "fast", "subpix", "lk", "canny", "fld"]
 TAP_PYR_LEVEL0, TAP_HALF, TAP_EDGES, TAP_FAST_LAST, TAP_LK_LAST, TAP_SUBPIX_LAST, TAP_FLD_LAST = 0, 32, 33, 34, 35, 36, 37
 
@@ -66,7 +68,7 @@ class FeFrameInfo(C.Structure):
 
 class FeStageTimes(C.Structure):
     _fields_ = [("ms", C.c_double * 16), ("launches", C.c_uint64 * 16), ("frames", C.c_uint64),
-                ("kernel_launches_total", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("kernel_launches_total", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("host_ms", C.c_double * 16)]
 
 
 POINT_ROW_DTYPE = np.dtype([("id", "<u8"), ("u", "<f4"), ("v", "<f4"), ("un", "<f4"), ("vn", "<f4")])
@@ -82,7 +84,7 @@ EXPORTS = [
     "plviwo_fe_last_error", "plviwo_fe_set_calib", "plviwo_fe_set_num_features", "plviwo_fe_change_feat_id", "plviwo_fe_feed",
     "plviwo_fe_feed_device", "plviwo_fe_submit", "plviwo_fe_collect", "plviwo_fe_get_point_rows", "plviwo_fe_get_last_obs",
     "plviwo_fe_get_line_rows", "plviwo_fe_get_line_points", "plviwo_fe_get_line_samples", "plviwo_fe_get_state",
-    "plviwo_fe_set_state", "plviwo_fe_tap", "plviwo_fe_enable_timing", "plviwo_fe_get_stage_times",
+    "plviwo_fe_set_state", "plviwo_fe_enable_taps", "plviwo_fe_tap", "plviwo_fe_enable_timing", "plviwo_fe_get_stage_times",
     "plviwo_op_equalize_pyramid", "plviwo_op_fast_cell", "plviwo_op_corner_subpix", "plviwo_op_lk", "plviwo_op_undistort",
     "plviwo_op_canny_half", "plviwo_op_fld", "plviwo_op_ransac_fundamental",
 ]
@@ -116,6 +118,7 @@ def lib() -> C.CDLL:
         L.plviwo_fe_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.plviwo_fe_tap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.plviwo_fe_enable_timing.argtypes = [C.c_void_p, C.c_int]
+        L.plviwo_fe_enable_taps.argtypes = [C.c_void_p, C.c_int]
         L.plviwo_fe_get_stage_times.argtypes = [C.c_void_p, C.POINTER(FeStageTimes), C.c_int]
         L.plviwo_fe_default_config.argtypes = [C.POINTER(FeConfig)]
         L.plviwo_fe_default_config.restype = None
@@ -377,6 +380,9 @@ class FrontEnd:
             _check(self._lib.plviwo_fe_tap(self._h, what, out.ctypes.data, n.value, C.byref(n)), self._h)
         return out
 
+    def enable_taps(self, on: bool = True):
+        _check(self._lib.plviwo_fe_enable_taps(self._h, 1 if on else 0), self._h)
+
     def enable_timing(self, on: bool = True):
         _check(self._lib.plviwo_fe_enable_timing(self._h, 1 if on else 0), self._h)
 
@@ -385,7 +391,8 @@ class FrontEnd:
         _check(self._lib.plviwo_fe_get_stage_times(self._h, C.byref(t), 1 if reset else 0), self._h)
         return {"ms": {s: t.ms[i] for i, s in enumerate(STAGES)}, "launches": {s: int(t.launches[i]) for i, s in enumerate(STAGES)},
                 "frames": int(t.frames), "kernel_launches_total": int(t.kernel_launches_total),
-                "h2d_bytes": int(t.h2d_bytes), "d2h_bytes": int(t.d2h_bytes)}
+                "h2d_bytes": int(t.h2d_bytes), "d2h_bytes": int(t.d2h_bytes),
+                "host_ms": {k: t.host_ms[i] for i, k in enumerate(HOST_STAGES)}}
 
 
 # ------------------------------------------------------------------------------------------- tracker state blob

@@ -23,6 +23,7 @@ SOURCES = [
     ("fe_context.cu", []),
     ("fe_capi.cu", []),
     ("ransac.cpp", []),
+    ("host_simd.cpp", []),
 ]
 HEADERS = ["fe_kernels.h", "fe_context.h", os.path.join("..", "..", "include", "plviwo_fe.h")]
 

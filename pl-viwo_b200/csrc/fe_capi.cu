@@ -236,10 +236,15 @@ int plviwo_fe_enable_timing(FeHandle *h, int on) {
   h->ctx->timing = on != 0;
   return FE_OK;
 }
+int plviwo_fe_enable_taps(FeHandle *h, int on) {
+  if (!h) return FE_BAD_ARG;
+  h->ctx->taps = on != 0;
+  return FE_OK;
+}
 int plviwo_fe_get_stage_times(FeHandle *h, FeStageTimes *out, int reset) {
   if (!h || !out) return FE_BAD_ARG;
-  *out = h->ctx->times;
-  if (reset) std::memset(&h->ctx->times, 0, sizeof(h->ctx->times));
+  *out = h->ctx->snapshot_times();
+  if (reset) h->ctx->reset_times();
   return FE_OK;
 }
 
@@ -439,24 +444,8 @@ int plviwo_op_undistort(int device, const float *pts, int n, const double K[4], 
 namespace {
 struct TmpFld {
   FldBuffers fb;
-  ~TmpFld() {
-    cudaFree(fb.edges); cudaFree(fb.chain_pts); cudaFree(fb.chain_off); cudaFree(fb.n_chains);
-    cudaFree(fb.segs); cudaFree(fb.seg_cnt); cudaFree(fb.out);
-  }
-  int alloc(int w, int h, int T, int out_cap) {
-    fb.words_per_row = (w + 31) / 32;
-    fb.max_chains = w * h / (T + 1) + 1;
-    fb.out_cap = out_cap;
-    if (cudaMalloc(&fb.edges, (size_t)fb.words_per_row * h * sizeof(unsigned)) != cudaSuccess) return 1;
-    if (cudaMalloc(&fb.chain_pts, (size_t)w * h * sizeof(int2)) != cudaSuccess) return 1;
-    if (cudaMalloc(&fb.chain_off, (size_t)(fb.max_chains + 1) * sizeof(int)) != cudaSuccess) return 1;
-    if (cudaMalloc(&fb.n_chains, 2 * sizeof(int)) != cudaSuccess) return 1;
-    if (cudaMalloc(&fb.segs, (size_t)(w * h / kSegsPerChainDiv + fb.max_chains + 2) * sizeof(float4)) != cudaSuccess) return 1;
-    if (cudaMalloc(&fb.seg_cnt, (size_t)2 * fb.max_chains * sizeof(int)) != cudaSuccess) return 1;
-    if (cudaMalloc(&fb.out, (size_t)out_cap * sizeof(float4)) != cudaSuccess) return 1;
-    cudaMemset(fb.n_chains, 0, 2 * sizeof(int));
-    return 0;
-  }
+  ~TmpFld() { fb.release(); }
+  int alloc(int w, int h, int T, int out_cap) { return fb.alloc(w, h, T, out_cap); }
 };
 }  // namespace
 
@@ -489,7 +478,7 @@ int plviwo_op_fld(int device, const uint8_t *img, int w, int h, int length_thres
   launch_fld(raw.im, length_threshold, distance_threshold, f.fb, 0);
   OP_CUDA(cudaDeviceSynchronize());
   int counts[2] = {0, 0};
-  OP_CUDA(cudaMemcpy(counts, f.fb.n_chains, sizeof(counts), cudaMemcpyDeviceToHost));
+  OP_CUDA(cudaMemcpy(counts, f.fb.counters + 3, sizeof(counts), cudaMemcpyDeviceToHost));
   int n = std::min(counts[1], out_cap);
   *n_out = n;
   if (lines) {

@@ -11,6 +11,7 @@
 #include "fe_context.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 
@@ -23,6 +24,15 @@ namespace plviwo {
   } while (0)
 
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+namespace {
+struct HostTimer {  // accumulates wall time into FeStageTimes::host_ms[idx]
+  double *acc;
+  std::chrono::steady_clock::time_point t0;
+  explicit HostTimer(double *a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+  ~HostTimer() { *acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+}  // namespace
 
 // cudaMemcpyAsync with byte accounting (FeStageTimes::h2d_bytes / d2h_bytes)
 #define FE_COPY(dst, src, bytes, kind, stream)                                   \
@@ -58,7 +68,6 @@ int FeContext::init() {
   FE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   FE_CUDA(cudaStreamCreateWithPriority(&s_img_, cudaStreamNonBlocking, lo));
   FE_CUDA(cudaStreamCreateWithPriority(&s_pt_, cudaStreamNonBlocking, hi));
-  FE_CUDA(cudaStreamCreateWithPriority(&s_line_, cudaStreamNonBlocking, lo));
   FE_CUDA(cudaMalloc(&d_hist_, 256 * sizeof(unsigned)));
   FE_CUDA(cudaMemset(d_hist_, 0, 256 * sizeof(unsigned)));
   FE_CUDA(cudaMalloc(&d_counters_, 4 * sizeof(unsigned)));
@@ -66,6 +75,7 @@ int FeContext::init() {
 
   const int nslots = std::max(cfg_.lookahead, 0) + 2;
   slots_.resize(nslots);
+  for (int i = 0; i < nslots; i++) slots_[i].index = i;
   for (FrameSlot &s : slots_) {
     int rc = alloc_image(s.raw, W_, H_);
     if (rc) return rc;
@@ -84,42 +94,49 @@ int FeContext::init() {
       rc = alloc_image(s.half, W_ / 2, H_ / 2);
       if (rc) return rc;
       FldBuffers &fb = s.fld;
-      const int hw = W_ / 2, hh = H_ / 2;
-      fb.words_per_row = (hw + 31) / 32;
-      fb.max_chains = hw * hh / (cfg_.fld_length_threshold + 1) + 1;
-      fb.out_cap = 4096;
-      FE_CUDA(cudaMalloc(&fb.edges, (size_t)fb.words_per_row * hh * sizeof(unsigned)));
-      FE_CUDA(cudaMalloc(&fb.chain_pts, (size_t)hw * hh * sizeof(int2)));
-      FE_CUDA(cudaMalloc(&fb.chain_off, (size_t)(fb.max_chains + 1) * sizeof(int)));
-      FE_CUDA(cudaMalloc(&fb.n_chains, 2 * sizeof(int)));
-      FE_CUDA(cudaMemset(fb.n_chains, 0, 2 * sizeof(int)));
-      FE_CUDA(cudaMalloc(&fb.segs, (size_t)(hw * hh / kSegsPerChainDiv + fb.max_chains + 2) * sizeof(float4)));
-      FE_CUDA(cudaMalloc(&fb.seg_cnt, (size_t)2 * fb.max_chains * sizeof(int)));
-      FE_CUDA(cudaMalloc(&fb.out, (size_t)fb.out_cap * sizeof(float4)));
+      if (fb.alloc(W_ / 2, H_ / 2, cfg_.fld_length_threshold, 4096)) return fail(cudaGetLastError(), "FldBuffers::alloc");
       FE_CUDA(cudaMallocHost(&s.h_segs, (size_t)fb.out_cap * sizeof(float4)));
       FE_CUDA(cudaMallocHost(&s.h_fld_counts, 2 * sizeof(int)));
     }
     FE_CUDA(cudaMallocHost(&s.h_raw, (size_t)W_ * H_));
+    FE_CUDA(cudaStreamCreateWithPriority(&s.s_line, cudaStreamNonBlocking, lo));
     FE_CUDA(cudaEventCreateWithFlags(&s.ev_pyr, cudaEventDisableTiming));
     FE_CUDA(cudaEventCreateWithFlags(&s.ev_lines, cudaEventDisableTiming));
     for (auto &e : s.ev_t) FE_CUDA(cudaEventCreate(&e));
   }
   for (auto &e : ev_pt_) FE_CUDA(cudaEventCreate(&e));
+  FE_CUDA(cudaEventCreateWithFlags(&ev_sync_, cudaEventDisableTiming));
+  FE_CUDA(cudaMallocHost(&h_flag_lk_, 16 * sizeof(int)));
+  std::memset(h_flag_lk_, 0, 16 * sizeof(int));
 
-  // detection scratch (Grider_GRID may shrink the grid when num_features < grid_x * grid_y; cells never get larger
-  // than the image, so size for the worst case)
+  // detection: FAST output buffers live in the frame slots (pre-detection runs ahead of the tracker)
   max_cells_ = std::max(cfg_.grid_x * cfg_.grid_y, 1);
   max_bands_ = (H_ + kFastBandRows - 1) / kFastBandRows;
   kps_cap_ = W_ * H_ / 4 + 1024;
+  cand_cap_ = std::max(max_cells_ * (cfg_.num_features + 1), 1024);
+  if (cand_cap_ > 65536) cand_cap_ = 65536;
   FE_CUDA(cudaMalloc(&d_cells_, (size_t)max_cells_ * sizeof(FastCell)));
-  FE_CUDA(cudaMallocHost(&h_cells_, (size_t)max_cells_ * sizeof(FastCell)));
-  FE_CUDA(cudaMalloc(&d_fast_total_, sizeof(unsigned)));
-  FE_CUDA(cudaMalloc(&d_kps_, (size_t)kps_cap_ * sizeof(unsigned)));
-  FE_CUDA(cudaMallocHost(&h_kps_, (size_t)kps_cap_ * sizeof(unsigned)));
-  FE_CUDA(cudaMalloc(&d_band_off_, (size_t)max_cells_ * max_bands_ * sizeof(int)));
-  FE_CUDA(cudaMalloc(&d_band_cnt_, (size_t)max_cells_ * max_bands_ * sizeof(int)));
-  FE_CUDA(cudaMallocHost(&h_band_, (size_t)(1 + 2 * max_cells_ * max_bands_) * sizeof(int)));
+  FE_CUDA(cudaStreamCreateWithPriority(&s_det_, cudaStreamNonBlocking, lo));
+  FE_CUDA(cudaStreamCreateWithPriority(&s_det2_, cudaStreamNonBlocking, lo));
+  for (FrameSlot &s : slots_) {
+    FE_CUDA(cudaMalloc(&s.d_fast_total, sizeof(unsigned)));
+    FE_CUDA(cudaMalloc(&s.d_kps, (size_t)kps_cap_ * sizeof(unsigned)));
+    FE_CUDA(cudaMallocHost(&s.h_kps, (size_t)kps_cap_ * sizeof(unsigned)));
+    FE_CUDA(cudaMalloc(&s.d_band_off, (size_t)max_cells_ * max_bands_ * sizeof(int)));
+    FE_CUDA(cudaMalloc(&s.d_band_cnt, (size_t)max_cells_ * max_bands_ * sizeof(int)));
+    FE_CUDA(cudaMallocHost(&s.h_band, (size_t)(1 + 2 * max_cells_ * max_bands_) * sizeof(int)));
+    FE_CUDA(cudaMalloc(&s.d_cand, (size_t)cand_cap_ * sizeof(float2)));
+    FE_CUDA(cudaMallocHost(&s.h_cand_in, (size_t)cand_cap_ * sizeof(float2)));
+    FE_CUDA(cudaMallocHost(&s.h_cand_out, (size_t)cand_cap_ * sizeof(float2)));
+    FE_CUDA(cudaMallocHost(&s.h_flags, 16 * sizeof(int)));
+    std::memset(s.h_flags, 0, 16 * sizeof(int));
+    FE_CUDA(cudaEventCreateWithFlags(&s.ev_l0, cudaEventDisableTiming));
+    FE_CUDA(cudaEventCreateWithFlags(&s.ev_fast, cudaEventDisableTiming));
+    for (auto &e : s.ev_fast_t) FE_CUDA(cudaEventCreate(&e));
+  }
   occ_bits_.assign((size_t)((W_ + 63) / 64) * H_, 0);
+  layout_cells();
+  worker_ = std::thread([this] { worker_main(); });
 
   max_pts_ = std::max(4096, 8 * cfg_.num_features) + 4096 * (cfg_.line_samples > 0 ? 8 : 0);
   FE_CUDA(cudaMalloc(&d_pts0_, (size_t)max_pts_ * sizeof(float2)));
@@ -137,28 +154,74 @@ int FeContext::init() {
 }
 
 FeContext::~FeContext() {
+  {
+    std::lock_guard<std::mutex> lk(wmu_);
+    wstop_ = true;
+  }
+  wcv_.notify_all();
+  if (worker_.joinable()) worker_.join();
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
   for (FrameSlot &s : slots_) {
     cudaFree(s.raw.p);
     for (int l = 0; l < s.pyr.n; l++) cudaFree(s.pyr.lvl[l].p);
     cudaFree(s.half.p);
-    cudaFree(s.fld.edges); cudaFree(s.fld.chain_pts); cudaFree(s.fld.chain_off); cudaFree(s.fld.n_chains);
-    cudaFree(s.fld.segs); cudaFree(s.fld.seg_cnt); cudaFree(s.fld.out);
+    s.fld.release();
     cudaFreeHost(s.h_segs); cudaFreeHost(s.h_fld_counts); cudaFreeHost(s.h_raw);
+    cudaFree(s.d_fast_total); cudaFree(s.d_kps); cudaFreeHost(s.h_kps); cudaFree(s.d_band_off); cudaFree(s.d_band_cnt);
+    cudaFreeHost(s.h_flags);
+    cudaFreeHost(s.h_band); cudaFree(s.d_cand); cudaFreeHost(s.h_cand_in); cudaFreeHost(s.h_cand_out);
+    if (s.ev_l0) cudaEventDestroy(s.ev_l0);
+    if (s.ev_fast) cudaEventDestroy(s.ev_fast);
+    for (auto &e : s.ev_fast_t) if (e) cudaEventDestroy(e);
+    if (s.s_line) cudaStreamDestroy(s.s_line);
     if (s.ev_pyr) cudaEventDestroy(s.ev_pyr);
     if (s.ev_lines) cudaEventDestroy(s.ev_lines);
     for (auto &e : s.ev_t) if (e) cudaEventDestroy(e);
   }
   for (auto &e : ev_pt_) if (e) cudaEventDestroy(e);
+  if (ev_sync_) cudaEventDestroy(ev_sync_);
+  cudaFreeHost(h_flag_lk_);
   cudaFree(d_hist_); cudaFree(d_counters_);
-  cudaFree(d_cells_); cudaFreeHost(h_cells_); cudaFree(d_fast_total_); cudaFree(d_kps_); cudaFreeHost(h_kps_);
-  cudaFree(d_band_off_); cudaFree(d_band_cnt_); cudaFreeHost(h_band_);
+  cudaFree(d_cells_);
+  if (s_det_) cudaStreamDestroy(s_det_);
+  if (s_det2_) cudaStreamDestroy(s_det2_);
   cudaFree(d_pts0_); cudaFree(d_pts1_); cudaFree(d_p0n_); cudaFree(d_p1n_); cudaFree(d_status_);
   cudaFreeHost(h_pts0_); cudaFreeHost(h_pts1_); cudaFreeHost(h_p0n_); cudaFreeHost(h_p1n_); cudaFreeHost(h_status_);
   if (s_img_) cudaStreamDestroy(s_img_);
   if (s_pt_) cudaStreamDestroy(s_pt_);
-  if (s_line_) cudaStreamDestroy(s_line_);
+}
+
+// Low-latency wait: poll an event instead of a blocking synchronise (the tracker thread has nothing else to do)
+int FeContext::spin_sync(cudaStream_t st) {
+  FE_CUDA(cudaEventRecord(ev_sync_, st));
+  while (true) {
+    cudaError_t e = cudaEventQuery(ev_sync_);
+    if (e == cudaSuccess) return FE_OK;
+    if (e != cudaErrorNotReady) return fail(e, "cudaEventQuery");
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+}
+
+// Waits for a k_signal sequence number.  Polls memory only; every ~2M polls it asks the driver whether the stream
+// died, so a faulting kernel turns into an error instead of a hang.
+int FeContext::wait_flag(volatile int *flag, int value, cudaStream_t st, std::string *err) {
+  unsigned spins = 0;
+  while (*flag != value) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+    if ((++spins & 0x1fffff) == 0) {
+      cudaError_t e = cudaStreamQuery(st);
+      if (e != cudaSuccess && e != cudaErrorNotReady) {
+        *err = std::string("stream failed while waiting for a completion signal: ") + cudaGetErrorString(e);
+        return FE_CUDA_ERROR;
+      }
+    }
+  }
+  return FE_OK;
 }
 
 int FeContext::set_calib(const double K[4], const double D[4]) {
@@ -206,23 +269,25 @@ int FeContext::enqueue_frame_independent(FrameSlot &s) {
   times.kernel_launches_total++;
   if (tm) cudaEventRecord(s.ev_t[3], s_img_);
   FE_CUDA(cudaEventRecord(s.ev_lines, s_img_));  // reused as "half image ready" until the line stream re-records it
+  FE_CUDA(cudaEventRecord(s.ev_l0, s_img_));
   if (s.pyr.n > 2) {
     launch_pyr_rest(s.pyr, d_counters_ + 1, s_img_);
-    times.kernel_launches_total++;
+    times.kernel_launches_total += s.pyr.n - 2;
   }
   if (tm) cudaEventRecord(s.ev_t[4], s_img_);
   FE_CUDA(cudaEventRecord(s.ev_pyr, s_img_));
   if (cfg_.use_lines && s.has_vp) {
-    FE_CUDA(cudaStreamWaitEvent(s_line_, s.ev_lines, 0));
-    if (tm) cudaEventRecord(s.ev_t[5], s_line_);
-    launch_canny(s.half, cfg_.canny_th1, cfg_.canny_th2, s.fld, s_line_);
-    if (tm) cudaEventRecord(s.ev_t[6], s_line_);
-    launch_fld(s.half, cfg_.fld_length_threshold, cfg_.fld_distance_threshold, s.fld, s_line_);
-    times.kernel_launches_total += 4;
-    if (tm) cudaEventRecord(s.ev_t[7], s_line_);
-    FE_COPY(s.h_fld_counts, s.fld.n_chains, 2 * sizeof(int), cudaMemcpyDeviceToHost, s_line_);
-    FE_COPY(s.h_segs, s.fld.out, 1024 * sizeof(float4), cudaMemcpyDeviceToHost, s_line_);
-    FE_CUDA(cudaEventRecord(s.ev_lines, s_line_));
+    FE_CUDA(cudaStreamWaitEvent(s.s_line, s.ev_lines, 0));
+    if (tm) cudaEventRecord(s.ev_t[5], s.s_line);
+    launch_canny(s.half, cfg_.canny_th1, cfg_.canny_th2, s.fld, s.s_line);
+    if (tm) cudaEventRecord(s.ev_t[6], s.s_line);
+    launch_fld(s.half, cfg_.fld_length_threshold, cfg_.fld_distance_threshold, s.fld, s.s_line);
+    times.kernel_launches_total += 9;
+    if (tm) cudaEventRecord(s.ev_t[7], s.s_line);
+    FE_COPY(s.h_fld_counts, s.fld.counters + 3, 2 * sizeof(int), cudaMemcpyDeviceToHost, s.s_line);
+    FE_COPY(s.h_segs, s.fld.out, 1024 * sizeof(float4), cudaMemcpyDeviceToHost, s.s_line);
+    FE_CUDA(cudaEventRecord(s.ev_lines, s.s_line));
+    launch_signal(&s.h_flags[2], ++s.seq_lines, s.s_line);
   }
   FE_CUDA(cudaGetLastError());
   return FE_OK;
@@ -230,6 +295,7 @@ int FeContext::enqueue_frame_independent(FrameSlot &s) {
 
 int FeContext::submit(double t, const uint8_t *image, int stride, bool on_device, const uint8_t *mask, int mask_stride,
                       const double vp[6]) {
+  HostTimer ht(&times.host_ms[0]);
   FE_CUDA(cudaSetDevice(device_));
   int si = -1;
   for (int i = 0; i < (int)slots_.size(); i++)
@@ -269,8 +335,206 @@ int FeContext::submit(double t, const uint8_t *image, int stride, bool on_device
   if (timing) cudaEventRecord(s.ev_t[1], s_img_);
   int rc = enqueue_frame_independent(s);
   if (rc) return rc;
+  rc = enqueue_fast_all_cells(s);
+  if (rc) return rc;
   queue_.push_back(si);
   return FE_OK;
+}
+
+// ------------------------------------------------------------------------------------------ pre-detection
+void FeContext::layout_cells() {
+  // Grider_GRID geometry (Grider_GRID.h:88-100): the grider may shrink ITS grid when num_features < grid_x * grid_y
+  // while the cell indices still come from the caller's grid; cells that leave the image are skipped (:117-118)
+  const int gx = cfg_.grid_x, gy = cfg_.grid_y;
+  int ggx = gx, ggy = gy;
+  if (cfg_.num_features < ggx * ggy) {
+    double ratio = (double)ggx / (double)ggy;
+    ggy = (int)std::ceil(std::sqrt(cfg_.num_features / ratio));
+    ggx = (int)std::ceil(ggy * ratio);
+  }
+  cells_nfg_ = (int)((double)cfg_.num_features / (double)(ggx * ggy)) + 1;
+  cells_csx_ = W_ / ggx;
+  cells_csy_ = H_ / ggy;
+  cells_.clear();
+  cell_of_loc_.assign((size_t)gx * gy, -1);
+  if (cells_csx_ > 0 && cells_csy_ > 0) {
+    for (int x = 0; x < gx; x++)
+      for (int y = 0; y < gy; y++) {
+        int px = x * cells_csx_, py = y * cells_csy_;
+        if (px + cells_csx_ > W_ || py + cells_csy_ > H_) continue;
+        if ((int)cells_.size() >= max_cells_) continue;
+        cell_of_loc_[(size_t)x * gy + y] = (int)cells_.size();
+        cells_.push_back(FastCell{px, py, cells_csx_, cells_csy_});
+      }
+  }
+  cells_nb_ = cells_csy_ > 0 ? (cells_csy_ + kFastBandRows - 1) / kFastBandRows : 0;
+  cells_num_features_ = cfg_.num_features;
+  cells_uploaded_ = false;
+}
+
+int FeContext::enqueue_fast_all_cells(FrameSlot &s) {
+  if (cells_num_features_ != cfg_.num_features) {
+    FE_CUDA(cudaStreamSynchronize(s_det_));   // d_cells_ may still be read by an earlier frame's FAST
+    layout_cells();
+  }
+  if (!cells_uploaded_ && !cells_.empty()) {
+    FE_CUDA(cudaMemcpyAsync(d_cells_, cells_.data(), cells_.size() * sizeof(FastCell), cudaMemcpyHostToDevice, s_det_));
+    cells_uploaded_ = true;
+  }
+  s.cells = cells_;
+  s.cell_of_loc = cell_of_loc_;
+  s.predet_ncell = (int)cells_.size();
+  s.predet_nb = cells_nb_;
+  s.predet_nfg = cells_nfg_;
+  s.predet_num_features = cfg_.num_features;
+  s.predet_state.store(1);
+  const int ncell = s.predet_ncell, nb = s.predet_nb;
+  if (ncell > 0) {
+    FE_CUDA(cudaStreamWaitEvent(s_det_, s.ev_l0, 0));
+    FE_CUDA(cudaMemsetAsync(s.d_fast_total, 0, sizeof(unsigned), s_det_));
+    if (timing) cudaEventRecord(s.ev_fast_t[0], s_det_);
+    launch_fast(s.pyr.lvl[0], d_cells_, ncell, nb, cells_csx_, cfg_.fast_threshold, s.d_fast_total, s.d_band_off, s.d_band_cnt,
+                s.d_kps, kps_cap_, s_det_);
+    times.kernel_launches_total++;
+    if (timing) cudaEventRecord(s.ev_fast_t[1], s_det_);
+    const int ntab = ncell * nb;
+    const int spec = std::min(16384, kps_cap_);   // speculative first chunk of the compact keypoint list
+    FE_COPY(s.h_band, s.d_fast_total, sizeof(unsigned), cudaMemcpyDeviceToHost, s_det_);
+    FE_COPY(s.h_band + 1, s.d_band_off, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, s_det_);
+    FE_COPY(s.h_band + 1 + ntab, s.d_band_cnt, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, s_det_);
+    FE_COPY(s.h_kps, s.d_kps, (size_t)spec * sizeof(unsigned), cudaMemcpyDeviceToHost, s_det_);
+  }
+  FE_CUDA(cudaEventRecord(s.ev_fast, s_det_));
+  launch_signal(&s.h_flags[0], ++s.seq_fast, s_det_);
+  {
+    std::lock_guard<std::mutex> lk(wmu_);
+    wqueue_.push_back(s.index);
+  }
+  wcv_.notify_one();
+  return FE_OK;
+}
+
+namespace {
+// std::sort's permutation depends only on the comparator's answers, not on the element type, so the corners are sorted
+// as 8-byte (response, packed xy) records instead of 28-byte cv::KeyPoints: same introsort, same tie permutation.
+struct KpSort {
+  float response;
+  unsigned xy;
+};
+bool compare_response(KpSort first, KpSort second) { return first.response > second.response; }  // Grider_FAST.h:57
+}  // namespace
+
+void FeContext::worker_main() {
+  cudaSetDevice(device_);
+  while (true) {
+    int si;
+    {
+      std::unique_lock<std::mutex> lk(wmu_);
+      wcv_.wait(lk, [this] { return wstop_ || !wqueue_.empty(); });
+      if (wqueue_.empty()) return;   // stop requested and nothing left
+      si = wqueue_.front();
+      wqueue_.pop_front();
+    }
+    FrameSlot &s = slots_[si];
+    int rc = run_predetection(s);
+    s.predet_state.store(rc == FE_OK ? 2 : -1);
+  }
+}
+
+// worker thread: std::sort per cell (Grider_GRID.h:128), first num_features_grid of each (:133), cornerSubPix (:163-179)
+int FeContext::run_predetection(FrameSlot &s) {
+  auto bad = [&](cudaError_t e, const char *what) {
+    worker_error_ = std::string(what) + ": " + cudaGetErrorString(e);
+    return FE_CUDA_ERROR;
+  };
+  HostTimer wt(&worker_ms_[0]);
+  cudaError_t e;
+  {
+    HostTimer w1(&worker_ms_[1]);
+    if (wait_flag(&s.h_flags[0], s.seq_fast, s_det_, &worker_error_)) return FE_CUDA_ERROR;
+    e = cudaSuccess;
+  }
+  const int ncell = s.predet_ncell, nb = s.predet_nb, nfg = s.predet_nfg;
+  s.cell_first.assign(ncell + 1, 0);
+  s.cand_sel.clear();
+  s.cand_ref.clear();
+  s.cell_kps_tap.clear();
+  s.cell_kps_first.assign(ncell + 1, 0);
+  if (ncell == 0) return FE_OK;
+  const int ntab = ncell * nb;
+  const int spec = std::min(16384, kps_cap_);
+  const int total = std::min(s.h_band[0], kps_cap_);
+  if (total > spec) {
+    e = cudaMemcpyAsync(s.h_kps + spec, s.d_kps + spec, (size_t)(total - spec) * sizeof(unsigned), cudaMemcpyDeviceToHost, s_det2_);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s_det2_);
+    if (e != cudaSuccess) return bad(e, "keypoint tail copy");
+    worker_d2h_ += (uint64_t)(total - spec) * sizeof(unsigned);
+  }
+  const int *band_off = s.h_band + 1, *band_cnt = s.h_band + 1 + ntab;
+  std::vector<KpSort> kps;
+  HostTimer *w2 = new HostTimer(&worker_ms_[2]);
+  for (int c = 0; c < ncell; c++) {
+    kps.clear();
+    for (int b = 0; b < nb; b++) {
+      const int off = band_off[c * nb + b], cnt = band_cnt[c * nb + b];
+      for (int k = 0; k < cnt && off + k < total; k++) {
+        const unsigned v = s.h_kps[off + k];
+        kps.push_back(KpSort{(float)(v >> 24), v});
+        if (taps) s.cell_kps_tap.insert(s.cell_kps_tap.end(), {(int)(v & 0xfff), (int)((v >> 12) & 0xfff), (int)(v >> 24)});
+      }
+    }
+    s.cell_kps_first[c + 1] = (int)s.cell_kps_tap.size() / 3;
+    std::sort(kps.begin(), kps.end(), compare_response);   // unstable: ties are permuted exactly like the reference
+    const float x0 = (float)s.cells[c].x, y0 = (float)s.cells[c].y;
+    for (size_t i = 0; i < (size_t)nfg && i < kps.size() && (int)s.cand_sel.size() < cand_cap_; i++)
+      s.cand_sel.push_back(Pt{(float)(kps[i].xy & 0xfff) + x0, (float)((kps[i].xy >> 12) & 0xfff) + y0});
+    s.cell_first[c + 1] = (int)s.cand_sel.size();
+  }
+  delete w2;
+  const int nc = (int)s.cand_sel.size();
+  s.cand_ref.resize(nc);
+  if (nc > 0) {
+    HostTimer w3(&worker_ms_[3]);
+    // zero-copy: the kernel refines the candidates in place in pinned host memory
+    for (int i = 0; i < nc; i++) s.h_cand_out[i] = make_float2(s.cand_sel[i].x, s.cand_sel[i].y);
+    launch_corner_subpix(s.pyr.lvl[0], s.h_cand_out, nc, s_det2_);
+    launch_signal(&s.h_flags[1], ++s.seq_subpix, s_det2_);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return bad(e, "cornerSubPix launch");
+    if (wait_flag(&s.h_flags[1], s.seq_subpix, s_det2_, &worker_error_)) return FE_CUDA_ERROR;
+    worker_launches_ += 2;
+    worker_h2d_ += (uint64_t)nc * sizeof(float2);
+    worker_d2h_ += (uint64_t)nc * sizeof(float2);
+    for (int i = 0; i < nc; i++) s.cand_ref[i] = Pt{s.h_cand_out[i].x, s.h_cand_out[i].y};
+  }
+  return FE_OK;
+}
+
+int FeContext::wait_predetection(FrameSlot &s) {
+  // normally long done (the frame was submitted at least one frame ago); spin briefly, then yield
+  int spins = 0;
+  while (true) {
+    int st = s.predet_state.load(std::memory_order_acquire);
+    if (st == 2) return FE_OK;
+    if (st == -1) {
+      last_error = "pre-detection failed: " + worker_error_;
+      return FE_CUDA_ERROR;
+    }
+    if (st == 0) {
+      last_error = "pre-detection was never queued for this frame";
+      return FE_INTERNAL;
+    }
+    if (++spins > 2000) std::this_thread::yield();
+  }
+}
+
+FeStageTimes FeContext::snapshot_times() const {
+  FeStageTimes t = times;
+  t.kernel_launches_total += worker_launches_.load();
+  t.h2d_bytes += worker_h2d_.load();
+  t.d2h_bytes += worker_d2h_.load();
+  for (int i = 0; i < 4; i++) t.host_ms[8 + i] = worker_ms_[i];
+  return t;
 }
 
 static void acc_time(FeStageTimes &t, int stage, cudaEvent_t a, cudaEvent_t b) {
@@ -284,6 +548,7 @@ static void acc_time(FeStageTimes &t, int stage, cudaEvent_t a, cudaEvent_t b) {
 }
 
 int FeContext::collect(FeFrameInfo *info) {
+  HostTimer ht(&times.host_ms[5]);
   FE_CUDA(cudaSetDevice(device_));
   if (queue_.empty()) {
     last_error = "collect: nothing submitted";
@@ -404,15 +669,9 @@ int FeContext::klt_feed(FrameSlot &cur, FeFrameInfo *info) {
   return FE_OK;
 }
 
-namespace {
-struct KpSort {  // same footprint as cv::KeyPoint; sorted with the reference's by-value comparator
-  float x, y, size, angle, response;
-  int octave, class_id;
-};
-bool compare_response(KpSort first, KpSort second) { return first.response > second.response; }  // Grider_FAST.h:57
-}  // namespace
 
 int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, std::vector<uint64_t> &ids0, FeFrameInfo *info) {
+  HostTimer ht(&times.host_ms[1]);
   const int d = cfg_.min_px_dist;
   const int cols = W_, rows = H_;
   const int close_w = (int)((float)cols / (float)d), close_h = (int)((float)rows / (float)d);
@@ -472,55 +731,31 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
       if ((int)grid_grid[(size_t)y * gx + x] < num_features_grid_req && (int)mask_grid[(size_t)y * gx + x] != 255)
         valid_locs.emplace_back(x, y);
 
-  // ---- Grider_GRID::perform_griding (Grider_GRID.h:74-180)
+  // ---- Grider_GRID::perform_griding (Grider_GRID.h:74-180).  FAST, the unstable sort, the top-num_features_grid cut
+  // and cornerSubPix do not depend on tracker state and were computed for EVERY cell when the frame was submitted
+  // (run_predetection); only the state-dependent part is left: which cells are valid and the mask test (:140-147).
   std::vector<Pt> ext;  // pts0_ext after sub-pixel refinement
-  tap_fast_.clear();
-  tap_subpix_.clear();
+  if (taps) {
+    tap_fast_.clear();
+    tap_subpix_.clear();
+  }
   if (!valid_locs.empty()) {
-    int ggx = gx, ggy = gy;
-    if (cfg_.num_features < ggx * ggy) {  // :88-92
-      double ratio = (double)ggx / (double)ggy;
-      ggy = (int)std::ceil(std::sqrt(cfg_.num_features / ratio));
-      ggx = (int)std::ceil(ggy * ratio);
+    FrameSlot &slot = const_cast<FrameSlot &>(img);
+    if (slot.predet_num_features != cfg_.num_features) {   // set_num_features() after the frame was submitted
+      int rc = wait_predetection(slot);
+      if (rc) return rc;
+      rc = enqueue_fast_all_cells(slot);
+      if (rc) return rc;
     }
-    const int nfg = (int)((double)cfg_.num_features / (double)(ggx * ggy)) + 1;
-    const int csx = cols / ggx, csy = rows / ggy;
-    if (csx <= 0 || csy <= 0) {
-      last_error = "perform_griding: zero cell size";
-      return FE_BAD_ARG;
+    {
+      HostTimer hw(&times.host_ms[7]);
+      int rc = wait_predetection(slot);
+      if (rc) return rc;
     }
-    // cells in valid_locs order; out-of-image cells are skipped (:117-118)
-    std::vector<int> cell_of_loc(valid_locs.size(), -1);
-    int ncell = 0;
-    for (size_t r = 0; r < valid_locs.size(); r++) {
-      int x = valid_locs[r].first * csx, y = valid_locs[r].second * csy;
-      if (x + csx > cols || y + csy > rows) continue;
-      if (ncell >= max_cells_) break;
-      h_cells_[ncell] = FastCell{x, y, csx, csy};
-      cell_of_loc[r] = ncell++;
-    }
-    if (ncell > 0) {
-      const int nb = (csy + kFastBandRows - 1) / kFastBandRows;
-      FE_COPY(d_cells_, h_cells_, (size_t)ncell * sizeof(FastCell), cudaMemcpyHostToDevice, s_pt_);
-      FE_CUDA(cudaMemsetAsync(d_fast_total_, 0, sizeof(unsigned), s_pt_));
-      if (timing) cudaEventRecord(ev_pt_[0], s_pt_);
-      launch_fast(img.pyr.lvl[0], d_cells_, ncell, nb, csx, cfg_.fast_threshold, d_fast_total_, d_band_off_, d_band_cnt_,
-                  d_kps_, kps_cap_, s_pt_);
-      times.kernel_launches_total++;
-      if (timing) cudaEventRecord(ev_pt_[1], s_pt_);
-      const int ntab = ncell * nb;
-      const int spec = 8192;  // speculative first chunk of the compact keypoint list
-      FE_COPY(h_band_, d_fast_total_, sizeof(unsigned), cudaMemcpyDeviceToHost, s_pt_);
-      FE_COPY(h_band_ + 1, d_band_off_, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, s_pt_);
-      FE_COPY(h_band_ + 1 + ntab, d_band_cnt_, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, s_pt_);
-      FE_COPY(h_kps_, d_kps_, (size_t)std::min(spec, kps_cap_) * sizeof(unsigned), cudaMemcpyDeviceToHost, s_pt_);
-      FE_CUDA(cudaStreamSynchronize(s_pt_));
-      if (timing) acc_time(times, FE_STAGE_FAST, ev_pt_[0], ev_pt_[1]);
-      int total = std::min(h_band_[0], kps_cap_);
-      if (total > spec) {
-        FE_COPY(h_kps_ + spec, d_kps_ + spec, (size_t)(total - spec) * sizeof(unsigned), cudaMemcpyDeviceToHost, s_pt_);
-        FE_CUDA(cudaStreamSynchronize(s_pt_));
-      }
+    if (timing && slot.predet_ncell > 0) acc_time(times, FE_STAGE_FAST, slot.ev_fast_t[0], slot.ev_fast_t[1]);
+    bool any_cell = false;
+    for (auto &loc : valid_locs) any_cell = any_cell || slot.cell_of_loc[(size_t)loc.first * gy + loc.second] >= 0;
+    if (any_cell) {
       // mask0_updated as a bit mask: caller mask > 127 or inside a (2d+1)^2 square of a kept point (:457-461)
       std::fill(occ_bits_.begin(), occ_bits_.end(), 0);
       if (!img.mask.empty())
@@ -542,49 +777,21 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
           }
         }
       }
-      const int *band_off = h_band_ + 1, *band_cnt = h_band_ + 1 + ntab;
-      std::vector<KpSort> kps;
-      std::vector<Pt> selected;
-      for (size_t r = 0; r < valid_locs.size(); r++) {
-        int c = cell_of_loc[r];
+      for (auto &loc : valid_locs) {     // cells in valid_locs order (:108-156)
+        const int c = slot.cell_of_loc[(size_t)loc.first * gy + loc.second];
         if (c < 0) continue;
-        kps.clear();
-        for (int b = 0; b < nb; b++) {
-          int off = band_off[c * nb + b], cnt = band_cnt[c * nb + b];
-          for (int k = 0; k < cnt && off + k < total; k++) {
-            unsigned v = h_kps_[off + k];
-            KpSort kp{(float)(v & 0xfff), (float)((v >> 12) & 0xfff), 7.f, -1.f, (float)(v >> 24), 0, -1};
-            kps.push_back(kp);
-            tap_fast_.insert(tap_fast_.end(), {valid_locs[r].first, valid_locs[r].second, (int)(v & 0xfff), (int)((v >> 12) & 0xfff), (int)(v >> 24)});
-          }
-        }
-        std::sort(kps.begin(), kps.end(), compare_response);  // Grider_GRID.h:128 (unstable, ties!)
-        const int x0 = h_cells_[c].x, y0 = h_cells_[c].y;
-        for (size_t i = 0; i < (size_t)nfg && i < kps.size(); i++) {  // :133-149
-          Pt p{kps[i].x + (float)x0, kps[i].y + (float)y0};
+        if (taps)
+          for (int k = slot.cell_kps_first[c]; k < slot.cell_kps_first[c + 1]; k++)
+            tap_fast_.insert(tap_fast_.end(), {loc.first, loc.second, slot.cell_kps_tap[3 * k], slot.cell_kps_tap[3 * k + 1],
+                                               slot.cell_kps_tap[3 * k + 2]});
+        for (int i = slot.cell_first[c]; i < slot.cell_first[c + 1]; i++) {   // :133-149
+          const Pt p = slot.cand_sel[i];
           if ((int)p.x < 0 || (int)p.x > cols || (int)p.y < 0 || (int)p.y > rows) continue;
-          int ix = (int)p.x, iy = (int)p.y;
+          const int ix = (int)p.x, iy = (int)p.y;
           if (iy >= rows || ix >= cols) continue;  // the reference would read out of bounds here; cannot happen
           if ((occ_bits_[(size_t)iy * bw + (ix >> 6)] >> (ix & 63)) & 1ull) continue;
-          selected.push_back(p);
-        }
-      }
-      // cv::cornerSubPix on every selected point (:163-179)
-      int ns = std::min((int)selected.size(), max_pts_);
-      if (ns > 0) {
-        for (int i = 0; i < ns; i++) h_pts0_[i] = make_float2(selected[i].x, selected[i].y);
-        FE_COPY(d_pts0_, h_pts0_, (size_t)ns * sizeof(float2), cudaMemcpyHostToDevice, s_pt_);
-        if (timing) cudaEventRecord(ev_pt_[2], s_pt_);
-        launch_corner_subpix(img.pyr.lvl[0], d_pts0_, ns, s_pt_);
-        times.kernel_launches_total++;
-        if (timing) cudaEventRecord(ev_pt_[3], s_pt_);
-        FE_COPY(h_pts1_, d_pts0_, (size_t)ns * sizeof(float2), cudaMemcpyDeviceToHost, s_pt_);
-        FE_CUDA(cudaStreamSynchronize(s_pt_));
-        if (timing) acc_time(times, FE_STAGE_SUBPIX, ev_pt_[2], ev_pt_[3]);
-        ext.resize(ns);
-        for (int i = 0; i < ns; i++) {
-          ext[i] = Pt{h_pts1_[i].x, h_pts1_[i].y};
-          tap_subpix_.insert(tap_subpix_.end(), {selected[i].x, selected[i].y, ext[i].x, ext[i].y});
+          ext.push_back(slot.cand_ref[i]);      // cornerSubPix result of exactly this point (:163-179)
+          if (taps) tap_subpix_.insert(tap_subpix_.end(), {p.x, p.y, slot.cand_ref[i].x, slot.cand_ref[i].y});
         }
       }
     }
@@ -606,6 +813,7 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
 
 int FeContext::perform_matching(const FrameSlot &f0, const FrameSlot &f1, std::vector<Pt> &pts0, std::vector<Pt> &pts1,
                                 std::vector<uint8_t> &mask_out, bool &mask_empty, FeFrameInfo *info) {
+  HostTimer ht(&times.host_ms[2]);
   mask_out.clear();
   mask_empty = true;
   const int n = (int)pts0.size();
@@ -628,9 +836,11 @@ int FeContext::perform_matching(const FrameSlot &f0, const FrameSlot &f1, std::v
     }
   }
   const int nt = std::min(n, max_pts_) + ns;
-  for (int i = 0; i < n && i < max_pts_; i++) h_pts0_[i] = make_float2(pts0[i].x, pts0[i].y);
-  FE_COPY(d_pts0_, h_pts0_, (size_t)nt * sizeof(float2), cudaMemcpyHostToDevice, s_pt_);
-  FE_COPY(d_pts1_, d_pts0_, (size_t)nt * sizeof(float2), cudaMemcpyDeviceToDevice, s_pt_);
+  for (int i = 0; i < n && i < max_pts_; i++) {
+    h_pts0_[i] = make_float2(pts0[i].x, pts0[i].y);
+    h_pts1_[i] = h_pts0_[i];   // OPTFLOW_USE_INITIAL_FLOW with pts1 = pts0 (:134-138)
+  }
+  for (int k = 0; k < ns; k++) h_pts1_[n + k] = h_pts0_[n + k];
   LkParams prm;
   prm.win = cfg_.win_size;
   prm.max_level = cfg_.pyr_levels;
@@ -639,31 +849,43 @@ int FeContext::perform_matching(const FrameSlot &f0, const FrameSlot &f1, std::v
   prm.min_eig = 1e-4f;
   prm.undistort = 1;
   for (int i = 0; i < 4; i++) { prm.K[i] = cfg_.K[i]; prm.D[i] = cfg_.D[i]; }
+  // The feature arrays are a few KB: the kernel reads and writes them in pinned, device-mapped host memory directly
+  // (no copy-engine operation queued behind the next frame's 700 KB upload, one synchronisation per frame).
+  times.h2d_bytes += (size_t)nt * 2 * sizeof(float2);
+  times.d2h_bytes += (size_t)nt * (3 * sizeof(float2) + 1);
   if (timing) cudaEventRecord(ev_pt_[4], s_pt_);
-  launch_lk(f0.pyr, f1.pyr, d_pts0_, d_pts1_, d_status_, d_p0n_, d_p1n_, nt, prm, s_pt_);
+  launch_lk(f0.pyr, f1.pyr, h_pts0_, h_pts1_, h_status_, h_p0n_, h_p1n_, nt, prm, s_pt_);
   times.kernel_launches_total++;
   if (timing) cudaEventRecord(ev_pt_[5], s_pt_);
-  FE_COPY(h_pts1_, d_pts1_, (size_t)nt * sizeof(float2), cudaMemcpyDeviceToHost, s_pt_);
-  FE_COPY(h_status_, d_status_, (size_t)nt, cudaMemcpyDeviceToHost, s_pt_);
-  FE_COPY(h_p0n_, d_p0n_, (size_t)nt * sizeof(float2), cudaMemcpyDeviceToHost, s_pt_);
-  FE_COPY(h_p1n_, d_p1n_, (size_t)nt * sizeof(float2), cudaMemcpyDeviceToHost, s_pt_);
-  FE_CUDA(cudaStreamSynchronize(s_pt_));
-  if (timing) acc_time(times, FE_STAGE_LK, ev_pt_[4], ev_pt_[5]);
+  launch_signal(h_flag_lk_, ++seq_lk_, s_pt_);
+  FE_CUDA(cudaGetLastError());
+  {
+    int rc = wait_flag(h_flag_lk_, seq_lk_, s_pt_, &last_error);
+    if (rc) return rc;
+  }
+  if (timing) {
+    FE_CUDA(cudaEventSynchronize(ev_pt_[5]));
+    acc_time(times, FE_STAGE_LK, ev_pt_[4], ev_pt_[5]);
+  }
 
   // RANSAC gate on the normalised coordinates (:869-873)
   const double max_focal = std::max(cfg_.K[0], cfg_.K[1]);
   std::vector<uint8_t> mask_rsc(n, 0);
   int mask_valid = 0;
-  int n_in = ransac_fundamental(reinterpret_cast<const float *>(h_p0n_), reinterpret_cast<const float *>(h_p1n_), n,
-                                2.0 / max_focal, 0.999, mask_rsc.data(), &mask_valid);
+  int n_in;
+  {
+    HostTimer hr(&times.host_ms[3]);
+    n_in = ransac_fundamental(reinterpret_cast<const float *>(h_p0n_), reinterpret_cast<const float *>(h_p1n_), n,
+                              2.0 / max_focal, 0.999, mask_rsc.data(), &mask_valid);
+  }
   mask_out.resize(n);
   int n_klt = 0;
-  tap_lk_.clear();
+  if (taps) tap_lk_.clear();
   for (int i = 0; i < n; i++) {  // :876-885
     mask_out[i] = (h_status_[i] && mask_valid && mask_rsc[i]) ? 1 : 0;
     n_klt += h_status_[i] ? 1 : 0;
     pts1[i] = Pt{h_pts1_[i].x, h_pts1_[i].y};
-    tap_lk_.insert(tap_lk_.end(), {pts0[i].x, pts0[i].y, pts1[i].x, pts1[i].y, (float)h_status_[i], (float)(mask_valid && mask_rsc[i])});
+    if (taps) tap_lk_.insert(tap_lk_.end(), {pts0[i].x, pts0[i].y, pts1[i].x, pts1[i].y, (float)h_status_[i], (float)(mask_valid && mask_rsc[i])});
   }
   for (int k = 0; k < ns; k++) {
     sample_uv.insert(sample_uv.end(), {h_pts0_[n + k].x, h_pts0_[n + k].y, h_pts1_[n + k].x, h_pts1_[n + k].y});
@@ -715,13 +937,18 @@ int line_classification(const float4 &line, const double vp[6]) {  // :318-333
 }  // namespace
 
 int FeContext::lsd_feed(FrameSlot &cur, FeFrameInfo *info) {
-  FE_CUDA(cudaEventSynchronize(cur.ev_lines));
+  HostTimer ht(&times.host_ms[4]);
+  {
+    HostTimer hw(&times.host_ms[6]);
+    int rc = wait_flag(&cur.h_flags[2], cur.seq_lines, cur.s_line, &last_error);
+    if (rc) return rc;
+  }
   int nseg = std::min(cur.h_fld_counts[1], cur.fld.out_cap);
   if (nseg > 1024) {
-    FE_COPY(cur.h_segs + 1024, cur.fld.out + 1024, (size_t)(nseg - 1024) * sizeof(float4), cudaMemcpyDeviceToHost, s_line_);
-    FE_CUDA(cudaStreamSynchronize(s_line_));
+    FE_COPY(cur.h_segs + 1024, cur.fld.out + 1024, (size_t)(nseg - 1024) * sizeof(float4), cudaMemcpyDeviceToHost, cur.s_line);
+    FE_CUDA(cudaStreamSynchronize(cur.s_line));
   }
-  tap_fld_.assign(reinterpret_cast<float *>(cur.h_segs), reinterpret_cast<float *>(cur.h_segs) + 4 * (size_t)nseg);
+  if (taps) tap_fld_.assign(reinterpret_cast<float *>(cur.h_segs), reinterpret_cast<float *>(cur.h_segs) + 4 * (size_t)nseg);
   // perform_detection_monocular (:194-236): x2, FilterShortLines(40), a fresh id for EVERY detected line
   std::vector<float4> lines_new;
   std::vector<uint64_t> ids_new;
@@ -742,19 +969,28 @@ int FeContext::lsd_feed(FrameSlot &cur, FeFrameInfo *info) {
   std::vector<std::vector<Pt>> positions;
   std::vector<float4> filt_lines;
   std::vector<uint64_t> filt_ids;
+  const int npt = (int)points.size();
+  std::vector<float> spx(npt), spy(npt);
+  std::vector<uint8_t> pass(npt + 8);
+  for (int j = 0; j < npt; j++) {
+    spx[j] = points[j].x;
+    spy[j] = points[j].y;
+  }
   for (size_t i = 0; i < lines_new.size(); i++) {
     const float4 &l = lines_new[i];
-    double lx1 = l.x, lx2 = l.y, ly1 = l.z, ly2 = l.w;  // index mix-up reproduced (:754-757)
-    double min_lx = lx1, max_lx = lx2, min_ly = ly1, max_ly = ly2;
+    float lx1 = l.x, lx2 = l.y, ly1 = l.z, ly2 = l.w;  // index mix-up reproduced (:754-757)
+    float min_lx = lx1, max_lx = lx2, min_ly = ly1, max_ly = ly2;
     if (lx1 > lx2) std::swap(min_lx, max_lx);
     if (ly1 > ly2) std::swap(min_ly, max_ly);
+    const float pa = l.w - l.y, pb = l.x - l.z, pc = l.z * l.y - l.x * l.w;
+    const float plen2 = 36.f * (pa * pa + pb * pb);
+    if (!line_candidates(spx.data(), spy.data(), npt, min_lx, max_lx, min_ly, max_ly, pa, pb, pc, plen2, pass.data())) continue;
     std::map<int, double> pol;
     std::vector<Pt> feats;
     bool find_point = false;
-    for (size_t j = 0; j < points.size(); j++) {
-      float x = points[j].x, y = points[j].y;
-      if (x < min_lx || x > max_lx || y < min_ly || y > max_ly) continue;
-      float dist = point_line_distance(l, x, y);
+    for (int j = 0; j < npt; j++) {
+      if (!pass[j]) continue;
+      float dist = point_line_distance(l, spx[j], spy[j]);
       if (dist > 5) continue;
       pol[(int)pids[j]] = dist;
       feats.push_back(points[j]);
@@ -927,7 +1163,12 @@ int FeContext::set_state(const void *buf, size_t n_bytes) {
     launch_eq_pyr1(s.raw, d_hist_, d_counters_, 0, s.pyr.lvl[0], s.pyr.n > 1 ? s.pyr.lvl[1] : DevImage(),
                    cfg_.use_lines ? s.half : DevImage(), s_img_);
     if (s.pyr.n > 2) launch_pyr_rest(s.pyr, d_counters_ + 1, s_img_);
+    FE_CUDA(cudaEventRecord(s.ev_l0, s_img_));
     FE_CUDA(cudaStreamSynchronize(s_img_));
+    {
+      int rc = enqueue_fast_all_cells(s);
+      if (rc) return rc;
+    }
     if (hd.has_mask) {
       s.mask.resize((size_t)W_ * H_);
       get(s.mask.data(), (size_t)W_ * H_);

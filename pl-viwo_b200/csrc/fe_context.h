@@ -4,9 +4,14 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <condition_variable>
 #include <cstdint>
+#include <deque>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/plviwo_fe.h"
@@ -18,6 +23,8 @@ struct Pt {
   float x, y;
 };
 
+int line_candidates(const float *px, const float *py, int n, float min_lx, float max_lx, float min_ly, float max_ly, float pa,
+                    float pb, float pc, float plen2, uint8_t *pass);
 int ransac_fundamental(const float *m1, const float *m2, int count, double threshold, double confidence, uint8_t *mask,
                        int *mask_valid);
 
@@ -35,9 +42,31 @@ struct FrameSlot {
   double vp[6] = {0, 0, 0, 0, 0, 0};
   bool has_vp = false;
   bool busy = false;
+  int index = 0;
   cudaEvent_t ev_pyr = nullptr, ev_lines = nullptr;
+  cudaStream_t s_line = nullptr;   // per-slot stream: line extraction of different frames overlaps
   cudaEvent_t ev_t[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool timed = false;
+
+  // ---- pre-detection: everything perform_griding computes that does NOT depend on tracker state.  FAST runs on
+  // every grid cell of the frame as soon as level 0 exists; a worker thread sorts each cell's corners with the
+  // reference's std::sort, takes the first num_features_grid of each and refines them (cornerSubPix).  The top-off
+  // detection at collect() time then only applies the state-dependent tests (valid cells, mask, min distance).
+  unsigned *d_fast_total = nullptr, *d_kps = nullptr, *h_kps = nullptr;
+  int *d_band_off = nullptr, *d_band_cnt = nullptr, *h_band = nullptr;   // h_band: [total, off..., cnt...]
+  float2 *d_cand = nullptr, *h_cand_in = nullptr, *h_cand_out = nullptr;
+  cudaEvent_t ev_l0 = nullptr, ev_fast = nullptr;
+  cudaEvent_t ev_fast_t[2] = {nullptr, nullptr};
+  int *h_flags = nullptr;                 // pinned: [0] FAST done, [1] sub-pixel done, [2] lines done (sequence numbers)
+  int seq_fast = 0, seq_subpix = 0, seq_lines = 0;
+  std::atomic<int> predet_state{0};        // 0 none, 1 queued, 2 ready, -1 failed
+  int predet_nfg = 0, predet_ncell = 0, predet_nb = 0, predet_num_features = -1;
+  std::vector<FastCell> cells;            // cell layout this frame's FAST ran on
+  std::vector<int> cell_of_loc;
+  std::vector<int> cell_first;             // first candidate of cell c in cand_sel / cand_ref (size ncell + 1)
+  std::vector<Pt> cand_sel, cand_ref;      // top num_features_grid corners of every cell, before / after refinement
+  std::vector<int32_t> cell_kps_tap;       // optional (taps on): every cell's FAST list as (x, y, score), cell_kps_first
+  std::vector<int> cell_kps_first;
 };
 
 class FeContext {
@@ -72,12 +101,26 @@ class FeContext {
   std::vector<float> sample_uv;
   std::vector<uint8_t> sample_status;
   bool timing = false;
+  bool taps = false;     // record the debug taps (FAST lists, sub-pixel, LK, FLD) — off on the hot path
   FeStageTimes times{};
+  FeStageTimes snapshot_times() const;
+  void reset_times() {
+    times = FeStageTimes{};
+    worker_launches_ = 0; worker_h2d_ = 0; worker_d2h_ = 0;
+    for (double &v : worker_ms_) v = 0;
+  }
 
  private:
   int fail(cudaError_t e, const char *what);
+  int spin_sync(cudaStream_t st);
+  int wait_flag(volatile int *flag, int value, cudaStream_t st, std::string *err);
   int alloc_image(DevImage &im, int w, int h);
   int enqueue_frame_independent(FrameSlot &s);
+  void layout_cells();                       // all grid cells of the frame (Grider_GRID geometry)
+  int enqueue_fast_all_cells(FrameSlot &s);  // main thread, stream s_det_
+  int run_predetection(FrameSlot &s);        // worker thread: sort / top-k / cornerSubPix
+  void worker_main();
+  int wait_predetection(FrameSlot &s);
   // TrackKLT
   int klt_feed(FrameSlot &cur, FeFrameInfo *info);
   int perform_detection(const FrameSlot &img, std::vector<Pt> &pts, std::vector<uint64_t> &ids, FeFrameInfo *info);
@@ -90,8 +133,8 @@ class FeContext {
   FeConfig cfg_;
   int device_;
   int W_, H_;
-  cudaStream_t s_img_ = nullptr, s_pt_ = nullptr, s_line_ = nullptr;
-  std::vector<FrameSlot> slots_;
+  cudaStream_t s_img_ = nullptr, s_pt_ = nullptr;
+  std::deque<FrameSlot> slots_;           // deque: FrameSlot holds an atomic and never moves
   std::vector<int> queue_;      // submitted, not yet collected (slot indices, FIFO)
   int last_slot_ = -1;          // slot holding the previous frame's pyramid (img_pyramid_last)
   unsigned *d_hist_ = nullptr, *d_counters_ = nullptr;
@@ -106,12 +149,23 @@ class FeContext {
   std::vector<std::map<int, double>> pol_last_;
   uint64_t line_currid_ = 1;
 
-  // ---- detection scratch
-  FastCell *d_cells_ = nullptr, *h_cells_ = nullptr;
-  unsigned *d_fast_total_ = nullptr, *d_kps_ = nullptr, *h_kps_ = nullptr;
-  int *d_band_off_ = nullptr, *d_band_cnt_ = nullptr, *h_band_ = nullptr;  // h_band_: [total, off..., cnt...]
-  int max_cells_ = 0, max_bands_ = 0, kps_cap_ = 0;
+  // ---- detection: static cell layout + worker
+  FastCell *d_cells_ = nullptr;
+  std::vector<FastCell> cells_;            // every in-image cell, x-major like valid_locs
+  std::vector<int> cell_of_loc_;           // caller-grid (x * grid_y + y) -> index into cells_ or -1
+  int cells_nfg_ = 0, cells_nb_ = 0, cells_csx_ = 0, cells_csy_ = 0, cells_num_features_ = -1;
+  int max_cells_ = 0, max_bands_ = 0, kps_cap_ = 0, cand_cap_ = 0;
+  bool cells_uploaded_ = false;
   std::vector<uint64_t> occ_bits_;
+  cudaStream_t s_det_ = nullptr, s_det2_ = nullptr;
+  std::thread worker_;
+  std::mutex wmu_;
+  std::condition_variable wcv_;
+  std::deque<int> wqueue_;
+  bool wstop_ = false;
+  std::atomic<uint64_t> worker_launches_{0}, worker_h2d_{0}, worker_d2h_{0};
+  std::string worker_error_;
+  double worker_ms_[4] = {0, 0, 0, 0};
   // ---- tracking scratch
   int max_pts_ = 0;
   float2 *d_pts0_ = nullptr, *d_pts1_ = nullptr, *d_p0n_ = nullptr, *d_p1n_ = nullptr;
@@ -119,6 +173,9 @@ class FeContext {
   float2 *h_pts0_ = nullptr, *h_pts1_ = nullptr, *h_p0n_ = nullptr, *h_p1n_ = nullptr;
   uint8_t *h_status_ = nullptr;
   cudaEvent_t ev_pt_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_sync_ = nullptr;
+  int *h_flag_lk_ = nullptr;
+  int seq_lk_ = 0;
   // ---- taps
   std::vector<int32_t> tap_fast_;
   std::vector<float> tap_lk_, tap_subpix_, tap_fld_;

@@ -26,8 +26,10 @@ void launch_hist(const DevImage &src, unsigned *d_hist, cudaStream_t s);
 // half = exact 2x2 INTER_AREA of level 0 (may be null).  d_hist is cleared for the next frame by the last CTA.
 void launch_eq_pyr1(const DevImage &src, unsigned *d_hist, unsigned *d_counter, int equalize, const DevImage &l0,
                     const DevImage &l1, const DevImage &half, cudaStream_t s);
-// levels 2..n-1 in ONE launch: level 2 by all CTAs, the remaining (tiny) levels by the last CTA to finish.
+// levels 2..n-1, one short launch per level (4 outputs per thread).
 void launch_pyr_rest(const Pyramid &pyr, unsigned *d_counter, cudaStream_t s);
+
+void launch_signal(int *host_flag, int value, cudaStream_t s);
 
 // ---- FAST (kernels_fast.cu) ------------------------------------------------------------------------------
 struct FastCell {
@@ -59,14 +61,20 @@ void launch_undistort(const float2 *d_pts, float2 *d_out, int n, const double K[
 struct FldBuffers {
   unsigned *edges = nullptr;      // bit-packed edge map, words_per_row * h
   int words_per_row = 0;
-  int2 *chain_pts = nullptr;      // all chain points, chain after chain (capacity = w * h)
-  int *chain_off = nullptr;       // chain start offsets (capacity max_chains + 1)
-  int *n_chains = nullptr;        // [0] = number of chains kept, [1] = number of segments
+  int *label = nullptr;           // connected-component label per pixel (root = smallest raster index), -1 = no edge
+  int *cnt = nullptr;             // pixels per component (at the root)
+  int *bbox = nullptr;            // 3 planes at the root: max y, min x, max x (min y is the root's row)
+  int *comp_root = nullptr;       // roots of the components big enough to hold a chain
+  int *counters = nullptr;        // [0] components [1] - [2] chain-point cursor [3] chains [4] segments
+  int2 *chain_pts = nullptr;      // chain points, one slice per component (capacity = w * h)
+  int *chain_seed = nullptr, *chain_off = nullptr, *chain_len = nullptr, *order = nullptr;
   int max_chains = 0;
-  float4 *segs = nullptr;         // per-chain segment slots: chain c owns [c * kSegsPerChain ...)
-  int *seg_cnt = nullptr;         // segments found in chain c
+  float4 *segs = nullptr;         // segment slots (chain_off / 21 + j)
+  int *seg_cnt = nullptr;         // [0, max_chains): segments per chain in seed order; [max_chains, 2 max_chains): slot base
   float4 *out = nullptr;          // compacted, ordered segments
   int out_cap = 0;
+  int alloc(int w, int h, int length_threshold, int out_capacity);   // returns 0 on success
+  void release();
 };
 constexpr int kSegsPerChainDiv = 21;  // a chain of n points yields at most n / 21 + 1 segments
 void launch_canny(const DevImage &half, float th_low, float th_high, FldBuffers &fb, cudaStream_t s);

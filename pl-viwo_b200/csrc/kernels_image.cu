@@ -243,75 +243,61 @@ void launch_eq_pyr1(const DevImage &src, unsigned *d_hist, unsigned *d_counter, 
 }
 
 // ---------------------------------------------------------------------------------------- remaining levels
-__device__ __forceinline__ int pyr_down_px(const uint8_t *__restrict__ src, int sw, int sh, int spitch, int x, int y,
-                                           bool cg) {
-  int acc = 0;
+constexpr int kRestThreads = 256;
+
+// One level from the previous one: a thread produces 4 horizontally adjacent outputs (one 32-bit store).  The upper
+// levels are tiny (320x140 and below), L2 resident, and each costs one short launch; an earlier version that let the
+// last CTA of level 2 compute all remaining levels alone measured 51 us, this is ~3 us per level.
+__global__ void __launch_bounds__(kRestThreads)
+    k_pyr_down(const uint8_t *__restrict__ src, int sw, int sh, int spitch, uint8_t *__restrict__ dst, int dw, int dh,
+               int dpitch) {
+  const int quads = (dw + 3) >> 2;
+  const int i = blockIdx.x * kRestThreads + threadIdx.x;
+  if (i >= quads * dh) return;
+  const int y = i / quads, x0 = (i - y * quads) << 2;
+  // 5 source rows x 11 source columns feed 4 outputs
+  int col[11];
+#pragma unroll
+  for (int k = 0; k < 11; k++) col[k] = reflect101(2 * x0 + k - 2, sw);
+  int hs[4] = {0, 0, 0, 0};
   const int wgt[5] = {1, 4, 6, 4, 1};
 #pragma unroll
   for (int j = 0; j < 5; j++) {
-    int ry = reflect101(2 * y + j - 2, sh);
-    const uint8_t *row = src + (size_t)ry * spitch;
-    int hsum = 0;
+    const uint8_t *row = src + (size_t)reflect101(2 * y + j - 2, sh) * spitch;
+    int v[11];
 #pragma unroll
-    for (int i = 0; i < 5; i++) {
-      int rx = reflect101(2 * x + i - 2, sw);
-      int v = cg ? (int)__ldcg(row + rx) : (int)row[rx];
-      hsum += wgt[i] * v;
-    }
-    acc += wgt[j] * hsum;
+    for (int k = 0; k < 11; k++) v[k] = row[col[k]];
+#pragma unroll
+    for (int o = 0; o < 4; o++)
+      hs[o] += wgt[j] * (v[2 * o] + 4 * v[2 * o + 1] + 6 * v[2 * o + 2] + 4 * v[2 * o + 3] + v[2 * o + 4]);
   }
-  return (acc + 128) >> 8;
+  uint8_t *d = dst + (size_t)y * dpitch + x0;
+  if (x0 + 4 <= dw) {
+    unsigned packed = 0;
+#pragma unroll
+    for (int o = 0; o < 4; o++) packed |= (unsigned)((hs[o] + 128) >> 8) << (8 * o);
+    *reinterpret_cast<unsigned *>(d) = packed;
+  } else {
+    for (int o = 0; x0 + o < dw; o++) d[o] = (uint8_t)((hs[o] + 128) >> 8);
+  }
 }
 
-struct PyrRestArgs {
-  uint8_t *p[kMaxLevels];
-  int w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels];
-  int n;
-};
-
-constexpr int kRestThreads = 256;
-constexpr int kRestTileW = 32, kRestTileH = 8;
-
-__global__ void __launch_bounds__(kRestThreads) k_pyr_rest(PyrRestArgs a, unsigned *__restrict__ counter) {
-  __shared__ unsigned s_last;
-  {  // level 2 from level 1: one output per thread
-    int x = blockIdx.x * kRestTileW + (threadIdx.x & (kRestTileW - 1));
-    int y = blockIdx.y * kRestTileH + (threadIdx.x / kRestTileW);
-    if (x < a.w[2] && y < a.h[2]) a.p[2][(size_t)y * a.pitch[2] + x] = (uint8_t)pyr_down_px(a.p[1], a.w[1], a.h[1], a.pitch[1], x, y, false);
-  }
-  if (a.n <= 3) return;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    s_last = (atomicAdd(counter, 1u) == gridDim.x * gridDim.y - 1) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int l = 3; l < a.n; l++) {
-    int n = a.w[l] * a.h[l];
-    for (int i = threadIdx.x; i < n; i += kRestThreads) {
-      int y = i / a.w[l], x = i - y * a.w[l];
-      a.p[l][(size_t)y * a.pitch[l] + x] = (uint8_t)pyr_down_px(a.p[l - 1], a.w[l - 1], a.h[l - 1], a.pitch[l - 1], x, y, true);
-    }
-    __threadfence();
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *counter = 0;
+// Completion signal: a one-thread kernel at the tail of a stream writes a sequence number into pinned host memory.
+// The host threads poll that word instead of calling into the driver (cudaEventQuery / cudaStreamSynchronize from
+// two threads serialise on the context lock and cost 10-100 us each).
+__global__ void k_signal(volatile int *flag, int value) {
+  *flag = value;
+  __threadfence_system();
 }
+void launch_signal(int *host_flag, int value, cudaStream_t s) { k_signal<<<1, 1, 0, s>>>(host_flag, value); }
 
 void launch_pyr_rest(const Pyramid &pyr, unsigned *d_counter, cudaStream_t s) {
-  if (pyr.n <= 2) return;
-  PyrRestArgs a;
-  a.n = pyr.n;
-  for (int l = 0; l < pyr.n; l++) {
-    a.p[l] = pyr.lvl[l].p;
-    a.w[l] = pyr.lvl[l].w;
-    a.h[l] = pyr.lvl[l].h;
-    a.pitch[l] = pyr.lvl[l].pitch;
+  (void)d_counter;
+  for (int l = 2; l < pyr.n; l++) {
+    const DevImage &a = pyr.lvl[l - 1], &b = pyr.lvl[l];
+    int n = ((b.w + 3) >> 2) * b.h;
+    k_pyr_down<<<(n + kRestThreads - 1) / kRestThreads, kRestThreads, 0, s>>>(a.p, a.w, a.h, a.pitch, b.p, b.w, b.h, b.pitch);
   }
-  dim3 grid((a.w[2] + kRestTileW - 1) / kRestTileW, (a.h[2] + kRestTileH - 1) / kRestTileH);
-  k_pyr_rest<<<grid, kRestThreads, 0, s>>>(a, d_counter);
 }
 
 }  // namespace plviwo

@@ -7,14 +7,19 @@
 //                                    maximum above the threshold is an edge and no hysteresis walk is needed
 //   lineDetection / getPointChain / extractSegments / additionalOperationsOnSegment    Appendix B
 //
-// Structure.  The chain walk is order dependent (visited pixels are consumed, seeds are taken in raster order),
-// so it stays sequential per frame: ONE warp owns the whole bit-packed edge map in shared memory (640x280 bits =
-// 22 KB), its lanes scan for the next seed together and lane 0 walks the chain with a 2 KB decision table.
-// Frames/streams run concurrently on different SMs.  Everything after the walk is parallel over chains (one
-// thread per chain fits segments with running double-precision sums, identical to refitting from scratch) and
-// an ordered compaction restores the reference's output order.
+// Structure.  The chain walk is order dependent (visited pixels are consumed, seeds are taken in raster order), but
+// a walk never leaves the 8-connected component of its seed, so different components cannot influence each other:
+// the sequential algorithm is exactly "for every connected component, run the raster-order walk on that component
+// alone; then list all chains by the raster index of their seed".  So
+//   1. connected components of the edge map by union-find (label = smallest raster index = the component's first seed),
+//   2. one warp per component with >= length_threshold + 1 pixels: it copies the component's pixels into a private
+//      bit map in shared memory, its lanes scan for the next seed together and lane 0 walks the chain,
+//   3. chains are ranked by seed index, segments are fitted by one thread per chain (running double-precision sums,
+//      identical to refitting from scratch) and an ordered compaction restores the reference's output order.
+// The first version walked the whole frame with a single thread: 14.6 ms per 640x280 frame.
 #include "fe_kernels.h"
 
+#include <algorithm>
 #include <cmath>
 
 namespace plviwo {
@@ -105,131 +110,250 @@ void launch_unpack_edges(const FldBuffers &fb, int w, int h, uint8_t *d_out, cud
   k_unpack_edges<<<grid, 256, 0, s>>>(fb.edges, fb.words_per_row, w, h, d_out);
 }
 
-// ------------------------------------------------------------------------------------------- chain walk
-// Decision table of getPointChain for step > 0: [direction + 3][8-neighbour mask] -> neighbour index, 8 = stop.
-__constant__ uint8_t c_chain_lut[8 * 256];
-static bool g_chain_lut_ready[64] = {false};
-
-static void build_chain_lut(uint8_t *lut) {
-  for (int d = -3; d <= 4; d++) {
-    for (int mask = 0; mask < 256; mask++) {
-      float min_dir_diff = 7.0f;
-      int chosen = 8;
-      for (int i = 0; i < 8; i++) {
-        if (!((mask >> i) & 1)) continue;
-        int curr_dir = i > 4 ? i - 8 : i;
-        int dir_diff = std::abs(curr_dir - d);
-        dir_diff = dir_diff > 4 ? 8 - dir_diff : dir_diff;
-        if (dir_diff <= min_dir_diff) {
-          min_dir_diff = (float)dir_diff;
-          chosen = i;
-        }
-      }
-      lut[(d + 3) * 256 + mask] = (uint8_t)(min_dir_diff < 2 ? chosen : 8);
-    }
+// --------------------------------------------------------------------------- connected components (8-conn)
+__device__ __forceinline__ int ccl_find(const int *parent, int i) {
+  int p = __ldcg(parent + i);
+  while (p != i) {
+    i = p;
+    p = __ldcg(parent + i);
+  }
+  return i;
+}
+__device__ __forceinline__ void ccl_union(int *parent, int a, int b) {
+  while (true) {
+    a = ccl_find(parent, a);
+    b = ccl_find(parent, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }   // link the larger root under the smaller index
+    int old = atomicMin(parent + a, b);
+    if (old == a) return;
+    a = old;
   }
 }
 
-// padded bitmap in shared memory: row stride ws words, 1 zero row above and below, x shifted by +1
+__global__ void k_ccl_init(const unsigned *__restrict__ edges, int words_per_row, int w, int h, int *__restrict__ label,
+                           int *__restrict__ cnt, int *__restrict__ bbox /* maxy, minx, maxx planes */,
+                           int *__restrict__ counters) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 8) counters[i] = 0;
+  if (i >= w * h) return;
+  const int y = i / w, x = i - y * w;
+  const bool e = (edges[(size_t)y * words_per_row + (x >> 5)] >> (x & 31)) & 1u;
+  label[i] = e ? i : -1;
+  cnt[i] = 0;
+  bbox[i] = 0;                 // max y
+  bbox[w * h + i] = 0x7fffffff;  // min x
+  bbox[2 * w * h + i] = -1;    // max x
+}
+
+__global__ void k_ccl_merge(int w, int h, int *__restrict__ label) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w * h) return;
+  if (label[i] < 0) return;
+  const int y = i / w, x = i - y * w;
+  // backward half of the 8-neighbourhood: W, NW, N, NE
+  if (x > 0 && label[i - 1] >= 0) ccl_union(label, i, i - 1);
+  if (y > 0) {
+    if (x > 0 && label[i - w - 1] >= 0) ccl_union(label, i, i - w - 1);
+    if (label[i - w] >= 0) ccl_union(label, i, i - w);
+    if (x < w - 1 && label[i - w + 1] >= 0) ccl_union(label, i, i - w + 1);
+  }
+}
+
+// flatten + per-component pixel count and bounding box (warp-aggregated atomics keyed by the root)
+__global__ void k_ccl_flatten(int w, int h, int *__restrict__ label, int *__restrict__ cnt, int *__restrict__ bbox) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int root = -1;
+  if (i < w * h && label[i] >= 0) {
+    root = ccl_find(label, i);
+    label[i] = root;
+  }
+  const unsigned active = __ballot_sync(0xffffffffu, root >= 0);
+  if (root < 0) return;
+  const int y = i / w, x = i - y * w;
+  const unsigned peers = __match_any_sync(active, root);
+  const int n = __popc(peers);
+  const int ymax = __reduce_max_sync(peers, y);
+  const int xmin = __reduce_min_sync(peers, x);
+  const int xmax = __reduce_max_sync(peers, x);
+  if ((threadIdx.x & 31) == __ffs(peers) - 1) {
+    atomicAdd(cnt + root, n);
+    atomicMax(bbox + root, ymax);
+    atomicMin(bbox + w * h + root, xmin);
+    atomicMax(bbox + 2 * w * h + root, xmax);
+  }
+}
+
+// components large enough to hold a chain of length_threshold + 1 pixels
+__global__ void k_ccl_roots(int w, int h, const int *__restrict__ label, const int *__restrict__ cnt, int min_pixels,
+                            int *__restrict__ comp_root, int *__restrict__ counters, int max_comps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w * h) return;
+  if (label[i] == i && cnt[i] >= min_pixels) {
+    int k = atomicAdd(counters + 0, 1);
+    if (k < max_comps) comp_root[k] = i;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- chain walk
+// getPointChain for step > 0: among the set neighbours take the one whose direction is closest to the running
+// direction (circular difference; ties go to the LATER neighbour index), accept only a difference < 2.
+__device__ __forceinline__ int choose_neighbour(unsigned mask, int direction) {
+  const int i0 = direction < 0 ? direction + 8 : direction;      // neighbour index with difference 0
+  if ((mask >> i0) & 1u) return i0;
+  const int ia = (i0 + 1) & 7, ib = (i0 + 7) & 7;               // the two neighbours with difference 1
+  const bool sa = (mask >> ia) & 1u, sb = (mask >> ib) & 1u;
+  if (sa && sb) return max(ia, ib);
+  if (sa) return ia;
+  if (sb) return ib;
+  return 8;
+}
+
+// padded private bit map: row stride ws words, 1 zero row above and below, local x stored at bit x + 1
 __device__ __forceinline__ unsigned row3(const unsigned *bm, int ws, int py, int x) {
-  // bits (x-1, x, x+1) of padded row py, as the low 3 bits (x in image coordinates, stored at bit x + 1)
   const unsigned *r = bm + py * ws;
-  int wi = x >> 5, sh = x & 31;  // bit position of (x - 1) in padded coords is x
+  const int wi = x >> 5, sh = x & 31;
   return __funnelshift_r(r[wi], r[wi + 1], sh) & 7u;
 }
 
-__global__ void __launch_bounds__(32)
-    k_fld_walk(const unsigned *__restrict__ edges, int words_per_row, int w, int h, int length_threshold,
-               int2 *__restrict__ chain_pts, int *__restrict__ chain_off, int *__restrict__ n_chains, int max_chains) {
+// counters: [0] components, [1] next component to take, [2] chain-point cursor, [3] chains, [4] segments
+constexpr int kWalkThreads = 128;
+constexpr int kWalkCtas = 48;   // per frame; components are pulled from an atomic queue
+
+__global__ void __launch_bounds__(kWalkThreads)
+    k_fld_walk_cc(const int *__restrict__ label, const int *__restrict__ cnt, const int *__restrict__ bbox, int w, int h,
+                  const int *__restrict__ comp_root, int *__restrict__ counters, int max_comps, int length_threshold,
+                  int2 *__restrict__ chain_pts, int *__restrict__ chain_seed, int *__restrict__ chain_off,
+                  int *__restrict__ chain_len, int max_chains) {
   extern __shared__ unsigned bm[];
-  const int lane = threadIdx.x;
-  const int ws = ((w + 2 + 31) >> 5) + 1;  // +1 so the funnel shift may read one word past the row
-  const int prow = h + 2;
-  for (int i = lane; i < prow * ws; i += 32) bm[i] = 0;
-  __syncwarp();
-  // copy with a 1-bit shift (padded x = x + 1)
-  for (int i = lane; i < h * words_per_row; i += 32) {
-    int y = i / words_per_row, wi = i - y * words_per_row;
-    unsigned v = edges[i];
-    if (wi == words_per_row - 1 && (w & 31)) v &= (1u << (w & 31)) - 1u;
-    unsigned *dst = bm + (y + 1) * ws + wi;
-    // lanes of one row touch neighbouring words: use shared atomics for the carry-over bit
-    atomicOr(dst, v << 1);
-    if (v >> 31) atomicOr(dst + 1, 1u);
-  }
-  __syncwarp();
-
-  int nchains = 0, npts = 0;
-  // raster scan over image words (padded row y + 1, padded bit x + 1)
-  int y = 0, xw = 0;            // current row and 32-pixel group
-  unsigned done_mask = 0;       // pixels of the current group already passed (bits below the last seed, inclusive)
-  while (y < h) {
-    // each lane inspects one 32-pixel group of the current row, starting at xw
-    const int groups = (w + 31) >> 5;
-    int g = xw + lane;
-    unsigned v = 0;
-    if (g < groups) {
-      const unsigned *r = bm + (y + 1) * ws;
-      v = __funnelshift_r(r[g], r[g + 1], 1);  // pixels 32g .. 32g+31
-      if (g == xw) v &= ~done_mask;
-    }
-    unsigned any = __ballot_sync(0xffffffffu, v != 0);
-    if (!any) {
-      xw += 32;
-      done_mask = 0;
-      if (xw >= groups) { xw = 0; y++; }
-      continue;
-    }
-    int first = __ffs(any) - 1;
-    unsigned vv = __shfl_sync(0xffffffffu, v, first);
-    int bit = __ffs(vv) - 1;
-    int sx = ((xw + first) << 5) + bit, sy = y;
-    if (first != 0) done_mask = 0;
-    xw += first;
-    done_mask |= (bit == 31) ? 0xffffffffu : ((2u << bit) - 1u);
-
-    if (lane == 0) {
-      // ---- walk one chain (getPointChain loop of lineDetection)
-      int start = npts;
-      int cx = sx, cy = sy;
-      chain_pts[npts++] = make_int2(cx, cy);
-      bm[(cy + 1) * ws + ((cx + 1) >> 5)] &= ~(1u << ((cx + 1) & 31));
-      int direction = 0, step = 0;
-      while (true) {
-        unsigned t = row3(bm, ws, cy, cx), m = row3(bm, ws, cy + 1, cx), b = row3(bm, ws, cy + 2, cx);
-        unsigned mask = ((b >> 2) & 1u) | (((b >> 1) & 1u) << 1) | ((b & 1u) << 2) | ((m & 1u) << 3) | ((t & 1u) << 4) |
-                        (((t >> 1) & 1u) << 5) | (((t >> 2) & 1u) << 6) | (((m >> 2) & 1u) << 7);
-        if (!mask) break;
-        int i;
-        if (step == 0) {
-          i = __ffs(mask) - 1;
-          direction = i > 4 ? i - 8 : i;
-        } else {
-          i = c_chain_lut[(direction + 3) * 256 + mask];
-          if (i == 8) break;
-          int cd = i > 4 ? i - 8 : i;
-          direction = (direction * step + cd) / (step + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ncomp = min(counters[0], max_comps);
+  __shared__ int s_ci;
+  while (true) {
+    // dynamic work queue: a few long-lived CTAs pull components, so the walk never floods the SMs' shared memory
+    // while the latency-critical tracking kernels of the same or other camera streams want to start
+    __syncthreads();   // the previous component's walk is finished
+    if (tid == 0) s_ci = atomicAdd(counters + 1, 1);
+    __syncthreads();
+    const int ci = s_ci;
+    if (ci >= ncomp) break;
+    const int root = comp_root[ci];
+    const int y0 = root / w, y1 = bbox[root];
+    const int x0 = bbox[w * h + root], x1 = bbox[2 * w * h + root];
+    const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+    const int ws = ((bw + 2 + 31) >> 5) + 1;
+    for (int i = tid; i < (bh + 2) * ws; i += kWalkThreads) bm[i] = 0;
+    __syncthreads();
+    // private bit map of this component: one coalesced label load + ballot per 32 pixels, 4 loads in flight per warp
+    const int groups = (bw + 31) >> 5;
+    const int items = bh * groups;
+    for (int it0 = warp * 4; it0 < items; it0 += (kWalkThreads / 32) * 4) {
+      int lab[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int it = it0 + u;
+        lab[u] = -2;
+        if (it < items) {
+          const int ly = it / groups, g = it - ly * groups;
+          const int lx = (g << 5) + lane;
+          if (lx < bw) lab[u] = label[(size_t)(y0 + ly) * w + x0 + lx];
         }
-        const int dr = (i <= 2) ? 1 : ((i == 3 || i == 7) ? 0 : -1);
-        const int dc = (i == 0 || i == 6 || i == 7) ? 1 : ((i == 1 || i == 5) ? 0 : -1);
-        cx += dc;
-        cy += dr;
-        chain_pts[npts++] = make_int2(cx, cy);
-        step++;
-        bm[(cy + 1) * ws + ((cx + 1) >> 5)] &= ~(1u << ((cx + 1) & 31));
       }
-      if (npts - start < length_threshold + 1 || nchains >= max_chains) {
-        npts = start;  // chain too short: dropped (its pixels stay consumed)
-      } else {
-        chain_off[nchains++] = start;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int it = it0 + u;
+        const unsigned word = __ballot_sync(0xffffffffu, lab[u] == root);
+        if (lane == 0 && word && it < items) {
+          const int ly = it / groups, g = it - ly * groups;
+          unsigned *dst = bm + (ly + 1) * ws + g;
+          atomicOr(dst, word << 1);
+          if (word >> 31) atomicOr(dst + 1, 1u);
+        }
       }
     }
-    __syncwarp();
+    __syncthreads();
+    if (warp != 0) continue;   // warp 0 scans and walks; the others wait at the barrier above
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counters + 2, cnt[root]);   // this component's slice of the chain-point pool
+    base = __shfl_sync(0xffffffffu, base, 0);
+    int npts = base;
+    // raster scan over the private map
+    int y = 0, xw = 0;
+    while (y < bh) {
+      const int g = xw + lane;
+      unsigned v = 0;
+      if (g < groups) {
+        const unsigned *r = bm + (y + 1) * ws;
+        v = __funnelshift_r(r[g], r[g + 1], 1);  // local pixels 32g .. 32g+31
+      }
+      const unsigned any = __ballot_sync(0xffffffffu, v != 0);
+      if (!any) {
+        xw += 32;
+        if (xw >= groups) { xw = 0; y++; }
+        continue;
+      }
+      const int first = __ffs(any) - 1;
+      const unsigned vv = __shfl_sync(0xffffffffu, v, first);
+      const int bit = __ffs(vv) - 1;
+      const int sx = ((xw + first) << 5) + bit, sy = y;
+      xw += first;
+      if (lane == 0) {
+        // ---- walk one chain (the getPointChain loop of lineDetection); coordinates local to the bounding box
+        const int start = npts;
+        int cx = sx, cy = sy;
+        chain_pts[npts++] = make_int2(x0 + cx, y0 + cy);
+        bm[(cy + 1) * ws + ((cx + 1) >> 5)] &= ~(1u << ((cx + 1) & 31));
+        int direction = 0, step = 0;
+        while (true) {
+          const unsigned t = row3(bm, ws, cy, cx), m = row3(bm, ws, cy + 1, cx), b = row3(bm, ws, cy + 2, cx);
+          const unsigned mask = ((b >> 2) & 1u) | (((b >> 1) & 1u) << 1) | ((b & 1u) << 2) | ((m & 1u) << 3) |
+                                ((t & 1u) << 4) | (((t >> 1) & 1u) << 5) | (((t >> 2) & 1u) << 6) | (((m >> 2) & 1u) << 7);
+          if (!mask) break;
+          int i;
+          if (step == 0) {
+            i = __ffs(mask) - 1;
+            direction = i > 4 ? i - 8 : i;
+          } else {
+            i = choose_neighbour(mask, direction);
+            if (i == 8) break;
+            const int cd = i > 4 ? i - 8 : i;
+            direction = (direction * step + cd) / (step + 1);
+          }
+          const int dr = (i <= 2) ? 1 : ((i == 3 || i == 7) ? 0 : -1);
+          const int dc = (i == 0 || i == 6 || i == 7) ? 1 : ((i == 1 || i == 5) ? 0 : -1);
+          cx += dc;
+          cy += dr;
+          chain_pts[npts++] = make_int2(x0 + cx, y0 + cy);
+          step++;
+          bm[(cy + 1) * ws + ((cx + 1) >> 5)] &= ~(1u << ((cx + 1) & 31));
+        }
+        if (npts - start < length_threshold + 1) {
+          npts = start;  // chain too short: dropped (its pixels stay consumed)
+        } else {
+          const int c = atomicAdd(counters + 3, 1);
+          if (c < max_chains) {
+            chain_seed[c] = (y0 + sy) * w + (x0 + sx);
+            chain_off[c] = start;
+            chain_len[c] = npts - start;
+          }
+        }
+      }
+      npts = __shfl_sync(0xffffffffu, npts, 0);
+      __syncwarp();
+    }
   }
-  if (lane == 0) {
-    chain_off[nchains] = npts;
-    n_chains[0] = nchains;
-  }
+}
+
+// rank of every chain by the raster index of its seed (seeds are distinct pixels): order[rank] = chain
+__global__ void k_fld_order(const int *__restrict__ chain_seed, const int *__restrict__ counters, int max_chains,
+                            int *__restrict__ order) {
+  const int n = min(counters[3], max_chains);
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int mine = chain_seed[c];
+  int rank = 0;
+  for (int k = 0; k < n; k++) rank += chain_seed[k] < mine ? 1 : 0;
+  order[rank] = c;
 }
 
 // --------------------------------------------------------------------------------- segments from chains
@@ -273,16 +397,19 @@ __device__ __forceinline__ void incident_point(const double l[3], float &px, flo
   py = fy < 0.0f ? 0.0f : (fy >= (H - 1.0f) ? (H - 1.0f) : fy);
 }
 
+// one thread per chain, in seed order; chain c writes its segments to slots chain_off[c] / 21 + j (collision free:
+// every segment consumes at least 21 chain points and the chains' point ranges are disjoint)
 __global__ void k_fld_segments(const uint8_t *__restrict__ img, int W, int H, int pitch, int T, float dist_thr,
                                const int2 *__restrict__ chain_pts, const int *__restrict__ chain_off,
-                               const int *__restrict__ n_chains, float4 *__restrict__ segs, int *__restrict__ seg_cnt,
-                               int *__restrict__ seg_base) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_chains[0]) return;
+                               const int *__restrict__ chain_len, const int *__restrict__ order,
+                               const int *__restrict__ counters, int max_chains, float4 *__restrict__ segs,
+                               int *__restrict__ seg_cnt, int *__restrict__ seg_base) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= min(counters[3], max_chains)) return;
+  const int c = order[r];
   const int2 *points = chain_pts + chain_off[c];
-  const int total = chain_off[c + 1] - chain_off[c];
-  // segment slots of chain c start at chain_off[c] / 21 + c (every chain of n points yields <= n/21 + 1 segments)
-  const int slot0 = chain_off[c] / kSegsPerChainDiv + c;
+  const int total = chain_len[c];
+  const int slot0 = chain_off[c] / kSegsPerChainDiv;
   int nseg = 0;
   int i, j;
   for (i = 0; i + T < total; i++) {
@@ -359,17 +486,17 @@ __global__ void k_fld_segments(const uint8_t *__restrict__ img, int W, int H, in
     segs[slot0 + nseg] = make_float4(e1x, e1y, e2x, e2y);
     nseg++;
   }
-  seg_cnt[c] = nseg;
-  seg_base[c] = slot0;
+  seg_cnt[r] = nseg;      // indexed by RANK so the compaction below walks chains in seed order
+  seg_base[r] = slot0;
 }
 
 // ordered compaction of the per-chain segment slots (one block)
 __global__ void __launch_bounds__(256)
     k_fld_compact(const float4 *__restrict__ segs, const int *__restrict__ seg_cnt, const int *__restrict__ seg_base,
-                  int *__restrict__ n_chains, float4 *__restrict__ out, int out_cap) {
+                  int *__restrict__ counters, int max_chains, float4 *__restrict__ out, int out_cap) {
   __shared__ int warp_tot[8];
   __shared__ int s_running;
-  const int n = n_chains[0];
+  const int n = min(counters[3], max_chains);
   const int tid = threadIdx.x;
   if (tid == 0) s_running = 0;
   __syncthreads();
@@ -393,31 +520,65 @@ __global__ void __launch_bounds__(256)
     if (tid == 255) s_running = off + cnt;
     __syncthreads();
   }
-  if (tid == 0) n_chains[1] = s_running;
+  if (tid == 0) counters[4] = s_running;
+}
+
+int FldBuffers::alloc(int w, int h, int length_threshold, int out_capacity) {
+  const size_t n = (size_t)w * h;
+  words_per_row = (w + 31) / 32;
+  max_chains = (int)(n / (length_threshold + 1)) + 1;
+  out_cap = out_capacity;
+  bool ok = true;
+  auto A = [&](auto **p, size_t bytes) { ok = ok && cudaMalloc((void **)p, bytes) == cudaSuccess; };
+  A(&edges, (size_t)words_per_row * h * sizeof(unsigned));
+  A(&label, n * sizeof(int));
+  A(&cnt, n * sizeof(int));
+  A(&bbox, 3 * n * sizeof(int));
+  A(&comp_root, (size_t)max_chains * sizeof(int));
+  A(&counters, 8 * sizeof(int));
+  A(&chain_pts, n * sizeof(int2));
+  A(&chain_seed, (size_t)max_chains * sizeof(int));
+  A(&chain_off, (size_t)max_chains * sizeof(int));
+  A(&chain_len, (size_t)max_chains * sizeof(int));
+  A(&order, (size_t)max_chains * sizeof(int));
+  A(&segs, (n / kSegsPerChainDiv + 2) * sizeof(float4));
+  A(&seg_cnt, (size_t)2 * max_chains * sizeof(int));
+  A(&out, (size_t)out_cap * sizeof(float4));
+  if (ok) ok = cudaMemset(counters, 0, 8 * sizeof(int)) == cudaSuccess;
+  return ok ? 0 : 1;
+}
+
+void FldBuffers::release() {
+  cudaFree(edges); cudaFree(label); cudaFree(cnt); cudaFree(bbox); cudaFree(comp_root); cudaFree(counters);
+  cudaFree(chain_pts); cudaFree(chain_seed); cudaFree(chain_off); cudaFree(chain_len); cudaFree(order);
+  cudaFree(segs); cudaFree(seg_cnt); cudaFree(out);
+  *this = FldBuffers();
 }
 
 void launch_fld(const DevImage &half, int length_threshold, float distance_threshold, FldBuffers &fb, cudaStream_t s) {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!g_chain_lut_ready[dev & 63]) {
-    uint8_t lut[8 * 256];
-    build_chain_lut(lut);
-    cudaMemcpyToSymbol(c_chain_lut, lut, sizeof(lut));
-    g_chain_lut_ready[dev & 63] = true;
-  }
-  const int ws = ((half.w + 2 + 31) >> 5) + 1;
-  size_t smem = (size_t)(half.h + 2) * ws * sizeof(unsigned);
+  const int w = half.w, h = half.h, n = w * h;
+  const int tpb = 256, nb = (n + tpb - 1) / tpb;
+  k_ccl_init<<<nb, tpb, 0, s>>>(fb.edges, fb.words_per_row, w, h, fb.label, fb.cnt, fb.bbox, fb.counters);
+  k_ccl_merge<<<nb, tpb, 0, s>>>(w, h, fb.label);
+  k_ccl_flatten<<<nb, tpb, 0, s>>>(w, h, fb.label, fb.cnt, fb.bbox);
+  k_ccl_roots<<<nb, tpb, 0, s>>>(w, h, fb.label, fb.cnt, length_threshold + 1, fb.comp_root, fb.counters, fb.max_chains);
+  const int ws = ((w + 2 + 31) >> 5) + 1;
+  size_t smem = (size_t)(h + 2) * ws * sizeof(unsigned);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(k_fld_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_fld_walk_cc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  k_fld_walk<<<1, 32, smem, s>>>(fb.edges, fb.words_per_row, half.w, half.h, length_threshold, fb.chain_pts, fb.chain_off,
-                                 fb.n_chains, fb.max_chains);
-  int blocks = (fb.max_chains + 63) / 64;
-  k_fld_segments<<<blocks, 64, 0, s>>>(half.p, half.w, half.h, half.pitch, length_threshold, distance_threshold,
-                                       fb.chain_pts, fb.chain_off, fb.n_chains, fb.segs, fb.seg_cnt, fb.seg_cnt + fb.max_chains);
-  k_fld_compact<<<1, 256, 0, s>>>(fb.segs, fb.seg_cnt, fb.seg_cnt + fb.max_chains, fb.n_chains, fb.out, fb.out_cap);
+  k_fld_walk_cc<<<kWalkCtas, kWalkThreads, smem, s>>>(fb.label, fb.cnt, fb.bbox, w, h, fb.comp_root, fb.counters, fb.max_chains,
+                                               length_threshold, fb.chain_pts, fb.chain_seed, fb.chain_off, fb.chain_len,
+                                               fb.max_chains);
+  int blocks = (fb.max_chains + 127) / 128;
+  k_fld_order<<<blocks, 128, 0, s>>>(fb.chain_seed, fb.counters, fb.max_chains, fb.order);
+  k_fld_segments<<<(fb.max_chains + 63) / 64, 64, 0, s>>>(half.p, w, h, half.pitch, length_threshold, distance_threshold,
+                                                          fb.chain_pts, fb.chain_off, fb.chain_len, fb.order, fb.counters,
+                                                          fb.max_chains, fb.segs, fb.seg_cnt, fb.seg_cnt + fb.max_chains);
+  k_fld_compact<<<1, 256, 0, s>>>(fb.segs, fb.seg_cnt, fb.seg_cnt + fb.max_chains, fb.counters, fb.max_chains, fb.out,
+                                  fb.out_cap);
 }
 
 }  // namespace plviwo

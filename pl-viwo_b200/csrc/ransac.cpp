@@ -281,6 +281,41 @@ bool get_subset(const float *m1, const float *m2, int count, float *ms1, float *
   return i == model_points && iters < max_attempts;
 }
 
+// FMEstimatorCallback::computeError on structure-of-arrays inputs (doubles prepared once per call); the loop has no
+// cross-iteration dependence, so the compiler vectorises it.  Operation order per element is the library's.
+struct Soa {
+  std::vector<double> x1, y1, x2, y2;
+};
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("avx2", "default")))
+#endif
+int count_inliers(const Soa &p, int count, const double *F, float t, float *err, uint8_t *mask) {
+  const double *X1 = p.x1.data(), *Y1 = p.y1.data(), *X2 = p.x2.data(), *Y2 = p.y2.data();
+  const double f0 = F[0], f1 = F[1], f2 = F[2], f3 = F[3], f4 = F[4], f5 = F[5], f6 = F[6], f7 = F[7], f8 = F[8];
+  for (int i = 0; i < count; i++) {
+    double x1 = X1[i], y1 = Y1[i], x2 = X2[i], y2 = Y2[i];
+    double a = f0 * x1 + f1 * y1 + f2;
+    double b = f3 * x1 + f4 * y1 + f5;
+    double c = f6 * x1 + f7 * y1 + f8;
+    double s2 = 1. / (a * a + b * b);
+    double d2 = x2 * a + y2 * b + c;
+    a = f0 * x2 + f3 * y2 + f6;
+    b = f1 * x2 + f4 * y2 + f7;
+    c = f2 * x2 + f5 * y2 + f8;
+    double s1 = 1. / (a * a + b * b);
+    double d1 = x1 * a + y1 * b + c;
+    double e1 = d1 * d1 * s1, e2 = d2 * d2 * s2;
+    err[i] = (float)(e1 > e2 ? e1 : e2);
+  }
+  int good = 0;
+  for (int i = 0; i < count; i++) {
+    uint8_t f = err[i] <= t;
+    mask[i] = f;
+    good += f;
+  }
+  return good;
+}
+
 void compute_error(const float *m1, const float *m2, int count, const double *F, float *err) {
   for (int i = 0; i < count; i++) {
     double x1 = m1[2 * i], y1 = m1[2 * i + 1], x2 = m2[2 * i], y2 = m2[2 * i + 1];
@@ -339,6 +374,12 @@ int ransac_fundamental(const float *m1, const float *m2, int count, double thres
     // ---- RANSACPointSetRegistrator::run
     int niters = max_iters, max_good = 0;
     const float t = (float)(threshold * threshold);
+    Soa soa;
+    soa.x1.resize(count); soa.y1.resize(count); soa.x2.resize(count); soa.y2.resize(count);
+    for (int k = 0; k < count; k++) {
+      soa.x1[k] = m1[2 * k]; soa.y1[k] = m1[2 * k + 1];
+      soa.x2[k] = m2[2 * k]; soa.y2[k] = m2[2 * k + 1];
+    }
     for (int iter = 0; iter < niters; iter++) {
       if (!get_subset(m1, m2, count, ms1, ms2, rng, 10000)) {
         if (iter == 0) return 0;
@@ -347,13 +388,7 @@ int ransac_fundamental(const float *m1, const float *m2, int count, double thres
       int nmodels = run_7point(ms1, ms2, F);
       if (nmodels <= 0) continue;
       for (int i = 0; i < nmodels; i++) {
-        compute_error(m1, m2, count, F + 9 * i, err.data());
-        int good = 0;
-        for (int k = 0; k < count; k++) {
-          uint8_t f = err[k] <= t;
-          cur[k] = f;
-          good += f;
-        }
+        int good = count_inliers(soa, count, F + 9 * i, t, err.data(), cur.data());
         if (good > std::max(max_good, model_points - 1)) {
           std::swap(cur, best);
           max_good = good;

@@ -50,6 +50,7 @@ def _run(fe, synth, n_frames, kw, seed=1000, width=1280, height=560, line_heavy=
                               moving_mask=moving_mask, hard=hard)
     oracle = ofe.FrontEnd(ofe.FeConfig(K=seq.K, D=seq.D, use_lines=use_lines, **kw))
     gpu = fe.FrontEnd(fe.default_config(width=width, height=height, K=seq.K, D=seq.D, use_lines=int(use_lines), **kw))
+    gpu.enable_taps(True)
     s = dict(frames=0, n_feat=0, n_status_agree=0, n_klt_fail=0, n_rsc_fail=0, line_frames=0, line_rows_equal=0,
              n_line_rows=0, first_divergence=None, detections=0, new_pts=0, fast_equal=0, n_fast_kps=0, id_errors=0,
              n_uv_outliers=0, n_outliers_not_scalar_exact=0)
