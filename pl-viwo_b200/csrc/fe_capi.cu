@@ -1,5 +1,6 @@
 // extern "C" surface declared in include/plviwo_fe.h.  Thin: argument checks, exception firewall, and the
 // stand-alone kernel entry points used by the parity tests and micro-benchmarks.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -14,6 +15,13 @@ struct FeHandle {
 };
 
 static thread_local std::string g_create_error;
+
+// See bench.py / INTEGRATION.md: one hardware queue per stream.  Only effective if no CUDA context exists yet.
+namespace {
+struct EnvInit {
+  EnvInit() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+} g_env_init;
+}  // namespace
 
 #define API_BEGIN try {
 #define API_END                                   \

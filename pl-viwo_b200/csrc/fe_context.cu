@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace plviwo {
@@ -66,12 +67,9 @@ int FeContext::init() {
   FE_CUDA(cudaSetDevice(device_));
   int lo = 0, hi = 0;
   FE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  FE_CUDA(cudaStreamCreateWithPriority(&s_img_, cudaStreamNonBlocking, lo));
   FE_CUDA(cudaStreamCreateWithPriority(&s_pt_, cudaStreamNonBlocking, hi));
-  FE_CUDA(cudaMalloc(&d_hist_, 256 * sizeof(unsigned)));
-  FE_CUDA(cudaMemset(d_hist_, 0, 256 * sizeof(unsigned)));
-  FE_CUDA(cudaMalloc(&d_counters_, 4 * sizeof(unsigned)));
-  FE_CUDA(cudaMemset(d_counters_, 0, 4 * sizeof(unsigned)));
+  init_device_constants();
+  use_graphs_ = std::getenv("PLVIWO_NO_GRAPHS") == nullptr;
 
   const int nslots = std::max(cfg_.lookahead, 0) + 2;
   slots_.resize(nslots);
@@ -100,6 +98,14 @@ int FeContext::init() {
     }
     FE_CUDA(cudaMallocHost(&s.h_raw, (size_t)W_ * H_));
     FE_CUDA(cudaStreamCreateWithPriority(&s.s_line, cudaStreamNonBlocking, lo));
+    FE_CUDA(cudaStreamCreateWithPriority(&s.s_a, cudaStreamNonBlocking, lo));
+    FE_CUDA(cudaStreamCreateWithPriority(&s.s_b, cudaStreamNonBlocking, lo));
+    FE_CUDA(cudaMalloc(&s.d_hist, 256 * sizeof(unsigned)));
+    FE_CUDA(cudaMemset(s.d_hist, 0, 256 * sizeof(unsigned)));
+    FE_CUDA(cudaMalloc(&s.d_counters, 4 * sizeof(unsigned)));
+    FE_CUDA(cudaMemset(s.d_counters, 0, 4 * sizeof(unsigned)));
+    FE_CUDA(cudaMalloc(&s.d_seq, 4 * sizeof(int)));
+    FE_CUDA(cudaMemset(s.d_seq, 0, 4 * sizeof(int)));
     FE_CUDA(cudaEventCreateWithFlags(&s.ev_pyr, cudaEventDisableTiming));
     FE_CUDA(cudaEventCreateWithFlags(&s.ev_lines, cudaEventDisableTiming));
     for (auto &e : s.ev_t) FE_CUDA(cudaEventCreate(&e));
@@ -116,7 +122,6 @@ int FeContext::init() {
   cand_cap_ = std::max(max_cells_ * (cfg_.num_features + 1), 1024);
   if (cand_cap_ > 65536) cand_cap_ = 65536;
   FE_CUDA(cudaMalloc(&d_cells_, (size_t)max_cells_ * sizeof(FastCell)));
-  FE_CUDA(cudaStreamCreateWithPriority(&s_det_, cudaStreamNonBlocking, lo));
   FE_CUDA(cudaStreamCreateWithPriority(&s_det2_, cudaStreamNonBlocking, lo));
   for (FrameSlot &s : slots_) {
     FE_CUDA(cudaMalloc(&s.d_fast_total, sizeof(unsigned)));
@@ -174,6 +179,10 @@ FeContext::~FeContext() {
     if (s.ev_l0) cudaEventDestroy(s.ev_l0);
     if (s.ev_fast) cudaEventDestroy(s.ev_fast);
     for (auto &e : s.ev_fast_t) if (e) cudaEventDestroy(e);
+    destroy_graphs(s);
+    cudaFree(s.d_hist); cudaFree(s.d_counters); cudaFree(s.d_seq);
+    if (s.s_a) cudaStreamDestroy(s.s_a);
+    if (s.s_b) cudaStreamDestroy(s.s_b);
     if (s.s_line) cudaStreamDestroy(s.s_line);
     if (s.ev_pyr) cudaEventDestroy(s.ev_pyr);
     if (s.ev_lines) cudaEventDestroy(s.ev_lines);
@@ -182,13 +191,10 @@ FeContext::~FeContext() {
   for (auto &e : ev_pt_) if (e) cudaEventDestroy(e);
   if (ev_sync_) cudaEventDestroy(ev_sync_);
   cudaFreeHost(h_flag_lk_);
-  cudaFree(d_hist_); cudaFree(d_counters_);
   cudaFree(d_cells_);
-  if (s_det_) cudaStreamDestroy(s_det_);
   if (s_det2_) cudaStreamDestroy(s_det2_);
   cudaFree(d_pts0_); cudaFree(d_pts1_); cudaFree(d_p0n_); cudaFree(d_p1n_); cudaFree(d_status_);
   cudaFreeHost(h_pts0_); cudaFreeHost(h_pts1_); cudaFreeHost(h_p0n_); cudaFreeHost(h_p1n_); cudaFreeHost(h_status_);
-  if (s_img_) cudaStreamDestroy(s_img_);
   if (s_pt_) cudaStreamDestroy(s_pt_);
 }
 
@@ -255,41 +261,136 @@ void FeContext::undistort_host(float u, float v, float &un, float &vn) const {
 }
 
 // ------------------------------------------------------------------------------------------------ submit
-int FeContext::enqueue_frame_independent(FrameSlot &s) {
-  const bool tm = timing;
-  s.timed = tm;
-  if (cfg_.histogram_method == FE_HIST_HISTOGRAM) {
-    launch_hist(s.raw, d_hist_, s_img_);
-    times.kernel_launches_total++;
-  }
-  if (tm) cudaEventRecord(s.ev_t[2], s_img_);
+// The frame-independent work of a frame, as three recordable paths.  Each is issued on a per-slot stream either
+// directly (first use of a slot, or while the cell layout changes) or as a replay of a CUDA graph captured from
+// exactly these calls: ~30 launches per frame collapse into three graph launches.  Stage-timing events are part of
+// the paths, so timings can be read whether or not the graphs are used.
+int FeContext::record_image_path(FrameSlot &s, cudaStream_t st) {
+  const int eq = cfg_.histogram_method == FE_HIST_HISTOGRAM ? 1 : 0;
+  if (eq) launch_hist(s.raw, s.d_hist, st);
+  if (timing) cudaEventRecord(s.ev_t[2], st);
   DevImage half = cfg_.use_lines ? s.half : DevImage();
-  launch_eq_pyr1(s.raw, d_hist_, d_counters_, cfg_.histogram_method == FE_HIST_HISTOGRAM ? 1 : 0, s.pyr.lvl[0],
-                 s.pyr.n > 1 ? s.pyr.lvl[1] : DevImage(), half, s_img_);
-  times.kernel_launches_total++;
-  if (tm) cudaEventRecord(s.ev_t[3], s_img_);
-  FE_CUDA(cudaEventRecord(s.ev_lines, s_img_));  // reused as "half image ready" until the line stream re-records it
-  FE_CUDA(cudaEventRecord(s.ev_l0, s_img_));
-  if (s.pyr.n > 2) {
-    launch_pyr_rest(s.pyr, d_counters_ + 1, s_img_);
-    times.kernel_launches_total += s.pyr.n - 2;
-  }
-  if (tm) cudaEventRecord(s.ev_t[4], s_img_);
-  FE_CUDA(cudaEventRecord(s.ev_pyr, s_img_));
-  if (cfg_.use_lines && s.has_vp) {
-    FE_CUDA(cudaStreamWaitEvent(s.s_line, s.ev_lines, 0));
-    if (tm) cudaEventRecord(s.ev_t[5], s.s_line);
-    launch_canny(s.half, cfg_.canny_th1, cfg_.canny_th2, s.fld, s.s_line);
-    if (tm) cudaEventRecord(s.ev_t[6], s.s_line);
-    launch_fld(s.half, cfg_.fld_length_threshold, cfg_.fld_distance_threshold, s.fld, s.s_line);
-    times.kernel_launches_total += 9;
-    if (tm) cudaEventRecord(s.ev_t[7], s.s_line);
-    FE_COPY(s.h_fld_counts, s.fld.counters + 3, 2 * sizeof(int), cudaMemcpyDeviceToHost, s.s_line);
-    FE_COPY(s.h_segs, s.fld.out, 1024 * sizeof(float4), cudaMemcpyDeviceToHost, s.s_line);
-    FE_CUDA(cudaEventRecord(s.ev_lines, s.s_line));
-    launch_signal(&s.h_flags[2], ++s.seq_lines, s.s_line);
-  }
+  launch_eq_pyr1(s.raw, s.d_hist, s.d_counters, eq, s.pyr.lvl[0], s.pyr.n > 1 ? s.pyr.lvl[1] : DevImage(), half, st);
+  if (timing) cudaEventRecord(s.ev_t[3], st);
+  if (s.pyr.n > 2) launch_pyr_rest(s.pyr, s.d_counters + 1, st);
+  if (timing) cudaEventRecord(s.ev_t[4], st);
   FE_CUDA(cudaGetLastError());
+  return FE_OK;
+}
+
+int FeContext::record_fast_path(FrameSlot &s, cudaStream_t st) {
+  const int ncell = (int)cells_.size(), nb = cells_nb_;
+  if (ncell > 0) {
+    FE_CUDA(cudaMemsetAsync(s.d_fast_total, 0, sizeof(unsigned), st));
+    if (timing) cudaEventRecord(s.ev_fast_t[0], st);
+    launch_fast(s.pyr.lvl[0], d_cells_, ncell, nb, cells_csx_, cfg_.fast_threshold, s.d_fast_total, s.d_band_off, s.d_band_cnt,
+                s.d_kps, kps_cap_, st);
+    if (timing) cudaEventRecord(s.ev_fast_t[1], st);
+    const int ntab = ncell * nb;
+    const int spec = std::min(16384, kps_cap_);   // speculative first chunk of the compact keypoint list
+    FE_CUDA(cudaMemcpyAsync(s.h_band, s.d_fast_total, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    FE_CUDA(cudaMemcpyAsync(s.h_band + 1, s.d_band_off, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FE_CUDA(cudaMemcpyAsync(s.h_band + 1 + ntab, s.d_band_cnt, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FE_CUDA(cudaMemcpyAsync(s.h_kps, s.d_kps, (size_t)spec * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  }
+  launch_signal_inc(&s.h_flags[0], s.d_seq + 0, st);
+  FE_CUDA(cudaGetLastError());
+  return FE_OK;
+}
+
+int FeContext::record_line_path(FrameSlot &s, cudaStream_t st) {
+  if (timing) cudaEventRecord(s.ev_t[5], st);
+  launch_canny(s.half, cfg_.canny_th1, cfg_.canny_th2, s.fld, st);
+  if (timing) cudaEventRecord(s.ev_t[6], st);
+  launch_fld(s.half, cfg_.fld_length_threshold, cfg_.fld_distance_threshold, s.fld, st);
+  if (timing) cudaEventRecord(s.ev_t[7], st);
+  FE_CUDA(cudaMemcpyAsync(s.h_fld_counts, s.fld.counters + 3, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  FE_CUDA(cudaMemcpyAsync(s.h_segs, s.fld.out, 1024 * sizeof(float4), cudaMemcpyDeviceToHost, st));
+  launch_signal_inc(&s.h_flags[2], s.d_seq + 2, st);
+  FE_CUDA(cudaGetLastError());
+  return FE_OK;
+}
+
+void FeContext::destroy_graphs(FrameSlot &s) {
+  if (s.g_image) cudaGraphExecDestroy(s.g_image);
+  if (s.g_fast) cudaGraphExecDestroy(s.g_fast);
+  if (s.g_lines) cudaGraphExecDestroy(s.g_lines);
+  s.g_image = s.g_fast = s.g_lines = nullptr;
+  s.graph_version = -1;
+}
+
+int FeContext::build_graphs(FrameSlot &s) {
+  destroy_graphs(s);
+  auto capture = [&](cudaStream_t st, int (FeContext::*fn)(FrameSlot &, cudaStream_t), cudaGraphExec_t *out) -> int {
+    // thread-local capture mode: the worker thread keeps issuing its own CUDA calls meanwhile
+    FE_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = (this->*fn)(s, st);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc) {
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    if (e != cudaSuccess) return fail(e, "cudaStreamEndCapture");
+    e = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(e, "cudaGraphInstantiate");
+    return FE_OK;
+  };
+  int rc = capture(s.s_a, &FeContext::record_image_path, &s.g_image);
+  if (rc) return rc;
+  rc = capture(s.s_b, &FeContext::record_fast_path, &s.g_fast);
+  if (rc) return rc;
+  if (cfg_.use_lines) {
+    rc = capture(s.s_line, &FeContext::record_line_path, &s.g_lines);
+    if (rc) return rc;
+  }
+  s.graph_version = layout_version_;
+  return FE_OK;
+}
+
+int FeContext::enqueue_frame_independent(FrameSlot &s) {
+  s.timed = timing;
+  const bool lines = cfg_.use_lines && s.has_vp;
+  // a slot replays its graphs from its second use on (the first use runs the same calls directly, which also gets
+  // every lazy one-time initialisation out of the way before anything is captured)
+  bool replay = use_graphs_ && s.warmed && !timing;   // stage timing needs real event records: direct launches
+  if (replay && s.graph_version != layout_version_) {
+    int rc = build_graphs(s);
+    if (rc) return rc;
+  }
+  if (replay) {
+    FE_CUDA(cudaGraphLaunch(s.g_image, s.s_a));
+  } else {
+    int rc = record_image_path(s, s.s_a);
+    if (rc) return rc;
+  }
+  FE_CUDA(cudaEventRecord(s.ev_pyr, s.s_a));
+  FE_CUDA(cudaStreamWaitEvent(s.s_b, s.ev_pyr, 0));
+  if (replay) {
+    FE_CUDA(cudaGraphLaunch(s.g_fast, s.s_b));
+  } else {
+    int rc = record_fast_path(s, s.s_b);
+    if (rc) return rc;
+  }
+  s.seq_fast++;
+  if (lines) {
+    FE_CUDA(cudaStreamWaitEvent(s.s_line, s.ev_pyr, 0));
+    if (replay) {
+      FE_CUDA(cudaGraphLaunch(s.g_lines, s.s_line));
+    } else {
+      int rc = record_line_path(s, s.s_line);
+      if (rc) return rc;
+    }
+    s.seq_lines++;
+  }
+  s.warmed = true;
+  // bookkeeping (identical for both ways of issuing the work)
+  const int ncell = (int)cells_.size(), ntab = ncell * cells_nb_;
+  times.kernel_launches_total += (cfg_.histogram_method == FE_HIST_HISTOGRAM ? 1 : 0) + 1 + std::max(s.pyr.n - 2, 0) +
+                                 (ncell > 0 ? 1 : 0) + 1 + (lines ? 11 : 0);
+  if (ncell > 0) times.d2h_bytes += sizeof(unsigned) + (size_t)2 * ntab * sizeof(int) + (size_t)std::min(16384, kps_cap_) * sizeof(unsigned);
+  if (lines) times.d2h_bytes += 2 * sizeof(int) + 1024 * sizeof(float4);
   return FE_OK;
 }
 
@@ -305,6 +406,10 @@ int FeContext::submit(double t, const uint8_t *image, int stride, bool on_device
     return FE_BAD_ARG;
   }
   FrameSlot &s = slots_[si];
+  if (s.predet_state.load() == 1) {   // the worker may still be refining this slot's previous frame
+    int rc = wait_predetection(s);
+    if (rc) return rc;
+  }
   s.busy = true;
   s.timestamp = t;
   s.has_vp = vp != nullptr;
@@ -315,9 +420,9 @@ int FeContext::submit(double t, const uint8_t *image, int stride, bool on_device
   } else {
     s.mask.clear();
   }
-  if (timing) cudaEventRecord(s.ev_t[0], s_img_);
+  if (timing) cudaEventRecord(s.ev_t[0], s.s_a);
   if (on_device) {
-    FE_CUDA(cudaMemcpy2DAsync(s.raw.p, s.raw.pitch, image, stride, W_, H_, cudaMemcpyDeviceToDevice, s_img_));
+    FE_CUDA(cudaMemcpy2DAsync(s.raw.p, s.raw.pitch, image, stride, W_, H_, cudaMemcpyDeviceToDevice, s.s_a));
   } else {
     cudaPointerAttributes attr;
     bool pinned = cudaPointerGetAttributes(&attr, image) == cudaSuccess && attr.type == cudaMemoryTypeHost;
@@ -329,14 +434,19 @@ int FeContext::submit(double t, const uint8_t *image, int stride, bool on_device
       src = s.h_raw;
       sstride = W_;
     }
-    FE_CUDA(cudaMemcpy2DAsync(s.raw.p, s.raw.pitch, src, sstride, W_, H_, cudaMemcpyHostToDevice, s_img_));
+    FE_CUDA(cudaMemcpy2DAsync(s.raw.p, s.raw.pitch, src, sstride, W_, H_, cudaMemcpyHostToDevice, s.s_a));
     times.h2d_bytes += (size_t)W_ * H_;
   }
-  if (timing) cudaEventRecord(s.ev_t[1], s_img_);
-  int rc = enqueue_frame_independent(s);
+  if (timing) cudaEventRecord(s.ev_t[1], s.s_a);
+  int rc = enqueue_fast_all_cells(s);   // layout bookkeeping first: it decides whether the graphs are still valid
   if (rc) return rc;
-  rc = enqueue_fast_all_cells(s);
+  rc = enqueue_frame_independent(s);
   if (rc) return rc;
+  {
+    std::lock_guard<std::mutex> lk(wmu_);
+    wqueue_.push_back(s.index);
+  }
+  wcv_.notify_one();
   queue_.push_back(si);
   return FE_OK;
 }
@@ -372,13 +482,16 @@ void FeContext::layout_cells() {
   cells_uploaded_ = false;
 }
 
+// Host-side part of starting a frame's pre-detection: make sure the device cell table matches the current
+// num_features, remember the layout the frame is processed with.  The FAST launch itself is record_fast_path().
 int FeContext::enqueue_fast_all_cells(FrameSlot &s) {
   if (cells_num_features_ != cfg_.num_features) {
-    FE_CUDA(cudaStreamSynchronize(s_det_));   // d_cells_ may still be read by an earlier frame's FAST
+    FE_CUDA(cudaDeviceSynchronize());   // d_cells_ may still be read by an earlier frame's FAST
     layout_cells();
+    layout_version_++;
   }
   if (!cells_uploaded_ && !cells_.empty()) {
-    FE_CUDA(cudaMemcpyAsync(d_cells_, cells_.data(), cells_.size() * sizeof(FastCell), cudaMemcpyHostToDevice, s_det_));
+    FE_CUDA(cudaMemcpy(d_cells_, cells_.data(), cells_.size() * sizeof(FastCell), cudaMemcpyHostToDevice));
     cells_uploaded_ = true;
   }
   s.cells = cells_;
@@ -388,29 +501,6 @@ int FeContext::enqueue_fast_all_cells(FrameSlot &s) {
   s.predet_nfg = cells_nfg_;
   s.predet_num_features = cfg_.num_features;
   s.predet_state.store(1);
-  const int ncell = s.predet_ncell, nb = s.predet_nb;
-  if (ncell > 0) {
-    FE_CUDA(cudaStreamWaitEvent(s_det_, s.ev_l0, 0));
-    FE_CUDA(cudaMemsetAsync(s.d_fast_total, 0, sizeof(unsigned), s_det_));
-    if (timing) cudaEventRecord(s.ev_fast_t[0], s_det_);
-    launch_fast(s.pyr.lvl[0], d_cells_, ncell, nb, cells_csx_, cfg_.fast_threshold, s.d_fast_total, s.d_band_off, s.d_band_cnt,
-                s.d_kps, kps_cap_, s_det_);
-    times.kernel_launches_total++;
-    if (timing) cudaEventRecord(s.ev_fast_t[1], s_det_);
-    const int ntab = ncell * nb;
-    const int spec = std::min(16384, kps_cap_);   // speculative first chunk of the compact keypoint list
-    FE_COPY(s.h_band, s.d_fast_total, sizeof(unsigned), cudaMemcpyDeviceToHost, s_det_);
-    FE_COPY(s.h_band + 1, s.d_band_off, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, s_det_);
-    FE_COPY(s.h_band + 1 + ntab, s.d_band_cnt, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, s_det_);
-    FE_COPY(s.h_kps, s.d_kps, (size_t)spec * sizeof(unsigned), cudaMemcpyDeviceToHost, s_det_);
-  }
-  FE_CUDA(cudaEventRecord(s.ev_fast, s_det_));
-  launch_signal(&s.h_flags[0], ++s.seq_fast, s_det_);
-  {
-    std::lock_guard<std::mutex> lk(wmu_);
-    wqueue_.push_back(s.index);
-  }
-  wcv_.notify_one();
   return FE_OK;
 }
 
@@ -451,7 +541,7 @@ int FeContext::run_predetection(FrameSlot &s) {
   cudaError_t e;
   {
     HostTimer w1(&worker_ms_[1]);
-    if (wait_flag(&s.h_flags[0], s.seq_fast, s_det_, &worker_error_)) return FE_CUDA_ERROR;
+    if (wait_flag(&s.h_flags[0], s.seq_fast, s.s_b, &worker_error_)) return FE_CUDA_ERROR;
     e = cudaSuccess;
   }
   const int ncell = s.predet_ncell, nb = s.predet_nb, nfg = s.predet_nfg;
@@ -577,6 +667,7 @@ int FeContext::collect(FeFrameInfo *info) {
   if (cur.timed) {
     FE_CUDA(cudaEventSynchronize(cur.ev_pyr));
     acc_time(times, FE_STAGE_H2D, cur.ev_t[0], cur.ev_t[1]);
+    if (cur.predet_ncell > 0 && cur.predet_state.load() == 2) acc_time(times, FE_STAGE_FAST, cur.ev_fast_t[0], cur.ev_fast_t[1]);
     if (cfg_.histogram_method == FE_HIST_HISTOGRAM) acc_time(times, FE_STAGE_HIST, cur.ev_t[1], cur.ev_t[2]);
     acc_time(times, FE_STAGE_EQ_PYR, cur.ev_t[2], cur.ev_t[3]);
     acc_time(times, FE_STAGE_PYR_REST, cur.ev_t[3], cur.ev_t[4]);
@@ -746,13 +837,20 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
       if (rc) return rc;
       rc = enqueue_fast_all_cells(slot);
       if (rc) return rc;
+      rc = record_fast_path(slot, slot.s_b);
+      if (rc) return rc;
+      slot.seq_fast++;
+      {
+        std::lock_guard<std::mutex> lk(wmu_);
+        wqueue_.push_back(slot.index);
+      }
+      wcv_.notify_one();
     }
     {
       HostTimer hw(&times.host_ms[7]);
       int rc = wait_predetection(slot);
       if (rc) return rc;
     }
-    if (timing && slot.predet_ncell > 0) acc_time(times, FE_STAGE_FAST, slot.ev_fast_t[0], slot.ev_fast_t[1]);
     bool any_cell = false;
     for (auto &loc : valid_locs) any_cell = any_cell || slot.cell_of_loc[(size_t)loc.first * gy + loc.second] >= 0;
     if (any_cell) {
@@ -854,12 +952,15 @@ int FeContext::perform_matching(const FrameSlot &f0, const FrameSlot &f1, std::v
   times.h2d_bytes += (size_t)nt * 2 * sizeof(float2);
   times.d2h_bytes += (size_t)nt * (3 * sizeof(float2) + 1);
   if (timing) cudaEventRecord(ev_pt_[4], s_pt_);
+  HostTimer *tl = new HostTimer(&times.host_ms[12]);
   launch_lk(f0.pyr, f1.pyr, h_pts0_, h_pts1_, h_status_, h_p0n_, h_p1n_, nt, prm, s_pt_);
   times.kernel_launches_total++;
   if (timing) cudaEventRecord(ev_pt_[5], s_pt_);
   launch_signal(h_flag_lk_, ++seq_lk_, s_pt_);
   FE_CUDA(cudaGetLastError());
+  delete tl;
   {
+    HostTimer tw(&times.host_ms[13]);
     int rc = wait_flag(h_flag_lk_, seq_lk_, s_pt_, &last_error);
     if (rc) return rc;
   }
@@ -1152,23 +1253,34 @@ int FeContext::set_state(const void *buf, size_t n_bytes) {
       get(&val, sizeof(val));
       pol_last_[i][key] = val;
     }
-  for (FrameSlot &s : slots_) s.busy = false;
+  for (FrameSlot &s : slots_) {
+    if (s.predet_state.load() == 1) wait_predetection(s);
+    s.busy = false;
+  }
+  FE_CUDA(cudaDeviceSynchronize());
   last_slot_ = -1;
   if (hd.has_image) {
     FrameSlot &s = slots_[0];
     s.busy = true;
-    FE_CUDA(cudaMemcpy2DAsync(s.raw.p, s.raw.pitch, p, W_, W_, H_, cudaMemcpyHostToDevice, s_img_));
+    FE_CUDA(cudaMemcpy2DAsync(s.raw.p, s.raw.pitch, p, W_, W_, H_, cudaMemcpyHostToDevice, s.s_a));
     p += (size_t)W_ * H_;
     // the stored image is already equalised: rebuild the pyramid from it without a LUT
-    launch_eq_pyr1(s.raw, d_hist_, d_counters_, 0, s.pyr.lvl[0], s.pyr.n > 1 ? s.pyr.lvl[1] : DevImage(),
-                   cfg_.use_lines ? s.half : DevImage(), s_img_);
-    if (s.pyr.n > 2) launch_pyr_rest(s.pyr, d_counters_ + 1, s_img_);
-    FE_CUDA(cudaEventRecord(s.ev_l0, s_img_));
-    FE_CUDA(cudaStreamSynchronize(s_img_));
+    launch_eq_pyr1(s.raw, s.d_hist, s.d_counters, 0, s.pyr.lvl[0], s.pyr.n > 1 ? s.pyr.lvl[1] : DevImage(),
+                   cfg_.use_lines ? s.half : DevImage(), s.s_a);
+    if (s.pyr.n > 2) launch_pyr_rest(s.pyr, s.d_counters + 1, s.s_a);
+    FE_CUDA(cudaEventRecord(s.ev_pyr, s.s_a));
+    FE_CUDA(cudaStreamSynchronize(s.s_a));
     {
       int rc = enqueue_fast_all_cells(s);
       if (rc) return rc;
+      FE_CUDA(cudaStreamWaitEvent(s.s_b, s.ev_pyr, 0));
+      rc = record_fast_path(s, s.s_b);
+      if (rc) return rc;
+      s.seq_fast++;
+      std::lock_guard<std::mutex> lk(wmu_);
+      wqueue_.push_back(s.index);
     }
+    wcv_.notify_one();
     if (hd.has_mask) {
       s.mask.resize((size_t)W_ * H_);
       get(s.mask.data(), (size_t)W_ * H_);

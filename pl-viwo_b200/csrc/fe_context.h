@@ -44,7 +44,13 @@ struct FrameSlot {
   bool busy = false;
   int index = 0;
   cudaEvent_t ev_pyr = nullptr, ev_lines = nullptr;
-  cudaStream_t s_line = nullptr;   // per-slot stream: line extraction of different frames overlaps
+  cudaStream_t s_line = nullptr;   // per-slot streams: the frame-independent work of different frames overlaps
+  cudaStream_t s_a = nullptr, s_b = nullptr;
+  unsigned *d_hist = nullptr, *d_counters = nullptr;
+  int *d_seq = nullptr;            // device-side sequence numbers of the completion signals [fast, -, lines]
+  cudaGraphExec_t g_image = nullptr, g_fast = nullptr, g_lines = nullptr;
+  int graph_version = -1;
+  bool warmed = false;
   cudaEvent_t ev_t[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool timed = false;
 
@@ -116,6 +122,11 @@ class FeContext {
   int wait_flag(volatile int *flag, int value, cudaStream_t st, std::string *err);
   int alloc_image(DevImage &im, int w, int h);
   int enqueue_frame_independent(FrameSlot &s);
+  int record_image_path(FrameSlot &s, cudaStream_t st);
+  int record_fast_path(FrameSlot &s, cudaStream_t st);
+  int record_line_path(FrameSlot &s, cudaStream_t st);
+  int build_graphs(FrameSlot &s);
+  void destroy_graphs(FrameSlot &s);
   void layout_cells();                       // all grid cells of the frame (Grider_GRID geometry)
   int enqueue_fast_all_cells(FrameSlot &s);  // main thread, stream s_det_
   int run_predetection(FrameSlot &s);        // worker thread: sort / top-k / cornerSubPix
@@ -133,11 +144,10 @@ class FeContext {
   FeConfig cfg_;
   int device_;
   int W_, H_;
-  cudaStream_t s_img_ = nullptr, s_pt_ = nullptr;
+  cudaStream_t s_pt_ = nullptr;
   std::deque<FrameSlot> slots_;           // deque: FrameSlot holds an atomic and never moves
   std::vector<int> queue_;      // submitted, not yet collected (slot indices, FIFO)
   int last_slot_ = -1;          // slot holding the previous frame's pyramid (img_pyramid_last)
-  unsigned *d_hist_ = nullptr, *d_counters_ = nullptr;
 
   // ---- point tracker state (TrackBase.h:173-192)
   std::vector<Pt> pts_last_;
@@ -156,6 +166,8 @@ class FeContext {
   int cells_nfg_ = 0, cells_nb_ = 0, cells_csx_ = 0, cells_csy_ = 0, cells_num_features_ = -1;
   int max_cells_ = 0, max_bands_ = 0, kps_cap_ = 0, cand_cap_ = 0;
   bool cells_uploaded_ = false;
+  int layout_version_ = 0;
+  bool use_graphs_ = true;
   std::vector<uint64_t> occ_bits_;
   cudaStream_t s_det_ = nullptr, s_det2_ = nullptr;
   std::thread worker_;

@@ -30,6 +30,8 @@ void launch_eq_pyr1(const DevImage &src, unsigned *d_hist, unsigned *d_counter, 
 void launch_pyr_rest(const Pyramid &pyr, unsigned *d_counter, cudaStream_t s);
 
 void launch_signal(int *host_flag, int value, cudaStream_t s);
+void launch_signal_inc(int *host_flag, int *dev_seq, cudaStream_t s);
+void init_device_constants();   // constant-memory tables (sub-pixel mask); call once per device before capturing graphs
 
 // ---- FAST (kernels_fast.cu) ------------------------------------------------------------------------------
 struct FastCell {

@@ -290,6 +290,14 @@ __global__ void k_signal(volatile int *flag, int value) {
   __threadfence_system();
 }
 void launch_signal(int *host_flag, int value, cudaStream_t s) { k_signal<<<1, 1, 0, s>>>(host_flag, value); }
+// Same, with the sequence number kept in device memory so that the launch can live in a replayed CUDA graph.
+__global__ void k_signal_inc(volatile int *flag, int *dev_seq) {
+  int v = *dev_seq + 1;
+  *dev_seq = v;
+  *flag = v;
+  __threadfence_system();
+}
+void launch_signal_inc(int *host_flag, int *dev_seq, cudaStream_t s) { k_signal_inc<<<1, 1, 0, s>>>(host_flag, dev_seq); }
 
 void launch_pyr_rest(const Pyramid &pyr, unsigned *d_counter, cudaStream_t s) {
   (void)d_counter;

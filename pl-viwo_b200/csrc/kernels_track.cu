@@ -9,6 +9,7 @@
 #include "fe_kernels.h"
 
 #include <cfloat>
+#include <climits>
 #include <cmath>
 
 namespace plviwo {
@@ -97,8 +98,13 @@ __global__ void __launch_bounds__(kSpWarps * 32)
   if (lane == 0) pts[pi] = cI;
 }
 
+void init_device_constants() {
+  DevImage dummy;
+  launch_corner_subpix(dummy, nullptr, -1, 0);
+}
+
 void launch_corner_subpix(const DevImage &img, float2 *d_pts, int n, cudaStream_t s) {
-  if (n <= 0) return;
+  if (n == 0) return;
   int dev = 0;
   cudaGetDevice(&dev);
   if (!g_subpix_mask_ready[dev & 63]) {
@@ -114,6 +120,7 @@ void launch_corner_subpix(const DevImage &img, float2 *d_pts, int n, cudaStream_
     cudaMemcpyToSymbol(c_subpix_mask, m, sizeof(m));
     g_subpix_mask_ready[dev & 63] = true;
   }
+  if (n < 0) return;
   k_corner_subpix<<<(n + kSpWarps - 1) / kSpWarps, kSpWarps * 32, 0, s>>>(img.p, img.w, img.h, img.pitch, d_pts, n);
 }
 
@@ -350,6 +357,195 @@ __global__ void __launch_bounds__(kLkWarps * 32)
   }
 }
 
+// ------------------------------------------------------------------------------------------ LK, 15 x 15 window
+// Register-blocked specialisation for the reference's window (TrackKLT.h:144).  Lane l owns the 2 x 4 block of window
+// pixels at rows 2*(l/4).., columns 4*(l%4).. (the 16th row / column is masked off), keeps its I, Ix, Iy values and
+// the 3 x 5 block of the next image it interpolates from in registers, and only re-reads the next image when the
+// integer window position moves.  An iteration is then ~100 independent integer/float instructions plus one
+// two-value shuffle reduction, instead of eight dependent load-compute rounds.
+constexpr int kW15 = 15;
+constexpr int kLk15Warps = 2;
+
+__global__ void __launch_bounds__(kLk15Warps * 32)
+    k_lk15(LkArgs a, const float2 *__restrict__ pts0, float2 *__restrict__ pts1, uint8_t *__restrict__ status,
+           float2 *__restrict__ p0n, float2 *__restrict__ p1n, int n) {
+  constexpr int win = kW15, np = win + 3, nd = win + 1;
+  __shared__ uint8_t raw_s[kLk15Warps][np * np + 12];
+  __shared__ short ddx_s[kLk15Warps][nd * nd];
+  __shared__ short ddy_s[kLk15Warps][nd * nd];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pi = blockIdx.x * kLk15Warps + warp;
+  if (pi >= n) return;
+  uint8_t *raw = raw_s[warp];
+  short *ddx = ddx_s[warp], *ddy = ddy_s[warp];
+  const int r0 = (lane >> 2) * 2, c0 = (lane & 3) * 4;
+
+  const float2 prev_in = pts0[pi];
+  float2 next = pts1[pi];   // OPTFLOW_USE_INITIAL_FLOW
+  bool ok = true;
+  const float half = (win - 1) * 0.5f;
+  const float FLT_SCALE = 1.f / (1 << 20);
+
+  for (int level = a.max_level; level >= 0; level--) {
+    const int cols = a.w[level], rows = a.h[level];
+    const float lscale = 1.f / (float)(1 << level);
+    float2 prevPt = make_float2(prev_in.x * lscale, prev_in.y * lscale);
+    if (level == a.max_level) {
+      next.x = next.x * lscale;
+      next.y = next.y * lscale;
+    } else {
+      next.x = next.x * 2.f;
+      next.y = next.y * 2.f;
+    }
+    prevPt.x -= half;
+    prevPt.y -= half;
+    const int ipx = __float2int_rd(prevPt.x), ipy = __float2int_rd(prevPt.y);
+    if (ipx < -win || ipx >= cols || ipy < -win || ipy >= rows) {
+      if (level == 0) ok = false;
+      continue;
+    }
+    const float fa = prevPt.x - ipx, fb = prevPt.y - ipy;
+    const int iw00 = __float2int_rn((1.f - fa) * (1.f - fb) * 16384.f);
+    const int iw01 = __float2int_rn(fa * (1.f - fb) * 16384.f);
+    const int iw10 = __float2int_rn((1.f - fa) * fb * 16384.f);
+    const int iw11 = 16384 - iw00 - iw01 - iw10;
+
+    const uint8_t *I = a.p0[level];
+    const int pitchI = a.pitch0[level];
+    __syncwarp();
+    for (int i = lane; i < np * np; i += 32) {
+      int r = i / np, c = i - r * np;
+      int x = reflect101(ipx - 1 + c, cols), y = reflect101(ipy - 1 + r, rows);
+      raw[i] = I[(size_t)y * pitchI + x];
+    }
+    __syncwarp();
+    for (int i = lane; i < nd * nd; i += 32) {
+      int r = i / nd, c = i - r * nd;
+      int gx = ipx + c, gy = ipy + r;
+      int vx = 0, vy = 0;
+      if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
+        const uint8_t *q = raw + (r + 1) * np + (c + 1);
+        int tl = q[-np - 1], tc = q[-np], tr = q[-np + 1];
+        int ml = q[-1], mr = q[1];
+        int bl = q[np - 1], bc = q[np], br = q[np + 1];
+        vx = 3 * (tr + br) + 10 * mr - 3 * (tl + bl) - 10 * ml;
+        vy = 3 * (bl + br) + 10 * bc - 3 * (tl + tr) - 10 * tc;
+      }
+      ddx[i] = (short)vx;
+      ddy[i] = (short)vy;
+    }
+    __syncwarp();
+    // this lane's 2 x 4 block of the interpolated patches
+    int Iw[8], Ixw[8], Iyw[8];
+    float A11 = 0, A12 = 0, A22 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int y = r0 + (k >> 2), x = c0 + (k & 3);
+      int ival = 0, ixval = 0, iyval = 0;
+      if (y < win && x < win) {
+        const uint8_t *q = raw + (y + 1) * np + (x + 1);
+        ival = (q[0] * iw00 + q[1] * iw01 + q[np] * iw10 + q[np + 1] * iw11 + (1 << 8)) >> 9;
+        const int di = y * nd + x;
+        ixval = (ddx[di] * iw00 + ddx[di + 1] * iw01 + ddx[di + nd] * iw10 + ddx[di + nd + 1] * iw11 + (1 << 13)) >> 14;
+        iyval = (ddy[di] * iw00 + ddy[di + 1] * iw01 + ddy[di + nd] * iw10 + ddy[di + nd + 1] * iw11 + (1 << 13)) >> 14;
+      }
+      Iw[k] = ival; Ixw[k] = ixval; Iyw[k] = iyval;
+      A11 += (float)(ixval * ixval);
+      A12 += (float)(ixval * iyval);
+      A22 += (float)(iyval * iyval);
+    }
+    A11 = warp_sum(A11) * FLT_SCALE;
+    A12 = warp_sum(A12) * FLT_SCALE;
+    A22 = warp_sum(A22) * FLT_SCALE;
+    float Dt = A11 * A22 - A12 * A12;
+    const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+    if (minEig < a.min_eig || Dt < FLT_EPSILON) {
+      if (level == 0) ok = false;
+      continue;
+    }
+    Dt = 1.f / Dt;
+    float2 result = next;   // nextPts[ptidx] as stored by OpenCV; only rewritten after an update step
+    next.x -= half;
+    next.y -= half;
+    float2 prevDelta = make_float2(0.f, 0.f);
+    const uint8_t *J = a.p1[level];
+    const int pitchJ = a.pitch1[level];
+    int jb[3][5];
+    int cached_x = INT_MIN, cached_y = INT_MIN;
+    for (int j = 0; j < a.max_count; j++) {
+      const int inx = __float2int_rd(next.x), iny = __float2int_rd(next.y);
+      if (inx < -win || inx >= cols || iny < -win || iny >= rows) {
+        if (level == 0) ok = false;
+        break;
+      }
+      const float ja = next.x - inx, jbf = next.y - iny;
+      const int jw00 = __float2int_rn((1.f - ja) * (1.f - jbf) * 16384.f);
+      const int jw01 = __float2int_rn(ja * (1.f - jbf) * 16384.f);
+      const int jw10 = __float2int_rn((1.f - ja) * jbf * 16384.f);
+      const int jw11 = 16384 - jw00 - jw01 - jw10;
+      if (inx != cached_x || iny != cached_y) {   // warp-uniform
+        cached_x = inx;
+        cached_y = iny;
+        const bool inside = inx >= 0 && iny >= 0 && inx + win < cols && iny + win < rows;
+        if (inside) {
+          const uint8_t *Jp = J + (size_t)(iny + r0) * pitchJ + inx + c0;
+#pragma unroll
+          for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 5; c++) jb[r][c] = Jp[(size_t)r * pitchJ + c];
+        } else {
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            const uint8_t *row = J + (size_t)reflect101(iny + r0 + r, rows) * pitchJ;
+#pragma unroll
+            for (int c = 0; c < 5; c++) jb[r][c] = row[reflect101(inx + c0 + c, cols)];
+          }
+        }
+      }
+      float b1 = 0, b2 = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int r = k >> 2, c = k & 3;
+        const int jv = (jb[r][c] * jw00 + jb[r][c + 1] * jw01 + jb[r + 1][c] * jw10 + jb[r + 1][c + 1] * jw11 + (1 << 8)) >> 9;
+        const int diff = jv - Iw[k];
+        b1 += (float)(diff * Ixw[k]);
+        b2 += (float)(diff * Iyw[k]);
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        b1 += __shfl_xor_sync(0xffffffffu, b1, d);
+        b2 += __shfl_xor_sync(0xffffffffu, b2, d);
+      }
+      b1 *= FLT_SCALE;
+      b2 *= FLT_SCALE;
+      const float2 delta = make_float2((A12 * b2 - A22 * b1) * Dt, (A12 * b1 - A11 * b2) * Dt);
+      next.x += delta.x;
+      next.y += delta.y;
+      result = make_float2(next.x + half, next.y + half);
+      if ((double)delta.x * (double)delta.x + (double)delta.y * (double)delta.y <= (double)a.eps_sq) break;
+      if (j > 0 && fabs((double)(delta.x + prevDelta.x)) < 0.01 && fabs((double)(delta.y + prevDelta.y)) < 0.01) {
+        result.x -= delta.x * 0.5f;
+        result.y -= delta.y * 0.5f;
+        break;
+      }
+      prevDelta = delta;
+    }
+    next = result;
+    if (level == 0 && ok) {
+      int fx = __float2int_rd(next.x - half), fy = __float2int_rd(next.y - half);
+      if (fx < -win || fx >= cols || fy < -win || fy >= rows) ok = false;
+    }
+  }
+  if (lane == 0) {
+    pts1[pi] = next;
+    status[pi] = ok ? 1 : 0;
+  }
+  if (a.undistort) {
+    if (lane == 0) p0n[pi] = undistort_radtan(prev_in, a.calib.K, a.calib.D);
+    if (lane == 1) p1n[pi] = undistort_radtan(next, a.calib.K, a.calib.D);
+  }
+}
+
 void launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *d_pts0, float2 *d_pts1, uint8_t *d_status,
                float2 *d_p0n, float2 *d_p1n, int n, const LkParams &prm, cudaStream_t s) {
   if (n <= 0) return;
@@ -371,6 +567,10 @@ void launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *d_pts0, f
   a.min_eig = prm.min_eig;
   a.undistort = prm.undistort;
   for (int i = 0; i < 4; i++) { a.calib.K[i] = prm.K[i]; a.calib.D[i] = prm.D[i]; }
+  if (prm.win == kW15) {
+    k_lk15<<<(n + kLk15Warps - 1) / kLk15Warps, kLk15Warps * 32, 0, s>>>(a, d_pts0, d_pts1, d_status, d_p0n, d_p1n, n);
+    return;
+  }
   const int win = prm.win, np = win + 3, nd = win + 1, nw = win * win;
   const int per_warp = ((np * np + 15) & ~15) + 2 * ((nd * nd * 2 + 15) & ~15) + 3 * ((nw * 2 + 15) & ~15);
   size_t smem = (size_t)per_warp * kLkWarps;
