@@ -40,7 +40,7 @@ WORKLOAD = dict(width=1280, height=560, num_features=400, fast_threshold=20, gri
                 pyr_levels=4, win_size=15)
 WORKLOAD_NAME = "BASELINE.json configs[1]: synthetic KAIST-shaped 1280x560 mono, point+line front end, 400 pts, 5x5 grid, maxLevel 4, win 15"
 SEQ_FRAMES = 300
-LOOKAHEAD = 16
+LOOKAHEAD = 24
 METRIC = "front-end frames/sec @1280x560"
 
 

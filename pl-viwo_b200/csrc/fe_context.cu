@@ -141,7 +141,10 @@ int FeContext::init() {
   }
   occ_bits_.assign((size_t)((W_ + 63) / 64) * H_, 0);
   layout_cells();
-  worker_ = std::thread([this] { worker_main(); });
+  const char *nw_env = std::getenv("PLVIWO_WORKERS");
+  int nworkers = nw_env ? std::atoi(nw_env) : 2;
+  if (nworkers < 1) nworkers = 1;
+  for (int i = 0; i < nworkers; i++) workers_.emplace_back([this] { worker_main(); });
 
   max_pts_ = std::max(4096, 8 * cfg_.num_features) + 4096 * (cfg_.line_samples > 0 ? 8 : 0);
   FE_CUDA(cudaMalloc(&d_pts0_, (size_t)max_pts_ * sizeof(float2)));
@@ -164,7 +167,8 @@ FeContext::~FeContext() {
     wstop_ = true;
   }
   wcv_.notify_all();
-  if (worker_.joinable()) worker_.join();
+  for (auto &w : workers_)
+    if (w.joinable()) w.join();
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
   for (FrameSlot &s : slots_) {
@@ -537,10 +541,15 @@ int FeContext::run_predetection(FrameSlot &s) {
     worker_error_ = std::string(what) + ": " + cudaGetErrorString(e);
     return FE_CUDA_ERROR;
   };
-  HostTimer wt(&worker_ms_[0]);
+  double wl[4] = {0, 0, 0, 0};
+  struct Flush {
+    FeContext *c; double *l;
+    ~Flush() { std::lock_guard<std::mutex> lk(c->wstat_mu_); for (int i = 0; i < 4; i++) c->worker_ms_[i] += l[i]; }
+  } flush{this, wl};
+  HostTimer wt(&wl[0]);
   cudaError_t e;
   {
-    HostTimer w1(&worker_ms_[1]);
+    HostTimer w1(&wl[1]);
     if (wait_flag(&s.h_flags[0], s.seq_fast, s.s_b, &worker_error_)) return FE_CUDA_ERROR;
     e = cudaSuccess;
   }
@@ -555,14 +564,14 @@ int FeContext::run_predetection(FrameSlot &s) {
   const int spec = std::min(16384, kps_cap_);
   const int total = std::min(s.h_band[0], kps_cap_);
   if (total > spec) {
-    e = cudaMemcpyAsync(s.h_kps + spec, s.d_kps + spec, (size_t)(total - spec) * sizeof(unsigned), cudaMemcpyDeviceToHost, s_det2_);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s_det2_);
+    e = cudaMemcpyAsync(s.h_kps + spec, s.d_kps + spec, (size_t)(total - spec) * sizeof(unsigned), cudaMemcpyDeviceToHost, s.s_b);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.s_b);
     if (e != cudaSuccess) return bad(e, "keypoint tail copy");
     worker_d2h_ += (uint64_t)(total - spec) * sizeof(unsigned);
   }
   const int *band_off = s.h_band + 1, *band_cnt = s.h_band + 1 + ntab;
   std::vector<KpSort> kps;
-  HostTimer *w2 = new HostTimer(&worker_ms_[2]);
+  HostTimer *w2 = new HostTimer(&wl[2]);
   for (int c = 0; c < ncell; c++) {
     kps.clear();
     for (int b = 0; b < nb; b++) {
@@ -584,14 +593,14 @@ int FeContext::run_predetection(FrameSlot &s) {
   const int nc = (int)s.cand_sel.size();
   s.cand_ref.resize(nc);
   if (nc > 0) {
-    HostTimer w3(&worker_ms_[3]);
+    HostTimer w3(&wl[3]);
     // zero-copy: the kernel refines the candidates in place in pinned host memory
     for (int i = 0; i < nc; i++) s.h_cand_out[i] = make_float2(s.cand_sel[i].x, s.cand_sel[i].y);
-    launch_corner_subpix(s.pyr.lvl[0], s.h_cand_out, nc, s_det2_);
-    launch_signal(&s.h_flags[1], ++s.seq_subpix, s_det2_);
+    launch_corner_subpix(s.pyr.lvl[0], s.h_cand_out, nc, s.s_b);
+    launch_signal(&s.h_flags[1], ++s.seq_subpix, s.s_b);
     e = cudaGetLastError();
     if (e != cudaSuccess) return bad(e, "cornerSubPix launch");
-    if (wait_flag(&s.h_flags[1], s.seq_subpix, s_det2_, &worker_error_)) return FE_CUDA_ERROR;
+    if (wait_flag(&s.h_flags[1], s.seq_subpix, s.s_b, &worker_error_)) return FE_CUDA_ERROR;
     worker_launches_ += 2;
     worker_h2d_ += (uint64_t)nc * sizeof(float2);
     worker_d2h_ += (uint64_t)nc * sizeof(float2);
@@ -1071,8 +1080,15 @@ int FeContext::lsd_feed(FrameSlot &cur, FeFrameInfo *info) {
   std::vector<float4> filt_lines;
   std::vector<uint64_t> filt_ids;
   const int npt = (int)points.size();
-  std::vector<float> spx(npt), spy(npt);
-  std::vector<uint8_t> pass(npt + 8);
+  std::vector<float> &spx = sc_px_, &spy = sc_py_;
+  std::vector<uint8_t> &pass = sc_pass_;
+  spx.resize(npt);
+  spy.resize(npt);
+  pass.resize(npt + 8);
+  pol_new.reserve(64);
+  positions.reserve(64);
+  filt_lines.reserve(64);
+  filt_ids.reserve(64);
   for (int j = 0; j < npt; j++) {
     spx[j] = points[j].x;
     spy[j] = points[j].y;

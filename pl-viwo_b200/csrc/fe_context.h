@@ -170,7 +170,7 @@ class FeContext {
   bool use_graphs_ = true;
   std::vector<uint64_t> occ_bits_;
   cudaStream_t s_det_ = nullptr, s_det2_ = nullptr;
-  std::thread worker_;
+  std::vector<std::thread> workers_;      // pre-detection workers (frames are independent: any worker takes any frame)
   std::mutex wmu_;
   std::condition_variable wcv_;
   std::deque<int> wqueue_;
@@ -178,6 +178,9 @@ class FeContext {
   std::atomic<uint64_t> worker_launches_{0}, worker_h2d_{0}, worker_d2h_{0};
   std::string worker_error_;
   double worker_ms_[4] = {0, 0, 0, 0};
+  std::mutex wstat_mu_;
+  std::vector<float> sc_px_, sc_py_;      // scratch of the line tracker
+  std::vector<uint8_t> sc_pass_;
   // ---- tracking scratch
   int max_pts_ = 0;
   float2 *d_pts0_ = nullptr, *d_pts1_ = nullptr, *d_p0n_ = nullptr, *d_p1n_ = nullptr;

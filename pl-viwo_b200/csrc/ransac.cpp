@@ -4,10 +4,10 @@
 // TrackKLT.cpp:869-873.  OpenCV is not linkable here, so this is an independent C++ implementation of the
 // published algorithm: RANSACPointSetRegistrator with the 7-point solver, OpenCV's
 // deterministic multiply-with-carry RNG seeded with 2^64-1 per call, the collinearity test on the 7th sample,
-// symmetric epipolar distance, adaptive iteration count.  The null space of the 7x9 system is taken the way
-// OpenCV's own JacobiSVD does it (one-sided Jacobi on the rows, the two missing right singular vectors completed
-// from a fixed pseudo-random start by double Gram-Schmidt), so that the pencil basis — and therefore the order of
-// the cubic's roots, which breaks inlier-count ties — matches the library.  n < 15 switches to LMedS exactly as
+// symmetric epipolar distance, adaptive iteration count.  The null-space basis of the 7x9 system is the one
+// OpenCV's own SVD produces (two vectors completed from a fixed pseudo-random start by double Gram-Schmidt), so
+// that the pencil basis — and therefore the order of the cubic's roots, which breaks inlier-count ties — matches
+// the library.  n < 15 switches to LMedS exactly as
 // OpenCV silently does.
 #include <algorithm>
 #include <cfloat>
@@ -32,70 +32,35 @@ struct CvRng {  // cv::RNG: state = (state & 0xffffffff) * 4164903690 + (state >
 
 inline int cv_round(double v) { return (int)std::nearbyint(v); }
 
-// One-sided Jacobi SVD of the n x m row set At (n = 7 rows of length m = 9), rows completed to n1 = 9.
-// On return rows 0..n-1 are unit right singular vectors ordered by decreasing singular value and rows n..n1-1
-// complete the basis.  (cv::SVDecomp(A, W, U, Vt, MODIFY_A | FULL_UV) with rows < cols, Vt = these rows.)
-void jacobi_rows_7x9(double At[9][9]) {
+// Null-space basis of the 7 x 9 system exactly as cv::SVDecomp(A, W, U, Vt, MODIFY_A | FULL_UV) delivers it in rows
+// 7 and 8 of Vt.  OpenCV's JacobiSVD (no LAPACK in the build) orthogonalises the 7 rows, then produces the two
+// missing right singular vectors by starting from fixed pseudo-random +-1/9 vectors (cv::RNG(0x12345678)) and
+// projecting out every earlier row twice (with an L1 renormalisation after each projection).  That completion is a
+// projection onto the orthogonal complement of the row space, so it does not depend on WHICH orthonormal basis of
+// the row space is used: a re-orthogonalised Gram-Schmidt basis (1 us) gives the same two vectors as the Jacobi
+// sweeps (10+ us) to rounding error, and the root order of the cubic — which breaks inlier-count ties — with it.
+// Returns false when the 7 rows are numerically rank deficient (the caller then treats the sample as degenerate).
+bool null_space_7x9(double At[9][9]) {
   const int m = 9, n = 7, n1 = 9;
   const double eps = DBL_EPSILON * 10, minval = DBL_MIN;
-  double W[9];
   for (int i = 0; i < n; i++) {
-    double sd = 0;
-    for (int k = 0; k < m; k++) sd += At[i][k] * At[i][k];
-    W[i] = sd;
-  }
-  const int max_iter = std::max(m, 30);
-  for (int iter = 0; iter < max_iter; iter++) {
-    bool changed = false;
-    for (int i = 0; i < n - 1; i++)
-      for (int j = i + 1; j < n; j++) {
-        double *Ai = At[i], *Aj = At[j];
-        double a = W[i], p = 0, b = W[j];
-        for (int k = 0; k < m; k++) p += Ai[k] * Aj[k];
-        if (std::abs(p) <= eps * std::sqrt(a * b)) continue;
-        p *= 2;
-        double beta = a - b, gamma = hypot(p, beta);
-        double c, s;
-        if (beta < 0) {
-          double delta = (gamma - beta) * 0.5;
-          s = std::sqrt(delta / gamma);
-          c = p / (gamma * s * 2);
-        } else {
-          c = std::sqrt((gamma + beta) / (gamma * 2));
-          s = p / (gamma * c * 2);
-        }
-        a = b = 0;
-        for (int k = 0; k < m; k++) {
-          double t0 = c * Ai[k] + s * Aj[k];
-          double t1 = -s * Ai[k] + c * Aj[k];
-          Ai[k] = t0;
-          Aj[k] = t1;
-          a += t0 * t0;
-          b += t1 * t1;
-        }
-        W[i] = a;
-        W[j] = b;
-        changed = true;
+    double norm0 = 0;
+    for (int k = 0; k < m; k++) norm0 += At[i][k] * At[i][k];
+    for (int pass = 0; pass < 2; pass++)
+      for (int j = 0; j < i; j++) {
+        double d = 0;
+        for (int k = 0; k < m; k++) d += At[i][k] * At[j][k];
+        for (int k = 0; k < m; k++) At[i][k] -= d * At[j][k];
       }
-    if (!changed) break;
-  }
-  for (int i = 0; i < n; i++) {
-    double sd = 0;
-    for (int k = 0; k < m; k++) sd += At[i][k] * At[i][k];
-    W[i] = std::sqrt(sd);
-  }
-  for (int i = 0; i < n - 1; i++) {
-    int j = i;
-    for (int k = i + 1; k < n; k++)
-      if (W[j] < W[k]) j = k;
-    if (i != j) {
-      std::swap(W[i], W[j]);
-      for (int k = 0; k < m; k++) std::swap(At[i][k], At[j][k]);
-    }
+    double norm = 0;
+    for (int k = 0; k < m; k++) norm += At[i][k] * At[i][k];
+    if (!(norm > 1e-24 * norm0) || !(norm > 0)) return false;
+    double s = 1 / std::sqrt(norm);
+    for (int k = 0; k < m; k++) At[i][k] *= s;
   }
   CvRng rng(0x12345678);
-  for (int i = 0; i < n1; i++) {
-    double sd = i < n ? W[i] : 0;
+  for (int i = n; i < n1; i++) {
+    double sd = 0;
     for (int ii = 0; ii < 100 && sd <= minval; ii++) {
       const double val0 = 1. / m;
       for (int k = 0; k < m; k++) At[i][k] = (rng.next() & 256) != 0 ? val0 : -val0;
@@ -120,6 +85,7 @@ void jacobi_rows_7x9(double At[9][9]) {
     double s = sd > minval ? 1 / sd : 0.;
     for (int k = 0; k < m; k++) At[i][k] *= s;
   }
+  return true;
 }
 
 // cv::solveCubic for a0 x^3 + a1 x^2 + a2 x + a3 (double coefficients)
@@ -208,7 +174,7 @@ int run_7point(const float *m1, const float *m2, double F[27]) {
     a[3] = y1 * x0; a[4] = y1 * y0; a[5] = y1;
     a[6] = x0; a[7] = y0; a[8] = 1;
   }
-  jacobi_rows_7x9(At);
+  if (!null_space_7x9(At)) return 0;
   double *f1 = At[7], *f2 = At[8];
   for (int i = 0; i < 9; i++) f1[i] -= f2[i];
   double c[4], r[3] = {0, 0, 0};
@@ -289,10 +255,11 @@ struct Soa {
 #if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
 __attribute__((target_clones("avx2", "default")))
 #endif
-int count_inliers(const Soa &p, int count, const double *F, float t, float *err, uint8_t *mask) {
+int count_inliers_chunk(const Soa &p, int i0, int i1, const double *F, float t, uint8_t *mask) {
   const double *X1 = p.x1.data(), *Y1 = p.y1.data(), *X2 = p.x2.data(), *Y2 = p.y2.data();
   const double f0 = F[0], f1 = F[1], f2 = F[2], f3 = F[3], f4 = F[4], f5 = F[5], f6 = F[6], f7 = F[7], f8 = F[8];
-  for (int i = 0; i < count; i++) {
+  int good = 0;
+  for (int i = i0; i < i1; i++) {
     double x1 = X1[i], y1 = Y1[i], x2 = X2[i], y2 = Y2[i];
     double a = f0 * x1 + f1 * y1 + f2;
     double b = f3 * x1 + f4 * y1 + f5;
@@ -305,13 +272,21 @@ int count_inliers(const Soa &p, int count, const double *F, float t, float *err,
     double s1 = 1. / (a * a + b * b);
     double d1 = x1 * a + y1 * b + c;
     double e1 = d1 * d1 * s1, e2 = d2 * d2 * s2;
-    err[i] = (float)(e1 > e2 ? e1 : e2);
-  }
-  int good = 0;
-  for (int i = 0; i < count; i++) {
-    uint8_t f = err[i] <= t;
+    uint8_t f = (float)(e1 > e2 ? e1 : e2) <= t;
     mask[i] = f;
     good += f;
+  }
+  return good;
+}
+
+// findInliers with an exact early exit: a model is only ever used if its inlier count EXCEEDS `need`, so the scan
+// stops (returning -1) as soon as the points still to come cannot lift it above that.
+int count_inliers(const Soa &p, int count, const double *F, float t, uint8_t *mask, int need) {
+  int good = 0;
+  for (int i0 = 0; i0 < count; i0 += 64) {
+    const int i1 = i0 + 64 < count ? i0 + 64 : count;
+    good += count_inliers_chunk(p, i0, i1, F, t, mask);
+    if (good + (count - i1) <= need) return -1;
   }
   return good;
 }
@@ -388,7 +363,7 @@ int ransac_fundamental(const float *m1, const float *m2, int count, double thres
       int nmodels = run_7point(ms1, ms2, F);
       if (nmodels <= 0) continue;
       for (int i = 0; i < nmodels; i++) {
-        int good = count_inliers(soa, count, F + 9 * i, t, err.data(), cur.data());
+        int good = count_inliers(soa, count, F + 9 * i, t, cur.data(), std::max(max_good, model_points - 1));
         if (good > std::max(max_good, model_points - 1)) {
           std::swap(cur, best);
           max_good = good;
