@@ -134,13 +134,11 @@ int plviwo_fe_set_calib(FeHandle *h, const double K[4], const double D[4]) {
 }
 int plviwo_fe_set_num_features(FeHandle *h, int n) {
   if (!h || n < 1) return FE_BAD_ARG;
-  h->ctx->set_num_features(n);
-  return FE_OK;
+  return h->ctx->set_num_features(n);
 }
 int plviwo_fe_change_feat_id(FeHandle *h, uint64_t id_old, uint64_t id_new) {
   if (!h) return FE_BAD_ARG;
-  h->ctx->change_feat_id(id_old, id_new);
-  return FE_OK;
+  return h->ctx->change_feat_id(id_old, id_new);
 }
 
 int plviwo_fe_feed(FeHandle *h, double timestamp, const uint8_t *image, int width, int height, int stride,
@@ -184,12 +182,12 @@ extern "C" {
 
 int plviwo_fe_get_point_rows(FeHandle *h, FePointRow *out, int cap, int *n_out) {
   if (!h) return FE_BAD_ARG;
-  return copy_out(h->ctx->point_rows, out, cap, n_out);
+  return copy_out(h->ctx->result().point_rows, out, cap, n_out);
 }
 int plviwo_fe_get_last_obs(FeHandle *h, uint64_t *ids, float *uv, int cap, int *n_out) {
   if (!h) return FE_BAD_ARG;
-  const auto &p = h->ctx->get_last_obs();
-  const auto &id = h->ctx->get_last_ids();
+  const auto &p = h->ctx->result().obs;
+  const auto &id = h->ctx->result().obs_ids;
   if (n_out) *n_out = (int)p.size();
   if (!ids && !uv) return FE_OK;
   if (cap < (int)p.size()) return FE_OVERFLOW;
@@ -204,19 +202,19 @@ int plviwo_fe_get_last_obs(FeHandle *h, uint64_t *ids, float *uv, int cap, int *
 }
 int plviwo_fe_get_line_rows(FeHandle *h, FeLineRow *out, int cap, int *n_out) {
   if (!h) return FE_BAD_ARG;
-  return copy_out(h->ctx->line_rows, out, cap, n_out);
+  return copy_out(h->ctx->result().line_rows, out, cap, n_out);
 }
 int plviwo_fe_get_line_points(FeHandle *h, FeLinePoint *out, int cap, int *n_out) {
   if (!h) return FE_BAD_ARG;
-  return copy_out(h->ctx->line_points, out, cap, n_out);
+  return copy_out(h->ctx->result().line_points, out, cap, n_out);
 }
 int plviwo_fe_get_line_samples(FeHandle *h, float *uv01, uint8_t *status, int cap, int *n_out) {
   if (!h) return FE_BAD_ARG;
-  const auto &s = h->ctx->sample_status;
+  const auto &s = h->ctx->result().sample_status;
   if (n_out) *n_out = (int)s.size();
   if (!uv01 && !status) return FE_OK;
   if (cap < (int)s.size()) return FE_OVERFLOW;
-  if (uv01 && !s.empty()) std::memcpy(uv01, h->ctx->sample_uv.data(), s.size() * 4 * sizeof(float));
+  if (uv01 && !s.empty()) std::memcpy(uv01, h->ctx->result().sample_uv.data(), s.size() * 4 * sizeof(float));
   if (status && !s.empty()) std::memcpy(status, s.data(), s.size());
   return FE_OK;
 }

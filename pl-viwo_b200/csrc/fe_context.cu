@@ -35,14 +35,54 @@ struct HostTimer {  // accumulates wall time into FeStageTimes::host_ms[idx]
 };
 }  // namespace
 
-// cudaMemcpyAsync with byte accounting (FeStageTimes::h2d_bytes / d2h_bytes)
-#define FE_COPY(dst, src, bytes, kind, stream)                                   \
+// cudaMemcpyAsync with byte accounting (FeStageTimes::h2d_bytes / d2h_bytes) into the calling thread's statistics
+#define FE_COPY(st, dst, src, bytes, kind, stream)                               \
   do {                                                                           \
     size_t b__ = (bytes);                                                        \
-    if ((kind) == cudaMemcpyHostToDevice) times.h2d_bytes += b__;                \
-    if ((kind) == cudaMemcpyDeviceToHost) times.d2h_bytes += b__;                \
+    if ((kind) == cudaMemcpyHostToDevice) (st).h2d_bytes += b__;                 \
+    if ((kind) == cudaMemcpyDeviceToHost) (st).d2h_bytes += b__;                 \
     FE_CUDA(cudaMemcpyAsync((dst), (src), b__, (kind), (stream)));               \
   } while (0)
+
+// Error text of the calling thread; the public entry points copy it into FeContext::last_error, the tracker threads
+// into the frame's FrameResult.
+static thread_local std::string t_err;
+
+static inline void cpu_pause() {
+#if defined(__x86_64__)
+  __builtin_ia32_pause();
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------ WorkQueue
+void WorkQueue::push(int v) {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    q_.push_back(v);
+  }
+  n_.fetch_add(1, std::memory_order_release);
+  cv_.notify_one();
+}
+bool WorkQueue::pop(int *v) {
+  for (int spins = 0; spins < 20000; spins++) {   // ~1 ms
+    if (n_.load(std::memory_order_acquire) > 0 || stop_.load(std::memory_order_relaxed)) break;
+    cpu_pause();
+  }
+  std::unique_lock<std::mutex> lk(mu_);
+  cv_.wait(lk, [this] { return stop_.load() || !q_.empty(); });
+  if (q_.empty()) return false;
+  *v = q_.front();
+  q_.pop_front();
+  n_.fetch_sub(1, std::memory_order_relaxed);
+  return true;
+}
+void WorkQueue::stop() {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    stop_.store(true);
+  }
+  cv_.notify_all();
+}
 
 FeContext::FeContext(const FeConfig &cfg, int device) : cfg_(cfg), device_(device), W_(cfg.width), H_(cfg.height) {
   currid_ = 4 * (uint64_t)cfg.numaruco + 1;  // TrackBase.cpp:34
@@ -50,8 +90,32 @@ FeContext::FeContext(const FeConfig &cfg, int device) : cfg_(cfg), device_(devic
 }
 
 int FeContext::fail(cudaError_t e, const char *what) {
-  last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  t_err = std::string(what) + ": " + cudaGetErrorString(e);
   return FE_CUDA_ERROR;
+}
+int FeContext::err(int code, const std::string &msg) {
+  t_err = msg;
+  return code;
+}
+
+void FeContext::flush_stats(FeStageTimes &l) {
+  std::lock_guard<std::mutex> lk(wstat_mu_);
+  for (int i = 0; i < 16; i++) {
+    times_.ms[i] += l.ms[i];
+    times_.launches[i] += l.launches[i];
+    times_.host_ms[i] += l.host_ms[i];
+  }
+  times_.frames += l.frames;
+  times_.kernel_launches_total += l.kernel_launches_total;
+  times_.h2d_bytes += l.h2d_bytes;
+  times_.d2h_bytes += l.d2h_bytes;
+  l = FeStageTimes{};
+}
+void FeContext::reset_times() {
+  std::lock_guard<std::mutex> lk(wstat_mu_);
+  times_ = FeStageTimes{};
+  worker_launches_ = 0; worker_h2d_ = 0; worker_d2h_ = 0;
+  for (double &v : worker_ms_) v = 0;
 }
 
 int FeContext::alloc_image(DevImage &im, int w, int h) {
@@ -142,9 +206,11 @@ int FeContext::init() {
   occ_bits_.assign((size_t)((W_ + 63) / 64) * H_, 0);
   layout_cells();
   const char *nw_env = std::getenv("PLVIWO_WORKERS");
-  int nworkers = nw_env ? std::atoi(nw_env) : 2;
+  int nworkers = nw_env ? std::atoi(nw_env) : 3;
   if (nworkers < 1) nworkers = 1;
   for (int i = 0; i < nworkers; i++) workers_.emplace_back([this] { worker_main(); });
+  klt_thread_ = std::thread([this] { klt_main(); });
+  line_thread_ = std::thread([this] { line_main(); });
 
   max_pts_ = std::max(4096, 8 * cfg_.num_features) + 4096 * (cfg_.line_samples > 0 ? 8 : 0);
   FE_CUDA(cudaMalloc(&d_pts0_, (size_t)max_pts_ * sizeof(float2)));
@@ -162,6 +228,10 @@ int FeContext::init() {
 }
 
 FeContext::~FeContext() {
+  klt_q_.stop();
+  if (klt_thread_.joinable()) klt_thread_.join();
+  line_q_.stop();
+  if (line_thread_.joinable()) line_thread_.join();
   {
     std::lock_guard<std::mutex> lk(wmu_);
     wstop_ = true;
@@ -209,9 +279,7 @@ int FeContext::spin_sync(cudaStream_t st) {
     cudaError_t e = cudaEventQuery(ev_sync_);
     if (e == cudaSuccess) return FE_OK;
     if (e != cudaErrorNotReady) return fail(e, "cudaEventQuery");
-#if defined(__x86_64__)
-    __builtin_ia32_pause();
-#endif
+    cpu_pause();
   }
 }
 
@@ -220,9 +288,7 @@ int FeContext::spin_sync(cudaStream_t st) {
 int FeContext::wait_flag(volatile int *flag, int value, cudaStream_t st, std::string *err) {
   unsigned spins = 0;
   while (*flag != value) {
-#if defined(__x86_64__)
-    __builtin_ia32_pause();
-#endif
+    cpu_pause();
     if ((++spins & 0x1fffff) == 0) {
       cudaError_t e = cudaStreamQuery(st);
       if (e != cudaSuccess && e != cudaErrorNotReady) {
@@ -242,14 +308,35 @@ int FeContext::set_calib(const double K[4], const double D[4]) {
   return FE_OK;
 }
 
-void FeContext::change_feat_id(uint64_t id_old, uint64_t id_new) {  // TrackBase.cpp:267-285 (tracker side)
+// The tracker state belongs to the tracker threads while frames are in flight: the two setters below are only legal
+// between frames (nothing submitted and not yet collected), which is the only place the reference can call them too.
+int FeContext::change_feat_id(uint64_t id_old, uint64_t id_new) {  // TrackBase.cpp:267-285 (tracker side)
+  if (!queue_.empty()) {
+    last_error = "change_feat_id: collect the pending frames first";
+    return FE_BAD_ARG;
+  }
   for (uint64_t &id : ids_last_)
     if (id == id_old) id = id_new;
+  if (cur_res_ != &state_res_) {   // keep get_last_obs / get_last_ids in step
+    FrameResult &r = const_cast<FrameResult &>(*cur_res_);
+    for (uint64_t &id : r.obs_ids)
+      if (id == id_old) id = id_new;
+  }
+  for (uint64_t &id : state_res_.obs_ids)
+    if (id == id_old) id = id_new;
+  return FE_OK;
+}
+int FeContext::set_num_features(int n) {
+  if (!queue_.empty()) {
+    last_error = "set_num_features: collect the pending frames first";
+    return FE_BAD_ARG;
+  }
+  cfg_.num_features = n;
+  return FE_OK;
 }
 
 // cv::undistortPoints on one point (Appendix A6) — only for the two endpoints of each line row
-void FeContext::undistort_host(float u, float v, float &un, float &vn) const {
-  const double *K = cfg_.K, *D = cfg_.D;
+void FeContext::undistort_host(const double K[4], const double D[4], float u, float v, float &un, float &vn) {
   double x0 = ((double)u - K[2]) / K[0], y0 = ((double)v - K[3]) / K[1];
   double x = x0, y = y0;
   for (int j = 0; j < 5; j++) {
@@ -391,24 +478,29 @@ int FeContext::enqueue_frame_independent(FrameSlot &s) {
   s.warmed = true;
   // bookkeeping (identical for both ways of issuing the work)
   const int ncell = (int)cells_.size(), ntab = ncell * cells_nb_;
-  times.kernel_launches_total += (cfg_.histogram_method == FE_HIST_HISTOGRAM ? 1 : 0) + 1 + std::max(s.pyr.n - 2, 0) +
+  mst_.kernel_launches_total += (cfg_.histogram_method == FE_HIST_HISTOGRAM ? 1 : 0) + 1 + std::max(s.pyr.n - 2, 0) +
                                  (ncell > 0 ? 1 : 0) + 1 + (lines ? 11 : 0);
-  if (ncell > 0) times.d2h_bytes += sizeof(unsigned) + (size_t)2 * ntab * sizeof(int) + (size_t)std::min(16384, kps_cap_) * sizeof(unsigned);
-  if (lines) times.d2h_bytes += 2 * sizeof(int) + 1024 * sizeof(float4);
+  if (ncell > 0) mst_.d2h_bytes += sizeof(unsigned) + (size_t)2 * ntab * sizeof(int) + (size_t)std::min(16384, kps_cap_) * sizeof(unsigned);
+  if (lines) mst_.d2h_bytes += 2 * sizeof(int) + 1024 * sizeof(float4);
   return FE_OK;
 }
 
 int FeContext::submit(double t, const uint8_t *image, int stride, bool on_device, const uint8_t *mask, int mask_stride,
                       const double vp[6]) {
-  HostTimer ht(&times.host_ms[0]);
+  int rc = submit_impl(t, image, stride, on_device, mask, mask_stride, vp);
+  if (rc) last_error = t_err;
+  flush_stats(mst_);
+  return rc;
+}
+
+int FeContext::submit_impl(double t, const uint8_t *image, int stride, bool on_device, const uint8_t *mask, int mask_stride,
+                           const double vp[6]) {
+  HostTimer ht(&mst_.host_ms[0]);
   FE_CUDA(cudaSetDevice(device_));
   int si = -1;
   for (int i = 0; i < (int)slots_.size(); i++)
     if (!slots_[i].busy && i != last_slot_) { si = i; break; }
-  if (si < 0) {
-    last_error = "submit: lookahead window full (collect a frame first)";
-    return FE_BAD_ARG;
-  }
+  if (si < 0) return err(FE_BAD_ARG, "submit: lookahead window full (collect a frame first)");
   FrameSlot &s = slots_[si];
   if (s.predet_state.load() == 1) {   // the worker may still be refining this slot's previous frame
     int rc = wait_predetection(s);
@@ -416,6 +508,11 @@ int FeContext::submit(double t, const uint8_t *image, int stride, bool on_device
   }
   s.busy = true;
   s.timestamp = t;
+  s.res.clear();
+  for (int i = 0; i < 4; i++) {
+    s.K[i] = cfg_.K[i];
+    s.D[i] = cfg_.D[i];
+  }
   s.has_vp = vp != nullptr;
   if (vp) std::memcpy(s.vp, vp, sizeof(s.vp));
   if (mask) {
@@ -439,7 +536,7 @@ int FeContext::submit(double t, const uint8_t *image, int stride, bool on_device
       sstride = W_;
     }
     FE_CUDA(cudaMemcpy2DAsync(s.raw.p, s.raw.pitch, src, sstride, W_, H_, cudaMemcpyHostToDevice, s.s_a));
-    times.h2d_bytes += (size_t)W_ * H_;
+    mst_.h2d_bytes += (size_t)W_ * H_;
   }
   if (timing) cudaEventRecord(s.ev_t[1], s.s_a);
   int rc = enqueue_fast_all_cells(s);   // layout bookkeeping first: it decides whether the graphs are still valid
@@ -452,6 +549,8 @@ int FeContext::submit(double t, const uint8_t *image, int stride, bool on_device
   }
   wcv_.notify_one();
   queue_.push_back(si);
+  s.stage.store(1, std::memory_order_release);
+  klt_q_.push(si);
   return FE_OK;
 }
 
@@ -615,20 +714,15 @@ int FeContext::wait_predetection(FrameSlot &s) {
   while (true) {
     int st = s.predet_state.load(std::memory_order_acquire);
     if (st == 2) return FE_OK;
-    if (st == -1) {
-      last_error = "pre-detection failed: " + worker_error_;
-      return FE_CUDA_ERROR;
-    }
-    if (st == 0) {
-      last_error = "pre-detection was never queued for this frame";
-      return FE_INTERNAL;
-    }
+    if (st == -1) return err(FE_CUDA_ERROR, "pre-detection failed: " + worker_error_);
+    if (st == 0) return err(FE_INTERNAL, "pre-detection was never queued for this frame");
     if (++spins > 2000) std::this_thread::yield();
   }
 }
 
-FeStageTimes FeContext::snapshot_times() const {
-  FeStageTimes t = times;
+FeStageTimes FeContext::snapshot_times() {
+  std::lock_guard<std::mutex> lk(wstat_mu_);
+  FeStageTimes t = times_;
   t.kernel_launches_total += worker_launches_.load();
   t.h2d_bytes += worker_h2d_.load();
   t.d2h_bytes += worker_d2h_.load();
@@ -646,53 +740,94 @@ static void acc_time(FeStageTimes &t, int stage, cudaEvent_t a, cudaEvent_t b) {
   }
 }
 
-int FeContext::collect(FeFrameInfo *info) {
-  HostTimer ht(&times.host_ms[5]);
-  FE_CUDA(cudaSetDevice(device_));
-  if (queue_.empty()) {
-    last_error = "collect: nothing submitted";
-    return FE_BAD_ARG;
+// ------------------------------------------------------------------------------------- tracker threads
+// Point tracker: frames in submission order.  Owns pts_last_ / ids_last_ / currid_ while frames are in flight.
+void FeContext::klt_main() {
+  cudaSetDevice(device_);
+  int si;
+  while (klt_q_.pop(&si)) {
+    FrameSlot &cur = slots_[si];
+    cur.res.info.timestamp = cur.timestamp;
+    int rc = cudaStreamWaitEvent(s_pt_, cur.ev_pyr, 0) == cudaSuccess ? FE_OK : fail(cudaGetLastError(), "cudaStreamWaitEvent");
+    if (rc == FE_OK) rc = klt_feed(cur);
+    if (rc) {
+      cur.res.rc = rc;
+      cur.res.error = t_err;
+    }
+    cur.res.obs = pts_last_;
+    cur.res.obs_ids = ids_last_;
+    klt_last_slot_ = si;   // move forward in time (TrackKLT.cpp:182-189)
+    flush_stats(kst_);
+    if (rc == FE_OK && cfg_.use_lines && cur.has_vp) {
+      cur.stage.store(2, std::memory_order_release);
+      line_q_.push(si);
+    } else {
+      cur.stage.store(3, std::memory_order_release);
+    }
   }
+}
+
+// Line tracker: runs one frame behind the point tracker at most (it needs that frame's tracked points).
+void FeContext::line_main() {
+  cudaSetDevice(device_);
+  int si;
+  while (line_q_.pop(&si)) {
+    FrameSlot &cur = slots_[si];
+    int rc = lsd_feed(cur);
+    if (rc) {
+      cur.res.rc = rc;
+      cur.res.error = t_err;
+    }
+    flush_stats(lst_);
+    cur.stage.store(3, std::memory_order_release);
+  }
+}
+
+int FeContext::collect(FeFrameInfo *info) {
+  int rc = collect_impl(info);
+  if (rc) last_error = t_err;
+  flush_stats(mst_);
+  return rc;
+}
+
+int FeContext::collect_impl(FeFrameInfo *info) {
+  HostTimer ht(&mst_.host_ms[5]);
+  FE_CUDA(cudaSetDevice(device_));
+  if (queue_.empty()) return err(FE_BAD_ARG, "collect: nothing submitted");
   const int si = queue_.front();
   queue_.erase(queue_.begin());
   FrameSlot &cur = slots_[si];
+  // wait for the tracker threads: spin (the result is normally there already, or a few microseconds away), then yield
+  for (unsigned spins = 0; cur.stage.load(std::memory_order_acquire) != 3; spins++) {
+    if (spins < 40000) cpu_pause();
+    else std::this_thread::yield();
+  }
+  cur.stage.store(0, std::memory_order_relaxed);
   cur_slot_ = si;
-  FeFrameInfo local;
-  std::memset(&local, 0, sizeof(local));
-  local.timestamp = cur.timestamp;
-  point_rows.clear();
-  line_rows.clear();
-  line_points.clear();
-  sample_uv.clear();
-  sample_status.clear();
-
-  FE_CUDA(cudaStreamWaitEvent(s_pt_, cur.ev_pyr, 0));
-  int rc = klt_feed(cur, &local);
-  if (rc) return rc;
-  if (cfg_.use_lines && cur.has_vp) {
-    rc = lsd_feed(cur, &local);
-    if (rc) return rc;
-  }
-  if (cur.timed) {
-    FE_CUDA(cudaEventSynchronize(cur.ev_pyr));
-    acc_time(times, FE_STAGE_H2D, cur.ev_t[0], cur.ev_t[1]);
-    if (cur.predet_ncell > 0 && cur.predet_state.load() == 2) acc_time(times, FE_STAGE_FAST, cur.ev_fast_t[0], cur.ev_fast_t[1]);
-    if (cfg_.histogram_method == FE_HIST_HISTOGRAM) acc_time(times, FE_STAGE_HIST, cur.ev_t[1], cur.ev_t[2]);
-    acc_time(times, FE_STAGE_EQ_PYR, cur.ev_t[2], cur.ev_t[3]);
-    acc_time(times, FE_STAGE_PYR_REST, cur.ev_t[3], cur.ev_t[4]);
-    if (cfg_.use_lines && cur.has_vp) {
-      acc_time(times, FE_STAGE_CANNY, cur.ev_t[5], cur.ev_t[6]);
-      acc_time(times, FE_STAGE_FLD, cur.ev_t[6], cur.ev_t[7]);
-    }
-  }
-  times.frames++;
-  // move forward in time (TrackKLT.cpp:182-189): the previous "last" slot becomes free
+  cur_res_ = &cur.res;
+  FrameResult &res = cur.res;
+  // the previous collected frame's slot becomes free: its pyramid is no longer the point tracker's "last" image and its
+  // rows are no longer exposed
   if (last_slot_ >= 0) slots_[last_slot_].busy = false;
   last_slot_ = si;
-  local.n_point_rows = (int)point_rows.size();
-  local.n_line_rows = (int)line_rows.size();
-  local.n_last_obs = (int)pts_last_.size();
-  if (info) *info = local;
+  if (res.rc) return err(res.rc, res.error);
+  if (cur.timed) {
+    FE_CUDA(cudaEventSynchronize(cur.ev_pyr));
+    acc_time(mst_, FE_STAGE_H2D, cur.ev_t[0], cur.ev_t[1]);
+    if (cur.predet_ncell > 0 && cur.predet_state.load() == 2) acc_time(mst_, FE_STAGE_FAST, cur.ev_fast_t[0], cur.ev_fast_t[1]);
+    if (cfg_.histogram_method == FE_HIST_HISTOGRAM) acc_time(mst_, FE_STAGE_HIST, cur.ev_t[1], cur.ev_t[2]);
+    acc_time(mst_, FE_STAGE_EQ_PYR, cur.ev_t[2], cur.ev_t[3]);
+    acc_time(mst_, FE_STAGE_PYR_REST, cur.ev_t[3], cur.ev_t[4]);
+    if (cfg_.use_lines && cur.has_vp) {
+      acc_time(mst_, FE_STAGE_CANNY, cur.ev_t[5], cur.ev_t[6]);
+      acc_time(mst_, FE_STAGE_FLD, cur.ev_t[6], cur.ev_t[7]);
+    }
+  }
+  mst_.frames++;
+  res.info.n_point_rows = (int)res.point_rows.size();
+  res.info.n_line_rows = (int)res.line_rows.size();
+  res.info.n_last_obs = (int)res.obs.size();
+  if (info) *info = res.info;
   return FE_OK;
 }
 
@@ -714,28 +849,31 @@ int FeContext::feed(double t, const uint8_t *image, int w, int h, int stride, bo
 // -------------------------------------------------------------------------------------------- TrackKLT
 static inline bool mask_hit(const FrameSlot &s, int W, int y, int x) { return !s.mask.empty() && s.mask[(size_t)y * W + x] > 127; }
 
-int FeContext::klt_feed(FrameSlot &cur, FeFrameInfo *info) {
+int FeContext::klt_feed(FrameSlot &cur) {
+  FrameResult &res = cur.res;
+  FeFrameInfo *info = &res.info;
+  std::vector<FePointRow> &point_rows = res.point_rows;
   // TrackKLT.cpp:110-123 — nothing tracked last time: detect on the CURRENT image only
-  if (pts_last_.empty() || last_slot_ < 0) {
+  if (pts_last_.empty() || klt_last_slot_ < 0) {
     std::vector<Pt> good;
     std::vector<uint64_t> good_ids;
-    int rc = perform_detection(cur, good, good_ids, info);
+    int rc = perform_detection(cur, good, good_ids, res);
     if (rc) return rc;
     pts_last_ = good;
     ids_last_ = good_ids;
     info->first_frame = 1;
     return FE_OK;
   }
-  FrameSlot &last = slots_[last_slot_];
+  FrameSlot &last = slots_[klt_last_slot_];
   // top-off on the PREVIOUS image with the previous points (:127-130)
   std::vector<Pt> pts_old = pts_last_;
   std::vector<uint64_t> ids_old = ids_last_;
-  int rc = perform_detection(last, pts_old, ids_old, info);
+  int rc = perform_detection(last, pts_old, ids_old, res);
   if (rc) return rc;
   std::vector<Pt> pts_new = pts_old;
   std::vector<uint8_t> mask_ll;
   bool mask_empty = true;
-  rc = perform_matching(last, cur, pts_old, pts_new, mask_ll, mask_empty, info);
+  rc = perform_matching(last, cur, pts_old, pts_new, mask_ll, mask_empty, res);
   if (rc) return rc;
   if (mask_empty) {  // :143-152
     pts_last_.clear();
@@ -770,8 +908,12 @@ int FeContext::klt_feed(FrameSlot &cur, FeFrameInfo *info) {
 }
 
 
-int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, std::vector<uint64_t> &ids0, FeFrameInfo *info) {
-  HostTimer ht(&times.host_ms[1]);
+int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, std::vector<uint64_t> &ids0, FrameResult &res) {
+  HostTimer ht(&kst_.host_ms[1]);
+  FeFrameInfo *info = &res.info;
+  std::vector<int32_t> &tap_fast_ = res.tap_fast;
+  std::vector<float> &tap_subpix_ = res.tap_subpix;
+  const bool taps = this->taps.load(std::memory_order_relaxed);
   const int d = cfg_.min_px_dist;
   const int cols = W_, rows = H_;
   const int close_w = (int)((float)cols / (float)d), close_h = (int)((float)rows / (float)d);
@@ -856,7 +998,7 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
       wcv_.notify_one();
     }
     {
-      HostTimer hw(&times.host_ms[7]);
+      HostTimer hw(&kst_.host_ms[7]);
       int rc = wait_predetection(slot);
       if (rc) return rc;
     }
@@ -919,8 +1061,13 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
 }
 
 int FeContext::perform_matching(const FrameSlot &f0, const FrameSlot &f1, std::vector<Pt> &pts0, std::vector<Pt> &pts1,
-                                std::vector<uint8_t> &mask_out, bool &mask_empty, FeFrameInfo *info) {
-  HostTimer ht(&times.host_ms[2]);
+                                std::vector<uint8_t> &mask_out, bool &mask_empty, FrameResult &res) {
+  HostTimer ht(&kst_.host_ms[2]);
+  FeFrameInfo *info = &res.info;
+  std::vector<float> &tap_lk_ = res.tap_lk, &sample_uv = res.sample_uv;
+  std::vector<uint8_t> &sample_status = res.sample_status;
+  const bool taps = this->taps.load(std::memory_order_relaxed);
+  const bool timing = f1.timed;
   mask_out.clear();
   mask_empty = true;
   const int n = (int)pts0.size();
@@ -955,36 +1102,36 @@ int FeContext::perform_matching(const FrameSlot &f0, const FrameSlot &f1, std::v
   prm.eps_sq = 0.01f * 0.01f;
   prm.min_eig = 1e-4f;
   prm.undistort = 1;
-  for (int i = 0; i < 4; i++) { prm.K[i] = cfg_.K[i]; prm.D[i] = cfg_.D[i]; }
+  for (int i = 0; i < 4; i++) { prm.K[i] = f1.K[i]; prm.D[i] = f1.D[i]; }
   // The feature arrays are a few KB: the kernel reads and writes them in pinned, device-mapped host memory directly
   // (no copy-engine operation queued behind the next frame's 700 KB upload, one synchronisation per frame).
-  times.h2d_bytes += (size_t)nt * 2 * sizeof(float2);
-  times.d2h_bytes += (size_t)nt * (3 * sizeof(float2) + 1);
+  kst_.h2d_bytes += (size_t)nt * 2 * sizeof(float2);
+  kst_.d2h_bytes += (size_t)nt * (3 * sizeof(float2) + 1);
   if (timing) cudaEventRecord(ev_pt_[4], s_pt_);
-  HostTimer *tl = new HostTimer(&times.host_ms[12]);
+  HostTimer *tl = new HostTimer(&kst_.host_ms[12]);
   launch_lk(f0.pyr, f1.pyr, h_pts0_, h_pts1_, h_status_, h_p0n_, h_p1n_, nt, prm, s_pt_);
-  times.kernel_launches_total++;
+  kst_.kernel_launches_total++;
   if (timing) cudaEventRecord(ev_pt_[5], s_pt_);
   launch_signal(h_flag_lk_, ++seq_lk_, s_pt_);
   FE_CUDA(cudaGetLastError());
   delete tl;
   {
-    HostTimer tw(&times.host_ms[13]);
-    int rc = wait_flag(h_flag_lk_, seq_lk_, s_pt_, &last_error);
+    HostTimer tw(&kst_.host_ms[13]);
+    int rc = wait_flag(h_flag_lk_, seq_lk_, s_pt_, &t_err);
     if (rc) return rc;
   }
   if (timing) {
     FE_CUDA(cudaEventSynchronize(ev_pt_[5]));
-    acc_time(times, FE_STAGE_LK, ev_pt_[4], ev_pt_[5]);
+    acc_time(kst_, FE_STAGE_LK, ev_pt_[4], ev_pt_[5]);
   }
 
   // RANSAC gate on the normalised coordinates (:869-873)
-  const double max_focal = std::max(cfg_.K[0], cfg_.K[1]);
+  const double max_focal = std::max(f1.K[0], f1.K[1]);
   std::vector<uint8_t> mask_rsc(n, 0);
   int mask_valid = 0;
   int n_in;
   {
-    HostTimer hr(&times.host_ms[3]);
+    HostTimer hr(&kst_.host_ms[3]);
     n_in = ransac_fundamental(reinterpret_cast<const float *>(h_p0n_), reinterpret_cast<const float *>(h_p1n_), n,
                               2.0 / max_focal, 0.999, mask_rsc.data(), &mask_valid);
   }
@@ -1046,16 +1193,22 @@ int line_classification(const float4 &line, const double vp[6]) {  // :318-333
 }
 }  // namespace
 
-int FeContext::lsd_feed(FrameSlot &cur, FeFrameInfo *info) {
-  HostTimer ht(&times.host_ms[4]);
+int FeContext::lsd_feed(FrameSlot &cur) {
+  HostTimer ht(&lst_.host_ms[4]);
+  FrameResult &res = cur.res;
+  FeFrameInfo *info = &res.info;
+  std::vector<FeLineRow> &line_rows = res.line_rows;
+  std::vector<FeLinePoint> &line_points = res.line_points;
+  std::vector<float> &tap_fld_ = res.tap_fld;
+  const bool taps = this->taps.load(std::memory_order_relaxed);
   {
-    HostTimer hw(&times.host_ms[6]);
-    int rc = wait_flag(&cur.h_flags[2], cur.seq_lines, cur.s_line, &last_error);
+    HostTimer hw(&lst_.host_ms[6]);
+    int rc = wait_flag(&cur.h_flags[2], cur.seq_lines, cur.s_line, &t_err);
     if (rc) return rc;
   }
   int nseg = std::min(cur.h_fld_counts[1], cur.fld.out_cap);
   if (nseg > 1024) {
-    FE_COPY(cur.h_segs + 1024, cur.fld.out + 1024, (size_t)(nseg - 1024) * sizeof(float4), cudaMemcpyDeviceToHost, cur.s_line);
+    FE_COPY(lst_, cur.h_segs + 1024, cur.fld.out + 1024, (size_t)(nseg - 1024) * sizeof(float4), cudaMemcpyDeviceToHost, cur.s_line);
     FE_CUDA(cudaStreamSynchronize(cur.s_line));
   }
   if (taps) tap_fld_.assign(reinterpret_cast<float *>(cur.h_segs), reinterpret_cast<float *>(cur.h_segs) + 4 * (size_t)nseg);
@@ -1073,8 +1226,8 @@ int FeContext::lsd_feed(FrameSlot &cur, FeFrameInfo *info) {
   info->n_lines_detected = (int)lines_new.size();
 
   // AssignPointToLines (:744-792) against the CURRENT points of the point tracker (:127-129)
-  const std::vector<Pt> &points = pts_last_;
-  const std::vector<uint64_t> &pids = ids_last_;
+  const std::vector<Pt> &points = res.obs;        // the point tracker's pts_last / ids_last after THIS frame
+  const std::vector<uint64_t> &pids = res.obs_ids;
   std::vector<std::map<int, double>> pol_new;
   std::vector<std::vector<Pt>> positions;
   std::vector<float4> filt_lines;
@@ -1162,8 +1315,8 @@ int FeContext::lsd_feed(FrameSlot &cur, FeFrameInfo *info) {
     r.id = good_ids[i];
     const float4 &l = filt_lines[i];
     r.line[0] = l.x; r.line[1] = l.y; r.line[2] = l.z; r.line[3] = l.w;
-    undistort_host(l.x, l.y, r.line_n[0], r.line_n[1]);
-    undistort_host(l.z, l.w, r.line_n[2], r.line_n[3]);
+    undistort_host(cur.K, cur.D, l.x, l.y, r.line_n[0], r.line_n[1]);
+    undistort_host(cur.K, cur.D, l.z, l.w, r.line_n[2], r.line_n[3]);
     r.D = line_classification(l, cur.vp);
     r.n_pts = (int)pol_new[i].size();
     r.pt_offset = (int)line_points.size();
@@ -1197,8 +1350,16 @@ struct StateHeader {
 };
 }  // namespace
 
+// Both are only legal between frames (nothing in flight): the tracker threads are idle then and their state is visible
+// to the caller's thread through the release/acquire pair on FrameSlot::stage.
 int FeContext::get_state(void *buf, size_t cap, size_t *n_bytes) {
+  if (!queue_.empty()) {
+    last_error = "get_state: collect the pending frames first";
+    return FE_BAD_ARG;
+  }
+  int rc = [&]() -> int {
   FE_CUDA(cudaSetDevice(device_));
+  const int last_slot_ = klt_last_slot_;
   StateHeader hd;
   std::memset(&hd, 0, sizeof(hd));
   hd.magic = 0x504c5657u;
@@ -1237,11 +1398,15 @@ int FeContext::get_state(void *buf, size_t cap, size_t *n_bytes) {
   }
   if (hd.has_mask) put(slots_[last_slot_].mask.data(), (size_t)W_ * H_);
   return FE_OK;
+  }();
+  if (rc == FE_CUDA_ERROR) last_error = t_err;
+  return rc;
 }
 
 int FeContext::set_state(const void *buf, size_t n_bytes) {
-  FE_CUDA(cudaSetDevice(device_));
   if (!buf || n_bytes < sizeof(StateHeader) || !queue_.empty()) return FE_BAD_ARG;
+  int rc = [&]() -> int {
+  FE_CUDA(cudaSetDevice(device_));
   const uint8_t *p = static_cast<const uint8_t *>(buf);
   StateHeader hd;
   std::memcpy(&hd, p, sizeof(hd));
@@ -1275,6 +1440,12 @@ int FeContext::set_state(const void *buf, size_t n_bytes) {
   }
   FE_CUDA(cudaDeviceSynchronize());
   last_slot_ = -1;
+  klt_last_slot_ = -1;
+  cur_slot_ = -1;
+  state_res_.clear();
+  state_res_.obs = pts_last_;
+  state_res_.obs_ids = ids_last_;
+  cur_res_ = &state_res_;
   if (hd.has_image) {
     FrameSlot &s = slots_[0];
     s.busy = true;
@@ -1304,13 +1475,20 @@ int FeContext::set_state(const void *buf, size_t n_bytes) {
       s.mask.clear();
     }
     last_slot_ = 0;
+    klt_last_slot_ = 0;
   }
   return FE_OK;
+  }();
+  if (rc == FE_CUDA_ERROR) last_error = t_err;
+  return rc;
 }
 
 int FeContext::tap(int what, void *buf, size_t cap, size_t *n_bytes) {
   FE_CUDA(cudaSetDevice(device_));
   const int si = cur_slot_ >= 0 ? cur_slot_ : last_slot_;
+  const FrameResult &res = *cur_res_;
+  const std::vector<int32_t> &tap_fast_ = res.tap_fast;
+  const std::vector<float> &tap_lk_ = res.tap_lk, &tap_subpix_ = res.tap_subpix, &tap_fld_ = res.tap_fld;
   auto copy_vec = [&](const void *src, size_t n) -> int {
     if (n_bytes) *n_bytes = n;
     if (!buf) return FE_OK;

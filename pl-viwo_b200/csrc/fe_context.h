@@ -28,6 +28,46 @@ int line_candidates(const float *px, const float *py, int n, float min_lx, float
 int ransac_fundamental(const float *m1, const float *m2, int count, double threshold, double confidence, uint8_t *mask,
                        int *mask_valid);
 
+// Everything one frame hands back to the caller: the rows the reference would push into its two databases, the
+// tracker's "last" observations after the frame, and the optional debug taps.  Filled by the tracker threads, exposed
+// by collect().
+struct FrameResult {
+  FeFrameInfo info{};
+  std::vector<FePointRow> point_rows;
+  std::vector<FeLineRow> line_rows;
+  std::vector<FeLinePoint> line_points;
+  std::vector<float> sample_uv;
+  std::vector<uint8_t> sample_status;
+  std::vector<Pt> obs;              // pts_last / ids_last after this frame (TrackBase::get_last_obs / get_last_ids)
+  std::vector<uint64_t> obs_ids;
+  std::vector<int32_t> tap_fast;
+  std::vector<float> tap_lk, tap_subpix, tap_fld;
+  int rc = FE_OK;
+  std::string error;
+  void clear() {
+    info = FeFrameInfo{};
+    point_rows.clear(); line_rows.clear(); line_points.clear(); sample_uv.clear(); sample_status.clear();
+    obs.clear(); obs_ids.clear(); tap_fast.clear(); tap_lk.clear(); tap_subpix.clear(); tap_fld.clear();
+    rc = FE_OK;
+    error.clear();
+  }
+};
+
+// Hand-off between the threads of one handle: the consumer spins briefly (steady-state pipelining never sleeps) and
+// then blocks on a condition variable (an idle handle costs no CPU).
+class WorkQueue {
+ public:
+  void push(int v);
+  bool pop(int *v);   // false: stop requested and nothing left
+  void stop();
+ private:
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<int> q_;
+  std::atomic<int> n_{0};
+  std::atomic<bool> stop_{false};
+};
+
 // Everything that belongs to one submitted frame and can be produced without tracker state.
 struct FrameSlot {
   DevImage raw;          // staged input (device)
@@ -42,6 +82,9 @@ struct FrameSlot {
   double vp[6] = {0, 0, 0, 0, 0, 0};
   bool has_vp = false;
   bool busy = false;
+  double K[4] = {0, 0, 0, 0}, D[4] = {0, 0, 0, 0};   // calibration in force when the frame was submitted
+  FrameResult res;
+  std::atomic<int> stage{0};     // 0 idle, 1 submitted, 2 point tracker done, 3 complete (line tracker done)
   int index = 0;
   cudaEvent_t ev_pyr = nullptr, ev_lines = nullptr;
   cudaStream_t s_line = nullptr;   // per-slot streams: the frame-independent work of different frames overlaps
@@ -89,11 +132,10 @@ class FeContext {
   int feed(double t, const uint8_t *image, int w, int h, int stride, bool on_device, const uint8_t *mask,
            int mask_stride, const double vp[6], FeFrameInfo *info);
 
-  // TrackBase::get_last_obs / get_last_ids
-  const std::vector<Pt> &get_last_obs() const { return pts_last_; }
-  const std::vector<uint64_t> &get_last_ids() const { return ids_last_; }
-  void set_num_features(int n) { cfg_.num_features = n; }
-  void change_feat_id(uint64_t id_old, uint64_t id_new);
+  // results of the last collected frame (TrackBase::get_last_obs / get_last_ids are result().obs / obs_ids)
+  const FrameResult &result() const { return *cur_res_; }
+  int set_num_features(int n);
+  int change_feat_id(uint64_t id_old, uint64_t id_new);
 
   int get_state(void *buf, size_t cap, size_t *n_bytes);
   int set_state(const void *buf, size_t n_bytes);
@@ -101,23 +143,20 @@ class FeContext {
 
   const FeConfig &cfg() const { return cfg_; }
   std::string last_error;
-  std::vector<FePointRow> point_rows;
-  std::vector<FeLineRow> line_rows;
-  std::vector<FeLinePoint> line_points;
-  std::vector<float> sample_uv;
-  std::vector<uint8_t> sample_status;
-  bool timing = false;
-  bool taps = false;     // record the debug taps (FAST lists, sub-pixel, LK, FLD) — off on the hot path
-  FeStageTimes times{};
-  FeStageTimes snapshot_times() const;
-  void reset_times() {
-    times = FeStageTimes{};
-    worker_launches_ = 0; worker_h2d_ = 0; worker_d2h_ = 0;
-    for (double &v : worker_ms_) v = 0;
-  }
+  std::atomic<bool> timing{false};
+  std::atomic<bool> taps{false};     // record the debug taps (FAST lists, sub-pixel, LK, FLD) — off on the hot path
+  FeStageTimes snapshot_times();
+  void reset_times();
 
  private:
   int fail(cudaError_t e, const char *what);
+  int err(int code, const std::string &msg);
+  int submit_impl(double t, const uint8_t *image, int stride, bool on_device, const uint8_t *mask, int mask_stride,
+                  const double vp[6]);
+  int collect_impl(FeFrameInfo *info);
+  void flush_stats(FeStageTimes &local);
+  void klt_main();
+  void line_main();
   int spin_sync(cudaStream_t st);
   int wait_flag(volatile int *flag, int value, cudaStream_t st, std::string *err);
   int alloc_image(DevImage &im, int w, int h);
@@ -133,21 +172,30 @@ class FeContext {
   void worker_main();
   int wait_predetection(FrameSlot &s);
   // TrackKLT
-  int klt_feed(FrameSlot &cur, FeFrameInfo *info);
-  int perform_detection(const FrameSlot &img, std::vector<Pt> &pts, std::vector<uint64_t> &ids, FeFrameInfo *info);
+  int klt_feed(FrameSlot &cur);
+  int perform_detection(const FrameSlot &img, std::vector<Pt> &pts, std::vector<uint64_t> &ids, FrameResult &res);
   int perform_matching(const FrameSlot &f0, const FrameSlot &f1, std::vector<Pt> &pts0, std::vector<Pt> &pts1,
-                       std::vector<uint8_t> &mask_out, bool &mask_empty, FeFrameInfo *info);
+                       std::vector<uint8_t> &mask_out, bool &mask_empty, FrameResult &res);
   // TrackLSD
-  int lsd_feed(FrameSlot &cur, FeFrameInfo *info);
-  void undistort_host(float u, float v, float &un, float &vn) const;
+  int lsd_feed(FrameSlot &cur);
+  static void undistort_host(const double K[4], const double D[4], float u, float v, float &un, float &vn);
 
   FeConfig cfg_;
   int device_;
   int W_, H_;
   cudaStream_t s_pt_ = nullptr;
   std::deque<FrameSlot> slots_;           // deque: FrameSlot holds an atomic and never moves
-  std::vector<int> queue_;      // submitted, not yet collected (slot indices, FIFO)
-  int last_slot_ = -1;          // slot holding the previous frame's pyramid (img_pyramid_last)
+  std::vector<int> queue_;      // submitted, not yet collected (slot indices, FIFO) — caller's thread only
+  int last_slot_ = -1;          // slot of the last COLLECTED frame (kept until the next collect: its rows are exposed)
+  int klt_last_slot_ = -1;      // point-tracker thread: slot holding the previous frame's pyramid (img_pyramid_last)
+  FrameResult state_res_;       // what result() shows before the first collect / after set_state
+  const FrameResult *cur_res_ = &state_res_;
+  // ---- the two tracker threads: frames flow submit -> point tracker -> line tracker -> collect, each stage in frame
+  // order; the point tracker of frame t+1 overlaps the line association of frame t
+  std::thread klt_thread_, line_thread_;
+  WorkQueue klt_q_, line_q_;
+  FeStageTimes times_{};        // merged statistics (stat_mu_)
+  FeStageTimes mst_{}, kst_{}, lst_{};   // per-thread accumulators: caller, point tracker, line tracker
 
   // ---- point tracker state (TrackBase.h:173-192)
   std::vector<Pt> pts_last_;
@@ -191,9 +239,6 @@ class FeContext {
   cudaEvent_t ev_sync_ = nullptr;
   int *h_flag_lk_ = nullptr;
   int seq_lk_ = 0;
-  // ---- taps
-  std::vector<int32_t> tap_fast_;
-  std::vector<float> tap_lk_, tap_subpix_, tap_fld_;
   int cur_slot_ = -1;
 };
 
