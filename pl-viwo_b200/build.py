@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc] + ARCH + COMMON + extra + ["-c", s, "-o", o]
+            cmd = [nvcc] + ARCH + COMMON + extra + os.environ.get("PLVIWO_NVCC_FLAGS", "").split() + ["-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)

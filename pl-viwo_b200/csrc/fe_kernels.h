@@ -31,6 +31,7 @@ void launch_pyr_rest(const Pyramid &pyr, unsigned *d_counter, cudaStream_t s);
 
 void launch_signal(int *host_flag, int value, cudaStream_t s);
 void launch_signal_inc(int *host_flag, int *dev_seq, cudaStream_t s);
+void init_fld_constants();      // chain-walk decision table (kernels_lines.cu)
 void init_device_constants();   // constant-memory tables (sub-pixel mask); call once per device before capturing graphs
 
 // ---- FAST (kernels_fast.cu) ------------------------------------------------------------------------------

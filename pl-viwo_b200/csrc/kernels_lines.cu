@@ -20,6 +20,7 @@
 #include "fe_kernels.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cmath>
 
 namespace plviwo {
@@ -184,163 +185,313 @@ __global__ void k_ccl_flatten(int w, int h, int *__restrict__ label, int *__rest
   }
 }
 
-// components large enough to hold a chain of length_threshold + 1 pixels
+// components large enough to hold a chain of length_threshold + 1 pixels, in three size classes so that the walk
+// below starts the big ones first (the walk of one component is sequential: the largest component is the critical path)
+constexpr int kClassA = 1024, kClassB = 128;   // pixels
+__host__ __device__ inline int comp_cap_a(int n) { return n / kClassA + 1; }
+__host__ __device__ inline int comp_cap_b(int n) { return n / kClassB + 1; }
+
 __global__ void k_ccl_roots(int w, int h, const int *__restrict__ label, const int *__restrict__ cnt, int min_pixels,
                             int *__restrict__ comp_root, int *__restrict__ counters, int max_comps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= w * h) return;
-  if (label[i] == i && cnt[i] >= min_pixels) {
-    int k = atomicAdd(counters + 0, 1);
-    if (k < max_comps) comp_root[k] = i;
+  if (label[i] != i) return;
+  const int c = cnt[i];
+  if (c < min_pixels) return;
+  const int n = w * h;
+  if (c >= kClassA) {
+    comp_root[atomicAdd(counters + 0, 1)] = i;                                   // at most n / kClassA of these
+  } else if (c >= kClassB) {
+    comp_root[comp_cap_a(n) + atomicAdd(counters + 5, 1)] = i;                   // at most n / kClassB
+  } else {
+    int k = atomicAdd(counters + 6, 1);
+    if (k < max_comps) comp_root[comp_cap_a(n) + comp_cap_b(n) + k] = i;
   }
 }
 
 // ------------------------------------------------------------------------------------------- chain walk
-// getPointChain for step > 0: among the set neighbours take the one whose direction is closest to the running
-// direction (circular difference; ties go to the LATER neighbour index), accept only a difference < 2.
-__device__ __forceinline__ int choose_neighbour(unsigned mask, int direction) {
+// getPointChain: among the set neighbours take the one whose direction is closest to the running direction (circular
+// difference; ties go to the LATER neighbour index), accept only a difference < 2; the first step of a chain takes the
+// first set neighbour.  Neighbour index i -> (dr, dc): 0 (+1,+1) 1 (+1,0) 2 (+1,-1) 3 (0,-1) 4 (-1,-1) 5 (-1,0) 6 (-1,+1)
+// 7 (0,+1).  The whole decision is a table: [first step?][neighbour key][running direction + 3] -> i | (dr+1) << 4 |
+// (dc+1) << 6 (i == 8: stop); the 8 direction entries of a key are one 8-byte load and the entry is picked with a byte
+// permute once the direction is known, so the direction update is not on the path to the table address.
+// The neighbour key is taken from a 5 x 5 bit window B (bit 5 (r + 2) + (c + 2) = pixel (r, c) relative to the window
+// centre): for a pixel at offset (dr, dc) from the centre, Bs = B >> (6 + 5 dr + dc) has neighbour i at bit
+// {12, 11, 10, 5, 0, 1, 2, 7}[i], and key = (Bs & 0xA7) | ((Bs >> 2) & 0x700) packs those into 11 bits.
+static int choose_neighbour_host(unsigned mask, int direction) {
   const int i0 = direction < 0 ? direction + 8 : direction;      // neighbour index with difference 0
   if ((mask >> i0) & 1u) return i0;
   const int ia = (i0 + 1) & 7, ib = (i0 + 7) & 7;               // the two neighbours with difference 1
   const bool sa = (mask >> ia) & 1u, sb = (mask >> ib) & 1u;
-  if (sa && sb) return max(ia, ib);
+  if (sa && sb) return ia > ib ? ia : ib;
   if (sa) return ia;
   if (sb) return ib;
   return 8;
 }
+static inline int nb_dr(int i) { return (i <= 2) ? 1 : ((i == 3 || i == 7) ? 0 : -1); }
+static inline int nb_dc(int i) { return (i == 0 || i == 6 || i == 7) ? 1 : ((i == 1 || i == 5) ? 0 : -1); }
 
-// padded private bit map: row stride ws words, 1 zero row above and below, local x stored at bit x + 1
-__device__ __forceinline__ unsigned row3(const unsigned *bm, int ws, int py, int x) {
-  const unsigned *r = bm + py * ws;
-  const int wi = x >> 5, sh = x & 31;
-  return __funnelshift_r(r[wi], r[wi + 1], sh) & 7u;
+constexpr int kKeys = 2048;
+constexpr int kLut1 = 2 * kKeys * 8;    // [first step?][neighbour key][direction + 3] -> decision
+constexpr int kLut2 = 8 * 8 * 8;        // [min(step, 7)][direction + 3][i] -> next direction + 3
+constexpr int kLutSize = kLut1 + kLut2;
+__device__ __align__(16) uint8_t g_walk_lut[kLutSize];
+static bool g_walk_lut_ready[64] = {false};
+
+void init_fld_constants() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (g_walk_lut_ready[dev & 63]) return;
+  static uint8_t lut[kLutSize];
+  static const int key_bit[8] = {10, 9, 8, 5, 0, 1, 2, 7};   // key bit of neighbour i (see above)
+  for (int first = 0; first < 2; first++)
+    for (unsigned key = 0; key < (unsigned)kKeys; key++) {
+      unsigned mask = 0;
+      for (int i = 0; i < 8; i++) mask |= ((key >> key_bit[i]) & 1u) << i;
+      for (int d = 0; d < 8; d++) {
+        int i = 8;
+        if (mask) i = first ? __builtin_ffs((int)mask) - 1 : choose_neighbour_host(mask, d - 3);
+        const int dr = i < 8 ? nb_dr(i) : 0, dc = i < 8 ? nb_dc(i) : 0;
+        lut[(first * kKeys + key) * 8 + d] = (uint8_t)(i | ((dr + 1) << 4) | ((dc + 1) << 6));
+      }
+    }
+  // running direction after taking neighbour i at step `step`: direction = (direction * step + cd) / (step + 1), C integer
+  // division; from step 7 on the result no longer depends on step (|cd - direction| <= 7 < step + 1)
+  for (int sc = 0; sc < 8; sc++)
+    for (int d = 0; d < 8; d++)
+      for (int i = 0; i < 8; i++) {
+        const int cd = i > 4 ? i - 8 : i;
+        const int nd = sc == 0 ? cd : ((d - 3) * sc + cd) / (sc + 1);
+        lut[kLut1 + (sc * 8 + d) * 8 + i] = (uint8_t)(nd + 3);
+      }
+  cudaMemcpyToSymbol(g_walk_lut, lut, sizeof(lut));
+  g_walk_lut_ready[dev & 63] = true;
 }
 
-// counters: [0] components, [1] next component to take, [2] chain-point cursor, [3] chains, [4] segments
-constexpr int kWalkThreads = 128;
-constexpr int kWalkCtas = 48;   // per frame; components are pulled from an atomic queue
+// counters: [0] class-A components, [1] next component to take, [2] chain-point cursor, [3] chains, [4] segments,
+//           [5] class-B components, [6] class-C components
+constexpr int kWalkThreads = 256;
+constexpr int kWalkCtas = 148 * 2;   // components are pulled from an atomic queue, biggest class first
+constexpr int kPadRows = 2;          // zero rows above and below the private bit map (the walk looks 2 pixels ahead)
 
+// explicit shared-memory accesses by 32-bit shared address (keeps the address arithmetic out of the walk loop)
+__device__ __forceinline__ unsigned lds_u32(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned lds_u8(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 lds_u64(unsigned addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(unsigned addr, unsigned v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// One CTA per component.  All its warps gather the component's private bit map (shared memory: row stride
+// ws = groups + 2 words with one zero word on each side, two zero rows above and below; word g + 1 of row ly + 2 is the
+// component's part of edge word (y0 + ly, g0 + g), so the gather needs no shifting).  Then warp 0 walks.  The walk is a
+// chain of dependent steps and a GPU thread retires a dependent instruction every ~4 cycles, so the step is spread
+// over the warp and software-pipelined: lane j < 25 reads pixel j of the 5 x 5 window around the CURRENT pixel (one
+// shared load, one ballot) while the decision for the current pixel is taken from the window fetched around the
+// PREVIOUS pixel (shift, 11-bit key, one table look-up).  The dependent chain of a step is
+// shift -> key -> table load -> decode, ~90 cycles; the first version (one thread, 6 loads + ~150 instructions per
+// step) needed ~600.
 __global__ void __launch_bounds__(kWalkThreads)
-    k_fld_walk_cc(const int *__restrict__ label, const int *__restrict__ cnt, const int *__restrict__ bbox, int w, int h,
+    k_fld_walk_cc(const unsigned *__restrict__ edges, int words_per_row, const int *__restrict__ label,
+                  const int *__restrict__ cnt, const int *__restrict__ bbox, int w, int h,
                   const int *__restrict__ comp_root, int *__restrict__ counters, int max_comps, int length_threshold,
                   int2 *__restrict__ chain_pts, int *__restrict__ chain_seed, int *__restrict__ chain_off,
                   int *__restrict__ chain_len, int max_chains) {
-  extern __shared__ unsigned bm[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ncomp = min(counters[0], max_comps);
+  extern __shared__ __align__(16) uint8_t walk_smem[];   // decision tables, then the private bit map
+  uint8_t *lut = walk_smem;
+  unsigned *bm = reinterpret_cast<unsigned *>(walk_smem + kLutSize);
   __shared__ int s_ci;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = w * h;
+  const int nA = min(counters[0], comp_cap_a(n)), nB = min(counters[5], comp_cap_b(n)), nC = min(counters[6], max_comps);
+  const int ncomp = nA + nB + nC;
+  if ((int)blockIdx.x >= ncomp) return;
+  for (int i = tid; i < kLutSize / 4; i += kWalkThreads)
+    reinterpret_cast<unsigned *>(lut)[i] = reinterpret_cast<const unsigned *>(g_walk_lut)[i];
+  const bool vec4 = (w & 3) == 0;
+  // this lane's pixel of the 5 x 5 window (lanes >= 25 look at the centre; their ballot bits are dropped)
+  const int my_dr = lane < 25 ? lane / 5 - 2 : 0;
+  const int my_dc = lane < 25 ? lane % 5 - 2 : 0;
   while (true) {
-    // dynamic work queue: a few long-lived CTAs pull components, so the walk never floods the SMs' shared memory
-    // while the latency-critical tracking kernels of the same or other camera streams want to start
-    __syncthreads();   // the previous component's walk is finished
+    __syncthreads();   // the previous component's walk is finished (and the table is in place)
     if (tid == 0) s_ci = atomicAdd(counters + 1, 1);
     __syncthreads();
-    const int ci = s_ci;
-    if (ci >= ncomp) break;
-    const int root = comp_root[ci];
+    const int q = s_ci;
+    if (q >= ncomp) break;
+    const int root = comp_root[q < nA ? q : (q < nA + nB ? comp_cap_a(n) + (q - nA) : comp_cap_a(n) + comp_cap_b(n) + (q - nA - nB))];
     const int y0 = root / w, y1 = bbox[root];
-    const int x0 = bbox[w * h + root], x1 = bbox[2 * w * h + root];
-    const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
-    const int ws = ((bw + 2 + 31) >> 5) + 1;
-    for (int i = tid; i < (bh + 2) * ws; i += kWalkThreads) bm[i] = 0;
+    const int g0 = bbox[n + root] >> 5, g1 = bbox[2 * n + root] >> 5;
+    const int groups = g1 - g0 + 1, bh = y1 - y0 + 1;
+    const int ws = groups + 2;
+    for (int i = tid; i < (bh + 2 * kPadRows) * ws; i += kWalkThreads) bm[i] = 0;
     __syncthreads();
-    // private bit map of this component: one coalesced label load + ballot per 32 pixels, 4 loads in flight per warp
-    const int groups = (bw + 31) >> 5;
-    const int items = bh * groups;
-    for (int it0 = warp * 4; it0 < items; it0 += (kWalkThreads / 32) * 4) {
-      int lab[4];
+    // ---- gather: private word = edge word AND (label == root).  A warp covers 128 pixels (4 words) per round with one
+    // 16-byte label load per lane, skipped where the edge map is empty; 4 rounds in flight.
+    {
+      const int segs = (groups + 3) >> 2;          // 4-word segments per row
+      const int items = bh * segs;
+      const unsigned gmask = 0xffu << (lane & 24);
+      for (int it0 = warp * 4; it0 < items; it0 += (kWalkThreads / 32) * 4) {
+        int4 lab[4];
+        unsigned nib[4];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int it = it0 + u;
-        lab[u] = -2;
-        if (it < items) {
-          const int ly = it / groups, g = it - ly * groups;
-          const int lx = (g << 5) + lane;
-          if (lx < bw) lab[u] = label[(size_t)(y0 + ly) * w + x0 + lx];
+        for (int u = 0; u < 4; u++) {
+          const int it = it0 + u;
+          nib[u] = 0;
+          lab[u] = make_int4(-2, -2, -2, -2);
+          if (it < items) {
+            const int ly = it / segs, sg = it - ly * segs;
+            const int g = 4 * sg + (lane >> 3);
+            if (g < groups) {
+              const unsigned e = __ldg(edges + (size_t)(y0 + ly) * words_per_row + g0 + g);
+              nib[u] = (e >> (4 * (lane & 7))) & 15u;
+              if (nib[u]) {
+                const int *lp = label + (size_t)(y0 + ly) * w + ((g0 + g) << 5) + 4 * (lane & 7);
+                if (vec4) {
+                  lab[u] = *reinterpret_cast<const int4 *>(lp);
+                } else {
+                  if (nib[u] & 1u) lab[u].x = lp[0];
+                  if (nib[u] & 2u) lab[u].y = lp[1];
+                  if (nib[u] & 4u) lab[u].z = lp[2];
+                  if (nib[u] & 8u) lab[u].w = lp[3];
+                }
+              }
+            }
+          }
         }
-      }
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int it = it0 + u;
-        const unsigned word = __ballot_sync(0xffffffffu, lab[u] == root);
-        if (lane == 0 && word && it < items) {
-          const int ly = it / groups, g = it - ly * groups;
-          unsigned *dst = bm + (ly + 1) * ws + g;
-          atomicOr(dst, word << 1);
-          if (word >> 31) atomicOr(dst + 1, 1u);
+        for (int u = 0; u < 4; u++) {
+          const int it = it0 + u;
+          unsigned bits = (lab[u].x == root ? 1u : 0u) | (lab[u].y == root ? 2u : 0u) | (lab[u].z == root ? 4u : 0u) |
+                          (lab[u].w == root ? 8u : 0u);
+          bits = (bits & nib[u]) << (4 * (lane & 7));
+          const unsigned word = __reduce_or_sync(gmask, bits);
+          if ((lane & 7) == 0 && word && it < items) {
+            const int ly = it / segs, sg = it - ly * segs;
+            bm[(ly + kPadRows) * ws + 1 + 4 * sg + (lane >> 3)] = word;
+          }
         }
       }
     }
     __syncthreads();
     if (warp != 0) continue;   // warp 0 scans and walks; the others wait at the barrier above
-    int base = 0;
-    if (lane == 0) base = atomicAdd(counters + 2, cnt[root]);   // this component's slice of the chain-point pool
-    base = __shfl_sync(0xffffffffu, base, 0);
-    int npts = base;
-    // raster scan over the private map
-    int y = 0, xw = 0;
-    while (y < bh) {
-      const int g = xw + lane;
-      unsigned v = 0;
-      if (g < groups) {
-        const unsigned *r = bm + (y + 1) * ws;
-        v = __funnelshift_r(r[g], r[g + 1], 1);  // local pixels 32g .. 32g+31
-      }
+#ifdef PLVIWO_WALK_PROF
+    long long prof_t0 = clock64(), prof_scan = 0, prof_walk = 0, prof_pro = 0, prof_epi = 0;
+    int prof_chains = 0, prof_probes = 0;
+#endif
+    // ---- sequential part: raster-order seeds, one chain per seed.  All state below is warp-uniform.
+    int npts = 0;
+    if (lane == 0) npts = atomicAdd(counters + 2, cnt[root]);   // this component's slice of the chain-point pool
+    npts = __shfl_sync(0xffffffffu, npts, 0);
+    const int xbase = (g0 << 5) - 32;                // global x of bit 0 of a private row
+    const unsigned bm_addr = (unsigned)__cvta_generic_to_shared(bm), lut_addr = (unsigned)__cvta_generic_to_shared(lut);
+    const int my_off = my_dr * ws;
+    int sy = 0, sg = 0;                              // scan position (row, word): everything before it is consumed
+    while (sy < bh) {
+      // next seed: first set bit at or after the scan position, 32 words per probe
+#ifdef PLVIWO_WALK_PROF
+      long long prof_a = clock64();
+      prof_probes++;
+#endif
+      const int g = sg + lane;
+      const unsigned v = g < groups ? bm[(sy + kPadRows) * ws + 1 + g] : 0u;
       const unsigned any = __ballot_sync(0xffffffffu, v != 0);
       if (!any) {
-        xw += 32;
-        if (xw >= groups) { xw = 0; y++; }
+        sg += 32;
+        if (sg >= groups) { sg = 0; sy++; }
         continue;
       }
       const int first = __ffs(any) - 1;
-      const unsigned vv = __shfl_sync(0xffffffffu, v, first);
-      const int bit = __ffs(vv) - 1;
-      const int sx = ((xw + first) << 5) + bit, sy = y;
-      xw += first;
-      if (lane == 0) {
-        // ---- walk one chain (the getPointChain loop of lineDetection); coordinates local to the bounding box
-        const int start = npts;
-        int cx = sx, cy = sy;
-        chain_pts[npts++] = make_int2(x0 + cx, y0 + cy);
-        bm[(cy + 1) * ws + ((cx + 1) >> 5)] &= ~(1u << ((cx + 1) & 31));
-        int direction = 0, step = 0;
-        while (true) {
-          const unsigned t = row3(bm, ws, cy, cx), m = row3(bm, ws, cy + 1, cx), b = row3(bm, ws, cy + 2, cx);
-          const unsigned mask = ((b >> 2) & 1u) | (((b >> 1) & 1u) << 1) | ((b & 1u) << 2) | ((m & 1u) << 3) |
-                                ((t & 1u) << 4) | (((t >> 1) & 1u) << 5) | (((t >> 2) & 1u) << 6) | (((m >> 2) & 1u) << 7);
-          if (!mask) break;
-          int i;
-          if (step == 0) {
-            i = __ffs(mask) - 1;
-            direction = i > 4 ? i - 8 : i;
-          } else {
-            i = choose_neighbour(mask, direction);
-            if (i == 8) break;
-            const int cd = i > 4 ? i - 8 : i;
-            direction = (direction * step + cd) / (step + 1);
-          }
-          const int dr = (i <= 2) ? 1 : ((i == 3 || i == 7) ? 0 : -1);
-          const int dc = (i == 0 || i == 6 || i == 7) ? 1 : ((i == 1 || i == 5) ? 0 : -1);
-          cx += dc;
-          cy += dr;
-          chain_pts[npts++] = make_int2(x0 + cx, y0 + cy);
-          step++;
-          bm[(cy + 1) * ws + ((cx + 1) >> 5)] &= ~(1u << ((cx + 1) & 31));
-        }
-        if (npts - start < length_threshold + 1) {
-          npts = start;  // chain too short: dropped (its pixels stay consumed)
-        } else {
-          const int c = atomicAdd(counters + 3, 1);
-          if (c < max_chains) {
-            chain_seed[c] = (y0 + sy) * w + (x0 + sx);
-            chain_off[c] = start;
-            chain_len[c] = npts - start;
-          }
+      const unsigned wv = __shfl_sync(0xffffffffu, v, first);
+      sg += first;
+      // ---- walk one chain; p = bit position in the private row (pixel local x + 32), rb = word index of the row start
+      int p = ((sg + 1) << 5) + __ffs(wv) - 1, cy = sy;
+      int rb = (cy + kPadRows) * ws;
+      const int start = npts;
+      const int seed = (y0 + cy) * w + xbase + p;
+      int step = 0;
+      unsigned dsel = 0, sh = 6;              // dsel: running direction + 3 (byte selector)
+      unsigned tb = lut_addr + kKeys * 8;     // first-step half of the table
+#ifdef PLVIWO_WALK_PROF
+      long long prof_b = clock64();
+      prof_scan += prof_b - prof_a;
+      prof_chains++;
+#endif
+      // consume the seed (lane 0 still holds nothing of it: the scan word wv is the seed's word), then fetch its 5 x 5
+      // window.  Shared-memory operations of one warp execute in order, so the loads see the cleared bit.
+      if (lane == 0) sts_u32(bm_addr + 4u * (unsigned)(rb + (p >> 5)), wv & ~(1u << (p & 31)));
+      unsigned B;
+      {
+        const int qb = p + my_dc;
+        const unsigned word = lds_u32(bm_addr + 4u * (unsigned)(rb + my_off + (qb >> 5)));
+        B = __ballot_sync(0xffffffffu, (word >> (qb & 31)) & 1u);
+      }
+#ifdef PLVIWO_WALK_PROF
+      long long prof_c = clock64();
+      prof_pro += prof_c - prof_b;
+#endif
+      while (true) {
+        // B: window around the previous pixel (the seed itself in the first round); the current pixel sits at offset
+        // (dr, dc) of the previous move inside it and sh = 6 + 5 dr + dc.  Start fetching the current pixel's window.
+        const int qb = p + my_dc;
+        const unsigned waddr = bm_addr + 4u * (unsigned)(rb + my_off + (qb >> 5));
+        const unsigned word = lds_u32(waddr);
+        const unsigned Bs = B >> sh;
+        const unsigned key = (Bs & 0xA7u) | ((Bs >> 2) & 0x700u);
+        const uint2 ev = lds_u64(tb + key * 8u);
+        if (lane == 0) chain_pts[npts] = make_int2(xbase + p, y0 + cy);
+        npts++;
+        B = __ballot_sync(0xffffffffu, (word >> (qb & 31)) & 1u);
+        const unsigned e = __byte_perm(ev.x, ev.y, dsel);   // byte dsel of the 8 entries
+        const unsigned i = e & 15u;
+        if (i == 8u) break;
+        dsel = lds_u8(lut_addr + kLut1 + ((unsigned)min(step, 7) * 8u + dsel) * 8u + i);
+        step++;
+        tb = lut_addr;
+        const unsigned r1 = (e >> 4) & 3u, c1 = (e >> 6) & 3u;   // dr + 1, dc + 1
+        sh = 5u * r1 + c1;
+        // consume the new pixel: the lane that just fetched it (window position 6 + sh) rewrites its word without it
+        if (lane == (int)(sh + 6u)) sts_u32(waddr, word & ~(1u << (qb & 31)));
+        p += (int)c1 - 1;
+        cy += (int)r1 - 1;
+        rb += ((int)r1 - 1) * ws;
+      }
+#ifdef PLVIWO_WALK_PROF
+      long long prof_d = clock64();
+      prof_walk += prof_d - prof_c;
+#endif
+      if (npts - start < length_threshold + 1) {
+        npts = start;  // chain too short: dropped (its pixels stay consumed)
+      } else if (lane == 0) {
+        const int c = atomicAdd(counters + 3, 1);
+        if (c < max_chains) {
+          chain_seed[c] = seed;
+          chain_off[c] = start;
+          chain_len[c] = npts - start;
         }
       }
-      npts = __shfl_sync(0xffffffffu, npts, 0);
-      __syncwarp();
+#ifdef PLVIWO_WALK_PROF
+      prof_epi += clock64() - prof_d;
+#endif
     }
+#ifdef PLVIWO_WALK_PROF
+    if (lane == 0 && cnt[root] >= 512)
+      printf("comp root %d px %d bbox %dx%d: total %lld cyc, scan %lld (probes %d), prologue %lld, loop %lld, epilogue %lld, chains %d\n", root, cnt[root], groups * 32,
+             bh, clock64() - prof_t0, prof_scan, prof_probes, prof_pro, prof_walk, prof_epi, prof_chains);
+#endif
   }
 }
 
@@ -531,10 +682,10 @@ int FldBuffers::alloc(int w, int h, int length_threshold, int out_capacity) {
   bool ok = true;
   auto A = [&](auto **p, size_t bytes) { ok = ok && cudaMalloc((void **)p, bytes) == cudaSuccess; };
   A(&edges, (size_t)words_per_row * h * sizeof(unsigned));
-  A(&label, n * sizeof(int));
+  A(&label, (n + 32) * sizeof(int));   // slack: the walk gathers labels with 16-byte loads
   A(&cnt, n * sizeof(int));
   A(&bbox, 3 * n * sizeof(int));
-  A(&comp_root, (size_t)max_chains * sizeof(int));
+  A(&comp_root, (size_t)(max_chains + comp_cap_a((int)n) + comp_cap_b((int)n)) * sizeof(int));
   A(&counters, 8 * sizeof(int));
   A(&chain_pts, n * sizeof(int2));
   A(&chain_seed, (size_t)max_chains * sizeof(int));
@@ -562,14 +713,15 @@ void launch_fld(const DevImage &half, int length_threshold, float distance_thres
   k_ccl_merge<<<nb, tpb, 0, s>>>(w, h, fb.label);
   k_ccl_flatten<<<nb, tpb, 0, s>>>(w, h, fb.label, fb.cnt, fb.bbox);
   k_ccl_roots<<<nb, tpb, 0, s>>>(w, h, fb.label, fb.cnt, length_threshold + 1, fb.comp_root, fb.counters, fb.max_chains);
-  const int ws = ((w + 2 + 31) >> 5) + 1;
-  size_t smem = (size_t)(h + 2) * ws * sizeof(unsigned);
+  init_fld_constants();
+  const int ws = ((w + 31) >> 5) + 2;
+  size_t smem = (size_t)kLutSize + (size_t)(h + 2 * kPadRows) * ws * sizeof(unsigned);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaFuncSetAttribute(k_fld_walk_cc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  k_fld_walk_cc<<<kWalkCtas, kWalkThreads, smem, s>>>(fb.label, fb.cnt, fb.bbox, w, h, fb.comp_root, fb.counters, fb.max_chains,
+  k_fld_walk_cc<<<kWalkCtas, kWalkThreads, smem, s>>>(fb.edges, fb.words_per_row, fb.label, fb.cnt, fb.bbox, w, h, fb.comp_root, fb.counters, fb.max_chains,
                                                length_threshold, fb.chain_pts, fb.chain_seed, fb.chain_off, fb.chain_len,
                                                fb.max_chains);
   int blocks = (fb.max_chains + 127) / 128;

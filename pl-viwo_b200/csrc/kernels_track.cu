@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(kSpWarps * 32)
 void init_device_constants() {
   DevImage dummy;
   launch_corner_subpix(dummy, nullptr, -1, 0);
+  init_fld_constants();
 }
 
 void launch_corner_subpix(const DevImage &img, float2 *d_pts, int n, cudaStream_t s) {
