@@ -42,6 +42,8 @@ WORKLOAD_NAME = "BASELINE.json configs[1]: synthetic KAIST-shaped 1280x560 mono,
 SEQ_FRAMES = 300
 LOOKAHEAD = 24
 METRIC = "front-end frames/sec @1280x560"
+KERNEL_OF_STAGE = {"hist": "k_hist", "eq_pyr1": "k_eq_pyr1", "pyr_rest": "k_pyr_down", "fast": "k_fast", "subpix": "k_corner_subpix",
+                   "lk": "k_lk15", "canny": "k_canny", "fld_walk": "k_fld_walk_cc", "fld_ccl": "k_ccl_merge", "fld_seg": "k_fld_segments"}
 
 
 def algorithmic_bytes(n_lk_pts: float, cfg=WORKLOAD) -> dict:
@@ -57,8 +59,9 @@ def algorithmic_bytes(n_lk_pts: float, cfg=WORKLOAD) -> dict:
         "eq_pyr1": N + N + sizes[1] + N // 4,                 # read frame, write level 0, level 1, half-res image
         "pyr_rest": sum(sizes[l - 1] + sizes[l] for l in range(2, L + 1)),
         "fast": N,                                            # worst case: every cell valid
-        "canny": N // 4 + N // 32,                            # read half-res, write bit-packed edges
-        "fld": N // 32 + N // 4,                              # read edge bits; chain pixels are bounded by the edge count
+        "canny": N // 4 + N // 4,                             # Canny read + write (one byte per half-res pixel)
+        "fld_walk": N // 4,                                   # chain walk: every half-res pixel read once
+        "fld_ccl": 0, "fld_seg": 0,                           # implementation artefacts of the parallel walk: no SURVEY bytes
         "lk": n_lk_pts * (L + 1) * ((w + 3) ** 2 + (w + 1) ** 2),
         "subpix": 0,
     }
@@ -189,6 +192,60 @@ def run_gpu_pass(fe_mod, torch, handle, seq, srcs, steps, warmup, on_device, pit
     return dict(ms=float(ev0.elapsed_time(ev1)), wall_ms=wall_ms, stage=st, rows=rows, p50_ms=1e3 * float(np.median(per)))
 
 
+def run_gpu_multi(fe_mod, torch, seq, d_ptrs, pitch, n_streams, steps, warmup, cfg_kw, dev):
+    """configs[4] shape on one GPU: n_streams independent handles (own CUDA streams, own tracker threads), each driven by
+    one host thread through submit/collect.  All streams replay the same device-resident sequence from different
+    start frames (they never exchange data, so this is n_streams times the single-stream work)."""
+    import threading
+    n = len(d_ptrs)
+    la = 8
+    handles = [fe_mod.FrontEnd(fe_mod.default_config(K=seq.K, D=seq.D, lookahead=la, **cfg_kw), device=dev) for _ in range(n_streams)]
+    start = threading.Barrier(n_streams + 1)
+    mid = threading.Barrier(n_streams + 1)
+    frames_done = [0] * n_streams
+
+    def drive(k):
+        h = handles[k]
+        off = (k * 37) % n
+        tot = warmup + steps
+        sub = 0
+        start.wait()
+        for i in range(tot):
+            if i == warmup:
+                mid.wait()      # everybody warmed up
+                mid.wait()      # timed region starts
+            while sub < tot and sub <= i + la:
+                t = (off + sub) % n
+                h.submit(seq.timestamp(sub), d_ptrs[t], stride=pitch, on_device=True, vanishing_points=seq.vanishing_points(t))
+                sub += 1
+            h.collect()
+            if i >= warmup:
+                frames_done[k] += 1
+
+    th = [threading.Thread(target=drive, args=(k,)) for k in range(n_streams)]
+    for t in th:
+        t.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.wait()
+    mid.wait()
+    torch.cuda.synchronize()
+    ev0.record()
+    t0 = time.perf_counter()
+    mid.wait()
+    for t in th:
+        t.join()
+    torch.cuda.synchronize()
+    ev1.record()
+    ev1.synchronize()
+    wall = time.perf_counter() - t0
+    for h in handles:
+        h.close()
+    ms = float(ev0.elapsed_time(ev1))
+    return {"streams": n_streams, "frames": sum(frames_done), "ms": ms, "value": sum(frames_done) / (ms * 1e-3), "unit": "frames/s",
+            "wall_fps": sum(frames_done) / wall, "lookahead": la,
+            "note": "BASELINE.json configs[4] shape on ONE GPU: independent streams, one host driver thread each, frames resident in HBM"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -197,6 +254,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=150, help="frames of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi-streams", type=int, default=4, help="streams per GPU of the extra multi-stream measurement (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -271,12 +329,18 @@ def main():
     sync_fps = n_sync / (time.perf_counter() - t0)
     handle.close()
 
+    multi = None
+    if world == 1 and args.multi_streams > 1:
+        multi = run_gpu_multi(fe_mod, torch, seq, d_ptrs, W, args.multi_streams, min(args.steps, 400), args.warmup, kw, dev)
+
     ms, ms_e2e = res["ms"], res_e2e["ms"]
+    total_frames = args.steps * world
     if dist is not None:
+        # whole-job numbers: SUM of frames, MAX of elapsed time over the ranks (pl-viwo_b200/shard.py)
         tt = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(tt[0]), float(tt[1])
-    total_frames = args.steps * world
+        total_frames = int(round(fe_mod.shard.distributed_throughput(dist, torch, args.steps, ms, device="cuda") * ms * 1e-3))
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -296,13 +360,28 @@ def main():
     if st["launches"]["lk"]:
         lk_pts = res_t["rows"] / max(st["launches"]["lk"], 1)  # lower bound: rows written; LK input is slightly larger
     ab = algorithmic_bytes(max(lk_pts, 1.0))
-    stage_ms = {k: v for k, v in st["ms"].items() if k not in ("h2d",) and st["launches"][k]}
+    # single kernels only: "fld" is the sum of fld_ccl + fld_walk + fld_seg, pyr_rest / fld_ccl / fld_seg are 3-4 launches
+    stage_ms = {k: v for k, v in st["ms"].items() if k not in ("h2d", "fld") and st["launches"][k]}
     dom = max(stage_ms, key=lambda k: stage_ms[k]) if stage_ms else "lk"
     avg_ms = stage_ms.get(dom, 0.0) / max(st["launches"][dom], 1)
     achieved = (ab[dom] / (avg_ms * 1e-3)) / 1e9 if avg_ms > 0 else 0.0
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full summary
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["kernels"].get(KERNEL_OF_STAGE.get(dom, dom))
+    except Exception:
+        pass
+    per_kernel = {}
+    for k, v in stage_ms.items():
+        ms_k = v / max(st["launches"][k], 1)
+        per_kernel[k] = {"avg_ms": ms_k, "algorithmic_bytes": ab.get(k, 0),
+                         "GBps": (ab.get(k, 0) / (ms_k * 1e-3)) / 1e9 if ms_k > 0 else 0.0}
+        per_kernel[k]["frac"] = per_kernel[k]["GBps"] / peak if peak else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ab[dom], "avg_launch_ms": avg_ms,
+                "note": "the dominant kernel is the sequential chain walk of the line detector: latency bound, not HBM "
+                        "bound (DESIGN.md 'Kernels'); per_kernel lists every kernel of the frame",
+                "per_kernel": per_kernel,
                 "stage_ms_per_frame": {k: v / nfr for k, v in st["ms"].items()},
                 "host_ms_per_frame": {k: v / max(res["stage"]["frames"], 1) for k, v in res["stage"]["host_ms"].items()},
                 "whole_frame": {"algorithmic_bytes": ab["frame_total"],
@@ -317,7 +396,8 @@ def main():
         "metric": METRIC, "value": total_frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/int32 fixed-point + f32 (LK), f64 (sub-pixel, undistort, RANSAC)", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME, "streams_per_gpu": 1, "lookahead": LOOKAHEAD, "sequence_frames": SEQ_FRAMES,
+        "config": {"workload": WORKLOAD_NAME, "streams_per_gpu": 1, "streams": world, "stream_to_gpu": "stream s -> rank s mod N, seed 1000 + s",
+                   "lookahead": LOOKAHEAD, "sequence_frames": SEQ_FRAMES,
                    "cache": "inputs larger than L2 (215 MB device-resident sequence, every frame read once per pass)"},
         "p50_ms_per_frame": res["p50_ms"],
         "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s",
@@ -326,7 +406,7 @@ def main():
                 "api": "plviwo_fe_submit/plviwo_fe_collect from pinned host frames, lookahead %d" % LOOKAHEAD,
                 "sync_feed_fps": sync_fps},
         "gpu_launches": res["stage"]["kernel_launches_total"],
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "multi_stream": multi,
     }
     print(json.dumps(line))
     if dist is not None:

@@ -120,7 +120,8 @@ typedef struct FeFrameInfo {
 /* Stage timings accumulated with CUDA events on the handle's own streams (ms, and launch counts). */
 enum FeStage {
   FE_STAGE_H2D = 0, FE_STAGE_HIST, FE_STAGE_EQ_PYR, FE_STAGE_PYR_REST, FE_STAGE_FAST, FE_STAGE_SUBPIX, FE_STAGE_LK,
-  FE_STAGE_CANNY, FE_STAGE_FLD, FE_STAGE_COUNT
+  FE_STAGE_CANNY, FE_STAGE_FLD /* whole segment extraction: CCL + WALK + SEG */, FE_STAGE_FLD_CCL, FE_STAGE_FLD_WALK,
+  FE_STAGE_FLD_SEG, FE_STAGE_COUNT
 };
 typedef struct FeStageTimes {
   double ms[16];

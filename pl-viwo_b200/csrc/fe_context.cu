@@ -202,6 +202,7 @@ int FeContext::init() {
     FE_CUDA(cudaEventCreateWithFlags(&s.ev_l0, cudaEventDisableTiming));
     FE_CUDA(cudaEventCreateWithFlags(&s.ev_fast, cudaEventDisableTiming));
     for (auto &e : s.ev_fast_t) FE_CUDA(cudaEventCreate(&e));
+    for (auto &e : s.ev_sp_t) FE_CUDA(cudaEventCreate(&e));
   }
   occ_bits_.assign((size_t)((W_ + 63) / 64) * H_, 0);
   layout_cells();
@@ -253,6 +254,7 @@ FeContext::~FeContext() {
     if (s.ev_l0) cudaEventDestroy(s.ev_l0);
     if (s.ev_fast) cudaEventDestroy(s.ev_fast);
     for (auto &e : s.ev_fast_t) if (e) cudaEventDestroy(e);
+    for (auto &e : s.ev_sp_t) if (e) cudaEventDestroy(e);
     destroy_graphs(s);
     cudaFree(s.d_hist); cudaFree(s.d_counters); cudaFree(s.d_seq);
     if (s.s_a) cudaStreamDestroy(s.s_a);
@@ -288,7 +290,10 @@ int FeContext::spin_sync(cudaStream_t st) {
 int FeContext::wait_flag(volatile int *flag, int value, cudaStream_t st, std::string *err) {
   unsigned spins = 0;
   while (*flag != value) {
-    cpu_pause();
+    // a few microseconds of pure spinning (the usual wait is shorter than a context switch), then let other threads of
+    // an oversubscribed host run between polls
+    if (spins < 4000) cpu_pause();
+    else std::this_thread::yield();
     if ((++spins & 0x1fffff) == 0) {
       cudaError_t e = cudaStreamQuery(st);
       if (e != cudaSuccess && e != cudaErrorNotReady) {
@@ -393,7 +398,7 @@ int FeContext::record_line_path(FrameSlot &s, cudaStream_t st) {
   if (timing) cudaEventRecord(s.ev_t[5], st);
   launch_canny(s.half, cfg_.canny_th1, cfg_.canny_th2, s.fld, st);
   if (timing) cudaEventRecord(s.ev_t[6], st);
-  launch_fld(s.half, cfg_.fld_length_threshold, cfg_.fld_distance_threshold, s.fld, st);
+  launch_fld(s.half, cfg_.fld_length_threshold, cfg_.fld_distance_threshold, s.fld, st, timing ? &s.ev_t[8] : nullptr);
   if (timing) cudaEventRecord(s.ev_t[7], st);
   FE_CUDA(cudaMemcpyAsync(s.h_fld_counts, s.fld.counters + 3, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   FE_CUDA(cudaMemcpyAsync(s.h_segs, s.fld.out, 1024 * sizeof(float4), cudaMemcpyDeviceToHost, st));
@@ -691,11 +696,15 @@ int FeContext::run_predetection(FrameSlot &s) {
   delete w2;
   const int nc = (int)s.cand_sel.size();
   s.cand_ref.resize(nc);
+  s.sp_timed = false;
   if (nc > 0) {
     HostTimer w3(&wl[3]);
     // zero-copy: the kernel refines the candidates in place in pinned host memory
     for (int i = 0; i < nc; i++) s.h_cand_out[i] = make_float2(s.cand_sel[i].x, s.cand_sel[i].y);
+    s.sp_timed = s.timed;
+    if (s.sp_timed) cudaEventRecord(s.ev_sp_t[0], s.s_b);
     launch_corner_subpix(s.pyr.lvl[0], s.h_cand_out, nc, s.s_b);
+    if (s.sp_timed) cudaEventRecord(s.ev_sp_t[1], s.s_b);
     launch_signal(&s.h_flags[1], ++s.seq_subpix, s.s_b);
     e = cudaGetLastError();
     if (e != cudaSuccess) return bad(e, "cornerSubPix launch");
@@ -814,13 +823,19 @@ int FeContext::collect_impl(FeFrameInfo *info) {
   if (cur.timed) {
     FE_CUDA(cudaEventSynchronize(cur.ev_pyr));
     acc_time(mst_, FE_STAGE_H2D, cur.ev_t[0], cur.ev_t[1]);
-    if (cur.predet_ncell > 0 && cur.predet_state.load() == 2) acc_time(mst_, FE_STAGE_FAST, cur.ev_fast_t[0], cur.ev_fast_t[1]);
+    if (cur.predet_ncell > 0 && cur.predet_state.load() == 2) {
+      acc_time(mst_, FE_STAGE_FAST, cur.ev_fast_t[0], cur.ev_fast_t[1]);
+      if (cur.sp_timed) acc_time(mst_, FE_STAGE_SUBPIX, cur.ev_sp_t[0], cur.ev_sp_t[1]);
+    }
     if (cfg_.histogram_method == FE_HIST_HISTOGRAM) acc_time(mst_, FE_STAGE_HIST, cur.ev_t[1], cur.ev_t[2]);
     acc_time(mst_, FE_STAGE_EQ_PYR, cur.ev_t[2], cur.ev_t[3]);
     acc_time(mst_, FE_STAGE_PYR_REST, cur.ev_t[3], cur.ev_t[4]);
     if (cfg_.use_lines && cur.has_vp) {
       acc_time(mst_, FE_STAGE_CANNY, cur.ev_t[5], cur.ev_t[6]);
       acc_time(mst_, FE_STAGE_FLD, cur.ev_t[6], cur.ev_t[7]);
+      acc_time(mst_, FE_STAGE_FLD_CCL, cur.ev_t[6], cur.ev_t[8]);
+      acc_time(mst_, FE_STAGE_FLD_WALK, cur.ev_t[8], cur.ev_t[9]);
+      acc_time(mst_, FE_STAGE_FLD_SEG, cur.ev_t[9], cur.ev_t[7]);
     }
   }
   mst_.frames++;

@@ -94,7 +94,7 @@ struct FrameSlot {
   cudaGraphExec_t g_image = nullptr, g_fast = nullptr, g_lines = nullptr;
   int graph_version = -1;
   bool warmed = false;
-  cudaEvent_t ev_t[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_t[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool timed = false;
 
   // ---- pre-detection: everything perform_griding computes that does NOT depend on tracker state.  FAST runs on
@@ -106,6 +106,8 @@ struct FrameSlot {
   float2 *d_cand = nullptr, *h_cand_in = nullptr, *h_cand_out = nullptr;
   cudaEvent_t ev_l0 = nullptr, ev_fast = nullptr;
   cudaEvent_t ev_fast_t[2] = {nullptr, nullptr};
+  cudaEvent_t ev_sp_t[2] = {nullptr, nullptr};   // cornerSubPix stage timing (worker thread)
+  bool sp_timed = false;
   int *h_flags = nullptr;                 // pinned: [0] FAST done, [1] sub-pixel done, [2] lines done (sequence numbers)
   int seq_fast = 0, seq_subpix = 0, seq_lines = 0;
   std::atomic<int> predet_state{0};        // 0 none, 1 queued, 2 ready, -1 failed

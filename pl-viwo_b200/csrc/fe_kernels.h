@@ -81,7 +81,9 @@ struct FldBuffers {
 };
 constexpr int kSegsPerChainDiv = 21;  // a chain of n points yields at most n / 21 + 1 segments
 void launch_canny(const DevImage &half, float th_low, float th_high, FldBuffers &fb, cudaStream_t s);
-void launch_fld(const DevImage &half, int length_threshold, float distance_threshold, FldBuffers &fb, cudaStream_t s);
+// ev (optional, 2 events): recorded after the connected-component kernels and after the chain walk (stage timing)
+void launch_fld(const DevImage &half, int length_threshold, float distance_threshold, FldBuffers &fb, cudaStream_t s,
+                cudaEvent_t *ev = nullptr);
 void launch_unpack_edges(const FldBuffers &fb, int w, int h, uint8_t *d_out, cudaStream_t s);
 
 }  // namespace plviwo

@@ -706,13 +706,15 @@ void FldBuffers::release() {
   *this = FldBuffers();
 }
 
-void launch_fld(const DevImage &half, int length_threshold, float distance_threshold, FldBuffers &fb, cudaStream_t s) {
+void launch_fld(const DevImage &half, int length_threshold, float distance_threshold, FldBuffers &fb, cudaStream_t s,
+                cudaEvent_t *ev) {
   const int w = half.w, h = half.h, n = w * h;
   const int tpb = 256, nb = (n + tpb - 1) / tpb;
   k_ccl_init<<<nb, tpb, 0, s>>>(fb.edges, fb.words_per_row, w, h, fb.label, fb.cnt, fb.bbox, fb.counters);
   k_ccl_merge<<<nb, tpb, 0, s>>>(w, h, fb.label);
   k_ccl_flatten<<<nb, tpb, 0, s>>>(w, h, fb.label, fb.cnt, fb.bbox);
   k_ccl_roots<<<nb, tpb, 0, s>>>(w, h, fb.label, fb.cnt, length_threshold + 1, fb.comp_root, fb.counters, fb.max_chains);
+  if (ev) cudaEventRecord(ev[0], s);
   init_fld_constants();
   const int ws = ((w + 31) >> 5) + 2;
   size_t smem = (size_t)kLutSize + (size_t)(h + 2 * kPadRows) * ws * sizeof(unsigned);
@@ -724,6 +726,7 @@ void launch_fld(const DevImage &half, int length_threshold, float distance_thres
   k_fld_walk_cc<<<kWalkCtas, kWalkThreads, smem, s>>>(fb.edges, fb.words_per_row, fb.label, fb.cnt, fb.bbox, w, h, fb.comp_root, fb.counters, fb.max_chains,
                                                length_threshold, fb.chain_pts, fb.chain_seed, fb.chain_off, fb.chain_len,
                                                fb.max_chains);
+  if (ev) cudaEventRecord(ev[1], s);
   int blocks = (fb.max_chains + 127) / 128;
   k_fld_order<<<blocks, 128, 0, s>>>(fb.chain_seed, fb.counters, fb.max_chains, fb.order);
   k_fld_segments<<<(fb.max_chains + 63) / 64, 64, 0, s>>>(half.p, w, h, half.pitch, length_threshold, distance_threshold,

@@ -19,5 +19,7 @@ def _load(name, filename, submodule_search=None):
 _pkg = _load("plviwo_b200", "__init__.py", [_DIR])
 synth = _load("plviwo_b200.synth", "synth.py")
 build = _load("plviwo_b200.build", "build.py")
+shard = _load("plviwo_b200.shard", "shard.py")
 _pkg.synth = synth
 _pkg.build = build
+_pkg.shard = shard

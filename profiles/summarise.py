@@ -117,6 +117,13 @@ def full():
                     mean("l2%"), mean("occ%"), mean("regs"), mean("smem_s"), mean("smem_d"), mean("grid"), mean("block")))
     open(os.path.join(ROOT, "profiles", "kernels_%s.txt" % tag), "w").write("\n".join(out) + "\n")
     print("\n".join(out))
+    import json
+    traffic = {}
+    for k, recs in per.items():
+        v = [r.get("dram_rd", 0.0) + r.get("dram_wr", 0.0) for r in recs]
+        traffic[k] = sum(v) / len(v)
+    json.dump({"source": "gpurun_out/full_%s.ncu-rep (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" % tag,
+               "kernels": traffic}, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 
 
 launches()
