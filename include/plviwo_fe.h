@@ -16,6 +16,7 @@
  *   FeatureDatabase::update_feature(id,t,cam,u,v,un,vn) rows          ov_core/src/feat/FeatureDatabase.cpp:60-85 plviwo_fe_get_point_rows
  *   TrackBase::get_last_obs() / get_last_ids()                        ov_core/src/track/TrackBase.h:137-146      plviwo_fe_get_last_obs
  *   LineFeatureDatabase::update_feature(id,t,cam,line,line_n,...)     linefeat/LineFeatureDatabase.cpp:40-76     plviwo_fe_get_line_rows (+ _line_points)
+ *   TrackLSD::LineClassification(line, vanishing_points)              PL-VIWO/src/update/cam/TrackLSD.cpp:318-333 plviwo_fe_classify_lines
  *   TrackBase::set_num_features / change_feat_id                      ov_core/src/track/TrackBase.cpp:267-285    plviwo_fe_set_num_features / _change_feat_id
  *   tracker members pts_last/ids_last/currid, lines_last/...          TrackBase.h:173-192, TrackLSD.h:248-279    plviwo_fe_get_state / _set_state
  *
@@ -169,6 +170,10 @@ int plviwo_fe_get_point_rows(FeHandle *h, FePointRow *out, int cap, int *n_out);
 int plviwo_fe_get_last_obs(FeHandle *h, uint64_t *ids, float *uv /* 2 per point */, int cap, int *n_out);
 int plviwo_fe_get_line_rows(FeHandle *h, FeLineRow *out, int cap, int *n_out);
 int plviwo_fe_get_line_points(FeHandle *h, FeLinePoint *out, int cap, int *n_out);
+/* Re-runs LineClassification (TrackLSD.cpp:318-366) on the line rows of the last completed frame with these vanishing
+ * points.  For callers that, like UpdaterCamera.cpp:105-110, only know the vanishing points after the point tracker was
+ * fed: feed with any vp (e.g. zeros), then classify, then read the rows. */
+int plviwo_fe_classify_lines(FeHandle *h, const double vp[6]);
 /* extension: LK-tracked samples of last frame's segments: per sample (line row index in the PREVIOUS frame,
  * u0 v0 u1 v1, status) */
 int plviwo_fe_get_line_samples(FeHandle *h, float *uv01 /* 4 per sample */, uint8_t *status, int cap, int *n_out);

@@ -82,7 +82,7 @@ _lib = None
 # every symbol include/plviwo_fe.h declares (tests/test_abi.py checks the header against this list and the .so)
 EXPORTS = [
     "plviwo_fe_abi_version", "plviwo_fe_default_config", "plviwo_fe_device_count", "plviwo_fe_create", "plviwo_fe_destroy",
-    "plviwo_fe_last_error", "plviwo_fe_set_calib", "plviwo_fe_set_num_features", "plviwo_fe_change_feat_id", "plviwo_fe_feed",
+    "plviwo_fe_last_error", "plviwo_fe_classify_lines", "plviwo_fe_set_calib", "plviwo_fe_set_num_features", "plviwo_fe_change_feat_id", "plviwo_fe_feed",
     "plviwo_fe_feed_device", "plviwo_fe_submit", "plviwo_fe_collect", "plviwo_fe_get_point_rows", "plviwo_fe_get_last_obs",
     "plviwo_fe_get_line_rows", "plviwo_fe_get_line_points", "plviwo_fe_get_line_samples", "plviwo_fe_get_state",
     "plviwo_fe_set_state", "plviwo_fe_enable_taps", "plviwo_fe_tap", "plviwo_fe_enable_timing", "plviwo_fe_get_stage_times",
@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
         L.plviwo_fe_destroy.argtypes = [C.c_void_p]
         L.plviwo_fe_set_calib.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.plviwo_fe_set_num_features.argtypes = [C.c_void_p, C.c_int]
+        L.plviwo_fe_classify_lines.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.plviwo_fe_change_feat_id.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         L.plviwo_fe_feed.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                      C.c_void_p, C.POINTER(FeFrameInfo)]
@@ -253,6 +254,11 @@ class FrontEnd:
 
     def set_num_features(self, n: int):
         _check(self._lib.plviwo_fe_set_num_features(self._h, n), self._h)
+
+    def classify_lines(self, vanishing_points):
+        """TrackLSD::LineClassification of the last frame's line rows with these vanishing points (3 x (x, y))."""
+        vp = (C.c_double * 6)(*np.asarray(vanishing_points, np.float64).reshape(6))
+        _check(self._lib.plviwo_fe_classify_lines(self._h, vp), self._h)
 
     def change_feat_id(self, id_old: int, id_new: int):
         _check(self._lib.plviwo_fe_change_feat_id(self._h, id_old, id_new), self._h)

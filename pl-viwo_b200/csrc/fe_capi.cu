@@ -208,6 +208,10 @@ int plviwo_fe_get_line_points(FeHandle *h, FeLinePoint *out, int cap, int *n_out
   if (!h) return FE_BAD_ARG;
   return copy_out(h->ctx->result().line_points, out, cap, n_out);
 }
+int plviwo_fe_classify_lines(FeHandle *h, const double vp[6]) {
+  if (!h || !vp) return FE_BAD_ARG;
+  return h->ctx->classify_lines(vp);
+}
 int plviwo_fe_get_line_samples(FeHandle *h, float *uv01, uint8_t *status, int cap, int *n_out) {
   if (!h) return FE_BAD_ARG;
   const auto &s = h->ctx->result().sample_status;

@@ -1354,6 +1354,12 @@ int FeContext::lsd_feed(FrameSlot &cur) {
   return FE_OK;
 }
 
+int FeContext::classify_lines(const double vp[6]) {
+  FrameResult &r = const_cast<FrameResult &>(*cur_res_);
+  for (FeLineRow &row : r.line_rows) row.D = line_classification(make_float4(row.line[0], row.line[1], row.line[2], row.line[3]), vp);
+  return FE_OK;
+}
+
 // ------------------------------------------------------------------------------------------ state / taps
 namespace {
 struct StateHeader {

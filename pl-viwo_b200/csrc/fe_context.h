@@ -137,6 +137,7 @@ class FeContext {
   // results of the last collected frame (TrackBase::get_last_obs / get_last_ids are result().obs / obs_ids)
   const FrameResult &result() const { return *cur_res_; }
   int set_num_features(int n);
+  int classify_lines(const double vp[6]);
   int change_feat_id(uint64_t id_old, uint64_t id_new);
 
   int get_state(void *buf, size_t cap, size_t *n_bytes);

@@ -315,3 +315,47 @@ def test_bad_arguments(fe):
     with pytest.raises(fe.FrontEndError):
         h.feed_new_camera(0.0, np.zeros((100, 100), np.uint8))   # size mismatch: the reference exit()s here
     h.close()
+
+
+def test_setters_between_frames_and_line_classification(fe, synth):
+    """TrackBase::set_num_features / change_feat_id (TrackBase.h:150, TrackBase.cpp:267-285) and the late
+    LineClassification entry point: the tracker must follow the oracle through a feature-count change, an id
+    re-mapping and vanishing points that only arrive after the frame was fed (UpdaterCamera.cpp:105-110 order)."""
+    seq = synth.SynthSequence(seed=1012, n_frames=10, hard=False)
+    kw = dict(CFG1)
+    oracle = ofe.FrontEnd(ofe.FeConfig(K=seq.K, D=seq.D, use_lines=True, **kw))
+    gpu = fe.FrontEnd(fe.default_config(width=1280, height=560, K=seq.K, D=seq.D, use_lines=1, **kw))
+    zeros = np.zeros((3, 2))
+    for t in range(10):
+        img, vps = seq.frame(t), seq.vanishing_points(t)
+        if t == 3:      # ask for more features: the next top-off detection uses the new grid quota
+            n_before = len(gpu.get_last_ids())
+            oracle.klt.cfg.num_features = 320
+            gpu.set_num_features(320)
+        if t == 6:      # loop-closure style id change of an active feature
+            ids = oracle.klt.get_last_ids()
+            old, new = int(ids[len(ids) // 2]), 10 ** 6 + 7
+            st = oracle.klt.get_state()
+            st["ids_last"] = [new if int(i) == old else int(i) for i in st["ids_last"]]
+            oracle.klt.set_state(st)
+            gpu.change_feat_id(old, new)
+            assert new in [int(v) for v in gpu.get_last_ids()]
+        prow_o, lrow_o = oracle.feed(seq.timestamp(t), img, None, vps)
+        gpu.feed_new_camera(seq.timestamp(t), img, None, zeros)      # vanishing points not known yet
+        gpu.classify_lines(vps)                                       # ... now they are
+        assert [int(v) for v in gpu.point_rows()["id"]] == [r.id for r in prow_o], t
+        assert np.array_equal(gpu.get_last_ids(), np.array(oracle.klt.get_last_ids(), np.uint64)), t
+        lrows, lpts = gpu.line_rows()
+        assert _compare_lines(lrows, lpts, lrow_o), t
+    assert len(gpu.get_last_ids()) > n_before + 20     # the larger quota took effect
+    # the setters are refused while frames are in flight
+    gpu2 = fe.FrontEnd(fe.default_config(width=1280, height=560, K=seq.K, D=seq.D, lookahead=2, **kw))
+    gpu2.submit(0.0, seq.frame(0), vanishing_points=zeros)
+    with pytest.raises(fe.FrontEndError):
+        gpu2.set_num_features(100)
+    with pytest.raises(fe.FrontEndError):
+        gpu2.change_feat_id(1, 2)
+    gpu2.collect()
+    gpu2.set_num_features(100)
+    gpu2.close()
+    gpu.close()
