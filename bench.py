@@ -194,44 +194,45 @@ def run_gpu_pass(fe_mod, torch, handle, seq, srcs, steps, warmup, on_device, pit
 
 def run_gpu_multi(fe_mod, torch, seq, d_ptrs, pitch, n_streams, steps, warmup, cfg_kw, dev):
     """configs[4] shape on one GPU: n_streams independent handles (own CUDA streams, own tracker threads), each driven by
-    one host thread through submit/collect.  All streams replay the same device-resident sequence from different
-    start frames (they never exchange data, so this is n_streams times the single-stream work)."""
+    one host thread through plviwo_fe_play (the submit/collect loop inside the library, so the Python GIL is not part of
+    the measurement).  All streams replay the same device-resident sequence from different start frames (they never
+    exchange data, so this is n_streams times the single-stream work)."""
     import threading
     n = len(d_ptrs)
-    la = 8
+    la = int(os.environ.get("PLVIWO_BENCH_LA", "8"))
     handles = [fe_mod.FrontEnd(fe_mod.default_config(K=seq.K, D=seq.D, lookahead=la, **cfg_kw), device=dev) for _ in range(n_streams)]
-    start = threading.Barrier(n_streams + 1)
-    mid = threading.Barrier(n_streams + 1)
+    gate = threading.Barrier(n_streams + 1)
     frames_done = [0] * n_streams
 
     def drive(k):
         h = handles[k]
         off = (k * 37) % n
-        tot = warmup + steps
-        sub = 0
-        start.wait()
-        for i in range(tot):
-            if i == warmup:
-                mid.wait()      # everybody warmed up
-                mid.wait()      # timed region starts
-            while sub < tot and sub <= i + la:
-                t = (off + sub) % n
-                h.submit(seq.timestamp(sub), d_ptrs[t], stride=pitch, on_device=True, vanishing_points=seq.vanishing_points(t))
-                sub += 1
-            h.collect()
-            if i >= warmup:
-                frames_done[k] += 1
+        idx = [(off + i) % n for i in range(warmup + steps)]
+        ts = [seq.timestamp(i) for i in range(warmup + steps)]
+        ptrs = [d_ptrs[t] for t in idx]
+        vps = [seq.vanishing_points(t) for t in idx] if not os.environ.get("PLVIWO_BENCH_NOLINES") else None
+        h.play(ts[:warmup], ptrs[:warmup], stride=pitch, on_device=True, vanishing_points=vps[:warmup] if vps else None)
+        gate.wait()      # everybody warmed up
+        gate.wait()      # timed region starts
+        if os.environ.get("PLVIWO_BENCH_TIMING"):
+            h.enable_timing(True)
+            h.stage_times(reset=True)
+        st = h.play(ts[warmup:], ptrs[warmup:], stride=pitch, on_device=True, vanishing_points=vps[warmup:] if vps else None)
+        frames_done[k] = int(st.frames)
+        if os.environ.get("PLVIWO_BENCH_TIMING") and k == 0:
+            tt = h.stage_times()
+            sys.stderr.write("stream0 stage ms/frame: %s\n" % {a: round(b / max(tt["frames"], 1), 4) for a, b in tt["ms"].items()})
+            sys.stderr.write("stream0 host ms/frame: %s\n" % {a: round(b / max(tt["frames"], 1), 4) for a, b in tt["host_ms"].items()})
 
     th = [threading.Thread(target=drive, args=(k,)) for k in range(n_streams)]
     for t in th:
         t.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    start.wait()
-    mid.wait()
+    gate.wait()
     torch.cuda.synchronize()
     ev0.record()
     t0 = time.perf_counter()
-    mid.wait()
+    gate.wait()
     for t in th:
         t.join()
     torch.cuda.synchronize()
@@ -243,7 +244,8 @@ def run_gpu_multi(fe_mod, torch, seq, d_ptrs, pitch, n_streams, steps, warmup, c
     ms = float(ev0.elapsed_time(ev1))
     return {"streams": n_streams, "frames": sum(frames_done), "ms": ms, "value": sum(frames_done) / (ms * 1e-3), "unit": "frames/s",
             "wall_fps": sum(frames_done) / wall, "lookahead": la,
-            "note": "BASELINE.json configs[4] shape on ONE GPU: independent streams, one host driver thread each, frames resident in HBM"}
+            "note": "BASELINE.json configs[4] shape on ONE GPU: independent streams, one host driver thread each "
+                    "(plviwo_fe_play), frames resident in HBM"}
 
 
 def main():
@@ -254,9 +256,17 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=150, help="frames of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--multi-streams", type=int, default=4, help="streams per GPU of the extra multi-stream measurement (0 = skip)")
+    ap.add_argument("--multi-streams", type=int, default=8, help="streams per GPU of the extra multi-stream measurement (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # exactly ONE line on stdout: libraries that print banners there (NCCL's version line) are sent to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -276,7 +286,7 @@ def main():
                                            "(oracle/frontend.py) driving the real OpenCV kernels through cv2" % steps},
                 "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "p50_ms_per_frame": r["p50_ms"]}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -383,7 +393,8 @@ def main():
                         "bound (DESIGN.md 'Kernels'); per_kernel lists every kernel of the frame",
                 "per_kernel": per_kernel,
                 "stage_ms_per_frame": {k: v / nfr for k, v in st["ms"].items()},
-                "host_ms_per_frame": {k: v / max(res["stage"]["frames"], 1) for k, v in res["stage"]["host_ms"].items()},
+                "host_ms_per_frame": {k: v / max(res["stage"]["frames"], 1) for k, v in res["stage"]["host_ms"].items()
+                                      if not k.startswith("unused")},
                 "whole_frame": {"algorithmic_bytes": ab["frame_total"],
                                 "achieved_GBps": ab["frame_total"] * (total_frames / (ms * 1e-3)) / 1e9 / world}}
     cpu = None
@@ -408,7 +419,7 @@ def main():
         "gpu_launches": res["stage"]["kernel_launches_total"],
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "multi_stream": multi,
     }
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -18,6 +18,7 @@
  *   LineFeatureDatabase::update_feature(id,t,cam,line,line_n,...)     linefeat/LineFeatureDatabase.cpp:40-76     plviwo_fe_get_line_rows (+ _line_points)
  *   TrackLSD::LineClassification(line, vanishing_points)              PL-VIWO/src/update/cam/TrackLSD.cpp:318-333 plviwo_fe_classify_lines
  *   TrackBase::set_num_features / change_feat_id                      ov_core/src/track/TrackBase.cpp:267-285    plviwo_fe_set_num_features / _change_feat_id
+ *   the bag loop feeding frames in order                               PL-VIWO/src/run_bag.cpp:272-340            plviwo_fe_submit / _collect / _play
  *   tracker members pts_last/ids_last/currid, lines_last/...          TrackBase.h:173-192, TrackLSD.h:248-279    plviwo_fe_get_state / _set_state
  *
  * No C++ types, no exceptions, no exit() cross this boundary: malformed input is FE_BAD_ARG where the reference
@@ -130,8 +131,8 @@ typedef struct FeStageTimes {
   uint64_t frames;
   uint64_t kernel_launches_total;
   uint64_t h2d_bytes, d2h_bytes;   /* bytes moved by the handle's own cudaMemcpyAsync calls */
-  double host_ms[16];              /* host wall time: submit, detection, matching, ransac, lines, collect, line wait,
-                                      pre-detection wait; worker thread: total, FAST wait, sort, sub-pixel round trip */
+  double host_ms[16];              /* host wall time: [0] submit, [1] detection, [2] matching, [3] ransac, [4] lines,
+                                      [5] collect, [6] line wait, [7] candidate-table wait, [12] LK launch, [13] LK wait */
 } FeStageTimes;
 
 /* ---- lifetime ----------------------------------------------------------------------------------------- */
@@ -164,6 +165,17 @@ int plviwo_fe_feed_device(FeHandle *h, double timestamp, const void *d_image, in
 int plviwo_fe_submit(FeHandle *h, double timestamp, const uint8_t *image, int stride, int on_device,
                      const uint8_t *mask, int mask_stride, const double vp[6]);
 int plviwo_fe_collect(FeHandle *h, FeFrameInfo *info);
+
+/* Whole-sequence playback (run_bag.cpp:272-340 feeds a bag frame by frame): submit/collect over n_frames frames with the
+ * handle's lookahead, entirely inside the library.  images[i] is a host or device pointer (on_device), vps has 6 doubles
+ * per frame or is NULL (no line tracker).  Rows are counted and folded into a checksum instead of being returned; the
+ * rows of the LAST frame stay available through the getters.  Results are identical to feeding frame by frame. */
+typedef struct FePlayStats {
+  uint64_t frames, point_rows, line_rows, resets;
+  double checksum;   /* sum over point rows of (id + u + v) plus sum over line rows of (id + x1 + y1 + x2 + y2) */
+} FePlayStats;
+int plviwo_fe_play(FeHandle *h, int n_frames, const uint8_t *const *images, int stride, int on_device, const double *timestamps,
+                   const double *vps, FePlayStats *out);
 
 /* ---- results of the last completed frame -------------------------------------------------------------- */
 int plviwo_fe_get_point_rows(FeHandle *h, FePointRow *out, int cap, int *n_out);
@@ -206,6 +218,10 @@ int plviwo_op_equalize_pyramid(int device, const uint8_t *img, int w, int h, int
                                uint8_t *out_levels /* concatenated tight levels 0..maxLevel */, uint8_t *out_half);
 int plviwo_op_fast_cell(int device, const uint8_t *img, int w, int h, int threshold, int32_t *xys /* x y score */,
                         int cap, int *n_out);
+/* std::sort(corners, compare_response) + first nfg (Grider_GRID.h:128-133) on packed corners x | y << 12 | score << 24.
+ * device < 0: the host instantiation of the sort (sorted[] = whole sorted list); device >= 0: the selection kernel
+ * (cand[] = x, y of the survivors, n_cand of them; sorted may be NULL). */
+int plviwo_op_sort_corners(int device, const uint32_t *packed, int n, int nfg, uint32_t *sorted, float *cand, int *n_cand);
 int plviwo_op_corner_subpix(int device, const uint8_t *img, int w, int h, float *pts /* in/out 2 per point */, int n);
 int plviwo_op_lk(int device, const uint8_t *img0, const uint8_t *img1, int w, int h, int win, int max_level,
                  const float *pts0, float *pts1 /* in: initial flow, out */, uint8_t *status, int n);

@@ -24,7 +24,7 @@ FE_OK, FE_BAD_ARG, FE_NO_DEVICE, FE_CUDA_ERROR, FE_OVERFLOW, FE_INTERNAL = range
 HIST_NONE, HIST_HISTOGRAM, HIST_CLAHE = 0, 1, 2
 _STATUS = {0: "FE_OK", 1: "FE_BAD_ARG", 2: "FE_NO_DEVICE", 3: "FE_CUDA_ERROR", 4: "FE_OVERFLOW", 5: "FE_INTERNAL"}
 HOST_STAGES = ["submit", "detection", "matching", "ransac", "lines", "collect", "line_wait", "predet_wait",
-               "worker_total", "worker_fast_wait", "worker_sort", "worker_subpix", "lk_launch", "lk_wait"]
+               "unused8", "unused9", "unused10", "unused11", "lk_launch", "lk_wait"]
 STAGES = ["h2d", "hist", "eq_pyr1", "pyr_rest", "fast", "subpix", "lk", "canny", "fld", "fld_ccl", "fld_walk", "fld_seg"]
 TAP_PYR_LEVEL0, TAP_HALF, TAP_EDGES, TAP_FAST_LAST, TAP_LK_LAST, TAP_SUBPIX_LAST, TAP_FLD_LAST = 0, 32, 33, 34, 35, 36, 37
 
@@ -67,6 +67,11 @@ class FeFrameInfo(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class FePlayStats(C.Structure):
+    _fields_ = [("frames", C.c_uint64), ("point_rows", C.c_uint64), ("line_rows", C.c_uint64), ("resets", C.c_uint64),
+                ("checksum", C.c_double)]
+
+
 class FeStageTimes(C.Structure):
     _fields_ = [("ms", C.c_double * 16), ("launches", C.c_uint64 * 16), ("frames", C.c_uint64),
                 ("kernel_launches_total", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("host_ms", C.c_double * 16)]
@@ -83,10 +88,10 @@ _lib = None
 EXPORTS = [
     "plviwo_fe_abi_version", "plviwo_fe_default_config", "plviwo_fe_device_count", "plviwo_fe_create", "plviwo_fe_destroy",
     "plviwo_fe_last_error", "plviwo_fe_classify_lines", "plviwo_fe_set_calib", "plviwo_fe_set_num_features", "plviwo_fe_change_feat_id", "plviwo_fe_feed",
-    "plviwo_fe_feed_device", "plviwo_fe_submit", "plviwo_fe_collect", "plviwo_fe_get_point_rows", "plviwo_fe_get_last_obs",
+    "plviwo_fe_feed_device", "plviwo_fe_submit", "plviwo_fe_collect", "plviwo_fe_play", "plviwo_fe_get_point_rows", "plviwo_fe_get_last_obs",
     "plviwo_fe_get_line_rows", "plviwo_fe_get_line_points", "plviwo_fe_get_line_samples", "plviwo_fe_get_state",
     "plviwo_fe_set_state", "plviwo_fe_enable_taps", "plviwo_fe_tap", "plviwo_fe_enable_timing", "plviwo_fe_get_stage_times",
-    "plviwo_op_equalize_pyramid", "plviwo_op_fast_cell", "plviwo_op_corner_subpix", "plviwo_op_lk", "plviwo_op_undistort",
+    "plviwo_op_equalize_pyramid", "plviwo_op_fast_cell", "plviwo_op_sort_corners", "plviwo_op_corner_subpix", "plviwo_op_lk", "plviwo_op_undistort",
     "plviwo_op_canny_half", "plviwo_op_fld", "plviwo_op_ransac_fundamental",
 ]
 
@@ -112,6 +117,8 @@ def lib() -> C.CDLL:
         L.plviwo_fe_feed_device.argtypes = L.plviwo_fe_feed.argtypes
         L.plviwo_fe_submit.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.plviwo_fe_collect.argtypes = [C.c_void_p, C.POINTER(FeFrameInfo)]
+        L.plviwo_fe_play.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double), C.POINTER(FePlayStats)]
         for name in ("plviwo_fe_get_point_rows", "plviwo_fe_get_line_rows", "plviwo_fe_get_line_points"):
             getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.plviwo_fe_get_last_obs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
@@ -128,6 +135,7 @@ def lib() -> C.CDLL:
         L.plviwo_op_equalize_pyramid.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.plviwo_op_fast_cell.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.plviwo_op_corner_subpix.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.plviwo_op_sort_corners.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         L.plviwo_op_lk.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int]
         L.plviwo_op_undistort.argtypes = [C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]
@@ -300,6 +308,23 @@ class FrontEnd:
         else:
             ptr, stride = image.ctypes.data, image.strides[0]
         _check(self._lib.plviwo_fe_submit(self._h, float(timestamp), ptr, stride, 1 if on_device else 0, None, 0, vp), self._h)
+
+    def play(self, timestamps, images, stride: int = 0, on_device: bool = False, vanishing_points=None) -> FePlayStats:
+        """Whole-sequence playback inside the library (plviwo_fe_play).  images: list of device pointers (on_device) or of
+        2-D uint8 arrays; vanishing_points: per frame 3 x (x, y) or None."""
+        n = len(images)
+        if on_device:
+            ptrs = (C.c_void_p * n)(*[int(p) for p in images])
+        else:
+            ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in images])
+            stride = stride or images[0].strides[0]
+        ts = (C.c_double * n)(*[float(t) for t in timestamps])
+        vp = None
+        if vanishing_points is not None:
+            vp = (C.c_double * (6 * n))(*[float(v) for f in vanishing_points for p in f for v in p])
+        st = FePlayStats()
+        _check(self._lib.plviwo_fe_play(self._h, n, ptrs, stride, 1 if on_device else 0, ts, vp, C.byref(st)), self._h)
+        return st
 
     def collect(self) -> FeFrameInfo:
         _check(self._lib.plviwo_fe_collect(self._h, C.byref(self.info)), self._h)
@@ -500,6 +525,20 @@ def op_fast_cell(img: np.ndarray, threshold: int, device: int = 0) -> np.ndarray
     n = C.c_int(0)
     _check(lib().plviwo_op_fast_cell(device, img.ctypes.data, w, h, threshold, out.ctypes.data, cap, C.byref(n)))
     return out[:n.value].copy()
+
+
+def op_sort_corners(packed: np.ndarray, nfg: int, device: int = -1):
+    """Grider_GRID.h:128-133 on packed corners (x | y << 12 | score << 24).  device < 0: host instantiation, returns the
+    whole sorted list; device >= 0: the selection kernel, returns the (x, y) of the first nfg."""
+    packed = np.ascontiguousarray(packed, np.uint32)
+    n = C.c_int(0)
+    if device < 0:
+        out = np.empty_like(packed)
+        _check(lib().plviwo_op_sort_corners(device, packed.ctypes.data, len(packed), nfg, out.ctypes.data, None, C.byref(n)))
+        return out
+    cand = np.zeros((nfg, 2), np.float32)
+    _check(lib().plviwo_op_sort_corners(device, packed.ctypes.data, len(packed), nfg, None, cand.ctypes.data, C.byref(n)))
+    return cand[:n.value]
 
 
 def op_corner_subpix(img: np.ndarray, pts: np.ndarray, device: int = 0) -> np.ndarray:

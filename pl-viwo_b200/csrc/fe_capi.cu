@@ -162,6 +162,13 @@ int plviwo_fe_submit(FeHandle *h, double timestamp, const uint8_t *image, int st
   return h->ctx->submit(timestamp, image, stride, on_device != 0, mask, mask_stride, vp);
   API_END
 }
+int plviwo_fe_play(FeHandle *h, int n_frames, const uint8_t *const *images, int stride, int on_device, const double *timestamps,
+                   const double *vps, FePlayStats *out) {
+  API_BEGIN
+  if (!h || n_frames < 0 || (n_frames > 0 && (!images || !timestamps)) || stride < h->ctx->cfg().width) return FE_BAD_ARG;
+  return h->ctx->play(n_frames, images, stride, on_device != 0, timestamps, vps, out);
+  API_END
+}
 int plviwo_fe_collect(FeHandle *h, FeFrameInfo *info) {
   API_BEGIN
   if (!h) return FE_BAD_ARG;
@@ -388,6 +395,41 @@ int plviwo_op_fast_cell(int device, const uint8_t *img, int w, int h, int thresh
   API_END
 }
 
+int plviwo_op_sort_corners(int device, const uint32_t *packed, int n, int nfg, uint32_t *sorted, float *cand, int *n_cand) {
+  API_BEGIN
+  if (!packed || n < 0 || nfg < 1) return FE_BAD_ARG;
+  if (device < 0) {   // host instantiation of introsort.h
+    if (!sorted) return FE_BAD_ARG;
+    std::memcpy(sorted, packed, (size_t)n * sizeof(uint32_t));
+    host_sort_corners(sorted, n);
+    if (n_cand) *n_cand = std::min(n, nfg);
+    return FE_OK;
+  }
+  if (!cand || !n_cand) return FE_BAD_ARG;
+  OP_CUDA(cudaSetDevice(device));
+  DevBuf<FastCell> cells;
+  DevBuf<unsigned> total, kps, scratch;
+  DevBuf<int> off, cnt, ccnt;
+  DevBuf<float2> csel;
+  if (cells.alloc(1) || total.alloc(2) || kps.alloc(n) || scratch.alloc(n) || off.alloc(1) || cnt.alloc(1) || ccnt.alloc(1) ||
+      csel.alloc(nfg))
+    return FE_CUDA_ERROR;
+  FastCell c{0, 0, 4095, 4095};
+  const unsigned tot[2] = {(unsigned)n, 0u};
+  const int zero = 0;
+  OP_CUDA(cudaMemcpy(cells.p, &c, sizeof(c), cudaMemcpyHostToDevice));
+  OP_CUDA(cudaMemcpy(total.p, tot, sizeof(tot), cudaMemcpyHostToDevice));
+  OP_CUDA(cudaMemcpy(off.p, &zero, sizeof(int), cudaMemcpyHostToDevice));
+  OP_CUDA(cudaMemcpy(cnt.p, &n, sizeof(int), cudaMemcpyHostToDevice));
+  if (n) OP_CUDA(cudaMemcpy(kps.p, packed, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  launch_fast_select(cells.p, 1, 1, total.p, off.p, cnt.p, kps.p, std::max(n, 1), scratch.p, nfg, csel.p, ccnt.p, 0);
+  OP_CUDA(cudaDeviceSynchronize());
+  OP_CUDA(cudaMemcpy(n_cand, ccnt.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (*n_cand > 0) OP_CUDA(cudaMemcpy(cand, csel.p, (size_t)*n_cand * sizeof(float2), cudaMemcpyDeviceToHost));
+  return FE_OK;
+  API_END
+}
+
 int plviwo_op_corner_subpix(int device, const uint8_t *img, int w, int h, float *pts, int n) {
   API_BEGIN
   if (!img || !pts || n < 0) return FE_BAD_ARG;
@@ -396,7 +438,7 @@ int plviwo_op_corner_subpix(int device, const uint8_t *img, int w, int h, float 
   DevBuf<float2> d;
   if (raw.alloc(w, h) || raw.upload(img) || d.alloc(n)) return FE_CUDA_ERROR;
   OP_CUDA(cudaMemcpy(d.p, pts, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice));
-  launch_corner_subpix(raw.im, d.p, n, 0);
+  launch_corner_subpix(raw.im, d.p, d.p, n, 0);
   OP_CUDA(cudaDeviceSynchronize());
   OP_CUDA(cudaMemcpy(pts, d.p, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost));
   return FE_OK;

@@ -114,8 +114,6 @@ void FeContext::flush_stats(FeStageTimes &l) {
 void FeContext::reset_times() {
   std::lock_guard<std::mutex> lk(wstat_mu_);
   times_ = FeStageTimes{};
-  worker_launches_ = 0; worker_h2d_ = 0; worker_d2h_ = 0;
-  for (double &v : worker_ms_) v = 0;
 }
 
 int FeContext::alloc_image(DevImage &im, int w, int h) {
@@ -186,9 +184,12 @@ int FeContext::init() {
   cand_cap_ = std::max(max_cells_ * (cfg_.num_features + 1), 1024);
   if (cand_cap_ > 65536) cand_cap_ = 65536;
   FE_CUDA(cudaMalloc(&d_cells_, (size_t)max_cells_ * sizeof(FastCell)));
-  FE_CUDA(cudaStreamCreateWithPriority(&s_det2_, cudaStreamNonBlocking, lo));
   for (FrameSlot &s : slots_) {
-    FE_CUDA(cudaMalloc(&s.d_fast_total, sizeof(unsigned)));
+    FE_CUDA(cudaMalloc(&s.d_fast_total, 2 * sizeof(unsigned)));
+    FE_CUDA(cudaMalloc(&s.d_sort_scratch, (size_t)kps_cap_ * sizeof(unsigned)));
+    FE_CUDA(cudaMalloc(&s.d_cand_cnt, (size_t)max_cells_ * sizeof(int)));
+    FE_CUDA(cudaMallocHost(&s.h_cand_cnt, (size_t)max_cells_ * sizeof(int)));
+    FE_CUDA(cudaMalloc(&s.d_cand_ref, (size_t)cand_cap_ * sizeof(float2)));
     FE_CUDA(cudaMalloc(&s.d_kps, (size_t)kps_cap_ * sizeof(unsigned)));
     FE_CUDA(cudaMallocHost(&s.h_kps, (size_t)kps_cap_ * sizeof(unsigned)));
     FE_CUDA(cudaMalloc(&s.d_band_off, (size_t)max_cells_ * max_bands_ * sizeof(int)));
@@ -206,10 +207,6 @@ int FeContext::init() {
   }
   occ_bits_.assign((size_t)((W_ + 63) / 64) * H_, 0);
   layout_cells();
-  const char *nw_env = std::getenv("PLVIWO_WORKERS");
-  int nworkers = nw_env ? std::atoi(nw_env) : 3;
-  if (nworkers < 1) nworkers = 1;
-  for (int i = 0; i < nworkers; i++) workers_.emplace_back([this] { worker_main(); });
   klt_thread_ = std::thread([this] { klt_main(); });
   line_thread_ = std::thread([this] { line_main(); });
 
@@ -233,13 +230,6 @@ FeContext::~FeContext() {
   if (klt_thread_.joinable()) klt_thread_.join();
   line_q_.stop();
   if (line_thread_.joinable()) line_thread_.join();
-  {
-    std::lock_guard<std::mutex> lk(wmu_);
-    wstop_ = true;
-  }
-  wcv_.notify_all();
-  for (auto &w : workers_)
-    if (w.joinable()) w.join();
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
   for (FrameSlot &s : slots_) {
@@ -248,6 +238,7 @@ FeContext::~FeContext() {
     cudaFree(s.half.p);
     s.fld.release();
     cudaFreeHost(s.h_segs); cudaFreeHost(s.h_fld_counts); cudaFreeHost(s.h_raw);
+    cudaFree(s.d_sort_scratch); cudaFree(s.d_cand_cnt); cudaFreeHost(s.h_cand_cnt); cudaFree(s.d_cand_ref);
     cudaFree(s.d_fast_total); cudaFree(s.d_kps); cudaFreeHost(s.h_kps); cudaFree(s.d_band_off); cudaFree(s.d_band_cnt);
     cudaFreeHost(s.h_flags);
     cudaFreeHost(s.h_band); cudaFree(s.d_cand); cudaFreeHost(s.h_cand_in); cudaFreeHost(s.h_cand_out);
@@ -268,7 +259,6 @@ FeContext::~FeContext() {
   if (ev_sync_) cudaEventDestroy(ev_sync_);
   cudaFreeHost(h_flag_lk_);
   cudaFree(d_cells_);
-  if (s_det2_) cudaStreamDestroy(s_det2_);
   cudaFree(d_pts0_); cudaFree(d_pts1_); cudaFree(d_p0n_); cudaFree(d_p1n_); cudaFree(d_status_);
   cudaFreeHost(h_pts0_); cudaFreeHost(h_pts1_); cudaFreeHost(h_p0n_); cudaFreeHost(h_p1n_); cudaFreeHost(h_status_);
   if (s_pt_) cudaStreamDestroy(s_pt_);
@@ -377,18 +367,31 @@ int FeContext::record_image_path(FrameSlot &s, cudaStream_t st) {
 int FeContext::record_fast_path(FrameSlot &s, cudaStream_t st) {
   const int ncell = (int)cells_.size(), nb = cells_nb_;
   if (ncell > 0) {
-    FE_CUDA(cudaMemsetAsync(s.d_fast_total, 0, sizeof(unsigned), st));
+    const int nfg = cells_nfg_, ntab_c = ncell * nfg;
+    FE_CUDA(cudaMemsetAsync(s.d_fast_total, 0, 2 * sizeof(unsigned), st));
     if (timing) cudaEventRecord(s.ev_fast_t[0], st);
     launch_fast(s.pyr.lvl[0], d_cells_, ncell, nb, cells_csx_, cfg_.fast_threshold, s.d_fast_total, s.d_band_off, s.d_band_cnt,
                 s.d_kps, kps_cap_, st);
+    // Grider_GRID.h:128-133 and :163-179 on the device: per-cell std::sort + top num_features_grid, then cornerSubPix of
+    // every survivor.  Only the candidate table (a few KB) goes back to the host.
+    launch_fast_select(d_cells_, ncell, nb, s.d_fast_total, s.d_band_off, s.d_band_cnt, s.d_kps, kps_cap_, s.d_sort_scratch, nfg,
+                       s.d_cand, s.d_cand_cnt, st);
     if (timing) cudaEventRecord(s.ev_fast_t[1], st);
-    const int ntab = ncell * nb;
-    const int spec = std::min(16384, kps_cap_);   // speculative first chunk of the compact keypoint list
-    FE_CUDA(cudaMemcpyAsync(s.h_band, s.d_fast_total, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    FE_CUDA(cudaMemcpyAsync(s.h_band + 1, s.d_band_off, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, st));
-    FE_CUDA(cudaMemcpyAsync(s.h_band + 1 + ntab, s.d_band_cnt, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, st));
-    FE_CUDA(cudaMemcpyAsync(s.h_kps, s.d_kps, (size_t)spec * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    if (timing) cudaEventRecord(s.ev_sp_t[0], st);
+    launch_corner_subpix(s.pyr.lvl[0], s.d_cand, s.d_cand_ref, ntab_c, st, s.d_cand_cnt, nfg);
+    if (timing) cudaEventRecord(s.ev_sp_t[1], st);
+    FE_CUDA(cudaMemcpyAsync(s.h_cand_cnt, s.d_cand_cnt, (size_t)ncell * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FE_CUDA(cudaMemcpyAsync(s.h_cand_in, s.d_cand, (size_t)ntab_c * sizeof(float2), cudaMemcpyDeviceToHost, st));
+    FE_CUDA(cudaMemcpyAsync(s.h_cand_out, s.d_cand_ref, (size_t)ntab_c * sizeof(float2), cudaMemcpyDeviceToHost, st));
+    if (taps) {   // debug tap: every cell's full corner list in the reference's order
+      const int ntab = ncell * nb;
+      FE_CUDA(cudaMemcpyAsync(s.h_band, s.d_fast_total, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+      FE_CUDA(cudaMemcpyAsync(s.h_band + 1, s.d_band_off, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, st));
+      FE_CUDA(cudaMemcpyAsync(s.h_band + 1 + ntab, s.d_band_cnt, (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost, st));
+      FE_CUDA(cudaMemcpyAsync(s.h_kps, s.d_kps, (size_t)kps_cap_ * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    }
   }
+  s.fast_taps = taps;
   launch_signal_inc(&s.h_flags[0], s.d_seq + 0, st);
   FE_CUDA(cudaGetLastError());
   return FE_OK;
@@ -450,7 +453,7 @@ int FeContext::enqueue_frame_independent(FrameSlot &s) {
   const bool lines = cfg_.use_lines && s.has_vp;
   // a slot replays its graphs from its second use on (the first use runs the same calls directly, which also gets
   // every lazy one-time initialisation out of the way before anything is captured)
-  bool replay = use_graphs_ && s.warmed && !timing;   // stage timing needs real event records: direct launches
+  bool replay = use_graphs_ && s.warmed && !timing && !taps;   // stage timing / taps: direct launches of the same calls
   if (replay && s.graph_version != layout_version_) {
     int rc = build_graphs(s);
     if (rc) return rc;
@@ -484,8 +487,9 @@ int FeContext::enqueue_frame_independent(FrameSlot &s) {
   // bookkeeping (identical for both ways of issuing the work)
   const int ncell = (int)cells_.size(), ntab = ncell * cells_nb_;
   mst_.kernel_launches_total += (cfg_.histogram_method == FE_HIST_HISTOGRAM ? 1 : 0) + 1 + std::max(s.pyr.n - 2, 0) +
-                                 (ncell > 0 ? 1 : 0) + 1 + (lines ? 11 : 0);
-  if (ncell > 0) mst_.d2h_bytes += sizeof(unsigned) + (size_t)2 * ntab * sizeof(int) + (size_t)std::min(16384, kps_cap_) * sizeof(unsigned);
+                                 (ncell > 0 ? 3 : 0) + 1 + (lines ? 11 : 0);
+  (void)ntab;
+  if (ncell > 0) mst_.d2h_bytes += (size_t)ncell * sizeof(int) + (size_t)2 * ncell * cells_nfg_ * sizeof(float2);
   if (lines) mst_.d2h_bytes += 2 * sizeof(int) + 1024 * sizeof(float4);
   return FE_OK;
 }
@@ -507,10 +511,6 @@ int FeContext::submit_impl(double t, const uint8_t *image, int stride, bool on_d
     if (!slots_[i].busy && i != last_slot_) { si = i; break; }
   if (si < 0) return err(FE_BAD_ARG, "submit: lookahead window full (collect a frame first)");
   FrameSlot &s = slots_[si];
-  if (s.predet_state.load() == 1) {   // the worker may still be refining this slot's previous frame
-    int rc = wait_predetection(s);
-    if (rc) return rc;
-  }
   s.busy = true;
   s.timestamp = t;
   s.res.clear();
@@ -548,11 +548,6 @@ int FeContext::submit_impl(double t, const uint8_t *image, int stride, bool on_d
   if (rc) return rc;
   rc = enqueue_frame_independent(s);
   if (rc) return rc;
-  {
-    std::lock_guard<std::mutex> lk(wmu_);
-    wqueue_.push_back(s.index);
-  }
-  wcv_.notify_one();
   queue_.push_back(si);
   s.stage.store(1, std::memory_order_release);
   klt_q_.push(si);
@@ -612,130 +607,51 @@ int FeContext::enqueue_fast_all_cells(FrameSlot &s) {
   return FE_OK;
 }
 
-namespace {
-// std::sort's permutation depends only on the comparator's answers, not on the element type, so the corners are sorted
-// as 8-byte (response, packed xy) records instead of 28-byte cv::KeyPoints: same introsort, same tie permutation.
-struct KpSort {
-  float response;
-  unsigned xy;
-};
-bool compare_response(KpSort first, KpSort second) { return first.response > second.response; }  // Grider_FAST.h:57
-}  // namespace
-
-void FeContext::worker_main() {
-  cudaSetDevice(device_);
-  while (true) {
-    int si;
-    {
-      std::unique_lock<std::mutex> lk(wmu_);
-      wcv_.wait(lk, [this] { return wstop_ || !wqueue_.empty(); });
-      if (wqueue_.empty()) return;   // stop requested and nothing left
-      si = wqueue_.front();
-      wqueue_.pop_front();
-    }
-    FrameSlot &s = slots_[si];
-    int rc = run_predetection(s);
-    s.predet_state.store(rc == FE_OK ? 2 : -1);
-  }
-}
-
-// worker thread: std::sort per cell (Grider_GRID.h:128), first num_features_grid of each (:133), cornerSubPix (:163-179)
-int FeContext::run_predetection(FrameSlot &s) {
-  auto bad = [&](cudaError_t e, const char *what) {
-    worker_error_ = std::string(what) + ": " + cudaGetErrorString(e);
-    return FE_CUDA_ERROR;
-  };
-  double wl[4] = {0, 0, 0, 0};
-  struct Flush {
-    FeContext *c; double *l;
-    ~Flush() { std::lock_guard<std::mutex> lk(c->wstat_mu_); for (int i = 0; i < 4; i++) c->worker_ms_[i] += l[i]; }
-  } flush{this, wl};
-  HostTimer wt(&wl[0]);
-  cudaError_t e;
-  {
-    HostTimer w1(&wl[1]);
-    if (wait_flag(&s.h_flags[0], s.seq_fast, s.s_b, &worker_error_)) return FE_CUDA_ERROR;
-    e = cudaSuccess;
-  }
+// The frame's candidate table (per cell: the first num_features_grid corners after the reference's std::sort, before and
+// after cornerSubPix) was produced on the device by record_fast_path; wait for its completion signal and unpack it.
+// Called by the thread that needs the table (the point tracker; set_state).
+int FeContext::wait_predetection(FrameSlot &s) {
+  const int st = s.predet_state.load(std::memory_order_acquire);
+  if (st == 2) return FE_OK;
+  if (st == 0) return err(FE_INTERNAL, "pre-detection was never queued for this frame");
+  if (wait_flag(&s.h_flags[0], s.seq_fast, s.s_b, &t_err)) return FE_CUDA_ERROR;
   const int ncell = s.predet_ncell, nb = s.predet_nb, nfg = s.predet_nfg;
   s.cell_first.assign(ncell + 1, 0);
   s.cand_sel.clear();
   s.cand_ref.clear();
   s.cell_kps_tap.clear();
   s.cell_kps_first.assign(ncell + 1, 0);
-  if (ncell == 0) return FE_OK;
-  const int ntab = ncell * nb;
-  const int spec = std::min(16384, kps_cap_);
-  const int total = std::min(s.h_band[0], kps_cap_);
-  if (total > spec) {
-    e = cudaMemcpyAsync(s.h_kps + spec, s.d_kps + spec, (size_t)(total - spec) * sizeof(unsigned), cudaMemcpyDeviceToHost, s.s_b);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s.s_b);
-    if (e != cudaSuccess) return bad(e, "keypoint tail copy");
-    worker_d2h_ += (uint64_t)(total - spec) * sizeof(unsigned);
-  }
-  const int *band_off = s.h_band + 1, *band_cnt = s.h_band + 1 + ntab;
-  std::vector<KpSort> kps;
-  HostTimer *w2 = new HostTimer(&wl[2]);
   for (int c = 0; c < ncell; c++) {
-    kps.clear();
-    for (int b = 0; b < nb; b++) {
-      const int off = band_off[c * nb + b], cnt = band_cnt[c * nb + b];
-      for (int k = 0; k < cnt && off + k < total; k++) {
-        const unsigned v = s.h_kps[off + k];
-        kps.push_back(KpSort{(float)(v >> 24), v});
-        if (taps) s.cell_kps_tap.insert(s.cell_kps_tap.end(), {(int)(v & 0xfff), (int)((v >> 12) & 0xfff), (int)(v >> 24)});
-      }
+    const int cnt = std::min(s.h_cand_cnt[c], nfg);
+    for (int i = 0; i < cnt && (int)s.cand_sel.size() < cand_cap_; i++) {
+      const float2 a = s.h_cand_in[c * nfg + i], r = s.h_cand_out[c * nfg + i];
+      s.cand_sel.push_back(Pt{a.x, a.y});
+      s.cand_ref.push_back(Pt{r.x, r.y});
     }
-    s.cell_kps_first[c + 1] = (int)s.cell_kps_tap.size() / 3;
-    std::sort(kps.begin(), kps.end(), compare_response);   // unstable: ties are permuted exactly like the reference
-    const float x0 = (float)s.cells[c].x, y0 = (float)s.cells[c].y;
-    for (size_t i = 0; i < (size_t)nfg && i < kps.size() && (int)s.cand_sel.size() < cand_cap_; i++)
-      s.cand_sel.push_back(Pt{(float)(kps[i].xy & 0xfff) + x0, (float)((kps[i].xy >> 12) & 0xfff) + y0});
     s.cell_first[c + 1] = (int)s.cand_sel.size();
   }
-  delete w2;
-  const int nc = (int)s.cand_sel.size();
-  s.cand_ref.resize(nc);
-  s.sp_timed = false;
-  if (nc > 0) {
-    HostTimer w3(&wl[3]);
-    // zero-copy: the kernel refines the candidates in place in pinned host memory
-    for (int i = 0; i < nc; i++) s.h_cand_out[i] = make_float2(s.cand_sel[i].x, s.cand_sel[i].y);
-    s.sp_timed = s.timed;
-    if (s.sp_timed) cudaEventRecord(s.ev_sp_t[0], s.s_b);
-    launch_corner_subpix(s.pyr.lvl[0], s.h_cand_out, nc, s.s_b);
-    if (s.sp_timed) cudaEventRecord(s.ev_sp_t[1], s.s_b);
-    launch_signal(&s.h_flags[1], ++s.seq_subpix, s.s_b);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return bad(e, "cornerSubPix launch");
-    if (wait_flag(&s.h_flags[1], s.seq_subpix, s.s_b, &worker_error_)) return FE_CUDA_ERROR;
-    worker_launches_ += 2;
-    worker_h2d_ += (uint64_t)nc * sizeof(float2);
-    worker_d2h_ += (uint64_t)nc * sizeof(float2);
-    for (int i = 0; i < nc; i++) s.cand_ref[i] = Pt{s.h_cand_out[i].x, s.h_cand_out[i].y};
+  if (s.fast_taps && ncell > 0) {
+    const int ntab = ncell * nb;
+    const int total = std::min(s.h_band[0], kps_cap_);
+    const int *band_off = s.h_band + 1, *band_cnt = s.h_band + 1 + ntab;
+    for (int c = 0; c < ncell; c++) {
+      for (int b = 0; b < nb; b++) {
+        const int off = band_off[c * nb + b], cnt = band_cnt[c * nb + b];
+        for (int k = 0; k < cnt && off + k < total; k++) {
+          const unsigned v = s.h_kps[off + k];
+          s.cell_kps_tap.insert(s.cell_kps_tap.end(), {(int)(v & 0xfff), (int)((v >> 12) & 0xfff), (int)(v >> 24)});
+        }
+      }
+      s.cell_kps_first[c + 1] = (int)s.cell_kps_tap.size() / 3;
+    }
   }
+  s.predet_state.store(2, std::memory_order_release);
   return FE_OK;
-}
-
-int FeContext::wait_predetection(FrameSlot &s) {
-  // normally long done (the frame was submitted at least one frame ago); spin briefly, then yield
-  int spins = 0;
-  while (true) {
-    int st = s.predet_state.load(std::memory_order_acquire);
-    if (st == 2) return FE_OK;
-    if (st == -1) return err(FE_CUDA_ERROR, "pre-detection failed: " + worker_error_);
-    if (st == 0) return err(FE_INTERNAL, "pre-detection was never queued for this frame");
-    if (++spins > 2000) std::this_thread::yield();
-  }
 }
 
 FeStageTimes FeContext::snapshot_times() {
   std::lock_guard<std::mutex> lk(wstat_mu_);
   FeStageTimes t = times_;
-  t.kernel_launches_total += worker_launches_.load();
-  t.h2d_bytes += worker_h2d_.load();
-  t.d2h_bytes += worker_d2h_.load();
-  for (int i = 0; i < 4; i++) t.host_ms[8 + i] = worker_ms_[i];
   return t;
 }
 
@@ -823,9 +739,10 @@ int FeContext::collect_impl(FeFrameInfo *info) {
   if (cur.timed) {
     FE_CUDA(cudaEventSynchronize(cur.ev_pyr));
     acc_time(mst_, FE_STAGE_H2D, cur.ev_t[0], cur.ev_t[1]);
-    if (cur.predet_ncell > 0 && cur.predet_state.load() == 2) {
+    if (cur.predet_ncell > 0) {
+      FE_CUDA(cudaStreamSynchronize(cur.s_b));
       acc_time(mst_, FE_STAGE_FAST, cur.ev_fast_t[0], cur.ev_fast_t[1]);
-      if (cur.sp_timed) acc_time(mst_, FE_STAGE_SUBPIX, cur.ev_sp_t[0], cur.ev_sp_t[1]);
+      acc_time(mst_, FE_STAGE_SUBPIX, cur.ev_sp_t[0], cur.ev_sp_t[1]);
     }
     if (cfg_.histogram_method == FE_HIST_HISTOGRAM) acc_time(mst_, FE_STAGE_HIST, cur.ev_t[1], cur.ev_t[2]);
     acc_time(mst_, FE_STAGE_EQ_PYR, cur.ev_t[2], cur.ev_t[3]);
@@ -843,6 +760,37 @@ int FeContext::collect_impl(FeFrameInfo *info) {
   res.info.n_line_rows = (int)res.line_rows.size();
   res.info.n_last_obs = (int)res.obs.size();
   if (info) *info = res.info;
+  return FE_OK;
+}
+
+int FeContext::play(int n_frames, const uint8_t *const *images, int stride, bool on_device, const double *timestamps,
+                    const double *vps, FePlayStats *out) {
+  if (!queue_.empty()) {
+    last_error = "play: frames submitted with plviwo_fe_submit are still pending";
+    return FE_BAD_ARG;
+  }
+  FePlayStats st;
+  std::memset(&st, 0, sizeof(st));
+  const int la = std::max(cfg_.lookahead, 0);
+  int sub = 0;
+  for (int i = 0; i < n_frames; i++) {
+    while (sub < n_frames && sub <= i + la) {
+      int rc = submit(timestamps[sub], images[sub], stride, on_device, nullptr, 0, vps ? vps + 6 * (size_t)sub : nullptr);
+      if (rc) return rc;
+      sub++;
+    }
+    FeFrameInfo info;
+    int rc = collect(&info);
+    if (rc) return rc;
+    const FrameResult &r = result();
+    st.frames++;
+    st.point_rows += r.point_rows.size();
+    st.line_rows += r.line_rows.size();
+    st.resets += info.reset ? 1 : 0;
+    for (const FePointRow &p : r.point_rows) st.checksum += (double)p.id + p.u + p.v;
+    for (const FeLineRow &l : r.line_rows) st.checksum += (double)l.id + l.line[0] + l.line[1] + l.line[2] + l.line[3];
+  }
+  if (out) *out = st;
   return FE_OK;
 }
 
@@ -1006,11 +954,6 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
       rc = record_fast_path(slot, slot.s_b);
       if (rc) return rc;
       slot.seq_fast++;
-      {
-        std::lock_guard<std::mutex> lk(wmu_);
-        wqueue_.push_back(slot.index);
-      }
-      wcv_.notify_one();
     }
     {
       HostTimer hw(&kst_.host_ms[7]);
@@ -1456,7 +1399,6 @@ int FeContext::set_state(const void *buf, size_t n_bytes) {
       pol_last_[i][key] = val;
     }
   for (FrameSlot &s : slots_) {
-    if (s.predet_state.load() == 1) wait_predetection(s);
     s.busy = false;
   }
   FE_CUDA(cudaDeviceSynchronize());
@@ -1485,10 +1427,7 @@ int FeContext::set_state(const void *buf, size_t n_bytes) {
       rc = record_fast_path(s, s.s_b);
       if (rc) return rc;
       s.seq_fast++;
-      std::lock_guard<std::mutex> lk(wmu_);
-      wqueue_.push_back(s.index);
     }
-    wcv_.notify_one();
     if (hd.has_mask) {
       s.mask.resize((size_t)W_ * H_);
       get(s.mask.data(), (size_t)W_ * H_);

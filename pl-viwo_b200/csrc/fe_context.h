@@ -98,16 +98,19 @@ struct FrameSlot {
   bool timed = false;
 
   // ---- pre-detection: everything perform_griding computes that does NOT depend on tracker state.  FAST runs on
-  // every grid cell of the frame as soon as level 0 exists; a worker thread sorts each cell's corners with the
-  // reference's std::sort, takes the first num_features_grid of each and refines them (cornerSubPix).  The top-off
-  // detection at collect() time then only applies the state-dependent tests (valid cells, mask, min distance).
+  // every grid cell of the frame as soon as level 0 exists; a second kernel sorts each cell's corners with the
+  // reference's std::sort (introsort.h), takes the first num_features_grid of each and a third refines them
+  // (cornerSubPix).  The top-off detection of the point tracker then only applies the state-dependent tests (valid
+  // cells, mask, min distance) to this candidate table.
   unsigned *d_fast_total = nullptr, *d_kps = nullptr, *h_kps = nullptr;
   int *d_band_off = nullptr, *d_band_cnt = nullptr, *h_band = nullptr;   // h_band: [total, off..., cnt...]
-  float2 *d_cand = nullptr, *h_cand_in = nullptr, *h_cand_out = nullptr;
+  float2 *d_cand = nullptr, *d_cand_ref = nullptr, *h_cand_in = nullptr, *h_cand_out = nullptr;   // fixed stride: cell c at c * nfg
+  int *d_cand_cnt = nullptr, *h_cand_cnt = nullptr;
+  unsigned *d_sort_scratch = nullptr;
+  bool fast_taps = false;                 // the full corner lists were copied back too (debug taps)
   cudaEvent_t ev_l0 = nullptr, ev_fast = nullptr;
   cudaEvent_t ev_fast_t[2] = {nullptr, nullptr};
-  cudaEvent_t ev_sp_t[2] = {nullptr, nullptr};   // cornerSubPix stage timing (worker thread)
-  bool sp_timed = false;
+  cudaEvent_t ev_sp_t[2] = {nullptr, nullptr};   // cornerSubPix stage timing
   int *h_flags = nullptr;                 // pinned: [0] FAST done, [1] sub-pixel done, [2] lines done (sequence numbers)
   int seq_fast = 0, seq_subpix = 0, seq_lines = 0;
   std::atomic<int> predet_state{0};        // 0 none, 1 queued, 2 ready, -1 failed
@@ -131,6 +134,8 @@ class FeContext {
   int submit(double t, const uint8_t *image, int stride, bool on_device, const uint8_t *mask, int mask_stride,
              const double vp[6]);
   int collect(FeFrameInfo *info);
+  int play(int n_frames, const uint8_t *const *images, int stride, bool on_device, const double *timestamps, const double *vps,
+           FePlayStats *out);
   int feed(double t, const uint8_t *image, int w, int h, int stride, bool on_device, const uint8_t *mask,
            int mask_stride, const double vp[6], FeFrameInfo *info);
 
@@ -171,8 +176,6 @@ class FeContext {
   void destroy_graphs(FrameSlot &s);
   void layout_cells();                       // all grid cells of the frame (Grider_GRID geometry)
   int enqueue_fast_all_cells(FrameSlot &s);  // main thread, stream s_det_
-  int run_predetection(FrameSlot &s);        // worker thread: sort / top-k / cornerSubPix
-  void worker_main();
   int wait_predetection(FrameSlot &s);
   // TrackKLT
   int klt_feed(FrameSlot &cur);
@@ -220,15 +223,6 @@ class FeContext {
   int layout_version_ = 0;
   bool use_graphs_ = true;
   std::vector<uint64_t> occ_bits_;
-  cudaStream_t s_det_ = nullptr, s_det2_ = nullptr;
-  std::vector<std::thread> workers_;      // pre-detection workers (frames are independent: any worker takes any frame)
-  std::mutex wmu_;
-  std::condition_variable wcv_;
-  std::deque<int> wqueue_;
-  bool wstop_ = false;
-  std::atomic<uint64_t> worker_launches_{0}, worker_h2d_{0}, worker_d2h_{0};
-  std::string worker_error_;
-  double worker_ms_[4] = {0, 0, 0, 0};
   std::mutex wstat_mu_;
   std::vector<float> sc_px_, sc_py_;      // scratch of the line tracker
   std::vector<uint8_t> sc_pass_;

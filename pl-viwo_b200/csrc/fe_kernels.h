@@ -43,8 +43,19 @@ struct FastCell {
 void launch_fast(const DevImage &img, const FastCell *d_cells, int n_cells, int max_bands, int max_cell_w, int threshold,
                  unsigned *d_total, int *d_band_off, int *d_band_cnt, unsigned *d_kps, int kps_cap, cudaStream_t s);
 
+// Per-cell std::sort + top num_features_grid (Grider_GRID.h:128-133) on the device.  d_total: 2 counters, both zero on
+// entry of launch_fast ([0] corners, [1] scratch cursor); d_scratch: kps_cap words; output: cell c's survivors at
+// d_cand_sel[c * nfg ..] (full-image coordinates), d_cand_cnt[c] of them.
+void launch_fast_select(const FastCell *d_cells, int n_cells, int max_bands, unsigned *d_total, const int *d_band_off,
+                        const int *d_band_cnt, const unsigned *d_kps, int kps_cap, unsigned *d_scratch, int nfg,
+                        float2 *d_cand_sel, int *d_cand_cnt, cudaStream_t s);
+void host_sort_corners(unsigned *v, int n);   // the same introsort on the host (tests)
+
 // ---- cornerSubPix (kernels_track.cu) ----------------------------------------------------------------------
-void launch_corner_subpix(const DevImage &img, float2 *d_pts, int n, cudaStream_t s);
+// n points; with d_cnt != null the points are a fixed-stride table (slot i belongs to cell i / stride and is live only if
+// i % stride < d_cnt[cell]).  d_in == d_out is allowed.
+void launch_corner_subpix(const DevImage &img, const float2 *d_in, float2 *d_out, int n, cudaStream_t s,
+                          const int *d_cnt = nullptr, int stride = 0);
 
 // ---- pyramidal LK + undistort (kernels_track.cu) ----------------------------------------------------------
 struct LkParams {

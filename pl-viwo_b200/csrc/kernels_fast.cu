@@ -11,6 +11,7 @@
 // plane, and survivors are emitted with an ordered block-wide compaction.  Bands of a cell reserve their slice
 // of the compact output with one atomic; the host (or the selection kernel) walks bands in order.
 #include "fe_kernels.h"
+#include "introsort.h"
 
 namespace plviwo {
 
@@ -155,6 +156,67 @@ __global__ void __launch_bounds__(kFastThreads)
     }
   }
 }
+
+// ------------------------------------------------------------------------------------- per-cell selection
+// Grider_GRID.h:128-133: std::sort(cell corners, compare_response), keep the first num_features_grid.  One CTA per
+// cell: the cell's corners (band slices of the compact list, i.e. row-major order — the order cv::FAST emits them in)
+// are gathered into shared memory, ONE thread runs libstdc++'s introsort on them (introsort.h: the tie permutation is
+// part of the contract), and the survivors are written as full-image float coordinates to a fixed-stride table
+// (cell c at c * nfg).  Cells with more corners than fit in shared memory sort in a global scratch slice.
+constexpr int kSelThreads = 128;
+constexpr int kSelSmemCap = 8192;
+constexpr int kSelMaxBands = 256;   // 4095 rows / kFastBandRows
+
+__global__ void __launch_bounds__(kSelThreads)
+    k_fast_select(const FastCell *__restrict__ cells, int max_bands, unsigned *__restrict__ total /* [0] corners, [1] scratch cursor */,
+                  const int *__restrict__ band_off, const int *__restrict__ band_cnt, const unsigned *__restrict__ kps,
+                  int kps_cap, unsigned *__restrict__ scratch, int nfg, float2 *__restrict__ cand_sel,
+                  int *__restrict__ cand_cnt) {
+  __shared__ unsigned sv[kSelSmemCap];
+  __shared__ int pref[kSelMaxBands + 1];
+  __shared__ int s_base;
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const int tot = min((int)total[0], kps_cap);
+  if (tid == 0) {
+    int acc = 0;
+    for (int b = 0; b < max_bands; b++) {
+      pref[b] = acc;
+      const int off = band_off[c * max_bands + b];
+      acc += max(0, min(band_cnt[c * max_bands + b], tot - off));
+    }
+    pref[max_bands] = acc;
+    s_base = acc > kSelSmemCap ? (int)atomicAdd(total + 1, (unsigned)acc) : 0;
+  }
+  __syncthreads();
+  const int n = pref[max_bands];
+  unsigned *v = n > kSelSmemCap ? scratch + s_base : sv;
+  for (int b = 0; b < max_bands; b++) {
+    const int off = band_off[c * max_bands + b], cnt = pref[b + 1] - pref[b];
+    for (int k = tid; k < cnt; k += kSelThreads) v[pref[b] + k] = kps[off + k];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    isort::sort(v, n);
+    cand_cnt[c] = min(n, nfg);
+  }
+  __syncthreads();
+  const float x0 = (float)cells[c].x, y0 = (float)cells[c].y;
+  for (int i = tid; i < min(n, nfg); i += kSelThreads) {
+    const unsigned p = v[i];
+    cand_sel[c * nfg + i] = make_float2((float)(p & 0xfffu) + x0, (float)((p >> 12) & 0xfffu) + y0);
+  }
+}
+
+void launch_fast_select(const FastCell *d_cells, int n_cells, int max_bands, unsigned *d_total, const int *d_band_off,
+                        const int *d_band_cnt, const unsigned *d_kps, int kps_cap, unsigned *d_scratch, int nfg,
+                        float2 *d_cand_sel, int *d_cand_cnt, cudaStream_t s) {
+  if (n_cells <= 0 || max_bands > kSelMaxBands) return;
+  k_fast_select<<<n_cells, kSelThreads, 0, s>>>(d_cells, max_bands, d_total, d_band_off, d_band_cnt, d_kps, kps_cap, d_scratch,
+                                                nfg, d_cand_sel, d_cand_cnt);
+}
+
+// host instantiation of the same sort (tests: compared with the real std::sort and with the kernel)
+void host_sort_corners(unsigned *v, int n) { isort::sort(v, n); }
 
 void launch_fast(const DevImage &img, const FastCell *d_cells, int n_cells, int max_bands, int max_cell_w, int threshold,
                  unsigned *d_total, int *d_band_off, int *d_band_cnt, unsigned *d_kps, int kps_cap, cudaStream_t s) {

@@ -44,13 +44,18 @@ __constant__ float c_subpix_mask[kSpW * kSpW];
 static bool g_subpix_mask_ready[64] = {false};
 
 __global__ void __launch_bounds__(kSpWarps * 32)
-    k_corner_subpix(const uint8_t *__restrict__ img, int w, int h, int pitch, float2 *__restrict__ pts, int n) {
+    k_corner_subpix(const uint8_t *__restrict__ img, int w, int h, int pitch, const float2 *pts_in, float2 *pts, int n,
+                    const int *__restrict__ cnt, int stride) {
   __shared__ float patch_s[kSpWarps][kSpP * kSpP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pi = blockIdx.x * kSpWarps + warp;
   if (pi >= n) return;
+  if (cnt != nullptr) {   // fixed-stride candidate table: dead slots are skipped
+    const int cell = pi / stride;
+    if (pi - cell * stride >= cnt[cell]) return;
+  }
   float *patch = patch_s[warp];
-  const float2 cT = pts[pi];
+  const float2 cT = pts_in[pi];
   float2 cI = cT;
   const double eps = 0.001 * 0.001;
   int iter = 0;
@@ -100,11 +105,12 @@ __global__ void __launch_bounds__(kSpWarps * 32)
 
 void init_device_constants() {
   DevImage dummy;
-  launch_corner_subpix(dummy, nullptr, -1, 0);
+  launch_corner_subpix(dummy, nullptr, nullptr, -1, 0);
   init_fld_constants();
 }
 
-void launch_corner_subpix(const DevImage &img, float2 *d_pts, int n, cudaStream_t s) {
+void launch_corner_subpix(const DevImage &img, const float2 *d_in, float2 *d_out, int n, cudaStream_t s, const int *d_cnt,
+                          int stride) {
   if (n == 0) return;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -122,7 +128,8 @@ void launch_corner_subpix(const DevImage &img, float2 *d_pts, int n, cudaStream_
     g_subpix_mask_ready[dev & 63] = true;
   }
   if (n < 0) return;
-  k_corner_subpix<<<(n + kSpWarps - 1) / kSpWarps, kSpWarps * 32, 0, s>>>(img.p, img.w, img.h, img.pitch, d_pts, n);
+  k_corner_subpix<<<(n + kSpWarps - 1) / kSpWarps, kSpWarps * 32, 0, s>>>(img.p, img.w, img.h, img.pitch, d_in, d_out, n, d_cnt,
+                                                                          stride);
 }
 
 // ============================================================================================== undistort

@@ -83,3 +83,22 @@ def test_synth_sequence_is_deterministic(synth):
     assert a.frame(0).shape == (192, 320) and a.frame(0).dtype == np.uint8
     m = synth.SynthSequence(seed=5, width=320, height=192, n_frames=5, moving_mask=True).mask(2)
     assert m.max() == 255 and m.min() == 0
+
+
+def test_introsort_restatement_equals_std_sort(fe):
+    """pl-viwo_b200/csrc/introsort.h (the sort the selection kernel runs) against the real libstdc++ std::sort with the
+    reference's comparator (oracle shim), on tie-heavy inputs: the PERMUTATION must be identical, not just the keys."""
+    from oracle import cvops
+    rng = np.random.default_rng(5)
+    for trial in range(300):
+        n = int(rng.integers(0, 70)) if trial < 100 else int(rng.integers(70, 6000))
+        span = int(rng.integers(1, 4)) if trial % 3 == 0 else int(rng.integers(1, 80))
+        resp = rng.integers(20, 20 + span, n).astype(np.uint32)
+        if trial % 5 == 1:
+            resp = np.sort(resp)
+        if trial % 5 == 2:
+            resp = np.sort(resp)[::-1].copy()
+        packed = (resp << 24) | np.arange(n, dtype=np.uint32)      # low bits = original index
+        got = fe.op_sort_corners(packed, 9, device=-1)
+        perm = cvops.sort_perm(resp.astype(np.float32))
+        assert np.array_equal(got & 0xffffff, np.asarray(perm, np.uint32)), (trial, n, span)

@@ -117,3 +117,19 @@ def test_fld_vs_restatement(fe, synth):
         got = fe.op_fld(small)
         assert len(got) == len(ref), (len(got), len(ref))
         assert np.abs(got - ref).max() < 1e-3
+
+
+def test_select_kernel_equals_host_std_sort(fe):
+    """k_fast_select (device introsort + top num_features_grid) against the host std::sort restatement, including a cell
+    larger than the shared-memory capacity (global scratch path)."""
+    rng = np.random.default_rng(11)
+    for n, span in [(0, 5), (1, 5), (17, 1), (400, 30), (3000, 8), (8192, 3), (9000, 4), (20000, 40)]:
+        resp = rng.integers(21, 21 + span, n).astype(np.uint32)
+        x = rng.integers(0, 4000, n).astype(np.uint32)
+        y = rng.integers(0, 4000, n).astype(np.uint32)
+        packed = (resp << 24) | (y << 12) | x
+        for nfg in (9, 17):
+            ref = fe.op_sort_corners(packed, nfg, device=-1)[:nfg]
+            got = fe.op_sort_corners(packed, nfg, device=0)
+            exp = np.stack([(ref & 0xfff).astype(np.float32), ((ref >> 12) & 0xfff).astype(np.float32)], 1)
+            assert got.shape == exp.shape and np.array_equal(got, exp), (n, span, nfg)
