@@ -63,7 +63,7 @@ typedef struct FeConfig {
   int32_t min_px_dist;
   int32_t pyr_levels;           /* OpenCV maxLevel (reference: 5) => pyr_levels + 1 images              */
   int32_t win_size;             /* LK window (reference: 15); odd, <= 31                                */
-  int32_t histogram_method;     /* FeHistogramMethod; FE_HIST_CLAHE is not implemented (FE_BAD_ARG)     */
+  int32_t histogram_method;     /* FeHistogramMethod (CLAHE = cv::createCLAHE(10.0, 8x8), TrackKLT.cpp:60-64) */
   int32_t numaruco;             /* first point id = 4 * numaruco + 2 (TrackBase.cpp:34)                 */
   int32_t use_lines;            /* OptionsCamera.h:108                                                  */
   int32_t fld_length_threshold; /* 20                                                                   */
@@ -216,6 +216,7 @@ int plviwo_fe_get_stage_times(FeHandle *h, FeStageTimes *out, int reset);
 /* ---- stand-alone kernels (tests / micro-benchmarks; all pointers are HOST buffers) --------------------- */
 int plviwo_op_equalize_pyramid(int device, const uint8_t *img, int w, int h, int levels /* maxLevel */,
                                uint8_t *out_levels /* concatenated tight levels 0..maxLevel */, uint8_t *out_half);
+int plviwo_op_clahe(int device, const uint8_t *img, int w, int h, uint8_t *out /* w*h */);   /* createCLAHE(10, 8x8)->apply */
 int plviwo_op_fast_cell(int device, const uint8_t *img, int w, int h, int threshold, int32_t *xys /* x y score */,
                         int cap, int *n_out);
 /* std::sort(corners, compare_response) + first nfg (Grider_GRID.h:128-133) on packed corners x | y << 12 | score << 24.

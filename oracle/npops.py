@@ -38,6 +38,60 @@ def equalize_hist(img: np.ndarray) -> np.ndarray:
 
 
 # ---------------------------------------------------------------------------------------------- A2
+def clahe(img: np.ndarray, clip: float = 10.0, tiles=(8, 8)) -> np.ndarray:
+    """cv::createCLAHE(clip, tiles)->apply on 8UC1 (TrackKLT.cpp:60-64), following OpenCV's clahe.cpp: extend to a
+    multiple of the tile grid with BORDER_REFLECT_101 (both directions as soon as one is not divisible), per tile:
+    histogram, clip at int(clip * area / 256) (>= 1), spread the excess (remainder: one count every 256 // remainder
+    bins), LUT = cvRound(cumsum * (255 / area)) in float32; output = bilinear blend of the 4 nearest tile LUTs in float32,
+    (l11 * xa1 + l12 * xa) * ya1 + (l21 * xa1 + l22 * xa) * ya.  Bit-exact against cv2 4.13 (tests/test_oracle_pins.py)."""
+    H, W = img.shape
+    tx, ty = tiles
+    if W % tx == 0 and H % ty == 0:
+        ext = img
+    else:
+        eh, ew = H + (ty - H % ty), W + (tx - W % tx)
+        ext = img[np.ix_(_reflect101(np.arange(eh), H), _reflect101(np.arange(ew), W))]
+    tw, th = ext.shape[1] // tx, ext.shape[0] // ty
+    area = tw * th
+    lut_scale = f32(255) / f32(area)
+    cl = max(int(clip * area / 256), 1)
+    luts = np.zeros((ty, tx, 256), np.uint8)
+    for j in range(ty):
+        for i in range(tx):
+            hist = np.bincount(ext[j * th:(j + 1) * th, i * tw:(i + 1) * tw].ravel(), minlength=256).astype(np.int64)
+            clipped = int(np.maximum(hist - cl, 0).sum())
+            hist = np.minimum(hist, cl)
+            batch = clipped // 256
+            residual = clipped - batch * 256
+            hist += batch
+            if residual != 0:
+                step = max(256 // residual, 1)
+                k = 0
+                while k < 256 and residual > 0:
+                    hist[k] += 1
+                    k += step
+                    residual -= 1
+            luts[j, i] = np.clip(np.rint(np.cumsum(hist).astype(f32) * lut_scale), 0, 255).astype(np.uint8)
+    inv_tw, inv_th = f32(1.0) / f32(tw), f32(1.0) / f32(th)
+    xf = np.arange(W).astype(f32) * inv_tw - f32(0.5)
+    tx1 = np.floor(xf).astype(np.int32)
+    xa = (xf - tx1.astype(f32)).astype(f32)
+    xa1 = (f32(1) - xa).astype(f32)
+    tx2, tx1 = np.minimum(tx1 + 1, tx - 1), np.maximum(tx1, 0)
+    yf = np.arange(H).astype(f32) * inv_th - f32(0.5)
+    ty1 = np.floor(yf).astype(np.int32)
+    ya = (yf - ty1.astype(f32)).astype(f32)
+    ya1 = (f32(1) - ya).astype(f32)
+    ty2, ty1 = np.minimum(ty1 + 1, ty - 1), np.maximum(ty1, 0)
+    v = img.astype(np.int32)
+    l11, l12 = luts[ty1[:, None], tx1[None, :], v].astype(f32), luts[ty1[:, None], tx2[None, :], v].astype(f32)
+    l21, l22 = luts[ty2[:, None], tx1[None, :], v].astype(f32), luts[ty2[:, None], tx2[None, :], v].astype(f32)
+    top = ((l11 * xa1[None, :]).astype(f32) + (l12 * xa[None, :]).astype(f32)).astype(f32)
+    bot = ((l21 * xa1[None, :]).astype(f32) + (l22 * xa[None, :]).astype(f32)).astype(f32)
+    res = ((top * ya1[:, None]).astype(f32) + (bot * ya[:, None]).astype(f32)).astype(f32)
+    return np.clip(np.rint(res), 0, 255).astype(np.uint8)
+
+
 def pyr_down(img: np.ndarray) -> np.ndarray:
     """cv::pyrDown: separable [1 4 6 4 1], BORDER_REFLECT_101, (v + 128) >> 8, size ((w+1)/2, (h+1)/2)."""
     h, w = img.shape

@@ -91,7 +91,7 @@ EXPORTS = [
     "plviwo_fe_feed_device", "plviwo_fe_submit", "plviwo_fe_collect", "plviwo_fe_play", "plviwo_fe_get_point_rows", "plviwo_fe_get_last_obs",
     "plviwo_fe_get_line_rows", "plviwo_fe_get_line_points", "plviwo_fe_get_line_samples", "plviwo_fe_get_state",
     "plviwo_fe_set_state", "plviwo_fe_enable_taps", "plviwo_fe_tap", "plviwo_fe_enable_timing", "plviwo_fe_get_stage_times",
-    "plviwo_op_equalize_pyramid", "plviwo_op_fast_cell", "plviwo_op_sort_corners", "plviwo_op_corner_subpix", "plviwo_op_lk", "plviwo_op_undistort",
+    "plviwo_op_equalize_pyramid", "plviwo_op_clahe", "plviwo_op_fast_cell", "plviwo_op_sort_corners", "plviwo_op_corner_subpix", "plviwo_op_lk", "plviwo_op_undistort",
     "plviwo_op_canny_half", "plviwo_op_fld", "plviwo_op_ransac_fundamental",
 ]
 
@@ -133,6 +133,7 @@ def lib() -> C.CDLL:
         L.plviwo_fe_default_config.restype = None
         L.plviwo_fe_device_count.argtypes = [C.POINTER(C.c_int)]
         L.plviwo_op_equalize_pyramid.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.plviwo_op_clahe.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.plviwo_op_fast_cell.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.plviwo_op_corner_subpix.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.plviwo_op_sort_corners.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
@@ -515,6 +516,13 @@ def op_equalize_pyramid(img: np.ndarray, levels: int, device: int = 0):
         lv.append(out[o:o + lw * lh].reshape(lh, lw))
         o += lw * lh
     return lv, half
+
+
+def op_clahe(img: np.ndarray, device: int = 0) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    _check(lib().plviwo_op_clahe(device, img.ctypes.data, img.shape[1], img.shape[0], out.ctypes.data))
+    return out
 
 
 def op_fast_cell(img: np.ndarray, threshold: int, device: int = 0) -> np.ndarray:

@@ -90,8 +90,8 @@ int plviwo_fe_create(const FeConfig *cfg, int device, FeHandle **out) {
   if (cfg->win_size < 3 || cfg->win_size > kMaxWin || (cfg->win_size & 1) == 0) return bad("win_size must be odd and in [3, 31]");
   if (cfg->pyr_levels < 0 || cfg->pyr_levels >= kMaxLevels) return bad("pyr_levels must be in [0, 7]");
   if (cfg->grid_x < 1 || cfg->grid_y < 1 || cfg->min_px_dist < 1 || cfg->num_features < 1) return bad("bad grid / distance / feature count");
-  if (cfg->histogram_method == FE_HIST_CLAHE) return bad("FE_HIST_CLAHE is not implemented");
-  if (cfg->histogram_method != FE_HIST_NONE && cfg->histogram_method != FE_HIST_HISTOGRAM) return bad("bad histogram_method");
+  if (cfg->histogram_method != FE_HIST_NONE && cfg->histogram_method != FE_HIST_HISTOGRAM && cfg->histogram_method != FE_HIST_CLAHE)
+    return bad("bad histogram_method");
   if (cfg->use_lines) {
     if ((cfg->width & 1) || (cfg->height & 1)) return bad("line tracker needs even image dimensions (exact 2x decimation)");
     if (cfg->canny_th1 != cfg->canny_th2) return bad("canny_th1 != canny_th2: hysteresis pass is not implemented");
@@ -333,6 +333,23 @@ int build_pyramid(const uint8_t *img, int w, int h, int levels, int win, int equ
 }
 }  // namespace
 extern "C" {
+
+int plviwo_op_clahe(int device, const uint8_t *img, int w, int h, uint8_t *out) {
+  API_BEGIN
+  if (!img || !out || w < 8 || h < 8) return FE_BAD_ARG;
+  OP_CUDA(cudaSetDevice(device));
+  TmpImage raw, l0;
+  DevBuf<uint8_t> luts;
+  DevBuf<unsigned> hist, counters;
+  if (raw.alloc(w, h) || raw.upload(img) || l0.alloc(w, h) || luts.alloc(64 * 256) || hist.alloc(256) || counters.alloc(4))
+    return FE_CUDA_ERROR;
+  launch_clahe_lut(raw.im, luts.p, 0);
+  launch_eq_pyr1(raw.im, hist.p, counters.p, 2, l0.im, DevImage(), DevImage(), 0, luts.p);
+  OP_CUDA(cudaDeviceSynchronize());
+  OP_CUDA(cudaMemcpy2D(out, w, l0.im.p, l0.im.pitch, w, h, cudaMemcpyDeviceToHost));
+  return FE_OK;
+  API_END
+}
 
 int plviwo_op_equalize_pyramid(int device, const uint8_t *img, int w, int h, int levels, uint8_t *out_levels, uint8_t *out_half) {
   API_BEGIN

@@ -164,6 +164,7 @@ int FeContext::init() {
     FE_CUDA(cudaStreamCreateWithPriority(&s.s_b, cudaStreamNonBlocking, lo));
     FE_CUDA(cudaMalloc(&s.d_hist, 256 * sizeof(unsigned)));
     FE_CUDA(cudaMemset(s.d_hist, 0, 256 * sizeof(unsigned)));
+    FE_CUDA(cudaMalloc(&s.d_clahe, 64 * 256));
     FE_CUDA(cudaMalloc(&s.d_counters, 4 * sizeof(unsigned)));
     FE_CUDA(cudaMemset(s.d_counters, 0, 4 * sizeof(unsigned)));
     FE_CUDA(cudaMalloc(&s.d_seq, 4 * sizeof(int)));
@@ -247,7 +248,7 @@ FeContext::~FeContext() {
     for (auto &e : s.ev_fast_t) if (e) cudaEventDestroy(e);
     for (auto &e : s.ev_sp_t) if (e) cudaEventDestroy(e);
     destroy_graphs(s);
-    cudaFree(s.d_hist); cudaFree(s.d_counters); cudaFree(s.d_seq);
+    cudaFree(s.d_hist); cudaFree(s.d_counters); cudaFree(s.d_seq); cudaFree(s.d_clahe);
     if (s.s_a) cudaStreamDestroy(s.s_a);
     if (s.s_b) cudaStreamDestroy(s.s_b);
     if (s.s_line) cudaStreamDestroy(s.s_line);
@@ -352,11 +353,12 @@ void FeContext::undistort_host(const double K[4], const double D[4], float u, fl
 // exactly these calls: ~30 launches per frame collapse into three graph launches.  Stage-timing events are part of
 // the paths, so timings can be read whether or not the graphs are used.
 int FeContext::record_image_path(FrameSlot &s, cudaStream_t st) {
-  const int eq = cfg_.histogram_method == FE_HIST_HISTOGRAM ? 1 : 0;
-  if (eq) launch_hist(s.raw, s.d_hist, st);
+  const int eq = cfg_.histogram_method == FE_HIST_HISTOGRAM ? 1 : (cfg_.histogram_method == FE_HIST_CLAHE ? 2 : 0);
+  if (eq == 1) launch_hist(s.raw, s.d_hist, st);
+  if (eq == 2) launch_clahe_lut(s.raw, s.d_clahe, st);
   if (timing) cudaEventRecord(s.ev_t[2], st);
   DevImage half = cfg_.use_lines ? s.half : DevImage();
-  launch_eq_pyr1(s.raw, s.d_hist, s.d_counters, eq, s.pyr.lvl[0], s.pyr.n > 1 ? s.pyr.lvl[1] : DevImage(), half, st);
+  launch_eq_pyr1(s.raw, s.d_hist, s.d_counters, eq, s.pyr.lvl[0], s.pyr.n > 1 ? s.pyr.lvl[1] : DevImage(), half, st, s.d_clahe);
   if (timing) cudaEventRecord(s.ev_t[3], st);
   if (s.pyr.n > 2) launch_pyr_rest(s.pyr, s.d_counters + 1, st);
   if (timing) cudaEventRecord(s.ev_t[4], st);
@@ -486,7 +488,7 @@ int FeContext::enqueue_frame_independent(FrameSlot &s) {
   s.warmed = true;
   // bookkeeping (identical for both ways of issuing the work)
   const int ncell = (int)cells_.size(), ntab = ncell * cells_nb_;
-  mst_.kernel_launches_total += (cfg_.histogram_method == FE_HIST_HISTOGRAM ? 1 : 0) + 1 + std::max(s.pyr.n - 2, 0) +
+  mst_.kernel_launches_total += (cfg_.histogram_method != FE_HIST_NONE ? 1 : 0) + 1 + std::max(s.pyr.n - 2, 0) +
                                  (ncell > 0 ? 3 : 0) + 1 + (lines ? 11 : 0);
   (void)ntab;
   if (ncell > 0) mst_.d2h_bytes += (size_t)ncell * sizeof(int) + (size_t)2 * ncell * cells_nfg_ * sizeof(float2);
@@ -744,7 +746,7 @@ int FeContext::collect_impl(FeFrameInfo *info) {
       acc_time(mst_, FE_STAGE_FAST, cur.ev_fast_t[0], cur.ev_fast_t[1]);
       acc_time(mst_, FE_STAGE_SUBPIX, cur.ev_sp_t[0], cur.ev_sp_t[1]);
     }
-    if (cfg_.histogram_method == FE_HIST_HISTOGRAM) acc_time(mst_, FE_STAGE_HIST, cur.ev_t[1], cur.ev_t[2]);
+    if (cfg_.histogram_method != FE_HIST_NONE) acc_time(mst_, FE_STAGE_HIST, cur.ev_t[1], cur.ev_t[2]);
     acc_time(mst_, FE_STAGE_EQ_PYR, cur.ev_t[2], cur.ev_t[3]);
     acc_time(mst_, FE_STAGE_PYR_REST, cur.ev_t[3], cur.ev_t[4]);
     if (cfg_.use_lines && cur.has_vp) {

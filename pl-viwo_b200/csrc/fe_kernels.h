@@ -24,8 +24,11 @@ struct Pyramid {
 void launch_hist(const DevImage &src, unsigned *d_hist, cudaStream_t s);
 // LUT from hist (cv::equalizeHist), level 0 = lut[src] (or a plain copy when equalize == 0), level 1 = pyrDown,
 // half = exact 2x2 INTER_AREA of level 0 (may be null).  d_hist is cleared for the next frame by the last CTA.
+// equalize: 0 copy, 1 cv::equalizeHist LUT from d_hist, 2 CLAHE blend of the 64 tile LUTs in d_clahe_luts.
 void launch_eq_pyr1(const DevImage &src, unsigned *d_hist, unsigned *d_counter, int equalize, const DevImage &l0,
-                    const DevImage &l1, const DevImage &half, cudaStream_t s);
+                    const DevImage &l1, const DevImage &half, cudaStream_t s, const uint8_t *d_clahe_luts = nullptr);
+// cv::createCLAHE(10.0, 8x8): the 64 tile LUTs (64 * 256 bytes) of the frame
+void launch_clahe_lut(const DevImage &src, uint8_t *d_luts, cudaStream_t s);
 // levels 2..n-1, one short launch per level (4 outputs per thread).
 void launch_pyr_rest(const Pyramid &pyr, unsigned *d_counter, cudaStream_t s);
 

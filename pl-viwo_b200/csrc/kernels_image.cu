@@ -68,6 +68,109 @@ void launch_hist(const DevImage &src, unsigned *d_hist, cudaStream_t s) {
   k_hist<<<grid, kHistThreads, 0, s>>>(src.p, src.w, src.h, src.pitch, d_hist);
 }
 
+// ------------------------------------------------------------------------------------------------ CLAHE
+// cv::createCLAHE(10.0, Size(8, 8))->apply (TrackKLT.cpp:60-64, TrackLSD.cpp:84-88).  Arithmetic of OpenCV's clahe.cpp:
+// the frame is extended to a multiple of the tile grid with BORDER_REFLECT_101 (both directions, even when only one is
+// not divisible), per tile a 256-bin histogram is clipped at clipLimit * area / 256 (>= 1), the excess is spread evenly
+// (the remainder one count every 256 / remainder bins), the LUT is cvRound(cumsum * (255 / area)) in float32; the output
+// pixel blends the LUTs of the 4 nearest tile centres bilinearly, float32, in the order
+// (l11 * xa1 + l12 * xa) * ya1 + (l21 * xa1 + l22 * xa) * ya.  The blend is part of k_eq_pyr1's staging; this kernel
+// builds the tile LUTs: one CTA per tile.
+struct ClaheGeom {
+  int tiles_x, tiles_y, tile_w, tile_h, clip;
+  float lut_scale, inv_tw, inv_th;
+};
+
+__global__ void __launch_bounds__(256)
+    k_clahe_lut(const uint8_t *__restrict__ src, int w, int h, int pitch, ClaheGeom g, uint8_t *__restrict__ luts) {
+  __shared__ unsigned sh[8][256];
+  __shared__ unsigned warp_tot[8];
+  __shared__ unsigned s_clipped;
+  const int tid = threadIdx.x;
+  const int tx = blockIdx.x % g.tiles_x, ty = blockIdx.x / g.tiles_x;
+  for (int i = tid; i < 8 * 256; i += 256) (&sh[0][0])[i] = 0;
+  if (tid == 0) s_clipped = 0;
+  __syncthreads();
+  unsigned *my = sh[tid >> 5];
+  const int x0 = tx * g.tile_w, y0 = ty * g.tile_h;
+  for (int i = tid; i < g.tile_w * g.tile_h; i += 256) {
+    const int r = i / g.tile_w, c = i - r * g.tile_w;
+    const int sx = reflect101(x0 + c, w), sy = reflect101(y0 + r, h);
+    atomicAdd(&my[src[(size_t)sy * pitch + sx]], 1u);
+  }
+  __syncthreads();
+  unsigned hv = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) hv += sh[k][tid];
+  // clip and redistribute
+  const unsigned clip = (unsigned)g.clip;
+  if (hv > clip) {
+    atomicAdd(&s_clipped, hv - clip);
+    hv = clip;
+  }
+  __syncthreads();
+  const unsigned clipped = s_clipped;
+  const unsigned batch = clipped / 256u, residual = clipped - batch * 256u;
+  hv += batch;
+  if (residual != 0) {
+    const unsigned step = max(256u / residual, 1u);
+    if ((unsigned)tid % step == 0 && (unsigned)tid / step < residual) hv += 1;
+  }
+  // inclusive scan over the 256 bins
+  unsigned v = hv;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    unsigned t = __shfl_up_sync(0xffffffffu, v, d);
+    if ((tid & 31) >= d) v += t;
+  }
+  if ((tid & 31) == 31) warp_tot[tid >> 5] = v;
+  __syncthreads();
+  unsigned base = 0;
+  for (int k = 0; k < (tid >> 5); k++) base += warp_tot[k];
+  const int r = __float2int_rn(__fmul_rn((float)(int)(v + base), g.lut_scale));
+  luts[(size_t)blockIdx.x * 256 + tid] = (uint8_t)min(max(r, 0), 255);
+}
+
+__device__ __forceinline__ unsigned clahe_px(const uint8_t *__restrict__ luts, const ClaheGeom &g, int x, int y, int v) {
+  const float txf = __fsub_rn(__fmul_rn((float)x, g.inv_tw), 0.5f), tyf = __fsub_rn(__fmul_rn((float)y, g.inv_th), 0.5f);
+  int tx1 = __float2int_rd(txf), ty1 = __float2int_rd(tyf);
+  const float xa = __fsub_rn(txf, (float)tx1), ya = __fsub_rn(tyf, (float)ty1);
+  const float xa1 = __fsub_rn(1.f, xa), ya1 = __fsub_rn(1.f, ya);
+  const int tx2 = min(tx1 + 1, g.tiles_x - 1), ty2 = min(ty1 + 1, g.tiles_y - 1);
+  tx1 = max(tx1, 0);
+  ty1 = max(ty1, 0);
+  const float l11 = (float)__ldg(luts + ((ty1 * g.tiles_x + tx1) << 8) + v), l12 = (float)__ldg(luts + ((ty1 * g.tiles_x + tx2) << 8) + v);
+  const float l21 = (float)__ldg(luts + ((ty2 * g.tiles_x + tx1) << 8) + v), l22 = (float)__ldg(luts + ((ty2 * g.tiles_x + tx2) << 8) + v);
+  const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa)), bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+  const int r = __float2int_rn(__fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya)));
+  return (unsigned)min(max(r, 0), 255);
+}
+
+static ClaheGeom clahe_geom(int w, int h) {
+  ClaheGeom g;
+  g.tiles_x = 8;
+  g.tiles_y = 8;
+  int ew = w, eh = h;
+  if (w % 8 != 0 || h % 8 != 0) {
+    ew = w + (8 - w % 8);
+    eh = h + (8 - h % 8);
+  }
+  g.tile_w = ew / 8;
+  g.tile_h = eh / 8;
+  const int area = g.tile_w * g.tile_h;
+  g.lut_scale = 255.f / (float)area;
+  g.clip = (int)(10.0 * area / 256);
+  if (g.clip < 1) g.clip = 1;
+  g.inv_tw = 1.0f / (float)g.tile_w;
+  g.inv_th = 1.0f / (float)g.tile_h;
+  return g;
+}
+
+void launch_clahe_lut(const DevImage &src, uint8_t *d_luts, cudaStream_t s) {
+  const ClaheGeom g = clahe_geom(src.w, src.h);
+  k_clahe_lut<<<64, 256, 0, s>>>(src.p, src.w, src.h, src.pitch, g, d_luts);
+}
+
 // ------------------------------------------------------------------------- equalise + level 0/1 + half-res
 // One CTA produces a 64 x 16 tile of level 1, i.e. consumes a (128 + 4) x (32 + 4) window of the raw frame
 // (5-tap [1 4 6 4 1] pyrDown halo of 2), staged in shared memory AFTER the LUT so level 0, level 1 and the
@@ -80,7 +183,8 @@ constexpr int kEqThreads = 256;
 
 __global__ void __launch_bounds__(kEqThreads)
     k_eq_pyr1(const uint8_t *__restrict__ src, int w, int h, int spitch, unsigned *__restrict__ hist,
-              unsigned *__restrict__ counter, int equalize, uint8_t *__restrict__ l0, int l0pitch,
+              unsigned *__restrict__ counter, int equalize, const uint8_t *__restrict__ clahe_luts, ClaheGeom cg,
+              uint8_t *__restrict__ l0, int l0pitch,
               uint8_t *__restrict__ l1, int w1, int h1, int l1pitch, uint8_t *__restrict__ half, int wh, int hh,
               int hpitch) {
   __shared__ __align__(16) uint8_t tile[kTileRows][kTileCols];
@@ -93,7 +197,7 @@ __global__ void __launch_bounds__(kEqThreads)
 
   const int tid = threadIdx.x;
   // ---- LUT (cv::equalizeHist, Appendix A1): every CTA rebuilds it from the 1 KB histogram
-  if (equalize) {
+  if (equalize == 1) {
     if (tid == 0) s_i0 = 256;
     __syncthreads();
     unsigned hv = hist[tid];
@@ -143,7 +247,16 @@ __global__ void __launch_bounds__(kEqThreads)
     if (gy > -h && gy < 2 * h - 1) {
       int ry = reflect101(gy, h);
       const uint8_t *row = src + (size_t)ry * spitch;
-      if (gx >= 0 && gx + 4 <= w) {
+      if (equalize == 2) {   // CLAHE: the mapping depends on the pixel position (the REFLECTED one in the halo)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          int x = gx + k;
+          if (x > -w && x < 2 * w - 1) {
+            const int rx = reflect101(x, w);
+            out |= clahe_px(clahe_luts, cg, rx, ry, row[rx]) << (8 * k);
+          }
+        }
+      } else if (gx >= 0 && gx + 4 <= w) {
         unsigned v = *reinterpret_cast<const unsigned *>(row + gx);
         out = (unsigned)lut[v & 0xff] | ((unsigned)lut[(v >> 8) & 0xff] << 8) | ((unsigned)lut[(v >> 16) & 0xff] << 16) |
               ((unsigned)lut[v >> 24] << 24);
@@ -219,7 +332,7 @@ __global__ void __launch_bounds__(kEqThreads)
   }
 
   // ---- the last CTA to finish clears the histogram for the next frame
-  if (equalize) {
+  if (equalize == 1) {
     __syncthreads();
     if (tid == 0) {
       __threadfence();
@@ -234,11 +347,12 @@ __global__ void __launch_bounds__(kEqThreads)
 }
 
 void launch_eq_pyr1(const DevImage &src, unsigned *d_hist, unsigned *d_counter, int equalize, const DevImage &l0,
-                    const DevImage &l1, const DevImage &half, cudaStream_t s) {
+                    const DevImage &l1, const DevImage &half, cudaStream_t s, const uint8_t *d_clahe_luts) {
   // tiles are laid over the level-1 footprint of the frame even when level 1 itself is not wanted (l1.p == null)
   const int w1 = (src.w + 1) / 2, h1 = (src.h + 1) / 2;
   dim3 grid((w1 + kT1W - 1) / kT1W, (h1 + kT1H - 1) / kT1H);
-  k_eq_pyr1<<<grid, kEqThreads, 0, s>>>(src.p, src.w, src.h, src.pitch, d_hist, d_counter, equalize, l0.p, l0.pitch, l1.p,
+  k_eq_pyr1<<<grid, kEqThreads, 0, s>>>(src.p, src.w, src.h, src.pitch, d_hist, d_counter, equalize, d_clahe_luts,
+                                        clahe_geom(src.w, src.h), l0.p, l0.pitch, l1.p,
                                         l1.p ? l1.w : 0, l1.p ? l1.h : 0, l1.pitch, half.p, half.w, half.h, half.pitch);
 }
 

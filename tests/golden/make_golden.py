@@ -21,6 +21,7 @@ def main():
     out = {"cv2_version": np.array(cv2.__version__), "img_a": a, "img_b": b}
     eq_a, eq_b = cvops.equalize_hist(a), cvops.equalize_hist(b)
     out["eq_a"] = eq_a
+    out["clahe_a"] = cvops.clahe(a)
     pyr = cvops.build_pyramid(eq_a, 15, 3)
     for l, p in enumerate(pyr):
         out["pyr_a_%d" % l] = p

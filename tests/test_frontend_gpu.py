@@ -200,6 +200,11 @@ def test_teacher_forced_moving_mask(fe, synth):
     _assert_teacher_forced(_run(fe, synth, 25, dict(CFG1, grid_y=3, pyr_levels=5), seed=1002, moving_mask=True))
 
 
+def test_teacher_forced_clahe(fe, synth):
+    """histogram_method = CLAHE (TrackKLT.cpp:60-64, TrackLSD.cpp:84-88): third pre-processing mode of the reference."""
+    _assert_teacher_forced(_run(fe, synth, 8, dict(CFG1, histogram_method=2), seed=1007))
+
+
 def test_teacher_forced_no_equalisation(fe, synth):
     _assert_teacher_forced(_run(fe, synth, 8, dict(CFG1, histogram_method=0), seed=1006))
 
@@ -310,7 +315,7 @@ def test_bad_arguments(fe):
     with pytest.raises(fe.FrontEndError):
         fe.FrontEnd(fe.default_config(win_size=14))
     with pytest.raises(fe.FrontEndError):
-        fe.FrontEnd(fe.default_config(histogram_method=2))
+        fe.FrontEnd(fe.default_config(histogram_method=7))
     h = fe.FrontEnd(fe.default_config())
     with pytest.raises(fe.FrontEndError):
         h.feed_new_camera(0.0, np.zeros((100, 100), np.uint8))   # size mismatch: the reference exit()s here

@@ -133,3 +133,17 @@ def test_select_kernel_equals_host_std_sort(fe):
             got = fe.op_sort_corners(packed, nfg, device=0)
             exp = np.stack([(ref & 0xfff).astype(np.float32), ((ref >> 12) & 0xfff).astype(np.float32)], 1)
             assert got.shape == exp.shape and np.array_equal(got, exp), (n, span, nfg)
+
+
+@pytest.mark.parametrize("shape", [(560, 1280), (283, 645), (280, 645), (283, 640), (64, 64), (1080, 1920)])
+def test_clahe_bit_exact(fe, synth, shape):
+    """k_clahe_lut + the CLAHE blend in k_eq_pyr1 against cv::createCLAHE(10.0, 8x8)->apply (TrackKLT.cpp:60-64)."""
+    from oracle import cvops
+    rng = np.random.default_rng(shape[0] + shape[1])
+    if shape == (560, 1280):
+        img = synth.SynthSequence(seed=5, n_frames=1).frame(0)
+    elif shape == (64, 64):
+        img = np.full(shape, 9, np.uint8)
+    else:
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+    assert np.array_equal(fe.op_clahe(img), cvops.clahe(img))

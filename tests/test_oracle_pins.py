@@ -24,6 +24,17 @@ def test_equalize_hist_bit_exact():
     assert np.array_equal(npops.equalize_hist(GOLD["img_a"]), GOLD["eq_a"])
 
 
+def test_clahe_bit_exact():
+    """NumPy restatement of cv::createCLAHE(10, 8x8) against the real one, incl. sizes that need the reflect extension."""
+    rng = np.random.default_rng(2)
+    imgs = [rng.integers(0, 256, (70, 160), dtype=np.uint8), rng.integers(90, 140, (283, 645), dtype=np.uint8),
+            rng.integers(0, 256, (283, 640), dtype=np.uint8), np.full((64, 64), 7, np.uint8),
+            (np.add.outer(np.arange(120), np.arange(200)) % 256).astype(np.uint8)]
+    for im in imgs:
+        assert np.array_equal(npops.clahe(im), cvops.clahe(im)), im.shape
+    assert np.array_equal(npops.clahe(GOLD["img_a"]), GOLD["clahe_a"])
+
+
 def test_pyramid_and_half_bit_exact():
     for img in _imgs()[:3]:
         a, b = npops.build_pyramid(img, 3, 4), cvops.build_pyramid(img, 3, 4)
