@@ -73,6 +73,9 @@ typedef struct FeConfig {
   int32_t line_samples;         /* extension (not in the reference): LK over this many points sampled   */
                                 /* along each of last frame's segments; 0 = off                         */
   int32_t lookahead;            /* frames that plviwo_fe_submit may run ahead of plviwo_fe_collect      */
+  int32_t downsample;           /* UpdaterCamera::feed_measurement's pre-step (UpdaterCamera.cpp:86-95): cv::pyrDown of */
+                                /* image and mask to (width/2, height/2) before tracking; width/height above are the    */
+                                /* INPUT size, K is the (already halved, OptionsCamera.cpp:123-126) tracking calibration */
   double K[4];                  /* fx fy cx cy                                                          */
   double D[4];                  /* radtan k1 k2 p1 p2                                                   */
 } FeConfig;

@@ -49,6 +49,11 @@ def clahe(img: np.ndarray) -> np.ndarray:
     return cv2.createCLAHE(10.0, (8, 8)).apply(img)
 
 
+def downsample(img: np.ndarray) -> np.ndarray:
+    """cv::pyrDown(img, out, Size(cols / 2.0, rows / 2.0)) — UpdaterCamera.cpp:90-93 (image and mask)."""
+    return cv2.pyrDown(img, dstsize=(int(img.shape[1] / 2.0), int(img.shape[0] / 2.0)))
+
+
 def build_pyramid(img: np.ndarray, win: int, max_level: int):
     """cv::buildOpticalFlowPyramid(img, pyr, win, maxLevel) — TrackKLT.cpp:71.  Returns the image levels only
     (derivative planes are an implementation artefact of OpenCV's LK)."""

@@ -55,6 +55,8 @@ class FeConfig:
     line_min_length: float = 40.0      # TrackLSD.cpp:231
     # extension (BASELINE.json config 3; NOT in the reference): LK over points sampled along last frame's segments
     line_samples: int = 0
+    # UpdaterCamera::feed_measurement's pre-step (UpdaterCamera.cpp:86-95, options/OptionsCamera.h:74)
+    downsample: bool = False
 
 
 @dataclass
@@ -538,6 +540,8 @@ class FrontEnd:
     def feed(self, timestamp, img, mask=None, vps=None):
         if mask is None:
             mask = np.zeros_like(img)
+        if self.cfg.downsample:          # UpdaterCamera.cpp:86-95
+            img, mask = self.klt.ops.downsample(img), self.klt.ops.downsample(mask)
         prows = self.klt.feed_new_camera(timestamp, img, mask)
         lrows = []
         if self.lsd is not None:

@@ -105,6 +105,13 @@ def pyr_down(img: np.ndarray) -> np.ndarray:
     return ((ver + 128) >> 8).astype(np.uint8)
 
 
+def downsample(img: np.ndarray) -> np.ndarray:
+    """cv::pyrDown(img, out, Size(cols / 2.0, rows / 2.0)) — UpdaterCamera.cpp:90-93: the same filter, but the output size
+    is the TRUNCATED half (an odd side loses its last sample compared with the default (n + 1) / 2)."""
+    h, w = img.shape
+    return pyr_down(img)[:int(h / 2.0), :int(w / 2.0)].copy()
+
+
 def build_pyramid(img: np.ndarray, win: int, max_level: int):
     """cv::buildOpticalFlowPyramid image levels: stops when the next level is <= win in either dimension."""
     pyr = [img]

@@ -41,7 +41,7 @@ class FeConfig(C.Structure):
         ("grid_x", C.c_int32), ("grid_y", C.c_int32), ("min_px_dist", C.c_int32), ("pyr_levels", C.c_int32),
         ("win_size", C.c_int32), ("histogram_method", C.c_int32), ("numaruco", C.c_int32), ("use_lines", C.c_int32),
         ("fld_length_threshold", C.c_int32), ("fld_distance_threshold", C.c_float), ("canny_th1", C.c_float),
-        ("canny_th2", C.c_float), ("line_min_length", C.c_float), ("line_samples", C.c_int32), ("lookahead", C.c_int32),
+        ("canny_th2", C.c_float), ("line_min_length", C.c_float), ("line_samples", C.c_int32), ("lookahead", C.c_int32), ("downsample", C.c_int32),
         ("K", C.c_double * 4), ("D", C.c_double * 4),
     ]
 
@@ -184,6 +184,7 @@ class Feature:
         self.uvs: List[Tuple[float, float]] = []
         self.uvs_norm: List[Tuple[float, float]] = []
         self.timestamps: List[float] = []
+        self.chi_test = True     # PL-VIWO's extra flag on ov_core::Feature (Chi_test)
 
 
 class FeatureDatabase:
@@ -202,6 +203,31 @@ class FeatureDatabase:
 
     def get_internal_data(self):
         return self.features_idlookup
+
+    def append_new_measurements(self, database: "FeatureDatabase"):
+        """FeatureDatabase::append_new_measurements (feat/FeatureDatabase.cpp:338-387): what UpdaterCamera does with the
+        tracker's database right after both trackers ran (UpdaterCamera.cpp:111) — copy the measurements this database
+        has not seen yet (matched by timestamp), create unknown features, propagate a failed chi-square flag."""
+        for fid, feat in database.get_internal_data().items():
+            mine = self.features_idlookup.get(fid)
+            if mine is not None:
+                if not feat.chi_test:
+                    mine.chi_test = False
+                    continue
+                if not mine.timestamps:
+                    mine.timestamps, mine.uvs, mine.uvs_norm = list(feat.timestamps), list(feat.uvs), list(feat.uvs_norm)
+                else:
+                    seen = list(mine.timestamps)      # the reference searches a COPY taken before appending
+                    for i, t in enumerate(feat.timestamps):
+                        if t not in seen:
+                            mine.timestamps.append(t)
+                            mine.uvs.append(feat.uvs[i])
+                            mine.uvs_norm.append(feat.uvs_norm[i])
+            else:
+                new = Feature(feat.featid)
+                new.timestamps, new.uvs, new.uvs_norm = list(feat.timestamps), list(feat.uvs), list(feat.uvs_norm)
+                new.chi_test = bool(feat.chi_test)
+                self.features_idlookup[fid] = new
 
 
 class LineFeature:

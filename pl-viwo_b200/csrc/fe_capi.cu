@@ -92,8 +92,10 @@ int plviwo_fe_create(const FeConfig *cfg, int device, FeHandle **out) {
   if (cfg->grid_x < 1 || cfg->grid_y < 1 || cfg->min_px_dist < 1 || cfg->num_features < 1) return bad("bad grid / distance / feature count");
   if (cfg->histogram_method != FE_HIST_NONE && cfg->histogram_method != FE_HIST_HISTOGRAM && cfg->histogram_method != FE_HIST_CLAHE)
     return bad("bad histogram_method");
+  const int tw = cfg->downsample ? (int)(cfg->width / 2.0) : cfg->width, th = cfg->downsample ? (int)(cfg->height / 2.0) : cfg->height;
+  if (cfg->downsample && (tw < 64 || th < 64)) return bad("downsampled image would be smaller than 64 pixels");
   if (cfg->use_lines) {
-    if ((cfg->width & 1) || (cfg->height & 1)) return bad("line tracker needs even image dimensions (exact 2x decimation)");
+    if ((tw & 1) || (th & 1)) return bad("line tracker needs even (tracking) image dimensions (exact 2x decimation)");
     if (cfg->canny_th1 != cfg->canny_th2) return bad("canny_th1 != canny_th2: hysteresis pass is not implemented");
     if (cfg->fld_length_threshold < 2) return bad("bad fld_length_threshold");
   }

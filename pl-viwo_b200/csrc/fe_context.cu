@@ -84,7 +84,12 @@ void WorkQueue::stop() {
   cv_.notify_all();
 }
 
-FeContext::FeContext(const FeConfig &cfg, int device) : cfg_(cfg), device_(device), W_(cfg.width), H_(cfg.height) {
+FeContext::FeContext(const FeConfig &cfg, int device)
+    : cfg_(cfg), device_(device), W_(cfg.width), H_(cfg.height), Win_(cfg.width), Hin_(cfg.height) {
+  if (cfg.downsample) {   // cv::Size(img.cols / 2.0, img.rows / 2.0): truncation (UpdaterCamera.cpp:91)
+    W_ = (int)(cfg.width / 2.0);
+    H_ = (int)(cfg.height / 2.0);
+  }
   currid_ = 4 * (uint64_t)cfg.numaruco + 1;  // TrackBase.cpp:34
   line_currid_ = 1;                          // TrackLSD.cpp:32
 }
@@ -139,6 +144,10 @@ int FeContext::init() {
   for (FrameSlot &s : slots_) {
     int rc = alloc_image(s.raw, W_, H_);
     if (rc) return rc;
+    if (cfg_.downsample) {
+      rc = alloc_image(s.raw_in, Win_, Hin_);
+      if (rc) return rc;
+    }
     // cv::buildOpticalFlowPyramid: a level is kept while both sides stay > winSize
     int w = W_, h = H_;
     s.pyr.n = 0;
@@ -158,7 +167,7 @@ int FeContext::init() {
       FE_CUDA(cudaMallocHost(&s.h_segs, (size_t)fb.out_cap * sizeof(float4)));
       FE_CUDA(cudaMallocHost(&s.h_fld_counts, 2 * sizeof(int)));
     }
-    FE_CUDA(cudaMallocHost(&s.h_raw, (size_t)W_ * H_));
+    FE_CUDA(cudaMallocHost(&s.h_raw, (size_t)Win_ * Hin_));
     FE_CUDA(cudaStreamCreateWithPriority(&s.s_line, cudaStreamNonBlocking, lo));
     FE_CUDA(cudaStreamCreateWithPriority(&s.s_a, cudaStreamNonBlocking, lo));
     FE_CUDA(cudaStreamCreateWithPriority(&s.s_b, cudaStreamNonBlocking, lo));
@@ -235,6 +244,7 @@ FeContext::~FeContext() {
   cudaDeviceSynchronize();
   for (FrameSlot &s : slots_) {
     cudaFree(s.raw.p);
+    cudaFree(s.raw_in.p);
     for (int l = 0; l < s.pyr.n; l++) cudaFree(s.pyr.lvl[l].p);
     cudaFree(s.half.p);
     s.fld.release();
@@ -524,13 +534,18 @@ int FeContext::submit_impl(double t, const uint8_t *image, int stride, bool on_d
   if (vp) std::memcpy(s.vp, vp, sizeof(s.vp));
   if (mask) {
     s.mask.resize((size_t)W_ * H_);
-    for (int y = 0; y < H_; y++) std::memcpy(&s.mask[(size_t)y * W_], mask + (size_t)y * mask_stride, W_);
+    if (cfg_.downsample) {   // cv::pyrDown(mask, .., Size(cols / 2.0, rows / 2.0)) (UpdaterCamera.cpp:92-93)
+      pyr_down_host(mask, Win_, Hin_, mask_stride, s.mask.data(), W_, H_);
+    } else {
+      for (int y = 0; y < H_; y++) std::memcpy(&s.mask[(size_t)y * W_], mask + (size_t)y * mask_stride, W_);
+    }
   } else {
     s.mask.clear();
   }
   if (timing) cudaEventRecord(s.ev_t[0], s.s_a);
+  DevImage &dst = cfg_.downsample ? s.raw_in : s.raw;
   if (on_device) {
-    FE_CUDA(cudaMemcpy2DAsync(s.raw.p, s.raw.pitch, image, stride, W_, H_, cudaMemcpyDeviceToDevice, s.s_a));
+    FE_CUDA(cudaMemcpy2DAsync(dst.p, dst.pitch, image, stride, Win_, Hin_, cudaMemcpyDeviceToDevice, s.s_a));
   } else {
     cudaPointerAttributes attr;
     bool pinned = cudaPointerGetAttributes(&attr, image) == cudaSuccess && attr.type == cudaMemoryTypeHost;
@@ -538,12 +553,16 @@ int FeContext::submit_impl(double t, const uint8_t *image, int stride, bool on_d
     const uint8_t *src = image;
     int sstride = stride;
     if (!pinned) {  // pageable caller memory: stage through the slot's pinned buffer
-      for (int y = 0; y < H_; y++) std::memcpy(s.h_raw + (size_t)y * W_, image + (size_t)y * stride, W_);
+      for (int y = 0; y < Hin_; y++) std::memcpy(s.h_raw + (size_t)y * Win_, image + (size_t)y * stride, Win_);
       src = s.h_raw;
-      sstride = W_;
+      sstride = Win_;
     }
-    FE_CUDA(cudaMemcpy2DAsync(s.raw.p, s.raw.pitch, src, sstride, W_, H_, cudaMemcpyHostToDevice, s.s_a));
-    mst_.h2d_bytes += (size_t)W_ * H_;
+    FE_CUDA(cudaMemcpy2DAsync(dst.p, dst.pitch, src, sstride, Win_, Hin_, cudaMemcpyHostToDevice, s.s_a));
+    mst_.h2d_bytes += (size_t)Win_ * Hin_;
+  }
+  if (cfg_.downsample) {   // cv::pyrDown(img, .., Size(cols / 2.0, rows / 2.0)) (UpdaterCamera.cpp:90-91)
+    launch_pyr_down(s.raw_in, s.raw, s.s_a);
+    mst_.kernel_launches_total++;
   }
   if (timing) cudaEventRecord(s.ev_t[1], s.s_a);
   int rc = enqueue_fast_all_cells(s);   // layout bookkeeping first: it decides whether the graphs are still valid
@@ -798,7 +817,7 @@ int FeContext::play(int n_frames, const uint8_t *const *images, int stride, bool
 
 int FeContext::feed(double t, const uint8_t *image, int w, int h, int stride, bool on_device, const uint8_t *mask,
                     int mask_stride, const double vp[6], FeFrameInfo *info) {
-  if (!image || w != W_ || h != H_ || stride < w || (mask && mask_stride < w)) {
+  if (!image || w != Win_ || h != Hin_ || stride < w || (mask && mask_stride < w)) {
     last_error = "feed: image/mask size does not match the handle";   // TrackKLT.cpp:37-43 exits here
     return FE_BAD_ARG;
   }

@@ -23,6 +23,7 @@ struct Pt {
   float x, y;
 };
 
+void pyr_down_host(const uint8_t *src, int sw, int sh, int stride, uint8_t *dst, int dw, int dh);
 int line_candidates(const float *px, const float *py, int n, float min_lx, float max_lx, float min_ly, float max_ly, float pa,
                     float pb, float pc, float plen2, uint8_t *pass);
 int ransac_fundamental(const float *m1, const float *m2, int count, double threshold, double confidence, uint8_t *mask,
@@ -70,7 +71,8 @@ class WorkQueue {
 
 // Everything that belongs to one submitted frame and can be produced without tracker state.
 struct FrameSlot {
-  DevImage raw;          // staged input (device)
+  DevImage raw;          // staged input (device), tracking size
+  DevImage raw_in;       // cfg.downsample: the full-size input, raw = pyrDown(raw_in)
   Pyramid pyr;           // equalised pyramid, level 0 = equalised frame
   DevImage half;         // half-resolution equalised frame (line detector input)
   FldBuffers fld;
@@ -189,7 +191,8 @@ class FeContext {
 
   FeConfig cfg_;
   int device_;
-  int W_, H_;
+  int W_, H_;            // tracking size (= input size, or half of it with cfg.downsample)
+  int Win_, Hin_;        // input size
   cudaStream_t s_pt_ = nullptr;
   std::deque<FrameSlot> slots_;           // deque: FrameSlot holds an atomic and never moves
   std::vector<int> queue_;      // submitted, not yet collected (slot indices, FIFO) — caller's thread only

@@ -31,6 +31,8 @@ void launch_eq_pyr1(const DevImage &src, unsigned *d_hist, unsigned *d_counter, 
 void launch_clahe_lut(const DevImage &src, uint8_t *d_luts, cudaStream_t s);
 // levels 2..n-1, one short launch per level (4 outputs per thread).
 void launch_pyr_rest(const Pyramid &pyr, unsigned *d_counter, cudaStream_t s);
+// cv::pyrDown(src, dst, Size(dst.w, dst.h)) for one image (|2 dst - src| <= 2 per side)
+void launch_pyr_down(const DevImage &src, const DevImage &dst, cudaStream_t s);
 
 void launch_signal(int *host_flag, int value, cudaStream_t s);
 void launch_signal_inc(int *host_flag, int *dev_seq, cudaStream_t s);

@@ -25,4 +25,41 @@ int line_candidates(const float *px, const float *py, int n, float min_lx, float
   return any;
 }
 
+// cv::pyrDown of an 8-bit image to (dw, dh) on the host: separable [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8.
+// Only used for the tracking MASK when cfg.downsample is set (UpdaterCamera.cpp:92-93); masks never leave the host.
+static inline int reflect101_host(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+void pyr_down_host(const uint8_t *src, int sw, int sh, int stride, uint8_t *dst, int dw, int dh) {
+  // horizontal pass of the 5 source rows a destination row needs, kept in a ring of 5 int rows
+  int *rows = new int[(size_t)5 * dw];
+  int have[5] = {-1, -1, -1, -1, -1};   // source row currently held by each ring slot
+  for (int y = 0; y < dh; y++) {
+    const int *r[5];
+    for (int k = 0; k < 5; k++) {
+      const int sy = reflect101_host(2 * y + k - 2, sh);
+      const int slot = sy % 5;
+      int *row = rows + (size_t)slot * dw;
+      if (have[slot] != sy) {
+        const uint8_t *s = src + (size_t)sy * stride;
+        for (int x = 0; x < dw; x++) {
+          const int c = 2 * x;
+          if (c >= 2 && c + 2 < sw)
+            row[x] = s[c - 2] + 4 * s[c - 1] + 6 * s[c] + 4 * s[c + 1] + s[c + 2];
+          else
+            row[x] = s[reflect101_host(c - 2, sw)] + 4 * s[reflect101_host(c - 1, sw)] + 6 * s[reflect101_host(c, sw)] +
+                     4 * s[reflect101_host(c + 1, sw)] + s[reflect101_host(c + 2, sw)];
+        }
+        have[slot] = sy;
+      }
+      r[k] = row;
+    }
+    uint8_t *d = dst + (size_t)y * dw;
+    for (int x = 0; x < dw; x++) d[x] = (uint8_t)((r[0][x] + 4 * r[1][x] + 6 * r[2][x] + 4 * r[3][x] + r[4][x] + 128) >> 8);
+  }
+  delete[] rows;
+}
+
 }  // namespace plviwo

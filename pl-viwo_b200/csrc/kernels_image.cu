@@ -413,6 +413,11 @@ __global__ void k_signal_inc(volatile int *flag, int *dev_seq) {
 }
 void launch_signal_inc(int *host_flag, int *dev_seq, cudaStream_t s) { k_signal_inc<<<1, 1, 0, s>>>(host_flag, dev_seq); }
 
+void launch_pyr_down(const DevImage &a, const DevImage &b, cudaStream_t s) {
+  int n = ((b.w + 3) >> 2) * b.h;
+  k_pyr_down<<<(n + kRestThreads - 1) / kRestThreads, kRestThreads, 0, s>>>(a.p, a.w, a.h, a.pitch, b.p, b.w, b.h, b.pitch);
+}
+
 void launch_pyr_rest(const Pyramid &pyr, unsigned *d_counter, cudaStream_t s) {
   (void)d_counter;
   for (int l = 2; l < pyr.n; l++) {

@@ -391,3 +391,31 @@ def test_play_equals_frame_by_frame(fe, synth):
     assert abs(st.checksum - chk) <= 1e-6 * max(1.0, abs(chk))
     assert np.array_equal(b.get_last_ids(), last_ids)
     b.close()
+
+
+@pytest.mark.parametrize("size,lines", [((1280, 560), True), ((1285, 563), False)])
+def test_downsample_prestep(fe, synth, size, lines):
+    """cfg.downsample: UpdaterCamera::feed_measurement's cv::pyrDown of image AND mask to the truncated half size
+    (UpdaterCamera.cpp:86-95) in front of both trackers; K is the halved calibration (OptionsCamera.cpp:123-126)."""
+    W, H = size
+    seq = synth.SynthSequence(seed=1014, width=W, height=H, n_frames=8, hard=False, moving_mask=True)
+    K = tuple(v / 2.0 for v in seq.K)
+    kw = dict(CFG1, num_features=150)
+    oracle = ofe.FrontEnd(ofe.FeConfig(K=K, D=seq.D, use_lines=lines, downsample=True, **kw))
+    gpu = fe.FrontEnd(fe.default_config(width=W, height=H, K=K, D=seq.D, use_lines=int(lines), downsample=1, **kw))
+    worst = 0.0
+    for t in range(8):
+        img, mask, vps = seq.frame(t), seq.mask(t), [(x / 2.0, y / 2.0) for x, y in seq.vanishing_points(t)]
+        prow_o, lrow_o = oracle.feed(seq.timestamp(t), img, mask, vps if lines else None)
+        gpu.feed_new_camera(seq.timestamp(t), img, mask, vps if lines else None)
+        assert np.array_equal(gpu.tap(fe.TAP_PYR_LEVEL0).reshape(int(H / 2.0), int(W / 2.0)), oracle.klt.trace["img_eq"]), t
+        rows = gpu.point_rows()
+        assert [int(v) for v in rows["id"]] == [r.id for r in prow_o], t
+        if len(rows):
+            uv_o = np.array([[r.u, r.v] for r in prow_o], np.float32)
+            worst = max(worst, float(np.abs(np.stack([rows["u"], rows["v"]], 1) - uv_o).max()))
+        if lines:
+            lrows, lpts = gpu.line_rows()
+            assert _compare_lines(lrows, lpts, lrow_o), t
+    assert worst < 0.05, worst
+    gpu.close()

@@ -25,7 +25,7 @@ def test_struct_layouts_match_header(fe):
     assert C.sizeof(fe.FePointRow) == 24 and fe.POINT_ROW_DTYPE.itemsize == 24
     assert C.sizeof(fe.FeLineRow) == 56 and fe.LINE_ROW_DTYPE.itemsize == 56
     assert C.sizeof(fe.FeLinePoint) == 16 and fe.LINE_POINT_DTYPE.itemsize == 16
-    assert C.sizeof(fe.FeConfig) == 19 * 4 + 4 + 64
+    assert C.sizeof(fe.FeConfig) == 20 * 4 + 64
     cfg = fe.default_config()
     assert (cfg.width, cfg.height, cfg.num_features, cfg.pyr_levels, cfg.win_size) == (1280, 560, 150, 5, 15)
     assert abs(cfg.K[0] - 816.90378992770002) < 1e-12 and cfg.fld_length_threshold == 20
@@ -102,3 +102,22 @@ def test_introsort_restatement_equals_std_sort(fe):
         got = fe.op_sort_corners(packed, 9, device=-1)
         perm = cvops.sort_perm(resp.astype(np.float32))
         assert np.array_equal(got & 0xffffff, np.asarray(perm, np.uint32)), (trial, n, span)
+
+
+def test_append_new_measurements(fe):
+    """The consumer side of the drop-in (UpdaterCamera.cpp:111): trackDATABASE->append_new_measurements(tracker db)."""
+    trk, upd = fe.FeatureDatabase(), fe.FeatureDatabase()
+    for t in (1.0, 2.0):
+        trk.update_feature(7, t, 0, 10 + t, 20 + t, 0.1, 0.2)
+    trk.update_feature(9, 2.0, 0, 1, 2, 0.01, 0.02)
+    upd.append_new_measurements(trk)
+    assert sorted(upd.get_internal_data()) == [7, 9] and upd.get_internal_data()[7].timestamps == [1.0, 2.0]
+    trk.update_feature(7, 3.0, 0, 13, 23, 0.1, 0.2)
+    upd.append_new_measurements(trk)                       # only the unseen timestamp is appended
+    assert upd.get_internal_data()[7].timestamps == [1.0, 2.0, 3.0] and len(upd.get_internal_data()[7].uvs) == 3
+    upd.append_new_measurements(trk)                       # idempotent
+    assert upd.get_internal_data()[7].timestamps == [1.0, 2.0, 3.0]
+    trk.get_internal_data()[9].chi_test = False
+    trk.update_feature(9, 3.0, 0, 1, 2, 0.01, 0.02)
+    upd.append_new_measurements(trk)                       # failed chi-square: flag copied, nothing appended
+    assert upd.get_internal_data()[9].chi_test is False and upd.get_internal_data()[9].timestamps == [2.0]

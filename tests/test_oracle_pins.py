@@ -35,6 +35,16 @@ def test_clahe_bit_exact():
     assert np.array_equal(npops.clahe(GOLD["img_a"]), GOLD["clahe_a"])
 
 
+def test_downsample_bit_exact():
+    """UpdaterCamera's pyrDown to the truncated half size (image and mask), incl. odd sides."""
+    rng = np.random.default_rng(4)
+    for shape in [(560, 1280), (563, 1285), (101, 64), (64, 99)]:
+        im = rng.integers(0, 256, shape, dtype=np.uint8)
+        assert np.array_equal(npops.downsample(im), cvops.downsample(im)), shape
+        m = (rng.random(shape) > 0.7).astype(np.uint8) * 255
+        assert np.array_equal(npops.downsample(m), cvops.downsample(m)), shape
+
+
 def test_pyramid_and_half_bit_exact():
     for img in _imgs()[:3]:
         a, b = npops.build_pyramid(img, 3, 4), cvops.build_pyramid(img, 3, 4)
