@@ -226,6 +226,8 @@ int FeContext::init() {
   FE_CUDA(cudaMalloc(&d_p0n_, (size_t)max_pts_ * sizeof(float2)));
   FE_CUDA(cudaMalloc(&d_p1n_, (size_t)max_pts_ * sizeof(float2)));
   FE_CUDA(cudaMalloc(&d_status_, (size_t)max_pts_));
+  FE_CUDA(cudaMalloc(&d_lk_done_, sizeof(unsigned)));
+  FE_CUDA(cudaMemset(d_lk_done_, 0, sizeof(unsigned)));
   FE_CUDA(cudaMallocHost(&h_pts0_, (size_t)max_pts_ * sizeof(float2)));
   FE_CUDA(cudaMallocHost(&h_pts1_, (size_t)max_pts_ * sizeof(float2)));
   FE_CUDA(cudaMallocHost(&h_p0n_, (size_t)max_pts_ * sizeof(float2)));
@@ -270,6 +272,7 @@ FeContext::~FeContext() {
   if (ev_sync_) cudaEventDestroy(ev_sync_);
   cudaFreeHost(h_flag_lk_);
   cudaFree(d_cells_);
+  cudaFree(d_lk_done_);
   cudaFree(d_pts0_); cudaFree(d_pts1_); cudaFree(d_p0n_); cudaFree(d_p1n_); cudaFree(d_status_);
   cudaFreeHost(h_pts0_); cudaFreeHost(h_pts1_); cudaFreeHost(h_p0n_); cudaFreeHost(h_p1n_); cudaFreeHost(h_status_);
   if (s_pt_) cudaStreamDestroy(s_pt_);
@@ -1088,10 +1091,12 @@ int FeContext::perform_matching(const FrameSlot &f0, const FrameSlot &f1, std::v
   kst_.d2h_bytes += (size_t)nt * (3 * sizeof(float2) + 1);
   if (timing) cudaEventRecord(ev_pt_[4], s_pt_);
   HostTimer *tl = new HostTimer(&kst_.host_ms[12]);
-  launch_lk(f0.pyr, f1.pyr, h_pts0_, h_pts1_, h_status_, h_p0n_, h_p1n_, nt, prm, s_pt_);
+  // the LK kernel publishes the completion sequence number itself (its last feature writes the pinned flag)
+  const bool self_signal = launch_lk(f0.pyr, f1.pyr, h_pts0_, h_pts1_, h_status_, h_p0n_, h_p1n_, nt, prm, s_pt_, h_flag_lk_,
+                                     ++seq_lk_, d_lk_done_);
   kst_.kernel_launches_total++;
   if (timing) cudaEventRecord(ev_pt_[5], s_pt_);
-  launch_signal(h_flag_lk_, ++seq_lk_, s_pt_);
+  if (!self_signal) launch_signal(h_flag_lk_, seq_lk_, s_pt_);
   FE_CUDA(cudaGetLastError());
   delete tl;
   {

@@ -234,6 +234,7 @@ class FeContext {
   int max_pts_ = 0;
   float2 *d_pts0_ = nullptr, *d_pts1_ = nullptr, *d_p0n_ = nullptr, *d_p1n_ = nullptr;
   uint8_t *d_status_ = nullptr;
+  unsigned *d_lk_done_ = nullptr;   // features finished in the running LK launch (completion signal)
   float2 *h_pts0_ = nullptr, *h_pts1_ = nullptr, *h_p0n_ = nullptr, *h_p1n_ = nullptr;
   uint8_t *h_status_ = nullptr;
   cudaEvent_t ev_pt_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

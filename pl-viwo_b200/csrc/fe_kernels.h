@@ -72,8 +72,12 @@ struct LkParams {
   double K[4], D[4];
   int undistort;   // also write normalised coordinates of pts0 / pts1
 };
-void launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *d_pts0, float2 *d_pts1, uint8_t *d_status,
-               float2 *d_p0n, float2 *d_p1n, int n, const LkParams &prm, cudaStream_t s);
+// host_flag / flag_value / d_done_counter (optional): the kernel itself publishes flag_value to the pinned word when its
+// last feature is done (d_done_counter: one zeroed device word).  Returns true if the kernel will do so; false means
+// the caller has to queue its own completion signal (generic-window kernel).
+bool launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *d_pts0, float2 *d_pts1, uint8_t *d_status,
+               float2 *d_p0n, float2 *d_p1n, int n, const LkParams &prm, cudaStream_t s, int *host_flag = nullptr,
+               int flag_value = 0, unsigned *d_done_counter = nullptr);
 void launch_undistort(const float2 *d_pts, float2 *d_out, int n, const double K[4], const double D[4], cudaStream_t s);
 
 // ---- lines (kernels_lines.cu) -------------------------------------------------------------------------------

@@ -366,38 +366,135 @@ __global__ void __launch_bounds__(kLkWarps * 32)
 }
 
 // ------------------------------------------------------------------------------------------ LK, 15 x 15 window
-// Register-blocked specialisation for the reference's window (TrackKLT.h:144).  Lane l owns the 2 x 4 block of window
-// pixels at rows 2*(l/4).., columns 4*(l%4).. (the 16th row / column is masked off), keeps its I, Ix, Iy values and
-// the 3 x 5 block of the next image it interpolates from in registers, and only re-reads the next image when the
-// integer window position moves.  An iteration is then ~100 independent integer/float instructions plus one
-// two-value shuffle reduction, instead of eight dependent load-compute rounds.
+// Specialisation for the reference's window (TrackKLT.h:144): ONE CTA PER FEATURE, one warp per pyramid level.
+//
+// The kernel's duration is the latency of its slowest feature, so the dependent chain of one feature is what counts:
+//   set-up   everything that depends only on the PREVIOUS image and the previous position — per level the raw
+//            neighbourhood, the Scharr derivatives, the fixed-point I / Ix / Iy patches and the 2 x 2 normal matrix —
+//            is built by warp l for level l, all levels at the same time (it used to be 5 x ~4.5k cycles in a row);
+//            lane i owns the 2 x 4 block of window pixels at rows 2*(i/4).., columns 4*(i%4).. (the 16th row / column
+//            is masked off), its 8 values per patch are parked in shared memory as int16;
+//   chain    warp 0 then runs the coarse-to-fine iterations, which only touch the NEXT image.  Per level a 25 x 25
+//            region of it (REFLECT_101 applied while staging) is copied to shared memory around the start position; a
+//            lane keeps the 3 x 5 block it interpolates from in registers and re-reads it — from shared memory — only
+//            when the integer window position moves; the region is re-staged if the window leaves it.  An iteration
+//            is ~100 independent integer/float instructions plus one two-value shuffle reduction.
+// Arithmetic and summation order are those of the generic kernel above (results are bit-identical to it).
 constexpr int kW15 = 15;
-constexpr int kLk15Warps = 2;
+constexpr int kLk15MaxLevels = 6;   // pyr_levels <= 5 (the reference uses 5); deeper pyramids take the generic kernel
+constexpr int kJMargin = 4;         // the staged region of the next image extends this far around a window
+constexpr int kJSpan = kW15 + 2;    // rows / columns a window touches: 15 + 1 (bilinear) + 1 (the lanes' masked 16th row)
+constexpr int kJR = kJSpan + 2 * kJMargin;   // 25
 
-__global__ void __launch_bounds__(kLk15Warps * 32)
+__global__ void __launch_bounds__(kLk15MaxLevels * 32)
     k_lk15(LkArgs a, const float2 *__restrict__ pts0, float2 *__restrict__ pts1, uint8_t *__restrict__ status,
-           float2 *__restrict__ p0n, float2 *__restrict__ p1n, int n) {
+           float2 *__restrict__ p0n, float2 *__restrict__ p1n, int n, int *host_flag, int flag_value, unsigned *done_counter) {
   constexpr int win = kW15, np = win + 3, nd = win + 1;
-  __shared__ uint8_t raw_s[kLk15Warps][np * np + 12];
-  __shared__ short ddx_s[kLk15Warps][nd * nd];
-  __shared__ short ddy_s[kLk15Warps][nd * nd];
+  constexpr int kRawLoads = (np * np + 31) / 32;   // 11
+  __shared__ uint8_t raw_s[kLk15MaxLevels][np * np + 12];
+  __shared__ short ddx_s[kLk15MaxLevels][nd * nd];
+  __shared__ short ddy_s[kLk15MaxLevels][nd * nd];
+  __shared__ short patch_s[kLk15MaxLevels][3][8][32];   // [level][I, Ix, Iy][k][lane]
+  __shared__ float amat_s[kLk15MaxLevels][4];           // [level][A11, A12, A22, level usable]
+  __shared__ uint8_t jreg_s[kJR * kJR + 7];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pi = blockIdx.x * kLk15Warps + warp;
-  if (pi >= n) return;
-  uint8_t *raw = raw_s[warp];
-  short *ddx = ddx_s[warp], *ddy = ddy_s[warp];
+  const int pi = blockIdx.x;
   const int r0 = (lane >> 2) * 2, c0 = (lane & 3) * 4;
-
   const float2 prev_in = pts0[pi];
-  float2 next = pts1[pi];   // OPTFLOW_USE_INITIAL_FLOW
-  bool ok = true;
   const float half = (win - 1) * 0.5f;
   const float FLT_SCALE = 1.f / (1 << 20);
 
+  // ---- set-up of level `warp`
+  if (warp <= a.max_level) {
+    const int l = warp;
+    const int cols = a.w[l], rows = a.h[l];
+    const float lscale = 1.f / (float)(1 << l);
+    const float px = prev_in.x * lscale - half, py = prev_in.y * lscale - half;
+    const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
+    const bool in_range = !(ipx < -win || ipx >= cols || ipy < -win || ipy >= rows);
+    float A11 = 0, A12 = 0, A22 = 0;
+    if (in_range) {
+      uint8_t *raw = raw_s[l];
+      short *ddx = ddx_s[l], *ddy = ddy_s[l];
+      {  // raw neighbourhood, origin (ipx - 1, ipy - 1): all loads in flight before the first store
+        const uint8_t *I = a.p0[l];
+        const int pitchI = a.pitch0[l];
+        uint8_t v[kRawLoads];
+#pragma unroll
+        for (int j = 0; j < kRawLoads; j++) {
+          const int i = lane + 32 * j;
+          v[j] = 0;
+          if (i < np * np) {
+            const int r = i / np, c = i - r * np;
+            v[j] = I[(size_t)reflect101(ipy - 1 + r, rows) * pitchI + reflect101(ipx - 1 + c, cols)];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kRawLoads; j++)
+          if (lane + 32 * j < np * np) raw[lane + 32 * j] = v[j];
+      }
+      const float fa = px - ipx, fb = py - ipy;
+      const int iw00 = __float2int_rn((1.f - fa) * (1.f - fb) * 16384.f);
+      const int iw01 = __float2int_rn(fa * (1.f - fb) * 16384.f);
+      const int iw10 = __float2int_rn((1.f - fa) * fb * 16384.f);
+      const int iw11 = 16384 - iw00 - iw01 - iw10;
+      __syncwarp();
+      // Scharr derivatives at (ipx + c, ipy + r), c, r in [0, win]; zero outside the frame
+      for (int i = lane; i < nd * nd; i += 32) {
+        int r = i / nd, c = i - r * nd;
+        int gx = ipx + c, gy = ipy + r;
+        int vx = 0, vy = 0;
+        if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
+          const uint8_t *q = raw + (r + 1) * np + (c + 1);
+          int tl = q[-np - 1], tc = q[-np], tr = q[-np + 1];
+          int ml = q[-1], mr = q[1];
+          int bl = q[np - 1], bc = q[np], br = q[np + 1];
+          vx = 3 * (tr + br) + 10 * mr - 3 * (tl + bl) - 10 * ml;
+          vy = 3 * (bl + br) + 10 * bc - 3 * (tl + tr) - 10 * tc;
+        }
+        ddx[i] = (short)vx;
+        ddy[i] = (short)vy;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int y = r0 + (k >> 2), x = c0 + (k & 3);
+        int ival = 0, ixval = 0, iyval = 0;
+        if (y < win && x < win) {
+          const uint8_t *q = raw + (y + 1) * np + (x + 1);
+          ival = (q[0] * iw00 + q[1] * iw01 + q[np] * iw10 + q[np + 1] * iw11 + (1 << 8)) >> 9;
+          const int di = y * nd + x;
+          ixval = (ddx[di] * iw00 + ddx[di + 1] * iw01 + ddx[di + nd] * iw10 + ddx[di + nd + 1] * iw11 + (1 << 13)) >> 14;
+          iyval = (ddy[di] * iw00 + ddy[di + 1] * iw01 + ddy[di + nd] * iw10 + ddy[di + nd + 1] * iw11 + (1 << 13)) >> 14;
+        }
+        patch_s[l][0][k][lane] = (short)ival;
+        patch_s[l][1][k][lane] = (short)ixval;
+        patch_s[l][2][k][lane] = (short)iyval;
+        A11 += (float)(ixval * ixval);
+        A12 += (float)(ixval * iyval);
+        A22 += (float)(iyval * iyval);
+      }
+      A11 = warp_sum(A11) * FLT_SCALE;
+      A12 = warp_sum(A12) * FLT_SCALE;
+      A22 = warp_sum(A22) * FLT_SCALE;
+    }
+    if (lane == 0) {
+      amat_s[l][0] = A11;
+      amat_s[l][1] = A12;
+      amat_s[l][2] = A22;
+      amat_s[l][3] = in_range ? 1.f : 0.f;
+    }
+  }
+  __syncthreads();
+  if (warp != 0) return;
+
+  // ---- the iteration chain (warp 0)
+  float2 next = pts1[pi];   // OPTFLOW_USE_INITIAL_FLOW
+  bool ok = true;
+#pragma unroll 1
   for (int level = a.max_level; level >= 0; level--) {
     const int cols = a.w[level], rows = a.h[level];
     const float lscale = 1.f / (float)(1 << level);
-    float2 prevPt = make_float2(prev_in.x * lscale, prev_in.y * lscale);
     if (level == a.max_level) {
       next.x = next.x * lscale;
       next.y = next.y * lscale;
@@ -405,66 +502,11 @@ __global__ void __launch_bounds__(kLk15Warps * 32)
       next.x = next.x * 2.f;
       next.y = next.y * 2.f;
     }
-    prevPt.x -= half;
-    prevPt.y -= half;
-    const int ipx = __float2int_rd(prevPt.x), ipy = __float2int_rd(prevPt.y);
-    if (ipx < -win || ipx >= cols || ipy < -win || ipy >= rows) {
+    if (amat_s[level][3] == 0.f) {
       if (level == 0) ok = false;
       continue;
     }
-    const float fa = prevPt.x - ipx, fb = prevPt.y - ipy;
-    const int iw00 = __float2int_rn((1.f - fa) * (1.f - fb) * 16384.f);
-    const int iw01 = __float2int_rn(fa * (1.f - fb) * 16384.f);
-    const int iw10 = __float2int_rn((1.f - fa) * fb * 16384.f);
-    const int iw11 = 16384 - iw00 - iw01 - iw10;
-
-    const uint8_t *I = a.p0[level];
-    const int pitchI = a.pitch0[level];
-    __syncwarp();
-    for (int i = lane; i < np * np; i += 32) {
-      int r = i / np, c = i - r * np;
-      int x = reflect101(ipx - 1 + c, cols), y = reflect101(ipy - 1 + r, rows);
-      raw[i] = I[(size_t)y * pitchI + x];
-    }
-    __syncwarp();
-    for (int i = lane; i < nd * nd; i += 32) {
-      int r = i / nd, c = i - r * nd;
-      int gx = ipx + c, gy = ipy + r;
-      int vx = 0, vy = 0;
-      if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
-        const uint8_t *q = raw + (r + 1) * np + (c + 1);
-        int tl = q[-np - 1], tc = q[-np], tr = q[-np + 1];
-        int ml = q[-1], mr = q[1];
-        int bl = q[np - 1], bc = q[np], br = q[np + 1];
-        vx = 3 * (tr + br) + 10 * mr - 3 * (tl + bl) - 10 * ml;
-        vy = 3 * (bl + br) + 10 * bc - 3 * (tl + tr) - 10 * tc;
-      }
-      ddx[i] = (short)vx;
-      ddy[i] = (short)vy;
-    }
-    __syncwarp();
-    // this lane's 2 x 4 block of the interpolated patches
-    int Iw[8], Ixw[8], Iyw[8];
-    float A11 = 0, A12 = 0, A22 = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const int y = r0 + (k >> 2), x = c0 + (k & 3);
-      int ival = 0, ixval = 0, iyval = 0;
-      if (y < win && x < win) {
-        const uint8_t *q = raw + (y + 1) * np + (x + 1);
-        ival = (q[0] * iw00 + q[1] * iw01 + q[np] * iw10 + q[np + 1] * iw11 + (1 << 8)) >> 9;
-        const int di = y * nd + x;
-        ixval = (ddx[di] * iw00 + ddx[di + 1] * iw01 + ddx[di + nd] * iw10 + ddx[di + nd + 1] * iw11 + (1 << 13)) >> 14;
-        iyval = (ddy[di] * iw00 + ddy[di + 1] * iw01 + ddy[di + nd] * iw10 + ddy[di + nd + 1] * iw11 + (1 << 13)) >> 14;
-      }
-      Iw[k] = ival; Ixw[k] = ixval; Iyw[k] = iyval;
-      A11 += (float)(ixval * ixval);
-      A12 += (float)(ixval * iyval);
-      A22 += (float)(iyval * iyval);
-    }
-    A11 = warp_sum(A11) * FLT_SCALE;
-    A12 = warp_sum(A12) * FLT_SCALE;
-    A22 = warp_sum(A22) * FLT_SCALE;
+    const float A11 = amat_s[level][0], A12 = amat_s[level][1], A22 = amat_s[level][2];
     float Dt = A11 * A22 - A12 * A12;
     const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
     if (minEig < a.min_eig || Dt < FLT_EPSILON) {
@@ -472,6 +514,13 @@ __global__ void __launch_bounds__(kLk15Warps * 32)
       continue;
     }
     Dt = 1.f / Dt;
+    int Iw[8], Ixw[8], Iyw[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      Iw[k] = patch_s[level][0][k][lane];
+      Ixw[k] = patch_s[level][1][k][lane];
+      Iyw[k] = patch_s[level][2][k][lane];
+    }
     float2 result = next;   // nextPts[ptidx] as stored by OpenCV; only rewritten after an update step
     next.x -= half;
     next.y -= half;
@@ -480,6 +529,7 @@ __global__ void __launch_bounds__(kLk15Warps * 32)
     const int pitchJ = a.pitch1[level];
     int jb[3][5];
     int cached_x = INT_MIN, cached_y = INT_MIN;
+    int reg_x0 = INT_MIN / 2, reg_y0 = INT_MIN / 2;   // origin of the staged region (none yet)
     for (int j = 0; j < a.max_count; j++) {
       const int inx = __float2int_rd(next.x), iny = __float2int_rd(next.y);
       if (inx < -win || inx >= cols || iny < -win || iny >= rows) {
@@ -494,21 +544,30 @@ __global__ void __launch_bounds__(kLk15Warps * 32)
       if (inx != cached_x || iny != cached_y) {   // warp-uniform
         cached_x = inx;
         cached_y = iny;
-        const bool inside = inx >= 0 && iny >= 0 && inx + win < cols && iny + win < rows;
-        if (inside) {
-          const uint8_t *Jp = J + (size_t)(iny + r0) * pitchJ + inx + c0;
+        if (inx < reg_x0 || inx + kJSpan > reg_x0 + kJR || iny < reg_y0 || iny + kJSpan > reg_y0 + kJR) {
+          // (re)stage the region around the window; pixel (rx, ry) of it is J(reflect(reg_x0 + rx), reflect(reg_y0 + ry))
+          reg_x0 = inx - kJMargin;
+          reg_y0 = iny - kJMargin;
+          __syncwarp();
+          constexpr int kJLoads = (kJR * kJR + 31) / 32;
+          uint8_t t[kJLoads];
 #pragma unroll
-          for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int c = 0; c < 5; c++) jb[r][c] = Jp[(size_t)r * pitchJ + c];
-        } else {
-#pragma unroll
-          for (int r = 0; r < 3; r++) {
-            const uint8_t *row = J + (size_t)reflect101(iny + r0 + r, rows) * pitchJ;
-#pragma unroll
-            for (int c = 0; c < 5; c++) jb[r][c] = row[reflect101(inx + c0 + c, cols)];
+          for (int q = 0; q < kJLoads; q++) {
+            const int i = lane + 32 * q;
+            const int ry = i / kJR, rx = i - ry * kJR;
+            t[q] = 0;
+            if (i < kJR * kJR) t[q] = J[(size_t)reflect101(reg_y0 + ry, rows) * pitchJ + reflect101(reg_x0 + rx, cols)];
           }
+#pragma unroll
+          for (int q = 0; q < kJLoads; q++)
+            if (lane + 32 * q < kJR * kJR) jreg_s[lane + 32 * q] = t[q];
+          __syncwarp();
         }
+        const uint8_t *Jp = jreg_s + (iny - reg_y0 + r0) * kJR + (inx - reg_x0 + c0);
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int c = 0; c < 5; c++) jb[r][c] = Jp[r * kJR + c];
       }
       float b1 = 0, b2 = 0;
 #pragma unroll
@@ -540,6 +599,7 @@ __global__ void __launch_bounds__(kLk15Warps * 32)
     }
     next = result;
     if (level == 0 && ok) {
+      // the reference asks for the error vector, so OpenCV re-checks the final position (lkpyramid.cpp err block)
       int fx = __float2int_rd(next.x - half), fy = __float2int_rd(next.y - half);
       if (fx < -win || fx >= cols || fy < -win || fy >= rows) ok = false;
     }
@@ -552,11 +612,24 @@ __global__ void __launch_bounds__(kLk15Warps * 32)
     if (lane == 0) p0n[pi] = undistort_radtan(prev_in, a.calib.K, a.calib.D);
     if (lane == 1) p1n[pi] = undistort_radtan(next, a.calib.K, a.calib.D);
   }
+  // ---- completion signal: the last feature to finish publishes the sequence number (results first, system-wide)
+  if (host_flag != nullptr) {
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+      if (atomicAdd(done_counter, 1u) == (unsigned)n - 1u) {
+        *done_counter = 0;
+        __threadfence_system();
+        *reinterpret_cast<volatile int *>(host_flag) = flag_value;
+      }
+    }
+  }
 }
 
-void launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *d_pts0, float2 *d_pts1, uint8_t *d_status,
-               float2 *d_p0n, float2 *d_p1n, int n, const LkParams &prm, cudaStream_t s) {
-  if (n <= 0) return;
+bool launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *d_pts0, float2 *d_pts1, uint8_t *d_status,
+               float2 *d_p0n, float2 *d_p1n, int n, const LkParams &prm, cudaStream_t s, int *host_flag, int flag_value,
+               unsigned *d_done_counter) {
+  if (n <= 0) return false;
   LkArgs a;
   int levels = prm.max_level + 1;
   if (levels > prev.n) levels = prev.n;
@@ -575,9 +648,9 @@ void launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *d_pts0, f
   a.min_eig = prm.min_eig;
   a.undistort = prm.undistort;
   for (int i = 0; i < 4; i++) { a.calib.K[i] = prm.K[i]; a.calib.D[i] = prm.D[i]; }
-  if (prm.win == kW15) {
-    k_lk15<<<(n + kLk15Warps - 1) / kLk15Warps, kLk15Warps * 32, 0, s>>>(a, d_pts0, d_pts1, d_status, d_p0n, d_p1n, n);
-    return;
+  if (prm.win == kW15 && levels <= kLk15MaxLevels) {   // one CTA per feature, one warp per level
+    k_lk15<<<n, levels * 32, 0, s>>>(a, d_pts0, d_pts1, d_status, d_p0n, d_p1n, n, host_flag, flag_value, d_done_counter);
+    return host_flag != nullptr;
   }
   const int win = prm.win, np = win + 3, nd = win + 1, nw = win * win;
   const int per_warp = ((np * np + 15) & ~15) + 2 * ((nd * nd * 2 + 15) & ~15) + 3 * ((nw * 2 + 15) & ~15);
@@ -588,6 +661,7 @@ void launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *d_pts0, f
     configured = smem;
   }
   k_lk<<<(n + kLkWarps - 1) / kLkWarps, kLkWarps * 32, smem, s>>>(a, d_pts0, d_pts1, d_status, d_p0n, d_p1n, n);
+  return false;
 }
 
 }  // namespace plviwo
