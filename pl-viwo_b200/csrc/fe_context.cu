@@ -76,6 +76,13 @@ bool WorkQueue::pop(int *v) {
   n_.fetch_sub(1, std::memory_order_relaxed);
   return true;
 }
+bool WorkQueue::peek(int *v) {
+  if (n_.load(std::memory_order_acquire) <= 0) return false;
+  std::lock_guard<std::mutex> lk(mu_);
+  if (q_.empty()) return false;
+  *v = q_.front();
+  return true;
+}
 void WorkQueue::stop() {
   {
     std::lock_guard<std::mutex> lk(mu_);
@@ -226,8 +233,26 @@ int FeContext::init() {
   FE_CUDA(cudaMalloc(&d_p0n_, (size_t)max_pts_ * sizeof(float2)));
   FE_CUDA(cudaMalloc(&d_p1n_, (size_t)max_pts_ * sizeof(float2)));
   FE_CUDA(cudaMalloc(&d_status_, (size_t)max_pts_));
-  FE_CUDA(cudaMalloc(&d_lk_done_, sizeof(unsigned)));
-  FE_CUDA(cudaMemset(d_lk_done_, 0, sizeof(unsigned)));
+  FE_CUDA(cudaMalloc(&d_lk_done_, 4 * sizeof(unsigned)));   // [ordinary, speculative, candidates set 0, set 1]
+  FE_CUDA(cudaMemset(d_lk_done_, 0, 4 * sizeof(unsigned)));
+  FE_CUDA(cudaMallocHost(&h_sp_pts0_, (size_t)max_pts_ * sizeof(float2)));
+  FE_CUDA(cudaMallocHost(&h_sp_pts1_, (size_t)max_pts_ * sizeof(float2)));
+  FE_CUDA(cudaMallocHost(&h_sp_p0n_, (size_t)max_pts_ * sizeof(float2)));
+  FE_CUDA(cudaMallocHost(&h_sp_p1n_, (size_t)max_pts_ * sizeof(float2)));
+  FE_CUDA(cudaMallocHost(&h_sp_status_, (size_t)max_pts_));
+  for (FrameSlot &s : slots_) {
+    FE_CUDA(cudaMallocHost(&s.h_sc_pts1, (size_t)cand_cap_ * sizeof(float2)));
+    FE_CUDA(cudaMallocHost(&s.h_sc_p0n, (size_t)cand_cap_ * sizeof(float2)));
+    FE_CUDA(cudaMallocHost(&s.h_sc_p1n, (size_t)cand_cap_ * sizeof(float2)));
+    FE_CUDA(cudaMallocHost(&s.h_sc_status, (size_t)cand_cap_));
+    FE_CUDA(cudaMalloc(&s.d_sc_done, sizeof(unsigned)));
+    FE_CUDA(cudaMemset(s.d_sc_done, 0, sizeof(unsigned)));
+  }
+  // Opt-in (PLVIWO_SPECULATION=1): measured on B200 it is throughput-neutral for one stream — the LK launch-to-flag
+  // latency under load (~60-100 us) is about the host work it would hide — and it costs ~40 % more LK work on the GPU, so
+  // it is off by default.  Results are bit-identical either way (tests/test_frontend_gpu.py).
+  use_spec_ = std::getenv("PLVIWO_SPECULATION") != nullptr && std::atoi(std::getenv("PLVIWO_SPECULATION")) != 0;
+  use_spec_cand_ = std::getenv("PLVIWO_NO_CANDIDATE_SPECULATION") == nullptr;
   FE_CUDA(cudaMallocHost(&h_pts0_, (size_t)max_pts_ * sizeof(float2)));
   FE_CUDA(cudaMallocHost(&h_pts1_, (size_t)max_pts_ * sizeof(float2)));
   FE_CUDA(cudaMallocHost(&h_p0n_, (size_t)max_pts_ * sizeof(float2)));
@@ -273,6 +298,11 @@ FeContext::~FeContext() {
   cudaFreeHost(h_flag_lk_);
   cudaFree(d_cells_);
   cudaFree(d_lk_done_);
+  cudaFreeHost(h_sp_pts0_); cudaFreeHost(h_sp_pts1_); cudaFreeHost(h_sp_p0n_); cudaFreeHost(h_sp_p1n_); cudaFreeHost(h_sp_status_);
+  for (FrameSlot &s : slots_) {
+    cudaFreeHost(s.h_sc_pts1); cudaFreeHost(s.h_sc_p0n); cudaFreeHost(s.h_sc_p1n); cudaFreeHost(s.h_sc_status);
+    cudaFree(s.d_sc_done);
+  }
   cudaFree(d_pts0_); cudaFree(d_pts1_); cudaFree(d_p0n_); cudaFree(d_p1n_); cudaFree(d_status_);
   cudaFreeHost(h_pts0_); cudaFreeHost(h_pts1_); cudaFreeHost(h_p0n_); cudaFreeHost(h_p1n_); cudaFreeHost(h_status_);
   if (s_pt_) cudaStreamDestroy(s_pt_);
@@ -488,6 +518,7 @@ int FeContext::enqueue_frame_independent(FrameSlot &s) {
     if (rc) return rc;
   }
   s.seq_fast++;
+  FE_CUDA(cudaEventRecord(s.ev_fast, s.s_b));
   if (lines) {
     FE_CUDA(cudaStreamWaitEvent(s.s_line, s.ev_pyr, 0));
     if (replay) {
@@ -506,6 +537,36 @@ int FeContext::enqueue_frame_independent(FrameSlot &s) {
   (void)ntab;
   if (ncell > 0) mst_.d2h_bytes += (size_t)ncell * sizeof(int) + (size_t)2 * ncell * cells_nfg_ * sizeof(float2);
   if (lines) mst_.d2h_bytes += 2 * sizeof(int) + 1024 * sizeof(float4);
+  return FE_OK;
+}
+
+// The second half of the speculation.  Every refined corner candidate of the PREVIOUS submitted frame — the only points
+// the top-off detection can add when this frame is tracked — is tracked into this frame straight from that frame's
+// device-side candidate table.  It depends on nothing but the two frames' images, so it is issued here, at submit time,
+// as part of this frame's state-independent work (typically many frames ahead of the trackers); the point tracker only
+// reads the few results that belong to candidates the detection really adds.
+int FeContext::track_candidates(FrameSlot &prev, FrameSlot &s) {
+  s.sc_prev = -1;
+  if (!use_spec_ || !use_spec_cand_ || cfg_.line_samples > 0) return FE_OK;
+  LkParams prm;
+  prm.win = cfg_.win_size;
+  prm.max_level = cfg_.pyr_levels;
+  prm.max_count = 30;
+  prm.eps_sq = 0.01f * 0.01f;
+  prm.min_eig = 1e-4f;
+  prm.undistort = 1;
+  for (int i = 0; i < 4; i++) { prm.K[i] = s.K[i]; prm.D[i] = s.D[i]; }
+  const int ntab = prev.predet_ncell * prev.predet_nfg;
+  if (ntab <= 0 || ntab > cand_cap_ || prev.predet_num_features != cfg_.num_features || !lk_table_mode_ok(prm, prev.pyr.n))
+    return FE_OK;
+  FE_CUDA(cudaStreamWaitEvent(s.s_b, prev.ev_fast, 0));   // the candidate table of the previous frame
+  launch_lk(prev.pyr, s.pyr, prev.d_cand_ref, s.h_sc_pts1, s.h_sc_status, s.h_sc_p0n, s.h_sc_p1n, ntab, prm, s.s_b, &s.h_flags[3],
+            ++s.seq_sc, s.d_sc_done, prev.d_cand_cnt, prev.predet_nfg, true);
+  FE_CUDA(cudaGetLastError());
+  mst_.kernel_launches_total++;
+  mst_.d2h_bytes += (size_t)ntab * (3 * sizeof(float2) + 1);
+  s.sc_prev = prev.index;
+  s.sc_ntab = ntab;
   return FE_OK;
 }
 
@@ -572,6 +633,12 @@ int FeContext::submit_impl(double t, const uint8_t *image, int stride, bool on_d
   if (rc) return rc;
   rc = enqueue_frame_independent(s);
   if (rc) return rc;
+  s.sc_prev = -1;
+  if (prev_submit_slot_ >= 0) {
+    rc = track_candidates(slots_[prev_submit_slot_], s);
+    if (rc) return rc;
+  }
+  prev_submit_slot_ = si;
   queue_.push_back(si);
   s.stage.store(1, std::memory_order_release);
   klt_q_.push(si);
@@ -752,6 +819,9 @@ int FeContext::collect_impl(FeFrameInfo *info) {
     else std::this_thread::yield();
   }
   cur.stage.store(0, std::memory_order_relaxed);
+  // the candidate tracks into this frame read the previous frame's pyramid and candidate table: that slot is released
+  // below, so the launch must be over (it was issued at submit time and normally finished long ago)
+  if (cur.sc_prev >= 0 && wait_flag(&cur.h_flags[3], cur.seq_sc, cur.s_b, &t_err)) return FE_CUDA_ERROR;
   cur_slot_ = si;
   cur_res_ = &cur.res;
   FrameResult &res = cur.res;
@@ -840,38 +910,66 @@ int FeContext::klt_feed(FrameSlot &cur) {
   FrameResult &res = cur.res;
   FeFrameInfo *info = &res.info;
   std::vector<FePointRow> &point_rows = res.point_rows;
+  // A speculative LK launch (perform_matching) may be tracking last frame's points into THIS frame already
+  const bool spec = spec_valid_ && spec_prev_slot_ == klt_last_slot_ && spec_next_slot_ == cur.index;
+  if (spec_valid_ && !spec) {   // launched for another pair of frames (cannot happen in order): drain it, do not use it
+    if (wait_flag(&h_flag_lk_[1], seq_sp_, s_pt_, &t_err)) return FE_CUDA_ERROR;
+  }
+  if (!spec) spec_n_ = 0;
+  spec_valid_ = false;
+  // candidate tracks of the previous frame into this one were issued when this frame was submitted (track_candidates)
+  const bool spec_cand = cur.sc_prev >= 0 && cur.sc_prev == klt_last_slot_;
+  auto resolve = [&](std::vector<int> &src, bool have_cand) {   // candidate codes -(2 + table slot) -> kCandBase + slot
+    for (int &v : src)
+      if (v <= -2) v = have_cand ? kCandBase + (-(v + 2)) : -1;
+  };
   // TrackKLT.cpp:110-123 — nothing tracked last time: detect on the CURRENT image only
   if (pts_last_.empty() || klt_last_slot_ < 0) {
+    if (spec_n_ > 0 && wait_flag(&h_flag_lk_[1], seq_sp_, s_pt_, &t_err)) return FE_CUDA_ERROR;
     std::vector<Pt> good;
     std::vector<uint64_t> good_ids;
-    int rc = perform_detection(cur, good, good_ids, res);
+    std::vector<int> src;
+    int rc = perform_detection(cur, good, good_ids, src, res);
     if (rc) return rc;
     pts_last_ = good;
     ids_last_ = good_ids;
     info->first_frame = 1;
+    // the new points are candidates of THIS frame: track them into the next one right away
+    resolve(src, true);   // candidates of THIS frame; whether they were tracked into the next one is checked there
+    last_src_ = src;
     return FE_OK;
   }
   FrameSlot &last = slots_[klt_last_slot_];
   // top-off on the PREVIOUS image with the previous points (:127-130)
   std::vector<Pt> pts_old = pts_last_;
   std::vector<uint64_t> ids_old = ids_last_;
-  int rc = perform_detection(last, pts_old, ids_old, res);
+  std::vector<int> src_old = last_src_;
+  src_old.resize(pts_old.size(), -1);
+  if (!spec) std::fill(src_old.begin(), src_old.end(), -1);
+  int rc = perform_detection(last, pts_old, ids_old, src_old, res);
   if (rc) return rc;
+  resolve(src_old, spec_cand);
   std::vector<Pt> pts_new = pts_old;
   std::vector<uint8_t> mask_ll;
   bool mask_empty = true;
-  rc = perform_matching(last, cur, pts_old, pts_new, mask_ll, mask_empty, res);
+  if (!spec_cand)
+    for (int &v : src_old)
+      if (v >= kCandBase) v = -1;
+  rc = perform_matching(last, cur, pts_old, src_old, spec || spec_cand, pts_new, mask_ll, mask_empty, res);
   if (rc) return rc;
   if (mask_empty) {  // :143-152
     pts_last_.clear();
     ids_last_.clear();
+    last_src_.clear();
     info->reset = 1;
     return FE_OK;
   }
   std::vector<Pt> good;
   std::vector<uint64_t> good_ids;
+  std::vector<int> good_src;
   good.reserve(pts_new.size());
   good_ids.reserve(pts_new.size());
+  good_src.reserve(pts_new.size());
   for (size_t i = 0; i < pts_new.size(); i++) {  // :159-173
     const Pt &p = pts_new[i];
     if (p.x < 0 || p.y < 0 || (int)p.x >= W_ || (int)p.y >= H_) continue;
@@ -879,23 +977,80 @@ int FeContext::klt_feed(FrameSlot &cur) {
     if (mask_ll[i]) {
       good.push_back(p);
       good_ids.push_back(ids_old[i]);
+      good_src.push_back(i < spec_of_lk_.size() ? spec_of_lk_[i] : -1);
       // :176-179 — undistort_cv(pt) of the tracked point is exactly the p1n the LK epilogue produced
       FePointRow r;
       r.id = ids_old[i];
       r.u = p.x;
       r.v = p.y;
-      r.un = h_p1n_[i].x;
-      r.vn = h_p1n_[i].y;
+      r.un = a_p1n_[i].x;
+      r.vn = a_p1n_[i].y;
       point_rows.push_back(r);
     }
   }
   pts_last_ = good;
   ids_last_ = good_ids;
+  last_src_ = good_src;
   return FE_OK;
 }
 
+// Speculative tracking.  LK treats every point on its own, so the tracks of frame t+1 do not depend on WHICH points
+// survive frame t's RANSAC gate, bounds / mask filter and top-off detection — only their positions matter, and every
+// point that can possibly be tracked into t+1 is known the moment frame t's LK finishes: the points whose KLT status is
+// good, and the refined corner candidates of frame t (the top-off detection can only add those).  So LK(t -> t+1) is
+// launched for that superset BEFORE frame t's RANSAC runs, and the host work of frame t (RANSAC, rows, next frame's
+// detection glue) overlaps the GPU's tracking instead of waiting for it.  Frame t+1 then picks its points' results out
+// of the speculative arrays by index; a point without a speculative result (no next frame was queued yet, or the layout
+// changed) goes through an ordinary launch.  Results are bit-identical either way.
+int FeContext::speculate(FrameSlot &prev, const float2 *lk_pts, const uint8_t *lk_status, int n) {
+  HostTimer hs(&kst_.host_ms[8]);
+  spec_of_lk_.assign((size_t)n, -1);
+  if (!use_spec_ || cfg_.line_samples > 0) return FE_OK;
+  int nxt = -1;
+  if (!klt_q_.peek(&nxt)) return FE_OK;          // the next frame has not been submitted yet
+  FrameSlot &fn = slots_[nxt];
+  LkParams prm;
+  prm.win = cfg_.win_size;
+  prm.max_level = cfg_.pyr_levels;
+  prm.max_count = 30;
+  prm.eps_sq = 0.01f * 0.01f;
+  prm.min_eig = 1e-4f;
+  prm.undistort = 1;
+  for (int i = 0; i < 4; i++) { prm.K[i] = fn.K[i]; prm.D[i] = fn.D[i]; }
+  // ---- (A) the points tracked into `prev` whose KLT status is good: latency-critical stream
+  int k = 0;
+  for (int i = 0; i < n && k < max_pts_; i++)
+    if (lk_status[i]) {
+      h_sp_pts0_[k] = lk_pts[i];
+      spec_of_lk_[(size_t)i] = k++;
+    }
+  spec_n_ = k;
+  spec_timed_ = false;
+  if (k > 0) {
+    HostTimer h11(&kst_.host_ms[11]);
+    FE_CUDA(cudaStreamWaitEvent(s_pt_, fn.ev_pyr, 0));
+    spec_timed_ = fn.timed;
+    if (spec_timed_) cudaEventRecord(ev_pt_[2], s_pt_);
+    const bool flow0 = lk_table_mode_ok(prm, prev.pyr.n);   // pts1 = pts0 is implicit for the 15 x 15 kernel
+    if (!flow0) std::memcpy(h_sp_pts1_, h_sp_pts0_, (size_t)k * sizeof(float2));
+    const bool self_signal = launch_lk(prev.pyr, fn.pyr, h_sp_pts0_, h_sp_pts1_, h_sp_status_, h_sp_p0n_, h_sp_p1n_, k, prm, s_pt_,
+                                       &h_flag_lk_[1], ++seq_sp_, d_lk_done_ + 1, nullptr, 0, flow0);
+    if (spec_timed_) cudaEventRecord(ev_pt_[3], s_pt_);
+    if (!self_signal) launch_signal(&h_flag_lk_[1], seq_sp_, s_pt_);
+    FE_CUDA(cudaGetLastError());
+    kst_.kernel_launches_total++;
+    kst_.h2d_bytes += (size_t)k * sizeof(float2);
+    kst_.d2h_bytes += (size_t)k * (3 * sizeof(float2) + 1);
+  }
+  spec_valid_ = k > 0;
+  spec_prev_slot_ = prev.index;
+  spec_next_slot_ = nxt;
+  return FE_OK;
+}
 
-int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, std::vector<uint64_t> &ids0, FrameResult &res) {
+int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, std::vector<uint64_t> &ids0, std::vector<int> &src,
+                                 FrameResult &res) {
+  src.resize(pts0.size(), -1);   // per point: index into the speculative LK arrays, -1 none, -(2 + i) = candidate i
   HostTimer ht(&kst_.host_ms[1]);
   FeFrameInfo *info = &res.info;
   std::vector<int32_t> &tap_fast_ = res.tap_fast;
@@ -930,10 +1085,12 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
       if (x - d >= 0 && x + d < cols && y - d >= 0 && y + d < rows) rects.emplace_back(x, y);
       pts0[keep] = kp;
       ids0[keep] = ids0[k];
+      src[keep] = src[k];
       keep++;
     }
     pts0.resize(keep);
     ids0.resize(keep);
+    src.resize(keep);
   }
   const double min_feat_percent = 0.50;
   int num_featsneeded = cfg_.num_features - (int)pts0.size();
@@ -964,6 +1121,7 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
   // and cornerSubPix do not depend on tracker state and were computed for EVERY cell when the frame was submitted
   // (run_predetection); only the state-dependent part is left: which cells are valid and the mask test (:140-147).
   std::vector<Pt> ext;  // pts0_ext after sub-pixel refinement
+  std::vector<int> ext_cand;   // ... and which candidate of the frame's table each one is
   if (taps) {
     tap_fast_.clear();
     tap_subpix_.clear();
@@ -978,6 +1136,7 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
       rc = record_fast_path(slot, slot.s_b);
       if (rc) return rc;
       slot.seq_fast++;
+      FE_CUDA(cudaEventRecord(slot.ev_fast, slot.s_b));
     }
     {
       HostTimer hw(&kst_.host_ms[7]);
@@ -1022,6 +1181,7 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
           if (iy >= rows || ix >= cols) continue;  // the reference would read out of bounds here; cannot happen
           if ((occ_bits_[(size_t)iy * bw + (ix >> 6)] >> (ix & 63)) & 1ull) continue;
           ext.push_back(slot.cand_ref[i]);      // cornerSubPix result of exactly this point (:163-179)
+          ext_cand.push_back(c * slot.predet_nfg + (i - slot.cell_first[c]));
           if (taps) tap_subpix_.insert(tap_subpix_.end(), {p.x, p.y, slot.cand_ref[i].x, slot.cand_ref[i].y});
         }
       }
@@ -1029,21 +1189,23 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
   }
   // reject new points that are close to an existing one (:497-512), then hand out ids (:519-527)
   int added = 0;
-  for (const Pt &kp : ext) {
+  for (size_t e = 0; e < ext.size(); e++) {
+    const Pt &kp = ext[e];
     int x_grid = (int)(kp.x / (float)d), y_grid = (int)(kp.y / (float)d);
     if (x_grid < 0 || x_grid >= close_w || y_grid < 0 || y_grid >= close_h) continue;
     if (grid_close[(size_t)y_grid * close_w + x_grid] > 127) continue;
     grid_close[(size_t)y_grid * close_w + x_grid] = 255;
     pts0.push_back(kp);
     ids0.push_back(++currid_);
+    src.push_back(-(2 + ext_cand[e]));   // slot of the candidate in the frame's fixed-stride table
     added++;
   }
   info->n_detected += added;
   return FE_OK;
 }
 
-int FeContext::perform_matching(const FrameSlot &f0, const FrameSlot &f1, std::vector<Pt> &pts0, std::vector<Pt> &pts1,
-                                std::vector<uint8_t> &mask_out, bool &mask_empty, FrameResult &res) {
+int FeContext::perform_matching(const FrameSlot &f0, FrameSlot &f1, std::vector<Pt> &pts0, const std::vector<int> &src, bool spec,
+                                std::vector<Pt> &pts1, std::vector<uint8_t> &mask_out, bool &mask_empty, FrameResult &res) {
   HostTimer ht(&kst_.host_ms[2]);
   FeFrameInfo *info = &res.info;
   std::vector<float> &tap_lk_ = res.tap_lk, &sample_uv = res.sample_uv;
@@ -1052,31 +1214,55 @@ int FeContext::perform_matching(const FrameSlot &f0, const FrameSlot &f1, std::v
   const bool timing = f1.timed;
   mask_out.clear();
   mask_empty = true;
+  spec_of_lk_.clear();
   const int n = (int)pts0.size();
-  if (n == 0) return FE_OK;                  // :836-837 (mask stays empty => caller resets)
-  mask_empty = false;
-  if (n < 10) {                              // :848-852
-    mask_out.assign(n, 0);
+  if (n == 0 || n < 10) {
+    // the speculative launch (if any) is not used: let it finish before its buffers are reused
+    if (spec_n_ > 0 && wait_flag(&h_flag_lk_[1], seq_sp_, s_pt_, &t_err)) return FE_CUDA_ERROR;
+    if (n == 0) return FE_OK;                // :836-837 (mask stays empty => caller resets)
+    mask_empty = false;
+    mask_out.assign(n, 0);                   // :848-852
     return FE_OK;
   }
-  // extension: samples along last frame's segments ride in the same LK launch (not part of the RANSAC gate)
+  mask_empty = false;
+  if (n > max_pts_) return err(FE_INTERNAL, "perform_matching: more points than the tracking buffers hold");
+  a_pts1_.resize(n);
+  a_status_.resize(n);
+  a_p0n_.resize(n);
+  a_p1n_.resize(n);
+  // points without a speculative result go through an ordinary launch (compact arrays; lk2_[k] = point index)
+  lk2_.clear();
+  bool need_a = false, need_b = false;
+  for (int i = 0; i < n; i++) {
+    const int v = spec ? src[i] : -1;
+    if (v >= kCandBase && v - kCandBase < f1.sc_ntab) need_b = true;
+    else if (v >= 0 && v < spec_n_) need_a = true;
+    else lk2_.push_back(i);
+  }
+  const int n2 = (int)lk2_.size();
+  // extension: samples along last frame's segments ride in the same launch (not part of the RANSAC gate)
   int ns = 0;
-  if (cfg_.line_samples > 0 && !lines_last_.empty()) {
+  if (cfg_.line_samples > 0) {
+    // the segments belong to the line tracker's thread: wait until it is done with the previous frame
+    for (unsigned spins = 0; f0.stage.load(std::memory_order_acquire) == 2; spins++) {
+      if (spins < 4000) cpu_pause();
+      else std::this_thread::yield();
+    }
     const int S = cfg_.line_samples;
     for (const float4 &l : lines_last_) {
-      for (int k = 0; k < S && n + ns < max_pts_; k++) {
+      for (int k = 0; k < S && n2 + ns < max_pts_; k++) {
         float a = S > 1 ? (float)k / (float)(S - 1) : 0.5f;
-        h_pts0_[n + ns] = make_float2(l.x + (l.z - l.x) * a, l.y + (l.w - l.y) * a);
+        h_pts0_[n2 + ns] = make_float2(l.x + (l.z - l.x) * a, l.y + (l.w - l.y) * a);
         ns++;
       }
     }
   }
-  const int nt = std::min(n, max_pts_) + ns;
-  for (int i = 0; i < n && i < max_pts_; i++) {
-    h_pts0_[i] = make_float2(pts0[i].x, pts0[i].y);
-    h_pts1_[i] = h_pts0_[i];   // OPTFLOW_USE_INITIAL_FLOW with pts1 = pts0 (:134-138)
+  const int nt = n2 + ns;
+  for (int k = 0; k < n2; k++) {
+    h_pts0_[k] = make_float2(pts0[lk2_[k]].x, pts0[lk2_[k]].y);
+    h_pts1_[k] = h_pts0_[k];   // OPTFLOW_USE_INITIAL_FLOW with pts1 = pts0 (:134-138)
   }
-  for (int k = 0; k < ns; k++) h_pts1_[n + k] = h_pts0_[n + k];
+  for (int k = 0; k < ns; k++) h_pts1_[n2 + k] = h_pts0_[n2 + k];
   LkParams prm;
   prm.win = cfg_.win_size;
   prm.max_level = cfg_.pyr_levels;
@@ -1087,26 +1273,68 @@ int FeContext::perform_matching(const FrameSlot &f0, const FrameSlot &f1, std::v
   for (int i = 0; i < 4; i++) { prm.K[i] = f1.K[i]; prm.D[i] = f1.D[i]; }
   // The feature arrays are a few KB: the kernel reads and writes them in pinned, device-mapped host memory directly
   // (no copy-engine operation queued behind the next frame's 700 KB upload, one synchronisation per frame).
-  kst_.h2d_bytes += (size_t)nt * 2 * sizeof(float2);
-  kst_.d2h_bytes += (size_t)nt * (3 * sizeof(float2) + 1);
-  if (timing) cudaEventRecord(ev_pt_[4], s_pt_);
-  HostTimer *tl = new HostTimer(&kst_.host_ms[12]);
-  // the LK kernel publishes the completion sequence number itself (its last feature writes the pinned flag)
-  const bool self_signal = launch_lk(f0.pyr, f1.pyr, h_pts0_, h_pts1_, h_status_, h_p0n_, h_p1n_, nt, prm, s_pt_, h_flag_lk_,
-                                     ++seq_lk_, d_lk_done_);
-  kst_.kernel_launches_total++;
-  if (timing) cudaEventRecord(ev_pt_[5], s_pt_);
-  if (!self_signal) launch_signal(h_flag_lk_, seq_lk_, s_pt_);
-  FE_CUDA(cudaGetLastError());
-  delete tl;
+  if (nt > 0) {
+    kst_.h2d_bytes += (size_t)nt * 2 * sizeof(float2);
+    kst_.d2h_bytes += (size_t)nt * (3 * sizeof(float2) + 1);
+    if (timing) cudaEventRecord(ev_pt_[4], s_pt_);
+    HostTimer tl(&kst_.host_ms[12]);
+    // the LK kernel publishes the completion sequence number itself (its last feature writes the pinned flag)
+    const bool self_signal = launch_lk(f0.pyr, f1.pyr, h_pts0_, h_pts1_, h_status_, h_p0n_, h_p1n_, nt, prm, s_pt_, h_flag_lk_,
+                                       ++seq_lk_, d_lk_done_);
+    kst_.kernel_launches_total++;
+    if (timing) cudaEventRecord(ev_pt_[5], s_pt_);
+    if (!self_signal) launch_signal(h_flag_lk_, seq_lk_, s_pt_);
+    FE_CUDA(cudaGetLastError());
+  }
   {
     HostTimer tw(&kst_.host_ms[13]);
-    int rc = wait_flag(h_flag_lk_, seq_lk_, s_pt_, &t_err);
-    if (rc) return rc;
+    if (spec_n_ > 0 && wait_flag(&h_flag_lk_[1], seq_sp_, s_pt_, &t_err)) return FE_CUDA_ERROR;
+    if (need_b && wait_flag(&f1.h_flags[3], f1.seq_sc, f1.s_b, &t_err)) return FE_CUDA_ERROR;
+    if (nt > 0 && wait_flag(h_flag_lk_, seq_lk_, s_pt_, &t_err)) return FE_CUDA_ERROR;
   }
-  if (timing) {
+  (void)need_a;
+  if (timing && nt > 0) {
     FE_CUDA(cudaEventSynchronize(ev_pt_[5]));
     acc_time(kst_, FE_STAGE_LK, ev_pt_[4], ev_pt_[5]);
+  }
+  if (spec && spec_timed_) {
+    FE_CUDA(cudaEventSynchronize(ev_pt_[3]));
+    acc_time(kst_, FE_STAGE_LK, ev_pt_[2], ev_pt_[3]);
+  }
+  // assemble the per-point results in the reference's order
+  HostTimer *ha = new HostTimer(&kst_.host_ms[9]);
+  if (spec)
+    for (int i = 0; i < n; i++) {
+      const int k = src[i];
+      if (k >= kCandBase && k - kCandBase < f1.sc_ntab) {
+        const int j = k - kCandBase;
+        a_pts1_[i] = f1.h_sc_pts1[j];
+        a_status_[i] = f1.h_sc_status[j];
+        a_p0n_[i] = f1.h_sc_p0n[j];
+        a_p1n_[i] = f1.h_sc_p1n[j];
+      } else if (k >= 0 && k < spec_n_) {
+        a_pts1_[i] = h_sp_pts1_[k];
+        a_status_[i] = h_sp_status_[k];
+        a_p0n_[i] = h_sp_p0n_[k];
+        a_p1n_[i] = h_sp_p1n_[k];
+      }
+    }
+  for (int k = 0; k < n2; k++) {
+    const int i = lk2_[k];
+    a_pts1_[i] = h_pts1_[k];
+    a_status_[i] = h_status_[k];
+    a_p0n_[i] = h_p0n_[k];
+    a_p1n_[i] = h_p1n_[k];
+  }
+  for (int k = 0; k < ns; k++) {
+    sample_uv.insert(sample_uv.end(), {h_pts0_[n2 + k].x, h_pts0_[n2 + k].y, h_pts1_[n2 + k].x, h_pts1_[n2 + k].y});
+    sample_status.push_back(h_status_[n2 + k]);
+  }
+  delete ha;
+  // this frame's tracks are known: start tracking into the NEXT frame before the host-side gate below
+  {
+    int rc = speculate(f1, a_pts1_.data(), a_status_.data(), n);
+    if (rc) return rc;
   }
 
   // RANSAC gate on the normalised coordinates (:869-873)
@@ -1116,21 +1344,17 @@ int FeContext::perform_matching(const FrameSlot &f0, const FrameSlot &f1, std::v
   int n_in;
   {
     HostTimer hr(&kst_.host_ms[3]);
-    n_in = ransac_fundamental(reinterpret_cast<const float *>(h_p0n_), reinterpret_cast<const float *>(h_p1n_), n,
+    n_in = ransac_fundamental(reinterpret_cast<const float *>(a_p0n_.data()), reinterpret_cast<const float *>(a_p1n_.data()), n,
                               2.0 / max_focal, 0.999, mask_rsc.data(), &mask_valid);
   }
   mask_out.resize(n);
   int n_klt = 0;
   if (taps) tap_lk_.clear();
   for (int i = 0; i < n; i++) {  // :876-885
-    mask_out[i] = (h_status_[i] && mask_valid && mask_rsc[i]) ? 1 : 0;
-    n_klt += h_status_[i] ? 1 : 0;
-    pts1[i] = Pt{h_pts1_[i].x, h_pts1_[i].y};
-    if (taps) tap_lk_.insert(tap_lk_.end(), {pts0[i].x, pts0[i].y, pts1[i].x, pts1[i].y, (float)h_status_[i], (float)(mask_valid && mask_rsc[i])});
-  }
-  for (int k = 0; k < ns; k++) {
-    sample_uv.insert(sample_uv.end(), {h_pts0_[n + k].x, h_pts0_[n + k].y, h_pts1_[n + k].x, h_pts1_[n + k].y});
-    sample_status.push_back(h_status_[n + k]);
+    mask_out[i] = (a_status_[i] && mask_valid && mask_rsc[i]) ? 1 : 0;
+    n_klt += a_status_[i] ? 1 : 0;
+    pts1[i] = Pt{a_pts1_[i].x, a_pts1_[i].y};
+    if (taps) tap_lk_.insert(tap_lk_.end(), {pts0[i].x, pts0[i].y, pts1[i].x, pts1[i].y, (float)a_status_[i], (float)(mask_valid && mask_rsc[i])});
   }
   info->n_lk_in = n;
   info->n_klt_ok = n_klt;
@@ -1431,6 +1655,9 @@ int FeContext::set_state(const void *buf, size_t n_bytes) {
   last_slot_ = -1;
   klt_last_slot_ = -1;
   cur_slot_ = -1;
+  spec_valid_ = false;
+  prev_submit_slot_ = -1;
+  last_src_.clear();
   state_res_.clear();
   state_res_.obs = pts_last_;
   state_res_.obs_ids = ids_last_;
@@ -1453,6 +1680,7 @@ int FeContext::set_state(const void *buf, size_t n_bytes) {
       rc = record_fast_path(s, s.s_b);
       if (rc) return rc;
       s.seq_fast++;
+      FE_CUDA(cudaEventRecord(s.ev_fast, s.s_b));
     }
     if (hd.has_mask) {
       s.mask.resize((size_t)W_ * H_);
@@ -1462,6 +1690,7 @@ int FeContext::set_state(const void *buf, size_t n_bytes) {
     }
     last_slot_ = 0;
     klt_last_slot_ = 0;
+    prev_submit_slot_ = 0;
   }
   return FE_OK;
   }();

@@ -60,6 +60,7 @@ class WorkQueue {
  public:
   void push(int v);
   bool pop(int *v);   // false: stop requested and nothing left
+  bool peek(int *v);  // front element without taking it; false if empty
   void stop();
  private:
   std::mutex mu_;
@@ -111,6 +112,11 @@ struct FrameSlot {
   int *d_cand_cnt = nullptr, *h_cand_cnt = nullptr;
   unsigned *d_sort_scratch = nullptr;
   bool fast_taps = false;                 // the full corner lists were copied back too (debug taps)
+  // tracks of the PREVIOUS submitted frame's candidates into this frame (FeContext::track_candidates), by table slot
+  float2 *h_sc_pts1 = nullptr, *h_sc_p0n = nullptr, *h_sc_p1n = nullptr;   // pinned
+  uint8_t *h_sc_status = nullptr;
+  unsigned *d_sc_done = nullptr;
+  int sc_prev = -1, sc_ntab = 0, seq_sc = 0;   // slot whose candidates were tracked (-1: none); completion flag h_flags[3]
   cudaEvent_t ev_l0 = nullptr, ev_fast = nullptr;
   cudaEvent_t ev_fast_t[2] = {nullptr, nullptr};
   cudaEvent_t ev_sp_t[2] = {nullptr, nullptr};   // cornerSubPix stage timing
@@ -182,9 +188,12 @@ class FeContext {
   int wait_predetection(FrameSlot &s);
   // TrackKLT
   int klt_feed(FrameSlot &cur);
-  int perform_detection(const FrameSlot &img, std::vector<Pt> &pts, std::vector<uint64_t> &ids, FrameResult &res);
-  int perform_matching(const FrameSlot &f0, const FrameSlot &f1, std::vector<Pt> &pts0, std::vector<Pt> &pts1,
-                       std::vector<uint8_t> &mask_out, bool &mask_empty, FrameResult &res);
+  int perform_detection(const FrameSlot &img, std::vector<Pt> &pts, std::vector<uint64_t> &ids, std::vector<int> &src,
+                        FrameResult &res);
+  int perform_matching(const FrameSlot &f0, FrameSlot &f1, std::vector<Pt> &pts0, const std::vector<int> &src, bool spec,
+                       std::vector<Pt> &pts1, std::vector<uint8_t> &mask_out, bool &mask_empty, FrameResult &res);
+  int speculate(FrameSlot &prev, const float2 *lk_pts, const uint8_t *lk_status, int n);
+  int track_candidates(FrameSlot &prev, FrameSlot &s);
   // TrackLSD
   int lsd_feed(FrameSlot &cur);
   static void undistort_host(const double K[4], const double D[4], float u, float v, float &un, float &vn);
@@ -234,7 +243,22 @@ class FeContext {
   int max_pts_ = 0;
   float2 *d_pts0_ = nullptr, *d_pts1_ = nullptr, *d_p0n_ = nullptr, *d_p1n_ = nullptr;
   uint8_t *d_status_ = nullptr;
-  unsigned *d_lk_done_ = nullptr;   // features finished in the running LK launch (completion signal)
+  unsigned *d_lk_done_ = nullptr;   // features finished in the running LK launches (completion signals) [ordinary, speculative]
+  // ---- speculative tracking (FeContext::speculate): LK(t -> t+1) for every point that may be tracked, launched before
+  // frame t's RANSAC gate
+  float2 *h_sp_pts0_ = nullptr, *h_sp_pts1_ = nullptr, *h_sp_p0n_ = nullptr, *h_sp_p1n_ = nullptr;   // pinned
+  uint8_t *h_sp_status_ = nullptr;
+  static constexpr int kCandBase = 1 << 24;   // src >= kCandBase: result of candidate table slot (src - kCandBase)
+  int prev_submit_slot_ = -1;                 // caller's thread: slot of the frame submitted last
+  int spec_n_ = 0, seq_sp_ = 0;
+  bool use_spec_cand_ = true;
+  int spec_prev_slot_ = -1, spec_next_slot_ = -1;
+  bool spec_valid_ = false, spec_timed_ = false, use_spec_ = true;
+  std::vector<int> spec_of_lk_;     // per point of this frame's LK arrays: its index in the speculative launch, or -1
+  std::vector<int> last_src_;       // parallel to pts_last_: the same for the surviving points
+  std::vector<int> lk2_;            // points that go through the ordinary launch
+  std::vector<float2> a_pts1_, a_p0n_, a_p1n_;   // this frame's tracking results in the reference's order
+  std::vector<uint8_t> a_status_;
   float2 *h_pts0_ = nullptr, *h_pts1_ = nullptr, *h_p0n_ = nullptr, *h_p1n_ = nullptr;
   uint8_t *h_status_ = nullptr;
   cudaEvent_t ev_pt_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -77,7 +77,12 @@ struct LkParams {
 // the caller has to queue its own completion signal (generic-window kernel).
 bool launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *d_pts0, float2 *d_pts1, uint8_t *d_status,
                float2 *d_p0n, float2 *d_p1n, int n, const LkParams &prm, cudaStream_t s, int *host_flag = nullptr,
-               int flag_value = 0, unsigned *d_done_counter = nullptr);
+               int flag_value = 0, unsigned *d_done_counter = nullptr, const int *d_tab_cnt = nullptr, int tab_stride = 0,
+               bool flow_is_zero = false, const unsigned *cell_mask = nullptr);
+// table mode (15 x 15 window, <= 6 pyramid images only — lk_table_mode_ok): d_pts0 is a fixed-stride candidate table (slot i
+// belongs to cell i / tab_stride, live iff i % tab_stride < d_tab_cnt[cell]); flow_is_zero: the initial guess is the
+// previous position, d_pts1 is written only; cell_mask (8 words, optional): only cells whose bit is set are tracked.
+bool lk_table_mode_ok(const LkParams &prm, int pyramid_images);
 void launch_undistort(const float2 *d_pts, float2 *d_out, int n, const double K[4], const double D[4], cudaStream_t s);
 
 // ---- lines (kernels_lines.cu) -------------------------------------------------------------------------------

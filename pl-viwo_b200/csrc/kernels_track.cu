@@ -8,6 +8,7 @@
 //   CamRadtan::undistort_f -> cv::undistortPoints (one Mat per point)               cam/CamRadtan.h:99-120
 #include "fe_kernels.h"
 
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -182,6 +183,8 @@ struct LkArgs {
   const uint8_t *p1[kMaxLevels];
   int w[kMaxLevels], h[kMaxLevels], pitch0[kMaxLevels], pitch1[kMaxLevels];
   int win, max_level, max_count, undistort;
+  int flow_is_zero;   // the initial guess is the previous position itself: pts1 is output only
+  unsigned cell_mask[8];   // table mode: cells whose candidates are tracked at all (bit c of word c / 32)
   float eps_sq, min_eig;
   CalibArgs calib;
 };
@@ -388,7 +391,8 @@ constexpr int kJR = kJSpan + 2 * kJMargin;   // 25
 
 __global__ void __launch_bounds__(kLk15MaxLevels * 32)
     k_lk15(LkArgs a, const float2 *__restrict__ pts0, float2 *__restrict__ pts1, uint8_t *__restrict__ status,
-           float2 *__restrict__ p0n, float2 *__restrict__ p1n, int n, int *host_flag, int flag_value, unsigned *done_counter) {
+           float2 *__restrict__ p0n, float2 *__restrict__ p1n, int n, int *host_flag, int flag_value, unsigned *done_counter,
+           const int *__restrict__ tab_cnt, int tab_stride) {
   constexpr int win = kW15, np = win + 3, nd = win + 1;
   constexpr int kRawLoads = (np * np + 31) / 32;   // 11
   __shared__ uint8_t raw_s[kLk15MaxLevels][np * np + 12];
@@ -400,6 +404,18 @@ __global__ void __launch_bounds__(kLk15MaxLevels * 32)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pi = blockIdx.x;
   const int r0 = (lane >> 2) * 2, c0 = (lane & 3) * 4;
+  if (tab_cnt != nullptr) {   // pts0 is a fixed-stride table (cell c at c * stride, tab_cnt[c] live entries)
+    const int cell = pi / tab_stride;
+    const bool cell_on = cell < 256 && ((a.cell_mask[cell >> 5] >> (cell & 31)) & 1u);
+    if (!cell_on || pi - cell * tab_stride >= tab_cnt[cell]) {   // dead slot: only the completion count
+      if (threadIdx.x == 0 && host_flag != nullptr && atomicAdd(done_counter, 1u) == (unsigned)n - 1u) {
+        *done_counter = 0;
+        __threadfence_system();
+        *reinterpret_cast<volatile int *>(host_flag) = flag_value;
+      }
+      return;
+    }
+  }
   const float2 prev_in = pts0[pi];
   const float half = (win - 1) * 0.5f;
   const float FLT_SCALE = 1.f / (1 << 20);
@@ -489,7 +505,7 @@ __global__ void __launch_bounds__(kLk15MaxLevels * 32)
   if (warp != 0) return;
 
   // ---- the iteration chain (warp 0)
-  float2 next = pts1[pi];   // OPTFLOW_USE_INITIAL_FLOW
+  float2 next = a.flow_is_zero ? prev_in : pts1[pi];   // OPTFLOW_USE_INITIAL_FLOW
   bool ok = true;
 #pragma unroll 1
   for (int level = a.max_level; level >= 0; level--) {
@@ -626,9 +642,13 @@ __global__ void __launch_bounds__(kLk15MaxLevels * 32)
   }
 }
 
+bool lk_table_mode_ok(const LkParams &prm, int pyramid_images) {
+  return prm.win == kW15 && std::min(prm.max_level + 1, pyramid_images) <= kLk15MaxLevels;
+}
+
 bool launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *d_pts0, float2 *d_pts1, uint8_t *d_status,
                float2 *d_p0n, float2 *d_p1n, int n, const LkParams &prm, cudaStream_t s, int *host_flag, int flag_value,
-               unsigned *d_done_counter) {
+               unsigned *d_done_counter, const int *d_tab_cnt, int tab_stride, bool flow_is_zero, const unsigned *cell_mask) {
   if (n <= 0) return false;
   LkArgs a;
   int levels = prm.max_level + 1;
@@ -647,11 +667,15 @@ bool launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *d_pts0, f
   a.eps_sq = prm.eps_sq;
   a.min_eig = prm.min_eig;
   a.undistort = prm.undistort;
+  a.flow_is_zero = flow_is_zero ? 1 : 0;
+  for (int i = 0; i < 8; i++) a.cell_mask[i] = cell_mask ? cell_mask[i] : 0xffffffffu;
   for (int i = 0; i < 4; i++) { a.calib.K[i] = prm.K[i]; a.calib.D[i] = prm.D[i]; }
   if (prm.win == kW15 && levels <= kLk15MaxLevels) {   // one CTA per feature, one warp per level
-    k_lk15<<<n, levels * 32, 0, s>>>(a, d_pts0, d_pts1, d_status, d_p0n, d_p1n, n, host_flag, flag_value, d_done_counter);
+    k_lk15<<<n, levels * 32, 0, s>>>(a, d_pts0, d_pts1, d_status, d_p0n, d_p1n, n, host_flag, flag_value, d_done_counter,
+                                     d_tab_cnt, tab_stride);
     return host_flag != nullptr;
   }
+  if (d_tab_cnt != nullptr || flow_is_zero) return false;   // table mode exists for the 15 x 15 kernel only (caller checks)
   const int win = prm.win, np = win + 3, nd = win + 1, nw = win * win;
   const int per_warp = ((np * np + 15) & ~15) + 2 * ((nd * nd * 2 + 15) & ~15) + 3 * ((nw * 2 + 15) & ~15);
   size_t smem = (size_t)per_warp * kLkWarps;

@@ -419,3 +419,36 @@ def test_downsample_prestep(fe, synth, size, lines):
             assert _compare_lines(lrows, lpts, lrow_o), t
     assert worst < 0.05, worst
     gpu.close()
+
+
+@pytest.mark.parametrize("kw,lookahead", [(CFG2, 6), (CFG_KAIST, 3)])
+def test_speculative_tracking_equals_synchronous(fe, synth, kw, lookahead, monkeypatch):
+    """With frames queued ahead and PLVIWO_SPECULATION=1, LK(t -> t+1) is launched speculatively for every trackable
+    point before frame t's RANSAC gate (FeContext::speculate, track_candidates).  Rows, ids and line rows must be
+    IDENTICAL (bitwise) to feeding frame by frame, where nothing is speculated, over a sequence long enough to contain
+    detections, losses and occluders."""
+    monkeypatch.setenv("PLVIWO_SPECULATION", "1")
+    n = 40
+    seq = synth.SynthSequence(seed=1015, n_frames=n)
+    cfg = dict(width=1280, height=560, K=seq.K, D=seq.D, **kw)
+    frames = [seq.frame(t) for t in range(n)]
+    a = fe.FrontEnd(fe.default_config(lookahead=0, **cfg))
+    ref = []
+    for t in range(n):
+        a.feed_new_camera(seq.timestamp(t), frames[t], None, seq.vanishing_points(t), update_db=False)
+        ref.append((a.point_rows().copy(), a.line_rows()[0].copy(), a.get_last_ids().copy()))
+    a.close()
+    b = fe.FrontEnd(fe.default_config(lookahead=lookahead, **cfg))
+    sub = 0
+    n_spec_rows = 0
+    for t in range(n):
+        while sub < n and sub <= t + lookahead:
+            b.submit(seq.timestamp(sub), frames[sub], vanishing_points=seq.vanishing_points(sub))
+            sub += 1
+        b.collect()
+        assert np.array_equal(b.point_rows(), ref[t][0]), t
+        assert np.array_equal(b.line_rows()[0], ref[t][1]), t
+        assert np.array_equal(b.get_last_ids(), ref[t][2]), t
+        n_spec_rows += len(ref[t][0])
+    assert n_spec_rows > 20 * 100
+    b.close()
