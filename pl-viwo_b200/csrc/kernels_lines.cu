@@ -531,10 +531,16 @@ __device__ __forceinline__ void fs_line(const FitSums &s, double l[3]) {
   l[1] = a[2] * b[0] - a[0] * b[2];
   l[2] = a[0] * b[1] - a[1] * b[0];
 }
+// distPointLine of the reference normalises the line IN PLACE on every call.  After the first call the norm is 1 up to
+// rounding; when x * x + y * y is exactly 1.0 the square root is exactly 1 and the three divisions are identities, so
+// they are skipped (bit-exact shortcut: a double-precision sqrt and three divisions per chain point otherwise).
 __device__ __forceinline__ double dist_point_line(double px, double py, double l[3]) {
   double x = l[0], y = l[1];
-  double w = sqrt(x * x + y * y);
-  l[0] = x / w; l[1] = y / w; l[2] = l[2] / w;
+  double n2 = x * x + y * y;
+  if (n2 != 1.0) {
+    double w = sqrt(n2);
+    l[0] = x / w; l[1] = y / w; l[2] = l[2] / w;
+  }
   return l[0] * px + l[1] * py + l[2];
 }
 __device__ __forceinline__ void incident_point(const double l[3], float &px, float &py, int W, int H) {

@@ -585,28 +585,40 @@ __global__ void __launch_bounds__(kLk15MaxLevels * 32)
 #pragma unroll
           for (int c = 0; c < 5; c++) jb[r][c] = Jp[r * kJR + c];
       }
-      float b1 = 0, b2 = 0;
+      // mismatch vector b = sum over the window of diff * (Ix, Iy).  Every term is an integer, so the sum is formed
+      // EXACTLY: per-lane int32 sums (8 terms of at most 8160 * 4080 each), then two hardware warp reductions per
+      // component on the 16-bit halves (the 32-lane total needs 34 bits), one rounding to float at the end.  OpenCV
+      // accumulates the same integers in float32 (order depends on its SIMD width); this is that sum without the
+      // accumulated rounding error, and a third of the latency of a shuffle tree.
+      int sb1 = 0, sb2 = 0;
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const int r = k >> 2, c = k & 3;
         const int jv = (jb[r][c] * jw00 + jb[r][c + 1] * jw01 + jb[r + 1][c] * jw10 + jb[r + 1][c + 1] * jw11 + (1 << 8)) >> 9;
         const int diff = jv - Iw[k];
-        b1 += (float)(diff * Ixw[k]);
-        b2 += (float)(diff * Iyw[k]);
+        sb1 += diff * Ixw[k];
+        sb2 += diff * Iyw[k];
       }
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        b1 += __shfl_xor_sync(0xffffffffu, b1, d);
-        b2 += __shfl_xor_sync(0xffffffffu, b2, d);
-      }
-      b1 *= FLT_SCALE;
-      b2 *= FLT_SCALE;
+      const int b1h = __reduce_add_sync(0xffffffffu, sb1 >> 16), b1l = __reduce_add_sync(0xffffffffu, sb1 & 0xffff);
+      const int b2h = __reduce_add_sync(0xffffffffu, sb2 >> 16), b2l = __reduce_add_sync(0xffffffffu, sb2 & 0xffff);
+      const float b1 = (float)(((long long)b1h << 16) + b1l) * FLT_SCALE;
+      const float b2 = (float)(((long long)b2h << 16) + b2l) * FLT_SCALE;
       const float2 delta = make_float2((A12 * b2 - A22 * b1) * Dt, (A12 * b1 - A11 * b2) * Dt);
       next.x += delta.x;
       next.y += delta.y;
       result = make_float2(next.x + half, next.y + half);
-      if ((double)delta.x * (double)delta.x + (double)delta.y * (double)delta.y <= (double)a.eps_sq) break;
-      if (j > 0 && fabs((double)(delta.x + prevDelta.x)) < 0.01 && fabs((double)(delta.y + prevDelta.y)) < 0.01) {
+      // delta.dot(delta) <= epsilon in double, decided in float whenever the float value is not within rounding distance
+      // of the threshold (the double expression is evaluated only then: same decision, no fp64 on the common path)
+      {
+        const float d2 = delta.x * delta.x + delta.y * delta.y;
+        bool stop;
+        if (d2 < a.eps_sq * 0.999999f) stop = true;
+        else if (d2 > a.eps_sq * 1.000001f) stop = false;
+        else stop = (double)delta.x * (double)delta.x + (double)delta.y * (double)delta.y <= (double)a.eps_sq;
+        if (stop) break;
+      }
+      // |float| < 0.01 (a double constant): 0.01f is the largest float below 0.01, so this is |float| <= 0.01f
+      if (j > 0 && fabsf(delta.x + prevDelta.x) <= 0.01f && fabsf(delta.y + prevDelta.y) <= 0.01f) {
         result.x -= delta.x * 0.5f;
         result.y -= delta.y * 0.5f;
         break;
