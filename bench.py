@@ -397,6 +397,20 @@ def main():
                                       if not k.startswith("unused")},
                 "whole_frame": {"algorithmic_bytes": ab["frame_total"],
                                 "achieved_GBps": ab["frame_total"] * (total_frames / (ms * 1e-3)) / 1e9 / world}}
+    # what the image-domain kernels reach when ONE launch carries a batch of frames' worth of pixels (134 MB > L2) instead
+    # of one 0.7 MB frame: same kernels, device-resident synthetic image, CUDA events around single launches
+    at_scale = None
+    try:
+        AW, AH = 16384, 8192
+        t = fe_mod.op_image_kernels_time(AW, AH, 5, device=dev)
+        NA = AW * AH
+        bytes_ = {"hist": NA, "eq_pyr1": NA + NA + NA // 4 + NA // 4, "fast": NA, "canny": NA // 4 + NA // 4}
+        at_scale = {"image": "%dx%d (= %.0f frames of 1280x560 per launch)" % (AW, AH, NA / (1280 * 560.0)),
+                    "kernels": {k: {"ms": t[k], "algorithmic_bytes": bytes_[k], "GBps": bytes_[k] / (t[k] * 1e-3) / 1e9,
+                                    "frac": bytes_[k] / (t[k] * 1e-3) / 1e9 / peak} for k in t if t[k] > 0}}
+    except Exception as e:   # never fatal for the bench line
+        at_scale = {"error": str(e)}
+    roofline["at_scale"] = at_scale
     cpu = None
     if not args.no_cpu_baseline:
         r = run_cpu(seq, frames, args.cpu_sample, 10)

@@ -234,6 +234,12 @@ int plviwo_op_undistort(int device, const float *pts, int n, const double K[4], 
 int plviwo_op_canny_half(int device, const uint8_t *img, int w, int h, float th, uint8_t *edges /* w*h bytes */);
 int plviwo_op_fld(int device, const uint8_t *img, int w, int h, int length_threshold, float distance_threshold,
                   float canny_th, float *lines /* 4 per segment */, int cap, int *n_out);
+/* Micro-benchmark of the image-domain kernels on a DEVICE-resident synthetic image of any size (w, h multiples of 4):
+ * equalise + pyramid level 1 + half image (k_hist, k_eq_pyr1), FAST over one grid of cells, Canny of the half image.
+ * Each kernel is timed alone with CUDA events over `iters` launches after 3 warm-up launches; ms[0..3] = hist, eq_pyr1,
+ * fast, canny (mean per launch).  Used by bench.py to report what the kernels reach when a launch carries enough
+ * bytes (a batch of frames' worth) instead of one 0.7 MB frame. */
+int plviwo_op_image_kernels_time(int device, int w, int h, int iters, float ms[4]);
 int plviwo_op_ransac_fundamental(const float *p0n, const float *p1n, int n, double threshold, double confidence,
                                  uint8_t *mask, int *n_inliers); /* host-side sequential step (K9) */
 

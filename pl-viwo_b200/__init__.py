@@ -92,7 +92,7 @@ EXPORTS = [
     "plviwo_fe_get_line_rows", "plviwo_fe_get_line_points", "plviwo_fe_get_line_samples", "plviwo_fe_get_state",
     "plviwo_fe_set_state", "plviwo_fe_enable_taps", "plviwo_fe_tap", "plviwo_fe_enable_timing", "plviwo_fe_get_stage_times",
     "plviwo_op_equalize_pyramid", "plviwo_op_clahe", "plviwo_op_fast_cell", "plviwo_op_sort_corners", "plviwo_op_corner_subpix", "plviwo_op_lk", "plviwo_op_undistort",
-    "plviwo_op_canny_half", "plviwo_op_fld", "plviwo_op_ransac_fundamental",
+    "plviwo_op_canny_half", "plviwo_op_fld", "plviwo_op_image_kernels_time", "plviwo_op_ransac_fundamental",
 ]
 
 
@@ -143,6 +143,7 @@ def lib() -> C.CDLL:
         L.plviwo_op_canny_half.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
         L.plviwo_op_fld.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_int,
                                     C.POINTER(C.c_int)]
+        L.plviwo_op_image_kernels_time.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.plviwo_op_ransac_fundamental.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p,
                                                    C.POINTER(C.c_int)]
         _lib = L
@@ -616,6 +617,13 @@ def op_fld(img: np.ndarray, length_threshold: int = 20, distance_threshold: floa
     _check(lib().plviwo_op_fld(device, img.ctypes.data, img.shape[1], img.shape[0], length_threshold, distance_threshold,
                                canny_th, out.ctypes.data, cap, C.byref(n)))
     return out[:n.value].copy()
+
+
+def op_image_kernels_time(w: int, h: int, iters: int = 10, device: int = 0) -> Dict[str, float]:
+    """Mean ms per launch of k_hist, k_eq_pyr1, k_fast, k_canny on a device-resident w x h image (micro-benchmark)."""
+    ms = (C.c_float * 4)()
+    _check(lib().plviwo_op_image_kernels_time(device, w, h, iters, ms))
+    return {"hist": ms[0], "eq_pyr1": ms[1], "fast": ms[2], "canny": ms[3]}
 
 
 def op_ransac_fundamental(p0n, p1n, threshold: float, confidence: float = 0.999):

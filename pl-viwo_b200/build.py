@@ -25,7 +25,7 @@ SOURCES = [
     ("ransac.cpp", []),
     ("host_simd.cpp", []),
 ]
-HEADERS = ["fe_kernels.h", "fe_context.h", os.path.join("..", "..", "include", "plviwo_fe.h")]
+HEADERS = ["fe_kernels.h", "fe_context.h", "tma_bulk.h", "introsort.h", os.path.join("..", "..", "include", "plviwo_fe.h")]
 
 
 def _nvcc() -> str:

@@ -560,6 +560,69 @@ int plviwo_op_fld(int device, const uint8_t *img, int w, int h, int length_thres
   API_END
 }
 
+int plviwo_op_image_kernels_time(int device, int w, int h, int iters, float ms[4]) {
+  API_BEGIN
+  if (!ms || w < 64 || h < 64 || (w & 3) || (h & 3) || iters < 1) return FE_BAD_ARG;
+  OP_CUDA(cudaSetDevice(device));
+  TmpImage raw, l0, l1, half;
+  DevBuf<unsigned> hist, counters, total, kps;
+  DevBuf<int> off, cnt;
+  DevBuf<FastCell> cells;
+  TmpFld f;
+  const int cw = 256, ch = 112;                       // the 5 x 5 grid cell of a 1280 x 560 frame
+  const int gx = w / cw, gy = h / ch, ncell = gx * gy;
+  const int nb = (ch + kFastBandRows - 1) / kFastBandRows;
+  const int kcap = 1 << 22;
+  if (raw.alloc(w, h) || l0.alloc(w, h) || l1.alloc((w + 1) / 2, (h + 1) / 2) || half.alloc(w / 2, h / 2) || hist.alloc(256) ||
+      counters.alloc(4) || total.alloc(2) || kps.alloc(kcap) || off.alloc((size_t)ncell * nb) || cnt.alloc((size_t)ncell * nb) ||
+      cells.alloc(std::max(ncell, 1)) || f.alloc(w / 2, h / 2, 20, 16))
+    return FE_CUDA_ERROR;
+  {  // synthetic texture: smooth ramps + hash noise (uploaded once)
+    std::vector<uint8_t> row((size_t)w);
+    std::vector<uint8_t> img((size_t)w * h);
+    for (int y = 0; y < h; y++)
+      for (int x = 0; x < w; x++) {
+        unsigned v = (unsigned)(x * 2654435761u) ^ (unsigned)(y * 40503u);
+        v ^= v >> 13; v *= 0x5bd1e995u; v ^= v >> 15;
+        img[(size_t)y * w + x] = (uint8_t)(40 + ((x / 7 + y / 5) & 63) + (v & 63));
+      }
+    if (raw.upload(img.data())) return FE_CUDA_ERROR;
+  }
+  std::vector<FastCell> hc;
+  for (int x = 0; x < gx; x++)
+    for (int y = 0; y < gy; y++) hc.push_back(FastCell{x * cw, y * ch, cw, ch});
+  if (ncell) OP_CUDA(cudaMemcpy(cells.p, hc.data(), hc.size() * sizeof(FastCell), cudaMemcpyHostToDevice));
+  OP_CUDA(cudaMemset(hist.p, 0, 256 * sizeof(unsigned)));
+  OP_CUDA(cudaMemset(counters.p, 0, 4 * sizeof(unsigned)));
+  cudaEvent_t e0, e1;
+  OP_CUDA(cudaEventCreate(&e0));
+  OP_CUDA(cudaEventCreate(&e1));
+  auto time_it = [&](int which) -> float {
+    float tot = 0;
+    for (int it = 0; it < iters + 3; it++) {
+      if (which == 0) cudaMemsetAsync(hist.p, 0, 256 * sizeof(unsigned), 0);
+      if (which == 2) cudaMemsetAsync(total.p, 0, 2 * sizeof(unsigned), 0);
+      cudaEventRecord(e0, 0);
+      if (which == 0) launch_hist(raw.im, hist.p, 0);
+      if (which == 1) launch_eq_pyr1(raw.im, hist.p, counters.p, 0, l0.im, l1.im, half.im, 0);
+      if (which == 2) launch_fast(l0.im, cells.p, ncell, nb, cw, 20, total.p, off.p, cnt.p, kps.p, kcap, 0);
+      if (which == 3) launch_canny(half.im, 50.f, 50.f, f.fb, 0);
+      cudaEventRecord(e1, 0);
+      cudaEventSynchronize(e1);
+      float t = 0;
+      cudaEventElapsedTime(&t, e0, e1);
+      if (it >= 3) tot += t;
+    }
+    return tot / iters;
+  };
+  for (int k = 0; k < 4; k++) ms[k] = time_it(k);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  OP_CUDA(cudaDeviceSynchronize());
+  return FE_OK;
+  API_END
+}
+
 int plviwo_op_ransac_fundamental(const float *p0n, const float *p1n, int n, double threshold, double confidence,
                                  uint8_t *mask, int *n_inliers) {
   API_BEGIN

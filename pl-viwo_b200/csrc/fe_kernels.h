@@ -1,9 +1,28 @@
 // Internal C++ interface between the host-side trackers and the sm_100a kernels (not part of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 
 namespace plviwo {
+
+// Opt-in to more than 48 KB of dynamic shared memory.  The attribute is per DEVICE (handles of one process may live on
+// different GPUs) and launches come from several host threads: remember the largest request per device.
+struct SmemOptIn {
+  std::atomic<size_t> granted[64];
+  SmemOptIn() { for (auto &g : granted) g.store(0); }
+  template <class Kernel>
+  void ensure(Kernel kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::atomic<size_t> &g = granted[dev & 63];
+    if (bytes > g.load(std::memory_order_relaxed)) {
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      g.store(bytes, std::memory_order_relaxed);
+    }
+  }
+};
 
 struct DevImage {
   uint8_t *p = nullptr;

@@ -223,11 +223,8 @@ void launch_fast(const DevImage &img, const FastCell *d_cells, int n_cells, int 
   if (n_cells <= 0) return;
   int smem_w = (max_cell_w + 15) & ~15;
   size_t smem = (size_t)(2 * kBH + 10) * smem_w;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  optin.ensure(k_fast, smem);
   dim3 grid(max_bands, n_cells);
   k_fast<<<grid, kFastThreads, smem, s>>>(img.p, img.pitch, d_cells, max_bands, threshold, d_total, d_band_off, d_band_cnt,
                                           d_kps, kps_cap, smem_w);

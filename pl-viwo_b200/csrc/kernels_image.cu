@@ -9,6 +9,7 @@
 // planes with a 15 px border; here the frame is read once, the equalised image is written once and shared,
 // and derivatives are formed on the fly inside the LK kernel.
 #include "fe_kernels.h"
+#include "tma_bulk.h"
 
 namespace plviwo {
 
@@ -180,6 +181,11 @@ constexpr int kT0W = 2 * kT1W, kT0H = 2 * kT1H;  // level-0 interior of the tile
 constexpr int kTileCols = kT0W + 8;            // staged columns: [2*tx0 - 4, 2*tx0 + 132), word aligned
 constexpr int kTileRows = kT0H + 4;            // staged rows:    [2*ty0 - 2, 2*ty0 + 34)
 constexpr int kEqThreads = 256;
+// Interior tiles (no reflected row or column, the 16-byte aligned span inside the row) are staged by the TMA unit: one
+// bulk copy per tile row of the span [2*tx0 - 16, 2*tx0 + 144), issued before the LUT is built so that the copy overlaps
+// the histogram scan.  Border tiles take the per-thread path with BORDER_REFLECT_101.
+constexpr int kBulkCols = kT0W + 32;           // 160 bytes per row
+constexpr int kBulkLead = 12;                  // bulk column of tile column 0: (2*tx0 - 4) - (2*tx0 - 16)
 
 __global__ void __launch_bounds__(kEqThreads)
     k_eq_pyr1(const uint8_t *__restrict__ src, int w, int h, int spitch, unsigned *__restrict__ hist,
@@ -188,6 +194,8 @@ __global__ void __launch_bounds__(kEqThreads)
               uint8_t *__restrict__ l1, int w1, int h1, int l1pitch, uint8_t *__restrict__ half, int wh, int hh,
               int hpitch) {
   __shared__ __align__(16) uint8_t tile[kTileRows][kTileCols];
+  __shared__ __align__(16) uint8_t rawt[kTileRows][kBulkCols];
+  __shared__ __align__(8) unsigned long long bulk_bar;
   __shared__ unsigned short hbuf[kTileRows][kT1W];
   __shared__ uint8_t lut[256];
   __shared__ unsigned warp_tot[kEqThreads / 32];
@@ -196,6 +204,19 @@ __global__ void __launch_bounds__(kEqThreads)
   __shared__ unsigned s_last;
 
   const int tid = threadIdx.x;
+  const int tx0 = blockIdx.x * kT1W, ty0 = blockIdx.y * kT1H;
+  const int gx_base = 2 * tx0 - 4, gy_base = 2 * ty0 - 2;
+  // ---- interior tile: start the bulk copies of the raw window now
+  const bool bulk = gy_base >= 0 && gy_base + kTileRows <= h && 2 * tx0 - 16 >= 0 && 2 * tx0 + kBulkCols - 16 <= w &&
+                    (spitch & 15) == 0 && ((size_t)src & 15) == 0;
+  if (bulk && tid == 0) {
+    const unsigned bar = smem_u32(&bulk_bar);
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, kTileRows * kBulkCols);
+    const uint8_t *g = src + (size_t)gy_base * spitch + (2 * tx0 - 16);
+#pragma unroll 4
+    for (int r = 0; r < kTileRows; r++) bulk_g2s(smem_u32(&rawt[r][0]), g + (size_t)r * spitch, kBulkCols, bar);
+  }
   // ---- LUT (cv::equalizeHist, Appendix A1): every CTA rebuilds it from the 1 KB histogram
   if (equalize == 1) {
     if (tid == 0) s_i0 = 256;
@@ -237,9 +258,24 @@ __global__ void __launch_bounds__(kEqThreads)
   __syncthreads();
 
   // ---- stage the raw window through the LUT
-  const int tx0 = blockIdx.x * kT1W, ty0 = blockIdx.y * kT1H;
-  const int gx_base = 2 * tx0 - 4, gy_base = 2 * ty0 - 2;
   constexpr int kWordsPerRow = kTileCols / 4;
+  if (bulk) {
+    mbar_wait(smem_u32(&bulk_bar), 0);
+    for (int i = tid; i < kTileRows * kWordsPerRow; i += kEqThreads) {
+      const int r = i / kWordsPerRow, wi = i - r * kWordsPerRow;
+      const unsigned v = *reinterpret_cast<const unsigned *>(&rawt[r][kBulkLead + 4 * wi]);
+      unsigned out;
+      if (equalize == 2) {
+        const int gy = gy_base + r, gx = gx_base + 4 * wi;
+        out = clahe_px(clahe_luts, cg, gx, gy, v & 0xff) | (clahe_px(clahe_luts, cg, gx + 1, gy, (v >> 8) & 0xff) << 8) |
+              (clahe_px(clahe_luts, cg, gx + 2, gy, (v >> 16) & 0xff) << 16) | (clahe_px(clahe_luts, cg, gx + 3, gy, v >> 24) << 24);
+      } else {
+        out = (unsigned)lut[v & 0xff] | ((unsigned)lut[(v >> 8) & 0xff] << 8) | ((unsigned)lut[(v >> 16) & 0xff] << 16) |
+              ((unsigned)lut[v >> 24] << 24);
+      }
+      *reinterpret_cast<unsigned *>(&tile[r][4 * wi]) = out;
+    }
+  } else
   for (int i = tid; i < kTileRows * kWordsPerRow; i += kEqThreads) {
     int r = i / kWordsPerRow, wi = i - r * kWordsPerRow;
     int gy = gy_base + r, gx = gx_base + 4 * wi;

@@ -20,6 +20,7 @@
 #include "fe_kernels.h"
 
 #include <algorithm>
+#include <mutex>
 #include <cstdio>
 #include <cmath>
 
@@ -240,6 +241,8 @@ __device__ __align__(16) uint8_t g_walk_lut[kLutSize];
 static bool g_walk_lut_ready[64] = {false};
 
 void init_fld_constants() {
+  static std::mutex mu;   // handles may be created from several host threads
+  std::lock_guard<std::mutex> lk(mu);
   int dev = 0;
   cudaGetDevice(&dev);
   if (g_walk_lut_ready[dev & 63]) return;
@@ -724,11 +727,8 @@ void launch_fld(const DevImage &half, int length_threshold, float distance_thres
   init_fld_constants();
   const int ws = ((w + 31) >> 5) + 2;
   size_t smem = (size_t)kLutSize + (size_t)(h + 2 * kPadRows) * ws * sizeof(unsigned);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(k_fld_walk_cc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  optin.ensure(k_fld_walk_cc, smem);
   k_fld_walk_cc<<<kWalkCtas, kWalkThreads, smem, s>>>(fb.edges, fb.words_per_row, fb.label, fb.cnt, fb.bbox, w, h, fb.comp_root, fb.counters, fb.max_chains,
                                                length_threshold, fb.chain_pts, fb.chain_seed, fb.chain_off, fb.chain_len,
                                                fb.max_chains);

@@ -9,6 +9,7 @@
 #include "fe_kernels.h"
 
 #include <algorithm>
+#include <mutex>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -115,6 +116,8 @@ void launch_corner_subpix(const DevImage &img, const float2 *d_in, float2 *d_out
   if (n == 0) return;
   int dev = 0;
   cudaGetDevice(&dev);
+  static std::mutex mu;   // handles may be created from several host threads
+  std::unique_lock<std::mutex> lk(mu);
   if (!g_subpix_mask_ready[dev & 63]) {
     float m[kSpW * kSpW];
     for (int i = 0; i < kSpW; i++) {
@@ -128,6 +131,7 @@ void launch_corner_subpix(const DevImage &img, const float2 *d_in, float2 *d_out
     cudaMemcpyToSymbol(c_subpix_mask, m, sizeof(m));
     g_subpix_mask_ready[dev & 63] = true;
   }
+  lk.unlock();
   if (n < 0) return;
   k_corner_subpix<<<(n + kSpWarps - 1) / kSpWarps, kSpWarps * 32, 0, s>>>(img.p, img.w, img.h, img.pitch, d_in, d_out, n, d_cnt,
                                                                           stride);
@@ -691,11 +695,8 @@ bool launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *d_pts0, f
   const int win = prm.win, np = win + 3, nd = win + 1, nw = win * win;
   const int per_warp = ((np * np + 15) & ~15) + 2 * ((nd * nd * 2 + 15) & ~15) + 3 * ((nw * 2 + 15) & ~15);
   size_t smem = (size_t)per_warp * kLkWarps;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(k_lk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  optin.ensure(k_lk, smem);
   k_lk<<<(n + kLkWarps - 1) / kLkWarps, kLkWarps * 32, smem, s>>>(a, d_pts0, d_pts1, d_status, d_p0n, d_p1n, n);
   return false;
 }
