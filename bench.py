@@ -131,11 +131,31 @@ def run_cpu(seq, frames, steps, warmup, threads=None):
     if threads:
         cv2.setNumThreads(threads)
     kw = {k: v for k, v in WORKLOAD.items() if k not in ("width", "height")}
-    fe = ofe.FrontEnd(ofe.FeConfig(K=seq.K, D=seq.D, **kw))
+    from oracle import cvops
+    in_kernels = [0.0]
+
+    class TimedOps:
+        """oracle.cvops with the time spent INSIDE the OpenCV calls (and the FastLineDetector / std::sort shim) added up:
+        the rest of a frame is the Python restatement of the reference's glue, which the C++ reference does much faster."""
+
+        def __getattr__(self, name):
+            f = getattr(cvops, name)
+            if not callable(f):
+                return f
+
+            def timed(*a, **k):
+                t = time.perf_counter()
+                r = f(*a, **k)
+                in_kernels[0] += time.perf_counter() - t
+                return r
+            return timed
+
+    fe = ofe.FrontEnd(ofe.FeConfig(K=seq.K, D=seq.D, **kw), ops=TimedOps())
     n = len(frames)
     for t in range(warmup):
         fe.feed(seq.timestamp(t), frames[t % n], None, seq.vanishing_points(t % n))
     per = []
+    in_kernels[0] = 0.0
     t0 = time.perf_counter()
     for k in range(steps):
         t = warmup + k
@@ -143,7 +163,9 @@ def run_cpu(seq, frames, steps, warmup, threads=None):
         fe.feed(seq.timestamp(t), frames[t % n], None, seq.vanishing_points(t % n))
         per.append(time.perf_counter() - a)
     dt = time.perf_counter() - t0
-    return dict(fps=steps / dt, ms_per_step=1e3 * dt / steps, p50_ms=1e3 * float(np.median(per)), cores=cv2.getNumThreads())
+    return dict(fps=steps / dt, ms_per_step=1e3 * dt / steps, p50_ms=1e3 * float(np.median(per)), cores=cv2.getNumThreads(),
+                kernel_ms=1e3 * in_kernels[0] / steps, glue_ms=1e3 * (dt - in_kernels[0]) / steps,
+                kernels_only_fps=steps / in_kernels[0] if in_kernels[0] > 0 else None)
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -283,7 +305,11 @@ def main():
                 "config": {"workload": WORKLOAD_NAME, "streams": 1},
                 "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
                                  "sample": "%d frames of the same synthetic sequence; reference glue restated in Python "
-                                           "(oracle/frontend.py) driving the real OpenCV kernels through cv2" % steps},
+                                           "(oracle/frontend.py) driving the real OpenCV kernels through cv2; per frame %.2f ms "
+                                           "inside OpenCV / the FLD shim + %.2f ms Python glue" % (steps, r["kernel_ms"], r["glue_ms"]),
+                                 "kernels_only_value": r["kernels_only_fps"],
+                                 "kernels_only_note": "frames/s if the reference's glue cost nothing (upper bound for any "
+                                                      "CPU implementation built on these OpenCV kernels)"},
                 "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "p50_ms_per_frame": r["p50_ms"]}
         emit(line)
@@ -416,7 +442,11 @@ def main():
         r = run_cpu(seq, frames, args.cpu_sample, 10)
         cpu = {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
                "sample": "%d frames of the same sequence; oracle/frontend.py (reference glue restated) driving real OpenCV "
-                         "kernels via cv2, %d OpenCV threads; p50 %.2f ms/frame" % (args.cpu_sample, r["cores"], r["p50_ms"])}
+                         "kernels via cv2, %d OpenCV threads; p50 %.2f ms/frame = %.2f ms inside OpenCV / the FLD shim + %.2f ms "
+                         "Python glue" % (args.cpu_sample, r["cores"], r["p50_ms"], r["kernel_ms"], r["glue_ms"]),
+               "kernels_only_value": r["kernels_only_fps"],
+               "kernels_only_note": "frames/s if the reference's glue cost nothing (upper bound for any CPU implementation "
+                                    "built on these OpenCV kernels)"}
     line = {
         "metric": METRIC, "value": total_frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -147,17 +147,16 @@ class TrackKLT:
             self.trace["reset"] = True
             return rows
         H, W = img_eq.shape
-        good, good_ids = [], []
-        for i in range(len(pts_new)):                             # :159-173
-            x, y = pts_new[i]
-            if x < 0 or y < 0 or int(x) >= W or int(y) >= H:
-                continue
-            if int(mask[int(y), int(x)]) > 127:
-                continue
-            if mask_ll[i]:
-                good.append(pts_new[i])
-                good_ids.append(ids_old[i])
-        good = np.asarray(good, f32).reshape(-1, 2)
+        # :159-173, element-wise on arrays (int() of the C++ = truncation towards zero = astype(int))
+        xs, ys = pts_new[:, 0], pts_new[:, 1]
+        xi, yi = xs.astype(np.int64), ys.astype(np.int64)
+        inb = ~((xs < 0) | (ys < 0) | (xi >= W) | (yi >= H))
+        keep = inb.copy()
+        keep[inb] &= ~(mask[yi[inb], xi[inb]] > 127)
+        keep &= np.asarray(mask_ll, bool)
+        sel = np.nonzero(keep)[0]
+        good = np.ascontiguousarray(pts_new[sel], f32).reshape(-1, 2)
+        good_ids = [ids_old[i] for i in sel]
         und = self.ops.undistort(good, self.K, self.D)            # :176-179
         for i in range(len(good)):
             rows.append(PointRow(int(good_ids[i]), float(good[i, 0]), float(good[i, 1]), float(und[i, 0]), float(und[i, 1])))
@@ -178,34 +177,34 @@ class TrackKLT:
         size_y = f32(H) / f32(cfg.grid_y)
         grid_grid = np.zeros((cfg.grid_y, cfg.grid_x), np.uint8)
         mask_upd = mask0.copy()
-        keep_pts, keep_ids = [], []
-        for k in range(len(pts0)):                                # :411-464
-            px, py = f32(pts0[k, 0]), f32(pts0[k, 1])
-            x, y = int(px), int(py)
-            edge = 10
-            if x < edge or x >= W - edge or y < edge or y >= H - edge:
-                continue
-            x_close = int(px / f32(d))
-            y_close = int(py / f32(d))
-            if x_close < 0 or x_close >= close_w or y_close < 0 or y_close >= close_h:
-                continue
-            x_grid = int(math.floor(px / size_x))
-            y_grid = int(math.floor(py / size_y))
-            if x_grid < 0 or x_grid >= cfg.grid_x or y_grid < 0 or y_grid >= cfg.grid_y:
-                continue
+        keep_idx = []
+        # :411-464.  The per-point quantities are float32 / int expressions of the point alone and are evaluated for
+        # all points at once (same element-wise arithmetic); only the order-dependent occupancy tests stay in the loop.
+        P = np.asarray(pts0, f32).reshape(-1, 2)
+        PX, PY = P[:, 0], P[:, 1]
+        X, Y = PX.astype(np.int64), PY.astype(np.int64)
+        edge = 10
+        XC, YC = (PX / f32(d)).astype(np.int64), (PY / f32(d)).astype(np.int64)
+        XG, YG = np.floor(PX / size_x).astype(np.int64), np.floor(PY / size_y).astype(np.int64)
+        ok = ~((X < edge) | (X >= W - edge) | (Y < edge) | (Y >= H - edge))
+        ok &= ~((XC < 0) | (XC >= close_w) | (YC < 0) | (YC >= close_h))
+        ok &= ~((XG < 0) | (XG >= cfg.grid_x) | (YG < 0) | (YG >= cfg.grid_y))
+        Xl, Yl, XCl, YCl, XGl, YGl = X.tolist(), Y.tolist(), XC.tolist(), YC.tolist(), XG.tolist(), YG.tolist()
+        for k in np.nonzero(ok)[0].tolist():
+            x, y, x_close, y_close = Xl[k], Yl[k], XCl[k], YCl[k]
             if grid_close[y_close, x_close] > 127:
                 continue
             if mask0[y, x] > 127:
                 continue
             grid_close[y_close, x_close] = 255
+            x_grid, y_grid = XGl[k], YGl[k]
             if grid_grid[y_grid, x_grid] < 255:
                 grid_grid[y_grid, x_grid] += 1
             if x - d >= 0 and x + d < W and y - d >= 0 and y + d < H:
                 mask_upd[y - d:y + d + 1, x - d:x + d + 1] = 255   # cv::rectangle FILLED, both corners inclusive
-            keep_pts.append((px, py))
-            keep_ids.append(ids0[k])
-        pts0 = np.asarray(keep_pts, f32).reshape(-1, 2)
-        ids0 = keep_ids
+            keep_idx.append(k)
+        ids0 = [ids0[k] for k in keep_idx]
+        pts0 = np.ascontiguousarray(P[keep_idx], f32).reshape(-1, 2)
         self.trace.setdefault("det", {})
         det = self.trace["det"] = {"pts_kept": pts0.copy(), "ran": False}
 
@@ -300,9 +299,9 @@ class TrackKLT:
         p1n = self.ops.undistort(p1, self.K, self.D)
         maxf = max(self.K[0], self.K[1])
         mask_rsc = self.ops.find_fundamental_mask(p0n, p1n, 2.0 / maxf)
-        out = np.zeros((n,), np.uint8)
-        for i in range(n):
-            out[i] = 1 if (mask_klt[i] and i < len(mask_rsc) and mask_rsc[i]) else 0
+        rsc = np.zeros((n,), bool)
+        rsc[:len(mask_rsc)] = np.asarray(mask_rsc, bool)[:n]
+        out = (np.asarray(mask_klt, bool) & rsc).astype(np.uint8)
         self.trace["lk_pts1"] = p1.copy()
         self.trace["mask_klt"] = mask_klt.copy()
         self.trace["mask_rsc"] = mask_rsc.copy()
@@ -351,17 +350,22 @@ def line_similar(line2: np.ndarray, line1: np.ndarray) -> bool:
 
 def line_class(line: np.ndarray, vp) -> bool:
     """TrackLSD::LineClass (TrackLSD.cpp:335-366), including the ``atan(dy) / dx`` quirk at :350-351."""
-    s = np.array([float(line[0]), float(line[1]), 1.0])
-    e = np.array([float(line[2]), float(line[3]), 1.0])
-    mid = (s + e) / 2
-    v3 = np.array([float(vp[0]), float(vp[1]), 1.0])
-    ln = np.cross(mid, v3)
+    # Eigen::Vector3d arithmetic written out in Python doubles (the interpreter cost of tiny NumPy arrays used to
+    # dominate the CPU baseline): s, e homogeneous end points, mid = (s + e) / 2, ln = mid x v3
+    s0, s1, e0, e1 = float(line[0]), float(line[1]), float(line[2]), float(line[3])
+    m0, m1, m2 = (s0 + e0) / 2, (s1 + e1) / 2, (1.0 + 1.0) / 2
+    v0, v1 = float(vp[0]), float(vp[1])
+    l0, l1, l2 = m1 * 1.0 - m2 * v1, m2 * v0 - m0 * 1.0, m0 * v1 - m1 * v0
     with np.errstate(all="ignore"):
-        dis = (abs(float(ln @ s)) + abs(float(ln @ e))) / (2 * math.sqrt(ln[0] * ln[0] + ln[1] * ln[1])) \
-            if (ln[0] != 0 or ln[1] != 0) else float("nan")
+        if l0 != 0 or l1 != 0:
+            dis = (abs(l0 * s0 + l1 * s1 + l2 * 1.0) + abs(l0 * e0 + l1 * e1 + l2 * 1.0)) / (2 * math.sqrt(l0 * l0 + l1 * l1))
+        else:
+            dis = float("nan")
         dis = abs(dis)
         a1 = float(np.arctan(f32(line[1]) - f32(line[3])) / (f32(line[0]) - f32(line[2])))   # float arithmetic
-        a2 = float(np.float64(math.atan(mid[1] - float(vp[1]))) / np.float64(mid[0] - float(vp[0])))
+        den = m0 - v0
+        num = math.atan(m1 - v1)
+        a2 = num / den if den != 0 else (math.copysign(math.inf, num) * math.copysign(1.0, den) if num != 0 else float("nan"))
         err = abs(a1 - a2)
     return bool(dis <= 5.0 and err <= 0.35)
 
@@ -438,9 +442,13 @@ class TrackLSD:
         min_ly, max_ly = np.minimum(ly1, ly2)[:, None], np.maximum(ly1, ly2)[:, None]
         px, py = points[:, 0].astype(np.float64)[None, :], points[:, 1].astype(np.float64)[None, :]
         inside = ~((px < min_lx) | (px > max_lx) | (py < min_ly) | (py > max_ly))   # :775
-        # PointLineDistance (:794-814) for every pair, float32 like the C++
-        x0, y0 = points[:, 0][None, :], points[:, 1][None, :]
-        x1, y1, x2, y2 = lines[:, 0][:, None], lines[:, 1][:, None], lines[:, 2][:, None], lines[:, 3][:, None]
+        # PointLineDistance (:794-814), float32 like the C++, evaluated only for the pairs that pass the box test (the
+        # reference calls it after the box test too, :775-780)
+        li, pj = np.nonzero(inside)
+        if len(li) == 0:
+            return relation, positions, np.zeros((0, 4), f32), new_ids
+        x0, y0 = points[pj, 0], points[pj, 1]
+        x1, y1, x2, y2 = lines[li, 0], lines[li, 1], lines[li, 2], lines[li, 3]
         cross = (x2 - x1) * (x0 - x1) + (y2 - y1) * (y0 - y1)
         d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1)
         d1 = np.sqrt((x0 - x1) * (x0 - x1) + (y0 - y1) * (y0 - y1))
@@ -450,14 +458,20 @@ class TrackLSD:
         with np.errstate(all="ignore"):
             d3 = np.abs(num.astype(np.float64) / den).astype(f32)
         dist = np.where(cross <= 0, d1, np.where(cross > d, d2, d3)).astype(f32)
-        hit = inside & ~(dist > 5)                                            # :780
-        for i in np.nonzero(hit.any(1))[0]:
-            js = np.nonzero(hit[i])[0]
-            pol = {int(pids[j]): float(dist[i, j]) for j in js}
+        hit = ~(dist > 5)                                                      # :780
+        li, pj, dist = li[hit], pj[hit], dist[hit]
+        # pairs are in (line, point) order; group them by line
+        if len(li) == 0:
+            return relation, positions, np.zeros((0, 4), f32), new_ids
+        starts = np.nonzero(np.r_[True, li[1:] != li[:-1]])[0].tolist() + [len(li)]
+        pj_l, dist_l, li_l = pj.tolist(), dist.tolist(), li.tolist()
+        for a0, a1 in zip(starts[:-1], starts[1:]):
+            i = li_l[a0]
+            pol = {int(pids[j]): dv for j, dv in zip(pj_l[a0:a1], dist_l[a0:a1])}
             relation.append(dict(sorted(pol.items())))
             new_lines.append(lines[i])
             new_ids.append(line_ids[i])
-            positions.append(points[js].copy())
+            positions.append(points[pj[a0:a1]].copy())
         return relation, positions, np.asarray(new_lines, f32).reshape(-1, 4), new_ids
 
     # -- TrackLSD.cpp:368-407
