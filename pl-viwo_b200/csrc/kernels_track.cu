@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <mutex>
 #include <cfloat>
+#include <cstdio>
 #include <climits>
 #include <cmath>
 
@@ -381,17 +382,23 @@ __global__ void __launch_bounds__(kLkWarps * 32)
 //            is built by warp l for level l, all levels at the same time (it used to be 5 x ~4.5k cycles in a row);
 //            lane i owns the 2 x 4 block of window pixels at rows 2*(i/4).., columns 4*(i%4).. (the 16th row / column
 //            is masked off), its 8 values per patch are parked in shared memory as int16;
-//   chain    warp 0 then runs the coarse-to-fine iterations, which only touch the NEXT image.  Per level a 25 x 25
-//            region of it (REFLECT_101 applied while staging) is copied to shared memory around the start position; a
-//            lane keeps the 3 x 5 block it interpolates from in registers and re-reads it — from shared memory — only
-//            when the integer window position moves; the region is re-staged if the window leaves it.  An iteration
-//            is ~100 independent integer/float instructions plus one two-value shuffle reduction.
-// Arithmetic and summation order are those of the generic kernel above (results are bit-identical to it).
+//   chain    warps 0..3 then run the coarse-to-fine iterations together, which only touch the NEXT image.  Per level a
+//            25 x 25 region of it (REFLECT_101 applied while staging) is copied to shared memory around the start
+//            position; of the 15 x 16 window slots each of the 120 active lanes owns two horizontally adjacent pixels,
+//            keeps the 2 x 3 block of the next image it interpolates them from in registers and re-reads it — from
+//            shared memory — only when the integer window position moves; the region is re-staged if the window leaves
+//            it.  The mismatch sums are exact integers (redux.sync per warp, 4 partials through shared memory, one named
+//            barrier per iteration), so splitting the window over several warps cannot change a single bit of the
+//            result; every warp repeats the scalar part of the iteration (position, weights, 2 x 2 solve, convergence
+//            tests) and they stay in lock step.
+// The per-pixel arithmetic is that of the generic kernel above; the only difference is that it accumulates the integer
+// products in float32 while this kernel sums them exactly.
 constexpr int kW15 = 15;
 constexpr int kLk15MaxLevels = 6;   // pyr_levels <= 5 (the reference uses 5); deeper pyramids take the generic kernel
 constexpr int kJMargin = 4;         // the staged region of the next image extends this far around a window
 constexpr int kJSpan = kW15 + 2;    // rows / columns a window touches: 15 + 1 (bilinear) + 1 (the lanes' masked 16th row)
 constexpr int kJR = kJSpan + 2 * kJMargin;   // 25
+constexpr int kChainWarps = 4;      // warps that share one feature's iteration chain
 
 __global__ void __launch_bounds__(kLk15MaxLevels * 32)
     k_lk15(LkArgs a, const float2 *__restrict__ pts0, float2 *__restrict__ pts1, uint8_t *__restrict__ status,
@@ -402,7 +409,8 @@ __global__ void __launch_bounds__(kLk15MaxLevels * 32)
   __shared__ uint8_t raw_s[kLk15MaxLevels][np * np + 12];
   __shared__ short ddx_s[kLk15MaxLevels][nd * nd];
   __shared__ short ddy_s[kLk15MaxLevels][nd * nd];
-  __shared__ short patch_s[kLk15MaxLevels][3][8][32];   // [level][I, Ix, Iy][k][lane]
+  __shared__ short patch_s[kLk15MaxLevels][3][kW15][16];   // [level][I, Ix, Iy][window row][window column (15 used)]
+  __shared__ int red_s[2][kChainWarps][4];                 // per-warp partial sums, double-buffered by iteration parity
   __shared__ float amat_s[kLk15MaxLevels][4];           // [level][A11, A12, A22, level usable]
   __shared__ uint8_t jreg_s[kJR * kJR + 7];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -420,6 +428,10 @@ __global__ void __launch_bounds__(kLk15MaxLevels * 32)
       return;
     }
   }
+#ifdef PLVIWO_LK_PROF
+  long long prof_t0 = clock64(), prof_tA = 0;
+  int prof_n = 0, prof_moves = 0, prof_stage = 0;
+#endif
   const float2 prev_in = pts0[pi];
   const float half = (win - 1) * 0.5f;
   const float FLT_SCALE = 1.f / (1 << 20);
@@ -487,9 +499,11 @@ __global__ void __launch_bounds__(kLk15MaxLevels * 32)
           ixval = (ddx[di] * iw00 + ddx[di + 1] * iw01 + ddx[di + nd] * iw10 + ddx[di + nd + 1] * iw11 + (1 << 13)) >> 14;
           iyval = (ddy[di] * iw00 + ddy[di + 1] * iw01 + ddy[di + nd] * iw10 + ddy[di + nd + 1] * iw11 + (1 << 13)) >> 14;
         }
-        patch_s[l][0][k][lane] = (short)ival;
-        patch_s[l][1][k][lane] = (short)ixval;
-        patch_s[l][2][k][lane] = (short)iyval;
+        if (y < win && x < 16) {
+          patch_s[l][0][y][x] = (short)ival;
+          patch_s[l][1][y][x] = (short)ixval;
+          patch_s[l][2][y][x] = (short)iyval;
+        }
         A11 += (float)(ixval * ixval);
         A12 += (float)(ixval * iyval);
         A22 += (float)(iyval * iyval);
@@ -506,11 +520,19 @@ __global__ void __launch_bounds__(kLk15MaxLevels * 32)
     }
   }
   __syncthreads();
-  if (warp != 0) return;
+#ifdef PLVIWO_LK_PROF
+  prof_tA = clock64();
+#endif
+  if (warp >= kChainWarps) return;
 
-  // ---- the iteration chain (warp 0)
+  // ---- the iteration chain (warps 0..3 in lock step; named barrier 1 over 128 threads)
+  const int gid = warp * 32 + lane;                 // 0..127; slots 120..127 idle
+  const int wy = gid >> 3, wx = (gid & 7) * 2;      // this lane's pixels: (wy, wx) and (wy, wx + 1)
+  const bool own0 = wy < win, own1 = wy < win && wx + 1 < win;
+  auto chain_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kChainWarps * 32) : "memory"); };
   float2 next = a.flow_is_zero ? prev_in : pts1[pi];   // OPTFLOW_USE_INITIAL_FLOW
   bool ok = true;
+  int parity = 0;
 #pragma unroll 1
   for (int level = a.max_level; level >= 0; level--) {
     const int cols = a.w[level], rows = a.h[level];
@@ -534,12 +556,16 @@ __global__ void __launch_bounds__(kLk15MaxLevels * 32)
       continue;
     }
     Dt = 1.f / Dt;
-    int Iw[8], Ixw[8], Iyw[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      Iw[k] = patch_s[level][0][k][lane];
-      Ixw[k] = patch_s[level][1][k][lane];
-      Iyw[k] = patch_s[level][2][k][lane];
+    int Iw0 = 0, Iw1 = 0, Ix0 = 0, Ix1 = 0, Iy0 = 0, Iy1 = 0;
+    if (own0) {
+      Iw0 = patch_s[level][0][wy][wx];
+      Ix0 = patch_s[level][1][wy][wx];
+      Iy0 = patch_s[level][2][wy][wx];
+    }
+    if (own1) {
+      Iw1 = patch_s[level][0][wy][wx + 1];
+      Ix1 = patch_s[level][1][wy][wx + 1];
+      Iy1 = patch_s[level][2][wy][wx + 1];
     }
     float2 result = next;   // nextPts[ptidx] as stored by OpenCV; only rewritten after an update step
     next.x -= half;
@@ -547,7 +573,7 @@ __global__ void __launch_bounds__(kLk15MaxLevels * 32)
     float2 prevDelta = make_float2(0.f, 0.f);
     const uint8_t *J = a.p1[level];
     const int pitchJ = a.pitch1[level];
-    int jb[3][5];
+    int j00 = 0, j01 = 0, j02 = 0, j10 = 0, j11 = 0, j12 = 0;   // the 2 x 3 block of the next image under this lane's pixels
     int cached_x = INT_MIN, cached_y = INT_MIN;
     int reg_x0 = INT_MIN / 2, reg_y0 = INT_MIN / 2;   // origin of the staged region (none yet)
     for (int j = 0; j < a.max_count; j++) {
@@ -561,52 +587,73 @@ __global__ void __launch_bounds__(kLk15MaxLevels * 32)
       const int jw01 = __float2int_rn(ja * (1.f - jbf) * 16384.f);
       const int jw10 = __float2int_rn((1.f - ja) * jbf * 16384.f);
       const int jw11 = 16384 - jw00 - jw01 - jw10;
-      if (inx != cached_x || iny != cached_y) {   // warp-uniform
+#ifdef PLVIWO_LK_PROF
+      prof_n++;
+      if (inx != cached_x || iny != cached_y) prof_moves++;
+#endif
+      if (inx != cached_x || iny != cached_y) {   // uniform over the four warps
         cached_x = inx;
         cached_y = iny;
         if (inx < reg_x0 || inx + kJSpan > reg_x0 + kJR || iny < reg_y0 || iny + kJSpan > reg_y0 + kJR) {
           // (re)stage the region around the window; pixel (rx, ry) of it is J(reflect(reg_x0 + rx), reflect(reg_y0 + ry))
+#ifdef PLVIWO_LK_PROF
+          prof_stage++;
+#endif
           reg_x0 = inx - kJMargin;
           reg_y0 = iny - kJMargin;
-          __syncwarp();
-          constexpr int kJLoads = (kJR * kJR + 31) / 32;
+          chain_sync();   // everybody is done reading the old region
+          constexpr int kJLoads = (kJR * kJR + kChainWarps * 32 - 1) / (kChainWarps * 32);
           uint8_t t[kJLoads];
 #pragma unroll
           for (int q = 0; q < kJLoads; q++) {
-            const int i = lane + 32 * q;
+            const int i = gid + kChainWarps * 32 * q;
             const int ry = i / kJR, rx = i - ry * kJR;
             t[q] = 0;
             if (i < kJR * kJR) t[q] = J[(size_t)reflect101(reg_y0 + ry, rows) * pitchJ + reflect101(reg_x0 + rx, cols)];
           }
 #pragma unroll
           for (int q = 0; q < kJLoads; q++)
-            if (lane + 32 * q < kJR * kJR) jreg_s[lane + 32 * q] = t[q];
-          __syncwarp();
+            if (gid + kChainWarps * 32 * q < kJR * kJR) jreg_s[gid + kChainWarps * 32 * q] = t[q];
+          chain_sync();
         }
-        const uint8_t *Jp = jreg_s + (iny - reg_y0 + r0) * kJR + (inx - reg_x0 + c0);
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-          for (int c = 0; c < 5; c++) jb[r][c] = Jp[r * kJR + c];
+        if (own0) {
+          const uint8_t *Jp = jreg_s + (iny - reg_y0 + wy) * kJR + (inx - reg_x0 + wx);
+          j00 = Jp[0]; j01 = Jp[1]; j02 = Jp[2];
+          j10 = Jp[kJR]; j11 = Jp[kJR + 1]; j12 = Jp[kJR + 2];
+        }
       }
       // mismatch vector b = sum over the window of diff * (Ix, Iy).  Every term is an integer, so the sum is formed
-      // EXACTLY: per-lane int32 sums (8 terms of at most 8160 * 4080 each), then two hardware warp reductions per
-      // component on the 16-bit halves (the 32-lane total needs 34 bits), one rounding to float at the end.  OpenCV
-      // accumulates the same integers in float32 (order depends on its SIMD width); this is that sum without the
-      // accumulated rounding error, and a third of the latency of a shuffle tree.
+      // EXACTLY: per-lane int32 sums, hardware warp reductions on the 16-bit halves (the window total needs 34 bits),
+      // four warp partials through shared memory, one rounding to float at the end.  OpenCV accumulates the same
+      // integers in float32 (order depends on its SIMD width); this is that sum without the accumulated rounding error.
       int sb1 = 0, sb2 = 0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const int r = k >> 2, c = k & 3;
-        const int jv = (jb[r][c] * jw00 + jb[r][c + 1] * jw01 + jb[r + 1][c] * jw10 + jb[r + 1][c + 1] * jw11 + (1 << 8)) >> 9;
-        const int diff = jv - Iw[k];
-        sb1 += diff * Ixw[k];
-        sb2 += diff * Iyw[k];
+      {
+        const int jv0 = (j00 * jw00 + j01 * jw01 + j10 * jw10 + j11 * jw11 + (1 << 8)) >> 9;
+        const int jv1 = (j01 * jw00 + j02 * jw01 + j11 * jw10 + j12 * jw11 + (1 << 8)) >> 9;
+        const int d0 = own0 ? jv0 - Iw0 : 0, d1 = own1 ? jv1 - Iw1 : 0;
+        sb1 = d0 * Ix0 + d1 * Ix1;
+        sb2 = d0 * Iy0 + d1 * Iy1;
       }
-      const int b1h = __reduce_add_sync(0xffffffffu, sb1 >> 16), b1l = __reduce_add_sync(0xffffffffu, sb1 & 0xffff);
-      const int b2h = __reduce_add_sync(0xffffffffu, sb2 >> 16), b2l = __reduce_add_sync(0xffffffffu, sb2 & 0xffff);
-      const float b1 = (float)(((long long)b1h << 16) + b1l) * FLT_SCALE;
-      const float b2 = (float)(((long long)b2h << 16) + b2l) * FLT_SCALE;
+      const int p1h = __reduce_add_sync(0xffffffffu, sb1 >> 16), p1l = __reduce_add_sync(0xffffffffu, sb1 & 0xffff);
+      const int p2h = __reduce_add_sync(0xffffffffu, sb2 >> 16), p2l = __reduce_add_sync(0xffffffffu, sb2 & 0xffff);
+      if (lane == 0) {
+        red_s[parity][warp][0] = p1h;
+        red_s[parity][warp][1] = p1l;
+        red_s[parity][warp][2] = p2h;
+        red_s[parity][warp][3] = p2l;
+      }
+      chain_sync();
+      long long t1h = 0, t1l = 0, t2h = 0, t2l = 0;
+#pragma unroll
+      for (int w = 0; w < kChainWarps; w++) {
+        t1h += red_s[parity][w][0];
+        t1l += red_s[parity][w][1];
+        t2h += red_s[parity][w][2];
+        t2l += red_s[parity][w][3];
+      }
+      parity ^= 1;
+      const float b1 = (float)((t1h << 16) + t1l) * FLT_SCALE;
+      const float b2 = (float)((t2h << 16) + t2l) * FLT_SCALE;
       const float2 delta = make_float2((A12 * b2 - A22 * b1) * Dt, (A12 * b1 - A11 * b2) * Dt);
       next.x += delta.x;
       next.y += delta.y;
@@ -636,6 +683,10 @@ __global__ void __launch_bounds__(kLk15MaxLevels * 32)
       if (fx < -win || fx >= cols || fy < -win || fy >= rows) ok = false;
     }
   }
+  if (warp != 0) return;
+#ifdef PLVIWO_LK_PROF
+  if (lane == 0) printf("lkp %d %lld %lld %d %d %d %d\n", pi, clock64() - prof_t0, prof_tA - prof_t0, prof_n, prof_moves, prof_stage, (int)ok);
+#endif
   if (lane == 0) {
     pts1[pi] = next;
     status[pi] = ok ? 1 : 0;
@@ -687,7 +738,7 @@ bool launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *d_pts0, f
   for (int i = 0; i < 8; i++) a.cell_mask[i] = cell_mask ? cell_mask[i] : 0xffffffffu;
   for (int i = 0; i < 4; i++) { a.calib.K[i] = prm.K[i]; a.calib.D[i] = prm.D[i]; }
   if (prm.win == kW15 && levels <= kLk15MaxLevels) {   // one CTA per feature, one warp per level
-    k_lk15<<<n, levels * 32, 0, s>>>(a, d_pts0, d_pts1, d_status, d_p0n, d_p1n, n, host_flag, flag_value, d_done_counter,
+    k_lk15<<<n, std::max(levels, kChainWarps) * 32, 0, s>>>(a, d_pts0, d_pts1, d_status, d_p0n, d_p1n, n, host_flag, flag_value, d_done_counter,
                                      d_tab_cnt, tab_stride);
     return host_flag != nullptr;
   }
