@@ -24,7 +24,7 @@ FE_OK, FE_BAD_ARG, FE_NO_DEVICE, FE_CUDA_ERROR, FE_OVERFLOW, FE_INTERNAL = range
 HIST_NONE, HIST_HISTOGRAM, HIST_CLAHE = 0, 1, 2
 _STATUS = {0: "FE_OK", 1: "FE_BAD_ARG", 2: "FE_NO_DEVICE", 3: "FE_CUDA_ERROR", 4: "FE_OVERFLOW", 5: "FE_INTERNAL"}
 HOST_STAGES = ["submit", "detection", "matching", "ransac", "lines", "collect", "line_wait", "predet_wait",
-               "speculate", "assemble", "spec_cand_wait", "spec_launch", "lk_launch", "lk_wait"]
+               "speculate", "assemble", "unused10", "spec_launch", "lk_launch", "lk_wait"]
 STAGES = ["h2d", "hist", "eq_pyr1", "pyr_rest", "fast", "subpix", "lk", "canny", "fld", "fld_ccl", "fld_walk", "fld_seg"]
 TAP_PYR_LEVEL0, TAP_HALF, TAP_EDGES, TAP_FAST_LAST, TAP_LK_LAST, TAP_SUBPIX_LAST, TAP_FLD_LAST = 0, 32, 33, 34, 35, 36, 37
 
@@ -327,7 +327,8 @@ class FrontEnd:
                                                C.byref(self.info)), self._h)
         return self.info
 
-    def submit(self, timestamp: float, image, stride: int = 0, on_device: bool = False, vanishing_points=None):
+    def submit(self, timestamp: float, image, stride: int = 0, on_device: bool = False, vanishing_points=None,
+               mask: Optional[np.ndarray] = None):
         vp = None
         if vanishing_points is not None:
             vp = (C.c_double * 6)(*[float(v) for p in vanishing_points for v in p])
@@ -335,7 +336,11 @@ class FrontEnd:
             ptr = int(image)
         else:
             ptr, stride = image.ctypes.data, image.strides[0]
-        _check(self._lib.plviwo_fe_submit(self._h, float(timestamp), ptr, stride, 1 if on_device else 0, None, 0, vp), self._h)
+        mptr, mstride = None, 0
+        if mask is not None:     # the library copies the mask during the call
+            mask = np.ascontiguousarray(mask, np.uint8)
+            mptr, mstride = mask.ctypes.data, mask.strides[0]
+        _check(self._lib.plviwo_fe_submit(self._h, float(timestamp), ptr, stride, 1 if on_device else 0, mptr, mstride, vp), self._h)
 
     def play(self, timestamps, images, stride: int = 0, on_device: bool = False, vanishing_points=None) -> FePlayStats:
         """Whole-sequence playback inside the library (plviwo_fe_play).  images: list of device pointers (on_device) or of

@@ -707,20 +707,11 @@ int FeContext::wait_predetection(FrameSlot &s) {
   if (st == 0) return err(FE_INTERNAL, "pre-detection was never queued for this frame");
   if (wait_flag(&s.h_flags[0], s.seq_fast, s.s_b, &t_err)) return FE_CUDA_ERROR;
   const int ncell = s.predet_ncell, nb = s.predet_nb, nfg = s.predet_nfg;
-  s.cell_first.assign(ncell + 1, 0);
-  s.cand_sel.clear();
-  s.cand_ref.clear();
+  // the table itself (h_cand_cnt / h_cand_in / h_cand_out, fixed stride nfg per cell) is read in place by the top-off
+  // detection, and only for the cells that turn out to be valid
+  (void)nfg;
   s.cell_kps_tap.clear();
   s.cell_kps_first.assign(ncell + 1, 0);
-  for (int c = 0; c < ncell; c++) {
-    const int cnt = std::min(s.h_cand_cnt[c], nfg);
-    for (int i = 0; i < cnt && (int)s.cand_sel.size() < cand_cap_; i++) {
-      const float2 a = s.h_cand_in[c * nfg + i], r = s.h_cand_out[c * nfg + i];
-      s.cand_sel.push_back(Pt{a.x, a.y});
-      s.cand_ref.push_back(Pt{r.x, r.y});
-    }
-    s.cell_first[c + 1] = (int)s.cand_sel.size();
-  }
   if (s.fast_taps && ncell > 0) {
     const int ntab = ncell * nb;
     const int total = std::min(s.h_band[0], kps_cap_);
@@ -1174,15 +1165,18 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
           for (int k = slot.cell_kps_first[c]; k < slot.cell_kps_first[c + 1]; k++)
             tap_fast_.insert(tap_fast_.end(), {loc.first, loc.second, slot.cell_kps_tap[3 * k], slot.cell_kps_tap[3 * k + 1],
                                                slot.cell_kps_tap[3 * k + 2]});
-        for (int i = slot.cell_first[c]; i < slot.cell_first[c + 1]; i++) {   // :133-149
-          const Pt p = slot.cand_sel[i];
+        const int nfg_t = slot.predet_nfg, cnt = std::min(slot.h_cand_cnt[c], nfg_t);
+        for (int k = 0; k < cnt; k++) {   // :133-149
+          const int i = c * nfg_t + k;    // slot of the candidate in the frame's fixed-stride table
+          const Pt p = Pt{slot.h_cand_in[i].x, slot.h_cand_in[i].y};
           if ((int)p.x < 0 || (int)p.x > cols || (int)p.y < 0 || (int)p.y > rows) continue;
           const int ix = (int)p.x, iy = (int)p.y;
           if (iy >= rows || ix >= cols) continue;  // the reference would read out of bounds here; cannot happen
           if ((occ_bits_[(size_t)iy * bw + (ix >> 6)] >> (ix & 63)) & 1ull) continue;
-          ext.push_back(slot.cand_ref[i]);      // cornerSubPix result of exactly this point (:163-179)
-          ext_cand.push_back(c * slot.predet_nfg + (i - slot.cell_first[c]));
-          if (taps) tap_subpix_.insert(tap_subpix_.end(), {p.x, p.y, slot.cand_ref[i].x, slot.cand_ref[i].y});
+          const Pt pr = Pt{slot.h_cand_out[i].x, slot.h_cand_out[i].y};
+          ext.push_back(pr);                    // cornerSubPix result of exactly this point (:163-179)
+          ext_cand.push_back(i);
+          if (taps) tap_subpix_.insert(tap_subpix_.end(), {p.x, p.y, pr.x, pr.y});
         }
       }
     }

@@ -126,8 +126,6 @@ struct FrameSlot {
   int predet_nfg = 0, predet_ncell = 0, predet_nb = 0, predet_num_features = -1;
   std::vector<FastCell> cells;            // cell layout this frame's FAST ran on
   std::vector<int> cell_of_loc;
-  std::vector<int> cell_first;             // first candidate of cell c in cand_sel / cand_ref (size ncell + 1)
-  std::vector<Pt> cand_sel, cand_ref;      // top num_features_grid corners of every cell, before / after refinement
   std::vector<int32_t> cell_kps_tap;       // optional (taps on): every cell's FAST list as (x, y, score), cell_kps_first
   std::vector<int> cell_kps_first;
 };

@@ -452,3 +452,45 @@ def test_speculative_tracking_equals_synchronous(fe, synth, kw, lookahead, monke
         n_spec_rows += len(ref[t][0])
     assert n_spec_rows > 20 * 100
     b.close()
+
+
+def test_pipelined_with_masks_and_device_frames(fe, synth):
+    """submit/collect with a per-frame tracking mask, and frames that already live in device memory
+    (plviwo_fe_submit(on_device) / plviwo_fe_feed_device), give the rows of the synchronous host-memory feed."""
+    import torch
+    n = 14
+    seq = synth.SynthSequence(seed=1016, n_frames=n, moving_mask=True)
+    cfg = dict(width=1280, height=560, K=seq.K, D=seq.D, **CFG1)
+    frames = [seq.frame(t) for t in range(n)]
+    masks = [seq.mask(t) for t in range(n)]
+    a = fe.FrontEnd(fe.default_config(lookahead=0, **cfg))
+    ref = []
+    for t in range(n):
+        a.feed_new_camera(seq.timestamp(t), frames[t], masks[t], seq.vanishing_points(t), update_db=False)
+        ref.append((a.point_rows().copy(), a.line_rows()[0].copy()))
+    a.close()
+    # pipelined, masks, host frames
+    b = fe.FrontEnd(fe.default_config(lookahead=3, **cfg))
+    sub = 0
+    for t in range(n):
+        while sub < n and sub <= t + 3:
+            b.submit(seq.timestamp(sub), frames[sub], vanishing_points=seq.vanishing_points(sub), mask=masks[sub])
+            sub += 1
+        b.collect()
+        assert np.array_equal(b.point_rows(), ref[t][0]), t
+        assert np.array_equal(b.line_rows()[0], ref[t][1]), t
+    b.close()
+    # device-resident frames with a pitch larger than the width, no masks: compare with a mask-free synchronous run
+    c0 = fe.FrontEnd(fe.default_config(lookahead=0, **cfg))
+    c1 = fe.FrontEnd(fe.default_config(lookahead=0, **cfg))
+    d = torch.zeros((n, 560, 1536), dtype=torch.uint8, device="cuda")
+    for t in range(n):
+        d[t, :, :1280] = torch.from_numpy(frames[t]).cuda()
+    torch.cuda.synchronize()
+    for t in range(n):
+        c0.feed_new_camera(seq.timestamp(t), frames[t], None, seq.vanishing_points(t), update_db=False)
+        c1.feed_device(seq.timestamp(t), d[t].data_ptr(), 1280, 560, 1536, seq.vanishing_points(t))
+        assert np.array_equal(c0.point_rows(), c1.point_rows()), t
+        assert np.array_equal(c0.line_rows()[0], c1.line_rows()[0]), t
+    c0.close()
+    c1.close()
