@@ -217,6 +217,59 @@ int plviwo_fe_tap(FeHandle *h, int what, void *buf, size_t cap, size_t *n_bytes)
 int plviwo_fe_enable_timing(FeHandle *h, int on);   /* CUDA-event stage timing (adds event records only)   */
 int plviwo_fe_get_stage_times(FeHandle *h, FeStageTimes *out, int reset);
 
+/* ---- stereo rig: TrackKLT with use_stereo = true ------------------------------------------------------- */
+/*
+ *   reference interface                                               file:line                                   replaced by
+ *   ----------------------------------------------------------------  ------------------------------------------  -----------------------------
+ *   TrackKLT::TrackKLT(cameras {0, 1}, ..., stereo = true, ...)       ov_core/src/track/TrackKLT.h:54-57          plviwo_fe_stereo_create
+ *   TrackKLT::feed_new_camera(message with two images) -> feed_stereo ov_core/src/track/TrackKLT.cpp:34-94, 202-393 plviwo_fe_stereo_feed
+ *   TrackKLT::perform_detection_stereo                                TrackKLT.cpp:530-827                        (inside feed / collect)
+ *   FeatureDatabase::update_feature rows of cam_id_left / _right      TrackKLT.cpp:352-363                        plviwo_fe_stereo_get_point_rows
+ *   TrackBase::get_last_obs()[cam] / get_last_ids()[cam]              TrackBase.h:137-146                         plviwo_fe_stereo_get_last_obs
+ *
+ * One FeStereoHandle = one stereo pair (camera 0 = left, 1 = right; OptionsCamera stereo_pairs) on one device.  Both
+ * images have the size given in FeConfig; cfg->K / cfg->D calibrate the left camera, K_right / D_right the right one
+ * (NULL: same as left).  Points only: the reference's line tracker has no stereo path (TrackLSD.cpp:57-60 feeds the
+ * LEFT image to its monocular path) — run a monocular FeHandle on the left image for the lines.  cfg->use_lines,
+ * line_samples and downsample are ignored here.
+ */
+typedef struct FeStereoHandle FeStereoHandle;
+typedef struct FeStereoInfo {
+  double timestamp;
+  int32_t n_point_rows[2];   /* rows of the left / right camera                                   */
+  int32_t n_last_obs[2];     /* pts_last sizes after the pair                                     */
+  int32_t reset;             /* 1: both temporal masks empty, tracker cleared (TrackKLT.cpp:286-300) */
+  int32_t first_frame;       /* 1: detection-only pair (:221-241)                                 */
+  int32_t detection_ran[2];
+  int32_t n_detected[2];     /* points added per camera by the top-off detection                  */
+  int32_t n_stereo_new;      /* new left points that were also found in the right image (:668-678) */
+  int32_t n_lk_in[2], n_klt_ok[2], n_ransac_ok[2];
+  int32_t n_stereo_rows;     /* ids present in both cameras' rows of this pair                    */
+} FeStereoInfo;
+
+int plviwo_fe_stereo_create(const FeConfig *cfg, const double K_right[4], const double D_right[4], int device,
+                            FeStereoHandle **out);
+int plviwo_fe_stereo_destroy(FeStereoHandle *h);
+const char *plviwo_fe_stereo_last_error(const FeStereoHandle *h);
+int plviwo_fe_stereo_set_calib(FeStereoHandle *h, int cam, const double K[4], const double D[4]);
+int plviwo_fe_stereo_set_num_features(FeStereoHandle *h, int num_features);
+int plviwo_fe_stereo_change_feat_id(FeStereoHandle *h, uint64_t id_old, uint64_t id_new);
+/* Synchronous drop-in for feed_new_camera with two images (HOST buffers, 8UC1, same stride; masks may be NULL). */
+int plviwo_fe_stereo_feed(FeStereoHandle *h, double timestamp, const uint8_t *image_left, const uint8_t *image_right, int width,
+                          int height, int stride, const uint8_t *mask_left, const uint8_t *mask_right, int mask_stride,
+                          FeStereoInfo *info);
+/* Pipelined form (as plviwo_fe_submit / _collect): the frame-independent work of both images runs up to cfg.lookahead
+ * pairs ahead; images are host or device pointers (on_device). */
+int plviwo_fe_stereo_submit(FeStereoHandle *h, double timestamp, const uint8_t *image_left, const uint8_t *image_right, int stride,
+                            int on_device, const uint8_t *mask_left, const uint8_t *mask_right, int mask_stride);
+int plviwo_fe_stereo_collect(FeStereoHandle *h, FeStereoInfo *info);
+int plviwo_fe_stereo_get_point_rows(FeStereoHandle *h, int cam, FePointRow *out, int cap, int *n_out);
+int plviwo_fe_stereo_get_last_obs(FeStereoHandle *h, int cam, uint64_t *ids, float *uv /* 2 per point */, int cap, int *n_out);
+/* State blob: 32-byte header (magic 'PLVS', currid, sizes) followed by one monocular state blob per camera. */
+int plviwo_fe_stereo_get_state(FeStereoHandle *h, void *buf, size_t cap, size_t *n_bytes);
+int plviwo_fe_stereo_set_state(FeStereoHandle *h, const void *buf, size_t n_bytes);
+int plviwo_fe_stereo_get_stage_times(FeStereoHandle *h, FeStageTimes *out, int reset);   /* both cameras summed */
+
 /* ---- stand-alone kernels (tests / micro-benchmarks; all pointers are HOST buffers) --------------------- */
 int plviwo_op_equalize_pyramid(int device, const uint8_t *img, int w, int h, int levels /* maxLevel */,
                                uint8_t *out_levels /* concatenated tight levels 0..maxLevel */, uint8_t *out_half);

@@ -67,6 +67,13 @@ class FeFrameInfo(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class FeStereoInfo(C.Structure):
+    _fields_ = [("timestamp", C.c_double), ("n_point_rows", C.c_int32 * 2), ("n_last_obs", C.c_int32 * 2), ("reset", C.c_int32),
+                ("first_frame", C.c_int32), ("detection_ran", C.c_int32 * 2), ("n_detected", C.c_int32 * 2),
+                ("n_stereo_new", C.c_int32), ("n_lk_in", C.c_int32 * 2), ("n_klt_ok", C.c_int32 * 2),
+                ("n_ransac_ok", C.c_int32 * 2), ("n_stereo_rows", C.c_int32)]
+
+
 class FePlayStats(C.Structure):
     _fields_ = [("frames", C.c_uint64), ("point_rows", C.c_uint64), ("line_rows", C.c_uint64), ("resets", C.c_uint64),
                 ("checksum", C.c_double)]
@@ -93,6 +100,10 @@ EXPORTS = [
     "plviwo_fe_set_state", "plviwo_fe_enable_taps", "plviwo_fe_tap", "plviwo_fe_enable_timing", "plviwo_fe_get_stage_times",
     "plviwo_op_equalize_pyramid", "plviwo_op_clahe", "plviwo_op_fast_cell", "plviwo_op_sort_corners", "plviwo_op_corner_subpix", "plviwo_op_lk", "plviwo_op_undistort",
     "plviwo_op_canny_half", "plviwo_op_fld", "plviwo_op_image_kernels_time", "plviwo_op_ransac_fundamental",
+    "plviwo_fe_stereo_create", "plviwo_fe_stereo_destroy", "plviwo_fe_stereo_last_error", "plviwo_fe_stereo_set_calib",
+    "plviwo_fe_stereo_set_num_features", "plviwo_fe_stereo_change_feat_id", "plviwo_fe_stereo_feed", "plviwo_fe_stereo_submit",
+    "plviwo_fe_stereo_collect", "plviwo_fe_stereo_get_point_rows", "plviwo_fe_stereo_get_last_obs", "plviwo_fe_stereo_get_state",
+    "plviwo_fe_stereo_set_state", "plviwo_fe_stereo_get_stage_times",
 ]
 
 
@@ -129,6 +140,24 @@ def lib() -> C.CDLL:
         L.plviwo_fe_enable_timing.argtypes = [C.c_void_p, C.c_int]
         L.plviwo_fe_enable_taps.argtypes = [C.c_void_p, C.c_int]
         L.plviwo_fe_get_stage_times.argtypes = [C.c_void_p, C.POINTER(FeStageTimes), C.c_int]
+        L.plviwo_fe_stereo_last_error.restype = C.c_char_p
+        L.plviwo_fe_stereo_last_error.argtypes = [C.c_void_p]
+        L.plviwo_fe_stereo_create.argtypes = [C.POINTER(FeConfig), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int,
+                                              C.POINTER(C.c_void_p)]
+        L.plviwo_fe_stereo_destroy.argtypes = [C.c_void_p]
+        L.plviwo_fe_stereo_set_calib.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.plviwo_fe_stereo_set_num_features.argtypes = [C.c_void_p, C.c_int]
+        L.plviwo_fe_stereo_change_feat_id.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+        L.plviwo_fe_stereo_feed.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_int, C.POINTER(FeStereoInfo)]
+        L.plviwo_fe_stereo_submit.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_int]
+        L.plviwo_fe_stereo_collect.argtypes = [C.c_void_p, C.POINTER(FeStereoInfo)]
+        L.plviwo_fe_stereo_get_point_rows.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.plviwo_fe_stereo_get_last_obs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.plviwo_fe_stereo_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.plviwo_fe_stereo_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.plviwo_fe_stereo_get_stage_times.argtypes = [C.c_void_p, C.POINTER(FeStageTimes), C.c_int]
         L.plviwo_fe_default_config.argtypes = [C.POINTER(FeConfig)]
         L.plviwo_fe_default_config.restype = None
         L.plviwo_fe_device_count.argtypes = [C.POINTER(C.c_int)]
@@ -465,6 +494,144 @@ _STATE_MAGIC = 0x504C5657
 _STATE_HDR = np.dtype([("magic", "<u4"), ("version", "<u4"), ("w", "<i4"), ("h", "<i4"), ("currid", "<u8"),
                        ("line_currid", "<u8"), ("n_pts", "<i4"), ("n_lines", "<i4"), ("has_image", "<i4"),
                        ("has_mask", "<i4"), ("n_pol", "<i4"), ("reserved", "<i4")])
+
+
+class StereoFrontEnd:
+    """One stereo rig: ov_core::TrackKLT with use_stereo = true behind one FeStereoHandle (camera 0 = left, 1 = right)."""
+
+    def __init__(self, cfg: Optional[FeConfig] = None, K_right=None, D_right=None, device: int = 0, **kw):
+        self.cfg = cfg if cfg is not None else default_config(**kw)
+        self._h = C.c_void_p()
+        self._lib = lib()
+        kr = None if K_right is None else (C.c_double * 4)(*K_right)
+        dr = None if D_right is None else (C.c_double * 4)(*D_right)
+        rc = self._lib.plviwo_fe_stereo_create(C.byref(self.cfg), kr, dr, device, C.byref(self._h))
+        if rc != FE_OK:
+            raise FrontEndError(rc, (self._lib.plviwo_fe_stereo_last_error(None) or b"").decode())
+        self.database = FeatureDatabase()      # one database shared by both cameras (UpdaterCamera.cpp:47-56)
+        self.info = FeStereoInfo()
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.plviwo_fe_stereo_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != FE_OK:
+            raise FrontEndError(rc, (self._lib.plviwo_fe_stereo_last_error(self._h) or b"").decode())
+
+    def set_calib(self, cam: int, K, D):
+        self._check(self._lib.plviwo_fe_stereo_set_calib(self._h, cam, (C.c_double * 4)(*K), (C.c_double * 4)(*D)))
+
+    def set_num_features(self, n: int):
+        self._check(self._lib.plviwo_fe_stereo_set_num_features(self._h, n))
+
+    def change_feat_id(self, id_old: int, id_new: int):
+        self._check(self._lib.plviwo_fe_stereo_change_feat_id(self._h, id_old, id_new))
+
+    @staticmethod
+    def _img(a):
+        if a.dtype != np.uint8 or a.ndim != 2:
+            raise FrontEndError(FE_BAD_ARG, "image must be a 2-D uint8 array")
+        return np.ascontiguousarray(a)
+
+    def feed_new_camera(self, timestamp: float, image_left, image_right, mask_left=None, mask_right=None,
+                        update_db: bool = True) -> FeStereoInfo:
+        """TrackKLT::feed_new_camera with a two-image message (TrackKLT.cpp:34-94 -> feed_stereo)."""
+        il, ir = self._img(image_left), self._img(image_right)
+        if il.shape != ir.shape:
+            raise FrontEndError(FE_BAD_ARG, "left and right image sizes differ")
+        ml = None if mask_left is None else np.ascontiguousarray(mask_left, np.uint8)
+        mr = None if mask_right is None else np.ascontiguousarray(mask_right, np.uint8)
+        self._check(self._lib.plviwo_fe_stereo_feed(
+            self._h, float(timestamp), il.ctypes.data, ir.ctypes.data, il.shape[1], il.shape[0], il.strides[0],
+            None if ml is None else ml.ctypes.data, None if mr is None else mr.ctypes.data, il.shape[1], C.byref(self.info)))
+        if update_db:
+            self._push_rows(timestamp)
+        return self.info
+
+    def submit(self, timestamp: float, image_left, image_right, stride: int = 0, on_device: bool = False):
+        """image_*: numpy arrays (host) or integer device pointers (on_device, with stride)."""
+        if on_device:
+            pl, pr = int(image_left), int(image_right)
+        else:
+            pl, pr, stride = image_left.ctypes.data, image_right.ctypes.data, image_left.strides[0]
+        self._check(self._lib.plviwo_fe_stereo_submit(self._h, float(timestamp), pl, pr, stride, 1 if on_device else 0, None, None, 0))
+
+    def collect(self) -> FeStereoInfo:
+        self._check(self._lib.plviwo_fe_stereo_collect(self._h, C.byref(self.info)))
+        return self.info
+
+    def _push_rows(self, timestamp):
+        for cam in (0, 1):    # left rows first, then right (TrackKLT.cpp:352-363)
+            for r in self.point_rows(cam):
+                self.database.update_feature(int(r["id"]), timestamp, cam, float(r["u"]), float(r["v"]), float(r["un"]), float(r["vn"]))
+
+    def point_rows(self, cam: int) -> np.ndarray:
+        n = C.c_int(0)
+        self._check(self._lib.plviwo_fe_stereo_get_point_rows(self._h, cam, None, 0, C.byref(n)))
+        out = np.zeros((n.value,), POINT_ROW_DTYPE)
+        if n.value:
+            self._check(self._lib.plviwo_fe_stereo_get_point_rows(self._h, cam, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def _last(self, cam: int):
+        n = C.c_int(0)
+        self._check(self._lib.plviwo_fe_stereo_get_last_obs(self._h, cam, None, None, 0, C.byref(n)))
+        ids = np.zeros((n.value,), np.uint64)
+        uv = np.zeros((n.value, 2), np.float32)
+        if n.value:
+            self._check(self._lib.plviwo_fe_stereo_get_last_obs(self._h, cam, ids.ctypes.data, uv.ctypes.data, n.value, C.byref(n)))
+        return ids, uv
+
+    def get_last_obs(self):
+        return {cam: self._last(cam)[1] for cam in (0, 1)}
+
+    def get_last_ids(self):
+        return {cam: self._last(cam)[0] for cam in (0, 1)}
+
+    def get_feature_database(self) -> FeatureDatabase:
+        return self.database
+
+    def get_state(self) -> bytes:
+        n = C.c_size_t(0)
+        self._check(self._lib.plviwo_fe_stereo_get_state(self._h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        self._check(self._lib.plviwo_fe_stereo_get_state(self._h, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value]
+
+    def set_state(self, blob: bytes):
+        self._check(self._lib.plviwo_fe_stereo_set_state(self._h, blob, len(blob)))
+
+    def stage_times(self, reset: bool = False) -> Dict[str, object]:
+        t = FeStageTimes()
+        self._check(self._lib.plviwo_fe_stereo_get_stage_times(self._h, C.byref(t), 1 if reset else 0))
+        return {"frames": int(t.frames), "kernel_launches_total": int(t.kernel_launches_total), "h2d_bytes": int(t.h2d_bytes),
+                "d2h_bytes": int(t.d2h_bytes)}
+
+
+_STEREO_HDR = np.dtype([("magic", "<u4"), ("version", "<u4"), ("currid", "<u8"), ("size", "<u8", (2,))])
+
+
+def pack_stereo_state(currid: int, blob_left: bytes, blob_right: bytes) -> bytes:
+    """Stereo state blob: header + one monocular blob (pack_state) per camera; the per-camera currid fields are ignored."""
+    hdr = np.zeros((), _STEREO_HDR)
+    hdr["magic"], hdr["version"], hdr["currid"] = 0x504C5653, 1, currid
+    hdr["size"] = (len(blob_left), len(blob_right))
+    return hdr.tobytes() + blob_left + blob_right
+
+
+def unpack_stereo_state(blob: bytes):
+    hdr = np.frombuffer(blob, _STEREO_HDR, 1)[0]
+    o = _STEREO_HDR.itemsize
+    a, b = int(hdr["size"][0]), int(hdr["size"][1])
+    return int(hdr["currid"]), unpack_state(blob[o:o + a]), unpack_state(blob[o + a:o + a + b])
 
 
 def pack_state(width, height, currid, pts_last, ids_last, img_last_eq=None, mask_last=None, line_currid=1,

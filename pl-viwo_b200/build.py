@@ -21,11 +21,12 @@ SOURCES = [
     ("kernels_track.cu", ["--fmad=false"]),
     ("kernels_lines.cu", ["--fmad=false"]),
     ("fe_context.cu", []),
+    ("fe_stereo.cu", []),
     ("fe_capi.cu", []),
     ("ransac.cpp", []),
     ("host_simd.cpp", []),
 ]
-HEADERS = ["fe_kernels.h", "fe_context.h", "tma_bulk.h", "introsort.h", os.path.join("..", "..", "include", "plviwo_fe.h")]
+HEADERS = ["fe_kernels.h", "fe_context.h", "fe_stereo.h", "tma_bulk.h", "introsort.h", os.path.join("..", "..", "include", "plviwo_fe.h")]
 
 
 def _nvcc() -> str:

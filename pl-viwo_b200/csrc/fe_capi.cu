@@ -7,11 +7,16 @@
 #include <vector>
 
 #include "fe_context.h"
+#include "fe_stereo.h"
 
 using namespace plviwo;
 
 struct FeHandle {
   FeContext *ctx;
+};
+
+struct FeStereoHandle {
+  FeStereo *st;
 };
 
 static thread_local std::string g_create_error;
@@ -632,6 +637,133 @@ int plviwo_op_ransac_fundamental(const float *p0n, const float *p1n, int n, doub
   if (n_inliers) *n_inliers = valid ? good : -1;
   return FE_OK;
   API_END
+}
+
+// ---- stereo rig (TrackKLT with use_stereo = true) -----------------------------------------------------------
+int plviwo_fe_stereo_create(const FeConfig *cfg, const double K_right[4], const double D_right[4], int device,
+                            FeStereoHandle **out) {
+  API_BEGIN
+  if (!cfg || !out) return FE_BAD_ARG;
+  *out = nullptr;
+  auto bad = [&](const char *why) {
+    g_create_error = why;
+    return FE_BAD_ARG;
+  };
+  if (cfg->width < 64 || cfg->height < 64 || cfg->width > 4095 || cfg->height > 4095) return bad("image size must be in [64, 4095]");
+  if (cfg->win_size < 3 || cfg->win_size > kMaxWin || (cfg->win_size & 1) == 0) return bad("win_size must be odd and in [3, 31]");
+  if (cfg->pyr_levels < 0 || cfg->pyr_levels >= kMaxLevels) return bad("pyr_levels must be in [0, 7]");
+  if (cfg->grid_x < 1 || cfg->grid_y < 1 || cfg->min_px_dist < 1 || cfg->num_features < 1) return bad("bad grid / distance / feature count");
+  if (cfg->histogram_method != FE_HIST_NONE && cfg->histogram_method != FE_HIST_HISTOGRAM && cfg->histogram_method != FE_HIST_CLAHE)
+    return bad("bad histogram_method");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    g_create_error = "no CUDA device: this front end has no CPU fallback";
+    return FE_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) return bad("device index out of range");
+  FeStereo *st = new FeStereo(*cfg, K_right, D_right, device);
+  int rc = st->init();
+  if (rc != FE_OK) {
+    g_create_error = st->last_error;
+    delete st;
+    return rc;
+  }
+  *out = new FeStereoHandle{st};
+  return FE_OK;
+  API_END
+}
+
+int plviwo_fe_stereo_destroy(FeStereoHandle *h) {
+  API_BEGIN
+  if (!h) return FE_BAD_ARG;
+  delete h->st;
+  delete h;
+  return FE_OK;
+  API_END
+}
+
+const char *plviwo_fe_stereo_last_error(const FeStereoHandle *h) { return h ? h->st->last_error.c_str() : g_create_error.c_str(); }
+
+int plviwo_fe_stereo_set_calib(FeStereoHandle *h, int cam, const double K[4], const double D[4]) {
+  if (!h || !K || !D) return FE_BAD_ARG;
+  return h->st->set_calib(cam, K, D);
+}
+int plviwo_fe_stereo_set_num_features(FeStereoHandle *h, int n) {
+  if (!h || n < 1) return FE_BAD_ARG;
+  return h->st->set_num_features(n);
+}
+int plviwo_fe_stereo_change_feat_id(FeStereoHandle *h, uint64_t id_old, uint64_t id_new) {
+  if (!h) return FE_BAD_ARG;
+  return h->st->change_feat_id(id_old, id_new);
+}
+
+int plviwo_fe_stereo_feed(FeStereoHandle *h, double timestamp, const uint8_t *image_left, const uint8_t *image_right, int width,
+                          int height, int stride, const uint8_t *mask_left, const uint8_t *mask_right, int mask_stride,
+                          FeStereoInfo *info) {
+  API_BEGIN
+  if (!h) return FE_BAD_ARG;
+  const uint8_t *img[2] = {image_left, image_right};
+  const uint8_t *msk[2] = {mask_left, mask_right};
+  return h->st->feed(timestamp, img, width, height, stride, false, msk, mask_stride, info);
+  API_END
+}
+
+int plviwo_fe_stereo_submit(FeStereoHandle *h, double timestamp, const uint8_t *image_left, const uint8_t *image_right, int stride,
+                            int on_device, const uint8_t *mask_left, const uint8_t *mask_right, int mask_stride) {
+  API_BEGIN
+  if (!h || !image_left || !image_right) return FE_BAD_ARG;
+  const uint8_t *img[2] = {image_left, image_right};
+  const uint8_t *msk[2] = {mask_left, mask_right};
+  return h->st->submit(timestamp, img, stride, on_device != 0, msk, mask_stride);
+  API_END
+}
+
+int plviwo_fe_stereo_collect(FeStereoHandle *h, FeStereoInfo *info) {
+  API_BEGIN
+  if (!h) return FE_BAD_ARG;
+  return h->st->collect(info);
+  API_END
+}
+
+int plviwo_fe_stereo_get_point_rows(FeStereoHandle *h, int cam, FePointRow *out, int cap, int *n_out) {
+  if (!h || cam < 0 || cam > 1) return FE_BAD_ARG;
+  return copy_out(h->st->rows(cam), out, cap, n_out);
+}
+
+int plviwo_fe_stereo_get_last_obs(FeStereoHandle *h, int cam, uint64_t *ids, float *uv, int cap, int *n_out) {
+  if (!h || cam < 0 || cam > 1) return FE_BAD_ARG;
+  const auto &p = h->st->last_obs(cam);
+  const auto &id = h->st->last_ids(cam);
+  if (n_out) *n_out = (int)p.size();
+  if (!ids && !uv) return FE_OK;
+  if (cap < (int)p.size()) return FE_OVERFLOW;
+  for (size_t i = 0; i < p.size(); i++) {
+    if (ids) ids[i] = id[i];
+    if (uv) {
+      uv[2 * i] = p[i].x;
+      uv[2 * i + 1] = p[i].y;
+    }
+  }
+  return FE_OK;
+}
+
+int plviwo_fe_stereo_get_state(FeStereoHandle *h, void *buf, size_t cap, size_t *n_bytes) {
+  API_BEGIN
+  if (!h) return FE_BAD_ARG;
+  return h->st->get_state(buf, cap, n_bytes);
+  API_END
+}
+int plviwo_fe_stereo_set_state(FeStereoHandle *h, const void *buf, size_t n_bytes) {
+  API_BEGIN
+  if (!h) return FE_BAD_ARG;
+  return h->st->set_state(buf, n_bytes);
+  API_END
+}
+int plviwo_fe_stereo_get_stage_times(FeStereoHandle *h, FeStageTimes *out, int reset) {
+  if (!h || !out) return FE_BAD_ARG;
+  *out = h->st->snapshot_times(reset != 0);
+  return FE_OK;
 }
 
 }  // extern "C"

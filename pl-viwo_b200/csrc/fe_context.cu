@@ -48,6 +48,8 @@ struct HostTimer {  // accumulates wall time into FeStageTimes::host_ms[idx]
 // into the frame's FrameResult.
 static thread_local std::string t_err;
 
+std::string &FeContext::thread_error() { return t_err; }
+
 static inline void cpu_pause() {
 #if defined(__x86_64__)
   __builtin_ia32_pause();
@@ -224,8 +226,10 @@ int FeContext::init() {
   }
   occ_bits_.assign((size_t)((W_ + 63) / 64) * H_, 0);
   layout_cells();
-  klt_thread_ = std::thread([this] { klt_main(); });
-  line_thread_ = std::thread([this] { line_main(); });
+  if (!external_) {
+    klt_thread_ = std::thread([this] { klt_main(); });
+    line_thread_ = std::thread([this] { line_main(); });
+  }
 
   max_pts_ = std::max(4096, 8 * cfg_.num_features) + 4096 * (cfg_.line_samples > 0 ? 8 : 0);
   FE_CUDA(cudaMalloc(&d_pts0_, (size_t)max_pts_ * sizeof(float2)));
@@ -579,7 +583,7 @@ int FeContext::submit(double t, const uint8_t *image, int stride, bool on_device
 }
 
 int FeContext::submit_impl(double t, const uint8_t *image, int stride, bool on_device, const uint8_t *mask, int mask_stride,
-                           const double vp[6]) {
+                           const double vp[6], int *slot_out) {
   HostTimer ht(&mst_.host_ms[0]);
   FE_CUDA(cudaSetDevice(device_));
   int si = -1;
@@ -634,6 +638,8 @@ int FeContext::submit_impl(double t, const uint8_t *image, int stride, bool on_d
   rc = enqueue_frame_independent(s);
   if (rc) return rc;
   s.sc_prev = -1;
+  if (slot_out) *slot_out = si;
+  if (external_) return FE_OK;   // the owner (FeStereo) runs the state machine and releases the slot
   if (prev_submit_slot_ >= 0) {
     rc = track_candidates(slots_[prev_submit_slot_], s);
     if (rc) return rc;
@@ -1039,64 +1045,72 @@ int FeContext::speculate(FrameSlot &prev, const float2 *lk_pts, const uint8_t *l
   return FE_OK;
 }
 
-int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, std::vector<uint64_t> &ids0, std::vector<int> &src,
-                                 FrameResult &res) {
-  src.resize(pts0.size(), -1);   // per point: index into the speculative LK arrays, -1 none, -(2 + i) = candidate i
-  HostTimer ht(&kst_.host_ms[1]);
-  FeFrameInfo *info = &res.info;
+// First loop of the top-off detection (TrackKLT.cpp:411-464; stereo: :545-598 left, :692-748 right): drop points near the
+// border, outside the grids, on an occupied min-distance cell (unless stereo_ids holds their id, :720-726) or on the mask.
+void FeContext::filter_existing(const std::vector<uint8_t> &mask_test, std::vector<Pt> &pts0, std::vector<uint64_t> &ids0,
+                                std::vector<int> *src, const std::vector<uint64_t> *stereo_ids, OccGrids &g) const {
+  const int d = cfg_.min_px_dist;
+  const int cols = W_, rows = H_;
+  const int close_w = (int)((float)cols / (float)d), close_h = (int)((float)rows / (float)d);
+  g.close_w = close_w;
+  g.close_h = close_h;
+  g.close.assign((size_t)close_w * close_h, 0);
+  const float size_x = (float)cols / (float)cfg_.grid_x, size_y = (float)rows / (float)cfg_.grid_y;
+  const int gx = cfg_.grid_x, gy = cfg_.grid_y;
+  g.grid.assign((size_t)gx * gy, 0);
+  g.rects.clear();
+  size_t keep = 0;
+  for (size_t k = 0; k < pts0.size(); k++) {
+    const Pt kp = pts0[k];
+    int x = (int)kp.x, y = (int)kp.y;
+    const int edge = 10;
+    if (x < edge || x >= cols - edge || y < edge || y >= rows - edge) continue;
+    int x_close = (int)(kp.x / (float)d), y_close = (int)(kp.y / (float)d);
+    if (x_close < 0 || x_close >= close_w || y_close < 0 || y_close >= close_h) continue;
+    int x_grid = (int)std::floor(kp.x / size_x), y_grid = (int)std::floor(kp.y / size_y);
+    if (x_grid < 0 || x_grid >= gx || y_grid < 0 || y_grid >= gy) continue;
+    if (g.close[(size_t)y_close * close_w + x_close] > 127) {
+      if (!stereo_ids || std::find(stereo_ids->begin(), stereo_ids->end(), ids0[k]) == stereo_ids->end()) continue;
+    }
+    if (!mask_test.empty() && mask_test[(size_t)y * cols + x] > 127) continue;
+    g.close[(size_t)y_close * close_w + x_close] = 255;
+    uint8_t &c = g.grid[(size_t)y_grid * gx + x_grid];
+    if (c < 255) c += 1;
+    if (x - d >= 0 && x + d < cols && y - d >= 0 && y + d < rows) g.rects.emplace_back(x, y);
+    pts0[keep] = kp;
+    ids0[keep] = ids0[k];
+    if (src) (*src)[keep] = (*src)[k];
+    keep++;
+  }
+  pts0.resize(keep);
+  ids0.resize(keep);
+  if (src) src->resize(keep);
+}
+
+// Valid cells (:479-492) + Grider_GRID::perform_griding (Grider_GRID.h:74-180) on the frame's candidate table.  FAST, the
+// unstable sort, the top-num_features_grid cut and cornerSubPix do not depend on tracker state and were computed for
+// EVERY cell when the frame was submitted; only the state-dependent part is left: which cells are valid and the mask
+// test (:140-147).  mask_resize is the mask the reference resizes to the grid, mask_clone the one it clones into
+// mask_updated (the same for the monocular path; the stereo path clones the LEFT mask for the right image, :691).
+int FeContext::grid_candidates(FrameSlot &slot, const std::vector<uint8_t> &mask_resize, const std::vector<uint8_t> &mask_clone,
+                               const OccGrids &g, std::vector<Pt> &ext, std::vector<int> &ext_cand, FrameResult &res) {
   std::vector<int32_t> &tap_fast_ = res.tap_fast;
   std::vector<float> &tap_subpix_ = res.tap_subpix;
   const bool taps = this->taps.load(std::memory_order_relaxed);
   const int d = cfg_.min_px_dist;
   const int cols = W_, rows = H_;
-  const int close_w = (int)((float)cols / (float)d), close_h = (int)((float)rows / (float)d);
-  std::vector<uint8_t> grid_close((size_t)close_w * close_h, 0);
-  const float size_x = (float)cols / (float)cfg_.grid_x, size_y = (float)rows / (float)cfg_.grid_y;
   const int gx = cfg_.grid_x, gy = cfg_.grid_y;
-  std::vector<uint8_t> grid_grid((size_t)gx * gy, 0);
-  // mask0_updated = mask0.clone() plus filled squares: kept as a bit mask, only built if detection really runs
   const int bw = (cols + 63) / 64;
-  std::vector<std::pair<int, int>> rects;
-  {
-    size_t keep = 0;
-    for (size_t k = 0; k < pts0.size(); k++) {  // TrackKLT.cpp:411-464
-      const Pt kp = pts0[k];
-      int x = (int)kp.x, y = (int)kp.y;
-      const int edge = 10;
-      if (x < edge || x >= cols - edge || y < edge || y >= rows - edge) continue;
-      int x_close = (int)(kp.x / (float)d), y_close = (int)(kp.y / (float)d);
-      if (x_close < 0 || x_close >= close_w || y_close < 0 || y_close >= close_h) continue;
-      int x_grid = (int)std::floor(kp.x / size_x), y_grid = (int)std::floor(kp.y / size_y);
-      if (x_grid < 0 || x_grid >= gx || y_grid < 0 || y_grid >= gy) continue;
-      if (grid_close[(size_t)y_close * close_w + x_close] > 127) continue;
-      if (mask_hit(img, cols, y, x)) continue;
-      grid_close[(size_t)y_close * close_w + x_close] = 255;
-      uint8_t &g = grid_grid[(size_t)y_grid * gx + x_grid];
-      if (g < 255) g += 1;
-      if (x - d >= 0 && x + d < cols && y - d >= 0 && y + d < rows) rects.emplace_back(x, y);
-      pts0[keep] = kp;
-      ids0[keep] = ids0[k];
-      src[keep] = src[k];
-      keep++;
-    }
-    pts0.resize(keep);
-    ids0.resize(keep);
-    src.resize(keep);
-  }
   const double min_feat_percent = 0.50;
-  int num_featsneeded = cfg_.num_features - (int)pts0.size();
-  if (num_featsneeded < std::min(20, (int)(min_feat_percent * cfg_.num_features))) return FE_OK;  // :468-471
-  info->detection_ran = 1;
-
   // mask0_grid = resize(mask0, grid, INTER_NEAREST) (:479-480)
   std::vector<uint8_t> mask_grid((size_t)gx * gy, 0);
-  if (!img.mask.empty()) {
+  if (!mask_resize.empty()) {
     const double ifx = 1.0 / ((double)gx / (double)cols), ify = 1.0 / ((double)gy / (double)rows);
     for (int y = 0; y < gy; y++) {
       int sy = std::min((int)std::floor(y * ify), rows - 1);
       for (int x = 0; x < gx; x++) {
         int sx = std::min((int)std::floor(x * ifx), cols - 1);
-        mask_grid[(size_t)y * gx + x] = img.mask[(size_t)sy * cols + sx];
+        mask_grid[(size_t)y * gx + x] = mask_resize[(size_t)sy * cols + sx];
       }
     }
   }
@@ -1105,90 +1119,103 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
   std::vector<std::pair<int, int>> valid_locs;
   for (int x = 0; x < gx; x++)        // x-major order (:486-492)
     for (int y = 0; y < gy; y++)
-      if ((int)grid_grid[(size_t)y * gx + x] < num_features_grid_req && (int)mask_grid[(size_t)y * gx + x] != 255)
+      if ((int)g.grid[(size_t)y * gx + x] < num_features_grid_req && (int)mask_grid[(size_t)y * gx + x] != 255)
         valid_locs.emplace_back(x, y);
 
-  // ---- Grider_GRID::perform_griding (Grider_GRID.h:74-180).  FAST, the unstable sort, the top-num_features_grid cut
-  // and cornerSubPix do not depend on tracker state and were computed for EVERY cell when the frame was submitted
-  // (run_predetection); only the state-dependent part is left: which cells are valid and the mask test (:140-147).
-  std::vector<Pt> ext;  // pts0_ext after sub-pixel refinement
-  std::vector<int> ext_cand;   // ... and which candidate of the frame's table each one is
+  ext.clear();        // pts0_ext after sub-pixel refinement
+  ext_cand.clear();   // ... and which candidate of the frame's table each one is
   if (taps) {
     tap_fast_.clear();
     tap_subpix_.clear();
   }
-  if (!valid_locs.empty()) {
-    FrameSlot &slot = const_cast<FrameSlot &>(img);
-    if (slot.predet_num_features != cfg_.num_features) {   // set_num_features() after the frame was submitted
-      int rc = wait_predetection(slot);
-      if (rc) return rc;
-      rc = enqueue_fast_all_cells(slot);
-      if (rc) return rc;
-      rc = record_fast_path(slot, slot.s_b);
-      if (rc) return rc;
-      slot.seq_fast++;
-      FE_CUDA(cudaEventRecord(slot.ev_fast, slot.s_b));
-    }
-    {
-      HostTimer hw(&kst_.host_ms[7]);
-      int rc = wait_predetection(slot);
-      if (rc) return rc;
-    }
-    bool any_cell = false;
-    for (auto &loc : valid_locs) any_cell = any_cell || slot.cell_of_loc[(size_t)loc.first * gy + loc.second] >= 0;
-    if (any_cell) {
-      // mask0_updated as a bit mask: caller mask > 127 or inside a (2d+1)^2 square of a kept point (:457-461)
-      std::fill(occ_bits_.begin(), occ_bits_.end(), 0);
-      if (!img.mask.empty())
-        for (int y = 0; y < rows; y++)
-          for (int x = 0; x < cols; x++)
-            if (img.mask[(size_t)y * cols + x] > 127) occ_bits_[(size_t)y * bw + (x >> 6)] |= 1ull << (x & 63);
-      for (auto &rc : rects) {
-        int x0 = rc.first - d, x1 = rc.first + d;
-        for (int y = rc.second - d; y <= rc.second + d; y++) {
-          uint64_t *row = &occ_bits_[(size_t)y * bw];
-          int w0 = x0 >> 6, w1 = x1 >> 6;
-          uint64_t m0 = ~0ull << (x0 & 63), m1 = (x1 & 63) == 63 ? ~0ull : ((1ull << ((x1 & 63) + 1)) - 1);
-          if (w0 == w1) {
-            row[w0] |= m0 & m1;
-          } else {
-            row[w0] |= m0;
-            for (int w = w0 + 1; w < w1; w++) row[w] = ~0ull;
-            row[w1] |= m1;
-          }
-        }
-      }
-      for (auto &loc : valid_locs) {     // cells in valid_locs order (:108-156)
-        const int c = slot.cell_of_loc[(size_t)loc.first * gy + loc.second];
-        if (c < 0) continue;
-        if (taps)
-          for (int k = slot.cell_kps_first[c]; k < slot.cell_kps_first[c + 1]; k++)
-            tap_fast_.insert(tap_fast_.end(), {loc.first, loc.second, slot.cell_kps_tap[3 * k], slot.cell_kps_tap[3 * k + 1],
-                                               slot.cell_kps_tap[3 * k + 2]});
-        const int nfg_t = slot.predet_nfg, cnt = std::min(slot.h_cand_cnt[c], nfg_t);
-        for (int k = 0; k < cnt; k++) {   // :133-149
-          const int i = c * nfg_t + k;    // slot of the candidate in the frame's fixed-stride table
-          const Pt p = Pt{slot.h_cand_in[i].x, slot.h_cand_in[i].y};
-          if ((int)p.x < 0 || (int)p.x > cols || (int)p.y < 0 || (int)p.y > rows) continue;
-          const int ix = (int)p.x, iy = (int)p.y;
-          if (iy >= rows || ix >= cols) continue;  // the reference would read out of bounds here; cannot happen
-          if ((occ_bits_[(size_t)iy * bw + (ix >> 6)] >> (ix & 63)) & 1ull) continue;
-          const Pt pr = Pt{slot.h_cand_out[i].x, slot.h_cand_out[i].y};
-          ext.push_back(pr);                    // cornerSubPix result of exactly this point (:163-179)
-          ext_cand.push_back(i);
-          if (taps) tap_subpix_.insert(tap_subpix_.end(), {p.x, p.y, pr.x, pr.y});
-        }
+  if (valid_locs.empty()) return FE_OK;
+  if (slot.predet_num_features != cfg_.num_features) {   // set_num_features() after the frame was submitted
+    int rc = wait_predetection(slot);
+    if (rc) return rc;
+    rc = enqueue_fast_all_cells(slot);
+    if (rc) return rc;
+    rc = record_fast_path(slot, slot.s_b);
+    if (rc) return rc;
+    slot.seq_fast++;
+    FE_CUDA(cudaEventRecord(slot.ev_fast, slot.s_b));
+  }
+  {
+    HostTimer hw(&kst_.host_ms[7]);
+    int rc = wait_predetection(slot);
+    if (rc) return rc;
+  }
+  bool any_cell = false;
+  for (auto &loc : valid_locs) any_cell = any_cell || slot.cell_of_loc[(size_t)loc.first * gy + loc.second] >= 0;
+  if (!any_cell) return FE_OK;
+  // mask0_updated as a bit mask: caller mask > 127 or inside a (2d+1)^2 square of a kept point (:457-461)
+  std::fill(occ_bits_.begin(), occ_bits_.end(), 0);
+  if (!mask_clone.empty())
+    for (int y = 0; y < rows; y++)
+      for (int x = 0; x < cols; x++)
+        if (mask_clone[(size_t)y * cols + x] > 127) occ_bits_[(size_t)y * bw + (x >> 6)] |= 1ull << (x & 63);
+  for (auto &rc : g.rects) {
+    int x0 = rc.first - d, x1 = rc.first + d;
+    for (int y = rc.second - d; y <= rc.second + d; y++) {
+      uint64_t *row = &occ_bits_[(size_t)y * bw];
+      int w0 = x0 >> 6, w1 = x1 >> 6;
+      uint64_t m0 = ~0ull << (x0 & 63), m1 = (x1 & 63) == 63 ? ~0ull : ((1ull << ((x1 & 63) + 1)) - 1);
+      if (w0 == w1) {
+        row[w0] |= m0 & m1;
+      } else {
+        row[w0] |= m0;
+        for (int w = w0 + 1; w < w1; w++) row[w] = ~0ull;
+        row[w1] |= m1;
       }
     }
   }
+  for (auto &loc : valid_locs) {     // cells in valid_locs order (:108-156)
+    const int c = slot.cell_of_loc[(size_t)loc.first * gy + loc.second];
+    if (c < 0) continue;
+    if (taps)
+      for (int k = slot.cell_kps_first[c]; k < slot.cell_kps_first[c + 1]; k++)
+        tap_fast_.insert(tap_fast_.end(), {loc.first, loc.second, slot.cell_kps_tap[3 * k], slot.cell_kps_tap[3 * k + 1],
+                                           slot.cell_kps_tap[3 * k + 2]});
+    const int nfg_t = slot.predet_nfg, cnt = std::min(slot.h_cand_cnt[c], nfg_t);
+    for (int k = 0; k < cnt; k++) {   // :133-149
+      const int i = c * nfg_t + k;    // slot of the candidate in the frame's fixed-stride table
+      const Pt p = Pt{slot.h_cand_in[i].x, slot.h_cand_in[i].y};
+      if ((int)p.x < 0 || (int)p.x > cols || (int)p.y < 0 || (int)p.y > rows) continue;
+      const int ix = (int)p.x, iy = (int)p.y;
+      if (iy >= rows || ix >= cols) continue;  // the reference would read out of bounds here; cannot happen
+      if ((occ_bits_[(size_t)iy * bw + (ix >> 6)] >> (ix & 63)) & 1ull) continue;
+      const Pt pr = Pt{slot.h_cand_out[i].x, slot.h_cand_out[i].y};
+      ext.push_back(pr);                    // cornerSubPix result of exactly this point (:163-179)
+      ext_cand.push_back(i);
+      if (taps) tap_subpix_.insert(tap_subpix_.end(), {p.x, p.y, pr.x, pr.y});
+    }
+  }
+  return FE_OK;
+}
+
+int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, std::vector<uint64_t> &ids0, std::vector<int> &src,
+                                 FrameResult &res) {
+  src.resize(pts0.size(), -1);   // per point: index into the speculative LK arrays, -1 none, -(2 + i) = candidate i
+  HostTimer ht(&kst_.host_ms[1]);
+  FeFrameInfo *info = &res.info;
+  const int d = cfg_.min_px_dist;
+  OccGrids g;
+  filter_existing(img.mask, pts0, ids0, &src, nullptr, g);   // TrackKLT.cpp:411-464
+  const double min_feat_percent = 0.50;
+  int num_featsneeded = cfg_.num_features - (int)pts0.size();
+  if (num_featsneeded < std::min(20, (int)(min_feat_percent * cfg_.num_features))) return FE_OK;  // :468-471
+  info->detection_ran = 1;
+  std::vector<Pt> ext;
+  std::vector<int> ext_cand;
+  int rc = grid_candidates(const_cast<FrameSlot &>(img), img.mask, img.mask, g, ext, ext_cand, res);
+  if (rc) return rc;
   // reject new points that are close to an existing one (:497-512), then hand out ids (:519-527)
   int added = 0;
   for (size_t e = 0; e < ext.size(); e++) {
     const Pt &kp = ext[e];
     int x_grid = (int)(kp.x / (float)d), y_grid = (int)(kp.y / (float)d);
-    if (x_grid < 0 || x_grid >= close_w || y_grid < 0 || y_grid >= close_h) continue;
-    if (grid_close[(size_t)y_grid * close_w + x_grid] > 127) continue;
-    grid_close[(size_t)y_grid * close_w + x_grid] = 255;
+    if (x_grid < 0 || x_grid >= g.close_w || y_grid < 0 || y_grid >= g.close_h) continue;
+    if (g.close[(size_t)y_grid * g.close_w + x_grid] > 127) continue;
+    g.close[(size_t)y_grid * g.close_w + x_grid] = 255;
     pts0.push_back(kp);
     ids0.push_back(++currid_);
     src.push_back(-(2 + ext_cand[e]));   // slot of the candidate in the frame's fixed-stride table

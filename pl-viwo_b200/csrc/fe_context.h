@@ -130,7 +130,18 @@ struct FrameSlot {
   std::vector<int> cell_kps_first;
 };
 
+// Occupancy bookkeeping of one top-off detection (TrackKLT.cpp:401-408): the min-distance grid, the per-cell counts and
+// the squares that mask0_updated gets around every kept point.
+struct OccGrids {
+  int close_w = 0, close_h = 0;
+  std::vector<uint8_t> close, grid;
+  std::vector<std::pair<int, int>> rects;
+};
+
+class FeStereo;
+
 class FeContext {
+  friend class FeStereo;
  public:
   FeContext(const FeConfig &cfg, int device);
   ~FeContext();
@@ -157,6 +168,7 @@ class FeContext {
   int tap(int what, void *buf, size_t cap, size_t *n_bytes);
 
   const FeConfig &cfg() const { return cfg_; }
+  static std::string &thread_error();   // error text of the calling thread (what last_error is filled from)
   std::string last_error;
   std::atomic<bool> timing{false};
   std::atomic<bool> taps{false};     // record the debug taps (FAST lists, sub-pixel, LK, FLD) — off on the hot path
@@ -167,7 +179,7 @@ class FeContext {
   int fail(cudaError_t e, const char *what);
   int err(int code, const std::string &msg);
   int submit_impl(double t, const uint8_t *image, int stride, bool on_device, const uint8_t *mask, int mask_stride,
-                  const double vp[6]);
+                  const double vp[6], int *slot_out = nullptr);
   int collect_impl(FeFrameInfo *info);
   void flush_stats(FeStageTimes &local);
   void klt_main();
@@ -188,6 +200,11 @@ class FeContext {
   int klt_feed(FrameSlot &cur);
   int perform_detection(const FrameSlot &img, std::vector<Pt> &pts, std::vector<uint64_t> &ids, std::vector<int> &src,
                         FrameResult &res);
+  // the two halves of the top-off detection that the monocular and the stereo state machines share
+  void filter_existing(const std::vector<uint8_t> &mask_test, std::vector<Pt> &pts, std::vector<uint64_t> &ids, std::vector<int> *src,
+                       const std::vector<uint64_t> *stereo_ids, OccGrids &g) const;
+  int grid_candidates(FrameSlot &slot, const std::vector<uint8_t> &mask_resize, const std::vector<uint8_t> &mask_clone,
+                      const OccGrids &g, std::vector<Pt> &ext, std::vector<int> &ext_cand, FrameResult &res);
   int perform_matching(const FrameSlot &f0, FrameSlot &f1, std::vector<Pt> &pts0, const std::vector<int> &src, bool spec,
                        std::vector<Pt> &pts1, std::vector<uint8_t> &mask_out, bool &mask_empty, FrameResult &res);
   int speculate(FrameSlot &prev, const float2 *lk_pts, const uint8_t *lk_status, int n);
@@ -197,6 +214,7 @@ class FeContext {
   static void undistort_host(const double K[4], const double D[4], float u, float v, float &un, float &vn);
 
   FeConfig cfg_;
+  bool external_ = false;   // the frame-independent pipeline only: a FeStereo owns the tracker state and the slots
   int device_;
   int W_, H_;            // tracking size (= input size, or half of it with cfg.downsample)
   int Win_, Hin_;        // input size

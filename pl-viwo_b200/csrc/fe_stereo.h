@@ -1,0 +1,73 @@
+// Stereo point tracker: ov_core::TrackKLT with use_stereo = true fed two images per message
+// (open_vins/ov_core/src/track/TrackKLT.cpp:202-393 feed_stereo, :530-827 perform_detection_stereo).
+// One FeStereo = one stereo rig on one device.  It owns two FeContext objects in "external" mode — each runs the
+// frame-independent pipeline of one camera (copy, equalise, pyramid, FAST on every cell, std::sort + top-k, cornerSubPix)
+// on its own streams at submit() — and runs the stereo state machine itself at collect().
+#pragma once
+#include <deque>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "fe_context.h"
+
+namespace plviwo {
+
+class FeStereo {
+ public:
+  FeStereo(const FeConfig &cfg, const double K_right[4], const double D_right[4], int device);
+  ~FeStereo();
+  int init();
+
+  int set_calib(int cam, const double K[4], const double D[4]);
+  int set_num_features(int n);
+  int change_feat_id(uint64_t id_old, uint64_t id_new);
+  int submit(double t, const uint8_t *const image[2], int stride, bool on_device, const uint8_t *const mask[2], int mask_stride);
+  int collect(FeStereoInfo *info);
+  int feed(double t, const uint8_t *const image[2], int w, int h, int stride, bool on_device, const uint8_t *const mask[2],
+           int mask_stride, FeStereoInfo *info);
+  int get_state(void *buf, size_t cap, size_t *n_bytes);
+  int set_state(const void *buf, size_t n_bytes);
+  FeStageTimes snapshot_times(bool reset);
+
+  // results of the last collected pair
+  const std::vector<FePointRow> &rows(int cam) const { return rows_[cam]; }
+  const std::vector<Pt> &last_obs(int cam) const { return pts_last_[cam]; }
+  const std::vector<uint64_t> &last_ids(int cam) const { return ids_last_[cam]; }
+  std::string last_error;
+
+ private:
+  struct Match {   // one perform_matching call (TrackKLT.cpp:829-886)
+    int n = 0;
+    bool launched = false, mask_empty = true;
+    std::vector<Pt> pts1;
+    std::vector<uint8_t> mask;
+    std::vector<float2> p1n;
+  };
+  int err(int code, const std::string &msg);
+  int collect_impl(FeStereoInfo *info);
+  int detection_stereo(FrameSlot &L, FrameSlot &R, std::vector<Pt> &pts0, std::vector<Pt> &pts1, std::vector<uint64_t> &ids0,
+                       std::vector<uint64_t> &ids1, FeStereoInfo &info);
+  int lk_launch(int cam, const Pyramid &p0, const Pyramid &p1, const std::vector<Pt> &pts, const double K[4], const double D[4],
+                bool undistort);
+  int lk_wait(int cam);
+  int matching_begin(int cam, FrameSlot &f0, FrameSlot &f1, const std::vector<Pt> &pts0, Match &m);
+  int matching_end(int cam, FrameSlot &f1, const std::vector<Pt> &pts0, Match &m, FeStereoInfo &info);
+
+  FeConfig cfg_;
+  int device_;
+  std::unique_ptr<FeContext> cam_[2];
+  std::deque<std::pair<int, int>> queue_;   // submitted, not yet collected (slot of the left, slot of the right image)
+  std::deque<double> queue_t_;
+  int last_[2] = {-1, -1};                  // slots holding the previous pair (img_pyramid_last)
+  // tracker state (TrackBase.h:173-192; one currid for both cameras)
+  std::vector<Pt> pts_last_[2];
+  std::vector<uint64_t> ids_last_[2];
+  uint64_t currid_ = 1;
+  std::vector<FePointRow> rows_[2];
+  FrameResult scratch_res_;
+  FeStageTimes st_{};
+};
+
+}  // namespace plviwo

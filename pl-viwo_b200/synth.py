@@ -134,11 +134,17 @@ class SynthSequence:
             self.occ.append((np.clip(tex, 40, 200), x0, y0, vx, vy))
 
     # ------------------------------------------------------------------ frames
-    def frame(self, t: int) -> np.ndarray:
+    def frame(self, t: int, cam: int = 0) -> np.ndarray:
+        """cam 0: the (left) camera; cam 1: the right camera of a stereo pair (KAIST-like rig, stereo_pairs 0-1 in
+        config_camera.yaml:5-7): the same scene seen with a constant horizontal disparity of 9 px and a small vertical
+        offset, its own pixel noise and gain."""
         t = int(t) % self.n_frames
         s = self.scale[t]
         # frame pixel p -> canvas pixel c = centre + s * (p - vp)
         M = np.array([[s, 0, self.cx[t] - s * self.vp[0]], [0, s, self.cy[t] - s * self.vp[1]]], np.float64)
+        if cam:
+            M[0, 2] += s * 9.0 * self.sc
+            M[1, 2] += s * 0.4 * self.sc
         img = cv2.warpAffine(self.canvas, M, (self.W, self.H), flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP,
                              borderMode=cv2.BORDER_REFLECT_101)
         for tex, x0, y0, vx, vy in self.occ:
@@ -149,18 +155,18 @@ class SynthSequence:
             ya, yb = max(y, 0), min(y + h, self.H)
             if xb > xa and yb > ya:
                 img[ya:yb, xa:xb] = tex[ya - y:yb - y, xa - x:xb - x]
-        rng = np.random.default_rng(self.seed * 100003 + t)
+        rng = np.random.default_rng(self.seed * 100003 + t + (50000017 if cam else 0))
         noise = rng.standard_normal(img.shape).astype(np.float32)
         # correlated (demosaic-like) noise keeps Canny(50,50) after equalisation readable
         noise = cv2.GaussianBlur(noise, (0, 0), 1.2 if self.line_heavy else 0.8) * (1.0 if self.line_heavy else 1.6)
-        img = self.gain[t] * img + self.offset[t] + self.noise_sigma * noise
+        img = (self.gain[t] * (1.03 if cam else 1.0)) * img + self.offset[t] + self.noise_sigma * noise
         return np.clip(np.rint(img), 0, 255).astype(np.uint8)
 
-    def mask(self, t: int) -> np.ndarray:
+    def mask(self, t: int, cam: int = 0) -> np.ndarray:
         """All-zero mask, or the moving circular mask of test_tracking.cpp:288-302 (r=100 px, 2.5 px/frame)."""
         m = np.zeros((self.H, self.W), np.uint8)
         if self.moving_mask:
-            cx = int((100 + 2.5 * t) % self.W)
+            cx = int((100 + 2.5 * t - (9 if cam else 0)) % self.W)
             cy = int(self.H / 2 + 0.3 * self.H * np.sin(t / 40.0))
             cv2.circle(m, (cx, cy), int(100 * self.sc), 255, -1)
         return m

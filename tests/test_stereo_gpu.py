@@ -1,0 +1,186 @@
+"""Stereo point front end (TrackKLT::feed_stereo / perform_detection_stereo, TrackKLT.cpp:202-393, 530-827) through the
+C ABI against the oracle (oracle/stereo.py), same bars as the monocular path: feature ids bit-exact, tracked UVs within
+0.05 px, status flags equal on >= 99.5 % of features.  Teacher-forced (state loaded from the oracle before every pair)
+and free-running; golden rows from cv2 (tests/golden/stereo_golden.npz)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import frontend as ofe
+from oracle import stereo as ost
+
+pytestmark = pytest.mark.gpu
+
+CFG1 = dict(num_features=200, fast_threshold=20, grid_x=5, grid_y=5, min_px_dist=10, pyr_levels=3, win_size=15)
+CFG2 = dict(num_features=400, fast_threshold=20, grid_x=5, grid_y=5, min_px_dist=10, pyr_levels=4, win_size=15)
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "stereo_golden.npz")
+
+
+def _blob(fe, o, W, H):
+    st = o.get_state()
+    cams = [fe.pack_state(W, H, st["currid"], st["pts_last"][c], st["ids_last"][c], st["img_last"][c], st["mask_last"][c])
+            for c in (0, 1)]
+    return fe.pack_stereo_state(st["currid"], cams[0], cams[1])
+
+
+def _run(fe, synth, n_frames, kw, seed=1000, width=1280, height=560, teacher_forced=True, hard=True, moving_mask=False,
+         K_right=None, lookahead=0):
+    seq = synth.SynthSequence(seed=seed, width=width, height=height, n_frames=n_frames, hard=hard, moving_mask=moving_mask)
+    o = ost.TrackKLTStereo(ofe.FeConfig(K=seq.K, D=seq.D, **kw), K_right=K_right)
+    g = fe.StereoFrontEnd(fe.default_config(width=width, height=height, K=seq.K, D=seq.D, lookahead=lookahead, **kw), K_right=K_right)
+    s = dict(frames=0, rows=0, rows_sym=0, order_equal=0, frames_equal=0, stereo_rows=0, det_left=0, det_right=0, new_stereo=0,
+             first_divergence=None)
+    duv, dun = [0.0], [0.0]
+    for t in range(n_frames):
+        il, ir = seq.frame(t, 0), seq.frame(t, 1)
+        ml = seq.mask(t, 0) if moving_mask else np.zeros_like(il)
+        mr = seq.mask(t, 1) if moving_mask else np.zeros_like(il)
+        if teacher_forced and t > 0:
+            g.set_state(_blob(fe, o, width, height))
+        rows_o = o.feed_new_camera(seq.timestamp(t), il, ir, ml, mr)
+        info = g.feed_new_camera(seq.timestamp(t), il, ir, ml if moving_mask else None, mr if moving_mask else None)
+        det = o.trace["det"]
+        assert bool(info.reset) == bool(o.trace["reset"]), t
+        assert bool(info.first_frame) == bool(o.trace["first"]), t
+        assert [bool(info.detection_ran[0]), bool(info.detection_ran[1])] == [det["ran_left"], det["ran_right"]], t
+        s["frames"] += 1
+        s["det_left"] += int(det["ran_left"])
+        s["det_right"] += int(det["ran_right"])
+        s["new_stereo"] += int(info.n_stereo_new)
+        s["stereo_rows"] += int(info.n_stereo_rows)
+        frame_equal = True
+        for cam in (0, 1):
+            rows = g.point_rows(cam)
+            ids_o = {r.id: r for r in rows_o[cam]}
+            ids_g = {int(r["id"]): r for r in rows}
+            sym = set(ids_o) ^ set(ids_g)
+            s["rows"] += len(ids_o)
+            s["rows_sym"] += len(sym)
+            if sym:
+                frame_equal = False
+            else:
+                s["order_equal"] += int([r.id for r in rows_o[cam]] == [int(v) for v in rows["id"]])
+            for fid in set(ids_o) & set(ids_g):
+                a, b = ids_g[fid], ids_o[fid]
+                duv.append(max(abs(float(a["u"]) - b.u), abs(float(a["v"]) - b.v)))
+                dun.append(max(abs(float(a["un"]) - b.un), abs(float(a["vn"]) - b.vn)))
+        if frame_equal:
+            s["frames_equal"] += 1
+            last_ids = g.get_last_ids()
+            for cam in (0, 1):
+                assert np.array_equal(last_ids[cam], np.array(o.ids_last[cam], np.uint64)), (t, cam)
+            if teacher_forced or s["first_divergence"] is None:
+                last = g.get_last_obs()
+                for cam in (0, 1):
+                    assert np.abs(last[cam] - o.pts_last[cam]).max(initial=0) < (0.05 if teacher_forced else 0.5), (t, cam)
+        elif s["first_divergence"] is None:
+            s["first_divergence"] = t
+            if not teacher_forced:
+                break
+    g.close()
+    duv, dun = np.array(duv), np.array(dun)
+    s.update(max_duv=float(duv.max()), duv_p99=float(np.percentile(duv, 99)), n_duv_gt_005=int((duv > 0.05).sum()),
+             max_dun=float(dun.max()))
+    print(s)
+    return s
+
+
+def _assert_parity(s):
+    assert s["rows"] > 0, s
+    assert s["rows_sym"] <= 0.005 * s["rows"], s              # a flipped status flag changes one row
+    assert s["order_equal"] >= 2 * s["frames_equal"], s       # and where the sets agree the row order is the reference's
+    assert s["duv_p99"] < 0.01, s
+    assert s["n_duv_gt_005"] <= max(1, int(0.001 * s["rows"])), s
+
+
+@pytest.mark.parametrize("kw,seed", [(CFG1, 1000), (CFG2, 1001)])
+def test_stereo_teacher_forced(fe, synth, kw, seed):
+    s = _run(fe, synth, 30, kw, seed=seed)
+    _assert_parity(s)
+    assert s["det_left"] >= 5 and s["det_right"] >= 1 and s["new_stereo"] > 100 and s["stereo_rows"] > 1000, s
+
+
+def test_stereo_teacher_forced_moving_mask_and_right_calib(fe, synth):
+    """Masks (the right working mask is a clone of the LEFT mask, TrackKLT.cpp:691) and a right camera with its own
+    intrinsics (undistortion and RANSAC threshold per camera, :866-872)."""
+    kr = tuple(v * 1.01 for v in synth.KAIST_K)
+    _assert_parity(_run(fe, synth, 20, dict(CFG1, grid_y=3, pyr_levels=5), seed=1002, moving_mask=True, K_right=kr))
+
+
+def test_stereo_free_running(fe, synth):
+    s = _run(fe, synth, 25, CFG1, seed=1003, teacher_forced=False)
+    assert s["rows_sym"] <= 0.005 * s["rows"], s
+    assert s["duv_p99"] < 0.05, s
+
+
+def test_stereo_small_image_and_reset(fe, synth):
+    """640x280, then a black pair: every track dies in both cameras, the tracker resets and re-detects identically."""
+    seq = synth.SynthSequence(seed=1012, width=640, height=280, n_frames=6, hard=False)
+    kw = dict(CFG1, num_features=120)
+    o = ost.TrackKLTStereo(ofe.FeConfig(K=seq.K, D=seq.D, **kw))
+    g = fe.StereoFrontEnd(fe.default_config(width=640, height=280, K=seq.K, D=seq.D, **kw))
+    z = np.zeros((280, 640), np.uint8)
+    frames = [(seq.frame(t, 0), seq.frame(t, 1)) for t in range(4)] + [(z, z), (seq.frame(4, 0), seq.frame(4, 1)),
+                                                                         (seq.frame(5, 0), seq.frame(5, 1))]
+    for t, (il, ir) in enumerate(frames):
+        ro = o.feed_new_camera(1.0 + t, il, ir, z, z)
+        info = g.feed_new_camera(1.0 + t, il, ir)
+        for cam in (0, 1):
+            assert [int(v) for v in g.point_rows(cam)["id"]] == [r.id for r in ro[cam]], (t, cam)
+            assert np.array_equal(g.get_last_ids()[cam], np.array(o.ids_last[cam], np.uint64)), (t, cam)
+        assert bool(info.reset) == bool(o.trace["reset"])
+    g.close()
+
+
+def test_stereo_state_roundtrip_and_pipelined(fe, synth):
+    """get_state / set_state round trip; submit / collect with lookahead gives the rows of feed()."""
+    seq = synth.SynthSequence(seed=1013, n_frames=10)
+    cfg = dict(width=1280, height=560, K=seq.K, D=seq.D, **CFG1)
+    a = fe.StereoFrontEnd(fe.default_config(**cfg))
+    b = fe.StereoFrontEnd(fe.default_config(lookahead=3, **cfg))
+    ref = []
+    for t in range(8):
+        a.feed_new_camera(seq.timestamp(t), seq.frame(t, 0), seq.frame(t, 1))
+        ref.append((a.point_rows(0).copy(), a.point_rows(1).copy()))
+        if t == 3:
+            blob = a.get_state()
+    # pipelined
+    frames = [(seq.frame(t, 0), seq.frame(t, 1)) for t in range(8)]
+    sub = 0
+    for t in range(8):
+        while sub < 8 and sub <= t + 3:
+            b.submit(seq.timestamp(sub), frames[sub][0], frames[sub][1])
+            sub += 1
+        b.collect()
+        for cam in (0, 1):
+            assert np.array_equal(b.point_rows(cam), ref[t][cam]), (t, cam)
+    # resume from the checkpoint taken after pair 3
+    c = fe.StereoFrontEnd(fe.default_config(**cfg))
+    c.set_state(blob)
+    assert c.get_state() == blob
+    for t in range(4, 8):
+        c.feed_new_camera(seq.timestamp(t), seq.frame(t, 0), seq.frame(t, 1))
+        for cam in (0, 1):
+            assert np.array_equal(c.point_rows(cam), ref[t][cam]), (t, cam)
+    for h in (a, b, c):
+        h.close()
+
+
+def test_stereo_golden_rows(fe, synth):
+    """Rows of the cv2-driven oracle committed as a fixture (tests/golden/make_golden_stereo.py)."""
+    gold = np.load(GOLDEN)
+    n, W, H = int(gold["n_frames"]), int(gold["width"]), int(gold["height"])
+    seq = synth.SynthSequence(seed=int(gold["seed"]), width=W, height=H, n_frames=n, hard=False)
+    kw = dict(CFG1, num_features=int(gold["num_features"]))
+    g = fe.StereoFrontEnd(fe.default_config(width=W, height=H, K=seq.K, D=seq.D, **kw))
+    for t in range(n):
+        g.feed_new_camera(seq.timestamp(t), seq.frame(t, 0), seq.frame(t, 1))
+        for cam in (0, 1):
+            rows = g.point_rows(cam)
+            ids = gold["ids_%d_%d" % (t, cam)]
+            assert np.array_equal(rows["id"], ids), (t, cam)
+            if len(ids):
+                uv = gold["uv_%d_%d" % (t, cam)]
+                assert np.abs(np.stack([rows["u"], rows["v"]], 1) - uv).max() < 0.05, (t, cam)
+    g.close()
