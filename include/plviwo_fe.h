@@ -229,9 +229,10 @@ int plviwo_fe_get_stage_times(FeHandle *h, FeStageTimes *out, int reset);
  *
  * One FeStereoHandle = one stereo pair (camera 0 = left, 1 = right; OptionsCamera stereo_pairs) on one device.  Both
  * images have the size given in FeConfig; cfg->K / cfg->D calibrate the left camera, K_right / D_right the right one
- * (NULL: same as left).  Points only: the reference's line tracker has no stereo path (TrackLSD.cpp:57-60 feeds the
- * LEFT image to its monocular path) — run a monocular FeHandle on the left image for the lines.  cfg->use_lines,
- * line_samples and downsample are ignored here.
+ * (NULL: same as left).  The reference's line tracker has no stereo path: with two images it runs its monocular code
+ * on the LEFT image against the stereo tracker's left points (TrackLSD.cpp:57-60, :127-129).  cfg->use_lines = 1 and a
+ * non-NULL vp do exactly that here; the line rows come back through plviwo_fe_stereo_get_line_rows.  line_samples and
+ * downsample are ignored.
  */
 typedef struct FeStereoHandle FeStereoHandle;
 typedef struct FeStereoInfo {
@@ -245,6 +246,7 @@ typedef struct FeStereoInfo {
   int32_t n_stereo_new;      /* new left points that were also found in the right image (:668-678) */
   int32_t n_lk_in[2], n_klt_ok[2], n_ransac_ok[2];
   int32_t n_stereo_rows;     /* ids present in both cameras' rows of this pair                    */
+  int32_t n_line_rows, n_lines_detected, n_line_matches;   /* left-image line tracker (0 when off)   */
 } FeStereoInfo;
 
 int plviwo_fe_stereo_create(const FeConfig *cfg, const double K_right[4], const double D_right[4], int device,
@@ -257,14 +259,18 @@ int plviwo_fe_stereo_change_feat_id(FeStereoHandle *h, uint64_t id_old, uint64_t
 /* Synchronous drop-in for feed_new_camera with two images (HOST buffers, 8UC1, same stride; masks may be NULL). */
 int plviwo_fe_stereo_feed(FeStereoHandle *h, double timestamp, const uint8_t *image_left, const uint8_t *image_right, int width,
                           int height, int stride, const uint8_t *mask_left, const uint8_t *mask_right, int mask_stride,
-                          FeStereoInfo *info);
+                          const double vp[6], FeStereoInfo *info);
 /* Pipelined form (as plviwo_fe_submit / _collect): the frame-independent work of both images runs up to cfg.lookahead
  * pairs ahead; images are host or device pointers (on_device). */
 int plviwo_fe_stereo_submit(FeStereoHandle *h, double timestamp, const uint8_t *image_left, const uint8_t *image_right, int stride,
-                            int on_device, const uint8_t *mask_left, const uint8_t *mask_right, int mask_stride);
+                            int on_device, const uint8_t *mask_left, const uint8_t *mask_right, int mask_stride, const double vp[6]);
 int plviwo_fe_stereo_collect(FeStereoHandle *h, FeStereoInfo *info);
 int plviwo_fe_stereo_get_point_rows(FeStereoHandle *h, int cam, FePointRow *out, int cap, int *n_out);
 int plviwo_fe_stereo_get_last_obs(FeStereoHandle *h, int cam, uint64_t *ids, float *uv /* 2 per point */, int cap, int *n_out);
+/* line rows of the LEFT camera (cam id 0), as plviwo_fe_get_line_rows / _line_points / _classify_lines */
+int plviwo_fe_stereo_get_line_rows(FeStereoHandle *h, FeLineRow *out, int cap, int *n_out);
+int plviwo_fe_stereo_get_line_points(FeStereoHandle *h, FeLinePoint *out, int cap, int *n_out);
+int plviwo_fe_stereo_classify_lines(FeStereoHandle *h, const double vp[6]);
 /* State blob: 32-byte header (magic 'PLVS', currid, sizes) followed by one monocular state blob per camera. */
 int plviwo_fe_stereo_get_state(FeStereoHandle *h, void *buf, size_t cap, size_t *n_bytes);
 int plviwo_fe_stereo_set_state(FeStereoHandle *h, const void *buf, size_t n_bytes);

@@ -8,7 +8,8 @@
 //
 // Both write into the UNCHANGED containers (ov_core::FeatureDatabase, viw::LineFeatureDatabase) with exactly the calls
 // the reference makes (TrackKLT.cpp:176-179, TrackLSD.cpp:163-167), so UpdaterCamera, CamHelper, LineHelper and the
-// initialisers keep working on the same objects.  One FeHandle per camera id; mono only (feed_stereo is not built).
+// initialisers keep working on the same objects.  One FeHandle per camera id for monocular feeds; a message with two
+// images and stereo = true goes through one FeStereoHandle (TrackKLT::feed_stereo, TrackKLT.cpp:202-393).
 #pragma once
 
 #include <array>
@@ -37,29 +38,46 @@ class TrackB200 : public ov_core::TrackBase {
             HistogramMethod histmethod, int fast_threshold, int gridx, int gridy, int minpxdist, bool use_lines = true,
             int device = 0)
       : TrackBase(cameras, numfeats, numaruco, stereo, histmethod), threshold_(fast_threshold), grid_x_(gridx), grid_y_(gridy),
-        min_px_dist_(minpxdist), use_lines_(use_lines), device_(device) {
-    if (stereo) throw std::invalid_argument("plviwo::TrackB200: stereo tracking is not built (mono streams only)");
-  }
+        min_px_dist_(minpxdist), use_lines_(use_lines), device_(device) {}
   ~TrackB200() override {
     for (auto &kv : handles_) plviwo_fe_destroy(kv.second);
+    if (stereo_) plviwo_fe_stereo_destroy(stereo_);
   }
 
-  // TrackKLT::feed_new_camera (TrackKLT.cpp:34-94): validates the message, one mono feed per image
+  // TrackKLT::feed_new_camera (TrackKLT.cpp:34-94): validates the message, then the same dispatch as :80-93
   void feed_new_camera(const ov_core::CameraData &message) override {
     if (message.sensor_ids.empty() || message.sensor_ids.size() != message.images.size() ||
         message.images.size() != message.masks.size())
       throw std::invalid_argument("plviwo::TrackB200: message data sizes do not match or are empty");   // reference: std::exit
-    for (size_t i = 0; i < message.images.size(); i++) feed_monocular(message, i);
+    const size_t num_images = message.images.size();
+    if (num_images == 1) {
+      feed_monocular(message, 0);
+    } else if (num_images == 2 && use_stereo) {
+      feed_stereo(message, 0, 1);
+    } else if (!use_stereo) {
+      for (size_t i = 0; i < num_images; i++) feed_monocular(message, i);
+    } else {
+      throw std::invalid_argument("plviwo::TrackB200: invalid number of images, only mono or stereo tracking");   // reference: std::exit
+    }
   }
 
   // line rows of the last frame of a camera (consumed by TrackLSDB200)
   FeHandle *handle(size_t cam_id) { return handles_.at(cam_id); }
+  FeStereoHandle *stereo_handle() { return stereo_; }   // non-null once a two-image message was fed
   bool lines_enabled() const { return use_lines_; }
 
  private:
   FeHandle *handle_for(size_t cam_id, const cv::Mat &img) {
     auto it = handles_.find(cam_id);
     if (it != handles_.end()) return it->second;
+    FeConfig cfg = make_config(img);
+    FeHandle *h = nullptr;
+    if (plviwo_fe_create(&cfg, device_, &h) != FE_OK)
+      throw std::runtime_error(std::string("plviwo_fe_create: ") + plviwo_fe_last_error(nullptr));
+    handles_[cam_id] = h;
+    return h;
+  }
+  FeConfig make_config(const cv::Mat &img) const {
     FeConfig cfg;
     plviwo_fe_default_config(&cfg);
     cfg.width = img.cols;
@@ -73,11 +91,7 @@ class TrackB200 : public ov_core::TrackBase {
     cfg.numaruco = numaruco_of_currid();
     cfg.use_lines = use_lines_ ? 1 : 0;
     cfg.lookahead = 0;   // online use: one frame in, one frame out
-    FeHandle *h = nullptr;
-    if (plviwo_fe_create(&cfg, device_, &h) != FE_OK)
-      throw std::runtime_error(std::string("plviwo_fe_create: ") + plviwo_fe_last_error(nullptr));
-    handles_[cam_id] = h;
-    return h;
+    return cfg;
   }
   int numaruco_of_currid() const { return (int)((currid.load() - 1) / 4); }   // TrackBase.cpp:34: currid = 4 * numaruco + 1
 
@@ -123,8 +137,69 @@ class TrackB200 : public ov_core::TrackBase {
     ids_last[cam_id] = ids;
   }
 
+  // TrackKLT::feed_stereo (TrackKLT.cpp:202-393) behind one FeStereoHandle.  The line tracker has no stereo path in the
+  // reference (TrackLSD.cpp:57-60 feeds the left image to its monocular code): the handle runs it on the left image.
+  void feed_stereo(const ov_core::CameraData &message, size_t msg_id_left, size_t msg_id_right) {
+    const size_t cam[2] = {(size_t)message.sensor_ids.at(msg_id_left), (size_t)message.sensor_ids.at(msg_id_right)};
+    const cv::Mat *img[2] = {&message.images.at(msg_id_left), &message.images.at(msg_id_right)};
+    const cv::Mat *mask[2] = {&message.masks.at(msg_id_left), &message.masks.at(msg_id_right)};
+    if (img[0]->cols != img[1]->cols || img[0]->rows != img[1]->rows || img[0]->step != img[1]->step)
+      throw std::invalid_argument("plviwo::TrackB200: stereo images must have the same size and step");
+    double K[2][4], D[2][4];
+    for (int c = 0; c < 2; c++) {
+      const Eigen::MatrixXd calib = camera_calib.at(cam[c])->get_value();
+      for (int i = 0; i < 4; i++) {
+        K[c][i] = calib(i);
+        D[c][i] = calib(4 + i);
+      }
+    }
+    if (!stereo_) {
+      FeConfig cfg = make_config(*img[0]);
+      for (int i = 0; i < 4; i++) {
+        cfg.K[i] = K[0][i];
+        cfg.D[i] = D[0][i];
+      }
+      if (plviwo_fe_stereo_create(&cfg, K[1], D[1], device_, &stereo_) != FE_OK)
+        throw std::runtime_error(std::string("plviwo_fe_stereo_create: ") + plviwo_fe_stereo_last_error(nullptr));
+    }
+    for (int c = 0; c < 2; c++) plviwo_fe_stereo_set_calib(stereo_, c, K[c], D[c]);
+    if (num_features != last_num_features_) {
+      plviwo_fe_stereo_set_num_features(stereo_, num_features);
+      last_num_features_ = num_features;
+    }
+    const bool has_mask = !mask[0]->empty() && !mask[1]->empty();
+    const double vp0[6] = {0, 0, 0, 0, 0, 0};   // TrackLSDB200 re-classifies with the real vanishing points
+    FeStereoInfo info;
+    const int rc = plviwo_fe_stereo_feed(stereo_, message.timestamp, img[0]->data, img[1]->data, img[0]->cols, img[0]->rows,
+                                         (int)img[0]->step, has_mask ? mask[0]->data : nullptr, has_mask ? mask[1]->data : nullptr,
+                                         has_mask ? (int)mask[0]->step : 0, use_lines_ ? vp0 : nullptr, &info);
+    if (rc != FE_OK) throw std::runtime_error(std::string("plviwo_fe_stereo_feed: ") + plviwo_fe_stereo_last_error(stereo_));
+    std::lock_guard<std::mutex> lckv(mtx_last_vars);
+    for (int c = 0; c < 2; c++) {   // left rows first, then right (TrackKLT.cpp:352-363)
+      rows_.resize((size_t)info.n_point_rows[c]);
+      int n = 0;
+      plviwo_fe_stereo_get_point_rows(stereo_, c, rows_.data(), (int)rows_.size(), &n);
+      for (int i = 0; i < n; i++) database->update_feature((size_t)rows_[i].id, message.timestamp, cam[c], rows_[i].u, rows_[i].v, rows_[i].un, rows_[i].vn);
+      ids_.resize((size_t)info.n_last_obs[c]);
+      uv_.resize(2 * (size_t)info.n_last_obs[c]);
+      plviwo_fe_stereo_get_last_obs(stereo_, c, ids_.data(), uv_.data(), info.n_last_obs[c], &n);
+      std::vector<cv::KeyPoint> kps((size_t)n);
+      std::vector<size_t> ids((size_t)n);
+      for (int i = 0; i < n; i++) {
+        kps[(size_t)i].pt.x = uv_[2 * (size_t)i];
+        kps[(size_t)i].pt.y = uv_[2 * (size_t)i + 1];
+        ids[(size_t)i] = (size_t)ids_[(size_t)i];
+      }
+      img_last[cam[c]] = *img[c];
+      img_mask_last[cam[c]] = *mask[c];
+      pts_last[cam[c]] = kps;
+      ids_last[cam[c]] = ids;
+    }
+  }
+
   int threshold_, grid_x_, grid_y_, min_px_dist_;
   bool use_lines_;
+  FeStereoHandle *stereo_ = nullptr;
   int device_;
   int last_num_features_ = -1;
   std::map<size_t, FeHandle *> handles_;
@@ -147,17 +222,30 @@ class TrackLSDB200 : public viw::TrackLSD {
     const int cam_id = message.sensor_ids.at(0);
     auto b200 = std::dynamic_pointer_cast<TrackB200>(feats_.at(cam_id));
     if (!b200 || !b200->lines_enabled()) throw std::invalid_argument("plviwo::TrackLSDB200 needs a plviwo::TrackB200 with lines enabled");
-    FeHandle *h = b200->handle((size_t)cam_id);
     const double vp[6] = {vanishing_points.at(0)(0), vanishing_points.at(0)(1), vanishing_points.at(1)(0),
                           vanishing_points.at(1)(1), vanishing_points.at(2)(0), vanishing_points.at(2)(1)};
-    plviwo_fe_classify_lines(h, vp);
     int n = 0, np = 0;
-    plviwo_fe_get_line_rows(h, nullptr, 0, &n);
-    plviwo_fe_get_line_points(h, nullptr, 0, &np);
-    std::vector<FeLineRow> rows((size_t)n);
-    std::vector<FeLinePoint> pts((size_t)np);
-    plviwo_fe_get_line_rows(h, rows.data(), n, &n);
-    plviwo_fe_get_line_points(h, pts.data(), np, &np);
+    std::vector<FeLineRow> rows;
+    std::vector<FeLinePoint> pts;
+    if (message.images.size() == 2 && b200->stereo_handle()) {   // TrackLSD.cpp:57-60: the left image of the pair
+      FeStereoHandle *h = b200->stereo_handle();
+      plviwo_fe_stereo_classify_lines(h, vp);
+      plviwo_fe_stereo_get_line_rows(h, nullptr, 0, &n);
+      plviwo_fe_stereo_get_line_points(h, nullptr, 0, &np);
+      rows.resize((size_t)n);
+      pts.resize((size_t)np);
+      plviwo_fe_stereo_get_line_rows(h, rows.data(), n, &n);
+      plviwo_fe_stereo_get_line_points(h, pts.data(), np, &np);
+    } else {
+      FeHandle *h = b200->handle((size_t)cam_id);
+      plviwo_fe_classify_lines(h, vp);
+      plviwo_fe_get_line_rows(h, nullptr, 0, &n);
+      plviwo_fe_get_line_points(h, nullptr, 0, &np);
+      rows.resize((size_t)n);
+      pts.resize((size_t)np);
+      plviwo_fe_get_line_rows(h, rows.data(), n, &n);
+      plviwo_fe_get_line_points(h, pts.data(), np, &np);
+    }
     for (const FeLineRow &r : rows) {
       Eigen::Vector4f line(r.line[0], r.line[1], r.line[2], r.line[3]), line_n(r.line_n[0], r.line_n[1], r.line_n[2], r.line_n[3]);
       std::map<int, double> points_line;

@@ -22,7 +22,7 @@ from typing import List, Optional
 import numpy as np
 
 from . import cvops
-from .frontend import FeConfig, PointRow, TrackKLT, HIST_HISTOGRAM, HIST_CLAHE, f32
+from .frontend import FeConfig, PointRow, TrackKLT, TrackLSD, HIST_HISTOGRAM, HIST_CLAHE, f32
 
 
 class TrackKLTStereo:
@@ -272,3 +272,42 @@ class TrackKLTStereo:
         self.trace["mask_klt_" + tag] = np.asarray(mask_klt).copy()
         self.trace["mask_rsc_" + tag] = np.asarray(mask_rsc).copy()
         return p1, out
+
+
+class _LeftView:
+    """What viw::TrackLSD reads from `trackFEATS.at(cam_id)` for camera 0 (TrackLSD.cpp:127-129): the stereo tracker's
+    LEFT observations and the left camera's calibration."""
+
+    def __init__(self, klt: TrackKLTStereo):
+        self._klt = klt
+
+    K = property(lambda self: self._klt.K[0])
+    D = property(lambda self: self._klt.D[0])
+
+    def get_last_obs(self):
+        return self._klt.pts_last[0].copy()
+
+    def get_last_ids(self):
+        return list(self._klt.ids_last[0])
+
+
+class StereoFrontEnd:
+    """UpdaterCamera::feed_measurement's tracker calls for a stereo rig (UpdaterCamera.cpp:105-110): the point tracker
+    gets both images, then the line tracker — which has no stereo path and runs its monocular code on the LEFT image
+    (TrackLSD.cpp:57-60) against the left points the point tracker has just produced."""
+
+    def __init__(self, cfg: FeConfig, K_right=None, D_right=None, ops=cvops):
+        self.cfg = cfg
+        self.klt = TrackKLTStereo(cfg, K_right, D_right, ops)
+        self.lsd = TrackLSD(cfg, _LeftView(self.klt), ops) if cfg.use_lines else None
+
+    def feed(self, timestamp, img_left, img_right, mask_left=None, mask_right=None, vps=None):
+        if mask_left is None:
+            mask_left = np.zeros_like(img_left)
+        if mask_right is None:
+            mask_right = np.zeros_like(img_right)
+        rows_l, rows_r = self.klt.feed_new_camera(timestamp, img_left, img_right, mask_left, mask_right)
+        lrows = []
+        if self.lsd is not None and vps is not None:
+            lrows = self.lsd.feed_new_camera(timestamp, img_left, mask_left, vps, img_eq=self.klt.trace["img_eq"][0])
+        return rows_l, rows_r, lrows

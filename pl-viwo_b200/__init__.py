@@ -71,7 +71,8 @@ class FeStereoInfo(C.Structure):
     _fields_ = [("timestamp", C.c_double), ("n_point_rows", C.c_int32 * 2), ("n_last_obs", C.c_int32 * 2), ("reset", C.c_int32),
                 ("first_frame", C.c_int32), ("detection_ran", C.c_int32 * 2), ("n_detected", C.c_int32 * 2),
                 ("n_stereo_new", C.c_int32), ("n_lk_in", C.c_int32 * 2), ("n_klt_ok", C.c_int32 * 2),
-                ("n_ransac_ok", C.c_int32 * 2), ("n_stereo_rows", C.c_int32)]
+                ("n_ransac_ok", C.c_int32 * 2), ("n_stereo_rows", C.c_int32), ("n_line_rows", C.c_int32),
+                ("n_lines_detected", C.c_int32), ("n_line_matches", C.c_int32)]
 
 
 class FePlayStats(C.Structure):
@@ -103,7 +104,8 @@ EXPORTS = [
     "plviwo_fe_stereo_create", "plviwo_fe_stereo_destroy", "plviwo_fe_stereo_last_error", "plviwo_fe_stereo_set_calib",
     "plviwo_fe_stereo_set_num_features", "plviwo_fe_stereo_change_feat_id", "plviwo_fe_stereo_feed", "plviwo_fe_stereo_submit",
     "plviwo_fe_stereo_collect", "plviwo_fe_stereo_get_point_rows", "plviwo_fe_stereo_get_last_obs", "plviwo_fe_stereo_get_state",
-    "plviwo_fe_stereo_set_state", "plviwo_fe_stereo_get_stage_times",
+    "plviwo_fe_stereo_set_state", "plviwo_fe_stereo_get_stage_times", "plviwo_fe_stereo_get_line_rows",
+    "plviwo_fe_stereo_get_line_points", "plviwo_fe_stereo_classify_lines",
 ]
 
 
@@ -149,9 +151,12 @@ def lib() -> C.CDLL:
         L.plviwo_fe_stereo_set_num_features.argtypes = [C.c_void_p, C.c_int]
         L.plviwo_fe_stereo_change_feat_id.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         L.plviwo_fe_stereo_feed.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                            C.c_void_p, C.c_int, C.POINTER(FeStereoInfo)]
+                                            C.c_void_p, C.c_int, C.c_void_p, C.POINTER(FeStereoInfo)]
         L.plviwo_fe_stereo_submit.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-                                              C.c_void_p, C.c_int]
+                                              C.c_void_p, C.c_int, C.c_void_p]
+        L.plviwo_fe_stereo_get_line_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.plviwo_fe_stereo_get_line_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.plviwo_fe_stereo_classify_lines.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.plviwo_fe_stereo_collect.argtypes = [C.c_void_p, C.POINTER(FeStereoInfo)]
         L.plviwo_fe_stereo_get_point_rows.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.plviwo_fe_stereo_get_last_obs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
@@ -509,6 +514,7 @@ class StereoFrontEnd:
         if rc != FE_OK:
             raise FrontEndError(rc, (self._lib.plviwo_fe_stereo_last_error(None) or b"").decode())
         self.database = FeatureDatabase()      # one database shared by both cameras (UpdaterCamera.cpp:47-56)
+        self.line_database = LineFeatureDatabase()
         self.info = FeStereoInfo()
 
     def close(self):
@@ -541,9 +547,17 @@ class StereoFrontEnd:
             raise FrontEndError(FE_BAD_ARG, "image must be a 2-D uint8 array")
         return np.ascontiguousarray(a)
 
+    @staticmethod
+    def _vp(vanishing_points):
+        if vanishing_points is None:
+            return None
+        return (C.c_double * 6)(*[float(v) for p in vanishing_points for v in p])
+
     def feed_new_camera(self, timestamp: float, image_left, image_right, mask_left=None, mask_right=None,
-                        update_db: bool = True) -> FeStereoInfo:
-        """TrackKLT::feed_new_camera with a two-image message (TrackKLT.cpp:34-94 -> feed_stereo)."""
+                        vanishing_points=None, update_db: bool = True) -> FeStereoInfo:
+        """TrackKLT::feed_new_camera with a two-image message (TrackKLT.cpp:34-94 -> feed_stereo), followed (when
+        vanishing points are given and cfg.use_lines) by TrackLSD::feed_new_camera, which takes the left image
+        (TrackLSD.cpp:57-60)."""
         il, ir = self._img(image_left), self._img(image_right)
         if il.shape != ir.shape:
             raise FrontEndError(FE_BAD_ARG, "left and right image sizes differ")
@@ -551,18 +565,20 @@ class StereoFrontEnd:
         mr = None if mask_right is None else np.ascontiguousarray(mask_right, np.uint8)
         self._check(self._lib.plviwo_fe_stereo_feed(
             self._h, float(timestamp), il.ctypes.data, ir.ctypes.data, il.shape[1], il.shape[0], il.strides[0],
-            None if ml is None else ml.ctypes.data, None if mr is None else mr.ctypes.data, il.shape[1], C.byref(self.info)))
+            None if ml is None else ml.ctypes.data, None if mr is None else mr.ctypes.data, il.shape[1],
+            self._vp(vanishing_points), C.byref(self.info)))
         if update_db:
             self._push_rows(timestamp)
         return self.info
 
-    def submit(self, timestamp: float, image_left, image_right, stride: int = 0, on_device: bool = False):
+    def submit(self, timestamp: float, image_left, image_right, stride: int = 0, on_device: bool = False, vanishing_points=None):
         """image_*: numpy arrays (host) or integer device pointers (on_device, with stride)."""
         if on_device:
             pl, pr = int(image_left), int(image_right)
         else:
             pl, pr, stride = image_left.ctypes.data, image_right.ctypes.data, image_left.strides[0]
-        self._check(self._lib.plviwo_fe_stereo_submit(self._h, float(timestamp), pl, pr, stride, 1 if on_device else 0, None, None, 0))
+        self._check(self._lib.plviwo_fe_stereo_submit(self._h, float(timestamp), pl, pr, stride, 1 if on_device else 0, None, None, 0,
+                                                      self._vp(vanishing_points)))
 
     def collect(self) -> FeStereoInfo:
         self._check(self._lib.plviwo_fe_stereo_collect(self._h, C.byref(self.info)))
@@ -572,6 +588,28 @@ class StereoFrontEnd:
         for cam in (0, 1):    # left rows first, then right (TrackKLT.cpp:352-363)
             for r in self.point_rows(cam):
                 self.database.update_feature(int(r["id"]), timestamp, cam, float(r["u"]), float(r["v"]), float(r["un"]), float(r["vn"]))
+        lrows, lpts = self.line_rows()
+        for r in lrows:
+            pts = lpts[r["pt_offset"]:r["pt_offset"] + r["n_pts"]]
+            self.line_database.update_feature(int(r["id"]), timestamp, 0, r["line"], r["line_n"],
+                                              {int(p["pid"]): float(p["dist"]) for p in pts},
+                                              np.stack([pts["u"], pts["v"]], 1) if len(pts) else np.zeros((0, 2)), int(r["D"]))
+
+    def line_rows(self):
+        n = C.c_int(0)
+        self._check(self._lib.plviwo_fe_stereo_get_line_rows(self._h, None, 0, C.byref(n)))
+        rows = np.zeros((n.value,), LINE_ROW_DTYPE)
+        if n.value:
+            self._check(self._lib.plviwo_fe_stereo_get_line_rows(self._h, rows.ctypes.data, n.value, C.byref(n)))
+        m = C.c_int(0)
+        self._check(self._lib.plviwo_fe_stereo_get_line_points(self._h, None, 0, C.byref(m)))
+        pts = np.zeros((m.value,), LINE_POINT_DTYPE)
+        if m.value:
+            self._check(self._lib.plviwo_fe_stereo_get_line_points(self._h, pts.ctypes.data, m.value, C.byref(m)))
+        return rows, pts
+
+    def classify_lines(self, vanishing_points):
+        self._check(self._lib.plviwo_fe_stereo_classify_lines(self._h, self._vp(vanishing_points)))
 
     def point_rows(self, cam: int) -> np.ndarray:
         n = C.c_int(0)

@@ -662,6 +662,11 @@ int plviwo_fe_stereo_create(const FeConfig *cfg, const double K_right[4], const 
     return FE_NO_DEVICE;
   }
   if (device < 0 || device >= ndev) return bad("device index out of range");
+  if (cfg->use_lines) {
+    if ((cfg->width & 1) || (cfg->height & 1)) return bad("line tracker needs even image dimensions (exact 2x decimation)");
+    if (cfg->canny_th1 != cfg->canny_th2) return bad("canny_th1 != canny_th2: hysteresis pass is not implemented");
+    if (cfg->fld_length_threshold < 2) return bad("bad fld_length_threshold");
+  }
   FeStereo *st = new FeStereo(*cfg, K_right, D_right, device);
   int rc = st->init();
   if (rc != FE_OK) {
@@ -700,22 +705,22 @@ int plviwo_fe_stereo_change_feat_id(FeStereoHandle *h, uint64_t id_old, uint64_t
 
 int plviwo_fe_stereo_feed(FeStereoHandle *h, double timestamp, const uint8_t *image_left, const uint8_t *image_right, int width,
                           int height, int stride, const uint8_t *mask_left, const uint8_t *mask_right, int mask_stride,
-                          FeStereoInfo *info) {
+                          const double vp[6], FeStereoInfo *info) {
   API_BEGIN
   if (!h) return FE_BAD_ARG;
   const uint8_t *img[2] = {image_left, image_right};
   const uint8_t *msk[2] = {mask_left, mask_right};
-  return h->st->feed(timestamp, img, width, height, stride, false, msk, mask_stride, info);
+  return h->st->feed(timestamp, img, width, height, stride, false, msk, mask_stride, vp, info);
   API_END
 }
 
 int plviwo_fe_stereo_submit(FeStereoHandle *h, double timestamp, const uint8_t *image_left, const uint8_t *image_right, int stride,
-                            int on_device, const uint8_t *mask_left, const uint8_t *mask_right, int mask_stride) {
+                            int on_device, const uint8_t *mask_left, const uint8_t *mask_right, int mask_stride, const double vp[6]) {
   API_BEGIN
   if (!h || !image_left || !image_right) return FE_BAD_ARG;
   const uint8_t *img[2] = {image_left, image_right};
   const uint8_t *msk[2] = {mask_left, mask_right};
-  return h->st->submit(timestamp, img, stride, on_device != 0, msk, mask_stride);
+  return h->st->submit(timestamp, img, stride, on_device != 0, msk, mask_stride, vp);
   API_END
 }
 
@@ -746,6 +751,19 @@ int plviwo_fe_stereo_get_last_obs(FeStereoHandle *h, int cam, uint64_t *ids, flo
     }
   }
   return FE_OK;
+}
+
+int plviwo_fe_stereo_get_line_rows(FeStereoHandle *h, FeLineRow *out, int cap, int *n_out) {
+  if (!h) return FE_BAD_ARG;
+  return copy_out(h->st->left_result().line_rows, out, cap, n_out);
+}
+int plviwo_fe_stereo_get_line_points(FeStereoHandle *h, FeLinePoint *out, int cap, int *n_out) {
+  if (!h) return FE_BAD_ARG;
+  return copy_out(h->st->left_result().line_points, out, cap, n_out);
+}
+int plviwo_fe_stereo_classify_lines(FeStereoHandle *h, const double vp[6]) {
+  if (!h || !vp) return FE_BAD_ARG;
+  return h->st->classify_lines(vp);
 }
 
 int plviwo_fe_stereo_get_state(FeStereoHandle *h, void *buf, size_t cap, size_t *n_bytes) {

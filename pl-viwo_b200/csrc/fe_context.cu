@@ -56,6 +56,14 @@ static inline void cpu_pause() {
 #endif
 }
 
+// How long a waiting thread spins before it starts yielding.  A handle keeps three host threads busy (caller, point
+// tracker, line tracker); on a host with fewer free cores than that (8 ranks on one box) a long pure spin steals the core
+// from the thread it is waiting for, while sched_yield on an idle core returns at once — so the pure spin is short.
+static const unsigned kSpin = [] {
+  const char *e = std::getenv("PLVIWO_SPIN");
+  return e ? (unsigned)std::max(0, std::atoi(e)) : 256u;
+}();
+
 // ------------------------------------------------------------------------------------------------ WorkQueue
 void WorkQueue::push(int v) {
   {
@@ -66,9 +74,10 @@ void WorkQueue::push(int v) {
   cv_.notify_one();
 }
 bool WorkQueue::pop(int *v) {
-  for (int spins = 0; spins < 20000; spins++) {   // ~1 ms
+  for (unsigned spins = 0; spins < 20000; spins++) {   // ~1 ms, then sleep on the condition variable
     if (n_.load(std::memory_order_acquire) > 0 || stop_.load(std::memory_order_relaxed)) break;
-    cpu_pause();
+    if (spins < kSpin) cpu_pause();
+    else std::this_thread::yield();
   }
   std::unique_lock<std::mutex> lk(mu_);
   cv_.wait(lk, [this] { return stop_.load() || !q_.empty(); });
@@ -330,7 +339,7 @@ int FeContext::wait_flag(volatile int *flag, int value, cudaStream_t st, std::st
   while (*flag != value) {
     // a few microseconds of pure spinning (the usual wait is shorter than a context switch), then let other threads of
     // an oversubscribed host run between polls
-    if (spins < 4000) cpu_pause();
+    if (spins < kSpin) cpu_pause();
     else std::this_thread::yield();
     if ((++spins & 0x1fffff) == 0) {
       cudaError_t e = cudaStreamQuery(st);
@@ -812,7 +821,7 @@ int FeContext::collect_impl(FeFrameInfo *info) {
   FrameSlot &cur = slots_[si];
   // wait for the tracker threads: spin (the result is normally there already, or a few microseconds away), then yield
   for (unsigned spins = 0; cur.stage.load(std::memory_order_acquire) != 3; spins++) {
-    if (spins < 40000) cpu_pause();
+    if (spins < kSpin) cpu_pause();
     else std::this_thread::yield();
   }
   cur.stage.store(0, std::memory_order_relaxed);
@@ -1266,7 +1275,7 @@ int FeContext::perform_matching(const FrameSlot &f0, FrameSlot &f1, std::vector<
   if (cfg_.line_samples > 0) {
     // the segments belong to the line tracker's thread: wait until it is done with the previous frame
     for (unsigned spins = 0; f0.stage.load(std::memory_order_acquire) == 2; spins++) {
-      if (spins < 4000) cpu_pause();
+      if (spins < kSpin) cpu_pause();
       else std::this_thread::yield();
     }
     const int S = cfg_.line_samples;

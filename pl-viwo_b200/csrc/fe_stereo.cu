@@ -24,10 +24,10 @@ namespace plviwo {
 
 FeStereo::FeStereo(const FeConfig &cfg, const double K_right[4], const double D_right[4], int device)
     : cfg_(cfg), device_(device) {
-  cfg_.use_lines = 0;
   cfg_.line_samples = 0;
   cfg_.downsample = 0;
   FeConfig cr = cfg_;
+  cr.use_lines = 0;   // TrackLSD.cpp:57-60: with two images the line tracker runs on the left one only
   for (int i = 0; i < 4; i++) {
     if (K_right) cr.K[i] = K_right[i];
     if (D_right) cr.D[i] = D_right[i];
@@ -74,10 +74,11 @@ int FeStereo::change_feat_id(uint64_t id_old, uint64_t id_new) {   // TrackBase.
 }
 
 int FeStereo::submit(double t, const uint8_t *const image[2], int stride, bool on_device, const uint8_t *const mask[2],
-                     int mask_stride) {
+                     int mask_stride, const double vp[6]) {
   int slot[2] = {-1, -1};
   for (int c = 0; c < 2; c++) {
-    int rc = cam_[c]->submit_impl(t, image[c], stride, on_device, mask ? mask[c] : nullptr, mask_stride, nullptr, &slot[c]);
+    int rc = cam_[c]->submit_impl(t, image[c], stride, on_device, mask ? mask[c] : nullptr, mask_stride, c == 0 ? vp : nullptr,
+                                  &slot[c]);
     cam_[c]->flush_stats(cam_[c]->mst_);
     if (rc) {
       if (c == 1 && slot[0] >= 0) cam_[0]->slots_[slot[0]].busy = false;
@@ -91,13 +92,13 @@ int FeStereo::submit(double t, const uint8_t *const image[2], int stride, bool o
 }
 
 int FeStereo::feed(double t, const uint8_t *const image[2], int w, int h, int stride, bool on_device, const uint8_t *const mask[2],
-                   int mask_stride, FeStereoInfo *info) {
+                   int mask_stride, const double vp[6], FeStereoInfo *info) {
   // TrackKLT.cpp:37-43 exits on a malformed message
   if (!image || !image[0] || !image[1] || w != cfg_.width || h != cfg_.height || stride < w ||
       (mask && (mask[0] || mask[1]) && mask_stride < w))
     return err(FE_BAD_ARG, "feed: image/mask size does not match the handle");
   if (!queue_.empty()) return err(FE_BAD_ARG, "feed: pairs submitted with plviwo_fe_stereo_submit are still pending");
-  int rc = submit(t, image, stride, on_device, mask, mask_stride);
+  int rc = submit(t, image, stride, on_device, mask, mask_stride, vp);
   if (rc) return rc;
   return collect(info);
 }
@@ -110,6 +111,24 @@ int FeStereo::collect(FeStereoInfo *info) {
   local.timestamp = queue_t_.front();
   const std::pair<int, int> cur = queue_.front();
   int rc = collect_impl(&local);
+  // UpdaterCamera.cpp:105-110: the line tracker runs after the point tracker, on the LEFT image, against the left points
+  // the stereo tracker has just produced (TrackLSD.cpp:57-60, :127-129)
+  {
+    FeContext &lc = *cam_[0];
+    FrameSlot &L = lc.slots_[cur.first];
+    L.res.obs = pts_last_[0];
+    L.res.obs_ids = ids_last_[0];
+    lc.cur_res_ = &L.res;
+    lc.cur_slot_ = cur.first;
+    if (rc == FE_OK && cfg_.use_lines && L.has_vp) {
+      rc = lc.lsd_feed(L);
+      if (rc) err(rc, FeContext::thread_error());
+      lc.flush_stats(lc.lst_);
+      local.n_line_rows = (int)L.res.line_rows.size();
+      local.n_lines_detected = L.res.info.n_lines_detected;
+      local.n_line_matches = L.res.info.n_line_matches;
+    }
+  }
   // move forward in time whatever happened (:366-378): the previous pair's slots become free
   queue_.pop_front();
   queue_t_.pop_front();

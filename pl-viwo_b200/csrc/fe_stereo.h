@@ -23,10 +23,11 @@ class FeStereo {
   int set_calib(int cam, const double K[4], const double D[4]);
   int set_num_features(int n);
   int change_feat_id(uint64_t id_old, uint64_t id_new);
-  int submit(double t, const uint8_t *const image[2], int stride, bool on_device, const uint8_t *const mask[2], int mask_stride);
+  int submit(double t, const uint8_t *const image[2], int stride, bool on_device, const uint8_t *const mask[2], int mask_stride,
+             const double vp[6]);
   int collect(FeStereoInfo *info);
   int feed(double t, const uint8_t *const image[2], int w, int h, int stride, bool on_device, const uint8_t *const mask[2],
-           int mask_stride, FeStereoInfo *info);
+           int mask_stride, const double vp[6], FeStereoInfo *info);
   int get_state(void *buf, size_t cap, size_t *n_bytes);
   int set_state(const void *buf, size_t n_bytes);
   FeStageTimes snapshot_times(bool reset);
@@ -35,6 +36,8 @@ class FeStereo {
   const std::vector<FePointRow> &rows(int cam) const { return rows_[cam]; }
   const std::vector<Pt> &last_obs(int cam) const { return pts_last_[cam]; }
   const std::vector<uint64_t> &last_ids(int cam) const { return ids_last_[cam]; }
+  const FrameResult &left_result() const { return cam_[0]->result(); }   // line rows / line points of the left image
+  int classify_lines(const double vp[6]) { return cam_[0]->classify_lines(vp); }
   std::string last_error;
 
  private:

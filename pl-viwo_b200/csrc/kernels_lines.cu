@@ -19,6 +19,8 @@
 // The first version walked the whole frame with a single thread: 14.6 ms per 640x280 frame.
 #include "fe_kernels.h"
 
+#include <cstdlib>
+
 #include <algorithm>
 #include <mutex>
 #include <cstdio>
@@ -729,7 +731,15 @@ void launch_fld(const DevImage &half, int length_threshold, float distance_thres
   size_t smem = (size_t)kLutSize + (size_t)(h + 2 * kPadRows) * ws * sizeof(unsigned);
   static SmemOptIn optin;
   optin.ensure(k_fld_walk_cc, smem);
-  k_fld_walk_cc<<<kWalkCtas, kWalkThreads, smem, s>>>(fb.edges, fb.words_per_row, fb.label, fb.cnt, fb.bbox, w, h, fb.comp_root, fb.counters, fb.max_chains,
+  // Grid size: the walk is bound by its longest component (a sequential chain of ~130-cycle steps), not by the number of
+  // walkers, and many frames' walks are in flight at once on a pipelined stream: a small persistent grid leaves the SMs'
+  // thread slots to the latency-critical kernels (LK) of the frames being tracked.  PLVIWO_WALK_CTAS overrides.
+  static const int walk_ctas = [] {
+    const char *e = std::getenv("PLVIWO_WALK_CTAS");
+    const int v = e ? std::atoi(e) : 0;
+    return v > 0 ? v : kWalkCtas;
+  }();
+  k_fld_walk_cc<<<walk_ctas, kWalkThreads, smem, s>>>(fb.edges, fb.words_per_row, fb.label, fb.cnt, fb.bbox, w, h, fb.comp_root, fb.counters, fb.max_chains,
                                                length_threshold, fb.chain_pts, fb.chain_seed, fb.chain_off, fb.chain_len,
                                                fb.max_chains);
   if (ev) cudaEventRecord(ev[1], s);
