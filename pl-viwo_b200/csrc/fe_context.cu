@@ -186,9 +186,31 @@ int FeContext::init() {
       FE_CUDA(cudaMallocHost(&s.h_fld_counts, 2 * sizeof(int)));
     }
     FE_CUDA(cudaMallocHost(&s.h_raw, (size_t)Win_ * Hin_));
-    FE_CUDA(cudaStreamCreateWithPriority(&s.s_line, cudaStreamNonBlocking, lo));
-    FE_CUDA(cudaStreamCreateWithPriority(&s.s_a, cudaStreamNonBlocking, lo));
-    FE_CUDA(cudaStreamCreateWithPriority(&s.s_b, cudaStreamNonBlocking, lo));
+    // Streams come from three small pools shared by the slots (slot i uses entry i mod pool size).  The device has 32
+    // hardware queues (CUDA_DEVICE_MAX_CONNECTIONS) and streams are mapped onto them round-robin: with three streams per
+    // slot a deep lookahead creates more streams than queues, and the tracking stream then shares a queue with some
+    // slot's line stream — an LK launch that lands behind a millisecond-long chain walk waits for it.  The pool sizes
+    // follow the kernel time each path needs per frame (line path ~1.6 ms, FAST path ~0.4 ms, image path ~0.05 ms).
+    {
+      auto pool_size = [&](const char *env, int dflt) {
+        const char *e = std::getenv(env);
+        int v = e ? std::atoi(e) : dflt;
+        if (v <= 0) v = nslots;   // 0: one stream per slot (no sharing)
+        return std::min(v, nslots);
+      };
+      const int nl = cfg_.use_lines ? pool_size("PLVIWO_LINE_STREAMS", 16) : 0, na = pool_size("PLVIWO_IMAGE_STREAMS", 4),
+                nb = pool_size("PLVIWO_FAST_STREAMS", 8);
+      const int i = s.index;
+      if (i < nl) FE_CUDA(cudaStreamCreateWithPriority(&s.s_line, cudaStreamNonBlocking, lo));
+      if (i < na) FE_CUDA(cudaStreamCreateWithPriority(&s.s_a, cudaStreamNonBlocking, lo));
+      if (i < nb) FE_CUDA(cudaStreamCreateWithPriority(&s.s_b, cudaStreamNonBlocking, lo));
+      s.owns_line = i < nl;
+      s.owns_a = i < na;
+      s.owns_b = i < nb;
+      if (!s.owns_line && nl > 0) s.s_line = slots_[i % nl].s_line;
+      if (!s.owns_a) s.s_a = slots_[i % na].s_a;
+      if (!s.owns_b) s.s_b = slots_[i % nb].s_b;
+    }
     FE_CUDA(cudaMalloc(&s.d_hist, 256 * sizeof(unsigned)));
     FE_CUDA(cudaMemset(s.d_hist, 0, 256 * sizeof(unsigned)));
     FE_CUDA(cudaMalloc(&s.d_clahe, 64 * 256));
@@ -299,9 +321,9 @@ FeContext::~FeContext() {
     for (auto &e : s.ev_sp_t) if (e) cudaEventDestroy(e);
     destroy_graphs(s);
     cudaFree(s.d_hist); cudaFree(s.d_counters); cudaFree(s.d_seq); cudaFree(s.d_clahe);
-    if (s.s_a) cudaStreamDestroy(s.s_a);
-    if (s.s_b) cudaStreamDestroy(s.s_b);
-    if (s.s_line) cudaStreamDestroy(s.s_line);
+    if (s.s_a && s.owns_a) cudaStreamDestroy(s.s_a);
+    if (s.s_b && s.owns_b) cudaStreamDestroy(s.s_b);
+    if (s.s_line && s.owns_line) cudaStreamDestroy(s.s_line);
     if (s.ev_pyr) cudaEventDestroy(s.ev_pyr);
     if (s.ev_lines) cudaEventDestroy(s.ev_lines);
     for (auto &e : s.ev_t) if (e) cudaEventDestroy(e);
@@ -1446,8 +1468,10 @@ int FeContext::lsd_feed(FrameSlot &cur) {
   }
   int nseg = std::min(cur.h_fld_counts[1], cur.fld.out_cap);
   if (nseg > 1024) {
-    FE_COPY(lst_, cur.h_segs + 1024, cur.fld.out + 1024, (size_t)(nseg - 1024) * sizeof(float4), cudaMemcpyDeviceToHost, cur.s_line);
-    FE_CUDA(cudaStreamSynchronize(cur.s_line));
+    // rare: more segments than the asynchronous copy carries.  The data is complete (the flag above), and the line stream
+    // is shared with other slots (the caller's thread may be capturing a graph on it), so this is a plain blocking copy
+    lst_.d2h_bytes += (size_t)(nseg - 1024) * sizeof(float4);
+    FE_CUDA(cudaMemcpy(cur.h_segs + 1024, cur.fld.out + 1024, (size_t)(nseg - 1024) * sizeof(float4), cudaMemcpyDeviceToHost));
   }
   if (taps) tap_fld_.assign(reinterpret_cast<float *>(cur.h_segs), reinterpret_cast<float *>(cur.h_segs) + 4 * (size_t)nseg);
   // perform_detection_monocular (:194-236): x2, FilterShortLines(40), a fresh id for EVERY detected line

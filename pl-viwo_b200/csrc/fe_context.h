@@ -92,6 +92,7 @@ struct FrameSlot {
   cudaEvent_t ev_pyr = nullptr, ev_lines = nullptr;
   cudaStream_t s_line = nullptr;   // per-slot streams: the frame-independent work of different frames overlaps
   cudaStream_t s_a = nullptr, s_b = nullptr;
+  bool owns_line = false, owns_a = false, owns_b = false;   // streams are pooled: only the first slots of a pool own theirs
   unsigned *d_hist = nullptr, *d_counters = nullptr;
   uint8_t *d_clahe = nullptr;      // CLAHE: 64 tile LUTs of this frame
   int *d_seq = nullptr;            // device-side sequence numbers of the completion signals [fast, -, lines]
