@@ -270,6 +270,37 @@ def run_gpu_multi(fe_mod, torch, seq, d_ptrs, pitch, n_streams, steps, warmup, c
                     "(plviwo_fe_play), frames resident in HBM"}
 
 
+def run_stereo(fe_mod, torch, seq, h_left, steps, warmup, kw, dev):
+    """SURVEY.md 8(f) rank 2: the stereo rig (TrackKLT::feed_stereo + the left-image line tracker) through
+    plviwo_fe_stereo_submit / _collect from pinned HOST pairs; pairs/s by wall clock around a device synchronise."""
+    n = min(len(h_left), 60)
+    H, W = h_left[0].shape
+    h_r = torch.empty((n, H, W), dtype=torch.uint8).pin_memory()
+    for t in range(n):
+        h_r[t].copy_(torch.from_numpy(seq.frame(t, 1)))
+    right = [h_r[t].numpy() for t in range(n)]
+    g = fe_mod.StereoFrontEnd(fe_mod.default_config(K=seq.K, D=seq.D, lookahead=LOOKAHEAD, **kw), device=dev)
+    tot, sub, rows = warmup + steps, 0, 0
+    for i in range(tot):
+        if i == warmup:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        while sub < tot and sub <= i + LOOKAHEAD:
+            t = sub % n
+            g.submit(seq.timestamp(sub), h_left[t], right[t], vanishing_points=seq.vanishing_points(t))
+            sub += 1
+        info = g.collect()
+        if i >= warmup:
+            rows += info.n_point_rows[0] + info.n_point_rows[1] + info.n_line_rows
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    st = g.stage_times()
+    g.close()
+    return {"value": steps / dt, "unit": "stereo pairs/s", "rows_per_pair": rows / max(steps, 1),
+            "h2d_bytes_per_pair": 2 * H * W, "gpu_launches": st["kernel_launches_total"],
+            "api": "plviwo_fe_stereo_submit/_collect from pinned host pairs (60-pair loop), left-image line tracker on, lookahead %d" % LOOKAHEAD}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -278,6 +309,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=150, help="frames of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stereo", action="store_true", help="skip the extra stereo-rig measurement")
     ap.add_argument("--multi-streams", type=int, default=8, help="streams per GPU of the extra multi-stream measurement (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -365,6 +397,12 @@ def main():
     sync_fps = n_sync / (time.perf_counter() - t0)
     handle.close()
 
+    stereo = None
+    if world == 1 and not args.no_stereo:
+        try:
+            stereo = run_stereo(fe_mod, torch, seq, h_np, min(args.steps, 300), args.warmup, kw, dev)
+        except Exception as e:   # an extra, never fatal for the bench line
+            stereo = {"error": str(e)}
     multi = None
     if world == 1 and args.multi_streams > 1:
         multi = run_gpu_multi(fe_mod, torch, seq, d_ptrs, W, args.multi_streams, min(args.steps, 400), args.warmup, kw, dev)
@@ -461,7 +499,7 @@ def main():
                 "api": "plviwo_fe_submit/plviwo_fe_collect from pinned host frames, lookahead %d" % LOOKAHEAD,
                 "sync_feed_fps": sync_fps},
         "gpu_launches": res["stage"]["kernel_launches_total"],
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "multi_stream": multi,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "multi_stream": multi, "stereo": stereo,
     }
     emit(line)
     if dist is not None:

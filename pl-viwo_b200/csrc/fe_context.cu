@@ -9,6 +9,7 @@
 // submit() on its own streams; collect() runs the state-dependent chain (top-off detection on the previous
 // image, LK, RANSAC gate, line association) in frame order.
 #include "fe_context.h"
+#include "sm_partition.h"
 
 #include <algorithm>
 #include <chrono>
@@ -152,7 +153,7 @@ int FeContext::init() {
   FE_CUDA(cudaSetDevice(device_));
   int lo = 0, hi = 0;
   FE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  FE_CUDA(cudaStreamCreateWithPriority(&s_pt_, cudaStreamNonBlocking, hi));
+  FE_CUDA(create_stream_on_partition(device_, SmPart::Tracking, hi, &s_pt_));
   init_device_constants();
   use_graphs_ = std::getenv("PLVIWO_NO_GRAPHS") == nullptr;
 
@@ -186,11 +187,10 @@ int FeContext::init() {
       FE_CUDA(cudaMallocHost(&s.h_fld_counts, 2 * sizeof(int)));
     }
     FE_CUDA(cudaMallocHost(&s.h_raw, (size_t)Win_ * Hin_));
-    // Streams come from three small pools shared by the slots (slot i uses entry i mod pool size).  The device has 32
-    // hardware queues (CUDA_DEVICE_MAX_CONNECTIONS) and streams are mapped onto them round-robin: with three streams per
-    // slot a deep lookahead creates more streams than queues, and the tracking stream then shares a queue with some
-    // slot's line stream — an LK launch that lands behind a millisecond-long chain walk waits for it.  The pool sizes
-    // follow the kernel time each path needs per frame (line path ~1.6 ms, FAST path ~0.4 ms, image path ~0.05 ms).
+    // One stream per slot and path by default; PLVIWO_LINE_STREAMS / _IMAGE_STREAMS / _FAST_STREAMS = n > 0 share n streams
+    // between the slots instead (slot i uses entry i mod n).  Measured on B200 (profiles/experiments_r1.md): sharing
+    // LOWERS single-stream throughput — the line path needs ~2.5 ms of kernel time per frame, so its throughput is
+    // (streams in flight) / 2.5 ms: 12 line streams 5.7k frames/s, 16: 7.3k, 24: 8.0k, one per slot (26): 9.3k.
     {
       auto pool_size = [&](const char *env, int dflt) {
         const char *e = std::getenv(env);
@@ -198,12 +198,12 @@ int FeContext::init() {
         if (v <= 0) v = nslots;   // 0: one stream per slot (no sharing)
         return std::min(v, nslots);
       };
-      const int nl = cfg_.use_lines ? pool_size("PLVIWO_LINE_STREAMS", 16) : 0, na = pool_size("PLVIWO_IMAGE_STREAMS", 4),
-                nb = pool_size("PLVIWO_FAST_STREAMS", 8);
+      const int nl = cfg_.use_lines ? pool_size("PLVIWO_LINE_STREAMS", 0) : 0, na = pool_size("PLVIWO_IMAGE_STREAMS", 0),
+                nb = pool_size("PLVIWO_FAST_STREAMS", 0);
       const int i = s.index;
-      if (i < nl) FE_CUDA(cudaStreamCreateWithPriority(&s.s_line, cudaStreamNonBlocking, lo));
-      if (i < na) FE_CUDA(cudaStreamCreateWithPriority(&s.s_a, cudaStreamNonBlocking, lo));
-      if (i < nb) FE_CUDA(cudaStreamCreateWithPriority(&s.s_b, cudaStreamNonBlocking, lo));
+      if (i < nl) FE_CUDA(create_stream_on_partition(device_, SmPart::Rest, lo, &s.s_line));
+      if (i < na) FE_CUDA(create_stream_on_partition(device_, SmPart::Rest, lo, &s.s_a));
+      if (i < nb) FE_CUDA(create_stream_on_partition(device_, SmPart::Rest, lo, &s.s_b));
       s.owns_line = i < nl;
       s.owns_a = i < na;
       s.owns_b = i < nb;

@@ -24,6 +24,33 @@ struct SmemOptIn {
   }
 };
 
+// One shared-memory / L1 split for EVERY kernel of the library (PLVIWO_CARVEOUT = percent of the SM's unified storage
+// preferred as shared memory; unset = the driver's per-kernel default).  Kernels that prefer different splits cannot share
+// an SM until it has drained and been reconfigured; with dozens of kernels of several frames resident at once — among
+// them millisecond-long persistent ones that opt in to > 48 KB — a short latency-critical launch then only gets the SMs
+// whose current split happens to suit it.
+int carveout_percent();   // -1: leave the default
+struct CarveoutOnce {
+  std::atomic<bool> done[64];
+  CarveoutOnce() { for (auto &d : done) d.store(false); }
+  template <class Kernel>
+  void apply(Kernel kernel) {
+    const int pct = carveout_percent();
+    if (pct < 0) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::atomic<bool> &d = done[dev & 63];
+    if (d.load(std::memory_order_relaxed)) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    d.store(true, std::memory_order_relaxed);
+  }
+};
+#define PLVIWO_CARVEOUT(kernel)   \
+  do {                            \
+    static CarveoutOnce c__;      \
+    c__.apply(kernel);            \
+  } while (0)
+
 struct DevImage {
   uint8_t *p = nullptr;
   int w = 0, h = 0, pitch = 0;

@@ -211,6 +211,7 @@ void launch_fast_select(const FastCell *d_cells, int n_cells, int max_bands, uns
                         const int *d_band_cnt, const unsigned *d_kps, int kps_cap, unsigned *d_scratch, int nfg,
                         float2 *d_cand_sel, int *d_cand_cnt, cudaStream_t s) {
   if (n_cells <= 0 || max_bands > kSelMaxBands) return;
+  PLVIWO_CARVEOUT(k_fast_select);
   k_fast_select<<<n_cells, kSelThreads, 0, s>>>(d_cells, max_bands, d_total, d_band_off, d_band_cnt, d_kps, kps_cap, d_scratch,
                                                 nfg, d_cand_sel, d_cand_cnt);
 }
@@ -226,6 +227,7 @@ void launch_fast(const DevImage &img, const FastCell *d_cells, int n_cells, int 
   static SmemOptIn optin;
   optin.ensure(k_fast, smem);
   dim3 grid(max_bands, n_cells);
+  PLVIWO_CARVEOUT(k_fast);
   k_fast<<<grid, kFastThreads, smem, s>>>(img.p, img.pitch, d_cells, max_bands, threshold, d_total, d_band_off, d_band_cnt,
                                           d_kps, kps_cap, smem_w);
 }

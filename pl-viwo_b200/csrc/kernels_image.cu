@@ -9,6 +9,8 @@
 // planes with a 15 px border; here the frame is read once, the equalised image is written once and shared,
 // and derivatives are formed on the fly inside the LK kernel.
 #include "fe_kernels.h"
+
+#include <cstdlib>
 #include "tma_bulk.h"
 
 namespace plviwo {
@@ -66,6 +68,7 @@ void launch_hist(const DevImage &src, unsigned *d_hist, cudaStream_t s) {
   int grid = (chunks + kHistThreads * 2 - 1) / (kHistThreads * 2);  // ~2 chunks per thread
   if (grid < 1) grid = 1;
   if (grid > 148 * 4) grid = 148 * 4;
+  PLVIWO_CARVEOUT(k_hist);
   k_hist<<<grid, kHistThreads, 0, s>>>(src.p, src.w, src.h, src.pitch, d_hist);
 }
 
@@ -169,6 +172,7 @@ static ClaheGeom clahe_geom(int w, int h) {
 
 void launch_clahe_lut(const DevImage &src, uint8_t *d_luts, cudaStream_t s) {
   const ClaheGeom g = clahe_geom(src.w, src.h);
+  PLVIWO_CARVEOUT(k_clahe_lut);
   k_clahe_lut<<<64, 256, 0, s>>>(src.p, src.w, src.h, src.pitch, g, d_luts);
 }
 
@@ -387,6 +391,7 @@ void launch_eq_pyr1(const DevImage &src, unsigned *d_hist, unsigned *d_counter, 
   // tiles are laid over the level-1 footprint of the frame even when level 1 itself is not wanted (l1.p == null)
   const int w1 = (src.w + 1) / 2, h1 = (src.h + 1) / 2;
   dim3 grid((w1 + kT1W - 1) / kT1W, (h1 + kT1H - 1) / kT1H);
+  PLVIWO_CARVEOUT(k_eq_pyr1);
   k_eq_pyr1<<<grid, kEqThreads, 0, s>>>(src.p, src.w, src.h, src.pitch, d_hist, d_counter, equalize, d_clahe_luts,
                                         clahe_geom(src.w, src.h), l0.p, l0.pitch, l1.p,
                                         l1.p ? l1.w : 0, l1.p ? l1.h : 0, l1.pitch, half.p, half.w, half.h, half.pitch);
@@ -439,7 +444,20 @@ __global__ void k_signal(volatile int *flag, int value) {
   *flag = value;
   __threadfence_system();
 }
-void launch_signal(int *host_flag, int value, cudaStream_t s) { k_signal<<<1, 1, 0, s>>>(host_flag, value); }
+int carveout_percent() {
+  static const int pct = [] {
+    const char *e = std::getenv("PLVIWO_CARVEOUT");
+    if (!e) return -1;
+    const int v = std::atoi(e);
+    return v < 0 ? -1 : (v > 100 ? 100 : v);
+  }();
+  return pct;
+}
+
+void launch_signal(int *host_flag, int value, cudaStream_t s) {
+  PLVIWO_CARVEOUT(k_signal);
+  k_signal<<<1, 1, 0, s>>>(host_flag, value);
+}
 // Same, with the sequence number kept in device memory so that the launch can live in a replayed CUDA graph.
 __global__ void k_signal_inc(volatile int *flag, int *dev_seq) {
   int v = *dev_seq + 1;
@@ -447,10 +465,14 @@ __global__ void k_signal_inc(volatile int *flag, int *dev_seq) {
   *flag = v;
   __threadfence_system();
 }
-void launch_signal_inc(int *host_flag, int *dev_seq, cudaStream_t s) { k_signal_inc<<<1, 1, 0, s>>>(host_flag, dev_seq); }
+void launch_signal_inc(int *host_flag, int *dev_seq, cudaStream_t s) {
+  PLVIWO_CARVEOUT(k_signal_inc);
+  k_signal_inc<<<1, 1, 0, s>>>(host_flag, dev_seq);
+}
 
 void launch_pyr_down(const DevImage &a, const DevImage &b, cudaStream_t s) {
   int n = ((b.w + 3) >> 2) * b.h;
+  PLVIWO_CARVEOUT(k_pyr_down);
   k_pyr_down<<<(n + kRestThreads - 1) / kRestThreads, kRestThreads, 0, s>>>(a.p, a.w, a.h, a.pitch, b.p, b.w, b.h, b.pitch);
 }
 
@@ -459,6 +481,7 @@ void launch_pyr_rest(const Pyramid &pyr, unsigned *d_counter, cudaStream_t s) {
   for (int l = 2; l < pyr.n; l++) {
     const DevImage &a = pyr.lvl[l - 1], &b = pyr.lvl[l];
     int n = ((b.w + 3) >> 2) * b.h;
+    PLVIWO_CARVEOUT(k_pyr_down);
     k_pyr_down<<<(n + kRestThreads - 1) / kRestThreads, kRestThreads, 0, s>>>(a.p, a.w, a.h, a.pitch, b.p, b.w, b.h, b.pitch);
   }
 }

@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(kCnThreads)
 void launch_canny(const DevImage &half, float th_low, float th_high, FldBuffers &fb, cudaStream_t s) {
   (void)th_high;  // low == high is enforced at create time (no hysteresis pass is implemented)
   dim3 grid((half.w + kCnW - 1) / kCnW, (half.h + kCnH - 1) / kCnH);
+  PLVIWO_CARVEOUT(k_canny);
   k_canny<<<grid, kCnThreads, 0, s>>>(half.p, half.w, half.h, half.pitch, (int)floorf(th_low), fb.edges, fb.words_per_row);
 }
 
@@ -111,6 +112,7 @@ __global__ void k_unpack_edges(const unsigned *__restrict__ edges, int words_per
 }
 void launch_unpack_edges(const FldBuffers &fb, int w, int h, uint8_t *d_out, cudaStream_t s) {
   dim3 grid((w + 255) / 256, h);
+  PLVIWO_CARVEOUT(k_unpack_edges);
   k_unpack_edges<<<grid, 256, 0, s>>>(fb.edges, fb.words_per_row, w, h, d_out);
 }
 
@@ -721,11 +723,38 @@ void launch_fld(const DevImage &half, int length_threshold, float distance_thres
                 cudaEvent_t *ev) {
   const int w = half.w, h = half.h, n = w * h;
   const int tpb = 256, nb = (n + tpb - 1) / tpb;
+  // measurement only (profiles/exp_bench.py): PLVIWO_EXP_SKIP = 1 skips the whole segment extraction (no segments come
+  // back), 2 keeps the connected components and skips walk + segments, 3 runs the component merge three times, 4 keeps
+  // components + walk and skips the segment fit
+  static const int exp_skip = [] {
+    const char *e = std::getenv("PLVIWO_EXP_SKIP");
+    return e ? std::atoi(e) : 0;
+  }();
+  if (exp_skip == 1) {
+    cudaMemsetAsync(fb.counters, 0, 8 * sizeof(int), s);
+    if (ev) { cudaEventRecord(ev[0], s); cudaEventRecord(ev[1], s); }
+    return;
+  }
+  PLVIWO_CARVEOUT(k_ccl_init);
   k_ccl_init<<<nb, tpb, 0, s>>>(fb.edges, fb.words_per_row, w, h, fb.label, fb.cnt, fb.bbox, fb.counters);
+  PLVIWO_CARVEOUT(k_ccl_merge);
   k_ccl_merge<<<nb, tpb, 0, s>>>(w, h, fb.label);
+  if (exp_skip == 3) {
+    PLVIWO_CARVEOUT(k_ccl_merge);
+    k_ccl_merge<<<nb, tpb, 0, s>>>(w, h, fb.label);
+    PLVIWO_CARVEOUT(k_ccl_merge);
+    k_ccl_merge<<<nb, tpb, 0, s>>>(w, h, fb.label);
+  }
+  PLVIWO_CARVEOUT(k_ccl_flatten);
   k_ccl_flatten<<<nb, tpb, 0, s>>>(w, h, fb.label, fb.cnt, fb.bbox);
+  PLVIWO_CARVEOUT(k_ccl_roots);
   k_ccl_roots<<<nb, tpb, 0, s>>>(w, h, fb.label, fb.cnt, length_threshold + 1, fb.comp_root, fb.counters, fb.max_chains);
   if (ev) cudaEventRecord(ev[0], s);
+  if (exp_skip == 2) {
+    cudaMemsetAsync(fb.counters + 3, 0, 2 * sizeof(int), s);
+    if (ev) cudaEventRecord(ev[1], s);
+    return;
+  }
   init_fld_constants();
   const int ws = ((w + 31) >> 5) + 2;
   size_t smem = (size_t)kLutSize + (size_t)(h + 2 * kPadRows) * ws * sizeof(unsigned);
@@ -739,15 +768,23 @@ void launch_fld(const DevImage &half, int length_threshold, float distance_thres
     const int v = e ? std::atoi(e) : 0;
     return v > 0 ? v : kWalkCtas;
   }();
+  PLVIWO_CARVEOUT(k_fld_walk_cc);
   k_fld_walk_cc<<<walk_ctas, kWalkThreads, smem, s>>>(fb.edges, fb.words_per_row, fb.label, fb.cnt, fb.bbox, w, h, fb.comp_root, fb.counters, fb.max_chains,
                                                length_threshold, fb.chain_pts, fb.chain_seed, fb.chain_off, fb.chain_len,
                                                fb.max_chains);
   if (ev) cudaEventRecord(ev[1], s);
+  if (exp_skip == 4) {   // walk kept, order / segments / compact skipped
+    cudaMemsetAsync(fb.counters + 3, 0, 2 * sizeof(int), s);
+    return;
+  }
   int blocks = (fb.max_chains + 127) / 128;
+  PLVIWO_CARVEOUT(k_fld_order);
   k_fld_order<<<blocks, 128, 0, s>>>(fb.chain_seed, fb.counters, fb.max_chains, fb.order);
+  PLVIWO_CARVEOUT(k_fld_segments);
   k_fld_segments<<<(fb.max_chains + 63) / 64, 64, 0, s>>>(half.p, w, h, half.pitch, length_threshold, distance_threshold,
                                                           fb.chain_pts, fb.chain_off, fb.chain_len, fb.order, fb.counters,
                                                           fb.max_chains, fb.segs, fb.seg_cnt, fb.seg_cnt + fb.max_chains);
+  PLVIWO_CARVEOUT(k_fld_compact);
   k_fld_compact<<<1, 256, 0, s>>>(fb.segs, fb.seg_cnt, fb.seg_cnt + fb.max_chains, fb.counters, fb.max_chains, fb.out,
                                   fb.out_cap);
 }

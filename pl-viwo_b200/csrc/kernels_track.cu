@@ -134,6 +134,7 @@ void launch_corner_subpix(const DevImage &img, const float2 *d_in, float2 *d_out
   }
   lk.unlock();
   if (n < 0) return;
+  PLVIWO_CARVEOUT(k_corner_subpix);
   k_corner_subpix<<<(n + kSpWarps - 1) / kSpWarps, kSpWarps * 32, 0, s>>>(img.p, img.w, img.h, img.pitch, d_in, d_out, n, d_cnt,
                                                                           stride);
 }
@@ -169,6 +170,7 @@ void launch_undistort(const float2 *d_pts, float2 *d_out, int n, const double K[
   if (n <= 0) return;
   CalibArgs c;
   for (int i = 0; i < 4; i++) { c.K[i] = K[i]; c.D[i] = D[i]; }
+  PLVIWO_CARVEOUT(k_undistort);
   k_undistort<<<(n + 127) / 128, 128, 0, s>>>(d_pts, d_out, n, c);
 }
 
@@ -738,6 +740,7 @@ bool launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *d_pts0, f
   for (int i = 0; i < 8; i++) a.cell_mask[i] = cell_mask ? cell_mask[i] : 0xffffffffu;
   for (int i = 0; i < 4; i++) { a.calib.K[i] = prm.K[i]; a.calib.D[i] = prm.D[i]; }
   if (prm.win == kW15 && levels <= kLk15MaxLevels) {   // one CTA per feature, one warp per level
+    PLVIWO_CARVEOUT(k_lk15);
     k_lk15<<<n, std::max(levels, kChainWarps) * 32, 0, s>>>(a, d_pts0, d_pts1, d_status, d_p0n, d_p1n, n, host_flag, flag_value, d_done_counter,
                                      d_tab_cnt, tab_stride);
     return host_flag != nullptr;
@@ -748,6 +751,7 @@ bool launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *d_pts0, f
   size_t smem = (size_t)per_warp * kLkWarps;
   static SmemOptIn optin;
   optin.ensure(k_lk, smem);
+  PLVIWO_CARVEOUT(k_lk);
   k_lk<<<(n + kLkWarps - 1) / kLkWarps, kLkWarps * 32, smem, s>>>(a, d_pts0, d_pts1, d_status, d_p0n, d_p1n, n);
   return false;
 }

@@ -3,7 +3,8 @@ per configuration, each configuration in its own process because the knobs are e
 
   python profiles/exp_bench.py --out gpurun_out/exp.jsonl  CFG [CFG ...]
   CFG = comma-separated KEY=VALUE pairs put into the child's environment; the pseudo keys TASKSET=a-b (cpu list),
-        STREAMS=n (n > 1: the multi-stream measurement instead of the single-stream one) and STEREO=1 are consumed here.
+        STREAMS=n (n > 1: the multi-stream measurement instead of the single-stream one) and STEREO=1 are consumed here;
+        EXP_LINES=0 switches the line tracker off, EXP_LA=n sets the lookahead.
 """
 import argparse
 import json
@@ -31,6 +32,10 @@ def child(args):
     d_ptrs = [d_seq[t].data_ptr() for t in range(n)]
     h_np = [h_seq[t].numpy() for t in range(n)]
     kw = dict(bench.WORKLOAD)
+    if os.environ.get("EXP_LINES") == "0":
+        kw["use_lines"] = 0
+    if os.environ.get("EXP_LA"):
+        bench.LOOKAHEAD = int(os.environ["EXP_LA"])
     out = {"cfg": args.tag}
     if args.stereo:
         right = np.load(CACHE.replace(".npy", "_r.npy"))
