@@ -23,17 +23,20 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------ histogram
-// Each thread walks 16-byte chunks (uint4 = 16 pixels); per-warp shared sub-histograms keep shared-memory
-// atomics off a single copy, one global atomic per non-empty bin per CTA at the end.
+// Each thread walks 16-byte chunks (uint4 = 16 pixels).  Neighbouring pixels have similar values, so the lanes of a warp
+// keep hitting the same few bins: every warp has kHistCopies interleaved copies of the histogram (bin b of copy c at
+// word 4 b + c, so the copies of one bin sit in different banks) and a lane uses copy (lane & 3) — same-bin updates from
+// different lane groups no longer serialise.  One global atomic per non-empty bin per CTA at the end.
 constexpr int kHistThreads = 256;
 constexpr int kHistWarps = kHistThreads / 32;
+constexpr int kHistCopies = 4;
 
 __global__ void __launch_bounds__(kHistThreads) k_hist(const uint8_t *__restrict__ src, int w, int h, int pitch,
                                                        unsigned *__restrict__ hist) {
-  __shared__ unsigned sh[kHistWarps][256];
-  for (int i = threadIdx.x; i < kHistWarps * 256; i += kHistThreads) (&sh[0][0])[i] = 0;
+  __shared__ __align__(16) unsigned sh[kHistWarps][256 * kHistCopies];
+  for (int i = threadIdx.x; i < kHistWarps * 256 * kHistCopies; i += kHistThreads) (&sh[0][0])[i] = 0;
   __syncthreads();
-  unsigned *my = sh[threadIdx.x >> 5];
+  unsigned *my = sh[threadIdx.x >> 5] + (threadIdx.x & (kHistCopies - 1));
   const int chunks_per_row = (w + 15) >> 4;
   const int total = chunks_per_row * h;
   for (int c = blockIdx.x * kHistThreads + threadIdx.x; c < total; c += gridDim.x * kHistThreads) {
@@ -45,20 +48,23 @@ __global__ void __launch_bounds__(kHistThreads) k_hist(const uint8_t *__restrict
       unsigned wds[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        atomicAdd(&my[wds[k] & 0xff], 1u);
-        atomicAdd(&my[(wds[k] >> 8) & 0xff], 1u);
-        atomicAdd(&my[(wds[k] >> 16) & 0xff], 1u);
-        atomicAdd(&my[wds[k] >> 24], 1u);
+        atomicAdd(&my[(wds[k] & 0xff) * kHistCopies], 1u);
+        atomicAdd(&my[((wds[k] >> 8) & 0xff) * kHistCopies], 1u);
+        atomicAdd(&my[((wds[k] >> 16) & 0xff) * kHistCopies], 1u);
+        atomicAdd(&my[(wds[k] >> 24) * kHistCopies], 1u);
       }
     } else {
-      for (int k = 0; x + k < w; k++) atomicAdd(&my[row[k]], 1u);
+      for (int k = 0; x + k < w; k++) atomicAdd(&my[row[k] * kHistCopies], 1u);
     }
   }
   __syncthreads();
   for (int b = threadIdx.x; b < 256; b += kHistThreads) {
     unsigned s = 0;
 #pragma unroll
-    for (int k = 0; k < kHistWarps; k++) s += sh[k][b];
+    for (int k = 0; k < kHistWarps; k++) {
+      const uint4 q = *reinterpret_cast<const uint4 *>(&sh[k][b * kHistCopies]);
+      s += q.x + q.y + q.z + q.w;
+    }
     if (s) atomicAdd(&hist[b], s);
   }
 }

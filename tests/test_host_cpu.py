@@ -26,6 +26,7 @@ def test_struct_layouts_match_header(fe):
     assert C.sizeof(fe.FeLineRow) == 56 and fe.LINE_ROW_DTYPE.itemsize == 56
     assert C.sizeof(fe.FeLinePoint) == 16 and fe.LINE_POINT_DTYPE.itemsize == 16
     assert C.sizeof(fe.FeConfig) == 20 * 4 + 64
+    assert C.sizeof(fe.FeStereoInfo) == 96                 # double + 21 int32, padded to 8 (checked against the C header)
     cfg = fe.default_config()
     assert (cfg.width, cfg.height, cfg.num_features, cfg.pyr_levels, cfg.win_size) == (1280, 560, 150, 5, 15)
     assert abs(cfg.K[0] - 816.90378992770002) < 1e-12 and cfg.fld_length_threshold == 20
@@ -39,6 +40,27 @@ def test_no_cpu_fallback(fe):
     assert e.value.code == fe.FE_NO_DEVICE
     with pytest.raises(fe.FrontEndError):
         fe.op_equalize_pyramid(np.zeros((64, 64), np.uint8), 2)
+
+
+def test_no_cpu_fallback_stereo(fe):
+    if fe.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(fe.FrontEndError) as e:
+        fe.StereoFrontEnd(fe.default_config())
+    assert e.value.code == fe.FE_NO_DEVICE
+
+
+def test_stereo_state_blob_pack_unpack(fe):
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 255, (64, 96), np.uint8)
+    blobs = []
+    for n in (5, 3):
+        pts = rng.uniform(0, 60, (n, 2)).astype(np.float32)
+        blobs.append(fe.pack_state(96, 64, 77, pts, np.arange(n) + 10, img, None))
+    blob = fe.pack_stereo_state(77, blobs[0], blobs[1])
+    currid, left, right = fe.unpack_stereo_state(blob)
+    assert currid == 77 and len(left["ids_last"]) == 5 and len(right["ids_last"]) == 3
+    assert np.array_equal(left["img_last"], img) and np.array_equal(right["img_last"], img)
 
 
 def test_state_blob_pack_unpack(fe):

@@ -107,6 +107,62 @@ def test_stereo_teacher_forced_moving_mask_and_right_calib(fe, synth):
     _assert_parity(_run(fe, synth, 20, dict(CFG1, grid_y=3, pyr_levels=5), seed=1002, moving_mask=True, K_right=kr))
 
 
+@pytest.mark.parametrize("hist", [0, 2])
+def test_stereo_teacher_forced_other_preprocessing(fe, synth, hist):
+    """histogram_method NONE and CLAHE (TrackKLT.cpp:57-67 runs per image of the message)."""
+    _assert_parity(_run(fe, synth, 8, dict(CFG1, histogram_method=hist), seed=1006 + hist))
+
+
+def test_stereo_teacher_forced_odd_size_and_wide_window(fe, synth):
+    """641 x 361 (odd sides: ragged pyramid levels, REFLECT_101 borders), 21 x 21 window = the generic LK kernel."""
+    _assert_parity(_run(fe, synth, 8, dict(CFG1, num_features=150, pyr_levels=3, win_size=21), seed=1008, width=641, height=361, hard=False))
+
+
+def test_stereo_bad_arguments_and_setters(fe, synth):
+    with pytest.raises(fe.FrontEndError):
+        fe.StereoFrontEnd(fe.default_config(win_size=14))
+    with pytest.raises(fe.FrontEndError):
+        fe.StereoFrontEnd(fe.default_config(width=641, height=361, use_lines=1))   # line tracker needs even sides
+    seq = synth.SynthSequence(seed=1015, width=640, height=280, n_frames=4, hard=False)
+    kw = dict(CFG1, num_features=100)
+    g = fe.StereoFrontEnd(fe.default_config(width=640, height=280, K=seq.K, D=seq.D, lookahead=1, use_lines=0, **kw))
+    with pytest.raises(fe.FrontEndError):
+        g.feed_new_camera(0.0, np.zeros((100, 100), np.uint8), np.zeros((100, 100), np.uint8))   # the reference exit()s here
+    with pytest.raises(fe.FrontEndError):
+        g.feed_new_camera(0.0, seq.frame(0), np.zeros((100, 100), np.uint8))
+    with pytest.raises(fe.FrontEndError):
+        g.collect()                                                                   # nothing submitted
+    g.submit(1.0, seq.frame(0, 0), seq.frame(0, 1))
+    g.submit(1.1, seq.frame(1, 0), seq.frame(1, 1))
+    with pytest.raises(fe.FrontEndError):
+        g.submit(1.2, seq.frame(2, 0), seq.frame(2, 1))                                # lookahead window full
+    with pytest.raises(fe.FrontEndError):
+        g.set_num_features(50)                                                        # pairs pending
+    g.collect()
+    g.collect()
+    ids = g.get_last_ids()
+    shared = sorted(set(ids[0].tolist()) & set(ids[1].tolist()))
+    assert shared, "no stereo features"
+    g.change_feat_id(shared[0], 10 ** 6)                                              # TrackBase.cpp:267-285, both cameras
+    ids2 = g.get_last_ids()
+    assert 10 ** 6 in ids2[0] and 10 ** 6 in ids2[1] and shared[0] not in ids2[0] and shared[0] not in ids2[1]
+    # set_num_features between pairs: the oracle with the same change stays in step
+    o = ost.TrackKLTStereo(ofe.FeConfig(K=seq.K, D=seq.D, **kw))
+    g2 = fe.StereoFrontEnd(fe.default_config(width=640, height=280, K=seq.K, D=seq.D, **kw))
+    z = np.zeros((280, 640), np.uint8)
+    for t in range(4):
+        if t == 2:
+            g2.set_num_features(160)
+            o.cfg.num_features = 160
+        ro = o.feed_new_camera(seq.timestamp(t), seq.frame(t, 0), seq.frame(t, 1), z, z)
+        g2.feed_new_camera(seq.timestamp(t), seq.frame(t, 0), seq.frame(t, 1))
+        for cam in (0, 1):
+            assert [int(v) for v in g2.point_rows(cam)["id"]] == [r.id for r in ro[cam]], (t, cam)
+            assert np.array_equal(g2.get_last_ids()[cam], np.array(o.ids_last[cam], np.uint64)), (t, cam)
+    g.close()
+    g2.close()
+
+
 def test_stereo_free_running(fe, synth):
     s = _run(fe, synth, 25, CFG1, seed=1003, teacher_forced=False)
     assert s["rows_sym"] <= 0.005 * s["rows"], s
