@@ -156,6 +156,15 @@ int FeContext::init() {
   FE_CUDA(create_stream_on_partition(device_, SmPart::Tracking, hi, &s_pt_));
   init_device_constants();
   use_graphs_ = std::getenv("PLVIWO_NO_GRAPHS") == nullptr;
+  // Line-path batching: the segment extraction of a frame is > 2 ms of kernel TIME (the sequential chain walk), and the
+  // device runs a bounded number of kernels at once, so a pipelined stream launches the line paths of consecutive frames
+  // together (kernel time per frame / batch).  Needs frames in flight: off for the synchronous drop-in (lookahead 0).
+  {
+    const char *e = std::getenv("PLVIWO_LINE_BATCH");
+    int v = e ? std::atoi(e) : (cfg_.lookahead >= 8 ? 4 : 1);
+    v = std::min(v, std::max(cfg_.lookahead / 2, 1));
+    line_batch_ = std::max(1, std::min(v, kMaxLineBatch));
+  }
 
   const int nslots = std::max(cfg_.lookahead, 0) + 2;
   slots_.resize(nslots);
@@ -298,6 +307,8 @@ int FeContext::init() {
 }
 
 FeContext::~FeContext() {
+  cudaSetDevice(device_);
+  flush_line_batch();   // a line thread waiting for the flag of an unlaunched batch would never be joined
   klt_q_.stop();
   if (klt_thread_.joinable()) klt_thread_.join();
   line_q_.stop();
@@ -554,24 +565,62 @@ int FeContext::enqueue_frame_independent(FrameSlot &s) {
   }
   s.seq_fast++;
   FE_CUDA(cudaEventRecord(s.ev_fast, s.s_b));
+  bool batched = false;
   if (lines) {
-    FE_CUDA(cudaStreamWaitEvent(s.s_line, s.ev_pyr, 0));
-    if (replay) {
-      FE_CUDA(cudaGraphLaunch(s.g_lines, s.s_line));
-    } else {
-      int rc = record_line_path(s, s.s_line);
-      if (rc) return rc;
-    }
     s.seq_lines++;
+    if (line_batch_ > 1 && !timing && !taps) {   // joins the batch; launched when it is full (or when collect needs it)
+      batched = true;
+      s.line_pending = true;
+      pending_lines_.push_back(s.index);
+      if ((int)pending_lines_.size() >= line_batch_) {
+        int rc = flush_line_batch();
+        if (rc) return rc;
+      }
+    } else {
+      FE_CUDA(cudaStreamWaitEvent(s.s_line, s.ev_pyr, 0));
+      if (replay) {
+        FE_CUDA(cudaGraphLaunch(s.g_lines, s.s_line));
+      } else {
+        int rc = record_line_path(s, s.s_line);
+        if (rc) return rc;
+      }
+    }
   }
   s.warmed = true;
   // bookkeeping (identical for both ways of issuing the work)
   const int ncell = (int)cells_.size(), ntab = ncell * cells_nb_;
   mst_.kernel_launches_total += (cfg_.histogram_method != FE_HIST_NONE ? 1 : 0) + 1 + std::max(s.pyr.n - 2, 0) +
-                                 (ncell > 0 ? 3 : 0) + 1 + (lines ? 11 : 0);
+                                 (ncell > 0 ? 3 : 0) + 1 + (lines && !batched ? 11 : 0);
   (void)ntab;
   if (ncell > 0) mst_.d2h_bytes += (size_t)ncell * sizeof(int) + (size_t)2 * ncell * cells_nfg_ * sizeof(float2);
   if (lines) mst_.d2h_bytes += 2 * sizeof(int) + 1024 * sizeof(float4);
+  return FE_OK;
+}
+
+int FeContext::flush_line_batch() {
+  const int n = (int)pending_lines_.size();
+  if (n == 0) return FE_OK;
+  cudaStream_t st = slots_[pending_lines_[0]].s_line;
+  FldBatch b;
+  b.n = n;
+  for (int k = 0; k < n; k++) {
+    FrameSlot &s = slots_[pending_lines_[k]];
+    FE_CUDA(cudaStreamWaitEvent(st, s.ev_pyr, 0));
+    b.half[k] = s.half;
+    b.f[k] = s.fld;
+  }
+  launch_canny_batch(b, cfg_.canny_th1, cfg_.canny_th2, st);
+  launch_fld_batch(b, cfg_.fld_length_threshold, cfg_.fld_distance_threshold, st);
+  for (int k = 0; k < n; k++) {
+    FrameSlot &s = slots_[pending_lines_[k]];
+    FE_CUDA(cudaMemcpyAsync(s.h_fld_counts, s.fld.counters + 3, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FE_CUDA(cudaMemcpyAsync(s.h_segs, s.fld.out, 1024 * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    launch_signal_inc(&s.h_flags[2], s.d_seq + 2, st);
+    s.line_pending = false;
+  }
+  FE_CUDA(cudaGetLastError());
+  mst_.kernel_launches_total += 10 + n;   // canny, 4 x components, walk, order, segments, compact + one signal per frame
+  pending_lines_.clear();
   return FE_OK;
 }
 
@@ -841,6 +890,10 @@ int FeContext::collect_impl(FeFrameInfo *info) {
   const int si = queue_.front();
   queue_.erase(queue_.begin());
   FrameSlot &cur = slots_[si];
+  if (cur.line_pending) {   // its line batch never filled up: launch what is there
+    int rc = flush_line_batch();
+    if (rc) return rc;
+  }
   // wait for the tracker threads: spin (the result is normally there already, or a few microseconds away), then yield
   for (unsigned spins = 0; cur.stage.load(std::memory_order_acquire) != 3; spins++) {
     if (spins < kSpin) cpu_pause();

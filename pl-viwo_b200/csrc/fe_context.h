@@ -85,6 +85,7 @@ struct FrameSlot {
   double vp[6] = {0, 0, 0, 0, 0, 0};
   bool has_vp = false;
   bool busy = false;
+  bool line_pending = false;     // the frame waits in the handle's line batch (its line path is not launched yet)
   double K[4] = {0, 0, 0, 0}, D[4] = {0, 0, 0, 0};   // calibration in force when the frame was submitted
   FrameResult res;
   std::atomic<int> stage{0};     // 0 idle, 1 submitted, 2 point tracker done, 3 complete (line tracker done)
@@ -192,6 +193,7 @@ class FeContext {
   int record_image_path(FrameSlot &s, cudaStream_t st);
   int record_fast_path(FrameSlot &s, cudaStream_t st);
   int record_line_path(FrameSlot &s, cudaStream_t st);
+  int flush_line_batch();   // launches the line paths of the frames waiting in pending_lines_ as ONE batch
   int build_graphs(FrameSlot &s);
   void destroy_graphs(FrameSlot &s);
   void layout_cells();                       // all grid cells of the frame (Grider_GRID geometry)
@@ -252,6 +254,8 @@ class FeContext {
   bool cells_uploaded_ = false;
   int layout_version_ = 0;
   bool use_graphs_ = true;
+  int line_batch_ = 1;                  // frames per line-path launch (PLVIWO_LINE_BATCH; 1 = per-frame graph replay)
+  std::vector<int> pending_lines_;      // caller's thread: slots whose line path waits for the batch to fill
   std::vector<uint64_t> occ_bits_;
   std::mutex wstat_mu_;
   std::vector<float> sc_px_, sc_py_;      // scratch of the line tracker

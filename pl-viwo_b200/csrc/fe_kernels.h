@@ -150,6 +150,17 @@ struct FldBuffers {
   int alloc(int w, int h, int length_threshold, int out_capacity);   // returns 0 on success
   void release();
 };
+// The line paths of several frames in one set of launches (grid.y / grid.z = frame): per-frame kernel TIME is what limits
+// a stream (the chain walk alone is > 1 ms of latency per frame and the device runs a limited number of kernels at
+// once), so frames submitted back to back share their launches.  All frames of a batch have the same size.
+constexpr int kMaxLineBatch = 8;
+struct FldBatch {
+  int n = 0;
+  DevImage half[kMaxLineBatch];
+  FldBuffers f[kMaxLineBatch];
+};
+void launch_canny_batch(const FldBatch &b, float th_low, float th_high, cudaStream_t s);
+void launch_fld_batch(const FldBatch &b, int length_threshold, float distance_threshold, cudaStream_t s, cudaEvent_t *ev = nullptr);
 constexpr int kSegsPerChainDiv = 21;  // a chain of n points yields at most n / 21 + 1 segments
 void launch_canny(const DevImage &half, float th_low, float th_high, FldBuffers &fb, cudaStream_t s);
 // ev (optional, 2 events): recorded after the connected-component kernels and after the chain walk (stage timing)

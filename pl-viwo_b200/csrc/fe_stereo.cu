@@ -121,7 +121,8 @@ int FeStereo::collect(FeStereoInfo *info) {
     lc.cur_res_ = &L.res;
     lc.cur_slot_ = cur.first;
     if (rc == FE_OK && cfg_.use_lines && L.has_vp) {
-      rc = lc.lsd_feed(L);
+      if (L.line_pending) rc = lc.flush_line_batch();
+      if (rc == FE_OK) rc = lc.lsd_feed(L);
       if (rc) err(rc, FeContext::thread_error());
       lc.flush_stats(lc.lst_);
       local.n_line_rows = (int)L.res.line_rows.size();

@@ -32,8 +32,11 @@ namespace plviwo {
 constexpr int kCnW = 64, kCnH = 16, kCnThreads = 256;
 
 __global__ void __launch_bounds__(kCnThreads)
-    k_canny(const uint8_t *__restrict__ img, int w, int h, int pitch, int low, unsigned *__restrict__ edges,
-            int words_per_row) {
+    k_canny(const __grid_constant__ FldBatch b, int low) {
+  const uint8_t *__restrict__ img = b.half[blockIdx.z].p;
+  const int w = b.half[blockIdx.z].w, h = b.half[blockIdx.z].h, pitch = b.half[blockIdx.z].pitch;
+  unsigned *__restrict__ edges = b.f[blockIdx.z].edges;
+  const int words_per_row = b.f[blockIdx.z].words_per_row;
   __shared__ uint8_t pix[kCnH + 4][kCnW + 4];
   __shared__ short sdx[kCnH + 2][kCnW + 2];
   __shared__ short sdy[kCnH + 2][kCnW + 2];
@@ -98,11 +101,18 @@ __global__ void __launch_bounds__(kCnThreads)
   }
 }
 
-void launch_canny(const DevImage &half, float th_low, float th_high, FldBuffers &fb, cudaStream_t s) {
+void launch_canny_batch(const FldBatch &b, float th_low, float th_high, cudaStream_t s) {
   (void)th_high;  // low == high is enforced at create time (no hysteresis pass is implemented)
-  dim3 grid((half.w + kCnW - 1) / kCnW, (half.h + kCnH - 1) / kCnH);
+  dim3 grid((b.half[0].w + kCnW - 1) / kCnW, (b.half[0].h + kCnH - 1) / kCnH, b.n);
   PLVIWO_CARVEOUT(k_canny);
-  k_canny<<<grid, kCnThreads, 0, s>>>(half.p, half.w, half.h, half.pitch, (int)floorf(th_low), fb.edges, fb.words_per_row);
+  k_canny<<<grid, kCnThreads, 0, s>>>(b, (int)floorf(th_low));
+}
+void launch_canny(const DevImage &half, float th_low, float th_high, FldBuffers &fb, cudaStream_t s) {
+  FldBatch b;
+  b.n = 1;
+  b.half[0] = half;
+  b.f[0] = fb;
+  launch_canny_batch(b, th_low, th_high, s);
 }
 
 __global__ void k_unpack_edges(const unsigned *__restrict__ edges, int words_per_row, int w, int h,
@@ -137,9 +147,12 @@ __device__ __forceinline__ void ccl_union(int *parent, int a, int b) {
   }
 }
 
-__global__ void k_ccl_init(const unsigned *__restrict__ edges, int words_per_row, int w, int h, int *__restrict__ label,
-                           int *__restrict__ cnt, int *__restrict__ bbox /* maxy, minx, maxx planes */,
-                           int *__restrict__ counters) {
+__global__ void k_ccl_init(const __grid_constant__ FldBatch b, int w, int h) {
+  const FldBuffers &fb = b.f[blockIdx.y];
+  const unsigned *__restrict__ edges = fb.edges;
+  const int words_per_row = fb.words_per_row;
+  int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt, *__restrict__ bbox = fb.bbox /* maxy, minx, maxx planes */;
+  int *__restrict__ counters = fb.counters;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 8) counters[i] = 0;
   if (i >= w * h) return;
@@ -152,7 +165,8 @@ __global__ void k_ccl_init(const unsigned *__restrict__ edges, int words_per_row
   bbox[2 * w * h + i] = -1;    // max x
 }
 
-__global__ void k_ccl_merge(int w, int h, int *__restrict__ label) {
+__global__ void k_ccl_merge(const __grid_constant__ FldBatch b, int w, int h) {
+  int *__restrict__ label = b.f[blockIdx.y].label;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= w * h) return;
   if (label[i] < 0) return;
@@ -167,7 +181,8 @@ __global__ void k_ccl_merge(int w, int h, int *__restrict__ label) {
 }
 
 // flatten + per-component pixel count and bounding box (warp-aggregated atomics keyed by the root)
-__global__ void k_ccl_flatten(int w, int h, int *__restrict__ label, int *__restrict__ cnt, int *__restrict__ bbox) {
+__global__ void k_ccl_flatten(const __grid_constant__ FldBatch b, int w, int h) {
+  int *__restrict__ label = b.f[blockIdx.y].label, *__restrict__ cnt = b.f[blockIdx.y].cnt, *__restrict__ bbox = b.f[blockIdx.y].bbox;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int root = -1;
   if (i < w * h && label[i] >= 0) {
@@ -196,8 +211,11 @@ constexpr int kClassA = 1024, kClassB = 128;   // pixels
 __host__ __device__ inline int comp_cap_a(int n) { return n / kClassA + 1; }
 __host__ __device__ inline int comp_cap_b(int n) { return n / kClassB + 1; }
 
-__global__ void k_ccl_roots(int w, int h, const int *__restrict__ label, const int *__restrict__ cnt, int min_pixels,
-                            int *__restrict__ comp_root, int *__restrict__ counters, int max_comps) {
+__global__ void k_ccl_roots(const __grid_constant__ FldBatch b, int w, int h, int min_pixels) {
+  const FldBuffers &fb = b.f[blockIdx.y];
+  const int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt;
+  int *__restrict__ comp_root = fb.comp_root, *__restrict__ counters = fb.counters;
+  const int max_comps = fb.max_chains;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= w * h) return;
   if (label[i] != i) return;
@@ -312,11 +330,16 @@ __device__ __forceinline__ void sts_u32(unsigned addr, unsigned v) {
 // shift -> key -> table load -> decode, ~90 cycles; the first version (one thread, 6 loads + ~150 instructions per
 // step) needed ~600.
 __global__ void __launch_bounds__(kWalkThreads)
-    k_fld_walk_cc(const unsigned *__restrict__ edges, int words_per_row, const int *__restrict__ label,
-                  const int *__restrict__ cnt, const int *__restrict__ bbox, int w, int h,
-                  const int *__restrict__ comp_root, int *__restrict__ counters, int max_comps, int length_threshold,
-                  int2 *__restrict__ chain_pts, int *__restrict__ chain_seed, int *__restrict__ chain_off,
-                  int *__restrict__ chain_len, int max_chains) {
+    k_fld_walk_cc(const __grid_constant__ FldBatch b, int w, int h, int length_threshold) {
+  const FldBuffers &fb = b.f[blockIdx.y];
+  const unsigned *__restrict__ edges = fb.edges;
+  const int words_per_row = fb.words_per_row;
+  const int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt, *__restrict__ bbox = fb.bbox;
+  const int *__restrict__ comp_root = fb.comp_root;
+  int *__restrict__ counters = fb.counters;
+  const int max_comps = fb.max_chains, max_chains = fb.max_chains;
+  int2 *__restrict__ chain_pts = fb.chain_pts;
+  int *__restrict__ chain_seed = fb.chain_seed, *__restrict__ chain_off = fb.chain_off, *__restrict__ chain_len = fb.chain_len;
   extern __shared__ __align__(16) uint8_t walk_smem[];   // decision tables, then the private bit map
   uint8_t *lut = walk_smem;
   unsigned *bm = reinterpret_cast<unsigned *>(walk_smem + kLutSize);
@@ -503,8 +526,11 @@ __global__ void __launch_bounds__(kWalkThreads)
 }
 
 // rank of every chain by the raster index of its seed (seeds are distinct pixels): order[rank] = chain
-__global__ void k_fld_order(const int *__restrict__ chain_seed, const int *__restrict__ counters, int max_chains,
-                            int *__restrict__ order) {
+__global__ void k_fld_order(const __grid_constant__ FldBatch b) {
+  const FldBuffers &fb = b.f[blockIdx.y];
+  const int *__restrict__ chain_seed = fb.chain_seed, *__restrict__ counters = fb.counters;
+  int *__restrict__ order = fb.order;
+  const int max_chains = fb.max_chains;
   const int n = min(counters[3], max_chains);
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
@@ -563,11 +589,16 @@ __device__ __forceinline__ void incident_point(const double l[3], float &px, flo
 
 // one thread per chain, in seed order; chain c writes its segments to slots chain_off[c] / 21 + j (collision free:
 // every segment consumes at least 21 chain points and the chains' point ranges are disjoint)
-__global__ void k_fld_segments(const uint8_t *__restrict__ img, int W, int H, int pitch, int T, float dist_thr,
-                               const int2 *__restrict__ chain_pts, const int *__restrict__ chain_off,
-                               const int *__restrict__ chain_len, const int *__restrict__ order,
-                               const int *__restrict__ counters, int max_chains, float4 *__restrict__ segs,
-                               int *__restrict__ seg_cnt, int *__restrict__ seg_base) {
+__global__ void k_fld_segments(const __grid_constant__ FldBatch b, int T, float dist_thr) {
+  const FldBuffers &fb = b.f[blockIdx.y];
+  const uint8_t *__restrict__ img = b.half[blockIdx.y].p;
+  const int W = b.half[blockIdx.y].w, H = b.half[blockIdx.y].h, pitch = b.half[blockIdx.y].pitch;
+  const int2 *__restrict__ chain_pts = fb.chain_pts;
+  const int *__restrict__ chain_off = fb.chain_off, *__restrict__ chain_len = fb.chain_len, *__restrict__ order = fb.order;
+  const int *__restrict__ counters = fb.counters;
+  const int max_chains = fb.max_chains;
+  float4 *__restrict__ segs = fb.segs;
+  int *__restrict__ seg_cnt = fb.seg_cnt, *__restrict__ seg_base = fb.seg_cnt + fb.max_chains;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= min(counters[3], max_chains)) return;
   const int c = order[r];
@@ -656,8 +687,13 @@ __global__ void k_fld_segments(const uint8_t *__restrict__ img, int W, int H, in
 
 // ordered compaction of the per-chain segment slots (one block)
 __global__ void __launch_bounds__(256)
-    k_fld_compact(const float4 *__restrict__ segs, const int *__restrict__ seg_cnt, const int *__restrict__ seg_base,
-                  int *__restrict__ counters, int max_chains, float4 *__restrict__ out, int out_cap) {
+    k_fld_compact(const __grid_constant__ FldBatch b) {
+  const FldBuffers &fb = b.f[blockIdx.y];
+  const float4 *__restrict__ segs = fb.segs;
+  const int *__restrict__ seg_cnt = fb.seg_cnt, *__restrict__ seg_base = fb.seg_cnt + fb.max_chains;
+  int *__restrict__ counters = fb.counters;
+  const int max_chains = fb.max_chains, out_cap = fb.out_cap;
+  float4 *__restrict__ out = fb.out;
   __shared__ int warp_tot[8];
   __shared__ int s_running;
   const int n = min(counters[3], max_chains);
@@ -719,39 +755,57 @@ void FldBuffers::release() {
   *this = FldBuffers();
 }
 
-void launch_fld(const DevImage &half, int length_threshold, float distance_threshold, FldBuffers &fb, cudaStream_t s,
-                cudaEvent_t *ev) {
-  const int w = half.w, h = half.h, n = w * h;
+// measurement only (PLVIWO_EXP_SKIP=5): a stand-in for the chain walk that stays resident for about as long (800 us)
+// with the same grid, block and shared-memory footprint but touches no memory
+__global__ void __launch_bounds__(kWalkThreads) k_fld_walk_sleep() {
+  extern __shared__ __align__(16) uint8_t walk_smem[];
+  if (threadIdx.x == 0) {
+    walk_smem[0] = 0;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+      __nanosleep(2000);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < 800000ull);
+  }
+  __syncthreads();
+}
+
+void launch_fld_batch(const FldBatch &b, int length_threshold, float distance_threshold, cudaStream_t s, cudaEvent_t *ev) {
+  const int w = b.half[0].w, h = b.half[0].h, n = w * h;
   const int tpb = 256, nb = (n + tpb - 1) / tpb;
+  const int max_chains = b.f[0].max_chains;
   // measurement only (profiles/exp_bench.py): PLVIWO_EXP_SKIP = 1 skips the whole segment extraction (no segments come
   // back), 2 keeps the connected components and skips walk + segments, 3 runs the component merge three times, 4 keeps
-  // components + walk and skips the segment fit
+  // components + walk and skips the segment fit, 5 replaces the walk by a kernel that only stays resident
   static const int exp_skip = [] {
     const char *e = std::getenv("PLVIWO_EXP_SKIP");
     return e ? std::atoi(e) : 0;
   }();
+  auto zero_counts = [&](int first, int count) {
+    for (int k = 0; k < b.n; k++) cudaMemsetAsync(b.f[k].counters + first, 0, count * sizeof(int), s);
+  };
   if (exp_skip == 1) {
-    cudaMemsetAsync(fb.counters, 0, 8 * sizeof(int), s);
+    zero_counts(0, 8);
     if (ev) { cudaEventRecord(ev[0], s); cudaEventRecord(ev[1], s); }
     return;
   }
+  const dim3 gpx(nb, b.n);
   PLVIWO_CARVEOUT(k_ccl_init);
-  k_ccl_init<<<nb, tpb, 0, s>>>(fb.edges, fb.words_per_row, w, h, fb.label, fb.cnt, fb.bbox, fb.counters);
+  k_ccl_init<<<gpx, tpb, 0, s>>>(b, w, h);
   PLVIWO_CARVEOUT(k_ccl_merge);
-  k_ccl_merge<<<nb, tpb, 0, s>>>(w, h, fb.label);
+  k_ccl_merge<<<gpx, tpb, 0, s>>>(b, w, h);
   if (exp_skip == 3) {
-    PLVIWO_CARVEOUT(k_ccl_merge);
-    k_ccl_merge<<<nb, tpb, 0, s>>>(w, h, fb.label);
-    PLVIWO_CARVEOUT(k_ccl_merge);
-    k_ccl_merge<<<nb, tpb, 0, s>>>(w, h, fb.label);
+    k_ccl_merge<<<gpx, tpb, 0, s>>>(b, w, h);
+    k_ccl_merge<<<gpx, tpb, 0, s>>>(b, w, h);
   }
   PLVIWO_CARVEOUT(k_ccl_flatten);
-  k_ccl_flatten<<<nb, tpb, 0, s>>>(w, h, fb.label, fb.cnt, fb.bbox);
+  k_ccl_flatten<<<gpx, tpb, 0, s>>>(b, w, h);
   PLVIWO_CARVEOUT(k_ccl_roots);
-  k_ccl_roots<<<nb, tpb, 0, s>>>(w, h, fb.label, fb.cnt, length_threshold + 1, fb.comp_root, fb.counters, fb.max_chains);
+  k_ccl_roots<<<gpx, tpb, 0, s>>>(b, w, h, length_threshold + 1);
   if (ev) cudaEventRecord(ev[0], s);
   if (exp_skip == 2) {
-    cudaMemsetAsync(fb.counters + 3, 0, 2 * sizeof(int), s);
+    zero_counts(3, 2);
     if (ev) cudaEventRecord(ev[1], s);
     return;
   }
@@ -760,33 +814,43 @@ void launch_fld(const DevImage &half, int length_threshold, float distance_thres
   size_t smem = (size_t)kLutSize + (size_t)(h + 2 * kPadRows) * ws * sizeof(unsigned);
   static SmemOptIn optin;
   optin.ensure(k_fld_walk_cc, smem);
-  // Grid size: the walk is bound by its longest component (a sequential chain of ~130-cycle steps), not by the number of
-  // walkers, and many frames' walks are in flight at once on a pipelined stream: a small persistent grid leaves the SMs'
-  // thread slots to the latency-critical kernels (LK) of the frames being tracked.  PLVIWO_WALK_CTAS overrides.
-  static const int walk_ctas = [] {
+  // Grid size per frame: the walk is bound by its longest component (a sequential chain of ~130-cycle steps), not by the
+  // number of walkers; a batch of frames shares one launch (grid.y = frame).  PLVIWO_WALK_CTAS overrides.
+  static const int walk_ctas_env = [] {
     const char *e = std::getenv("PLVIWO_WALK_CTAS");
-    const int v = e ? std::atoi(e) : 0;
-    return v > 0 ? v : kWalkCtas;
+    return e ? std::atoi(e) : 0;
   }();
+  const int walk_ctas = walk_ctas_env > 0 ? walk_ctas_env : (b.n > 1 ? 148 : kWalkCtas);
   PLVIWO_CARVEOUT(k_fld_walk_cc);
-  k_fld_walk_cc<<<walk_ctas, kWalkThreads, smem, s>>>(fb.edges, fb.words_per_row, fb.label, fb.cnt, fb.bbox, w, h, fb.comp_root, fb.counters, fb.max_chains,
-                                               length_threshold, fb.chain_pts, fb.chain_seed, fb.chain_off, fb.chain_len,
-                                               fb.max_chains);
-  if (ev) cudaEventRecord(ev[1], s);
-  if (exp_skip == 4) {   // walk kept, order / segments / compact skipped
-    cudaMemsetAsync(fb.counters + 3, 0, 2 * sizeof(int), s);
+  if (exp_skip == 5) {
+    static SmemOptIn optin_sleep;
+    optin_sleep.ensure(k_fld_walk_sleep, smem);
+    k_fld_walk_sleep<<<dim3(walk_ctas, b.n), kWalkThreads, smem, s>>>();
+    zero_counts(3, 2);
+    if (ev) cudaEventRecord(ev[1], s);
     return;
   }
-  int blocks = (fb.max_chains + 127) / 128;
+  k_fld_walk_cc<<<dim3(walk_ctas, b.n), kWalkThreads, smem, s>>>(b, w, h, length_threshold);
+  if (ev) cudaEventRecord(ev[1], s);
+  if (exp_skip == 4) {   // walk kept, order / segments / compact skipped
+    zero_counts(3, 2);
+    return;
+  }
   PLVIWO_CARVEOUT(k_fld_order);
-  k_fld_order<<<blocks, 128, 0, s>>>(fb.chain_seed, fb.counters, fb.max_chains, fb.order);
+  k_fld_order<<<dim3((max_chains + 127) / 128, b.n), 128, 0, s>>>(b);
   PLVIWO_CARVEOUT(k_fld_segments);
-  k_fld_segments<<<(fb.max_chains + 63) / 64, 64, 0, s>>>(half.p, w, h, half.pitch, length_threshold, distance_threshold,
-                                                          fb.chain_pts, fb.chain_off, fb.chain_len, fb.order, fb.counters,
-                                                          fb.max_chains, fb.segs, fb.seg_cnt, fb.seg_cnt + fb.max_chains);
+  k_fld_segments<<<dim3((max_chains + 63) / 64, b.n), 64, 0, s>>>(b, length_threshold, distance_threshold);
   PLVIWO_CARVEOUT(k_fld_compact);
-  k_fld_compact<<<1, 256, 0, s>>>(fb.segs, fb.seg_cnt, fb.seg_cnt + fb.max_chains, fb.counters, fb.max_chains, fb.out,
-                                  fb.out_cap);
+  k_fld_compact<<<dim3(1, b.n), 256, 0, s>>>(b);
+}
+
+void launch_fld(const DevImage &half, int length_threshold, float distance_threshold, FldBuffers &fb, cudaStream_t s,
+                cudaEvent_t *ev) {
+  FldBatch b;
+  b.n = 1;
+  b.half[0] = half;
+  b.f[0] = fb;
+  launch_fld_batch(b, length_threshold, distance_threshold, s, ev);
 }
 
 }  // namespace plviwo

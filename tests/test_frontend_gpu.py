@@ -286,6 +286,52 @@ def test_state_roundtrip_and_pipelined_submit(fe, synth):
         h.close()
 
 
+@pytest.mark.parametrize("lookahead,pattern", [(8, "steady"), (16, "steady"), (8, "ragged")])
+def test_batched_line_path_equals_frame_by_frame(fe, synth, lookahead, pattern):
+    """With lookahead >= 8 the line paths of consecutive frames share their kernel launches (grid.y = frame, batches of
+    min(4, lookahead / 2)); rows must equal the synchronous per-frame path bit for bit — also when collect() arrives before a
+    batch is full (ragged: collect after every 1, 2, 3, 5, ... submits) and when a handle is closed with frames pending."""
+    n = 14
+    seq = synth.SynthSequence(seed=1016, n_frames=n)
+    cfg = dict(width=1280, height=560, K=seq.K, D=seq.D, **CFG1)
+    a = fe.FrontEnd(fe.default_config(**cfg))
+    ref = []
+    for t in range(n):
+        a.feed_new_camera(seq.timestamp(t), seq.frame(t), None, seq.vanishing_points(t))
+        lr, lp = a.line_rows()
+        ref.append((a.point_rows().copy(), lr.copy(), lp.copy()))
+    a.close()
+    assert sum(len(r[1]) for r in ref) > 50
+    b = fe.FrontEnd(fe.default_config(lookahead=lookahead, **cfg))
+    frames = [seq.frame(t) for t in range(n)]
+    nsub = ncol = 0
+    burst = [1, 2, 3, 5, 1, 2] if pattern == "ragged" else None
+    k = 0
+    while ncol < n:
+        if burst is not None:
+            want = burst[k % len(burst)]
+            k += 1
+        else:
+            want = lookahead + 1 - (nsub - ncol)
+        for _ in range(max(want, 0)):
+            if nsub < n and nsub - ncol <= lookahead:
+                b.submit(seq.timestamp(nsub), frames[nsub], vanishing_points=seq.vanishing_points(nsub))
+                nsub += 1
+        ncoll_now = 1 if burst is None else min(nsub - ncol, 2)
+        for _ in range(max(ncoll_now, 1)):
+            if ncol < nsub:
+                b.collect()
+                lr, lp = b.line_rows()
+                assert np.array_equal(b.point_rows(), ref[ncol][0]), ncol
+                assert np.array_equal(lr, ref[ncol][1]), ncol
+                assert np.array_equal(lp, ref[ncol][2]), ncol
+                ncol += 1
+    # frames pending (some in an unlaunched batch) when the handle goes away: must not hang
+    for t in range(3):
+        b.submit(100.0 + t, frames[t], vanishing_points=seq.vanishing_points(t))
+    b.close()
+
+
 def test_multi_stream_isolation(fe, synth):
     """A stream's rows do not depend on what else runs on the GPU: 4 handles interleaved == each run alone."""
     seqs = [synth.SynthSequence(seed=1020 + k, n_frames=6, hard=False) for k in range(4)]

@@ -28,7 +28,8 @@ def _run(fe, synth, n_frames, kw, seed=1000, width=1280, height=560, teacher_for
          K_right=None, lookahead=0):
     seq = synth.SynthSequence(seed=seed, width=width, height=height, n_frames=n_frames, hard=hard, moving_mask=moving_mask)
     o = ost.TrackKLTStereo(ofe.FeConfig(K=seq.K, D=seq.D, **kw), K_right=K_right)
-    g = fe.StereoFrontEnd(fe.default_config(width=width, height=height, K=seq.K, D=seq.D, lookahead=lookahead, **kw), K_right=K_right)
+    g = fe.StereoFrontEnd(fe.default_config(width=width, height=height, K=seq.K, D=seq.D, lookahead=lookahead, use_lines=0, **kw),
+                          K_right=K_right)
     s = dict(frames=0, rows=0, rows_sym=0, order_equal=0, frames_equal=0, stereo_rows=0, det_left=0, det_right=0, new_stereo=0,
              first_divergence=None)
     duv, dun = [0.0], [0.0]
