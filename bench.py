@@ -40,7 +40,7 @@ WORKLOAD = dict(width=1280, height=560, num_features=400, fast_threshold=20, gri
                 pyr_levels=4, win_size=15)
 WORKLOAD_NAME = "BASELINE.json configs[1]: synthetic KAIST-shaped 1280x560 mono, point+line front end, 400 pts, 5x5 grid, maxLevel 4, win 15"
 SEQ_FRAMES = 300
-LOOKAHEAD = 24
+LOOKAHEAD = 48
 METRIC = "front-end frames/sec @1280x560"
 KERNEL_OF_STAGE = {"hist": "k_hist", "eq_pyr1": "k_eq_pyr1", "pyr_rest": "k_pyr_down", "fast": "k_fast", "subpix": "k_corner_subpix",
                    "lk": "k_lk15", "canny": "k_canny", "fld_walk": "k_fld_walk_cc", "fld_ccl": "k_ccl_merge", "fld_seg": "k_fld_segments"}
@@ -221,7 +221,7 @@ def run_gpu_multi(fe_mod, torch, seq, d_ptrs, pitch, n_streams, steps, warmup, c
     exchange data, so this is n_streams times the single-stream work)."""
     import threading
     n = len(d_ptrs)
-    la = int(os.environ.get("PLVIWO_BENCH_LA", "8"))
+    la = int(os.environ.get("PLVIWO_BENCH_LA", "16"))
     handles = [fe_mod.FrontEnd(fe_mod.default_config(K=seq.K, D=seq.D, lookahead=la, **cfg_kw), device=dev) for _ in range(n_streams)]
     gate = threading.Barrier(n_streams + 1)
     frames_done = [0] * n_streams

@@ -292,10 +292,16 @@ int FeContext::init() {
     FE_CUDA(cudaMalloc(&s.d_sc_done, sizeof(unsigned)));
     FE_CUDA(cudaMemset(s.d_sc_done, 0, sizeof(unsigned)));
   }
-  // Opt-in (PLVIWO_SPECULATION=1): measured on B200 it is throughput-neutral for one stream — the LK launch-to-flag
-  // latency under load (~60-100 us) is about the host work it would hide — and it costs ~40 % more LK work on the GPU, so
-  // it is off by default.  Results are bit-identical either way (tests/test_frontend_gpu.py).
-  use_spec_ = std::getenv("PLVIWO_SPECULATION") != nullptr && std::atoi(std::getenv("PLVIWO_SPECULATION")) != 0;
+  // Speculative tracking is on whenever frames are pipelined (PLVIWO_SPECULATION=0 switches it off): it takes RANSAC and
+  // the detection glue off the point tracker's dependent chain (100 -> 67 us per frame) at ~40 % more LK work.  It only
+  // pays when the line path keeps up — which it does since consecutive frames share their line-path launches
+  // (line_batch_) and the lookahead is deep enough (profiles/experiments_r1.md: 9.3 k -> 12.4 k frames/s).  Results are
+  // bit-identical either way (tests/test_frontend_gpu.py).  A synchronous handle (lookahead 0) never has a next frame to
+  // speculate into.
+  {
+    const char *e = std::getenv("PLVIWO_SPECULATION");
+    use_spec_ = e ? std::atoi(e) != 0 : cfg_.lookahead >= 1;
+  }
   use_spec_cand_ = std::getenv("PLVIWO_NO_CANDIDATE_SPECULATION") == nullptr;
   FE_CUDA(cudaMallocHost(&h_pts0_, (size_t)max_pts_ * sizeof(float2)));
   FE_CUDA(cudaMallocHost(&h_pts1_, (size_t)max_pts_ * sizeof(float2)));

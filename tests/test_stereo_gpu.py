@@ -135,10 +135,12 @@ def test_stereo_bad_arguments_and_setters(fe, synth):
         g.collect()                                                                   # nothing submitted
     g.submit(1.0, seq.frame(0, 0), seq.frame(0, 1))
     g.submit(1.1, seq.frame(1, 0), seq.frame(1, 1))
+    g.submit(1.2, seq.frame(2, 0), seq.frame(2, 1))                                    # lookahead + 2 slots, none holds a "last" pair yet
     with pytest.raises(fe.FrontEndError):
-        g.submit(1.2, seq.frame(2, 0), seq.frame(2, 1))                                # lookahead window full
+        g.submit(1.3, seq.frame(3, 0), seq.frame(3, 1))                                # lookahead window full
     with pytest.raises(fe.FrontEndError):
         g.set_num_features(50)                                                        # pairs pending
+    g.collect()
     g.collect()
     g.collect()
     ids = g.get_last_ids()
