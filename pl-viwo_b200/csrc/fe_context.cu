@@ -1600,27 +1600,33 @@ int FeContext::lsd_feed(FrameSlot &cur) {
     pol_last_ = pol_new;
     return FE_OK;
   }
-  // LineMatch (:368-407): i over new lines, j over last lines, the LAST satisfying j wins
+  // LineMatch (:368-407): i over new lines, j over last lines, the LAST satisfying j wins.  The reference walks every
+  // (i, j) pair and every point id of line j; a pair can only match if the two lines share a point id — j matches i iff
+  // they share >= 2 ids, or >= 1 id and LineSimilar holds (the inner loop stops at the first shared id when the lines are
+  // similar, at the second otherwise) — so the candidates come from an inverted index id -> last lines holding it.
   std::map<int, int> matches;
   const size_t n0 = pol_last_.size(), n1 = pol_new.size();
   if (n0 != 0 && n1 != 0) {
+    std::vector<std::pair<int, int>> &inv = sc_inv_;   // (point id, last line), sorted
+    inv.clear();
+    for (size_t j = 0; j < n0; j++)
+      for (auto &pt : pol_last_[j]) inv.emplace_back(pt.first, (int)j);
+    std::sort(inv.begin(), inv.end());
+    std::vector<int> &shared = sc_shared_, &touched = sc_touched_;
+    shared.assign(n0, 0);
     for (size_t i = 0; i < n1; i++) {
-      if (pol_new[i].size() < 1) continue;
-      for (size_t j = 0; j < n0; j++) {
-        if (pol_last_[j].size() < 1) continue;
-        int m = 0;
-        for (auto &pt : pol_last_[j]) {
-          if (pol_new[i].find(pt.first) == pol_new[i].end()) continue;
-          m += 1;
-          if (m >= 2) {
-            matches[(int)i] = (int)j;
-            break;
-          } else if (m == 1 && line_similar(filt_lines[i], lines_last_[j])) {
-            matches[(int)i] = (int)j;
-            break;
-          }
-        }
+      touched.clear();
+      for (auto &pt : pol_new[i]) {
+        auto lo = std::lower_bound(inv.begin(), inv.end(), std::make_pair(pt.first, -1));
+        for (; lo != inv.end() && lo->first == pt.first; ++lo)
+          if (shared[lo->second]++ == 0) touched.push_back(lo->second);
       }
+      int best = -1;
+      for (int j : touched) {
+        if (j > best && (shared[j] >= 2 || line_similar(filt_lines[i], lines_last_[j]))) best = j;
+        shared[j] = 0;
+      }
+      if (best >= 0) matches[(int)i] = best;
     }
   }
   info->n_line_matches = (int)matches.size();
@@ -1654,9 +1660,9 @@ int FeContext::lsd_feed(FrameSlot &cur) {
     }
     line_rows.push_back(r);
   }
-  lines_last_ = filt_lines;  // :175-182
-  line_ids_last_ = good_ids;
-  pol_last_ = pol_new;
+  lines_last_.swap(filt_lines);  // :175-182
+  line_ids_last_.swap(good_ids);
+  pol_last_.swap(pol_new);
   return FE_OK;
 }
 

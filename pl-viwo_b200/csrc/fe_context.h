@@ -260,6 +260,8 @@ class FeContext {
   std::mutex wstat_mu_;
   std::vector<float> sc_px_, sc_py_;      // scratch of the line tracker
   std::vector<uint8_t> sc_pass_;
+  std::vector<std::pair<int, int>> sc_inv_;
+  std::vector<int> sc_shared_, sc_touched_;
   // ---- tracking scratch
   int max_pts_ = 0;
   float2 *d_pts0_ = nullptr, *d_pts1_ = nullptr, *d_p0n_ = nullptr, *d_p1n_ = nullptr;
