@@ -25,7 +25,7 @@ struct SmemOptIn {
 };
 
 // One shared-memory / L1 split for EVERY kernel of the library (PLVIWO_CARVEOUT = percent of the SM's unified storage
-// preferred as shared memory; unset = the driver's per-kernel default).  Kernels that prefer different splits cannot share
+// preferred as shared memory; default 100, -1 = the driver's per-kernel default).  Kernels that prefer different splits cannot share
 // an SM until it has drained and been reconfigured; with dozens of kernels of several frames resident at once — among
 // them millisecond-long persistent ones that opt in to > 48 KB — a short latency-critical launch then only gets the SMs
 // whose current split happens to suit it.
