@@ -755,60 +755,20 @@ void FldBuffers::release() {
   *this = FldBuffers();
 }
 
-// measurement only (PLVIWO_EXP_SKIP=5): a stand-in for the chain walk that stays resident for about as long (800 us)
-// with the same grid, block and shared-memory footprint but touches no memory
-__global__ void __launch_bounds__(kWalkThreads) k_fld_walk_sleep() {
-  extern __shared__ __align__(16) uint8_t walk_smem[];
-  if (threadIdx.x == 0) {
-    walk_smem[0] = 0;
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    do {
-      __nanosleep(2000);
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    } while (t1 - t0 < 800000ull);
-  }
-  __syncthreads();
-}
-
 void launch_fld_batch(const FldBatch &b, int length_threshold, float distance_threshold, cudaStream_t s, cudaEvent_t *ev) {
   const int w = b.half[0].w, h = b.half[0].h, n = w * h;
   const int tpb = 256, nb = (n + tpb - 1) / tpb;
   const int max_chains = b.f[0].max_chains;
-  // measurement only (profiles/exp_bench.py): PLVIWO_EXP_SKIP = 1 skips the whole segment extraction (no segments come
-  // back), 2 keeps the connected components and skips walk + segments, 3 runs the component merge three times, 4 keeps
-  // components + walk and skips the segment fit, 5 replaces the walk by a kernel that only stays resident
-  static const int exp_skip = [] {
-    const char *e = std::getenv("PLVIWO_EXP_SKIP");
-    return e ? std::atoi(e) : 0;
-  }();
-  auto zero_counts = [&](int first, int count) {
-    for (int k = 0; k < b.n; k++) cudaMemsetAsync(b.f[k].counters + first, 0, count * sizeof(int), s);
-  };
-  if (exp_skip == 1) {
-    zero_counts(0, 8);
-    if (ev) { cudaEventRecord(ev[0], s); cudaEventRecord(ev[1], s); }
-    return;
-  }
   const dim3 gpx(nb, b.n);
   PLVIWO_CARVEOUT(k_ccl_init);
   k_ccl_init<<<gpx, tpb, 0, s>>>(b, w, h);
   PLVIWO_CARVEOUT(k_ccl_merge);
   k_ccl_merge<<<gpx, tpb, 0, s>>>(b, w, h);
-  if (exp_skip == 3) {
-    k_ccl_merge<<<gpx, tpb, 0, s>>>(b, w, h);
-    k_ccl_merge<<<gpx, tpb, 0, s>>>(b, w, h);
-  }
   PLVIWO_CARVEOUT(k_ccl_flatten);
   k_ccl_flatten<<<gpx, tpb, 0, s>>>(b, w, h);
   PLVIWO_CARVEOUT(k_ccl_roots);
   k_ccl_roots<<<gpx, tpb, 0, s>>>(b, w, h, length_threshold + 1);
   if (ev) cudaEventRecord(ev[0], s);
-  if (exp_skip == 2) {
-    zero_counts(3, 2);
-    if (ev) cudaEventRecord(ev[1], s);
-    return;
-  }
   init_fld_constants();
   const int ws = ((w + 31) >> 5) + 2;
   size_t smem = (size_t)kLutSize + (size_t)(h + 2 * kPadRows) * ws * sizeof(unsigned);
@@ -822,20 +782,8 @@ void launch_fld_batch(const FldBatch &b, int length_threshold, float distance_th
   }();
   const int walk_ctas = walk_ctas_env > 0 ? walk_ctas_env : (b.n > 1 ? 148 : kWalkCtas);
   PLVIWO_CARVEOUT(k_fld_walk_cc);
-  if (exp_skip == 5) {
-    static SmemOptIn optin_sleep;
-    optin_sleep.ensure(k_fld_walk_sleep, smem);
-    k_fld_walk_sleep<<<dim3(walk_ctas, b.n), kWalkThreads, smem, s>>>();
-    zero_counts(3, 2);
-    if (ev) cudaEventRecord(ev[1], s);
-    return;
-  }
   k_fld_walk_cc<<<dim3(walk_ctas, b.n), kWalkThreads, smem, s>>>(b, w, h, length_threshold);
   if (ev) cudaEventRecord(ev[1], s);
-  if (exp_skip == 4) {   // walk kept, order / segments / compact skipped
-    zero_counts(3, 2);
-    return;
-  }
   PLVIWO_CARVEOUT(k_fld_order);
   k_fld_order<<<dim3((max_chains + 127) / 128, b.n), 128, 0, s>>>(b);
   PLVIWO_CARVEOUT(k_fld_segments);
