@@ -257,6 +257,43 @@ def test_stereo_with_left_image_lines(fe, synth):
     assert line_equal == line_frames, (line_equal, line_frames)
 
 
+def test_stereo_pipelined_with_batched_lines(fe, synth):
+    """Stereo rig + left-image line tracker on a pipelined handle (lookahead 8: the line paths of 4 consecutive left images
+    share their launches, speculative LK is on for neither camera — the stereo state machine launches its own): rows equal
+    the synchronous handle's bit for bit, including when collect() arrives before a line batch is full."""
+    n = 10
+    seq = synth.SynthSequence(seed=1017, n_frames=n)
+    cfg = dict(width=1280, height=560, K=seq.K, D=seq.D, use_lines=1, **CFG1)
+    a = fe.StereoFrontEnd(fe.default_config(**cfg))
+    ref = []
+    for t in range(n):
+        a.feed_new_camera(seq.timestamp(t), seq.frame(t, 0), seq.frame(t, 1), vanishing_points=seq.vanishing_points(t))
+        lr, lp = a.line_rows()
+        ref.append((a.point_rows(0).copy(), a.point_rows(1).copy(), lr.copy(), lp.copy()))
+    a.close()
+    assert sum(len(r[2]) for r in ref) > 30
+    b = fe.StereoFrontEnd(fe.default_config(lookahead=8, **cfg))
+    frames = [(seq.frame(t, 0), seq.frame(t, 1)) for t in range(n)]
+    sub = col = 0
+    for burst in (2, 1, 3, 9, 9, 9, 9, 9, 9, 9):
+        for _ in range(burst):
+            if sub < n and sub - col <= 8:
+                b.submit(seq.timestamp(sub), frames[sub][0], frames[sub][1], vanishing_points=seq.vanishing_points(sub))
+                sub += 1
+        if col < sub:
+            info = b.collect()
+            lr, lp = b.line_rows()
+            assert np.array_equal(b.point_rows(0), ref[col][0]) and np.array_equal(b.point_rows(1), ref[col][1]), col
+            assert info.n_line_rows == len(ref[col][2]) and np.array_equal(lr, ref[col][2]) and np.array_equal(lp, ref[col][3]), col
+            col += 1
+    while col < n:
+        b.collect()
+        assert np.array_equal(b.point_rows(0), ref[col][0]), col
+        assert np.array_equal(b.line_rows()[0], ref[col][2]), col
+        col += 1
+    b.close()
+
+
 def test_stereo_golden_rows(fe, synth):
     """Rows of the cv2-driven oracle committed as a fixture (tests/golden/make_golden_stereo.py)."""
     gold = np.load(GOLDEN)
