@@ -299,6 +299,11 @@ int plviwo_op_fld(int device, const uint8_t *img, int w, int h, int length_thres
  * fast, canny (mean per launch).  Used by bench.py to report what the kernels reach when a launch carries enough
  * bytes (a batch of frames' worth) instead of one 0.7 MB frame. */
 int plviwo_op_image_kernels_time(int device, int w, int h, int iters, float ms[4]);
+/* TrackLSD::LineMatch (TrackLSD.cpp:368-407) on CSR inputs: line j of the last frame holds point ids
+ * last_pids[last_off[j] .. last_off[j + 1]), lines are x1 y1 x2 y2; match_out[i] = index of the last-frame line whose id new
+ * line i inherits, or -1.  Host-side step, no GPU needed. */
+int plviwo_op_line_match(int n_last, const int32_t *last_off, const int32_t *last_pids, const float *last_lines, int n_new,
+                         const int32_t *new_off, const int32_t *new_pids, const float *new_lines, int32_t *match_out);
 int plviwo_op_ransac_fundamental(const float *p0n, const float *p1n, int n, double threshold, double confidence,
                                  uint8_t *mask, int *n_inliers); /* host-side sequential step (K9) */
 

@@ -105,7 +105,7 @@ EXPORTS = [
     "plviwo_fe_stereo_set_num_features", "plviwo_fe_stereo_change_feat_id", "plviwo_fe_stereo_feed", "plviwo_fe_stereo_submit",
     "plviwo_fe_stereo_collect", "plviwo_fe_stereo_get_point_rows", "plviwo_fe_stereo_get_last_obs", "plviwo_fe_stereo_get_state",
     "plviwo_fe_stereo_set_state", "plviwo_fe_stereo_get_stage_times", "plviwo_fe_stereo_get_line_rows",
-    "plviwo_fe_stereo_get_line_points", "plviwo_fe_stereo_classify_lines",
+    "plviwo_fe_stereo_get_line_points", "plviwo_fe_stereo_classify_lines", "plviwo_op_line_match",
 ]
 
 
@@ -834,6 +834,26 @@ def op_image_kernels_time(w: int, h: int, iters: int = 10, device: int = 0) -> D
     ms = (C.c_float * 4)()
     _check(lib().plviwo_op_image_kernels_time(device, w, h, iters, ms))
     return {"hist": ms[0], "eq_pyr1": ms[1], "fast": ms[2], "canny": ms[3]}
+
+
+def op_line_match(pol_last, lines_last, pol_new, lines_new) -> Dict[int, int]:
+    """TrackLSD::LineMatch through the library's host implementation: pol_* are lists of point-id collections per line."""
+    def csr(pol):
+        off = np.zeros(len(pol) + 1, np.int32)
+        off[1:] = np.cumsum([len(p) for p in pol])
+        ids = np.array([int(k) for p in pol for k in sorted(p)], np.int32)
+        return off, ids
+    lo, lp = csr(pol_last)
+    no, npid = csr(pol_new)
+    ll = np.ascontiguousarray(lines_last, np.float32).reshape(-1, 4)
+    ln = np.ascontiguousarray(lines_new, np.float32).reshape(-1, 4)
+    out = np.full(len(pol_new), -1, np.int32)
+    L = lib()
+    L.plviwo_op_line_match.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
+    _check(L.plviwo_op_line_match(len(pol_last), lo.ctypes.data, lp.ctypes.data, ll.ctypes.data, len(pol_new), no.ctypes.data,
+                                  npid.ctypes.data, ln.ctypes.data, out.ctypes.data))
+    return {i: int(j) for i, j in enumerate(out) if j >= 0}
 
 
 def op_ransac_fundamental(p0n, p1n, threshold: float, confidence: float = 0.999):

@@ -639,6 +639,32 @@ int plviwo_op_ransac_fundamental(const float *p0n, const float *p1n, int n, doub
   API_END
 }
 
+// TrackLSD::LineMatch on CSR inputs (host-side step; tests)
+int plviwo_op_line_match(int n_last, const int32_t *last_off, const int32_t *last_pids, const float *last_lines, int n_new,
+                         const int32_t *new_off, const int32_t *new_pids, const float *new_lines, int32_t *match_out) {
+  API_BEGIN
+  if (n_last < 0 || n_new < 0 || !match_out || (n_last && (!last_off || !last_lines)) || (n_new && (!new_off || !new_lines)))
+    return FE_BAD_ARG;
+  std::vector<std::map<int, double>> pl((size_t)n_last), pn((size_t)n_new);
+  std::vector<float4> ll((size_t)n_last), ln((size_t)n_new);
+  for (int j = 0; j < n_last; j++) {
+    for (int k = last_off[j]; k < last_off[j + 1]; k++) pl[(size_t)j][last_pids[k]] = 0.0;
+    ll[(size_t)j] = make_float4(last_lines[4 * j], last_lines[4 * j + 1], last_lines[4 * j + 2], last_lines[4 * j + 3]);
+  }
+  for (int i = 0; i < n_new; i++) {
+    for (int k = new_off[i]; k < new_off[i + 1]; k++) pn[(size_t)i][new_pids[k]] = 0.0;
+    ln[(size_t)i] = make_float4(new_lines[4 * i], new_lines[4 * i + 1], new_lines[4 * i + 2], new_lines[4 * i + 3]);
+  }
+  std::map<int, int> matches;
+  std::vector<std::pair<int, int>> inv;
+  std::vector<int> shared, touched;
+  line_match_host(pl, pn, ln, ll, matches, inv, shared, touched);
+  for (int i = 0; i < n_new; i++) match_out[i] = -1;
+  for (auto &m : matches) match_out[m.first] = m.second;
+  return FE_OK;
+  API_END
+}
+
 // ---- stereo rig (TrackKLT with use_stereo = true) -----------------------------------------------------------
 int plviwo_fe_stereo_create(const FeConfig *cfg, const double K_right[4], const double D_right[4], int device,
                             FeStereoHandle **out) {

@@ -1512,6 +1512,37 @@ int line_classification(const float4 &line, const double vp[6]) {  // :318-333
 }
 }  // namespace
 
+// TrackLSD::LineMatch (:368-407): i over new lines, j over last lines, the LAST satisfying j wins.  The reference walks
+// every (i, j) pair and every point id of line j; a pair can only match if the two lines share a point id — j matches i
+// iff they share >= 2 ids, or >= 1 id and LineSimilar holds (the inner loop stops at the first shared id when the lines
+// are similar, at the second otherwise) — so the candidates come from an inverted index id -> last lines holding it.
+void line_match_host(const std::vector<std::map<int, double>> &pol_last, const std::vector<std::map<int, double>> &pol_new,
+                     const std::vector<float4> &lines_new, const std::vector<float4> &lines_last, std::map<int, int> &matches,
+                     std::vector<std::pair<int, int>> &inv, std::vector<int> &shared, std::vector<int> &touched) {
+  matches.clear();
+  const size_t n0 = pol_last.size(), n1 = pol_new.size();
+  if (n0 == 0 || n1 == 0) return;
+  inv.clear();   // (point id, last line), sorted
+  for (size_t j = 0; j < n0; j++)
+    for (auto &pt : pol_last[j]) inv.emplace_back(pt.first, (int)j);
+  std::sort(inv.begin(), inv.end());
+  shared.assign(n0, 0);
+  for (size_t i = 0; i < n1; i++) {
+    touched.clear();
+    for (auto &pt : pol_new[i]) {
+      auto lo = std::lower_bound(inv.begin(), inv.end(), std::make_pair(pt.first, -1));
+      for (; lo != inv.end() && lo->first == pt.first; ++lo)
+        if (shared[lo->second]++ == 0) touched.push_back(lo->second);
+    }
+    int best = -1;
+    for (int j : touched) {
+      if (j > best && (shared[j] >= 2 || line_similar(lines_new[i], lines_last[j]))) best = j;
+      shared[j] = 0;
+    }
+    if (best >= 0) matches[(int)i] = best;
+  }
+}
+
 int FeContext::lsd_feed(FrameSlot &cur) {
   HostTimer ht(&lst_.host_ms[4]);
   FrameResult &res = cur.res;
@@ -1600,35 +1631,9 @@ int FeContext::lsd_feed(FrameSlot &cur) {
     pol_last_ = pol_new;
     return FE_OK;
   }
-  // LineMatch (:368-407): i over new lines, j over last lines, the LAST satisfying j wins.  The reference walks every
-  // (i, j) pair and every point id of line j; a pair can only match if the two lines share a point id — j matches i iff
-  // they share >= 2 ids, or >= 1 id and LineSimilar holds (the inner loop stops at the first shared id when the lines are
-  // similar, at the second otherwise) — so the candidates come from an inverted index id -> last lines holding it.
+  // LineMatch (:368-407)
   std::map<int, int> matches;
-  const size_t n0 = pol_last_.size(), n1 = pol_new.size();
-  if (n0 != 0 && n1 != 0) {
-    std::vector<std::pair<int, int>> &inv = sc_inv_;   // (point id, last line), sorted
-    inv.clear();
-    for (size_t j = 0; j < n0; j++)
-      for (auto &pt : pol_last_[j]) inv.emplace_back(pt.first, (int)j);
-    std::sort(inv.begin(), inv.end());
-    std::vector<int> &shared = sc_shared_, &touched = sc_touched_;
-    shared.assign(n0, 0);
-    for (size_t i = 0; i < n1; i++) {
-      touched.clear();
-      for (auto &pt : pol_new[i]) {
-        auto lo = std::lower_bound(inv.begin(), inv.end(), std::make_pair(pt.first, -1));
-        for (; lo != inv.end() && lo->first == pt.first; ++lo)
-          if (shared[lo->second]++ == 0) touched.push_back(lo->second);
-      }
-      int best = -1;
-      for (int j : touched) {
-        if (j > best && (shared[j] >= 2 || line_similar(filt_lines[i], lines_last_[j]))) best = j;
-        shared[j] = 0;
-      }
-      if (best >= 0) matches[(int)i] = best;
-    }
-  }
+  line_match_host(pol_last_, pol_new, filt_lines, lines_last_, matches, sc_inv_, sc_shared_, sc_touched_);
   info->n_line_matches = (int)matches.size();
   std::vector<uint64_t> good_ids(filt_lines.size());
   for (size_t i = 0; i < filt_lines.size(); i++) {  // :146-158

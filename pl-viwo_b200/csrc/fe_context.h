@@ -26,6 +26,9 @@ struct Pt {
 void pyr_down_host(const uint8_t *src, int sw, int sh, int stride, uint8_t *dst, int dw, int dh);
 int line_candidates(const float *px, const float *py, int n, float min_lx, float max_lx, float min_ly, float max_ly, float pa,
                     float pb, float pc, float plen2, uint8_t *pass);
+void line_match_host(const std::vector<std::map<int, double>> &pol_last, const std::vector<std::map<int, double>> &pol_new,
+                     const std::vector<float4> &lines_new, const std::vector<float4> &lines_last, std::map<int, int> &matches,
+                     std::vector<std::pair<int, int>> &inv, std::vector<int> &shared, std::vector<int> &touched);
 int ransac_fundamental(const float *m1, const float *m2, int count, double threshold, double confidence, uint8_t *mask,
                        int *mask_valid);
 

@@ -143,3 +143,33 @@ def test_append_new_measurements(fe):
     trk.update_feature(9, 3.0, 0, 1, 2, 0.01, 0.02)
     upd.append_new_measurements(trk)                       # failed chi-square: flag copied, nothing appended
     assert upd.get_internal_data()[9].chi_test is False and upd.get_internal_data()[9].timestamps == [2.0]
+
+
+def test_line_match_inverted_index_equals_reference_loop(fe):
+    """The library's LineMatch (inverted index id -> last lines) against the oracle's line-by-line restatement of
+    TrackLSD::LineMatch (TrackLSD.cpp:368-407: triple loop, the LAST satisfying last-frame line wins) on random line sets
+    with few distinct point ids, so that lines share 0, 1 or several ids and LineSimilar decides the 1-id cases."""
+    from oracle import frontend as ofe
+    rng = np.random.default_rng(5)
+    n_matched = 0
+    for trial in range(60):
+        n0, n1 = int(rng.integers(0, 25)), int(rng.integers(0, 25))
+        npid = int(rng.integers(3, 40))
+
+        def lines(n):
+            a = rng.uniform(0, 300, (n, 2)).astype(np.float32)
+            d = rng.uniform(-60, 60, (n, 2)).astype(np.float32)
+            return np.concatenate([a, a + d], 1).astype(np.float32)
+
+        def pols(n):
+            return [{int(p): 1.0 for p in rng.choice(npid, size=min(int(rng.integers(1, 5)), npid), replace=False)} for _ in range(n)]
+        l0, l1 = lines(n0), lines(n1)
+        if n0 and n1 and trial % 3 == 0:      # some new lines lie on top of old ones (LineSimilar true)
+            k = min(n0, n1)
+            l1[:k] = l0[:k] + rng.uniform(-2, 2, (k, 4)).astype(np.float32)
+        p0, p1 = pols(n0), pols(n1)
+        want = ofe.TrackLSD.line_match(l1, l0, p0, p1)
+        got = fe.op_line_match(p0, l0, p1, l1)
+        assert got == {int(k): int(v) for k, v in want.items()}, trial
+        n_matched += len(want)
+    assert n_matched > 100
