@@ -38,10 +38,22 @@ FeStereo::FeStereo(const FeConfig &cfg, const double K_right[4], const double D_
   currid_ = 4 * (uint64_t)cfg.numaruco + 1;   // TrackBase.cpp:34
 }
 
-FeStereo::~FeStereo() {}
+FeStereo::~FeStereo() {
+  if (worker_.joinable()) {
+    cudaSetDevice(device_);
+    cam_[0]->flush_line_batch();   // the tracker thread may be waiting for the line result of an unlaunched batch
+    work_q_.stop();
+    worker_.join();
+  }
+}
+
+// error text of the calling thread; the tracker thread's ends up in the pair's record, the caller's in last_error
+static thread_local std::string t_serr;
+static thread_local bool t_on_worker = false;
 
 int FeStereo::err(int code, const std::string &msg) {
-  last_error = msg;
+  t_serr = msg;
+  if (!t_on_worker) last_error = msg;
   return code;
 }
 
@@ -50,6 +62,9 @@ int FeStereo::init() {
     int rc = cam_[c]->init();
     if (rc) return err(rc, cam_[c]->last_error.empty() ? FeContext::thread_error() : cam_[c]->last_error);
   }
+  const int n = std::max(cfg_.lookahead, 0) + 2;
+  for (int i = 0; i < n; i++) ring_.emplace_back(new Pair());
+  worker_ = std::thread([this] { track_main(); });
   return FE_OK;
 }
 
@@ -67,14 +82,24 @@ int FeStereo::set_num_features(int n) {
 
 int FeStereo::change_feat_id(uint64_t id_old, uint64_t id_new) {   // TrackBase.cpp:267-285 (tracker side)
   if (!queue_.empty()) return err(FE_BAD_ARG, "change_feat_id: collect the pending pairs first");
-  for (int c = 0; c < 2; c++)
+  for (int c = 0; c < 2; c++) {
     for (uint64_t &id : ids_last_[c])
       if (id == id_old) id = id_new;
+    for (uint64_t &id : obs_ids_[c])   // keep get_last_ids in step
+      if (id == id_old) id = id_new;
+  }
   return FE_OK;
 }
 
 int FeStereo::submit(double t, const uint8_t *const image[2], int stride, bool on_device, const uint8_t *const mask[2],
                      int mask_stride, const double vp[6]) {
+  int ri = -1;
+  for (int i = 0; i < (int)ring_.size(); i++)
+    if (ring_[i]->stage.load(std::memory_order_acquire) == 0 && std::find(queue_.begin(), queue_.end(), i) == queue_.end()) {
+      ri = i;
+      break;
+    }
+  if (ri < 0 || (int)queue_.size() > std::max(cfg_.lookahead, 0)) return err(FE_BAD_ARG, "submit: lookahead window full (collect a pair first)");
   int slot[2] = {-1, -1};
   for (int c = 0; c < 2; c++) {
     int rc = cam_[c]->submit_impl(t, image[c], stride, on_device, mask ? mask[c] : nullptr, mask_stride, c == 0 ? vp : nullptr,
@@ -86,8 +111,17 @@ int FeStereo::submit(double t, const uint8_t *const image[2], int stride, bool o
       return err(rc, FeContext::thread_error());
     }
   }
-  queue_.emplace_back(slot[0], slot[1]);
-  queue_t_.push_back(t);
+  Pair &p = *ring_[ri];
+  p.slot[0] = slot[0];
+  p.slot[1] = slot[1];
+  p.t = t;
+  p.rc = FE_OK;
+  p.error.clear();
+  std::memset(&p.info, 0, sizeof(p.info));
+  p.info.timestamp = t;
+  queue_.push_back(ri);
+  p.stage.store(1, std::memory_order_release);
+  work_q_.push(ri);
   return FE_OK;
 }
 
@@ -103,47 +137,83 @@ int FeStereo::feed(double t, const uint8_t *const image[2], int w, int h, int st
   return collect(info);
 }
 
+// Tracker thread: pairs in submission order.  Owns pts_last_ / ids_last_ / currid_ / last_ while pairs are in flight.
+void FeStereo::track_main() {
+  t_on_worker = true;
+  cudaSetDevice(device_);
+  int ri;
+  while (work_q_.pop(&ri)) {
+    Pair &p = *ring_[ri];
+    int rc = collect_impl(p);
+    FeContext &lc = *cam_[0];
+    FrameSlot &L = lc.slots_[p.slot[0]];
+    for (int c = 0; c < 2; c++) {
+      p.obs[c] = pts_last_[c];
+      p.obs_ids[c] = ids_last_[c];
+      p.info.n_point_rows[c] = (int)p.rows[c].size();
+      p.info.n_last_obs[c] = (int)pts_last_[c].size();
+    }
+    // UpdaterCamera.cpp:105-110: the line tracker runs after the point tracker, on the LEFT image, against the left points
+    // the stereo tracker has just produced (TrackLSD.cpp:57-60, :127-129).  Its line path was launched by the caller's
+    // thread (at submit, or by collect() when the batch never filled).
+    if (rc == FE_OK && cfg_.use_lines && L.has_vp) {
+      L.res.obs = pts_last_[0];
+      L.res.obs_ids = ids_last_[0];
+      rc = lc.lsd_feed(L);
+      if (rc) err(rc, FeContext::thread_error());
+      lc.flush_stats(lc.lst_);
+      p.info.n_line_rows = (int)L.res.line_rows.size();
+      p.info.n_lines_detected = L.res.info.n_lines_detected;
+      p.info.n_line_matches = L.res.info.n_line_matches;
+    }
+    for (int c = 0; c < 2; c++) cam_[c]->flush_stats(cam_[c]->kst_);
+    last_[0] = p.slot[0];   // move forward in time whatever happened (:366-378)
+    last_[1] = p.slot[1];
+    p.rc = rc;
+    if (rc) p.error = t_serr;
+    p.stage.store(2, std::memory_order_release);
+  }
+}
+
 int FeStereo::collect(FeStereoInfo *info) {
   if (cudaSetDevice(device_) != cudaSuccess) return err(FE_CUDA_ERROR, "cudaSetDevice failed");
   if (queue_.empty()) return err(FE_BAD_ARG, "collect: nothing submitted");
-  FeStereoInfo local;
-  std::memset(&local, 0, sizeof(local));
-  local.timestamp = queue_t_.front();
-  const std::pair<int, int> cur = queue_.front();
-  int rc = collect_impl(&local);
-  // UpdaterCamera.cpp:105-110: the line tracker runs after the point tracker, on the LEFT image, against the left points
-  // the stereo tracker has just produced (TrackLSD.cpp:57-60, :127-129)
-  {
-    FeContext &lc = *cam_[0];
-    FrameSlot &L = lc.slots_[cur.first];
-    L.res.obs = pts_last_[0];
-    L.res.obs_ids = ids_last_[0];
-    lc.cur_res_ = &L.res;
-    lc.cur_slot_ = cur.first;
-    if (rc == FE_OK && cfg_.use_lines && L.has_vp) {
-      if (L.line_pending) rc = lc.flush_line_batch();
-      if (rc == FE_OK) rc = lc.lsd_feed(L);
-      if (rc) err(rc, FeContext::thread_error());
-      lc.flush_stats(lc.lst_);
-      local.n_line_rows = (int)L.res.line_rows.size();
-      local.n_lines_detected = L.res.info.n_lines_detected;
-      local.n_line_matches = L.res.info.n_line_matches;
+  const int ri = queue_.front();
+  Pair &p = *ring_[ri];
+  FeContext &lc = *cam_[0];
+  FrameSlot &L = lc.slots_[p.slot[0]];
+  if (L.line_pending) {   // its line batch never filled up: launch what is there
+    int rc = lc.flush_line_batch();
+    if (rc) return err(rc, FeContext::thread_error());
+  }
+  for (unsigned spins = 0; p.stage.load(std::memory_order_acquire) != 2; spins++) {
+    if (spins < 256) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    } else {
+      std::this_thread::yield();
     }
   }
-  // move forward in time whatever happened (:366-378): the previous pair's slots become free
   queue_.pop_front();
-  queue_t_.pop_front();
-  for (int c = 0; c < 2; c++)
-    if (last_[c] >= 0) cam_[c]->slots_[last_[c]].busy = false;
-  last_[0] = cur.first;
-  last_[1] = cur.second;
   for (int c = 0; c < 2; c++) {
-    local.n_point_rows[c] = (int)rows_[c].size();
-    local.n_last_obs[c] = (int)pts_last_[c].size();
-    cam_[c]->flush_stats(cam_[c]->kst_);
+    rows_[c].swap(p.rows[c]);
+    obs_[c].swap(p.obs[c]);
+    obs_ids_[c].swap(p.obs_ids[c]);
+  }
+  lc.cur_res_ = &L.res;   // line rows / line points of the left image (plviwo_fe_stereo_get_line_rows)
+  lc.cur_slot_ = p.slot[0];
+  // the previous collected pair's slots become free: its pyramids are no longer the tracker's "last" pair (the tracker
+  // finished THIS pair, which was the last one to read them)
+  for (int c = 0; c < 2; c++) {
+    if (released_[c] >= 0) cam_[c]->slots_[released_[c]].busy = false;
+    released_[c] = p.slot[c];
   }
   st_.frames++;
-  if (info) *info = local;
+  if (info) *info = p.info;
+  const int rc = p.rc;
+  if (rc) last_error = p.error;
+  p.stage.store(0, std::memory_order_release);
   return rc;
 }
 
@@ -298,11 +368,12 @@ int FeStereo::detection_stereo(FrameSlot &L, FrameSlot &R, std::vector<Pt> &pts0
 }
 
 // ------------------------------------------------------------------------------------------------ feed_stereo
-int FeStereo::collect_impl(FeStereoInfo *info) {
-  const std::pair<int, int> cur = queue_.front();
-  FrameSlot &L = cam_[0]->slots_[cur.first], &R = cam_[1]->slots_[cur.second];
-  rows_[0].clear();
-  rows_[1].clear();
+int FeStereo::collect_impl(Pair &pair) {
+  FeStereoInfo *info = &pair.info;
+  FrameSlot &L = cam_[0]->slots_[pair.slot[0]], &R = cam_[1]->slots_[pair.slot[1]];
+  std::vector<FePointRow> *rows_out = pair.rows;
+  rows_out[0].clear();
+  rows_out[1].clear();
   // every tracking stream may read either image of the pair (the left->right launch runs on the left stream)
   for (int c = 0; c < 2; c++) {
     ST_CUDA(cudaStreamWaitEvent(cam_[c]->s_pt_, L.ev_pyr, 0));
@@ -353,7 +424,7 @@ int FeStereo::collect_impl(FeStereoInfo *info) {
     r.v = p.y;
     r.un = m.p1n[i].x;
     r.vn = m.p1n[i].y;
-    rows_[cam].push_back(r);
+    rows_out[cam].push_back(r);
   };
   std::vector<std::pair<size_t, size_t>> row_src[2];   // (index into the matching call) per good point, for the rows
   for (size_t i = 0; i < ml.pts1.size(); i++) {   // :298-334
@@ -457,7 +528,10 @@ int FeStereo::set_state(const void *buf, size_t n_bytes) {
     p += hd.size[c];
     pts_last_[c] = x.pts_last_;
     ids_last_[c] = x.ids_last_;
+    obs_[c] = x.pts_last_;
+    obs_ids_[c] = x.ids_last_;
     last_[c] = x.klt_last_slot_;
+    released_[c] = x.klt_last_slot_;   // the slot the image was loaded into is busy until the next pair has been collected
     x.last_slot_ = -1;   // slot ownership is ours: the context must not keep its own "last collected" exclusion
     x.flush_stats(x.mst_);
   }

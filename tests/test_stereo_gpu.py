@@ -81,7 +81,7 @@ def _run(fe, synth, n_frames, kw, seed=1000, width=1280, height=560, teacher_for
     g.close()
     duv, dun = np.array(duv), np.array(dun)
     s.update(max_duv=float(duv.max()), duv_p99=float(np.percentile(duv, 99)), n_duv_gt_005=int((duv > 0.05).sum()),
-             max_dun=float(dun.max()))
+             max_dun=float(dun.max()), dun_p99=float(np.percentile(dun, 99)))
     print(s)
     return s
 
@@ -92,6 +92,7 @@ def _assert_parity(s):
     assert s["order_equal"] >= 2 * s["frames_equal"], s       # and where the sets agree the row order is the reference's
     assert s["duv_p99"] < 0.01, s
     assert s["n_duv_gt_005"] <= max(1, int(0.001 * s["rows"])), s
+    assert s["dun_p99"] < 0.01 / 500.0, s                    # normalised coordinates: the same bar through the focal length
 
 
 @pytest.mark.parametrize("kw,seed", [(CFG1, 1000), (CFG2, 1001)])
@@ -164,6 +165,34 @@ def test_stereo_bad_arguments_and_setters(fe, synth):
             assert np.array_equal(g2.get_last_ids()[cam], np.array(o.ids_last[cam], np.uint64)), (t, cam)
     g.close()
     g2.close()
+
+
+def test_stereo_online_calibration_update(fe, synth):
+    """Intrinsics are refined online (StateHelper.cpp:166): set_calib per camera between pairs changes the normalised
+    coordinates of the rows and the RANSAC threshold from the next pair on, exactly as in the oracle."""
+    seq = synth.SynthSequence(seed=1018, width=640, height=280, n_frames=6, hard=False)
+    kw = dict(CFG1, num_features=120)
+    o = ost.TrackKLTStereo(ofe.FeConfig(K=seq.K, D=seq.D, **kw))
+    g = fe.StereoFrontEnd(fe.default_config(width=640, height=280, K=seq.K, D=seq.D, use_lines=0, **kw))
+    z = np.zeros((280, 640), np.uint8)
+    worst = 0.0
+    for t in range(6):
+        if t in (2, 4):
+            for cam in (0, 1):
+                K = tuple(v * (1.0 + 0.01 * (t + cam)) for v in seq.K)
+                D = tuple(v * (1.0 - 0.05 * (t + cam)) for v in seq.D)
+                o.set_calib(cam, K, D)
+                g.set_calib(cam, K, D)
+        ro = o.feed_new_camera(seq.timestamp(t), seq.frame(t, 0), seq.frame(t, 1), z, z)
+        g.feed_new_camera(seq.timestamp(t), seq.frame(t, 0), seq.frame(t, 1))
+        for cam in (0, 1):
+            rows = g.point_rows(cam)
+            assert [int(v) for v in rows["id"]] == [r.id for r in ro[cam]], (t, cam)
+            if len(rows):
+                un_o = np.array([[r.un, r.vn] for r in ro[cam]], np.float32)
+                worst = max(worst, float(np.abs(np.stack([rows["un"], rows["vn"]], 1) - un_o).max()))
+    g.close()
+    assert worst < 1e-4, worst
 
 
 def test_stereo_free_running(fe, synth):
