@@ -269,6 +269,8 @@ int FeContext::init() {
   if (!external_) {
     klt_thread_ = std::thread([this] { klt_main(); });
     line_thread_ = std::thread([this] { line_main(); });
+  } else if (cfg_.use_lines) {
+    line_thread_ = std::thread([this] { line_main(); });   // the owner queues frames whose points are known (line_q_)
   }
 
   max_pts_ = std::max(4096, 8 * cfg_.num_features) + 4096 * (cfg_.line_samples > 0 ? 8 : 0);

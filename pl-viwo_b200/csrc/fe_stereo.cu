@@ -99,7 +99,7 @@ int FeStereo::submit(double t, const uint8_t *const image[2], int stride, bool o
       ri = i;
       break;
     }
-  if (ri < 0 || (int)queue_.size() > std::max(cfg_.lookahead, 0)) return err(FE_BAD_ARG, "submit: lookahead window full (collect a pair first)");
+  if (ri < 0) return err(FE_BAD_ARG, "submit: lookahead window full (collect a pair first)");
   int slot[2] = {-1, -1};
   for (int c = 0; c < 2; c++) {
     int rc = cam_[c]->submit_impl(t, image[c], stride, on_device, mask ? mask[c] : nullptr, mask_stride, c == 0 ? vp : nullptr,
@@ -154,17 +154,16 @@ void FeStereo::track_main() {
       p.info.n_last_obs[c] = (int)pts_last_[c].size();
     }
     // UpdaterCamera.cpp:105-110: the line tracker runs after the point tracker, on the LEFT image, against the left points
-    // the stereo tracker has just produced (TrackLSD.cpp:57-60, :127-129).  Its line path was launched by the caller's
-    // thread (at submit, or by collect() when the batch never filled).
+    // the stereo tracker has just produced (TrackLSD.cpp:57-60, :127-129): hand the frame to the left context's line
+    // thread (the association of pair t overlaps the tracking of pair t + 1).  Its line path was launched by the
+    // caller's thread (at submit, or by collect() when the batch never filled).
+    p.lines_queued = false;
     if (rc == FE_OK && cfg_.use_lines && L.has_vp) {
       L.res.obs = pts_last_[0];
       L.res.obs_ids = ids_last_[0];
-      rc = lc.lsd_feed(L);
-      if (rc) err(rc, FeContext::thread_error());
-      lc.flush_stats(lc.lst_);
-      p.info.n_line_rows = (int)L.res.line_rows.size();
-      p.info.n_lines_detected = L.res.info.n_lines_detected;
-      p.info.n_line_matches = L.res.info.n_line_matches;
+      L.res.rc = FE_OK;
+      p.lines_queued = true;
+      lc.line_q_.push(p.slot[0]);
     }
     for (int c = 0; c < 2; c++) cam_[c]->flush_stats(cam_[c]->kst_);
     last_[0] = p.slot[0];   // move forward in time whatever happened (:366-378)
@@ -193,6 +192,19 @@ int FeStereo::collect(FeStereoInfo *info) {
 #endif
     } else {
       std::this_thread::yield();
+    }
+  }
+  if (p.lines_queued) {   // ... and for the line thread
+    for (unsigned spins = 0; L.stage.load(std::memory_order_acquire) != 3; spins++) {
+      if (spins >= 256) std::this_thread::yield();
+    }
+    L.stage.store(0, std::memory_order_relaxed);
+    p.info.n_line_rows = (int)L.res.line_rows.size();
+    p.info.n_lines_detected = L.res.info.n_lines_detected;
+    p.info.n_line_matches = L.res.info.n_line_matches;
+    if (L.res.rc && p.rc == FE_OK) {
+      p.rc = L.res.rc;
+      p.error = L.res.error;
     }
   }
   queue_.pop_front();

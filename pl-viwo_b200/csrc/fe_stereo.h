@@ -60,7 +60,8 @@ class FeStereo {
     std::vector<uint64_t> obs_ids[2];
     int rc = FE_OK;
     std::string error;
-    std::atomic<int> stage{0};           // 0 free, 1 submitted, 2 tracked (results complete)
+    bool lines_queued = false;           // the left frame went to the line thread (its slot's stage reaches 3 when done)
+    std::atomic<int> stage{0};           // 0 free, 1 submitted, 2 tracked (point results complete)
   };
   int err(int code, const std::string &msg);
   void track_main();
