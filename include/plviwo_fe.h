@@ -136,7 +136,8 @@ typedef struct FeStageTimes {
   uint64_t h2d_bytes, d2h_bytes;   /* bytes moved by the handle's own cudaMemcpyAsync calls */
   double host_ms[16];              /* host wall time: [0] submit, [1] detection, [2] matching, [3] ransac, [4] lines,
                                       [5] collect, [6] line wait, [7] candidate-table wait, [8] speculative LK launch,
-                                      [9] result assembly, [12] LK launch, [13] LK wait */
+                                      [9] result assembly, [10] AssignPointToLines, [11] speculative launch, [12] LK launch,
+                                      [13] LK wait, [14] LineMatch, [15] line rows */
 } FeStageTimes;
 
 /* ---- lifetime ----------------------------------------------------------------------------------------- */

@@ -1589,9 +1589,9 @@ int FeContext::lsd_feed(FrameSlot &cur) {
   const int npt = (int)points.size();
   std::vector<float> &spx = sc_px_, &spy = sc_py_;
   std::vector<uint8_t> &pass = sc_pass_;
-  spx.resize(npt);
-  spy.resize(npt);
-  pass.resize(npt + 8);
+  spx.assign((size_t)npt + 8, 0.f);   // padded to whole groups of 8 points (line_candidates reads them)
+  spy.assign((size_t)npt + 8, 0.f);
+  pass.assign((size_t)npt / 8 + 2, 0);   // one bit per point
   pol_new.reserve(64);
   positions.reserve(64);
   filt_lines.reserve(64);
@@ -1600,6 +1600,7 @@ int FeContext::lsd_feed(FrameSlot &cur) {
     spx[j] = points[j].x;
     spy[j] = points[j].y;
   }
+  HostTimer *t_assign = new HostTimer(&lst_.host_ms[10]);
   for (size_t i = 0; i < lines_new.size(); i++) {
     const float4 &l = lines_new[i];
     float lx1 = l.x, lx2 = l.y, ly1 = l.z, ly2 = l.w;  // index mix-up reproduced (:754-757)
@@ -1613,7 +1614,9 @@ int FeContext::lsd_feed(FrameSlot &cur) {
     std::vector<Pt> feats;
     bool find_point = false;
     for (int j = 0; j < npt; j++) {
-      if (!pass[j]) continue;
+      const unsigned grp = pass[j >> 3];
+      if (grp == 0) { j |= 7; continue; }
+      if (!((grp >> (j & 7)) & 1u)) continue;
       float dist = point_line_distance(l, spx[j], spy[j]);
       if (dist > 5) continue;
       pol[(int)pids[j]] = dist;
@@ -1627,6 +1630,7 @@ int FeContext::lsd_feed(FrameSlot &cur) {
       positions.push_back(feats);
     }
   }
+  delete t_assign;
   if (lines_last_.empty()) {  // first frame / lost (:95-115): no database rows
     lines_last_ = filt_lines;
     line_ids_last_ = filt_ids;
@@ -1635,7 +1639,11 @@ int FeContext::lsd_feed(FrameSlot &cur) {
   }
   // LineMatch (:368-407)
   std::map<int, int> matches;
-  line_match_host(pol_last_, pol_new, filt_lines, lines_last_, matches, sc_inv_, sc_shared_, sc_touched_);
+  {
+    HostTimer tm(&lst_.host_ms[14]);
+    line_match_host(pol_last_, pol_new, filt_lines, lines_last_, matches, sc_inv_, sc_shared_, sc_touched_);
+  }
+  HostTimer t_rows(&lst_.host_ms[15]);
   info->n_line_matches = (int)matches.size();
   std::vector<uint64_t> good_ids(filt_lines.size());
   for (size_t i = 0; i < filt_lines.size(); i++) {  // :146-158

@@ -1,28 +1,69 @@
 // Host-side inner loops of the line tracker that are worth vectorising (compiled by g++ only).
 #include <cstddef>
 #include <cstdint>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 namespace plviwo {
 
 // AssignPointToLines (TrackLSD.cpp:770-781), candidate test for ONE line against all points, structure-of-arrays:
-//   pass[j] = inside the (mis-indexed) bounding box of :775  AND  not farther than 6 px from the supporting line.
+//   bit j = inside the (mis-indexed) bounding box of :775  AND  not farther than 6 px from the supporting line.
 // The second test is a conservative pre-filter (a point more than 6 px from the infinite line is more than 5 px from
 // the segment whatever branch PointLineDistance takes); survivors go through the exact function.  Comparing the
 // float coordinate with a double that was converted from a float is the same as comparing the two floats.
-#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
-__attribute__((target_clones("avx2", "default")))
-#endif
-int line_candidates(const float *px, const float *py, int n, float min_lx, float max_lx, float min_ly, float max_ly, float pa,
-                    float pb, float pc, float plen2, uint8_t *pass) {
+// Result: one bit per point (bit j & 7 of bits[j >> 3]); returns non-zero if any point passed.  px / py / bits are padded
+// to a multiple of 8 points by the caller.
+static int line_candidates_scalar(const float *px, const float *py, int n, float min_lx, float max_lx, float min_ly, float max_ly,
+                                  float pa, float pb, float pc, float plen2, uint8_t *bits) {
   int any = 0;
-  for (int j = 0; j < n; j++) {
-    const float x = px[j], y = py[j];
-    const float t = pa * x + pb * y + pc;
-    const int ok = (!(x < min_lx) & !(x > max_lx) & !(y < min_ly) & !(y > max_ly)) & !(t * t > plen2);
-    pass[j] = (uint8_t)ok;
-    any |= ok;
+  for (int j0 = 0; j0 < n; j0 += 8) {
+    unsigned m = 0;
+    for (int k = 0; k < 8 && j0 + k < n; k++) {
+      const float x = px[j0 + k], y = py[j0 + k];
+      const float t = pa * x + pb * y + pc;
+      const int ok = (!(x < min_lx) & !(x > max_lx) & !(y < min_ly) & !(y > max_ly)) & !(t * t > plen2);
+      m |= (unsigned)ok << k;
+    }
+    bits[j0 >> 3] = (uint8_t)m;
+    any |= (int)m;
   }
   return any;
+}
+
+#if defined(__x86_64__) && defined(__GNUC__)
+// 8 points per iteration; multiplications and additions stay separate instructions (no FMA), as in the scalar form
+__attribute__((target("avx2"))) static int line_candidates_avx2(const float *px, const float *py, int n, float min_lx,
+                                                               float max_lx, float min_ly, float max_ly, float pa, float pb,
+                                                               float pc, float plen2, uint8_t *bits) {
+  const __m256 vminx = _mm256_set1_ps(min_lx), vmaxx = _mm256_set1_ps(max_lx), vminy = _mm256_set1_ps(min_ly),
+               vmaxy = _mm256_set1_ps(max_ly), va = _mm256_set1_ps(pa), vb = _mm256_set1_ps(pb), vc = _mm256_set1_ps(pc),
+               vl = _mm256_set1_ps(plen2);
+  int any = 0;
+  const int n8 = (n + 7) & ~7;   // the arrays are padded; padding points are masked out below
+  for (int j = 0; j < n8; j += 8) {
+    const __m256 x = _mm256_loadu_ps(px + j), y = _mm256_loadu_ps(py + j);
+    const __m256 t = _mm256_add_ps(_mm256_add_ps(_mm256_mul_ps(va, x), _mm256_mul_ps(vb, y)), vc);
+    // reject = x < min | x > max | y < min | y > max | t * t > plen2   (ordered comparisons: false on NaN, as the scalar form)
+    __m256 rej = _mm256_or_ps(_mm256_cmp_ps(x, vminx, _CMP_LT_OQ), _mm256_cmp_ps(x, vmaxx, _CMP_GT_OQ));
+    rej = _mm256_or_ps(rej, _mm256_or_ps(_mm256_cmp_ps(y, vminy, _CMP_LT_OQ), _mm256_cmp_ps(y, vmaxy, _CMP_GT_OQ)));
+    rej = _mm256_or_ps(rej, _mm256_cmp_ps(_mm256_mul_ps(t, t), vl, _CMP_GT_OQ));
+    unsigned m = ~(unsigned)_mm256_movemask_ps(rej) & 0xffu;
+    if (j + 8 > n) m &= (1u << (n - j)) - 1u;
+    bits[j >> 3] = (uint8_t)m;
+    any |= (int)m;
+  }
+  return any;
+}
+#endif
+
+int line_candidates(const float *px, const float *py, int n, float min_lx, float max_lx, float min_ly, float max_ly, float pa,
+                    float pb, float pc, float plen2, uint8_t *bits) {
+#if defined(__x86_64__) && defined(__GNUC__)
+  static const bool have_avx2 = __builtin_cpu_supports("avx2");
+  if (have_avx2) return line_candidates_avx2(px, py, n, min_lx, max_lx, min_ly, max_ly, pa, pb, pc, plen2, bits);
+#endif
+  return line_candidates_scalar(px, py, n, min_lx, max_lx, min_ly, max_ly, pa, pb, pc, plen2, bits);
 }
 
 // cv::pyrDown of an 8-bit image to (dw, dh) on the host: separable [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8.
