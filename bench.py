@@ -474,9 +474,11 @@ def main():
     ab = algorithmic_bytes(max(lk_pts, 1.0))
     # single kernels only: "fld" is the sum of fld_ccl + fld_walk + fld_seg, pyr_rest / fld_ccl / fld_seg are 3-4 launches
     stage_ms = {k: v for k, v in st["ms"].items() if k not in ("h2d", "fld") and st["launches"][k]}
+    # line-path kernels are launched once per BATCH of frames (grid.y = frame): a launch carries frames / launches frames
+    fpl = {k: (nfr / max(st["launches"][k], 1) if k in ("canny", "fld_ccl", "fld_walk", "fld_seg") else 1.0) for k in stage_ms}
     dom = max(stage_ms, key=lambda k: stage_ms[k]) if stage_ms else "lk"
     avg_ms = stage_ms.get(dom, 0.0) / max(st["launches"][dom], 1)
-    achieved = (ab[dom] / (avg_ms * 1e-3)) / 1e9 if avg_ms > 0 else 0.0
+    achieved = (ab[dom] * fpl.get(dom, 1.0) / (avg_ms * 1e-3)) / 1e9 if avg_ms > 0 else 0.0
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full summary
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["kernels"].get(KERNEL_OF_STAGE.get(dom, dom))
@@ -485,14 +487,16 @@ def main():
     per_kernel = {}
     for k, v in stage_ms.items():
         ms_k = v / max(st["launches"][k], 1)
-        per_kernel[k] = {"avg_ms": ms_k, "algorithmic_bytes": ab.get(k, 0),
-                         "GBps": (ab.get(k, 0) / (ms_k * 1e-3)) / 1e9 if ms_k > 0 else 0.0}
+        per_kernel[k] = {"avg_ms": ms_k, "frames_per_launch": round(fpl[k], 2), "algorithmic_bytes": ab.get(k, 0) * fpl[k],
+                         "GBps": (ab.get(k, 0) * fpl[k] / (ms_k * 1e-3)) / 1e9 if ms_k > 0 else 0.0}
         per_kernel[k]["frac"] = per_kernel[k]["GBps"] / peak if peak else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ab[dom], "avg_launch_ms": avg_ms,
-                "note": "the dominant kernel is the sequential chain walk of the line detector: latency bound, not HBM "
-                        "bound (DESIGN.md 'Kernels'); per_kernel lists every kernel of the frame",
+                "algorithmic_bytes_per_launch": ab[dom] * fpl.get(dom, 1.0), "frames_per_launch": round(fpl.get(dom, 1.0), 2),
+                "avg_launch_ms": avg_ms,
+                "note": "the dominant kernel is the sequential chain walk of the line detector (one launch per batch of "
+                        "frames): latency bound, not HBM bound (DESIGN.md 'Kernels'); per_kernel lists every kernel of the "
+                        "frame, stage_ms_per_frame their cost per frame",
                 "per_kernel": per_kernel,
                 "stage_ms_per_frame": {k: v / nfr for k, v in st["ms"].items()},
                 "host_ms_per_frame": {k: v / max(res["stage"]["frames"], 1) for k, v in res["stage"]["host_ms"].items()

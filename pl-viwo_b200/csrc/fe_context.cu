@@ -576,7 +576,8 @@ int FeContext::enqueue_frame_independent(FrameSlot &s) {
   bool batched = false;
   if (lines) {
     s.seq_lines++;
-    if (line_batch_ > 1 && !timing && !taps) {   // joins the batch; launched when it is full (or when collect needs it)
+    s.line_timed = 0;
+    if (line_batch_ > 1 && !taps) {   // joins the batch; launched when it is full (or when collect needs it)
       batched = true;
       s.line_pending = true;
       pending_lines_.push_back(s.index);
@@ -591,6 +592,7 @@ int FeContext::enqueue_frame_independent(FrameSlot &s) {
       } else {
         int rc = record_line_path(s, s.s_line);
         if (rc) return rc;
+        if (timing) s.line_timed = 1;
       }
     }
   }
@@ -617,8 +619,16 @@ int FeContext::flush_line_batch() {
     b.half[k] = s.half;
     b.f[k] = s.fld;
   }
+  FrameSlot &first = slots_[pending_lines_[0]];
+  const bool timed = timing;
+  if (timed) cudaEventRecord(first.ev_t[5], st);
   launch_canny_batch(b, cfg_.canny_th1, cfg_.canny_th2, st);
-  launch_fld_batch(b, cfg_.fld_length_threshold, cfg_.fld_distance_threshold, st);
+  if (timed) cudaEventRecord(first.ev_t[6], st);
+  launch_fld_batch(b, cfg_.fld_length_threshold, cfg_.fld_distance_threshold, st, timed ? &first.ev_t[8] : nullptr);
+  if (timed) {
+    cudaEventRecord(first.ev_t[7], st);
+    first.line_timed = n;
+  }
   for (int k = 0; k < n; k++) {
     FrameSlot &s = slots_[pending_lines_[k]];
     FE_CUDA(cudaMemcpyAsync(s.h_fld_counts, s.fld.counters + 3, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -930,13 +940,16 @@ int FeContext::collect_impl(FeFrameInfo *info) {
     if (cfg_.histogram_method != FE_HIST_NONE) acc_time(mst_, FE_STAGE_HIST, cur.ev_t[1], cur.ev_t[2]);
     acc_time(mst_, FE_STAGE_EQ_PYR, cur.ev_t[2], cur.ev_t[3]);
     acc_time(mst_, FE_STAGE_PYR_REST, cur.ev_t[3], cur.ev_t[4]);
-    if (cfg_.use_lines && cur.has_vp) {
-      acc_time(mst_, FE_STAGE_CANNY, cur.ev_t[5], cur.ev_t[6]);
-      acc_time(mst_, FE_STAGE_FLD, cur.ev_t[6], cur.ev_t[7]);
-      acc_time(mst_, FE_STAGE_FLD_CCL, cur.ev_t[6], cur.ev_t[8]);
-      acc_time(mst_, FE_STAGE_FLD_WALK, cur.ev_t[8], cur.ev_t[9]);
-      acc_time(mst_, FE_STAGE_FLD_SEG, cur.ev_t[9], cur.ev_t[7]);
-    }
+  }
+  // line stages: one set of events per LAUNCH — a batched line path is timed on the first frame of its batch, so
+  // launches[] counts batches and ms[] / launches[] is the duration of a launch that carries line_timed frames
+  if (cur.line_timed > 0) {
+    acc_time(mst_, FE_STAGE_CANNY, cur.ev_t[5], cur.ev_t[6]);
+    acc_time(mst_, FE_STAGE_FLD, cur.ev_t[6], cur.ev_t[7]);
+    acc_time(mst_, FE_STAGE_FLD_CCL, cur.ev_t[6], cur.ev_t[8]);
+    acc_time(mst_, FE_STAGE_FLD_WALK, cur.ev_t[8], cur.ev_t[9]);
+    acc_time(mst_, FE_STAGE_FLD_SEG, cur.ev_t[9], cur.ev_t[7]);
+    cur.line_timed = 0;
   }
   mst_.frames++;
   res.info.n_point_rows = (int)res.point_rows.size();

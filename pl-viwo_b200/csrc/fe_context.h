@@ -88,6 +88,7 @@ struct FrameSlot {
   double vp[6] = {0, 0, 0, 0, 0, 0};
   bool has_vp = false;
   bool busy = false;
+  int line_timed = 0;            // > 0: ev_t[5..9] hold the stage events of a line-path launch that carried this many frames
   bool line_pending = false;     // the frame waits in the handle's line batch (its line path is not launched yet)
   double K[4] = {0, 0, 0, 0}, D[4] = {0, 0, 0, 0};   // calibration in force when the frame was submitted
   FrameResult res;
