@@ -300,6 +300,11 @@ int plviwo_op_fld(int device, const uint8_t *img, int w, int h, int length_thres
  * fast, canny (mean per launch).  Used by bench.py to report what the kernels reach when a launch carries enough
  * bytes (a batch of frames' worth) instead of one 0.7 MB frame. */
 int plviwo_op_image_kernels_time(int device, int w, int h, int iters, float ms[4]);
+/* TrackLSD::AssignPointToLines (TrackLSD.cpp:744-792): kept[i] = 1 if line i (x1 y1 x2 y2) keeps at least one of the points;
+ * the k-th kept line's (point id, distance) pairs, in ascending point id, are entries off[k] .. off[k + 1] of pid_out /
+ * dist_out (off has n_lines + 1 entries).  Host-side step, no GPU needed. */
+int plviwo_op_assign_points(int n_lines, const float *lines, int n_pts, const float *pts /* 2 per point */, const uint64_t *pids,
+                            int32_t *kept, int32_t *off, int32_t *pid_out, float *dist_out, int cap, int *n_out);
 /* TrackLSD::LineMatch (TrackLSD.cpp:368-407) on CSR inputs: line j of the last frame holds point ids
  * last_pids[last_off[j] .. last_off[j + 1]), lines are x1 y1 x2 y2; match_out[i] = index of the last-frame line whose id new
  * line i inherits, or -1.  Host-side step, no GPU needed. */

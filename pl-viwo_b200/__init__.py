@@ -106,6 +106,7 @@ EXPORTS = [
     "plviwo_fe_stereo_collect", "plviwo_fe_stereo_get_point_rows", "plviwo_fe_stereo_get_last_obs", "plviwo_fe_stereo_get_state",
     "plviwo_fe_stereo_set_state", "plviwo_fe_stereo_get_stage_times", "plviwo_fe_stereo_get_line_rows",
     "plviwo_fe_stereo_get_line_points", "plviwo_fe_stereo_classify_lines", "plviwo_op_line_match",
+    "plviwo_op_assign_points",
 ]
 
 
@@ -834,6 +835,27 @@ def op_image_kernels_time(w: int, h: int, iters: int = 10, device: int = 0) -> D
     ms = (C.c_float * 4)()
     _check(lib().plviwo_op_image_kernels_time(device, w, h, iters, ms))
     return {"hist": ms[0], "eq_pyr1": ms[1], "fast": ms[2], "canny": ms[3]}
+
+
+def op_assign_points(lines, points, pids):
+    """TrackLSD::AssignPointToLines through the library's host implementation: returns (kept line indices,
+    [{point id: distance}] per kept line)."""
+    ln = np.ascontiguousarray(lines, np.float32).reshape(-1, 4)
+    pt = np.ascontiguousarray(points, np.float32).reshape(-1, 2)
+    pid = np.ascontiguousarray(pids, np.uint64).reshape(-1)
+    kept = np.zeros(len(ln), np.int32)
+    off = np.zeros(len(ln) + 1, np.int32)
+    cap = max(len(ln) * max(len(pt), 1), 1)
+    po = np.zeros(cap, np.int32)
+    do = np.zeros(cap, np.float32)
+    n = C.c_int(0)
+    L = lib()
+    L.plviwo_op_assign_points.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    _check(L.plviwo_op_assign_points(len(ln), ln.ctypes.data, len(pt), pt.ctypes.data, pid.ctypes.data, kept.ctypes.data,
+                                     off.ctypes.data, po.ctypes.data, do.ctypes.data, cap, C.byref(n)))
+    idx = np.nonzero(kept)[0]
+    return idx, [{int(po[k]): float(do[k]) for k in range(off[i], off[i + 1])} for i in range(len(idx))]
 
 
 def op_line_match(pol_last, lines_last, pol_new, lines_new) -> Dict[int, int]:

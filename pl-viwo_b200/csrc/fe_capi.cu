@@ -639,6 +639,47 @@ int plviwo_op_ransac_fundamental(const float *p0n, const float *p1n, int n, doub
   API_END
 }
 
+// TrackLSD::AssignPointToLines (host-side step; tests).  kept[i] = 1 if line i keeps at least one point; the points of
+// the kept lines follow in CSR form in (line, ascending point id) order: off[k] .. off[k + 1] for the k-th kept line.
+int plviwo_op_assign_points(int n_lines, const float *lines, int n_pts, const float *pts, const uint64_t *pids, int32_t *kept,
+                            int32_t *off, int32_t *pid_out, float *dist_out, int cap, int *n_out) {
+  API_BEGIN
+  if (n_lines < 0 || n_pts < 0 || !kept || !off || !n_out || (n_lines && !lines) || (n_pts && (!pts || !pids))) return FE_BAD_ARG;
+  std::vector<float4> ln((size_t)n_lines);
+  std::vector<uint64_t> ids((size_t)n_lines);
+  for (int i = 0; i < n_lines; i++) {
+    ln[(size_t)i] = make_float4(lines[4 * i], lines[4 * i + 1], lines[4 * i + 2], lines[4 * i + 3]);
+    ids[(size_t)i] = (uint64_t)i;
+  }
+  std::vector<Pt> p((size_t)n_pts);
+  std::vector<uint64_t> pid(pids, pids + n_pts);
+  for (int j = 0; j < n_pts; j++) p[(size_t)j] = Pt{pts[2 * j], pts[2 * j + 1]};
+  std::vector<std::map<int, double>> pol;
+  std::vector<std::vector<Pt>> positions;
+  std::vector<float4> fl;
+  std::vector<uint64_t> fid;
+  std::vector<float> sx, sy;
+  std::vector<uint8_t> pass;
+  assign_points_to_lines_host(ln, ids, p, pid, pol, positions, fl, fid, sx, sy, pass);
+  for (int i = 0; i < n_lines; i++) kept[i] = 0;
+  int n = 0;
+  off[0] = 0;
+  for (size_t k = 0; k < pol.size(); k++) {
+    kept[fid[k]] = 1;
+    for (auto &kv : pol[k]) {
+      if (n < cap && pid_out && dist_out) {
+        pid_out[n] = kv.first;
+        dist_out[n] = (float)kv.second;
+      }
+      n++;
+    }
+    off[k + 1] = n;
+  }
+  *n_out = n;
+  return n > cap ? FE_OVERFLOW : FE_OK;
+  API_END
+}
+
 // TrackLSD::LineMatch on CSR inputs (host-side step; tests)
 int plviwo_op_line_match(int n_last, const int32_t *last_off, const int32_t *last_pids, const float *last_lines, int n_new,
                          const int32_t *new_off, const int32_t *new_pids, const float *new_lines, int32_t *match_out) {

@@ -1527,6 +1527,61 @@ int line_classification(const float4 &line, const double vp[6]) {  // :318-333
 }
 }  // namespace
 
+// TrackLSD::AssignPointToLines (:744-792): per line the points inside its (mis-indexed, :754-757) bounding box and within
+// 5 px of the SEGMENT; lines without a point are dropped.  The candidate test of one line against all points is
+// vectorised (line_candidates, host_simd.cpp); survivors go through the exact PointLineDistance.
+void assign_points_to_lines_host(const std::vector<float4> &lines_new, const std::vector<uint64_t> &ids_new,
+                                 const std::vector<Pt> &points, const std::vector<uint64_t> &pids,
+                                 std::vector<std::map<int, double>> &pol_new, std::vector<std::vector<Pt>> &positions,
+                                 std::vector<float4> &filt_lines, std::vector<uint64_t> &filt_ids, std::vector<float> &spx,
+                                 std::vector<float> &spy, std::vector<uint8_t> &pass) {
+  const int npt = (int)points.size();
+  spx.assign((size_t)npt + 8, 0.f);   // padded to whole groups of 8 points (line_candidates reads them)
+  spy.assign((size_t)npt + 8, 0.f);
+  pass.assign((size_t)npt / 8 + 2, 0);   // one bit per point
+  pol_new.clear();
+  positions.clear();
+  filt_lines.clear();
+  filt_ids.clear();
+  pol_new.reserve(64);
+  positions.reserve(64);
+  filt_lines.reserve(64);
+  filt_ids.reserve(64);
+  for (int j = 0; j < npt; j++) {
+    spx[j] = points[j].x;
+    spy[j] = points[j].y;
+  }
+  for (size_t i = 0; i < lines_new.size(); i++) {
+    const float4 &l = lines_new[i];
+    float lx1 = l.x, lx2 = l.y, ly1 = l.z, ly2 = l.w;  // index mix-up reproduced (:754-757)
+    float min_lx = lx1, max_lx = lx2, min_ly = ly1, max_ly = ly2;
+    if (lx1 > lx2) std::swap(min_lx, max_lx);
+    if (ly1 > ly2) std::swap(min_ly, max_ly);
+    const float pa = l.w - l.y, pb = l.x - l.z, pc = l.z * l.y - l.x * l.w;
+    const float plen2 = 36.f * (pa * pa + pb * pb);
+    if (!line_candidates(spx.data(), spy.data(), npt, min_lx, max_lx, min_ly, max_ly, pa, pb, pc, plen2, pass.data())) continue;
+    std::map<int, double> pol;
+    std::vector<Pt> feats;
+    bool find_point = false;
+    for (int j = 0; j < npt; j++) {
+      const unsigned grp = pass[j >> 3];
+      if (grp == 0) { j |= 7; continue; }
+      if (!((grp >> (j & 7)) & 1u)) continue;
+      float dist = point_line_distance(l, spx[j], spy[j]);
+      if (dist > 5) continue;
+      pol[(int)pids[j]] = dist;
+      feats.push_back(points[j]);
+      find_point = true;
+    }
+    if (find_point) {
+      pol_new.push_back(pol);
+      filt_lines.push_back(l);
+      filt_ids.push_back(ids_new[i]);
+      positions.push_back(feats);
+    }
+  }
+}
+
 // TrackLSD::LineMatch (:368-407): i over new lines, j over last lines, the LAST satisfying j wins.  The reference walks
 // every (i, j) pair and every point id of line j; a pair can only match if the two lines share a point id — j matches i
 // iff they share >= 2 ids, or >= 1 id and LineSimilar holds (the inner loop stops at the first shared id when the lines
@@ -1599,50 +1654,8 @@ int FeContext::lsd_feed(FrameSlot &cur) {
   std::vector<std::vector<Pt>> positions;
   std::vector<float4> filt_lines;
   std::vector<uint64_t> filt_ids;
-  const int npt = (int)points.size();
-  std::vector<float> &spx = sc_px_, &spy = sc_py_;
-  std::vector<uint8_t> &pass = sc_pass_;
-  spx.assign((size_t)npt + 8, 0.f);   // padded to whole groups of 8 points (line_candidates reads them)
-  spy.assign((size_t)npt + 8, 0.f);
-  pass.assign((size_t)npt / 8 + 2, 0);   // one bit per point
-  pol_new.reserve(64);
-  positions.reserve(64);
-  filt_lines.reserve(64);
-  filt_ids.reserve(64);
-  for (int j = 0; j < npt; j++) {
-    spx[j] = points[j].x;
-    spy[j] = points[j].y;
-  }
   HostTimer *t_assign = new HostTimer(&lst_.host_ms[10]);
-  for (size_t i = 0; i < lines_new.size(); i++) {
-    const float4 &l = lines_new[i];
-    float lx1 = l.x, lx2 = l.y, ly1 = l.z, ly2 = l.w;  // index mix-up reproduced (:754-757)
-    float min_lx = lx1, max_lx = lx2, min_ly = ly1, max_ly = ly2;
-    if (lx1 > lx2) std::swap(min_lx, max_lx);
-    if (ly1 > ly2) std::swap(min_ly, max_ly);
-    const float pa = l.w - l.y, pb = l.x - l.z, pc = l.z * l.y - l.x * l.w;
-    const float plen2 = 36.f * (pa * pa + pb * pb);
-    if (!line_candidates(spx.data(), spy.data(), npt, min_lx, max_lx, min_ly, max_ly, pa, pb, pc, plen2, pass.data())) continue;
-    std::map<int, double> pol;
-    std::vector<Pt> feats;
-    bool find_point = false;
-    for (int j = 0; j < npt; j++) {
-      const unsigned grp = pass[j >> 3];
-      if (grp == 0) { j |= 7; continue; }
-      if (!((grp >> (j & 7)) & 1u)) continue;
-      float dist = point_line_distance(l, spx[j], spy[j]);
-      if (dist > 5) continue;
-      pol[(int)pids[j]] = dist;
-      feats.push_back(points[j]);
-      find_point = true;
-    }
-    if (find_point) {
-      pol_new.push_back(pol);
-      filt_lines.push_back(l);
-      filt_ids.push_back(ids_new[i]);
-      positions.push_back(feats);
-    }
-  }
+  assign_points_to_lines_host(lines_new, ids_new, points, pids, pol_new, positions, filt_lines, filt_ids, sc_px_, sc_py_, sc_pass_);
   delete t_assign;
   if (lines_last_.empty()) {  // first frame / lost (:95-115): no database rows
     lines_last_ = filt_lines;

@@ -26,6 +26,11 @@ struct Pt {
 void pyr_down_host(const uint8_t *src, int sw, int sh, int stride, uint8_t *dst, int dw, int dh);
 int line_candidates(const float *px, const float *py, int n, float min_lx, float max_lx, float min_ly, float max_ly, float pa,
                     float pb, float pc, float plen2, uint8_t *pass);
+void assign_points_to_lines_host(const std::vector<float4> &lines_new, const std::vector<uint64_t> &ids_new,
+                                 const std::vector<Pt> &points, const std::vector<uint64_t> &pids,
+                                 std::vector<std::map<int, double>> &pol_new, std::vector<std::vector<Pt>> &positions,
+                                 std::vector<float4> &filt_lines, std::vector<uint64_t> &filt_ids, std::vector<float> &spx,
+                                 std::vector<float> &spy, std::vector<uint8_t> &pass);
 void line_match_host(const std::vector<std::map<int, double>> &pol_last, const std::vector<std::map<int, double>> &pol_new,
                      const std::vector<float4> &lines_new, const std::vector<float4> &lines_last, std::map<int, int> &matches,
                      std::vector<std::pair<int, int>> &inv, std::vector<int> &shared, std::vector<int> &touched);

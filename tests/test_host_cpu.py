@@ -173,3 +173,32 @@ def test_line_match_inverted_index_equals_reference_loop(fe):
         assert got == {int(k): int(v) for k, v in want.items()}, trial
         n_matched += len(want)
     assert n_matched > 100
+
+
+def test_assign_points_to_lines_equals_oracle(fe):
+    """The library's AssignPointToLines (AVX2 candidate test, one bit per point, exact PointLineDistance on the survivors)
+    against the oracle's restatement of TrackLSD.cpp:744-792 — including the mis-indexed bounding box of :754-757 — on
+    random segments with points scattered on and around them; point counts that are not multiples of 8."""
+    from oracle import frontend as ofe
+    rng = np.random.default_rng(11)
+    n_pairs = 0
+    for trial in range(40):
+        n_lines, n_pts = int(rng.integers(0, 60)), int(rng.integers(0, 333))
+        a = rng.uniform(0, 560, (n_lines, 2)).astype(np.float32)
+        d = rng.uniform(-300, 300, (n_lines, 2)).astype(np.float32)
+        lines = np.concatenate([a, a + d], 1).astype(np.float32)
+        pts = rng.uniform(0, 560, (n_pts, 2)).astype(np.float32)
+        if n_lines and n_pts:      # half of the points sit within a few pixels of some segment
+            k = n_pts // 2
+            li = rng.integers(0, n_lines, k)
+            t = rng.uniform(-0.1, 1.1, (k, 1)).astype(np.float32)
+            pts[:k] = (lines[li, :2] + t * (lines[li, 2:] - lines[li, :2]) + rng.normal(0, 3.0, (k, 2))).astype(np.float32)
+        pids = rng.permutation(100000)[:n_pts].astype(np.uint64)
+        rel, pos, new_lines, new_ids = ofe.TrackLSD.assign_points_to_lines(lines, list(range(n_lines)), pts, [int(p) for p in pids])
+        idx, pol = fe.op_assign_points(lines, pts, pids)
+        assert list(idx) == list(new_ids), trial
+        for got, want in zip(pol, rel):
+            assert list(got.keys()) == [int(k) for k in want.keys()], trial
+            assert np.allclose(list(got.values()), [float(v) for v in want.values()], rtol=0, atol=1e-6), trial
+            n_pairs += len(want)
+    assert n_pairs > 500
