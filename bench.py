@@ -473,10 +473,13 @@ def main():
         lk_pts = res_t["rows"] / max(st["launches"]["lk"], 1)  # lower bound: rows written; LK input is slightly larger
     ab = algorithmic_bytes(max(lk_pts, 1.0))
     # single kernels only: "fld" is the sum of fld_ccl + fld_walk + fld_seg, pyr_rest / fld_ccl / fld_seg are 3-4 launches
-    stage_ms = {k: v for k, v in st["ms"].items() if k not in ("h2d", "fld") and st["launches"][k]}
-    # line-path kernels are launched once per BATCH of frames (grid.y = frame): a launch carries frames / launches frames
-    fpl = {k: (nfr / max(st["launches"][k], 1) if k in ("canny", "fld_ccl", "fld_walk", "fld_seg") else 1.0) for k in stage_ms}
-    dom = max(stage_ms, key=lambda k: stage_ms[k]) if stage_ms else "lk"
+    stage_ms = {k: v for k, v in st["ms"].items() if k not in ("h2d", "fld", "line_frames") and st["launches"][k]}
+    # line-path kernels are launched once per BATCH of frames (grid.y = frame): frames carried / launches per launch
+    LINE_STAGES = ("canny", "fld", "fld_ccl", "fld_walk", "fld_seg")
+    line_frames = st["launches"].get("line_frames", 0)
+    fpl = {k: (line_frames / max(st["launches"][k], 1) if k in LINE_STAGES and line_frames else 1.0) for k in st["ms"]}
+    frames_of = {k: (line_frames if k in LINE_STAGES and line_frames else nfr) for k in st["ms"]}
+    dom = max(stage_ms, key=lambda k: stage_ms[k] / max(frames_of[k], 1)) if stage_ms else "lk"   # largest cost per frame
     avg_ms = stage_ms.get(dom, 0.0) / max(st["launches"][dom], 1)
     achieved = (ab[dom] * fpl.get(dom, 1.0) / (avg_ms * 1e-3)) / 1e9 if avg_ms > 0 else 0.0
     traffic = None
@@ -498,7 +501,7 @@ def main():
                         "frames): latency bound, not HBM bound (DESIGN.md 'Kernels'); per_kernel lists every kernel of the "
                         "frame, stage_ms_per_frame their cost per frame",
                 "per_kernel": per_kernel,
-                "stage_ms_per_frame": {k: v / nfr for k, v in st["ms"].items()},
+                "stage_ms_per_frame": {k: v / max(frames_of[k], 1) for k, v in st["ms"].items() if k != "line_frames"},
                 "host_ms_per_frame": {k: v / max(res["stage"]["frames"], 1) for k, v in res["stage"]["host_ms"].items()
                                       if not k.startswith("unused")},
                 "whole_frame": {"algorithmic_bytes": ab["frame_total"],

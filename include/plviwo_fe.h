@@ -126,7 +126,9 @@ typedef struct FeFrameInfo {
 enum FeStage {
   FE_STAGE_H2D = 0, FE_STAGE_HIST, FE_STAGE_EQ_PYR, FE_STAGE_PYR_REST, FE_STAGE_FAST, FE_STAGE_SUBPIX, FE_STAGE_LK,
   FE_STAGE_CANNY, FE_STAGE_FLD /* whole segment extraction: CCL + WALK + SEG */, FE_STAGE_FLD_CCL, FE_STAGE_FLD_WALK,
-  FE_STAGE_FLD_SEG, FE_STAGE_COUNT
+  FE_STAGE_FLD_SEG, FE_STAGE_COUNT,
+  FE_STAGE_LINE_FRAMES = FE_STAGE_COUNT /* launches[] only: frames carried by the timed line-path launches (a launch of the
+                                           line path carries a batch of frames; ms[] / launches[] of CANNY..FLD_SEG is per launch) */
 };
 typedef struct FeStageTimes {
   double ms[16];

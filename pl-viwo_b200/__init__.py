@@ -25,7 +25,8 @@ HIST_NONE, HIST_HISTOGRAM, HIST_CLAHE = 0, 1, 2
 _STATUS = {0: "FE_OK", 1: "FE_BAD_ARG", 2: "FE_NO_DEVICE", 3: "FE_CUDA_ERROR", 4: "FE_OVERFLOW", 5: "FE_INTERNAL"}
 HOST_STAGES = ["submit", "detection", "matching", "ransac", "lines", "collect", "line_wait", "predet_wait",
                "speculate", "assemble", "line_assign", "spec_launch", "lk_launch", "lk_wait", "line_match", "line_rows"]
-STAGES = ["h2d", "hist", "eq_pyr1", "pyr_rest", "fast", "subpix", "lk", "canny", "fld", "fld_ccl", "fld_walk", "fld_seg"]
+STAGES = ["h2d", "hist", "eq_pyr1", "pyr_rest", "fast", "subpix", "lk", "canny", "fld", "fld_ccl", "fld_walk", "fld_seg",
+          "line_frames"]   # line_frames: launches[] only (frames carried by the timed line-path launches)
 TAP_PYR_LEVEL0, TAP_HALF, TAP_EDGES, TAP_FAST_LAST, TAP_LK_LAST, TAP_SUBPIX_LAST, TAP_FLD_LAST = 0, 32, 33, 34, 35, 36, 37
 
 

@@ -949,6 +949,7 @@ int FeContext::collect_impl(FeFrameInfo *info) {
     acc_time(mst_, FE_STAGE_FLD_CCL, cur.ev_t[6], cur.ev_t[8]);
     acc_time(mst_, FE_STAGE_FLD_WALK, cur.ev_t[8], cur.ev_t[9]);
     acc_time(mst_, FE_STAGE_FLD_SEG, cur.ev_t[9], cur.ev_t[7]);
+    mst_.launches[FE_STAGE_LINE_FRAMES] += (uint64_t)cur.line_timed;
     cur.line_timed = 0;
   }
   mst_.frames++;
