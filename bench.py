@@ -487,6 +487,8 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["kernels"].get(KERNEL_OF_STAGE.get(dom, dom))
     except Exception:
         pass
+    if traffic is not None and fpl.get(dom, 1.0) != 1.0:
+        traffic = traffic * fpl[dom]   # the ncu --set full capture profiles single-frame launches: scaled to the frames a launch carries
     per_kernel = {}
     for k, v in stage_ms.items():
         ms_k = v / max(st["launches"][k], 1)
