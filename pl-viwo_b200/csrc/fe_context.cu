@@ -1537,9 +1537,9 @@ void assign_points_to_lines_host(const std::vector<float4> &lines_new, const std
                                  std::vector<float4> &filt_lines, std::vector<uint64_t> &filt_ids, std::vector<float> &spx,
                                  std::vector<float> &spy, std::vector<uint8_t> &pass) {
   const int npt = (int)points.size();
-  spx.assign((size_t)npt + 8, 0.f);   // padded to whole groups of 8 points (line_candidates reads them)
-  spy.assign((size_t)npt + 8, 0.f);
-  pass.assign((size_t)npt / 8 + 2, 0);   // one bit per point
+  spx.assign((size_t)npt + 16, 0.f);   // padded to whole groups of 16 points (line_candidates reads them)
+  spy.assign((size_t)npt + 16, 0.f);
+  pass.assign((size_t)npt / 8 + 4, 0);   // one bit per point
   pol_new.clear();
   positions.clear();
   filt_lines.clear();
