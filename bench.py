@@ -201,7 +201,38 @@ def parity_against(fe_mod, seq, frames, rows_cpu, kw, dev):
                 duv.append(max(abs(float(a["u"]) - b[1]), abs(float(a["v"]) - b[2])))
     h.close()
     duv = np.array(duv) if duv else np.zeros(1)
-    return {"frames": len(rows_cpu), "frames_ids_identical": eq_frames, "first_frame_with_different_rows": first_div,
+    # the per-frame bar: the GPU tracker is loaded with the oracle's state before every frame (teacher forcing), so each
+    # frame is compared on identical inputs — what tests/test_frontend_gpu.py asserts, here over 40 frames as a number
+    from oracle import frontend as ofe
+    okw = {k: v for k, v in kw.items() if k not in ("width", "height")}
+    o = ofe.FrontEnd(ofe.FeConfig(K=seq.K, D=seq.D, **okw))
+    h = fe_mod.FrontEnd(fe_mod.default_config(K=seq.K, D=seq.D, lookahead=0, **kw), device=dev)
+    W, H = kw["width"], kw["height"]
+    tf_duv, tf_rows, tf_sym, tf_frames_equal = [], 0, 0, 0
+    for t in range(40):
+        if t > 0:
+            k, l = o.klt.get_state(), o.lsd.get_state()
+            h.set_state(fe_mod.pack_state(W, H, k["currid"], k["pts_last"], k["ids_last"], k["img_last"], k["mask_last"], l["currid"],
+                                          l["lines_last"], l["ids_last"], l["pol_last"]))
+        prow, _ = o.feed(seq.timestamp(t), frames[t % n], None, seq.vanishing_points(t % n))
+        h.feed_new_camera(seq.timestamp(t), frames[t % n], None, seq.vanishing_points(t % n), update_db=False)
+        got = h.point_rows()
+        ids_g = {int(i): k2 for k2, i in enumerate(got["id"])}
+        ids_c = {r.id: r for r in prow}
+        d = set(ids_g) ^ set(ids_c)
+        tf_rows += len(ids_c)
+        tf_sym += len(d)
+        tf_frames_equal += int(not d and [r.id for r in prow] == [int(i) for i in got["id"]])
+        for i in set(ids_g) & set(ids_c):
+            a, b = got[ids_g[i]], ids_c[i]
+            tf_duv.append(max(abs(float(a["u"]) - b.u), abs(float(a["v"]) - b.v)))
+    h.close()
+    tf_duv = np.array(tf_duv) if tf_duv else np.zeros(1)
+    teacher = {"frames": 40, "frames_rows_identical_ids_and_order": tf_frames_equal, "rows": tf_rows,
+               "rows_with_flipped_status": tf_sym, "status_agreement": 1.0 - tf_sym / max(tf_rows, 1),
+               "max_duv_px": float(tf_duv.max()), "p99_duv_px": float(np.percentile(tf_duv, 99)),
+               "rows_over_0.05px": int((tf_duv > 0.05).sum())}
+    return {"teacher_forced": teacher, "frames": len(rows_cpu), "frames_ids_identical": eq_frames, "first_frame_with_different_rows": first_div,
             "rows_compared": int(len(duv)), "max_duv_px": float(duv.max()), "p99_duv_px": float(np.percentile(duv, 99)),
             "rows_only_on_one_side_at_divergence": sym,
             "note": "free-running GPU (plviwo_fe_feed) vs the CPU baseline's oracle on the same frames; the teacher-forced "
