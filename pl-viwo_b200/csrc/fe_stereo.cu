@@ -106,7 +106,13 @@ int FeStereo::submit(double t, const uint8_t *const image[2], int stride, bool o
                                   &slot[c]);
     cam_[c]->flush_stats(cam_[c]->mst_);
     if (rc) {
-      if (c == 1 && slot[0] >= 0) cam_[0]->slots_[slot[0]].busy = false;
+      if (c == 1 && slot[0] >= 0) {   // give the left image's slot back (and take it out of an unlaunched line batch)
+        FeContext &lc = *cam_[0];
+        auto &pl = lc.pending_lines_;
+        pl.erase(std::remove(pl.begin(), pl.end(), slot[0]), pl.end());
+        lc.slots_[slot[0]].line_pending = false;
+        lc.slots_[slot[0]].busy = false;
+      }
       if (slot[c] >= 0) cam_[c]->slots_[slot[c]].busy = false;
       return err(rc, FeContext::thread_error());
     }
