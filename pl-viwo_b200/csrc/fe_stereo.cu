@@ -109,8 +109,11 @@ int FeStereo::submit(double t, const uint8_t *const image[2], int stride, bool o
       if (c == 1 && slot[0] >= 0) {   // give the left image's slot back (and take it out of an unlaunched line batch)
         FeContext &lc = *cam_[0];
         auto &pl = lc.pending_lines_;
-        pl.erase(std::remove(pl.begin(), pl.end(), slot[0]), pl.end());
-        lc.slots_[slot[0]].line_pending = false;
+        if (lc.slots_[slot[0]].line_pending) {
+          pl.erase(std::remove(pl.begin(), pl.end(), slot[0]), pl.end());
+          lc.slots_[slot[0]].line_pending = false;
+          lc.slots_[slot[0]].seq_lines--;   // its completion signal will never be queued
+        }
         lc.slots_[slot[0]].busy = false;
       }
       if (slot[c] >= 0) cam_[c]->slots_[slot[c]].busy = false;
