@@ -249,6 +249,35 @@ def test_reset_and_small_counts(fe, synth):
     gpu.close()
 
 
+def test_grider_regrids_itself_when_features_are_fewer_than_cells(fe, synth):
+    """Grider_GRID.h:88-100: with num_features < grid_x * grid_y the grider derives ITS OWN grid (15 features on a 5 x 5
+    grid -> 4 x 4 cells of 320 x 140) while the valid cells still index the caller's 5 x 5 grid; cells whose origin leaves
+    the image are skipped (:117-118), so 16 of the 25 locations are searched, one corner each.  The sequence also walks
+    through the < 10 points all-fail mask and the reset that follows.  Teacher-forced."""
+    seq = synth.SynthSequence(seed=1019, n_frames=12, hard=False)
+    kw = dict(CFG1, num_features=15)
+    oracle = ofe.FrontEnd(ofe.FeConfig(K=seq.K, D=seq.D, use_lines=False, **kw))
+    gpu = fe.FrontEnd(fe.default_config(width=1280, height=560, K=seq.K, D=seq.D, use_lines=0, **kw))
+    searched, resets = [], 0
+    for t in range(12):
+        if t > 0:
+            gpu.set_state(_oracle_state_blob(fe, oracle, 1280, 560))
+        prow_o, _ = oracle.feed(seq.timestamp(t), seq.frame(t))
+        info = gpu.feed_new_camera(seq.timestamp(t), seq.frame(t))
+        det = oracle.klt.trace.get("det", {})
+        if det.get("ran"):
+            searched.append(sum(c is not None for c in det["cells"]))
+            assert info.n_detected == len(det["new_ids"]), t
+        resets += int(info.reset)
+        assert bool(info.reset) == bool(oracle.klt.trace.get("reset")), t
+        assert list(gpu.point_rows()["id"]) == [r.id for r in prow_o], t
+        assert np.array_equal(gpu.get_last_ids(), np.array(oracle.klt.get_last_ids(), np.uint64)), t
+        if len(oracle.klt.pts_last):
+            assert np.abs(gpu.get_last_obs() - oracle.klt.pts_last).max() < 0.05, t
+    gpu.close()
+    assert searched and max(searched) == 16, searched     # 16 of the 25 caller cells exist in the grider's own 4 x 4 grid
+
+
 def test_state_roundtrip_and_pipelined_submit(fe, synth):
     """get_state/set_state round trip, and submit/collect with lookahead gives the same rows as feed()."""
     seq = synth.SynthSequence(seed=1011, n_frames=12)
