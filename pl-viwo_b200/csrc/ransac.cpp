@@ -13,6 +13,8 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -374,7 +376,11 @@ int ransac_fundamental(const float *m1, const float *m2, int count, double thres
     if (max_good > 0) std::memcpy(mask, best.data(), count);
     return max_good;
   }
-  // ---- LMeDSPointSetRegistrator::run (8 <= count < 15)
+  // ---- LMeDSPointSetRegistrator::run (8 <= count < 15).  Mask-exact against the library for count == 14.  For
+  // count <= 13 the median is the (count / 2 + 1)-th smallest error with count / 2 <= 6, i.e. the error of one of the 7
+  // SAMPLE points of the model, which is zero up to rounding (1e-33): the library's choice of the "best" model is then
+  // decided by the rounding noise of its own 7-point solver and cannot be reproduced by any other build of the same
+  // algorithm (tests/test_host_cpu.py documents it); this is a faithful LMedS, not a bit-copy, in that regime.
   {
     const double outlier_ratio = 0.45;
     int niters = ransac_update_num_iters(confidence, outlier_ratio, model_points, max_iters);

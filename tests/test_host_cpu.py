@@ -98,6 +98,34 @@ def test_ransac_host_matches_opencv(fe):
     assert n_in == -1 and not mine.any()
 
 
+def test_ransac_small_counts_lmeds_regime(fe):
+    """cv::findFundamentalMat(FM_RANSAC) silently runs LMedS below 15 points.  With 14 points the median is the 8th
+    smallest error — a point outside the 7-point sample — and the library's mask is reproduced exactly.  With 10..13
+    points the median is the error of one of the model's own sample points (zero up to rounding noise, ~1e-33), so
+    OpenCV's pick among the candidate models is decided by the rounding of its own solver: there the masks are only
+    required to be a valid LMedS answer (at least 7 inliers, and the tracker's >= 10-point precondition of
+    TrackKLT.cpp:848 keeps this regime to 10..13 points)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    thr = 2.0 / 816.9
+    exact14 = 0
+    for trial in range(60):
+        n = 14 if trial < 30 else int(rng.integers(10, 14))
+        X = np.c_[rng.uniform(-3, 3, n), rng.uniform(-2, 2, n), rng.uniform(4, 12, n)]
+        R, _ = cv2.Rodrigues(rng.normal(0, 0.03, 3))
+        X2 = X @ R.T + rng.normal(0, 0.3, 3)
+        p0 = (X[:, :2] / X[:, 2:]).astype(np.float32)
+        p1 = (X2[:, :2] / X2[:, 2:]).astype(np.float32) + rng.normal(0, 0.5 / 800, (n, 2)).astype(np.float32)
+        _F, m = cv2.findFundamentalMat(p0, p1, cv2.FM_RANSAC, thr, 0.999)
+        ref = np.zeros(n, np.uint8) if m is None else m.reshape(-1)
+        mine, n_in = fe.op_ransac_fundamental(p0, p1, thr, 0.999)
+        if n == 14:
+            exact14 += int(np.array_equal(ref, mine))
+        else:
+            assert n_in >= 7 and int(mine.sum()) == n_in, (n, n_in)
+    assert exact14 >= 29, exact14
+
+
 def test_synth_sequence_is_deterministic(synth):
     a = synth.SynthSequence(seed=5, width=320, height=192, n_frames=5)
     b = synth.SynthSequence(seed=5, width=320, height=192, n_frames=5)
