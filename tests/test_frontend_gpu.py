@@ -37,6 +37,8 @@ def _compare_lines(lrows, lpts, lrow_o):
             return False
         if np.abs(a["line"] - b.line).max() > 2e-3:
             return False
+        if np.abs(a["line_n"] - b.line_n).max() > 1e-5:    # undistorted endpoints (2e-3 px / f = 2.4e-6)
+            return False
         p = lpts[a["pt_offset"]:a["pt_offset"] + a["n_pts"]]
         if list(p["pid"]) != list(b.pids):
             return False
