@@ -343,6 +343,20 @@ int ransac_fundamental(const float *m1, const float *m2, int count, double thres
     std::memset(mask, 1, count);
     return count;
   }
+  // A repeated frame: every point tracked onto itself (LK's first step is exactly zero on identical images).  Every
+  // 7-point system is then rank 6 — its null space is the antisymmetric matrices, for which x' F x = 0 holds for EVERY
+  // point — and the library either returns such an F with all points as inliers or trips an internal assertion
+  // (OpenCV 4.13: cv::Exception out of findFundamentalMat, which the reference does not catch).  The useful one of the
+  // two outcomes is returned: all points are inliers.  (With a few moved points among static ones the sampled systems
+  // that contain a moved point have full rank and the loop below finds the static set as inliers by itself.)
+  {
+    bool all_static = true;
+    for (int k = 0; k < 2 * count && all_static; k++) all_static = m1[k] == m2[k];
+    if (all_static) {
+      std::memset(mask, 1, count);
+      return count;
+    }
+  }
   std::vector<float> err(count);
   std::vector<uint8_t> cur(count), best(count, 0);
   float ms1[14], ms2[14];

@@ -126,6 +126,27 @@ def test_ransac_small_counts_lmeds_regime(fe):
     assert exact14 >= 29, exact14
 
 
+def test_ransac_repeated_frame(fe):
+    """A repeated frame (every point tracked exactly onto itself) keeps its tracks: all points are inliers, as in the
+    library's non-asserting outcome; with a few lost points among them the static ones are the inliers.  (OpenCV 4.13
+    throws out of findFundamentalMat on most such inputs, which is why cv2 is not the checker here.)"""
+    rng = np.random.default_rng(4)
+    thr = 2.0 / 816.9
+    for n in (10, 14, 15, 60, 400):
+        p0 = np.c_[rng.uniform(-0.7, 0.7, n), rng.uniform(-0.3, 0.3, n)].astype(np.float32)
+        mask, n_in = fe.op_ransac_fundamental(p0, p0.copy(), thr, 0.999)
+        assert n_in == n and mask.all(), n
+    n = 300
+    p0 = np.c_[rng.uniform(-0.7, 0.7, n), rng.uniform(-0.3, 0.3, n)].astype(np.float32)
+    p1 = p0.copy()
+    lost = rng.choice(n, 20, replace=False)
+    p1[lost] += rng.uniform(0.02, 0.05, (20, 2)).astype(np.float32) * rng.choice([-1, 1], (20, 2))
+    mask, n_in = fe.op_ransac_fundamental(p0, p1, thr, 0.999)
+    static = np.ones(n, bool)
+    static[lost] = False
+    assert mask[static].all() and n_in >= n - 20
+
+
 def test_synth_sequence_is_deterministic(synth):
     a = synth.SynthSequence(seed=5, width=320, height=192, n_frames=5)
     b = synth.SynthSequence(seed=5, width=320, height=192, n_frames=5)
