@@ -251,3 +251,38 @@ def test_assign_points_to_lines_equals_oracle(fe):
             assert np.allclose(list(got.values()), [float(v) for v in want.values()], rtol=0, atol=1e-6), trial
             n_pairs += len(want)
     assert n_pairs > 500
+
+
+def test_ctypes_structs_match_the_c_header(fe, tmp_path):
+    """sizeof / offsetof of every struct of include/plviwo_fe.h, printed by a C program compiled from the header itself,
+    against the ctypes mirror the tests and bench.py use."""
+    import ctypes as C
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {"FeConfig": fe.FeConfig, "FePointRow": fe.FePointRow, "FeLineRow": fe.FeLineRow, "FeLinePoint": fe.FeLinePoint,
+               "FeFrameInfo": fe.FeFrameInfo, "FeStageTimes": fe.FeStageTimes, "FePlayStats": fe.FePlayStats,
+               "FeStereoInfo": fe.FeStereoInfo}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "plviwo_fe.h"', "int main(void) {"]
+    for name, cls in structs.items():
+        lines.append('  printf("%s size %%zu\\n", sizeof(%s));' % (name, name))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (name, fname, name, fname))
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).split("\n")
+    seen = 0
+    for ln in out:
+        if not ln:
+            continue
+        name, field, value = ln.split()
+        cls = structs[name]
+        if field == "size":
+            assert C.sizeof(cls) == int(value), ln
+        else:
+            assert getattr(cls, field).offset == int(value), ln
+        seen += 1
+    assert seen > 60
