@@ -1787,6 +1787,14 @@ int FeContext::set_state(const void *buf, size_t n_bytes) {
   std::memcpy(&hd, p, sizeof(hd));
   p += sizeof(hd);
   if (hd.magic != 0x504c5657u || hd.w != W_ || hd.h != H_) return FE_BAD_ARG;
+  if (hd.n_pts < 0 || hd.n_lines < 0 || hd.n_pol_entries < 0) return FE_BAD_ARG;
+  {   // the blob must hold everything its header announces (a truncated or foreign buffer is rejected, not read past)
+    const size_t need = sizeof(hd) + (size_t)hd.n_pts * (sizeof(Pt) + sizeof(uint64_t)) +
+                        (size_t)hd.n_lines * (sizeof(float4) + sizeof(uint64_t) + sizeof(int32_t)) +
+                        (size_t)hd.n_pol_entries * (sizeof(int32_t) + sizeof(double)) + (hd.has_image ? (size_t)W_ * H_ : 0) +
+                        (hd.has_image && hd.has_mask ? (size_t)W_ * H_ : 0);
+    if (n_bytes < need) return FE_BAD_ARG;
+  }
   auto get = [&](void *dst, size_t n) { std::memcpy(dst, p, n); p += n; };
   currid_ = hd.currid;
   line_currid_ = hd.line_currid;
