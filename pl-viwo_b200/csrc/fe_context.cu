@@ -1561,24 +1561,22 @@ void assign_points_to_lines_host(const std::vector<float4> &lines_new, const std
     const float pa = l.w - l.y, pb = l.x - l.z, pc = l.z * l.y - l.x * l.w;
     const float plen2 = 36.f * (pa * pa + pb * pb);
     if (!line_candidates(spx.data(), spy.data(), npt, min_lx, max_lx, min_ly, max_ly, pa, pb, pc, plen2, pass.data())) continue;
-    std::map<int, double> pol;
-    std::vector<Pt> feats;
-    bool find_point = false;
+    bool find_point = false;   // the line's containers are only created once a point is really within 5 px
     for (int j = 0; j < npt; j++) {
       const unsigned grp = pass[j >> 3];
       if (grp == 0) { j |= 7; continue; }
       if (!((grp >> (j & 7)) & 1u)) continue;
       float dist = point_line_distance(l, spx[j], spy[j]);
       if (dist > 5) continue;
-      pol[(int)pids[j]] = dist;
-      feats.push_back(points[j]);
-      find_point = true;
-    }
-    if (find_point) {
-      pol_new.push_back(pol);
-      filt_lines.push_back(l);
-      filt_ids.push_back(ids_new[i]);
-      positions.push_back(feats);
+      if (!find_point) {
+        pol_new.emplace_back();
+        positions.emplace_back();
+        filt_lines.push_back(l);
+        filt_ids.push_back(ids_new[i]);
+        find_point = true;
+      }
+      pol_new.back()[(int)pids[j]] = dist;
+      positions.back().push_back(points[j]);
     }
   }
 }
