@@ -3,19 +3,24 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A step = one frame of one camera stream through the whole point + line front end (equalise, pyramid, top-off
-FAST detection + sub-pixel, pyramidal LK, RANSAC gate, Canny + line segments, line/point association).
-Workload at every N: BASELINE.json configs[1] — synthetic KAIST-shaped 1280x560 sequence, 400 points, maxLevel 4,
-15x15 window, 5x5 grid, lines on — one independent stream per GPU (weak scaling: streams never exchange data, so
-there is no collective on the data path; NCCL is only used for the barrier and the max-over-ranks reduction).
+Workload at every N: BASELINE.json configs[4] — 64 independent camera streams, each the configs[1] front end
+(synthetic KAIST-shaped 1280x560 mono, point + line front end, 400 points, 5x5 grid, maxLevel 4, 15x15 window),
+stream s on rank s mod N (pl-viwo_b200/shard.py).  Streams never exchange data: no collective on the data path; NCCL
+only carries the barrier and the SUM(frames) / MAX(ms) reduction.
 
-  value  : frames/s with the frames already resident in HBM (device pointers handed to plviwo_fe_submit), the
-           sequence (215 MB) is larger than L2, so no frame is served from cache
-  e2e    : the same frames from pinned HOST memory through the C ABI (H2D of every frame and D2H of every result inside
-           the timed region)
+A STEP is a block of FRAMES_PER_STEP frames of EVERY stream through the whole point + line front end.  Before the timed
+region the pipeline is filled AND DRAINED (every submitted frame collected, device synchronised); the timed region then
+submits and collects exactly steps x FRAMES_PER_STEP frames per stream between two CUDA events, so every counted
+frame's copies, kernels and result read-back happen inside it (pipeline fill and drain included).
+
+  value  : frames/s, frames already resident in HBM (device pointers handed to the library; the resident sequences
+           are far larger than L2, every frame is read from HBM)
+  e2e    : the same from pinned HOST frames through the C ABI: H2D of every frame and D2H of every result row inside
+           the timed region
   roofline / cpu_baseline / clocks : see DESIGN.md "Measurement"
---impl reference times the reference's CPU path: the oracle's restatement of TrackKLT/TrackLSD driving the real
-OpenCV kernels (cv2) on the host cores — the reference itself cannot be compiled in this image.
+--impl reference times the reference's CPU path on the host cores: the oracle's restatement of TrackKLT / TrackLSD
+driving the real OpenCV kernels (cv2), one process per core group over independent streams (the reference itself needs
+OpenCV C++ / Eigen / ROS headers and cannot be compiled in this image).
 """
 from __future__ import annotations
 
@@ -25,30 +30,47 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# One hardware work queue per CUDA stream (default 8): otherwise the latency-critical LK launch can be queued behind a
-# multi-millisecond line-walk kernel of another stream that happens to share its queue.  Must be set before the
-# CUDA context exists.
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before the CUDA context exists
 
 WORKLOAD = dict(width=1280, height=560, num_features=400, fast_threshold=20, grid_x=5, grid_y=5, min_px_dist=10,
                 pyr_levels=4, win_size=15)
-WORKLOAD_NAME = "BASELINE.json configs[1]: synthetic KAIST-shaped 1280x560 mono, point+line front end, 400 pts, 5x5 grid, maxLevel 4, win 15"
-SEQ_FRAMES = 300
-LOOKAHEAD = 48
-PIPELINE_FILL = 2 * (LOOKAHEAD + 2) + 4   # untimed frames a fresh handle needs before it is in steady state
+N_STREAMS = 64
+SEQ_FRAMES = 64          # distinct frames per stream, played forwards and backwards (ping-pong: no jump at the wrap)
+FRAMES_PER_STEP = 32
 METRIC = "front-end frames/sec @1280x560"
+WORKLOAD_NAME = ("BASELINE.json configs[4]: 64 independent camera streams sharded s mod N, each the configs[1] front end "
+                 "(synthetic KAIST-shaped 1280x560 mono, point+line, 400 pts, 5x5 grid, maxLevel 4, win 15)")
+CACHE_DIR = os.environ.get("PLVIWO_BENCH_CACHE", os.path.join(tempfile.gettempdir(), "plviwo_bench_cache"))
 KERNEL_OF_STAGE = {"hist": "k_hist", "eq_pyr1": "k_eq_pyr1", "pyr_rest": "k_pyr_down", "fast": "k_fast", "subpix": "k_corner_subpix",
                    "lk": "k_lk15", "canny": "k_canny", "fld_walk": "k_fld_walk_cc", "fld_ccl": "k_ccl_merge", "fld_seg": "k_fld_segments"}
 
 
+def bench_config(world: int) -> dict:
+    """The workload description: IDENTICAL in both arms (the driver compares the dicts)."""
+    return {"workload": WORKLOAD_NAME, "streams": N_STREAMS, "gpus": world, "frames_per_step": FRAMES_PER_STEP,
+            "frames_per_step_note": "a step = %d frames of every stream" % FRAMES_PER_STEP,
+            "stream_to_gpu": "stream s -> rank s mod N, seed 1000 + s", "sequence_frames": SEQ_FRAMES,
+            "sequence_order": "ping-pong", **{k: v for k, v in WORKLOAD.items()}}
+
+
+def frame_index(i: int, n: int = SEQ_FRAMES) -> int:
+    """Ping-pong order over the n stored frames: 0 .. n-1, n-2 .. 1, 0 .. (continuous motion, no jump)."""
+    if n <= 1:
+        return 0
+    period = 2 * (n - 1)
+    k = i % period
+    return k if k < n else period - k
+
+
 def algorithmic_bytes(n_lk_pts: float, cfg=WORKLOAD) -> dict:
-    """every stage reads its input once and writes its output once."""
+    """every stage reads its input once and writes its output once (per frame)."""
     N = cfg["width"] * cfg["height"]
     L, w = cfg["pyr_levels"], cfg["win_size"]
     sizes, ww, hh = [], cfg["width"], cfg["height"]
@@ -80,7 +102,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -117,22 +139,67 @@ class ClockSampler:
         return out
 
 
-def make_frames(seed: int, n: int):
+# --------------------------------------------------------------------------------------------- synthetic sequences
+def _gen_stream(args):
+    """(seed, n) -> uint8 array (n, H, W); cached on disk so the four scaling runs and the reference arm of one round
+    generate each stream once.  Runs in worker processes (no CUDA there)."""
+    seed, n = args
+    path = os.path.join(CACHE_DIR, "seq_%d_%dx%d_%d.npy" % (seed, WORKLOAD["width"], WORKLOAD["height"], n))
+    try:
+        a = np.load(path)
+        if a.shape == (n, WORKLOAD["height"], WORKLOAD["width"]):
+            return a
+    except Exception:
+        pass
     import plviwo_b200  # noqa: F401
     from plviwo_b200 import synth
-    seq = synth.SynthSequence(seed=seed, width=WORKLOAD["width"], height=WORKLOAD["height"], n_frames=n)
-    return seq, [seq.frame(t) for t in range(n)]
+    seq = synth.SynthSequence(seed=seed, width=WORKLOAD["width"], height=WORKLOAD["height"], n_frames=300)
+    a = np.stack([seq.frame(t) for t in range(n)])
+    try:
+        os.makedirs(CACHE_DIR, exist_ok=True)
+        tmp = path + ".%d.tmp" % os.getpid()
+        with open(tmp, "wb") as f:
+            np.save(f, a)
+        os.replace(tmp, path)
+    except Exception:
+        pass
+    return a
+
+
+def stream_meta(seed: int):
+    """Calibration / timestamps / vanishing points of a stream (the generator's, without building its canvas)."""
+    import plviwo_b200  # noqa: F401
+    from plviwo_b200 import synth
+    sc = WORKLOAD["width"] / 1280.0
+    K = tuple(v * sc for v in synth.KAIST_K)
+    vps = [(1.0e5, 263.0 * sc), (608.0 * sc, -1.0e5), (608.0 * sc, 263.0 * sc)]
+    return K, synth.KAIST_D, vps
+
+
+def timestamp(i: int) -> float:
+    return 1.0 + 0.1 * i
+
+
+def generate_streams(seeds, n, workers):
+    """Frames of several streams, generated in parallel worker processes."""
+    import multiprocessing as mp
+    if len(seeds) == 1 or workers <= 1:
+        return [_gen_stream((s, n)) for s in seeds]
+    with mp.get_context("spawn").Pool(min(workers, len(seeds))) as pool:
+        return pool.map(_gen_stream, [(s, n) for s in seeds])
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def run_cpu(seq, frames, steps, warmup, threads=None, rows_out=None):
-    """The reference's CPU path: oracle restatement of the glue + the real OpenCV kernels (cv2)."""
+def _cpu_worker(args):
+    """One process = one core group: the oracle front end (reference glue restated, real OpenCV kernels) over one stream.
+    Returns timing of `frames` frames after `warm` warm-up frames."""
+    seed, threads, warm, frames, want_rows, barrier_file = args
     import cv2
+    cv2.setNumThreads(threads)
     from oracle import frontend as ofe
-    if threads:
-        cv2.setNumThreads(threads)
-    kw = {k: v for k, v in WORKLOAD.items() if k not in ("width", "height")}
     from oracle import cvops
+    data = _gen_stream((seed, SEQ_FRAMES))
+    K, D, vps = stream_meta(seed)
     in_kernels = [0.0]
 
     class TimedOps:
@@ -151,237 +218,273 @@ def run_cpu(seq, frames, steps, warmup, threads=None, rows_out=None):
                 return r
             return timed
 
-    fe = ofe.FrontEnd(ofe.FeConfig(K=seq.K, D=seq.D, **kw), ops=TimedOps())
-    n = len(frames)
-    def keep(prow):
-        if rows_out is not None:
-            rows_out.append(np.array([(r.id, r.u, r.v) for r in prow], np.float64).reshape(-1, 3))
-
-    for t in range(warmup):
-        keep(fe.feed(seq.timestamp(t), frames[t % n], None, seq.vanishing_points(t % n))[0])
-    per = []
+    kw = {k: v for k, v in WORKLOAD.items() if k not in ("width", "height")}
+    fe = ofe.FrontEnd(ofe.FeConfig(K=K, D=D, **kw), ops=TimedOps())
+    rows = []
+    for i in range(warm):
+        p, _ = fe.feed(timestamp(i), data[frame_index(i)], None, vps)
+        if want_rows:
+            rows.append(np.array([(r.id, r.u, r.v) for r in p], np.float64).reshape(-1, 3))
+    # all workers of a mode start their timed part together (file-system barrier: a spawn pool has no shared objects)
+    if barrier_file:
+        open(barrier_file + ".%d" % os.getpid(), "w").close()
+        n_expected = int(barrier_file.rsplit("_", 1)[1])
+        d, b = os.path.split(barrier_file)
+        t_end = time.time() + 120
+        while sum(1 for f in os.listdir(d) if f.startswith(b + ".")) < n_expected and time.time() < t_end:
+            time.sleep(0.002)
     in_kernels[0] = 0.0
+    per = []
     t0 = time.perf_counter()
-    for k in range(steps):
-        t = warmup + k
+    for k in range(frames):
+        i = warm + k
         a = time.perf_counter()
-        prow, _ = fe.feed(seq.timestamp(t), frames[t % n], None, seq.vanishing_points(t % n))
+        p, _ = fe.feed(timestamp(i), data[frame_index(i)], None, vps)
         per.append(time.perf_counter() - a)
-        keep(prow)
-    dt = time.perf_counter() - t0
-    return dict(fps=steps / dt, ms_per_step=1e3 * dt / steps, p50_ms=1e3 * float(np.median(per)), cores=cv2.getNumThreads(),
-                kernel_ms=1e3 * in_kernels[0] / steps, glue_ms=1e3 * (dt - in_kernels[0]) / steps,
-                kernels_only_fps=steps / in_kernels[0] if in_kernels[0] > 0 else None)
+        if want_rows:
+            rows.append(np.array([(r.id, r.u, r.v) for r in p], np.float64).reshape(-1, 3))
+    t1 = time.perf_counter()
+    # what the port does differently from the C++ reference inside OpenCV: cv2.calcOpticalFlowPyrLK (image form) builds
+    # both pyramids per call where the reference builds ONE per frame (TrackKLT.cpp:71) — one build too many; and the
+    # port equalises once where the reference equalises twice (TrackKLT.cpp:59 and TrackLSD.cpp:83) — one too few
+    eq = cv2.equalizeHist(data[0])
+    t = time.perf_counter()
+    for _ in range(10):
+        cv2.buildOpticalFlowPyramid(eq, (WORKLOAD["win_size"],) * 2, WORKLOAD["pyr_levels"], withDerivatives=False)
+    t_pyr = (time.perf_counter() - t) / 10
+    t = time.perf_counter()
+    for _ in range(10):
+        cv2.equalizeHist(data[1])
+    t_eq = (time.perf_counter() - t) / 10
+    return dict(t0=t0, t1=t1, frames=frames, kernel_s=in_kernels[0], p50_ms=1e3 * float(np.median(per)), t_pyr=t_pyr, t_eq=t_eq,
+                rows=rows if want_rows else None)
 
 
-def parity_against(fe_mod, seq, frames, rows_cpu, kw, dev):
-    """BASELINE.json's third metric ("KLT px err"): the frames the CPU baseline has just processed, through the synchronous
-    drop-in call on the GPU from the same initial state, both free-running.  The oracle is the checker here, nothing of it
-    is timed.  A single flipped status flag changes every later feature id, so id equality is reported
-    up to the first frame where the row sets differ and the pixel error over the rows both sides have."""
-    h = fe_mod.FrontEnd(fe_mod.default_config(K=seq.K, D=seq.D, lookahead=0, **kw), device=dev)
-    n = len(frames)
-    first_div, eq_frames, duv, rows_total, sym = None, 0, [], 0, 0
-    for t, want in enumerate(rows_cpu):
-        h.feed_new_camera(seq.timestamp(t), frames[t % n], None, seq.vanishing_points(t % n), update_db=False)
-        got = h.point_rows()
-        ids_g = {int(i): k for k, i in enumerate(got["id"])}
-        ids_c = {int(i): k for k, i in enumerate(want[:, 0])}
-        d = set(ids_g) ^ set(ids_c)
-        rows_total += len(ids_c)
-        if first_div is None:
-            if d:
-                first_div = t
-            else:
-                eq_frames += 1
-        if first_div is None or t == first_div:   # same tracks on both sides: compare positions
-            sym += len(d)
-            for i in set(ids_g) & set(ids_c):
-                a, b = got[ids_g[i]], want[ids_c[i]]
-                duv.append(max(abs(float(a["u"]) - b[1]), abs(float(a["v"]) - b[2])))
-    h.close()
-    duv = np.array(duv) if duv else np.zeros(1)
-    # the per-frame bar: the GPU tracker is loaded with the oracle's state before every frame (teacher forcing), so each
-    # frame is compared on identical inputs — what tests/test_frontend_gpu.py asserts, here over 40 frames as a number
+def run_cpu_mode(procs: int, threads: int, warm: int, frames: int, want_rows=False):
+    """`procs` worker processes (independent streams, seeds 1000 ..), `threads` OpenCV threads each."""
+    import multiprocessing as mp
+    bdir = tempfile.mkdtemp(prefix="plviwo_bar_")
+    bfile = os.path.join(bdir, "go_%d" % procs)
+    jobs = [(1000 + p, threads, warm, frames, want_rows and p == 0, bfile) for p in range(procs)]
+    if procs == 1:
+        res = [_cpu_worker(jobs[0][:5] + (None,))]
+    else:
+        with mp.get_context("spawn").Pool(procs) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    try:
+        for f in os.listdir(bdir):
+            os.unlink(os.path.join(bdir, f))
+        os.rmdir(bdir)
+    except Exception:
+        pass
+    # perf_counter is CLOCK_MONOTONIC: comparable across the processes of one box
+    elapsed = max(r["t1"] for r in res) - min(r["t0"] for r in res)
+    tot = sum(r["frames"] for r in res)
+    busy = sum(r["t1"] - r["t0"] for r in res)
+    kern = sum(r["kernel_s"] for r in res)
+    corr = sum((r["t1"] - r["t0"]) - r["frames"] * (r["t_pyr"] - r["t_eq"]) for r in res)
+    return dict(procs=procs, threads=threads, fps=tot / elapsed, elapsed_s=elapsed, frames=tot,
+                p50_ms=float(np.median([r["p50_ms"] for r in res])),
+                kernel_ms=1e3 * kern / tot, glue_ms=1e3 * (busy - kern) / tot,
+                kernels_only_fps=tot / elapsed * busy / kern if kern > 0 else None,
+                corrected_fps=tot / elapsed * busy / corr if corr > 0 else None,
+                rows=res[0]["rows"])
+
+
+def cpu_modes(cores: int):
+    """OpenCV thread counts 1, 4 (the reference's own choice, test_tracking.cpp:115) and all, processes filling the box."""
+    modes = [(max(cores, 1), 1)]
+    if cores >= 4:
+        modes.append((cores // 4, 4))
+    modes.append((1, cores))
+    return modes
+
+
+def run_cpu_arm(frames_per_proc: int, warm: int, sweep_frames: int, want_rows=False):
+    """Thread sweep on a short sample, then the timed run in the best mode."""
+    cores = len(os.sched_getaffinity(0))
+    _gen_stream((1000, SEQ_FRAMES))
+    sweep = []
+    for procs, threads in cpu_modes(cores):
+        generate_streams([1000 + p for p in range(procs)], SEQ_FRAMES, min(procs, cores))
+        r = run_cpu_mode(procs, threads, 8, sweep_frames)
+        sweep.append({k: r[k] for k in ("procs", "threads", "fps", "p50_ms", "kernel_ms", "glue_ms", "kernels_only_fps", "corrected_fps")})
+    best = max(sweep, key=lambda r: r["fps"])
+    r = run_cpu_mode(best["procs"], best["threads"], warm, frames_per_proc, want_rows)
+    return r, sweep, cores
+
+
+def cpu_baseline_dict(r, sweep, cores, label):
+    return {"value": r["fps"], "unit": "frames/s", "cores": r["procs"] * r["threads"], "kind": "port",
+            "host_cores": cores, "processes": r["procs"], "opencv_threads_per_process": r["threads"],
+            "sample": "%s: %d frames on each of %d independent streams (seeds 1000..), one process per stream with %d OpenCV "
+                      "thread(s); oracle/frontend.py (reference glue restated in Python) driving the real OpenCV kernels via "
+                      "cv2; per frame %.2f ms inside OpenCV / the FLD shim + %.2f ms Python glue"
+                      % (label, r["frames"] // r["procs"], r["procs"], r["threads"], r["kernel_ms"], r["glue_ms"]),
+            "kernels_only_value": r["kernels_only_fps"],
+            "kernels_only_note": "frames/s if the reference's glue cost nothing: the upper bound for any CPU implementation "
+                                 "built on these OpenCV kernels, and the denominator README / DESIGN quote",
+            "pyramid_corrected_value": r["corrected_fps"],
+            "pyramid_corrected_note": "per frame minus one cv::buildOpticalFlowPyramid (the image form of calcOpticalFlowPyrLK "
+                                      "builds two per call, the reference one per frame, TrackKLT.cpp:71) plus one "
+                                      "cv::equalizeHist (the reference equalises twice, TrackLSD.cpp:83), both timed in the run",
+            "thread_sweep": sweep, "p50_ms_per_frame": r["p50_ms"]}
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+class HandleEngine:
+    """One FeHandle per stream (plviwo_fe_create), each driven by its own host thread through plviwo_fe_play — the
+    submit / collect loop inside the library, so the Python GIL is not part of the measurement."""
+    name = "handles"
+
+    def __init__(self, fe_mod, dev, metas, lookahead):
+        self.fe = fe_mod
+        self.h = [fe_mod.FrontEnd(fe_mod.default_config(K=K, D=D, lookahead=lookahead, **WORKLOAD), device=dev) for K, D, _ in metas]
+        self.metas = metas
+        self.lookahead = lookahead
+
+    def run(self, first, n_frames, ptrs, pitch, on_device):
+        """Frames first .. first + n_frames - 1 of every stream; returns when every frame has been collected."""
+        done = [0] * len(self.h)
+        errs = []
+
+        def drive(k):
+            try:
+                idx = [frame_index(first + i) for i in range(n_frames)]
+                ts = [timestamp(first + i) for i in range(n_frames)]
+                vps = [self.metas[k][2]] * n_frames
+                st = self.h[k].play(ts, [ptrs[k][t] for t in idx], stride=pitch, on_device=on_device, vanishing_points=vps)
+                done[k] = int(st.frames)
+            except Exception as e:   # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=drive, args=(k,)) for k in range(len(self.h))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+        return sum(done)
+
+    def counters(self, reset=False):
+        tot = {"kernel_launches_total": 0, "h2d_bytes": 0, "d2h_bytes": 0, "frames": 0}
+        for h in self.h:
+            st = h.stage_times(reset=reset)
+            for k in tot:
+                tot[k] += st[k]
+        return tot
+
+    def stage_times(self, reset=False):
+        return [h.stage_times(reset=reset) for h in self.h]
+
+    def enable_timing(self, on):
+        for h in self.h:
+            h.enable_timing(on)
+
+    def close(self):
+        for h in self.h:
+            h.close()
+
+
+def make_engine(kind, fe_mod, dev, metas):
+    if kind == "group":
+        return fe_mod.GroupEngine(fe_mod, dev, metas, WORKLOAD)
+    la = int(os.environ.get("PLVIWO_BENCH_LA", "16" if len(metas) > 2 else "48"))
+    return HandleEngine(fe_mod, dev, metas, la)
+
+
+def timed_pass(torch, dist, eng, first, n_frames, ptrs, pitch, on_device):
+    """The timed region: barrier + synchronise, event, submit and collect n_frames of every stream, synchronise, event."""
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    eng.counters(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    t0 = time.perf_counter()
+    frames = eng.run(first, n_frames, ptrs, pitch, on_device)
+    torch.cuda.synchronize()
+    ev1.record()
+    ev1.synchronize()
+    wall = time.perf_counter() - t0
+    c = eng.counters(reset=False)
+    if dist is not None:
+        dist.barrier()
+    return dict(ms=float(ev0.elapsed_time(ev1)), wall_ms=1e3 * wall, frames=frames, counters=c)
+
+
+def parity_against(fe_mod, dev, data, meta, rows_cpu):
+    """BASELINE.json's third metric ("KLT px err").  The oracle is the checker here, nothing of it is timed.
+    (a) teacher forced over 40 frames: the GPU tracker is loaded with the oracle's state before every frame, so each frame
+        is compared on identical inputs (what tests/test_frontend_gpu.py asserts);
+    (b) free running: the frames the CPU baseline has just processed through the synchronous drop-in call from the same
+        initial state; one flipped status flag changes every later feature id, so id equality is reported
+        up to the first frame where the row sets differ."""
     from oracle import frontend as ofe
+    K, D, vps = meta
+    kw = dict(WORKLOAD)
     okw = {k: v for k, v in kw.items() if k not in ("width", "height")}
-    o = ofe.FrontEnd(ofe.FeConfig(K=seq.K, D=seq.D, **okw))
-    h = fe_mod.FrontEnd(fe_mod.default_config(K=seq.K, D=seq.D, lookahead=0, **kw), device=dev)
     W, H = kw["width"], kw["height"]
-    tf_duv, tf_rows, tf_sym, tf_frames_equal = [], 0, 0, 0
+    o = ofe.FrontEnd(ofe.FeConfig(K=K, D=D, **okw))
+    h = fe_mod.FrontEnd(fe_mod.default_config(K=K, D=D, lookahead=0, **kw), device=dev)
+    tf_duv, tf_rows, tf_sym, tf_equal = [], 0, 0, 0
     for t in range(40):
+        img = data[frame_index(t)]
         if t > 0:
             k, l = o.klt.get_state(), o.lsd.get_state()
             h.set_state(fe_mod.pack_state(W, H, k["currid"], k["pts_last"], k["ids_last"], k["img_last"], k["mask_last"], l["currid"],
                                           l["lines_last"], l["ids_last"], l["pol_last"]))
-        prow, _ = o.feed(seq.timestamp(t), frames[t % n], None, seq.vanishing_points(t % n))
-        h.feed_new_camera(seq.timestamp(t), frames[t % n], None, seq.vanishing_points(t % n), update_db=False)
+        prow, _ = o.feed(timestamp(t), img, None, vps)
+        h.feed_new_camera(timestamp(t), img, None, vps, update_db=False)
         got = h.point_rows()
         ids_g = {int(i): k2 for k2, i in enumerate(got["id"])}
         ids_c = {r.id: r for r in prow}
         d = set(ids_g) ^ set(ids_c)
         tf_rows += len(ids_c)
         tf_sym += len(d)
-        tf_frames_equal += int(not d and [r.id for r in prow] == [int(i) for i in got["id"]])
+        tf_equal += int(not d and [r.id for r in prow] == [int(i) for i in got["id"]])
         for i in set(ids_g) & set(ids_c):
             a, b = got[ids_g[i]], ids_c[i]
             tf_duv.append(max(abs(float(a["u"]) - b.u), abs(float(a["v"]) - b.v)))
     h.close()
     tf_duv = np.array(tf_duv) if tf_duv else np.zeros(1)
-    teacher = {"frames": 40, "frames_rows_identical_ids_and_order": tf_frames_equal, "rows": tf_rows,
+    teacher = {"frames": 40, "frames_rows_identical_ids_and_order": tf_equal, "rows": tf_rows,
                "rows_with_flipped_status": tf_sym, "status_agreement": 1.0 - tf_sym / max(tf_rows, 1),
                "max_duv_px": float(tf_duv.max()), "p99_duv_px": float(np.percentile(tf_duv, 99)),
-               "rows_over_0.05px": int((tf_duv > 0.05).sum())}
-    return {"teacher_forced": teacher, "frames": len(rows_cpu), "frames_ids_identical": eq_frames, "first_frame_with_different_rows": first_div,
-            "rows_compared": int(len(duv)), "max_duv_px": float(duv.max()), "p99_duv_px": float(np.percentile(duv, 99)),
-            "rows_only_on_one_side_at_divergence": sym,
-            "note": "free-running GPU (plviwo_fe_feed) vs the CPU baseline's oracle on the same frames; the teacher-forced "
-                    "per-frame bars (0.05 px, ids bit-exact, status >= 99.5 %) are asserted in tests/test_frontend_gpu.py"}
-
-
-# ----------------------------------------------------------------------------------------------- GPU arm
-def run_gpu_pass(fe_mod, torch, handle, seq, srcs, steps, warmup, on_device, pitch, dist, timing):
-    """Pipelined submit/collect over `steps` frames after `warmup` frames; returns (elapsed_ms by CUDA events, infos)."""
-    n = len(srcs)
-    # every frame slot of the handle runs its first frame with direct launches and captures its CUDA graphs on its second:
-    # the untimed part covers two rounds over the lookahead + 2 slots so that neither lands in the timed region
-    warmup = max(warmup, PIPELINE_FILL)
-    tot = warmup + steps
-    sub = 0
-    rows = 0
-
-    def submit(i):
-        t = i % n
-        if on_device:
-            handle.submit(seq.timestamp(i), srcs[t], stride=pitch, on_device=True, vanishing_points=seq.vanishing_points(t))
-        else:
-            handle.submit(seq.timestamp(i), srcs[t], vanishing_points=seq.vanishing_points(t))
-
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    per = []
-    for i in range(tot):
-        if i == warmup:
-            torch.cuda.synchronize()
-            if dist is not None:
-                dist.barrier()
-            torch.cuda.synchronize()
-            handle.enable_timing(timing)
-            handle.stage_times(reset=True)
-            ev0.record()
-            t_wall = time.perf_counter()
-        while sub < tot and sub <= i + LOOKAHEAD:
-            submit(sub)
-            sub += 1
-        info = handle.collect()
-        if i >= warmup:
-            per.append(time.perf_counter())   # completion times: the per-frame period is their difference
-            rows += info.n_point_rows + info.n_line_rows
-    torch.cuda.synchronize()
-    ev1.record()
-    ev1.synchronize()
-    wall_ms = 1e3 * (time.perf_counter() - t_wall)
-    if dist is not None:
-        dist.barrier()
-    st = handle.stage_times(reset=False)
-    handle.enable_timing(False)
-    period = np.diff(np.array(per)) if len(per) > 1 else np.zeros(1)
-    return dict(ms=float(ev0.elapsed_time(ev1)), wall_ms=wall_ms, stage=st, rows=rows, p50_ms=1e3 * float(np.median(period)),
-                p95_ms=1e3 * float(np.percentile(period, 95)))
-
-
-def run_gpu_multi(fe_mod, torch, seq, d_ptrs, pitch, n_streams, steps, warmup, cfg_kw, dev):
-    """configs[4] shape on one GPU: n_streams independent handles (own CUDA streams, own tracker threads), each driven by
-    one host thread through plviwo_fe_play (the submit/collect loop inside the library, so the Python GIL is not part of
-    the measurement).  All streams replay the same device-resident sequence from different start frames (they never
-    exchange data, so this is n_streams times the single-stream work)."""
-    import threading
-    n = len(d_ptrs)
-    la = int(os.environ.get("PLVIWO_BENCH_LA", "16"))
-    warmup = max(warmup, 2 * (la + 2) + 4)
-    handles = [fe_mod.FrontEnd(fe_mod.default_config(K=seq.K, D=seq.D, lookahead=la, **cfg_kw), device=dev) for _ in range(n_streams)]
-    gate = threading.Barrier(n_streams + 1)
-    frames_done = [0] * n_streams
-
-    def drive(k):
-        h = handles[k]
-        off = (k * 37) % n
-        idx = [(off + i) % n for i in range(warmup + steps)]
-        ts = [seq.timestamp(i) for i in range(warmup + steps)]
-        ptrs = [d_ptrs[t] for t in idx]
-        vps = [seq.vanishing_points(t) for t in idx] if not os.environ.get("PLVIWO_BENCH_NOLINES") else None
-        h.play(ts[:warmup], ptrs[:warmup], stride=pitch, on_device=True, vanishing_points=vps[:warmup] if vps else None)
-        gate.wait()      # everybody warmed up
-        gate.wait()      # timed region starts
-        if os.environ.get("PLVIWO_BENCH_TIMING"):
-            h.enable_timing(True)
-            h.stage_times(reset=True)
-        st = h.play(ts[warmup:], ptrs[warmup:], stride=pitch, on_device=True, vanishing_points=vps[warmup:] if vps else None)
-        frames_done[k] = int(st.frames)
-        if os.environ.get("PLVIWO_BENCH_TIMING") and k == 0:
-            tt = h.stage_times()
-            sys.stderr.write("stream0 stage ms/frame: %s\n" % {a: round(b / max(tt["frames"], 1), 4) for a, b in tt["ms"].items()})
-            sys.stderr.write("stream0 host ms/frame: %s\n" % {a: round(b / max(tt["frames"], 1), 4) for a, b in tt["host_ms"].items()})
-
-    th = [threading.Thread(target=drive, args=(k,)) for k in range(n_streams)]
-    for t in th:
-        t.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    gate.wait()
-    torch.cuda.synchronize()
-    ev0.record()
-    t0 = time.perf_counter()
-    gate.wait()
-    for t in th:
-        t.join()
-    torch.cuda.synchronize()
-    ev1.record()
-    ev1.synchronize()
-    wall = time.perf_counter() - t0
-    for h in handles:
+               "rows_over_0.05px": int((tf_duv > 0.05).sum()),
+               "rows_over_0.05px_note": "rows on which cv2's own LK is unstable (tests/test_frontend_gpu.py carve-out: each "
+                                        "must match the scalar restatement or be shown chaotic)"}
+    out = {"teacher_forced": teacher}
+    if rows_cpu:
+        h = fe_mod.FrontEnd(fe_mod.default_config(K=K, D=D, lookahead=0, **kw), device=dev)
+        first_div, eq_frames, duv, sym = None, 0, [], 0
+        for t, want in enumerate(rows_cpu):
+            h.feed_new_camera(timestamp(t), data[frame_index(t)], None, vps, update_db=False)
+            got = h.point_rows()
+            ids_g = {int(i): k for k, i in enumerate(got["id"])}
+            ids_c = {int(i): k for k, i in enumerate(want[:, 0])}
+            d = set(ids_g) ^ set(ids_c)
+            if first_div is None:
+                if d:
+                    first_div = t
+                else:
+                    eq_frames += 1
+            if first_div is None or t == first_div:
+                sym += len(d)
+                for i in set(ids_g) & set(ids_c):
+                    a, b = got[ids_g[i]], want[ids_c[i]]
+                    duv.append(max(abs(float(a["u"]) - b[1]), abs(float(a["v"]) - b[2])))
         h.close()
-    ms = float(ev0.elapsed_time(ev1))
-    return {"streams": n_streams, "frames": sum(frames_done), "ms": ms, "value": sum(frames_done) / (ms * 1e-3), "unit": "frames/s",
-            "wall_fps": sum(frames_done) / wall, "lookahead": la,
-            "note": "BASELINE.json configs[4] shape on ONE GPU: independent streams, one host driver thread each "
-                    "(plviwo_fe_play), frames resident in HBM"}
-
-
-def run_stereo(fe_mod, torch, seq, h_left, steps, warmup, kw, dev):
-    """SURVEY.md 8(f) rank 2: the stereo rig (TrackKLT::feed_stereo + the left-image line tracker) through
-    plviwo_fe_stereo_submit / _collect from pinned HOST pairs; pairs/s by wall clock around a device synchronise."""
-    n = min(len(h_left), 60)
-    H, W = h_left[0].shape
-    h_r = torch.empty((n, H, W), dtype=torch.uint8).pin_memory()
-    for t in range(n):
-        h_r[t].copy_(torch.from_numpy(seq.frame(t, 1)))
-    right = [h_r[t].numpy() for t in range(n)]
-    g = fe_mod.StereoFrontEnd(fe_mod.default_config(K=seq.K, D=seq.D, lookahead=LOOKAHEAD, **kw), device=dev)
-    warmup = max(warmup, PIPELINE_FILL)
-    tot, sub, rows = warmup + steps, 0, 0
-    for i in range(tot):
-        if i == warmup:
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-        while sub < tot and sub <= i + LOOKAHEAD:
-            t = sub % n
-            g.submit(seq.timestamp(sub), h_left[t], right[t], vanishing_points=seq.vanishing_points(t))
-            sub += 1
-        info = g.collect()
-        if i >= warmup:
-            rows += info.n_point_rows[0] + info.n_point_rows[1] + info.n_line_rows
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    st = g.stage_times()
-    g.close()
-    return {"value": steps / dt, "unit": "stereo pairs/s", "rows_per_pair": rows / max(steps, 1),
-            "h2d_bytes_per_pair": 2 * H * W, "gpu_launches": st["kernel_launches_total"],
-            "api": "plviwo_fe_stereo_submit/_collect from pinned host pairs (60-pair loop), left-image line tracker on, lookahead %d" % LOOKAHEAD}
+        duv = np.array(duv) if duv else np.zeros(1)
+        out.update({"frames": len(rows_cpu), "frames_ids_identical": eq_frames, "first_frame_with_different_rows": first_div,
+                    "rows_compared": int(len(duv)), "max_duv_px": float(duv.max()), "p99_duv_px": float(np.percentile(duv, 99)),
+                    "rows_only_on_one_side_at_divergence": sym})
+    return out
 
 
 def pin_to_gpu_numa_node(torch, dev):
-    """The handle's host threads poll flags and exchange the (small) feature arrays with the LK kernel through pinned host
-    memory: keep the rank on the cores of the NUMA node its GPU hangs off.  Returns the node, or None when the platform
-    does not say (single socket, virtualised PCI topology)."""
+    """Keep the rank on the cores of the NUMA node its GPU hangs off, when the platform says which that is."""
     try:
         pr = torch.cuda.get_device_properties(dev)
         bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
@@ -404,13 +507,12 @@ def pin_to_gpu_numa_node(torch, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=600)
-    ap.add_argument("--warmup", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=150, help="frames of the CPU baseline sample")
+    ap.add_argument("--engine", default=os.environ.get("PLVIWO_BENCH_ENGINE", "auto"), choices=["auto", "group", "handles"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-stereo", action="store_true", help="skip the extra stereo-rig measurement")
-    ap.add_argument("--multi-streams", type=int, default=8, help="streams per GPU of the extra multi-stream measurement (0 = skip)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the single-stream / synchronous / stereo extras")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     # exactly ONE line on stdout: libraries that print banners there (NCCL's version line) are sent to stderr
@@ -428,20 +530,16 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        seq, frames = make_frames(1000, SEQ_FRAMES)
-        steps = min(args.steps, 400)   # bounded sample of the same workload
-        r = run_cpu(seq, frames, steps, min(args.warmup, 20))
+        steps = min(args.steps, 20)
+        warm = min(args.warmup, 4) * 4
+        # a step of the reference arm = FRAMES_PER_STEP frames on each stream of its bounded sample (one stream per process)
+        r, sweep, cores = run_cpu_arm(steps * FRAMES_PER_STEP, warm, 24)
+        cb = cpu_baseline_dict(r, sweep, cores, "bounded sample of the 64-stream workload")
         line = {"metric": METRIC, "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
-                "warmup": min(args.warmup, 20), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": 1e3 * r["elapsed_s"] / steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "u8/int32 fixed-point + f32/f64 (OpenCV)", "data": "synthetic", "impl": "reference",
-                "config": {"workload": WORKLOAD_NAME, "streams": 1},
-                "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
-                                 "sample": "%d frames of the same synthetic sequence; reference glue restated in Python "
-                                           "(oracle/frontend.py) driving the real OpenCV kernels through cv2; per frame %.2f ms "
-                                           "inside OpenCV / the FLD shim + %.2f ms Python glue" % (steps, r["kernel_ms"], r["glue_ms"]),
-                                 "kernels_only_value": r["kernels_only_fps"],
-                                 "kernels_only_note": "frames/s if the reference's glue cost nothing (upper bound for any "
-                                                      "CPU implementation built on these OpenCV kernels)"},
+                "config": bench_config(args.gpus),
+                "sample_streams": r["procs"], "cpu_baseline": cb,
                 "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "p50_ms_per_frame": r["p50_ms"]}
         emit(line)
@@ -461,77 +559,108 @@ def main():
     torch.cuda.set_device(dev)
     numa = pin_to_gpu_numa_node(torch, dev)
 
-    seq, frames = make_frames(1000 + rank, SEQ_FRAMES)   # stream s = seed 1000 + s
-    H, W = frames[0].shape
-    # device-resident copy of the sequence (215 MB > 126 MB L2) and a pinned host copy
-    d_seq = torch.empty((len(frames), H, W), dtype=torch.uint8, device="cuda")
-    h_seq = torch.empty((len(frames), H, W), dtype=torch.uint8).pin_memory()
-    for t, f in enumerate(frames):
-        h_seq[t].copy_(torch.from_numpy(f))
+    # ---- this rank's streams (config 5): s -> rank s mod N, seed 1000 + s
+    streams = fe_mod.shard.streams_of_rank(N_STREAMS, rank, world)
+    S = len(streams)
+    seeds = [fe_mod.shard.seed_of_stream(s) for s in streams]
+    cores = len(os.sched_getaffinity(0))
+    t_gen = time.perf_counter()
+    data = generate_streams(seeds, SEQ_FRAMES, max(1, cores // max(world, 1)))
+    t_gen = time.perf_counter() - t_gen
+    metas = [stream_meta(s) for s in seeds]
+    H, W = WORKLOAD["height"], WORKLOAD["width"]
+    # device-resident copy (S x 64 frames x 0.72 MB: 2.9 GB at S = 64, far larger than the 126 MB L2) and a pinned host copy
+    d_seq = torch.empty((S, SEQ_FRAMES, H, W), dtype=torch.uint8, device="cuda")
+    h_seq = torch.empty((S, SEQ_FRAMES, H, W), dtype=torch.uint8).pin_memory()
+    for k in range(S):
+        h_seq[k].copy_(torch.from_numpy(data[k]))
     d_seq.copy_(h_seq)
     torch.cuda.synchronize()
-    d_ptrs = [d_seq[t].data_ptr() for t in range(len(frames))]
-    h_np = [h_seq[t].numpy() for t in range(len(frames))]
+    d_ptrs = [[d_seq[k, t].data_ptr() for t in range(SEQ_FRAMES)] for k in range(S)]
+    h_ptrs = [[h_seq[k, t].numpy() for t in range(SEQ_FRAMES)] for k in range(S)]
 
-    kw = {k: v for k, v in WORKLOAD.items()}
-    handle = fe_mod.FrontEnd(fe_mod.default_config(K=seq.K, D=seq.D, lookahead=LOOKAHEAD, **kw), device=dev)
+    kind = args.engine
+    if kind == "auto":
+        kind = "group" if hasattr(fe_mod, "GroupEngine") else "handles"
+    n_timed = args.steps * FRAMES_PER_STEP
+    n_warm = max(args.warmup * FRAMES_PER_STEP, 64)
 
-    # untimed dry pass first: a fresh process's GPU is still ramping its clocks during the first ~100 ms of work, longer
-    # than the 104 untimed frames (8 ms) in front of the timed region
-    run_gpu_pass(fe_mod, torch, handle, seq, d_ptrs, min(args.steps, 1000), args.warmup, True, W, dist, timing=False)
+    # ---- resident pass
+    eng = make_engine(kind, fe_mod, dev, metas)
+    eng.run(0, n_warm, d_ptrs, W, True)                       # untimed: graph capture, clocks, then DRAINED (run returns when
+    torch.cuda.synchronize()                                   # every frame is collected)
     sampler = ClockSampler(dev) if rank == 0 else None
-    res = run_gpu_pass(fe_mod, torch, handle, seq, d_ptrs, args.steps, args.warmup, True, W, dist, timing=False)
+    res = timed_pass(torch, dist, eng, n_warm, n_timed, d_ptrs, W, True)
     clocks = sampler.stop() if sampler else {}
-    # per-kernel durations: the same pass again with CUDA-event stage timing on (direct launches instead of graph replays)
-    res_t = run_gpu_pass(fe_mod, torch, handle, seq, d_ptrs, min(args.steps, 200), args.warmup, True, W, None, timing=True)
-    handle.close()
-    handle = fe_mod.FrontEnd(fe_mod.default_config(K=seq.K, D=seq.D, lookahead=LOOKAHEAD, **kw), device=dev)
-    run_gpu_pass(fe_mod, torch, handle, seq, h_np, min(args.steps, 1000), args.warmup, False, W, dist, timing=False)   # untimed dry pass
-    res_e2e = run_gpu_pass(fe_mod, torch, handle, seq, h_np, args.steps, args.warmup, False, W, dist, timing=False)
-    handle.close()
-    # strict drop-in: synchronous plviwo_fe_feed per frame from host memory
-    handle = fe_mod.FrontEnd(fe_mod.default_config(K=seq.K, D=seq.D, lookahead=0, **kw), device=dev)
-    n_sync = min(args.steps, 300)
-    for t in range(args.warmup):
-        handle.feed_new_camera(seq.timestamp(t), h_np[t % len(h_np)], None, seq.vanishing_points(t % len(h_np)), update_db=False)
+    if res["counters"]["kernel_launches_total"] == 0 or res["frames"] != n_timed * S:
+        raise SystemExit("bench.py: the timed region launched no kernel or lost frames (%r)" % (res,))
+    # ---- per-kernel durations: a short pass with CUDA-event stage timing on
+    stage = None
+    try:
+        eng.enable_timing(True)
+        eng.run(n_warm + n_timed, 8, d_ptrs, W, True)          # timing on: direct launches, first frames
+        eng.stage_times(reset=True)
+        eng.run(n_warm + n_timed + 8, min(n_timed, 96), d_ptrs, W, True)
+        stage = eng.stage_times(reset=False)
+        eng.enable_timing(False)
+    except Exception as e:   # noqa: BLE001
+        stage = {"error": str(e)}
+    eng.close()
+    # ---- end to end: the same through the C ABI from pinned HOST frames
+    eng = make_engine(kind, fe_mod, dev, metas)
+    eng.run(0, n_warm, h_ptrs, W, False)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for k in range(n_sync):
-        t = args.warmup + k
-        handle.feed_new_camera(seq.timestamp(t), h_np[t % len(h_np)], None, seq.vanishing_points(t % len(h_np)), update_db=False)
-    sync_fps = n_sync / (time.perf_counter() - t0)
-    handle.close()
+    res_e2e = timed_pass(torch, dist, eng, n_warm, n_timed, h_ptrs, W, False)
+    eng.close()
 
-    stereo = None
-    if world == 1 and not args.no_stereo:
-        try:
-            stereo = run_stereo(fe_mod, torch, seq, h_np, min(args.steps, 300), args.warmup, kw, dev)
-        except Exception as e:   # an extra, never fatal for the bench line
-            stereo = {"error": str(e)}
-    multi = None
-    if world == 1 and args.multi_streams > 1:
-        multi = run_gpu_multi(fe_mod, torch, seq, d_ptrs, W, args.multi_streams, min(args.steps, 400), args.warmup, kw, dev)
+    extras = {}
+    if world == 1 and not args.no_extras:
+        try:   # one pipelined stream (configs[1] alone on the GPU)
+            e1 = make_engine("handles", fe_mod, dev, metas[:1])
+            e1.run(0, 128, d_ptrs[:1], W, True)
+            r1 = timed_pass(torch, None, e1, 128, 600, d_ptrs[:1], W, True)
+            extras["single_stream"] = {"value": r1["frames"] / (r1["ms"] * 1e-3), "unit": "frames/s", "frames": r1["frames"],
+                                       "api": "plviwo_fe_play on one handle, lookahead %d, frames resident in HBM" % e1.lookahead}
+            e1.close()
+        except Exception as e:   # noqa: BLE001
+            extras["single_stream"] = {"error": str(e)}
+        try:   # strict drop-in: synchronous plviwo_fe_feed per frame from host memory
+            K, D, vps = metas[0]
+            h = fe_mod.FrontEnd(fe_mod.default_config(K=K, D=D, lookahead=0, **WORKLOAD), device=dev)
+            for t in range(16):
+                h.feed_new_camera(timestamp(t), h_ptrs[0][frame_index(t)], None, vps, update_db=False)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for t in range(16, 216):
+                h.feed_new_camera(timestamp(t), h_ptrs[0][frame_index(t)], None, vps, update_db=False)
+            extras["sync_feed_fps"] = 200 / (time.perf_counter() - t0)
+            h.close()
+        except Exception as e:   # noqa: BLE001
+            extras["sync_feed_fps"] = {"error": str(e)}
 
     ms, ms_e2e = res["ms"], res_e2e["ms"]
-    per_rank = [[ms, ms_e2e]]
-    total_frames = args.steps * world
+    frames_rank = res["frames"]
+    per_rank = [[ms, ms_e2e, float(frames_rank)]]
+    total_frames, total_frames_e2e = frames_rank, res_e2e["frames"]
+    launches = res["counters"]["kernel_launches_total"]
     if dist is not None:
         # whole-job numbers: SUM of frames, MAX of elapsed time over the ranks (pl-viwo_b200/shard.py)
-        tt = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
-        allms = [torch.zeros_like(tt) for _ in range(world)]
-        dist.all_gather(allms, tt)
-        per_rank = [[float(v[0]), float(v[1])] for v in allms]
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(tt[0]), float(tt[1])
-        total_frames = int(round(fe_mod.shard.distributed_throughput(dist, torch, args.steps, ms, device="cuda") * ms * 1e-3))
+        tt = torch.tensor([ms, ms_e2e, float(frames_rank)], device="cuda", dtype=torch.float64)
+        allv = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(allv, tt)
+        per_rank = [[float(v[0]), float(v[1]), float(v[2])] for v in allv]
+        ms, ms_e2e = max(v[0] for v in per_rank), max(v[1] for v in per_rank)
+        total_frames = int(round(fe_mod.shard.distributed_throughput(dist, torch, frames_rank, res["ms"], device="cuda") * ms * 1e-3))
+        total_frames_e2e = int(sum(v[2] for v in per_rank))
+        lt = torch.tensor([float(launches)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(lt)
+        launches = int(lt[0])
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
-    st = res_t["stage"]
-    nfr = max(st["frames"], 1)
-    # roofline of the dominant kernel (largest share of the timed region), live CUDA-event durations
+    # ---- roofline of the dominant kernel (largest cost per frame), live CUDA-event durations
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -539,102 +668,119 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-    lk_pts = 0.0
-    if st["launches"]["lk"]:
-        lk_pts = res_t["rows"] / max(st["launches"]["lk"], 1)  # lower bound: rows written; LK input is slightly larger
-    ab = algorithmic_bytes(max(lk_pts, 1.0))
-    # single kernels only: "fld" is the sum of fld_ccl + fld_walk + fld_seg, pyr_rest / fld_ccl / fld_seg are 3-4 launches
-    stage_ms = {k: v for k, v in st["ms"].items() if k not in ("h2d", "fld", "line_frames") and st["launches"][k]}
-    # line-path kernels are launched once per BATCH of frames (grid.y = frame): frames carried / launches per launch
-    LINE_STAGES = ("canny", "fld", "fld_ccl", "fld_walk", "fld_seg")
-    line_frames = st["launches"].get("line_frames", 0)
-    fpl = {k: (line_frames / max(st["launches"][k], 1) if k in LINE_STAGES and line_frames else 1.0) for k in st["ms"]}
-    frames_of = {k: (line_frames if k in LINE_STAGES and line_frames else nfr) for k in st["ms"]}
-    dom = max(stage_ms, key=lambda k: stage_ms[k] / max(frames_of[k], 1)) if stage_ms else "lk"   # largest cost per frame
-    avg_ms = stage_ms.get(dom, 0.0) / max(st["launches"][dom], 1)
-    achieved = (ab[dom] * fpl.get(dom, 1.0) / (avg_ms * 1e-3)) / 1e9 if avg_ms > 0 else 0.0
-    traffic = None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full summary
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["kernels"].get(KERNEL_OF_STAGE.get(dom, dom))
-    except Exception:
-        pass
-    if traffic is not None and fpl.get(dom, 1.0) != 1.0:
-        traffic = traffic * fpl[dom]   # the ncu --set full capture profiles single-frame launches: scaled to the frames a launch carries
-    per_kernel = {}
-    for k, v in stage_ms.items():
-        ms_k = v / max(st["launches"][k], 1)
-        per_kernel[k] = {"avg_ms": ms_k, "frames_per_launch": round(fpl[k], 2), "algorithmic_bytes": ab.get(k, 0) * fpl[k],
-                         "GBps": (ab.get(k, 0) * fpl[k] / (ms_k * 1e-3)) / 1e9 if ms_k > 0 else 0.0}
-        per_kernel[k]["frac"] = per_kernel[k]["GBps"] / peak if peak else None
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ab[dom] * fpl.get(dom, 1.0), "frames_per_launch": round(fpl.get(dom, 1.0), 2),
-                "avg_launch_ms": avg_ms,
-                "note": "the dominant kernel is the sequential chain walk of the line detector (one launch per batch of "
-                        "frames): latency bound, not HBM bound (DESIGN.md 'Kernels'); per_kernel lists every kernel of the "
-                        "frame, stage_ms_per_frame their cost per frame",
-                "per_kernel": per_kernel,
-                "stage_ms_per_frame": {k: v / max(frames_of[k], 1) for k, v in st["ms"].items() if k != "line_frames"},
-                "host_ms_per_frame": {k: v / max(res["stage"]["frames"], 1) for k, v in res["stage"]["host_ms"].items()
-                                      if not k.startswith("unused")},
-                "whole_frame": {"algorithmic_bytes": ab["frame_total"],
-                                "achieved_GBps": ab["frame_total"] * (total_frames / (ms * 1e-3)) / 1e9 / world}}
-    # what the image-domain kernels reach when ONE launch carries a batch of frames' worth of pixels (134 MB > L2) instead
-    # of one 0.7 MB frame: same kernels, device-resident synthetic image, CUDA events around single launches
-    at_scale = None
-    try:
+    roofline = build_roofline(stage, peak, peak_src, total_frames / (ms * 1e-3) / world, res)
+    try:   # what the image-domain kernels reach when ONE launch carries a batch of frames' worth of pixels
         AW, AH = 16384, 8192
         t = fe_mod.op_image_kernels_time(AW, AH, 5, device=dev)
         NA = AW * AH
         bytes_ = {"hist": NA, "eq_pyr1": NA + NA + NA // 4 + NA // 4, "fast": NA, "canny": NA // 4 + NA // 4}
-        at_scale = {"image": "%dx%d (= %.0f frames of 1280x560 per launch)" % (AW, AH, NA / (1280 * 560.0)),
-                    "kernels": {k: {"ms": t[k], "algorithmic_bytes": bytes_[k], "GBps": bytes_[k] / (t[k] * 1e-3) / 1e9,
-                                    "frac": bytes_[k] / (t[k] * 1e-3) / 1e9 / peak} for k in t if t[k] > 0}}
+        roofline["at_scale"] = {"image": "%dx%d (= %.0f frames of 1280x560 per launch)" % (AW, AH, NA / (1280 * 560.0)),
+                                "kernels": {k: {"ms": t[k], "algorithmic_bytes": bytes_[k], "GBps": bytes_[k] / (t[k] * 1e-3) / 1e9,
+                                                "frac": bytes_[k] / (t[k] * 1e-3) / 1e9 / peak} for k in t if t[k] > 0}}
     except Exception as e:   # never fatal for the bench line
-        at_scale = {"error": str(e)}
-    roofline["at_scale"] = at_scale
-    cpu = None
-    parity = None
-    if not args.no_cpu_baseline:
-        rows_cpu = []
-        r = run_cpu(seq, frames, args.cpu_sample, 10, rows_out=rows_cpu)
+        roofline["at_scale"] = {"error": str(e)}
+
+    cpu = parity = None
+    if not args.no_cpu_baseline and world == 1:
+        r, sweep, ncores = run_cpu_arm(160, 8, 16, want_rows=True)
+        cpu = cpu_baseline_dict(r, sweep, ncores, "bounded sample of the 64-stream workload")
         try:
-            parity = parity_against(fe_mod, seq, h_np, rows_cpu, kw, dev)
+            parity = parity_against(fe_mod, dev, data[0], metas[0], r["rows"][:120] if r["rows"] else None)
         except Exception as e:   # an extra, never fatal for the bench line
             parity = {"error": str(e)}
-        cpu = {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
-               "sample": "%d frames of the same sequence; oracle/frontend.py (reference glue restated) driving real OpenCV "
-                         "kernels via cv2, %d OpenCV threads; p50 %.2f ms/frame = %.2f ms inside OpenCV / the FLD shim + %.2f ms "
-                         "Python glue" % (args.cpu_sample, r["cores"], r["p50_ms"], r["kernel_ms"], r["glue_ms"]),
-               "kernels_only_value": r["kernels_only_fps"],
-               "kernels_only_note": "frames/s if the reference's glue cost nothing (upper bound for any CPU implementation "
-                                    "built on these OpenCV kernels)"}
+
+    cfg = bench_config(world)
     line = {
         "metric": METRIC, "value": total_frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u8/int32 fixed-point + f32 (LK), f64 (sub-pixel, undistort, RANSAC)", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME, "streams_per_gpu": 1, "streams": world, "stream_to_gpu": "stream s -> rank s mod N, seed 1000 + s",
-                   "lookahead": LOOKAHEAD, "sequence_frames": SEQ_FRAMES,
-                   "untimed_frames": max(args.warmup, PIPELINE_FILL),
+        "config": cfg,
+        "engine": {"kind": eng.name, "streams_per_gpu": S, "frames_timed_per_stream": n_timed, "untimed_frames_per_stream": n_warm,
+                   "timed_region": "pipeline drained before the first event; steps x frames_per_step frames of every stream "
+                                   "submitted AND collected between the events",
                    "host": {"cores": os.cpu_count(), "rank0_numa_node": numa, "rank0_cpus": len(os.sched_getaffinity(0))},
                    "per_rank_ms": {"resident": [round(v[0], 2) for v in per_rank], "e2e": [round(v[1], 2) for v in per_rank]},
-                   "cache": "inputs larger than L2 (215 MB device-resident sequence, every frame read once per pass)"},
-        "p50_ms_per_frame": res["p50_ms"], "p95_ms_per_frame": res["p95_ms"],
-        "p50_note": "median time between consecutive frame completions (plviwo_fe_collect returns) in the timed region; the "
-                    "strictly synchronous per-frame latency is 1000 / e2e.sync_feed_fps ms",
+                   "synthesis_s": round(t_gen, 1),
+                   "cache": "inputs larger than L2 (%.1f GB of device-resident frames per GPU, every frame read from HBM)"
+                            % (S * SEQ_FRAMES * H * W / 1e9)},
+        "p50_ms_per_frame": 1e3 / (total_frames / (ms * 1e-3)) if total_frames else None,
+        "p50_note": "reciprocal of the whole-job throughput (the batched engine completes frames a tick at a time); the strictly "
+                    "synchronous per-frame latency is 1000 / extras.sync_feed_fps ms",
         "klt_parity": parity,
-        "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s",
-                "h2d_bytes_per_step": res_e2e["stage"]["h2d_bytes"] / max(res_e2e["stage"]["frames"], 1),
-                "d2h_bytes_per_step": res_e2e["stage"]["d2h_bytes"] / max(res_e2e["stage"]["frames"], 1),
-                "api": "plviwo_fe_submit/plviwo_fe_collect from pinned host frames, lookahead %d" % LOOKAHEAD,
-                "sync_feed_fps": sync_fps},
-        "gpu_launches": res["stage"]["kernel_launches_total"],
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "multi_stream": multi, "stereo": stereo,
+        "e2e": {"value": total_frames_e2e / (ms_e2e * 1e-3), "unit": "frames/s",
+                "h2d_bytes_per_step": res_e2e["counters"]["h2d_bytes"] / args.steps,
+                "d2h_bytes_per_step": res_e2e["counters"]["d2h_bytes"] / args.steps,
+                "api": "pinned host frames through the C ABI (%s), H2D of every frame and D2H of every row inside the timed region" % eng.name},
+        "gpu_launches": launches,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
     }
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def build_roofline(stage, peak, peak_src, fps_per_gpu, res):
+    """roofline{} of the bench line from the library's CUDA-event stage times (per LAUNCH) of the timing pass."""
+    out = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None}
+    ab1 = algorithmic_bytes(300.0)
+    out["whole_frame"] = {"algorithmic_bytes": ab1["frame_total"], "achieved_GBps": ab1["frame_total"] * fps_per_gpu / 1e9,
+                          "frac": ab1["frame_total"] * fps_per_gpu / 1e9 / peak}
+    if not stage or isinstance(stage, dict) and "error" in stage:
+        out.update(kernel=None, achieved=0.0, frac=0.0, error=(stage or {}).get("error", "no stage times"))
+        return out
+    if isinstance(stage, dict) and "kernels" in stage:    # group engine: per-kernel records straight from the library
+        ks = stage["kernels"]
+        dom = max(ks, key=lambda k: ks[k]["ms_per_frame"]) if ks else None
+        if dom:
+            k = ks[dom]
+            out.update(kernel=dom, achieved=k["GBps"], frac=k["GBps"] / peak, avg_launch_ms=k["avg_ms"],
+                       algorithmic_bytes_per_launch=k["algorithmic_bytes"], frames_per_launch=k["frames_per_launch"])
+        out["per_kernel"] = ks
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["kernels"]
+            if dom and tr.get(dom) is not None:
+                out["traffic"] = tr[dom]
+        except Exception:
+            pass
+        return out
+    # handle engine: merge the per-handle FeStageTimes
+    ms, launches, frames = {}, {}, 0
+    for st in stage:
+        frames += st["frames"]
+        for k, v in st["ms"].items():
+            ms[k] = ms.get(k, 0.0) + v
+        for k, v in st["launches"].items():
+            launches[k] = launches.get(k, 0) + v
+    nfr = max(frames, 1)
+    lk_pts = 300.0
+    ab = algorithmic_bytes(lk_pts)
+    LINE = ("canny", "fld", "fld_ccl", "fld_walk", "fld_seg")
+    line_frames = launches.get("line_frames", 0)
+    stage_ms = {k: v for k, v in ms.items() if k not in ("h2d", "fld", "line_frames") and launches.get(k)}
+    fpl = {k: (line_frames / max(launches[k], 1) if k in LINE and line_frames else 1.0) for k in stage_ms}
+    frames_of = {k: (line_frames if k in LINE and line_frames else nfr) for k in stage_ms}
+    per_kernel = {}
+    for k, v in stage_ms.items():
+        a = v / max(launches[k], 1)
+        per_kernel[k] = {"avg_ms": a, "frames_per_launch": round(fpl[k], 2), "algorithmic_bytes": ab.get(k, 0) * fpl[k],
+                         "ms_per_frame": v / max(frames_of[k], 1),
+                         "GBps": (ab.get(k, 0) * fpl[k] / (a * 1e-3)) / 1e9 if a > 0 else 0.0}
+        per_kernel[k]["frac"] = per_kernel[k]["GBps"] / peak
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_frame"]) if per_kernel else None
+    if dom:
+        k = per_kernel[dom]
+        out.update(kernel=dom, achieved=k["GBps"], frac=k["frac"], avg_launch_ms=k["avg_ms"],
+                   algorithmic_bytes_per_launch=k["algorithmic_bytes"], frames_per_launch=k["frames_per_launch"])
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["kernels"].get(KERNEL_OF_STAGE.get(dom, dom))
+            out["traffic"] = tr * fpl[dom] if tr is not None else None
+        except Exception:
+            pass
+    else:
+        out.update(kernel=None, achieved=0.0, frac=0.0)
+    out["per_kernel"] = per_kernel
+    return out
 
 
 if __name__ == "__main__":

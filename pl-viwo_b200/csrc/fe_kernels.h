@@ -168,4 +168,48 @@ void launch_fld(const DevImage &half, int length_threshold, float distance_thres
                 cudaEvent_t *ev = nullptr);
 void launch_unpack_edges(const FldBuffers &fb, int w, int h, uint8_t *d_out, cudaStream_t s);
 
+// ---- batched multi-stream launches (FeGroup, fe_group.cu) ------------------------------------------------------
+// A stream group processes one frame of MANY camera streams per launch (grid.z = job).  Every frame slot of every
+// stream is described once, at creation, by a SlotRec in device memory; a launch gets a device array of jobs that name
+// slots by index, so the same launch sequence serves any mix of streams without re-encoding kernel arguments.
+struct SlotRec {
+  DevImage raw;                  // staging of a host-fed frame (device-resident inputs are read in place)
+  DevImage lvl[kMaxLevels];      // equalised pyramid, level 0 = equalised frame
+  int n_lvl;
+  DevImage half;                 // half-resolution equalised frame (line detector input)
+  uint8_t *mask;                 // caller mask of the frame (w * h bytes, tight); valid iff the slot's flag bit 0 is set
+  unsigned *hist, *counters;     // 256 bins (zero between frames), 4 counters
+  uint8_t *clahe;                // 64 tile LUTs
+  unsigned *fast_total;          // [0] corners [1] scratch cursor
+  unsigned *kps, *sort_scratch;
+  int *band_off, *band_cnt;
+  float2 *cand, *cand_ref;       // per-cell candidate table before / after cornerSubPix (cell c at c * nfg)
+  int *cand_cnt;
+  FldBuffers fld;
+};
+struct FrontJob {
+  const uint8_t *src;            // the frame: device pointer (caller's, or the slot's raw staging)
+  int src_pitch;
+  int slot;                      // index into the SlotRec table
+  int eq_mode;                   // 0 copy, 1 cv::equalizeHist, 2 CLAHE
+  int flags;                     // bit 0: the slot's mask buffer holds this frame's mask
+};
+struct FrontGeom {               // the same for every stream of a group
+  int w, h;                      // tracking size
+  int n_cells, max_bands, max_cell_w, fast_threshold, kps_cap, nfg;
+  const FastCell *cells;
+};
+// State-independent work of n_jobs frames: equalise + pyramid, FAST on every grid cell + std::sort/top-k + cornerSubPix.
+void launch_hist_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, const FrontGeom &g, int *slot_flags, cudaStream_t s);
+void launch_clahe_lut_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, const FrontGeom &g, cudaStream_t s);
+void launch_eq_pyr1_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, const FrontGeom &g, bool want_half, cudaStream_t s);
+void launch_pyr_level_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, int level, int dw, int dh, cudaStream_t s);
+void launch_fast_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, const FrontGeom &g, cudaStream_t s);
+void launch_fast_select_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, const FrontGeom &g, cudaStream_t s);
+void launch_corner_subpix_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, const FrontGeom &g, cudaStream_t s);
+// Line paths of n_jobs frames; line_slots: device array of slot indices.  ev as launch_fld.
+void launch_canny_table(const SlotRec *slots, const int *line_slots, int n_jobs, int w, int h, float th_low, cudaStream_t s);
+void launch_fld_table(const SlotRec *slots, const int *line_slots, int n_jobs, int w, int h, int max_chains, int length_threshold,
+                      float distance_threshold, cudaStream_t s, cudaEvent_t *ev = nullptr);
+
 }  // namespace plviwo

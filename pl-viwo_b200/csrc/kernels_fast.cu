@@ -66,10 +66,9 @@ __device__ __forceinline__ int fast_score(const uint8_t *__restrict__ px, int st
   return max(a0, -b0) - 1;
 }
 
-__global__ void __launch_bounds__(kFastThreads)
-    k_fast(const uint8_t *__restrict__ img, int pitch, const FastCell *__restrict__ cells, int max_bands, int threshold,
-           unsigned *__restrict__ total, int *__restrict__ band_off, int *__restrict__ band_cnt,
-           unsigned *__restrict__ kps, int kps_cap, int smem_w) {
+__device__ __forceinline__ void fast_body(const uint8_t *__restrict__ img, int pitch, const FastCell *__restrict__ cells, int max_bands,
+                                          int threshold, unsigned *__restrict__ total, int *__restrict__ band_off,
+                                          int *__restrict__ band_cnt, unsigned *__restrict__ kps, int kps_cap, int smem_w) {
   extern __shared__ uint8_t smem[];
   uint8_t *pix = smem;                               // (kBH + 8) rows x smem_w
   uint8_t *sc = smem + (kBH + 8) * smem_w;           // (kBH + 2) rows x smem_w
@@ -157,6 +156,20 @@ __global__ void __launch_bounds__(kFastThreads)
   }
 }
 
+__global__ void __launch_bounds__(kFastThreads)
+    k_fast(const uint8_t *__restrict__ img, int pitch, const FastCell *__restrict__ cells, int max_bands, int threshold,
+           unsigned *__restrict__ total, int *__restrict__ band_off, int *__restrict__ band_cnt,
+           unsigned *__restrict__ kps, int kps_cap, int smem_w) {
+  fast_body(img, pitch, cells, max_bands, threshold, total, band_off, band_cnt, kps, kps_cap, smem_w);
+}
+// grid = (band, cell, job)
+__global__ void __launch_bounds__(kFastThreads)
+    k_fast_b(const SlotRec *__restrict__ slots, const FrontJob *__restrict__ jobs, FrontGeom g, int smem_w) {
+  const SlotRec &sl = slots[jobs[blockIdx.z].slot];
+  fast_body(sl.lvl[0].p, sl.lvl[0].pitch, g.cells, g.max_bands, g.fast_threshold, sl.fast_total, sl.band_off, sl.band_cnt, sl.kps,
+            g.kps_cap, smem_w);
+}
+
 // ------------------------------------------------------------------------------------- per-cell selection
 // Grider_GRID.h:128-133: std::sort(cell corners, compare_response), keep the first num_features_grid.  One CTA per
 // cell: the cell's corners (band slices of the compact list, i.e. row-major order — the order cv::FAST emits them in)
@@ -167,8 +180,8 @@ constexpr int kSelThreads = 128;
 constexpr int kSelSmemCap = 8192;
 constexpr int kSelMaxBands = 256;   // 4095 rows / kFastBandRows
 
-__global__ void __launch_bounds__(kSelThreads)
-    k_fast_select(const FastCell *__restrict__ cells, int max_bands, unsigned *__restrict__ total /* [0] corners, [1] scratch cursor */,
+__device__ __forceinline__ void fast_select_body(const FastCell *__restrict__ cells, int max_bands,
+                  unsigned *__restrict__ total /* [0] corners, [1] scratch cursor */,
                   const int *__restrict__ band_off, const int *__restrict__ band_cnt, const unsigned *__restrict__ kps,
                   int kps_cap, unsigned *__restrict__ scratch, int nfg, float2 *__restrict__ cand_sel,
                   int *__restrict__ cand_cnt) {
@@ -205,6 +218,36 @@ __global__ void __launch_bounds__(kSelThreads)
     const unsigned p = v[i];
     cand_sel[c * nfg + i] = make_float2((float)(p & 0xfffu) + x0, (float)((p >> 12) & 0xfffu) + y0);
   }
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+    k_fast_select(const FastCell *__restrict__ cells, int max_bands, unsigned *__restrict__ total,
+                  const int *__restrict__ band_off, const int *__restrict__ band_cnt, const unsigned *__restrict__ kps,
+                  int kps_cap, unsigned *__restrict__ scratch, int nfg, float2 *__restrict__ cand_sel,
+                  int *__restrict__ cand_cnt) {
+  fast_select_body(cells, max_bands, total, band_off, band_cnt, kps, kps_cap, scratch, nfg, cand_sel, cand_cnt);
+}
+// grid = (cell, job)
+__global__ void __launch_bounds__(kSelThreads)
+    k_fast_select_b(const SlotRec *__restrict__ slots, const FrontJob *__restrict__ jobs, FrontGeom g) {
+  const SlotRec &sl = slots[jobs[blockIdx.y].slot];
+  fast_select_body(g.cells, g.max_bands, sl.fast_total, sl.band_off, sl.band_cnt, sl.kps, g.kps_cap, sl.sort_scratch, g.nfg, sl.cand,
+                   sl.cand_cnt);
+}
+
+void launch_fast_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, const FrontGeom &g, cudaStream_t s) {
+  if (n_jobs <= 0 || g.n_cells <= 0) return;
+  const int smem_w = (g.max_cell_w + 15) & ~15;
+  const size_t smem = (size_t)(2 * kBH + 10) * smem_w;
+  static SmemOptIn optin;
+  optin.ensure(k_fast_b, smem);
+  PLVIWO_CARVEOUT(k_fast_b);
+  k_fast_b<<<dim3(g.max_bands, g.n_cells, n_jobs), kFastThreads, smem, s>>>(slots, jobs, g, smem_w);
+}
+void launch_fast_select_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, const FrontGeom &g, cudaStream_t s) {
+  if (n_jobs <= 0 || g.n_cells <= 0 || g.max_bands > kSelMaxBands) return;
+  PLVIWO_CARVEOUT(k_fast_select_b);
+  k_fast_select_b<<<dim3(g.n_cells, n_jobs), kSelThreads, 0, s>>>(slots, jobs, g);
 }
 
 void launch_fast_select(const FastCell *d_cells, int n_cells, int max_bands, unsigned *d_total, const int *d_band_off,

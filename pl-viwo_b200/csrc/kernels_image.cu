@@ -42,17 +42,17 @@ __device__ __forceinline__ void hist_add16(unsigned *my, const uint4 &v) {
   }
 }
 
-__global__ void __launch_bounds__(kHistThreads) k_hist(const uint8_t *__restrict__ src, int w, int h, int pitch,
-                                                       unsigned *__restrict__ hist) {
+__device__ __forceinline__ void hist_body(const uint8_t *__restrict__ src, int w, int h, int pitch,
+                                          unsigned *__restrict__ hist, int block, int n_blocks) {
   __shared__ unsigned sh[kHistWarps][256];
   for (int i = threadIdx.x; i < kHistWarps * 256; i += kHistThreads) (&sh[0][0])[i] = 0;
   __syncthreads();
   unsigned *my = sh[threadIdx.x >> 5];
   const int chunks_per_row = (w + 15) >> 4;
   const int total = chunks_per_row * h;
-  const int stride = gridDim.x * kHistThreads;
-  const bool full_rows = (w & 15) == 0;   // every chunk is a whole, aligned uint4
-  int c = blockIdx.x * kHistThreads + threadIdx.x;
+  const int stride = n_blocks * kHistThreads;
+  const bool full_rows = (w & 15) == 0 && (pitch & 15) == 0 && ((size_t)src & 15) == 0;   // every chunk is a whole, aligned uint4
+  int c = block * kHistThreads + threadIdx.x;
   if (full_rows) {
     for (; c + (kHistUnroll - 1) * stride < total; c += kHistUnroll * stride) {
       uint4 v[kHistUnroll];
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kHistThreads) k_hist(const uint8_t *__restrict
     int y = c / chunks_per_row;
     int x = (c - y * chunks_per_row) << 4;
     const uint8_t *row = src + (size_t)y * pitch + x;
-    if (x + 16 <= w) {
+    if (x + 16 <= w && ((size_t)row & 15) == 0) {
       hist_add16(my, *reinterpret_cast<const uint4 *>(row));
     } else {
       for (int k = 0; x + k < w; k++) atomicAdd(&my[row[k]], 1u);
@@ -83,6 +83,35 @@ __global__ void __launch_bounds__(kHistThreads) k_hist(const uint8_t *__restrict
     for (int k = 0; k < kHistWarps; k++) s += sh[k][b];
     if (s) atomicAdd(&hist[b], s);
   }
+}
+
+__global__ void __launch_bounds__(kHistThreads) k_hist(const uint8_t *__restrict__ src, int w, int h, int pitch,
+                                                       unsigned *__restrict__ hist) {
+  hist_body(src, w, h, pitch, hist, blockIdx.x, gridDim.x);
+}
+
+// grid.z = job.  Block 0 of a job also publishes the frame's flags and zeroes the FAST counters of its slot (every later
+// kernel of the frame is ordered after this one on the same stream).
+__global__ void __launch_bounds__(kHistThreads)
+    k_hist_b(const SlotRec *__restrict__ slots, const FrontJob *__restrict__ jobs, int w, int h, int *__restrict__ slot_flags) {
+  const FrontJob job = jobs[blockIdx.z];
+  const SlotRec &sl = slots[job.slot];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    slot_flags[job.slot] = job.flags;
+    sl.fast_total[0] = 0;
+    sl.fast_total[1] = 0;
+  }
+  if (job.eq_mode != 1) return;
+  hist_body(job.src, w, h, job.src_pitch, sl.hist, blockIdx.x, gridDim.x);
+}
+
+void launch_hist_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, const FrontGeom &g, int *slot_flags, cudaStream_t s) {
+  if (n_jobs <= 0) return;
+  const int chunks = ((g.w + 15) >> 4) * g.h;
+  int grid = (chunks + kHistThreads * 4 - 1) / (kHistThreads * 4);   // one unrolled round of 4 chunks per thread
+  if (grid < 1) grid = 1;
+  PLVIWO_CARVEOUT(k_hist_b);
+  k_hist_b<<<dim3(grid, 1, n_jobs), kHistThreads, 0, s>>>(slots, jobs, g.w, g.h, slot_flags);
 }
 
 void launch_hist(const DevImage &src, unsigned *d_hist, cudaStream_t s) {
@@ -107,8 +136,8 @@ struct ClaheGeom {
   float lut_scale, inv_tw, inv_th;
 };
 
-__global__ void __launch_bounds__(256)
-    k_clahe_lut(const uint8_t *__restrict__ src, int w, int h, int pitch, ClaheGeom g, uint8_t *__restrict__ luts) {
+__device__ __forceinline__ void clahe_lut_body(const uint8_t *__restrict__ src, int w, int h, int pitch, const ClaheGeom &g,
+                                               uint8_t *__restrict__ luts) {
   __shared__ unsigned sh[8][256];
   __shared__ unsigned warp_tot[8];
   __shared__ unsigned s_clipped;
@@ -172,6 +201,17 @@ __device__ __forceinline__ unsigned clahe_px(const uint8_t *__restrict__ luts, c
   return (unsigned)min(max(r, 0), 255);
 }
 
+__global__ void __launch_bounds__(256)
+    k_clahe_lut(const uint8_t *__restrict__ src, int w, int h, int pitch, ClaheGeom g, uint8_t *__restrict__ luts) {
+  clahe_lut_body(src, w, h, pitch, g, luts);
+}
+__global__ void __launch_bounds__(256)
+    k_clahe_lut_b(const SlotRec *__restrict__ slots, const FrontJob *__restrict__ jobs, int w, int h, ClaheGeom g) {
+  const FrontJob job = jobs[blockIdx.z];
+  if (job.eq_mode != 2) return;
+  clahe_lut_body(job.src, w, h, job.src_pitch, g, slots[job.slot].clahe);
+}
+
 static ClaheGeom clahe_geom(int w, int h) {
   ClaheGeom g;
   g.tiles_x = 8;
@@ -198,6 +238,12 @@ void launch_clahe_lut(const DevImage &src, uint8_t *d_luts, cudaStream_t s) {
   k_clahe_lut<<<64, 256, 0, s>>>(src.p, src.w, src.h, src.pitch, g, d_luts);
 }
 
+void launch_clahe_lut_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, const FrontGeom &g, cudaStream_t s) {
+  if (n_jobs <= 0) return;
+  PLVIWO_CARVEOUT(k_clahe_lut_b);
+  k_clahe_lut_b<<<dim3(64, 1, n_jobs), 256, 0, s>>>(slots, jobs, g.w, g.h, clahe_geom(g.w, g.h));
+}
+
 // ------------------------------------------------------------------------- equalise + level 0/1 + half-res
 // One CTA produces a 64 x 16 tile of level 1, i.e. consumes a (128 + 4) x (32 + 4) window of the raw frame
 // (5-tap [1 4 6 4 1] pyrDown halo of 2), staged in shared memory AFTER the LUT so level 0, level 1 and the
@@ -213,9 +259,8 @@ constexpr int kEqThreads = 256;
 constexpr int kBulkCols = kT0W + 32;           // 160 bytes per row
 constexpr int kBulkLead = 12;                  // bulk column of tile column 0: (2*tx0 - 4) - (2*tx0 - 16)
 
-__global__ void __launch_bounds__(kEqThreads)
-    k_eq_pyr1(const uint8_t *__restrict__ src, int w, int h, int spitch, unsigned *__restrict__ hist,
-              unsigned *__restrict__ counter, int equalize, const uint8_t *__restrict__ clahe_luts, ClaheGeom cg,
+__device__ __forceinline__ void eq_pyr1_body(const uint8_t *__restrict__ src, int w, int h, int spitch, unsigned *__restrict__ hist,
+              unsigned *__restrict__ counter, int equalize, const uint8_t *__restrict__ clahe_luts, const ClaheGeom &cg,
               uint8_t *__restrict__ l0, int l0pitch,
               uint8_t *__restrict__ l1, int w1, int h1, int l1pitch, uint8_t *__restrict__ half, int wh, int hh,
               int hpitch) {
@@ -408,6 +453,33 @@ __global__ void __launch_bounds__(kEqThreads)
   }
 }
 
+__global__ void __launch_bounds__(kEqThreads)
+    k_eq_pyr1(const uint8_t *__restrict__ src, int w, int h, int spitch, unsigned *__restrict__ hist,
+              unsigned *__restrict__ counter, int equalize, const uint8_t *__restrict__ clahe_luts, ClaheGeom cg,
+              uint8_t *__restrict__ l0, int l0pitch,
+              uint8_t *__restrict__ l1, int w1, int h1, int l1pitch, uint8_t *__restrict__ half, int wh, int hh,
+              int hpitch) {
+  eq_pyr1_body(src, w, h, spitch, hist, counter, equalize, clahe_luts, cg, l0, l0pitch, l1, w1, h1, l1pitch, half, wh, hh, hpitch);
+}
+__global__ void __launch_bounds__(kEqThreads)
+    k_eq_pyr1_b(const SlotRec *__restrict__ slots, const FrontJob *__restrict__ jobs, int w, int h, ClaheGeom cg, int want_half) {
+  const FrontJob job = jobs[blockIdx.z];
+  const SlotRec &sl = slots[job.slot];
+  const DevImage &l1 = sl.lvl[1];
+  const bool has1 = sl.n_lvl > 1;
+  eq_pyr1_body(job.src, w, h, job.src_pitch, sl.hist, sl.counters, job.eq_mode, sl.clahe, cg, sl.lvl[0].p, sl.lvl[0].pitch,
+               has1 ? l1.p : nullptr, has1 ? l1.w : 0, has1 ? l1.h : 0, l1.pitch, want_half ? sl.half.p : nullptr, sl.half.w, sl.half.h,
+               sl.half.pitch);
+}
+
+void launch_eq_pyr1_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, const FrontGeom &g, bool want_half, cudaStream_t s) {
+  if (n_jobs <= 0) return;
+  const int w1 = (g.w + 1) / 2, h1 = (g.h + 1) / 2;
+  dim3 grid((w1 + kT1W - 1) / kT1W, (h1 + kT1H - 1) / kT1H, n_jobs);
+  PLVIWO_CARVEOUT(k_eq_pyr1_b);
+  k_eq_pyr1_b<<<grid, kEqThreads, 0, s>>>(slots, jobs, g.w, g.h, clahe_geom(g.w, g.h), want_half ? 1 : 0);
+}
+
 void launch_eq_pyr1(const DevImage &src, unsigned *d_hist, unsigned *d_counter, int equalize, const DevImage &l0,
                     const DevImage &l1, const DevImage &half, cudaStream_t s, const uint8_t *d_clahe_luts) {
   // tiles are laid over the level-1 footprint of the frame even when level 1 itself is not wanted (l1.p == null)
@@ -425,9 +497,8 @@ constexpr int kRestThreads = 256;
 // One level from the previous one: a thread produces 4 horizontally adjacent outputs (one 32-bit store).  The upper
 // levels are tiny (320x140 and below), L2 resident, and each costs one short launch; an earlier version that let the
 // last CTA of level 2 compute all remaining levels alone measured 51 us, this is ~3 us per level.
-__global__ void __launch_bounds__(kRestThreads)
-    k_pyr_down(const uint8_t *__restrict__ src, int sw, int sh, int spitch, uint8_t *__restrict__ dst, int dw, int dh,
-               int dpitch) {
+__device__ __forceinline__ void pyr_down_body(const uint8_t *__restrict__ src, int sw, int sh, int spitch, uint8_t *__restrict__ dst,
+                                              int dw, int dh, int dpitch) {
   const int quads = (dw + 3) >> 2;
   const int i = blockIdx.x * kRestThreads + threadIdx.x;
   if (i >= quads * dh) return;
@@ -457,6 +528,24 @@ __global__ void __launch_bounds__(kRestThreads)
   } else {
     for (int o = 0; x0 + o < dw; o++) d[o] = (uint8_t)((hs[o] + 128) >> 8);
   }
+}
+
+__global__ void __launch_bounds__(kRestThreads)
+    k_pyr_down(const uint8_t *__restrict__ src, int sw, int sh, int spitch, uint8_t *__restrict__ dst, int dw, int dh,
+               int dpitch) {
+  pyr_down_body(src, sw, sh, spitch, dst, dw, dh, dpitch);
+}
+__global__ void __launch_bounds__(kRestThreads)
+    k_pyr_down_b(const SlotRec *__restrict__ slots, const FrontJob *__restrict__ jobs, int level) {
+  const SlotRec &sl = slots[jobs[blockIdx.z].slot];
+  const DevImage &a = sl.lvl[level - 1], &b = sl.lvl[level];
+  pyr_down_body(a.p, a.w, a.h, a.pitch, b.p, b.w, b.h, b.pitch);
+}
+void launch_pyr_level_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, int level, int dw, int dh, cudaStream_t s) {
+  if (n_jobs <= 0) return;
+  const int n = ((dw + 3) >> 2) * dh;
+  PLVIWO_CARVEOUT(k_pyr_down_b);
+  k_pyr_down_b<<<dim3((n + kRestThreads - 1) / kRestThreads, 1, n_jobs), kRestThreads, 0, s>>>(slots, jobs, level);
 }
 
 // Completion signal: a one-thread kernel at the tail of a stream writes a sequence number into pinned host memory.

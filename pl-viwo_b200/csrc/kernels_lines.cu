@@ -463,6 +463,7 @@ __global__ void __launch_bounds__(kWalkThreads)
       // consume the seed (lane 0 still holds nothing of it: the scan word wv is the seed's word), then fetch its 5 x 5
       // window.  Shared-memory operations of one warp execute in order, so the loads see the cleared bit.
       if (lane == 0) sts_u32(bm_addr + 4u * (unsigned)(rb + (p >> 5)), wv & ~(1u << (p & 31)));
+      __syncwarp();   // the other lanes' window loads below must see the cleared bit (memory ordering inside the warp)
       unsigned B;
       {
         const int qb = p + my_dc;
@@ -495,6 +496,7 @@ __global__ void __launch_bounds__(kWalkThreads)
         sh = 5u * r1 + c1;
         // consume the new pixel: the lane that just fetched it (window position 6 + sh) rewrites its word without it
         if (lane == (int)(sh + 6u)) sts_u32(waddr, word & ~(1u << (qb & 31)));
+        __syncwarp();   // orders the store before the next round's window loads of the other lanes (and the seed scan)
         p += (int)c1 - 1;
         cy += (int)r1 - 1;
         rb += ((int)r1 - 1) * ws;
