@@ -343,14 +343,16 @@ class HandleEngine:
         self.metas = metas
         self.lookahead = lookahead
 
-    def run(self, first, n_frames, ptrs, pitch, on_device):
+    def run(self, first, n_frames, ptrs, pitch, on_device, frame_index=None):
         """Frames first .. first + n_frames - 1 of every stream; returns when every frame has been collected."""
         done = [0] * len(self.h)
         errs = []
 
+        fi = frame_index or globals()["frame_index"]
+
         def drive(k):
             try:
-                idx = [frame_index(first + i) for i in range(n_frames)]
+                idx = [fi(first + i) for i in range(n_frames)]
                 ts = [timestamp(first + i) for i in range(n_frames)]
                 vps = [self.metas[k][2]] * n_frames
                 st = self.h[k].play(ts, [ptrs[k][t] for t in idx], stride=pitch, on_device=on_device, vanishing_points=vps)
@@ -403,7 +405,7 @@ def timed_pass(torch, dist, eng, first, n_frames, ptrs, pitch, on_device):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     t0 = time.perf_counter()
-    frames = eng.run(first, n_frames, ptrs, pitch, on_device)
+    frames = eng.run(first, n_frames, ptrs, pitch, on_device, frame_index=frame_index)
     torch.cuda.synchronize()
     ev1.record()
     ev1.synchronize()
@@ -587,7 +589,7 @@ def main():
 
     # ---- resident pass
     eng = make_engine(kind, fe_mod, dev, metas)
-    eng.run(0, n_warm, d_ptrs, W, True)                       # untimed: graph capture, clocks, then DRAINED (run returns when
+    eng.run(0, n_warm, d_ptrs, W, True, frame_index=frame_index)                       # untimed: graph capture, clocks, then DRAINED (run returns when
     torch.cuda.synchronize()                                   # every frame is collected)
     sampler = ClockSampler(dev) if rank == 0 else None
     res = timed_pass(torch, dist, eng, n_warm, n_timed, d_ptrs, W, True)
@@ -598,9 +600,9 @@ def main():
     stage = None
     try:
         eng.enable_timing(True)
-        eng.run(n_warm + n_timed, 8, d_ptrs, W, True)          # timing on: direct launches, first frames
+        eng.run(n_warm + n_timed, 8, d_ptrs, W, True, frame_index=frame_index)          # timing on: direct launches, first frames
         eng.stage_times(reset=True)
-        eng.run(n_warm + n_timed + 8, min(n_timed, 96), d_ptrs, W, True)
+        eng.run(n_warm + n_timed + 8, min(n_timed, 96), d_ptrs, W, True, frame_index=frame_index)
         stage = eng.stage_times(reset=False)
         eng.enable_timing(False)
     except Exception as e:   # noqa: BLE001
@@ -608,7 +610,7 @@ def main():
     eng.close()
     # ---- end to end: the same through the C ABI from pinned HOST frames
     eng = make_engine(kind, fe_mod, dev, metas)
-    eng.run(0, n_warm, h_ptrs, W, False)
+    eng.run(0, n_warm, h_ptrs, W, False, frame_index=frame_index)
     torch.cuda.synchronize()
     res_e2e = timed_pass(torch, dist, eng, n_warm, n_timed, h_ptrs, W, False)
     eng.close()
@@ -617,7 +619,7 @@ def main():
     if world == 1 and not args.no_extras:
         try:   # one pipelined stream (configs[1] alone on the GPU)
             e1 = make_engine("handles", fe_mod, dev, metas[:1])
-            e1.run(0, 128, d_ptrs[:1], W, True)
+            e1.run(0, 128, d_ptrs[:1], W, True, frame_index=frame_index)
             r1 = timed_pass(torch, None, e1, 128, 600, d_ptrs[:1], W, True)
             extras["single_stream"] = {"value": r1["frames"] / (r1["ms"] * 1e-3), "unit": "frames/s", "frames": r1["frames"],
                                        "api": "plviwo_fe_play on one handle, lookahead %d, frames resident in HBM" % e1.lookahead}
@@ -729,8 +731,21 @@ def build_roofline(stage, peak, peak_src, fps_per_gpu, res):
     if not stage or isinstance(stage, dict) and "error" in stage:
         out.update(kernel=None, achieved=0.0, frac=0.0, error=(stage or {}).get("error", "no stage times"))
         return out
-    if isinstance(stage, dict) and "kernels" in stage:    # group engine: per-kernel records straight from the library
-        ks = stage["kernels"]
+    if isinstance(stage, dict) and "group" in stage:    # stream group: per-kernel CUDA-event times from the library
+        t = stage["group"]
+        ab = algorithmic_bytes(300.0)
+        bytes_of = {"hist": ab["hist"], "eq_pyr1": ab["eq_pyr1"], "pyr_rest": ab["pyr_rest"], "fast": ab["fast"], "canny": ab["canny"],
+                    "walk": ab["fld_walk"], "lk": ab["lk"]}
+        ks = {}
+        for k, msv in t["ms"].items():
+            n, fr = t["launches"][k], t["frames_of"][k]
+            if not n or not fr:
+                continue
+            fpl = fr / n
+            a = msv / n
+            ks[k] = {"avg_ms": a, "frames_per_launch": round(fpl, 2), "algorithmic_bytes": bytes_of.get(k, 0) * fpl,
+                     "ms_per_frame": msv / fr, "GBps": bytes_of.get(k, 0) * fpl / (a * 1e-3) / 1e9 if a > 0 else 0.0}
+            ks[k]["frac"] = ks[k]["GBps"] / peak
         dom = max(ks, key=lambda k: ks[k]["ms_per_frame"]) if ks else None
         if dom:
             k = ks[dom]
@@ -738,9 +753,10 @@ def build_roofline(stage, peak, peak_src, fps_per_gpu, res):
                        algorithmic_bytes_per_launch=k["algorithmic_bytes"], frames_per_launch=k["frames_per_launch"])
         out["per_kernel"] = ks
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["kernels"]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["group_kernels"]
             if dom and tr.get(dom) is not None:
-                out["traffic"] = tr[dom]
+                out["traffic"] = tr[dom]["dram_bytes_per_frame"] * ks[dom]["frames_per_launch"]
+                out["traffic_note"] = tr[dom].get("note")
         except Exception:
             pass
         return out

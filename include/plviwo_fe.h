@@ -279,6 +279,62 @@ int plviwo_fe_stereo_get_state(FeStereoHandle *h, void *buf, size_t cap, size_t 
 int plviwo_fe_stereo_set_state(FeStereoHandle *h, const void *buf, size_t n_bytes);
 int plviwo_fe_stereo_get_stage_times(FeStereoHandle *h, FeStageTimes *out, int reset);   /* both cameras summed */
 
+/* ---- stream group: many camera streams of one device tracked together ------------------------------------ */
+/*
+ *   reference interface                                               file:line                                   replaced by
+ *   ----------------------------------------------------------------  ------------------------------------------  -----------------------------
+ *   one TrackKLT + one TrackLSD per camera, built in a loop           PL-VIWO/src/update/cam/UpdaterCamera.cpp:36-66  plviwo_fe_group_create
+ *   the bag loop feeding every camera's frame in time order           PL-VIWO/src/run_bag.cpp:56-95, 272-340      plviwo_fe_group_submit / _collect / _play
+ *   trackFEATS[cam]->feed_new_camera + trackLSDS[cam]->feed_new_camera UpdaterCamera.cpp:105-110                   (one tick = one frame of every stream)
+ *   FeatureDatabase / LineFeatureDatabase ::update_feature rows       FeatureDatabase.cpp:60-85, LineFeatureDatabase.cpp:40-76  plviwo_fe_group_get_*_rows
+ *
+ * BASELINE.json configs[4] ("64 independent camera streams, multi-session batch throughput").  Stream s of a group is what
+ * one FeHandle is — its rows are bit-identical to those of a handle fed the same frames — but the frames of all streams
+ * of a tick share their kernel launches and the tracker state lives on the device (csrc/fe_group.h).  All streams share
+ * the FeConfig (image size, knobs); the calibration is per stream.  cfg->lookahead = ticks that submit may run ahead of
+ * collect.  Not supported in a group: cfg->downsample, cfg->line_samples, set_num_features / change_feat_id.
+ */
+typedef struct FeGroupHandle FeGroupHandle;
+enum FeGroupKernel {
+  FE_GK_HIST = 0, FE_GK_EQ_PYR1, FE_GK_PYR_REST, FE_GK_FAST, FE_GK_SELECT, FE_GK_SUBPIX, FE_GK_CANNY, FE_GK_CCL, FE_GK_WALK,
+  FE_GK_SEGMENTS, FE_GK_DETECT, FE_GK_LK, FE_GK_GATE, FE_GK_LINES, FE_GK_COUNT
+};
+typedef struct FeGroupTimes {
+  double ms[16];             /* CUDA-event time per kernel (FeGroupKernel), summed over launches (timing enabled) */
+  uint64_t launches[16];
+  uint64_t frames[16];       /* frames carried by those launches                                                   */
+  uint64_t ticks, frames_total, kernel_launches_total;
+  uint64_t h2d_bytes, d2h_bytes;   /* frames copied in; rows written back to pinned host memory                    */
+} FeGroupTimes;
+
+int plviwo_fe_group_create(const FeConfig *cfg, int n_streams, int device, FeGroupHandle **out);
+int plviwo_fe_group_destroy(FeGroupHandle *g);
+const char *plviwo_fe_group_last_error(const FeGroupHandle *g);
+int plviwo_fe_group_set_calib(FeGroupHandle *g, int stream, const double K[4], const double D[4]);
+/* One tick: images[s] = frame of stream s (host or device pointer, NULL: no frame for that stream), timestamps[s] its
+ * time; masks = NULL or per-stream host pointers (NULL entries allowed); vps = NULL (line tracker not fed) or 6 doubles per
+ * stream.  Device frames are read in place and must stay valid until the tick is collected. */
+int plviwo_fe_group_submit(FeGroupHandle *g, const double *timestamps, const uint8_t *const *images, int stride, int on_device,
+                           const uint8_t *const *masks, int mask_stride, const double *vps);
+/* Completes the oldest submitted tick; infos = NULL or n_streams records (timestamp -1 for a stream without a frame). */
+int plviwo_fe_group_collect(FeGroupHandle *g, FeFrameInfo *infos);
+/* n_ticks ticks of every stream inside the library: images[t * n_streams + s], timestamps[t], vps = 6 doubles per stream
+ * (fixed) or NULL; out = n_streams records. */
+int plviwo_fe_group_play(FeGroupHandle *g, int n_ticks, const uint8_t *const *images, int stride, int on_device,
+                         const double *timestamps, const double *vps, FePlayStats *out);
+/* rows of the last collected tick */
+int plviwo_fe_group_get_point_rows(FeGroupHandle *g, int stream, FePointRow *out, int cap, int *n_out);
+int plviwo_fe_group_get_last_obs(FeGroupHandle *g, int stream, uint64_t *ids, float *uv, int cap, int *n_out);
+int plviwo_fe_group_get_line_rows(FeGroupHandle *g, int stream, FeLineRow *out, int cap, int *n_out);
+int plviwo_fe_group_get_line_points(FeGroupHandle *g, int stream, FeLinePoint *out, int cap, int *n_out);
+/* per-stream tracker state, same blob as plviwo_fe_get_state / _set_state (teacher forcing, checkpoint / resume) */
+int plviwo_fe_group_get_state(FeGroupHandle *g, int stream, void *buf, size_t cap, size_t *n_bytes);
+int plviwo_fe_group_set_state(FeGroupHandle *g, int stream, const void *buf, size_t n_bytes);
+int plviwo_fe_group_tap(FeGroupHandle *g, int stream, int what /* FE_TAP_PYR_LEVEL0 + l, FE_TAP_HALF */, void *buf, size_t cap,
+                        size_t *n_bytes);
+int plviwo_fe_group_enable_timing(FeGroupHandle *g, int on);
+int plviwo_fe_group_get_times(FeGroupHandle *g, FeGroupTimes *out, int reset);
+
 /* ---- stand-alone kernels (tests / micro-benchmarks; all pointers are HOST buffers) --------------------- */
 int plviwo_op_equalize_pyramid(int device, const uint8_t *img, int w, int h, int levels /* maxLevel */,
                                uint8_t *out_levels /* concatenated tight levels 0..maxLevel */, uint8_t *out_half);

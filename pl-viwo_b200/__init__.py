@@ -86,6 +86,16 @@ class FeStageTimes(C.Structure):
                 ("kernel_launches_total", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("host_ms", C.c_double * 16)]
 
 
+GROUP_KERNELS = ["hist", "eq_pyr1", "pyr_rest", "fast", "select", "subpix", "canny", "ccl", "walk", "segments", "detect", "lk", "gate",
+                 "lines"]
+
+
+class FeGroupTimes(C.Structure):
+    _fields_ = [("ms", C.c_double * 16), ("launches", C.c_uint64 * 16), ("frames", C.c_uint64 * 16), ("ticks", C.c_uint64),
+                ("frames_total", C.c_uint64), ("kernel_launches_total", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64)]
+
+
 POINT_ROW_DTYPE = np.dtype([("id", "<u8"), ("u", "<f4"), ("v", "<f4"), ("un", "<f4"), ("vn", "<f4")])
 LINE_ROW_DTYPE = np.dtype([("id", "<u8"), ("line", "<f4", (4,)), ("line_n", "<f4", (4,)), ("D", "<i4"), ("n_pts", "<i4"),
                            ("pt_offset", "<i4"), ("matched", "<i4")])
@@ -108,6 +118,11 @@ EXPORTS = [
     "plviwo_fe_stereo_set_state", "plviwo_fe_stereo_get_stage_times", "plviwo_fe_stereo_get_line_rows",
     "plviwo_fe_stereo_get_line_points", "plviwo_fe_stereo_classify_lines", "plviwo_op_line_match",
     "plviwo_op_assign_points",
+    "plviwo_fe_group_create", "plviwo_fe_group_destroy", "plviwo_fe_group_last_error", "plviwo_fe_group_set_calib",
+    "plviwo_fe_group_submit", "plviwo_fe_group_collect", "plviwo_fe_group_play", "plviwo_fe_group_get_point_rows",
+    "plviwo_fe_group_get_last_obs", "plviwo_fe_group_get_line_rows", "plviwo_fe_group_get_line_points",
+    "plviwo_fe_group_get_state", "plviwo_fe_group_set_state", "plviwo_fe_group_tap", "plviwo_fe_group_enable_timing",
+    "plviwo_fe_group_get_times",
 ]
 
 
@@ -182,6 +197,24 @@ def lib() -> C.CDLL:
         L.plviwo_op_image_kernels_time.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.plviwo_op_ransac_fundamental.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p,
                                                    C.POINTER(C.c_int)]
+        L.plviwo_fe_group_last_error.restype = C.c_char_p
+        L.plviwo_fe_group_last_error.argtypes = [C.c_void_p]
+        L.plviwo_fe_group_create.argtypes = [C.POINTER(FeConfig), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.plviwo_fe_group_destroy.argtypes = [C.c_void_p]
+        L.plviwo_fe_group_set_calib.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.plviwo_fe_group_submit.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                             C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_double)]
+        L.plviwo_fe_group_collect.argtypes = [C.c_void_p, C.POINTER(FeFrameInfo)]
+        L.plviwo_fe_group_play.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_double),
+                                           C.POINTER(C.c_double), C.POINTER(FePlayStats)]
+        for name in ("plviwo_fe_group_get_point_rows", "plviwo_fe_group_get_line_rows", "plviwo_fe_group_get_line_points"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.plviwo_fe_group_get_last_obs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.plviwo_fe_group_get_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.plviwo_fe_group_set_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        L.plviwo_fe_group_tap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.plviwo_fe_group_enable_timing.argtypes = [C.c_void_p, C.c_int]
+        L.plviwo_fe_group_get_times.argtypes = [C.c_void_p, C.POINTER(FeGroupTimes), C.c_int]
         _lib = L
     return _lib
 
@@ -494,6 +527,186 @@ class FrontEnd:
                 "frames": int(t.frames), "kernel_launches_total": int(t.kernel_launches_total),
                 "h2d_bytes": int(t.h2d_bytes), "d2h_bytes": int(t.d2h_bytes),
                 "host_ms": {k: t.host_ms[i] for i, k in enumerate(HOST_STAGES)}}
+
+
+# ------------------------------------------------------------------------------------------- stream group
+class GroupFrontEnd:
+    """Many camera streams of one device behind one FeGroupHandle (BASELINE.json configs[4]): stream s is one TrackKLT + one
+    TrackLSD; a tick feeds one frame of every stream."""
+
+    def __init__(self, cfg: FeConfig, n_streams: int, device: int = 0, calibs=None):
+        self.cfg = cfg
+        self.n = int(n_streams)
+        self._h = C.c_void_p()
+        self._lib = lib()
+        rc = self._lib.plviwo_fe_group_create(C.byref(cfg), self.n, device, C.byref(self._h))
+        if rc != FE_OK:
+            raise FrontEndError(rc, (self._lib.plviwo_fe_group_last_error(None) or b"").decode())
+        self.infos = (FeFrameInfo * self.n)()
+        if calibs is not None:
+            for s, (K, D) in enumerate(calibs):
+                self.set_calib(s, K, D)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.plviwo_fe_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != FE_OK:
+            raise FrontEndError(rc, (self._lib.plviwo_fe_group_last_error(self._h) or b"").decode())
+
+    def set_calib(self, stream: int, K, D):
+        self._check(self._lib.plviwo_fe_group_set_calib(self._h, stream, (C.c_double * 4)(*K), (C.c_double * 4)(*D)))
+
+    def submit(self, timestamps, images, stride: int = 0, on_device: bool = False, vanishing_points=None, masks=None):
+        """images: per stream a 2-D uint8 array / device pointer (on_device) / None (no frame for that stream in this tick);
+        vanishing_points: per stream 3 x (x, y), or None (line tracker not fed)."""
+        n = self.n
+        ptrs = (C.c_void_p * n)()
+        keep = []
+        for s, im in enumerate(images):
+            if im is None:
+                ptrs[s] = None
+            elif on_device:
+                ptrs[s] = int(im)
+            else:
+                a = im if (im.dtype == np.uint8 and im.strides[1] == 1) else np.ascontiguousarray(im, np.uint8)
+                keep.append(a)
+                ptrs[s] = a.ctypes.data
+                stride = a.strides[0]
+        ts = (C.c_double * n)(*[float(t) for t in (timestamps if hasattr(timestamps, "__len__") else [timestamps] * n)])
+        vp = None
+        if vanishing_points is not None:
+            vp = (C.c_double * (6 * n))(*[float(v) for f in vanishing_points for p in f for v in p])
+        mp, mstride = None, 0
+        if masks is not None:
+            mp = (C.c_void_p * n)()
+            for s, m in enumerate(masks):
+                if m is None:
+                    mp[s] = None
+                else:
+                    a = np.ascontiguousarray(m, np.uint8)
+                    keep.append(a)
+                    mp[s] = a.ctypes.data
+                    mstride = a.strides[0]
+        self._check(self._lib.plviwo_fe_group_submit(self._h, ts, ptrs, stride, 1 if on_device else 0, mp, mstride, vp))
+
+    def collect(self):
+        self._check(self._lib.plviwo_fe_group_collect(self._h, self.infos))
+        return self.infos
+
+    def feed(self, timestamps, images, vanishing_points=None, masks=None):
+        self.submit(timestamps, images, vanishing_points=vanishing_points, masks=masks)
+        return self.collect()
+
+    def play(self, timestamps, ptr_table, stride: int, on_device: bool, vanishing_points=None):
+        """ptr_table: ctypes array of n_ticks * n_streams pointers (tick-major); vanishing_points: per stream 3 x (x, y)."""
+        n_ticks = len(timestamps)
+        ts = (C.c_double * n_ticks)(*[float(t) for t in timestamps])
+        vp = None
+        if vanishing_points is not None:
+            vp = (C.c_double * (6 * self.n))(*[float(v) for f in vanishing_points for p in f for v in p])
+        st = (FePlayStats * self.n)()
+        self._check(self._lib.plviwo_fe_group_play(self._h, n_ticks, ptr_table, stride, 1 if on_device else 0, ts, vp, st))
+        return st
+
+    def _rows(self, fn, stream, dtype):
+        n = C.c_int(0)
+        self._check(fn(self._h, stream, None, 0, C.byref(n)))
+        out = np.zeros((n.value,), dtype)
+        if n.value:
+            self._check(fn(self._h, stream, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def point_rows(self, stream: int) -> np.ndarray:
+        return self._rows(self._lib.plviwo_fe_group_get_point_rows, stream, POINT_ROW_DTYPE)
+
+    def line_rows(self, stream: int):
+        return (self._rows(self._lib.plviwo_fe_group_get_line_rows, stream, LINE_ROW_DTYPE),
+                self._rows(self._lib.plviwo_fe_group_get_line_points, stream, LINE_POINT_DTYPE))
+
+    def last_obs(self, stream: int):
+        n = C.c_int(0)
+        self._check(self._lib.plviwo_fe_group_get_last_obs(self._h, stream, None, None, 0, C.byref(n)))
+        ids = np.zeros((n.value,), np.uint64)
+        uv = np.zeros((n.value, 2), np.float32)
+        if n.value:
+            self._check(self._lib.plviwo_fe_group_get_last_obs(self._h, stream, ids.ctypes.data, uv.ctypes.data, n.value, C.byref(n)))
+        return ids, uv
+
+    def get_state(self, stream: int) -> bytes:
+        n = C.c_size_t(0)
+        self._check(self._lib.plviwo_fe_group_get_state(self._h, stream, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        self._check(self._lib.plviwo_fe_group_get_state(self._h, stream, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value]
+
+    def set_state(self, stream: int, blob: bytes):
+        self._check(self._lib.plviwo_fe_group_set_state(self._h, stream, blob, len(blob)))
+
+    def tap(self, stream: int, what: int) -> np.ndarray:
+        n = C.c_size_t(0)
+        self._check(self._lib.plviwo_fe_group_tap(self._h, stream, what, None, 0, C.byref(n)))
+        out = np.zeros((n.value,), np.uint8)
+        if n.value:
+            self._check(self._lib.plviwo_fe_group_tap(self._h, stream, what, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def enable_timing(self, on: bool = True):
+        self._check(self._lib.plviwo_fe_group_enable_timing(self._h, 1 if on else 0))
+
+    def times(self, reset: bool = False) -> Dict[str, object]:
+        t = FeGroupTimes()
+        self._check(self._lib.plviwo_fe_group_get_times(self._h, C.byref(t), 1 if reset else 0))
+        return {"ms": {k: t.ms[i] for i, k in enumerate(GROUP_KERNELS)}, "launches": {k: int(t.launches[i]) for i, k in enumerate(GROUP_KERNELS)},
+                "frames_of": {k: int(t.frames[i]) for i, k in enumerate(GROUP_KERNELS)}, "ticks": int(t.ticks),
+                "frames": int(t.frames_total), "kernel_launches_total": int(t.kernel_launches_total),
+                "h2d_bytes": int(t.h2d_bytes), "d2h_bytes": int(t.d2h_bytes)}
+
+
+class GroupEngine:
+    """bench.py adapter: the streams of one rank behind one stream group, driven through plviwo_fe_group_play (the
+    submit / collect loop inside the library)."""
+    name = "group"
+
+    def __init__(self, fe_mod, dev, metas, workload, lookahead=None):
+        la = int(os.environ.get("PLVIWO_BENCH_GROUP_LA", "0")) or lookahead or (3 if len(metas) >= 16 else 12)
+        self.lookahead = la
+        self.metas = metas
+        self.g = GroupFrontEnd(default_config(lookahead=la, **workload), len(metas), device=dev, calibs=[(K, D) for K, D, _ in metas])
+
+    def run(self, first, n_frames, ptrs, pitch, on_device, frame_index=None):
+        S = len(self.metas)
+        fi = frame_index or (lambda i: i)
+        tab = (C.c_void_p * (n_frames * S))()
+        for i in range(n_frames):
+            t = fi(first + i)
+            for k in range(S):
+                p = ptrs[k][t]
+                tab[i * S + k] = int(p) if on_device else p.ctypes.data
+        ts = [1.0 + 0.1 * (first + i) for i in range(n_frames)]
+        st = self.g.play(ts, tab, pitch, on_device, vanishing_points=[m[2] for m in self.metas])
+        return int(sum(x.frames for x in st))
+
+    def counters(self, reset=False):
+        t = self.g.times(reset=reset)
+        return {k: t[k] for k in ("kernel_launches_total", "h2d_bytes", "d2h_bytes", "frames")}
+
+    def stage_times(self, reset=False):
+        return {"group": self.g.times(reset=reset)}
+
+    def enable_timing(self, on):
+        self.g.enable_timing(on)
+
+    def close(self):
+        self.g.close()
 
 
 # ------------------------------------------------------------------------------------------- tracker state blob

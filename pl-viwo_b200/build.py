@@ -22,12 +22,14 @@ SOURCES = [
     ("kernels_lines.cu", ["--fmad=false"]),
     ("fe_context.cu", []),
     ("fe_stereo.cu", []),
+    ("fe_group.cu", []),
+    ("kernels_glue.cu", ["--fmad=false"]),
     ("fe_capi.cu", []),
     ("ransac.cpp", []),
     ("host_simd.cpp", []),
     ("sm_partition.cpp", []),
 ]
-HEADERS = ["fe_kernels.h", "fe_context.h", "fe_stereo.h", "sm_partition.h", "tma_bulk.h", "introsort.h", os.path.join("..", "..", "include", "plviwo_fe.h")]
+HEADERS = ["fe_kernels.h", "fe_group_dev.h", "fe_group.h", "ransac_core.h", "fe_context.h", "fe_stereo.h", "sm_partition.h", "tma_bulk.h", "introsort.h", os.path.join("..", "..", "include", "plviwo_fe.h")]
 
 
 def _nvcc() -> str:

@@ -8,6 +8,7 @@
 
 #include "fe_context.h"
 #include "fe_stereo.h"
+#include "fe_group.h"
 
 using namespace plviwo;
 
@@ -17,6 +18,10 @@ struct FeHandle {
 
 struct FeStereoHandle {
   FeStereo *st;
+};
+
+struct FeGroupHandle {
+  FeGroup *grp;
 };
 
 static thread_local std::string g_create_error;
@@ -37,6 +42,14 @@ struct EnvInit {
   catch (...) {                                   \
     return FE_INTERNAL;                           \
   }
+
+static int copy_rows(const void *src, int n, size_t elem, void *out, int cap, int *n_out) {
+  if (n_out) *n_out = n;
+  if (!out) return FE_OK;
+  if (cap < n) return FE_OVERFLOW;
+  if (n) std::memcpy(out, src, (size_t)n * elem);
+  return FE_OK;
+}
 
 extern "C" {
 
@@ -704,6 +717,147 @@ int plviwo_op_line_match(int n_last, const int32_t *last_off, const int32_t *las
   for (auto &m : matches) match_out[m.first] = m.second;
   return FE_OK;
   API_END
+}
+
+// ---- stream group (many camera streams of one device, csrc/fe_group.h) ---------------------------------------------
+int plviwo_fe_group_create(const FeConfig *cfg, int n_streams, int device, FeGroupHandle **out) {
+  API_BEGIN
+  if (!cfg || !out) return FE_BAD_ARG;
+  *out = nullptr;
+  auto bad = [&](const char *why) {
+    g_create_error = why;
+    return FE_BAD_ARG;
+  };
+  if (n_streams < 1 || n_streams > 4096) return bad("n_streams must be in [1, 4096]");
+  if (cfg->width < 64 || cfg->height < 64 || cfg->width > 4095 || cfg->height > 4095) return bad("image size must be in [64, 4095]");
+  if (cfg->win_size < 3 || cfg->win_size > kMaxWin || (cfg->win_size & 1) == 0) return bad("win_size must be odd and in [3, 31]");
+  if (cfg->pyr_levels < 0 || cfg->pyr_levels >= kMaxLevels) return bad("pyr_levels must be in [0, 7]");
+  if (cfg->grid_x < 1 || cfg->grid_y < 1 || cfg->min_px_dist < 1 || cfg->num_features < 1) return bad("bad grid / distance / feature count");
+  if (cfg->grid_x * cfg->grid_y > 256) return bad("a stream group supports at most 256 grid cells");
+  if (cfg->histogram_method != FE_HIST_NONE && cfg->histogram_method != FE_HIST_HISTOGRAM && cfg->histogram_method != FE_HIST_CLAHE)
+    return bad("bad histogram_method");
+  if (cfg->downsample) return bad("cfg.downsample is not supported in a stream group");
+  if (cfg->line_samples) return bad("cfg.line_samples is not supported in a stream group");
+  if (cfg->use_lines) {
+    if ((cfg->width & 1) || (cfg->height & 1)) return bad("line tracker needs even image dimensions (exact 2x decimation)");
+    if (cfg->canny_th1 != cfg->canny_th2) return bad("canny_th1 != canny_th2: hysteresis pass is not implemented");
+    if (cfg->fld_length_threshold < 2) return bad("bad fld_length_threshold");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    g_create_error = "no CUDA device: this front end has no CPU fallback";
+    return FE_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) return bad("device index out of range");
+  FeGroup *grp = new FeGroup(*cfg, n_streams, device);
+  int rc = grp->init();
+  if (rc != FE_OK) {
+    g_create_error = grp->last_error;
+    delete grp;
+    return rc;
+  }
+  *out = new FeGroupHandle{grp};
+  return FE_OK;
+  API_END
+}
+
+int plviwo_fe_group_destroy(FeGroupHandle *g) {
+  API_BEGIN
+  if (!g) return FE_BAD_ARG;
+  delete g->grp;
+  delete g;
+  return FE_OK;
+  API_END
+}
+
+const char *plviwo_fe_group_last_error(const FeGroupHandle *g) { return g ? g->grp->last_error.c_str() : g_create_error.c_str(); }
+
+int plviwo_fe_group_set_calib(FeGroupHandle *g, int stream, const double K[4], const double D[4]) {
+  if (!g) return FE_BAD_ARG;
+  return g->grp->set_calib(stream, K, D);
+}
+
+int plviwo_fe_group_submit(FeGroupHandle *g, const double *timestamps, const uint8_t *const *images, int stride, int on_device,
+                           const uint8_t *const *masks, int mask_stride, const double *vps) {
+  API_BEGIN
+  if (!g) return FE_BAD_ARG;
+  return g->grp->submit(timestamps, images, stride, on_device != 0, masks, mask_stride, vps);
+  API_END
+}
+
+int plviwo_fe_group_collect(FeGroupHandle *g, FeFrameInfo *infos) {
+  API_BEGIN
+  if (!g) return FE_BAD_ARG;
+  return g->grp->collect(infos);
+  API_END
+}
+
+int plviwo_fe_group_play(FeGroupHandle *g, int n_ticks, const uint8_t *const *images, int stride, int on_device,
+                         const double *timestamps, const double *vps, FePlayStats *out) {
+  API_BEGIN
+  if (!g || n_ticks < 0 || !images || !timestamps) return FE_BAD_ARG;
+  return g->grp->play(n_ticks, images, stride, on_device != 0, timestamps, vps, out);
+  API_END
+}
+
+int plviwo_fe_group_get_point_rows(FeGroupHandle *g, int stream, FePointRow *out, int cap, int *n_out) {
+  if (!g) return FE_BAD_ARG;
+  const GroupOutHeader *h = g->grp->header(stream);
+  if (!h) return FE_BAD_ARG;
+  return copy_rows(g->grp->point_rows(stream), h->info.n_point_rows, sizeof(FePointRow), out, cap, n_out);
+}
+int plviwo_fe_group_get_last_obs(FeGroupHandle *g, int stream, uint64_t *ids, float *uv, int cap, int *n_out) {
+  if (!g) return FE_BAD_ARG;
+  const GroupOutHeader *h = g->grp->header(stream);
+  if (!h) return FE_BAD_ARG;
+  const int n = h->n_obs;
+  if (n_out) *n_out = n;
+  if (!ids && !uv) return FE_OK;
+  if (cap < n) return FE_OVERFLOW;
+  if (ids && n) std::memcpy(ids, g->grp->obs_ids(stream), (size_t)n * sizeof(uint64_t));
+  if (uv && n) std::memcpy(uv, g->grp->obs_uv(stream), (size_t)n * 2 * sizeof(float));
+  return FE_OK;
+}
+int plviwo_fe_group_get_line_rows(FeGroupHandle *g, int stream, FeLineRow *out, int cap, int *n_out) {
+  if (!g) return FE_BAD_ARG;
+  const GroupOutHeader *h = g->grp->header(stream);
+  if (!h) return FE_BAD_ARG;
+  return copy_rows(g->grp->line_rows(stream), h->info.n_line_rows, sizeof(FeLineRow), out, cap, n_out);
+}
+int plviwo_fe_group_get_line_points(FeGroupHandle *g, int stream, FeLinePoint *out, int cap, int *n_out) {
+  if (!g) return FE_BAD_ARG;
+  const GroupOutHeader *h = g->grp->header(stream);
+  if (!h) return FE_BAD_ARG;
+  return copy_rows(g->grp->line_points(stream), h->info.n_line_rows > 0 ? h->n_line_points : 0, sizeof(FeLinePoint), out, cap, n_out);
+}
+int plviwo_fe_group_get_state(FeGroupHandle *g, int stream, void *buf, size_t cap, size_t *n_bytes) {
+  API_BEGIN
+  if (!g) return FE_BAD_ARG;
+  return g->grp->get_state(stream, buf, cap, n_bytes);
+  API_END
+}
+int plviwo_fe_group_set_state(FeGroupHandle *g, int stream, const void *buf, size_t n_bytes) {
+  API_BEGIN
+  if (!g) return FE_BAD_ARG;
+  return g->grp->set_state(stream, buf, n_bytes);
+  API_END
+}
+int plviwo_fe_group_tap(FeGroupHandle *g, int stream, int what, void *buf, size_t cap, size_t *n_bytes) {
+  API_BEGIN
+  if (!g) return FE_BAD_ARG;
+  return g->grp->tap(stream, what, buf, cap, n_bytes);
+  API_END
+}
+int plviwo_fe_group_enable_timing(FeGroupHandle *g, int on) {
+  if (!g) return FE_BAD_ARG;
+  g->grp->enable_timing(on != 0);
+  return FE_OK;
+}
+int plviwo_fe_group_get_times(FeGroupHandle *g, FeGroupTimes *out, int reset) {
+  if (!g || !out) return FE_BAD_ARG;
+  *out = g->grp->times(reset != 0);
+  return FE_OK;
 }
 
 // ---- stereo rig (TrackKLT with use_stereo = true) -----------------------------------------------------------

@@ -158,6 +158,8 @@ struct FldBatch {
   int n = 0;
   DevImage half[kMaxLineBatch];
   FldBuffers f[kMaxLineBatch];
+  __host__ __device__ const DevImage &half_of(int k) const { return half[k]; }
+  __host__ __device__ const FldBuffers &fld_of(int k) const { return f[k]; }
 };
 void launch_canny_batch(const FldBatch &b, float th_low, float th_high, cudaStream_t s);
 void launch_fld_batch(const FldBatch &b, int length_threshold, float distance_threshold, cudaStream_t s, cudaEvent_t *ev = nullptr);
@@ -207,6 +209,14 @@ void launch_pyr_level_batch(const SlotRec *slots, const FrontJob *jobs, int n_jo
 void launch_fast_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, const FrontGeom &g, cudaStream_t s);
 void launch_fast_select_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, const FrontGeom &g, cudaStream_t s);
 void launch_corner_subpix_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, const FrontGeom &g, cudaStream_t s);
+// The line kernels take either a FldBatch by value (a few frames of one handle) or this view of the slot table
+// (entry k of the launch = slot idx[k]); same kernel bodies, instantiated for both.
+struct FldTable {
+  const SlotRec *slots;
+  const int *idx;
+  __device__ const DevImage &half_of(int k) const { return slots[idx[k]].half; }
+  __device__ const FldBuffers &fld_of(int k) const { return slots[idx[k]].fld; }
+};
 // Line paths of n_jobs frames; line_slots: device array of slot indices.  ev as launch_fld.
 void launch_canny_table(const SlotRec *slots, const int *line_slots, int n_jobs, int w, int h, float th_low, cudaStream_t s);
 void launch_fld_table(const SlotRec *slots, const int *line_slots, int n_jobs, int w, int h, int max_chains, int length_threshold,

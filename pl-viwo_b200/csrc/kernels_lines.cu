@@ -31,12 +31,13 @@ namespace plviwo {
 // ------------------------------------------------------------------------------------------------ Canny
 constexpr int kCnW = 64, kCnH = 16, kCnThreads = 256;
 
+template <class B>
 __global__ void __launch_bounds__(kCnThreads)
-    k_canny(const __grid_constant__ FldBatch b, int low) {
-  const uint8_t *__restrict__ img = b.half[blockIdx.z].p;
-  const int w = b.half[blockIdx.z].w, h = b.half[blockIdx.z].h, pitch = b.half[blockIdx.z].pitch;
-  unsigned *__restrict__ edges = b.f[blockIdx.z].edges;
-  const int words_per_row = b.f[blockIdx.z].words_per_row;
+    k_canny(const __grid_constant__ B b, int low) {
+  const uint8_t *__restrict__ img = b.half_of(blockIdx.z).p;
+  const int w = b.half_of(blockIdx.z).w, h = b.half_of(blockIdx.z).h, pitch = b.half_of(blockIdx.z).pitch;
+  unsigned *__restrict__ edges = b.fld_of(blockIdx.z).edges;
+  const int words_per_row = b.fld_of(blockIdx.z).words_per_row;
   __shared__ uint8_t pix[kCnH + 4][kCnW + 4];
   __shared__ short sdx[kCnH + 2][kCnW + 2];
   __shared__ short sdy[kCnH + 2][kCnW + 2];
@@ -101,11 +102,19 @@ __global__ void __launch_bounds__(kCnThreads)
   }
 }
 
+template <class B>
+static void launch_canny_any(const B &b, int n, int w, int h, float th_low, cudaStream_t s) {
+  dim3 grid((w + kCnW - 1) / kCnW, (h + kCnH - 1) / kCnH, n);
+  PLVIWO_CARVEOUT(k_canny<B>);
+  k_canny<B><<<grid, kCnThreads, 0, s>>>(b, (int)floorf(th_low));
+}
 void launch_canny_batch(const FldBatch &b, float th_low, float th_high, cudaStream_t s) {
   (void)th_high;  // low == high is enforced at create time (no hysteresis pass is implemented)
-  dim3 grid((b.half[0].w + kCnW - 1) / kCnW, (b.half[0].h + kCnH - 1) / kCnH, b.n);
-  PLVIWO_CARVEOUT(k_canny);
-  k_canny<<<grid, kCnThreads, 0, s>>>(b, (int)floorf(th_low));
+  launch_canny_any(b, b.n, b.half[0].w, b.half[0].h, th_low, s);
+}
+void launch_canny_table(const SlotRec *slots, const int *line_slots, int n_jobs, int w, int h, float th_low, cudaStream_t s) {
+  if (n_jobs <= 0) return;
+  launch_canny_any(FldTable{slots, line_slots}, n_jobs, w, h, th_low, s);
 }
 void launch_canny(const DevImage &half, float th_low, float th_high, FldBuffers &fb, cudaStream_t s) {
   FldBatch b;
@@ -147,8 +156,9 @@ __device__ __forceinline__ void ccl_union(int *parent, int a, int b) {
   }
 }
 
-__global__ void k_ccl_init(const __grid_constant__ FldBatch b, int w, int h) {
-  const FldBuffers &fb = b.f[blockIdx.y];
+template <class B>
+__global__ void k_ccl_init(const __grid_constant__ B b, int w, int h) {
+  const FldBuffers &fb = b.fld_of(blockIdx.y);
   const unsigned *__restrict__ edges = fb.edges;
   const int words_per_row = fb.words_per_row;
   int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt, *__restrict__ bbox = fb.bbox /* maxy, minx, maxx planes */;
@@ -165,8 +175,9 @@ __global__ void k_ccl_init(const __grid_constant__ FldBatch b, int w, int h) {
   bbox[2 * w * h + i] = -1;    // max x
 }
 
-__global__ void k_ccl_merge(const __grid_constant__ FldBatch b, int w, int h) {
-  int *__restrict__ label = b.f[blockIdx.y].label;
+template <class B>
+__global__ void k_ccl_merge(const __grid_constant__ B b, int w, int h) {
+  int *__restrict__ label = b.fld_of(blockIdx.y).label;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= w * h) return;
   if (label[i] < 0) return;
@@ -181,8 +192,9 @@ __global__ void k_ccl_merge(const __grid_constant__ FldBatch b, int w, int h) {
 }
 
 // flatten + per-component pixel count and bounding box (warp-aggregated atomics keyed by the root)
-__global__ void k_ccl_flatten(const __grid_constant__ FldBatch b, int w, int h) {
-  int *__restrict__ label = b.f[blockIdx.y].label, *__restrict__ cnt = b.f[blockIdx.y].cnt, *__restrict__ bbox = b.f[blockIdx.y].bbox;
+template <class B>
+__global__ void k_ccl_flatten(const __grid_constant__ B b, int w, int h) {
+  int *__restrict__ label = b.fld_of(blockIdx.y).label, *__restrict__ cnt = b.fld_of(blockIdx.y).cnt, *__restrict__ bbox = b.fld_of(blockIdx.y).bbox;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int root = -1;
   if (i < w * h && label[i] >= 0) {
@@ -211,8 +223,9 @@ constexpr int kClassA = 1024, kClassB = 128;   // pixels
 __host__ __device__ inline int comp_cap_a(int n) { return n / kClassA + 1; }
 __host__ __device__ inline int comp_cap_b(int n) { return n / kClassB + 1; }
 
-__global__ void k_ccl_roots(const __grid_constant__ FldBatch b, int w, int h, int min_pixels) {
-  const FldBuffers &fb = b.f[blockIdx.y];
+template <class B>
+__global__ void k_ccl_roots(const __grid_constant__ B b, int w, int h, int min_pixels) {
+  const FldBuffers &fb = b.fld_of(blockIdx.y);
   const int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt;
   int *__restrict__ comp_root = fb.comp_root, *__restrict__ counters = fb.counters;
   const int max_comps = fb.max_chains;
@@ -329,9 +342,10 @@ __device__ __forceinline__ void sts_u32(unsigned addr, unsigned v) {
 // PREVIOUS pixel (shift, 11-bit key, one table look-up).  The dependent chain of a step is
 // shift -> key -> table load -> decode, ~90 cycles; the first version (one thread, 6 loads + ~150 instructions per
 // step) needed ~600.
+template <class B>
 __global__ void __launch_bounds__(kWalkThreads)
-    k_fld_walk_cc(const __grid_constant__ FldBatch b, int w, int h, int length_threshold) {
-  const FldBuffers &fb = b.f[blockIdx.y];
+    k_fld_walk_cc(const __grid_constant__ B b, int w, int h, int length_threshold) {
+  const FldBuffers &fb = b.fld_of(blockIdx.y);
   const unsigned *__restrict__ edges = fb.edges;
   const int words_per_row = fb.words_per_row;
   const int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt, *__restrict__ bbox = fb.bbox;
@@ -528,8 +542,9 @@ __global__ void __launch_bounds__(kWalkThreads)
 }
 
 // rank of every chain by the raster index of its seed (seeds are distinct pixels): order[rank] = chain
-__global__ void k_fld_order(const __grid_constant__ FldBatch b) {
-  const FldBuffers &fb = b.f[blockIdx.y];
+template <class B>
+__global__ void k_fld_order(const __grid_constant__ B b) {
+  const FldBuffers &fb = b.fld_of(blockIdx.y);
   const int *__restrict__ chain_seed = fb.chain_seed, *__restrict__ counters = fb.counters;
   int *__restrict__ order = fb.order;
   const int max_chains = fb.max_chains;
@@ -591,10 +606,11 @@ __device__ __forceinline__ void incident_point(const double l[3], float &px, flo
 
 // one thread per chain, in seed order; chain c writes its segments to slots chain_off[c] / 21 + j (collision free:
 // every segment consumes at least 21 chain points and the chains' point ranges are disjoint)
-__global__ void k_fld_segments(const __grid_constant__ FldBatch b, int T, float dist_thr) {
-  const FldBuffers &fb = b.f[blockIdx.y];
-  const uint8_t *__restrict__ img = b.half[blockIdx.y].p;
-  const int W = b.half[blockIdx.y].w, H = b.half[blockIdx.y].h, pitch = b.half[blockIdx.y].pitch;
+template <class B>
+__global__ void k_fld_segments(const __grid_constant__ B b, int T, float dist_thr) {
+  const FldBuffers &fb = b.fld_of(blockIdx.y);
+  const uint8_t *__restrict__ img = b.half_of(blockIdx.y).p;
+  const int W = b.half_of(blockIdx.y).w, H = b.half_of(blockIdx.y).h, pitch = b.half_of(blockIdx.y).pitch;
   const int2 *__restrict__ chain_pts = fb.chain_pts;
   const int *__restrict__ chain_off = fb.chain_off, *__restrict__ chain_len = fb.chain_len, *__restrict__ order = fb.order;
   const int *__restrict__ counters = fb.counters;
@@ -688,9 +704,10 @@ __global__ void k_fld_segments(const __grid_constant__ FldBatch b, int T, float 
 }
 
 // ordered compaction of the per-chain segment slots (one block)
+template <class B>
 __global__ void __launch_bounds__(256)
-    k_fld_compact(const __grid_constant__ FldBatch b) {
-  const FldBuffers &fb = b.f[blockIdx.y];
+    k_fld_compact(const __grid_constant__ B b) {
+  const FldBuffers &fb = b.fld_of(blockIdx.y);
   const float4 *__restrict__ segs = fb.segs;
   const int *__restrict__ seg_cnt = fb.seg_cnt, *__restrict__ seg_base = fb.seg_cnt + fb.max_chains;
   int *__restrict__ counters = fb.counters;
@@ -757,41 +774,50 @@ void FldBuffers::release() {
   *this = FldBuffers();
 }
 
-void launch_fld_batch(const FldBatch &b, int length_threshold, float distance_threshold, cudaStream_t s, cudaEvent_t *ev) {
-  const int w = b.half[0].w, h = b.half[0].h, n = w * h;
+template <class B>
+static void launch_fld_any(const B &b, int nb_frames, int w, int h, int max_chains, int length_threshold, float distance_threshold,
+                           cudaStream_t s, cudaEvent_t *ev) {
+  const int n = w * h;
   const int tpb = 256, nb = (n + tpb - 1) / tpb;
-  const int max_chains = b.f[0].max_chains;
-  const dim3 gpx(nb, b.n);
-  PLVIWO_CARVEOUT(k_ccl_init);
-  k_ccl_init<<<gpx, tpb, 0, s>>>(b, w, h);
-  PLVIWO_CARVEOUT(k_ccl_merge);
-  k_ccl_merge<<<gpx, tpb, 0, s>>>(b, w, h);
-  PLVIWO_CARVEOUT(k_ccl_flatten);
-  k_ccl_flatten<<<gpx, tpb, 0, s>>>(b, w, h);
-  PLVIWO_CARVEOUT(k_ccl_roots);
-  k_ccl_roots<<<gpx, tpb, 0, s>>>(b, w, h, length_threshold + 1);
+  const dim3 gpx(nb, nb_frames);
+  PLVIWO_CARVEOUT(k_ccl_init<B>);
+  k_ccl_init<B><<<gpx, tpb, 0, s>>>(b, w, h);
+  PLVIWO_CARVEOUT(k_ccl_merge<B>);
+  k_ccl_merge<B><<<gpx, tpb, 0, s>>>(b, w, h);
+  PLVIWO_CARVEOUT(k_ccl_flatten<B>);
+  k_ccl_flatten<B><<<gpx, tpb, 0, s>>>(b, w, h);
+  PLVIWO_CARVEOUT(k_ccl_roots<B>);
+  k_ccl_roots<B><<<gpx, tpb, 0, s>>>(b, w, h, length_threshold + 1);
   if (ev) cudaEventRecord(ev[0], s);
   init_fld_constants();
   const int ws = ((w + 31) >> 5) + 2;
   size_t smem = (size_t)kLutSize + (size_t)(h + 2 * kPadRows) * ws * sizeof(unsigned);
   static SmemOptIn optin;
-  optin.ensure(k_fld_walk_cc, smem);
+  optin.ensure(k_fld_walk_cc<B>, smem);
   // Grid size per frame: the walk is bound by its longest component (a sequential chain of ~130-cycle steps), not by the
   // number of walkers; a batch of frames shares one launch (grid.y = frame).  PLVIWO_WALK_CTAS overrides.
   static const int walk_ctas_env = [] {
     const char *e = std::getenv("PLVIWO_WALK_CTAS");
     return e ? std::atoi(e) : 0;
   }();
-  const int walk_ctas = walk_ctas_env > 0 ? walk_ctas_env : (b.n > 1 ? 148 : kWalkCtas);
-  PLVIWO_CARVEOUT(k_fld_walk_cc);
-  k_fld_walk_cc<<<dim3(walk_ctas, b.n), kWalkThreads, smem, s>>>(b, w, h, length_threshold);
+  const int walk_ctas = walk_ctas_env > 0 ? walk_ctas_env : (nb_frames > 8 ? 64 : (nb_frames > 1 ? 148 : kWalkCtas));
+  PLVIWO_CARVEOUT(k_fld_walk_cc<B>);
+  k_fld_walk_cc<B><<<dim3(walk_ctas, nb_frames), kWalkThreads, smem, s>>>(b, w, h, length_threshold);
   if (ev) cudaEventRecord(ev[1], s);
-  PLVIWO_CARVEOUT(k_fld_order);
-  k_fld_order<<<dim3((max_chains + 127) / 128, b.n), 128, 0, s>>>(b);
-  PLVIWO_CARVEOUT(k_fld_segments);
-  k_fld_segments<<<dim3((max_chains + 63) / 64, b.n), 64, 0, s>>>(b, length_threshold, distance_threshold);
-  PLVIWO_CARVEOUT(k_fld_compact);
-  k_fld_compact<<<dim3(1, b.n), 256, 0, s>>>(b);
+  PLVIWO_CARVEOUT(k_fld_order<B>);
+  k_fld_order<B><<<dim3((max_chains + 127) / 128, nb_frames), 128, 0, s>>>(b);
+  PLVIWO_CARVEOUT(k_fld_segments<B>);
+  k_fld_segments<B><<<dim3((max_chains + 63) / 64, nb_frames), 64, 0, s>>>(b, length_threshold, distance_threshold);
+  PLVIWO_CARVEOUT(k_fld_compact<B>);
+  k_fld_compact<B><<<dim3(1, nb_frames), 256, 0, s>>>(b);
+}
+void launch_fld_batch(const FldBatch &b, int length_threshold, float distance_threshold, cudaStream_t s, cudaEvent_t *ev) {
+  launch_fld_any(b, b.n, b.half[0].w, b.half[0].h, b.f[0].max_chains, length_threshold, distance_threshold, s, ev);
+}
+void launch_fld_table(const SlotRec *slots, const int *line_slots, int n_jobs, int w, int h, int max_chains, int length_threshold,
+                      float distance_threshold, cudaStream_t s, cudaEvent_t *ev) {
+  if (n_jobs <= 0) return;
+  launch_fld_any(FldTable{slots, line_slots}, n_jobs, w, h, max_chains, length_threshold, distance_threshold, s, ev);
 }
 
 void launch_fld(const DevImage &half, int length_threshold, float distance_threshold, FldBuffers &fb, cudaStream_t s,

@@ -7,6 +7,7 @@
 //   cv::calcOpticalFlowPyrLK(.., win, maxLevel, {COUNT|EPS, 30, 0.01}, USE_INITIAL_FLOW)  TrackKLT.cpp:855-858
 //   CamRadtan::undistort_f -> cv::undistortPoints (one Mat per point)               cam/CamRadtan.h:99-120
 #include "fe_kernels.h"
+#include "fe_group_dev.h"
 
 #include <algorithm>
 #include <mutex>
@@ -46,9 +47,8 @@ constexpr int kSpWarps = 4;
 __constant__ float c_subpix_mask[kSpW * kSpW];
 static bool g_subpix_mask_ready[64] = {false};
 
-__global__ void __launch_bounds__(kSpWarps * 32)
-    k_corner_subpix(const uint8_t *__restrict__ img, int w, int h, int pitch, const float2 *pts_in, float2 *pts, int n,
-                    const int *__restrict__ cnt, int stride) {
+__device__ __forceinline__ void corner_subpix_body(const uint8_t *__restrict__ img, int w, int h, int pitch, const float2 *pts_in,
+                                                   float2 *pts, int n, const int *__restrict__ cnt, int stride) {
   __shared__ float patch_s[kSpWarps][kSpP * kSpP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pi = blockIdx.x * kSpWarps + warp;
@@ -106,6 +106,18 @@ __global__ void __launch_bounds__(kSpWarps * 32)
   if (lane == 0) pts[pi] = cI;
 }
 
+__global__ void __launch_bounds__(kSpWarps * 32)
+    k_corner_subpix(const uint8_t *__restrict__ img, int w, int h, int pitch, const float2 *pts_in, float2 *pts, int n,
+                    const int *__restrict__ cnt, int stride) {
+  corner_subpix_body(img, w, h, pitch, pts_in, pts, n, cnt, stride);
+}
+// grid = (points, job): the fixed-stride candidate table of every job's slot
+__global__ void __launch_bounds__(kSpWarps * 32)
+    k_corner_subpix_b(const SlotRec *__restrict__ slots, const FrontJob *__restrict__ jobs, int n, int stride) {
+  const SlotRec &sl = slots[jobs[blockIdx.y].slot];
+  corner_subpix_body(sl.lvl[0].p, sl.lvl[0].w, sl.lvl[0].h, sl.lvl[0].pitch, sl.cand, sl.cand_ref, n, sl.cand_cnt, stride);
+}
+
 void init_device_constants() {
   DevImage dummy;
   launch_corner_subpix(dummy, nullptr, nullptr, -1, 0);
@@ -137,6 +149,14 @@ void launch_corner_subpix(const DevImage &img, const float2 *d_in, float2 *d_out
   PLVIWO_CARVEOUT(k_corner_subpix);
   k_corner_subpix<<<(n + kSpWarps - 1) / kSpWarps, kSpWarps * 32, 0, s>>>(img.p, img.w, img.h, img.pitch, d_in, d_out, n, d_cnt,
                                                                           stride);
+}
+
+void launch_corner_subpix_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, const FrontGeom &g, cudaStream_t s) {
+  const int n = g.n_cells * g.nfg;
+  if (n_jobs <= 0 || n <= 0) return;
+  launch_corner_subpix(DevImage(), nullptr, nullptr, -1, 0);   // constant table of this device
+  PLVIWO_CARVEOUT(k_corner_subpix_b);
+  k_corner_subpix_b<<<dim3((n + kSpWarps - 1) / kSpWarps, n_jobs), kSpWarps * 32, 0, s>>>(slots, jobs, n, g.nfg);
 }
 
 // ============================================================================================== undistort
@@ -196,9 +216,9 @@ struct LkArgs {
   CalibArgs calib;
 };
 
-__global__ void __launch_bounds__(kLkWarps * 32)
-    k_lk(LkArgs a, const float2 *__restrict__ pts0, float2 *__restrict__ pts1, uint8_t *__restrict__ status,
-         float2 *__restrict__ p0n, float2 *__restrict__ p1n, int n) {
+template <class Args>
+__device__ __forceinline__ void lk_body(const Args &a, const float2 *__restrict__ pts0, float2 *__restrict__ pts1,
+                                        uint8_t *__restrict__ status, float2 *__restrict__ p0n, float2 *__restrict__ p1n, int n) {
   extern __shared__ __align__(16) uint8_t lk_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pi = blockIdx.x * kLkWarps + warp;
@@ -221,7 +241,7 @@ __global__ void __launch_bounds__(kLkWarps * 32)
   short *Iyw = reinterpret_cast<short *>(base + raw_bytes + 2 * d_bytes + 2 * w_bytes);
 
   const float2 prev_in = pts0[pi];
-  float2 next = pts1[pi];   // OPTFLOW_USE_INITIAL_FLOW
+  float2 next = a.flow_is_zero ? prev_in : pts1[pi];   // OPTFLOW_USE_INITIAL_FLOW
   bool ok = true;
   const float half = (win - 1) * 0.5f;
   const float FLT_SCALE = 1.f / (1 << 20);
@@ -375,6 +395,12 @@ __global__ void __launch_bounds__(kLkWarps * 32)
   }
 }
 
+__global__ void __launch_bounds__(kLkWarps * 32)
+    k_lk(LkArgs a, const float2 *__restrict__ pts0, float2 *__restrict__ pts1, uint8_t *__restrict__ status,
+         float2 *__restrict__ p0n, float2 *__restrict__ p1n, int n) {
+  lk_body(a, pts0, pts1, status, p0n, p1n, n);
+}
+
 // ------------------------------------------------------------------------------------------ LK, 15 x 15 window
 // Specialisation for the reference's window (TrackKLT.h:144): ONE CTA PER FEATURE, one warp per pyramid level.
 //
@@ -402,10 +428,11 @@ constexpr int kJSpan = kW15 + 2;    // rows / columns a window touches: 15 + 1 (
 constexpr int kJR = kJSpan + 2 * kJMargin;   // 25
 constexpr int kChainWarps = 4;      // warps that share one feature's iteration chain
 
-__global__ void __launch_bounds__(kLk15MaxLevels * 32)
-    k_lk15(LkArgs a, const float2 *__restrict__ pts0, float2 *__restrict__ pts1, uint8_t *__restrict__ status,
-           float2 *__restrict__ p0n, float2 *__restrict__ p1n, int n, int *host_flag, int flag_value, unsigned *done_counter,
-           const int *__restrict__ tab_cnt, int tab_stride) {
+template <class Args>
+__device__ __forceinline__ void lk15_body(const Args &a, const float2 *__restrict__ pts0, float2 *__restrict__ pts1,
+                                          uint8_t *__restrict__ status, float2 *__restrict__ p0n, float2 *__restrict__ p1n, int n,
+                                          int *host_flag, int flag_value, unsigned *done_counter, const int *__restrict__ tab_cnt,
+                                          int tab_stride) {
   constexpr int win = kW15, np = win + 3, nd = win + 1;
   constexpr int kRawLoads = (np * np + 31) / 32;   // 11
   __shared__ uint8_t raw_s[kLk15MaxLevels][np * np + 12];
@@ -709,6 +736,84 @@ __global__ void __launch_bounds__(kLk15MaxLevels * 32)
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(kLk15MaxLevels * 32)
+    k_lk15(LkArgs a, const float2 *__restrict__ pts0, float2 *__restrict__ pts1, uint8_t *__restrict__ status,
+           float2 *__restrict__ p0n, float2 *__restrict__ p1n, int n, int *host_flag, int flag_value, unsigned *done_counter,
+           const int *__restrict__ tab_cnt, int tab_stride) {
+  lk15_body(a, pts0, pts1, status, p0n, p1n, n, host_flag, flag_value, done_counter, tab_cnt, tab_stride);
+}
+
+// ---- stream group: the points of every stream of a tracking launch in ONE launch (grid.y = job).  The arguments of a job
+// (pyramids of its previous and current slot, calibration in force) are assembled in shared memory; the per-feature work is
+// the body above, so a stream's tracks are bit-identical to those of a single handle.
+__device__ __forceinline__ void group_lk_args(LkArgs &a, const GroupDev &g, const TrackJob &job, const LkParams &prm) {
+  const SlotRec &s0 = g.slots[job.prev_slot], &s1 = g.slots[job.cur_slot];
+  int levels = prm.max_level + 1;
+  if (levels > s0.n_lvl) levels = s0.n_lvl;
+  for (int l = 0; l < levels; l++) {
+    a.p0[l] = s0.lvl[l].p;
+    a.p1[l] = s1.lvl[l].p;
+    a.w[l] = s0.lvl[l].w;
+    a.h[l] = s0.lvl[l].h;
+    a.pitch0[l] = s0.lvl[l].pitch;
+    a.pitch1[l] = s1.lvl[l].pitch;
+  }
+  a.win = prm.win;
+  a.max_level = levels - 1;
+  a.max_count = prm.max_count;
+  a.eps_sq = prm.eps_sq;
+  a.min_eig = prm.min_eig;
+  a.undistort = 1;
+  a.flow_is_zero = 1;   // pts_new = pts_old (TrackKLT.cpp:134)
+  for (int i = 0; i < 8; i++) a.cell_mask[i] = 0xffffffffu;
+  for (int i = 0; i < 4; i++) {
+    a.calib.K[i] = job.K[i];
+    a.calib.D[i] = job.D[i];
+  }
+}
+
+__global__ void __launch_bounds__(kLk15MaxLevels * 32)
+    k_lk15_g(const __grid_constant__ GroupDev g, const TrackJob *__restrict__ jobs, const __grid_constant__ LkParams prm) {
+  __shared__ LkArgs sa;
+  const TrackJob &job = jobs[blockIdx.y];
+  const int s = job.stream;
+  const int n = g.wn[s];
+  if (g.wmode[s] != 0 || n < 10 || (int)blockIdx.x >= n) return;   // TrackKLT.cpp:848-852: fewer than 10 points are not tracked
+  if (threadIdx.x == 0) group_lk_args(sa, g, job, prm);
+  __syncthreads();
+  const size_t o = (size_t)s * g.pts_cap;
+  lk15_body(sa, g.wpts + o, g.lk_pts1 + o, g.lk_status + o, g.lk_p0n + o, g.lk_p1n + o, n, nullptr, 0, nullptr, nullptr, 0);
+}
+__global__ void __launch_bounds__(kLkWarps * 32)
+    k_lk_g(const __grid_constant__ GroupDev g, const TrackJob *__restrict__ jobs, const __grid_constant__ LkParams prm) {
+  __shared__ LkArgs sa;
+  const TrackJob &job = jobs[blockIdx.y];
+  const int s = job.stream;
+  const int n = g.wn[s];
+  if (g.wmode[s] != 0 || n < 10 || (int)blockIdx.x * kLkWarps >= n) return;
+  if (threadIdx.x == 0) group_lk_args(sa, g, job, prm);
+  __syncthreads();
+  const size_t o = (size_t)s * g.pts_cap;
+  lk_body(sa, g.wpts + o, g.lk_pts1 + o, g.lk_status + o, g.lk_p0n + o, g.lk_p1n + o, n);
+}
+
+void launch_group_lk(const GroupDev &g, const TrackJob *jobs, int n_jobs, const LkParams &prm, cudaStream_t s) {
+  if (n_jobs <= 0) return;
+  if (prm.win == kW15 && prm.max_level + 1 <= kLk15MaxLevels) {
+    const int levels = prm.max_level + 1;
+    PLVIWO_CARVEOUT(k_lk15_g);
+    k_lk15_g<<<dim3(g.pts_cap, n_jobs), std::max(levels, kChainWarps) * 32, 0, s>>>(g, jobs, prm);
+    return;
+  }
+  const int win = prm.win, np = win + 3, nd = win + 1, nw = win * win;
+  const int per_warp = ((np * np + 15) & ~15) + 2 * ((nd * nd * 2 + 15) & ~15) + 3 * ((nw * 2 + 15) & ~15);
+  const size_t smem = (size_t)per_warp * kLkWarps;
+  static SmemOptIn optin;
+  optin.ensure(k_lk_g, smem);
+  PLVIWO_CARVEOUT(k_lk_g);
+  k_lk_g<<<dim3((g.pts_cap + kLkWarps - 1) / kLkWarps, n_jobs), kLkWarps * 32, smem, s>>>(g, jobs, prm);
 }
 
 bool lk_table_mode_ok(const LkParams &prm, int pyramid_images) {
