@@ -297,7 +297,7 @@ int plviwo_fe_stereo_get_stage_times(FeStereoHandle *h, FeStageTimes *out, int r
 typedef struct FeGroupHandle FeGroupHandle;
 enum FeGroupKernel {
   FE_GK_HIST = 0, FE_GK_EQ_PYR1, FE_GK_PYR_REST, FE_GK_FAST, FE_GK_SELECT, FE_GK_SUBPIX, FE_GK_CANNY, FE_GK_CCL, FE_GK_WALK,
-  FE_GK_SEGMENTS, FE_GK_DETECT, FE_GK_LK, FE_GK_GATE, FE_GK_LINES, FE_GK_COUNT
+  FE_GK_SEGMENTS, FE_GK_DETECT, FE_GK_LK, FE_GK_GATE, FE_GK_LINES, FE_GK_ACCEPT, FE_GK_COUNT
 };
 typedef struct FeGroupTimes {
   double ms[16];             /* CUDA-event time per kernel (FeGroupKernel), summed over launches (timing enabled) */
@@ -342,8 +342,9 @@ int plviwo_op_clahe(int device, const uint8_t *img, int w, int h, uint8_t *out /
 int plviwo_op_fast_cell(int device, const uint8_t *img, int w, int h, int threshold, int32_t *xys /* x y score */,
                         int cap, int *n_out);
 /* std::sort(corners, compare_response) + first nfg (Grider_GRID.h:128-133) on packed corners x | y << 12 | score << 24.
- * device < 0: the host instantiation of the sort (sorted[] = whole sorted list); device >= 0: the selection kernel
- * (cand[] = x, y of the survivors, n_cand of them; sorted may be NULL). */
+ * device < 0: the host instantiation of the sort (sorted[] = whole sorted list; cand, if not NULL, = x, y of the first nfg
+ * elements as the pruned selection the kernel runs computes them); device >= 0: the selection kernel (cand[] = x, y of
+ * the survivors, n_cand of them; sorted may be NULL). */
 int plviwo_op_sort_corners(int device, const uint32_t *packed, int n, int nfg, uint32_t *sorted, float *cand, int *n_cand);
 int plviwo_op_corner_subpix(int device, const uint8_t *img, int w, int h, float *pts /* in/out 2 per point */, int n);
 int plviwo_op_lk(int device, const uint8_t *img0, const uint8_t *img1, int w, int h, int win, int max_level,

@@ -87,7 +87,7 @@ class FeStageTimes(C.Structure):
 
 
 GROUP_KERNELS = ["hist", "eq_pyr1", "pyr_rest", "fast", "select", "subpix", "canny", "ccl", "walk", "segments", "detect", "lk", "gate",
-                 "lines"]
+                 "lines", "accept"]
 
 
 class FeGroupTimes(C.Structure):
@@ -987,14 +987,17 @@ def op_fast_cell(img: np.ndarray, threshold: int, device: int = 0) -> np.ndarray
     return out[:n.value].copy()
 
 
-def op_sort_corners(packed: np.ndarray, nfg: int, device: int = -1):
+def op_sort_corners(packed: np.ndarray, nfg: int, device: int = -1, prefix: bool = False):
     """Grider_GRID.h:128-133 on packed corners (x | y << 12 | score << 24).  device < 0: host instantiation, returns the
     whole sorted list; device >= 0: the selection kernel, returns the (x, y) of the first nfg."""
     packed = np.ascontiguousarray(packed, np.uint32)
     n = C.c_int(0)
     if device < 0:
         out = np.empty_like(packed)
-        _check(lib().plviwo_op_sort_corners(device, packed.ctypes.data, len(packed), nfg, out.ctypes.data, None, C.byref(n)))
+        pre = np.zeros((nfg, 2), np.float32)
+        _check(lib().plviwo_op_sort_corners(device, packed.ctypes.data, len(packed), nfg, out.ctypes.data, pre.ctypes.data, C.byref(n)))
+        if prefix:
+            return out, pre[:n.value]
         return out
     cand = np.zeros((nfg, 2), np.float32)
     _check(lib().plviwo_op_sort_corners(device, packed.ctypes.data, len(packed), nfg, None, cand.ctypes.data, C.byref(n)))

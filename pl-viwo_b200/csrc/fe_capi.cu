@@ -440,6 +440,14 @@ int plviwo_op_sort_corners(int device, const uint32_t *packed, int n, int nfg, u
     std::memcpy(sorted, packed, (size_t)n * sizeof(uint32_t));
     host_sort_corners(sorted, n);
     if (n_cand) *n_cand = std::min(n, nfg);
+    if (cand) {   // the pruned form the selection kernel runs (isort::sort_prefix): x, y of its first nfg elements
+      std::vector<uint32_t> tmp(packed, packed + n);
+      host_sort_corners(tmp.data(), n, nfg);
+      for (int i = 0; i < std::min(n, nfg); i++) {
+        cand[2 * i] = (float)(tmp[i] & 0xfffu);
+        cand[2 * i + 1] = (float)((tmp[i] >> 12) & 0xfffu);
+      }
+    }
     return FE_OK;
   }
   if (!cand || !n_cand) return FE_BAD_ARG;

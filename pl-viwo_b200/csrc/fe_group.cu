@@ -197,6 +197,7 @@ int FeGroup::init() {
   FG_CUDA(dev_alloc(dev_allocs_, &g_.lk_p1n, P));
   FG_CUDA(dev_alloc(dev_allocs_, &g_.lk_status, P));
   FG_CUDA(dev_alloc(dev_allocs_, &g_.close, (size_t)S_ * std::max(g_.close_w * g_.close_h, 1)));
+  FG_CUDA(dev_alloc(dev_allocs_, &g_.ext_in, (size_t)S_ * g_.cand_cap));
   FG_CUDA(dev_alloc(dev_allocs_, &g_.ext_pt, (size_t)S_ * g_.cand_cap));
   {
     std::vector<uint64_t> cur(S_, 4 * (uint64_t)cfg_.numaruco + 1);   // TrackBase.cpp:34
@@ -252,7 +253,10 @@ int FeGroup::init() {
   int lo = 0, hi = 0;
   FG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   FG_CUDA(cudaStreamCreateWithPriority(&s_copy_, cudaStreamNonBlocking, lo));
-  const int nfront = std::min(RB_, 3);
+  // front batches of consecutive ticks run on different streams: the tail of one batch's chain walk (a few long
+  // components, milliseconds) overlaps the next batches' kernels
+  int nfront = std::min(RB_, 6);
+  if (const char *e = std::getenv("PLVIWO_GROUP_FRONT_STREAMS")) nfront = std::max(1, std::min(std::atoi(e), RB_));
   s_front_.resize(nfront);
   for (auto &st : s_front_) FG_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, lo));
   s_track_.resize(lanes_);
@@ -454,7 +458,8 @@ int FeGroup::launch_front(FrontBatch &b, int buf) {
   const int nj = (int)b.jobs.size(), nl = (int)b.line_slots.size();
   b.launched = true;
   if (nj == 0) return FE_OK;
-  cudaStream_t st = s_front_[buf % s_front_.size()];
+  // stage timing: everything on ONE stream, so that a kernel's event interval holds that kernel alone
+  cudaStream_t st = timing_ ? s_front_[0] : s_front_[buf % s_front_.size()];
   FrontJob *hj = h_fjobs_ + (size_t)buf * B_ * S_, *dj = d_fjobs_ + (size_t)buf * B_ * S_;
   int *hl = h_ljobs_ + (size_t)buf * B_ * S_, *dl = d_ljobs_ + (size_t)buf * B_ * S_;
   std::memcpy(hj, b.jobs.data(), nj * sizeof(FrontJob));
@@ -503,9 +508,6 @@ int FeGroup::launch_front(FrontBatch &b, int buf) {
     launch_fast_select_batch(d_slots_, dj, nj, fg_, st);
     launches_++;
     step(FE_GK_SELECT, nj);
-    launch_corner_subpix_batch(d_slots_, dj, nj, fg_, st);
-    launches_++;
-    step(FE_GK_SUBPIX, nj);
   }
   if (nl > 0) {
     launch_canny_table(d_slots_, dl, nl, W_ / 2, H_ / 2, cfg_.canny_th1, st);
@@ -556,7 +558,7 @@ int FeGroup::launch_track(int tick) {
     const int j0 = jpos;
     while (jpos < nj && hj[jpos].stream < s_end) jpos++;
     const int j1 = jpos;
-    cudaStream_t st = s_track_[l];
+    cudaStream_t st = timing_ ? s_front_[0] : s_track_[l];
     const int n = j1 - j0;
     if (n > 0) {
       FG_CUDA(cudaStreamWaitEvent(st, ev_front_[tr.batch], 0));
@@ -575,6 +577,11 @@ int FeGroup::launch_track(int tick) {
       }
       launch_group_detect(g_, dj + j0, n, st);
       step(FE_GK_DETECT);
+      launch_group_subpix(g_, dj + j0, n, st);
+      step(FE_GK_SUBPIX);
+      launch_group_accept(g_, dj + j0, n, st);
+      step(FE_GK_ACCEPT);
+      launches_ += 2;
       launch_group_lk(g_, dj + j0, n, prm, st);
       step(FE_GK_LK);
       launch_group_gate(g_, dj + j0, n, st);
@@ -886,7 +893,6 @@ int FeGroup::set_state(int s, const void *buf, size_t n_bytes) {
     if (fg_.n_cells > 0) {
       launch_fast_batch(d_slots_, d_fjobs_, 1, fg_, st);
       launch_fast_select_batch(d_slots_, d_fjobs_, 1, fg_, st);
-      launch_corner_subpix_batch(d_slots_, d_fjobs_, 1, fg_, st);
     }
     FG_CUDA(cudaGetLastError());
     FG_CUDA(cudaStreamSynchronize(st));

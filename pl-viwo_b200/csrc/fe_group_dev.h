@@ -58,11 +58,12 @@ struct GroupDev {
   uint64_t *wids;
   int *wn;
   int *wmode;                    // 0 track, 1 first frame (detection only), 2 nothing to do
-  int *winfo;                    // per stream [detection_ran, n_detected]
+  int *winfo;                    // per stream [detection_ran, n_detected, overflow, candidates to refine]
   float2 *lk_pts1, *lk_p0n, *lk_p1n;
   uint8_t *lk_status;
   int *close;                    // min-distance grid of the detection, stream s at s * close_w * close_h
-  float2 *ext_pt;                // candidates that passed the mask test (refined), stream s at s * cand_cap
+  float2 *ext_in;                // candidates of the valid cells that passed the mask test, stream s at s * cand_cap
+  float2 *ext_pt;                // ... after cornerSubPix
   // ---- line tracker state, double buffered (buffer b of stream s at (2 * s + b) * cap)
   float4 *lines;
   uint64_t *line_ids;
@@ -85,6 +86,8 @@ struct GroupDev {
 
 // tracking launches (kernels_glue.cu, kernels_track.cu)
 void launch_group_detect(const GroupDev &g, const TrackJob *jobs, int n_jobs, cudaStream_t s);
+void launch_group_subpix(const GroupDev &g, const TrackJob *jobs, int n_jobs, cudaStream_t s);   // kernels_track.cu
+void launch_group_accept(const GroupDev &g, const TrackJob *jobs, int n_jobs, cudaStream_t s);
 void launch_group_lk(const GroupDev &g, const TrackJob *jobs, int n_jobs, const LkParams &prm, cudaStream_t s);
 void launch_group_gate(const GroupDev &g, const TrackJob *jobs, int n_jobs, cudaStream_t s);
 void launch_group_lines(const GroupDev &g, const TrackJob *jobs, int n_jobs, cudaStream_t s);

@@ -100,7 +100,7 @@ void launch_fast(const DevImage &img, const FastCell *d_cells, int n_cells, int 
 void launch_fast_select(const FastCell *d_cells, int n_cells, int max_bands, unsigned *d_total, const int *d_band_off,
                         const int *d_band_cnt, const unsigned *d_kps, int kps_cap, unsigned *d_scratch, int nfg,
                         float2 *d_cand_sel, int *d_cand_cnt, cudaStream_t s);
-void host_sort_corners(unsigned *v, int n);   // the same introsort on the host (tests)
+void host_sort_corners(unsigned *v, int n, int keep = 0);   // the same introsort on the host (tests); keep > 0: sort_prefix
 
 // ---- cornerSubPix (kernels_track.cu) ----------------------------------------------------------------------
 // n points; with d_cnt != null the points are a fixed-stride table (slot i belongs to cell i / stride and is live only if

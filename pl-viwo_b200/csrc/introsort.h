@@ -166,5 +166,53 @@ PLVIWO_HD void sort(unsigned *v, int n) {
   }
 }
 
+// The first `keep` elements of std::sort(v, v + n, compare_response), without sorting the rest (v[keep ..] is left in an
+// unspecified order).  Exactly the permutation std::sort produces for those positions, at the cost of a selection instead
+// of a sort: a partition step leaves every element of the left part "not less" than every element of the right part, and
+// neither the later partition steps of one part nor the final insertion sort (which moves an element left only past
+// STRICTLY smaller ones) ever carry an element across that boundary.  So a right part that starts at or beyond position
+// `keep` cannot influence the first `keep` outputs and its recursive call is skipped; the final insertion sort stops at the
+// first skipped boundary.  The depth counter runs as in the full sort (it only depends on the path to the left parts); if
+// it hits zero the part is heap-sorted as a whole, as std::sort does.
+PLVIWO_HD void sort_prefix(unsigned *v, int n, int keep) {
+  if (n <= 0) return;
+  if (keep >= n) {
+    sort(v, n);
+    return;
+  }
+  int stack_first[64], stack_last[64], stack_depth[64];
+  int sp = 0;
+  int bound = n;   // [0, bound) has gone through the whole introsort loop
+  stack_first[0] = 0; stack_last[0] = n; stack_depth[0] = 2 * lg(n);
+  sp = 1;
+  while (sp > 0) {
+    --sp;
+    int first = stack_first[sp], last = stack_last[sp], depth = stack_depth[sp];
+    while (last - first > kThreshold) {
+      if (depth == 0) {
+        heap_sort(v + first, last - first);
+        break;
+      }
+      --depth;
+      const int mid = first + (last - first) / 2;
+      move_median_to_first(v, first, first + 1, mid, last - 1);
+      const int cut = unguarded_partition(v, first + 1, last, first);
+      if (cut < keep) {   // the right part holds wanted positions: the recursive call
+        stack_first[sp] = cut; stack_last[sp] = last; stack_depth[sp] = depth;
+        sp++;
+      } else if (cut < bound) {
+        bound = cut;
+      }
+      last = cut;
+    }
+  }
+  if (bound > kThreshold) {   // std::__final_insertion_sort, restricted to [0, bound)
+    insertion_sort(v, 0, kThreshold);
+    for (int i = kThreshold; i != bound; ++i) unguarded_linear_insert(v, i);
+  } else {
+    insertion_sort(v, 0, bound);
+  }
+}
+
 }  // namespace isort
 }  // namespace plviwo

@@ -28,16 +28,32 @@ __device__ __forceinline__ bool has_arc9(unsigned m16) {
   return (r & 0xffffu) != 0;
 }
 
-__device__ __forceinline__ int fast_score(const uint8_t *__restrict__ px, int stride, int threshold) {
+// FAST-9/16 test and score of one pixel; get(dx, dy) returns the neighbour at that offset (compile-time offsets after
+// unrolling: shared-memory bytes in the generic path, byte extracts from registers in the 4-pixel path).
+// Necessary condition (exact, OpenCV's own early exit): 9 contiguous ring positions always contain position k or k + 8 for
+// every k, so a bright (dark) arc needs a brighter (darker) pixel in each opposite pair.  Two pairs — four pixels — reject
+// most pixels of a natural image before the other twelve are looked at.
+template <class Get>
+__device__ __forceinline__ bool fast_quick_t(Get get, int threshold) {
+  const int v = get(0, 0);
+  const int hi = v + threshold, lo = v - threshold;
+  const int p0 = get(0, 3), p8 = get(0, -3), p4 = get(3, 0), p12 = get(-3, 0);
+  const bool br = (p0 > hi || p8 > hi) && (p4 > hi || p12 > hi);
+  const bool dk = (p0 < lo || p8 < lo) && (p4 < lo || p12 < lo);
+  return br || dk;
+}
+
+template <class Get>
+__device__ __forceinline__ int fast_full_t(Get get, int threshold) {
   // ring offsets in OpenCV's order (Appendix A4)
-  const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-  const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
-  int v = px[0];
+  constexpr int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+  constexpr int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+  const int v = get(0, 0);
   int d[16];
   unsigned bright = 0, dark = 0;
 #pragma unroll
   for (int k = 0; k < 16; k++) {
-    d[k] = v - (int)px[dy[k] * stride + dx[k]];
+    d[k] = v - get(dx[k], dy[k]);
     bright |= (d[k] > threshold ? 1u : 0u) << k;
     dark |= (d[k] < -threshold ? 1u : 0u) << k;
   }
@@ -66,14 +82,22 @@ __device__ __forceinline__ int fast_score(const uint8_t *__restrict__ px, int st
   return max(a0, -b0) - 1;
 }
 
+__device__ __forceinline__ int fast_score(const uint8_t *__restrict__ px, int stride, int threshold) {
+  auto get = [&](int dx, int dy) { return (int)px[dy * stride + dx]; };
+  if (!fast_quick_t(get, threshold)) return 0;
+  return fast_full_t(get, threshold);
+}
+
+constexpr int kFastPad = 16;   // bytes in front of the staged pixels: the 4-pixel path reads the word left of column 0
+
 __device__ __forceinline__ void fast_body(const uint8_t *__restrict__ img, int pitch, const FastCell *__restrict__ cells, int max_bands,
                                           int threshold, unsigned *__restrict__ total, int *__restrict__ band_off,
                                           int *__restrict__ band_cnt, unsigned *__restrict__ kps, int kps_cap, int smem_w) {
-  extern __shared__ uint8_t smem[];
-  uint8_t *pix = smem;                               // (kBH + 8) rows x smem_w
-  uint8_t *sc = smem + (kBH + 8) * smem_w;           // (kBH + 2) rows x smem_w
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t *pix = smem + kFastPad;                              // (kBH + 8) rows x smem_w
+  uint8_t *sc = smem + 2 * kFastPad + (kBH + 8) * smem_w;      // (kBH + 2) rows x smem_w
   __shared__ int warp_tot[kFastThreads / 32];
-  __shared__ int s_base;
+  __shared__ int s_base, s_nlist;
 
   const FastCell cell = cells[blockIdx.y];
   const int band = blockIdx.x;
@@ -87,37 +111,135 @@ __device__ __forceinline__ void fast_body(const uint8_t *__restrict__ img, int p
   const int tid = threadIdx.x;
   // ---- stage pixel rows y0-4 .. y0+kBH+3 (cell-local), clipped to the cell
   const int py0 = y0 - 4;
-  for (int i = tid; i < (kBH + 8) * cw; i += kFastThreads) {
-    int r = i / cw, x = i - r * cw;
-    int y = py0 + r;
-    uint8_t v = 0;
-    if (y >= 0 && y < ch) v = img[(size_t)(cell.y + y) * pitch + cell.x + x];
-    pix[r * smem_w + x] = v;
+  if (((cell.x | cw | pitch) & 3) == 0 && ((size_t)img & 3) == 0) {   // whole 32-bit words (coalesced 128-byte rows per warp)
+    const int cww = cw >> 2;
+    for (int i = tid; i < (kBH + 8) * cww; i += kFastThreads) {
+      int r = i / cww, xw = i - r * cww;
+      int y = py0 + r;
+      unsigned v = 0;
+      if (y >= 0 && y < ch) v = __ldg(reinterpret_cast<const unsigned *>(img + (size_t)(cell.y + y) * pitch + cell.x) + xw);
+      *reinterpret_cast<unsigned *>(&pix[r * smem_w + 4 * xw]) = v;
+    }
+  } else {
+    for (int i = tid; i < (kBH + 8) * cw; i += kFastThreads) {
+      int r = i / cw, x = i - r * cw;
+      int y = py0 + r;
+      uint8_t v = 0;
+      if (y >= 0 && y < ch) v = img[(size_t)(cell.y + y) * pitch + cell.x + x];
+      pix[r * smem_w + x] = v;
+    }
   }
   __syncthreads();
   // ---- scores for rows y0-1 .. y0+kBH
-  for (int i = tid; i < (kBH + 2) * cw; i += kFastThreads) {
-    int r = i / cw, x = i - r * cw;
-    int y = y0 - 1 + r;
-    int s = 0;
-    if (x >= 3 && x < cw - 3 && y >= 3 && y < ch - 3) s = fast_score(&pix[(r + 3) * smem_w + x], smem_w, threshold);
-    sc[r * smem_w + x] = (uint8_t)s;
+  const bool words = ((cell.x | cw | pitch) & 3) == 0 && ((size_t)img & 3) == 0 && cw <= 2048;
+  if (words) {
+    // Two phases, so that the expensive part only runs on lanes that have work (a warp pays for the arc test and the score
+    // whenever ONE of its lanes needs them, and in a textured image there is such a pixel in nearly every 32):
+    //  1. the four-pixel quick test on every pixel — four horizontally adjacent pixels per thread, the 7 x 10 pixels they look
+    //     at are seven rows of three 32-bit words in registers (only the centre row and the rows 3 above / below are needed
+    //     here) — survivors are appended to a list in shared memory (warp-aggregated);
+    //  2. the full ring test and the score on the list, one survivor per lane.
+    unsigned short *list = reinterpret_cast<unsigned short *>(smem + 3 * kFastPad + (2 * kBH + 10) * smem_w);
+    const int cww = cw >> 2;
+    const int items = (kBH + 2) * cww;
+    for (int i = tid; i < (kBH + 2) * (smem_w >> 2); i += kFastThreads) reinterpret_cast<unsigned *>(sc)[i] = 0;
+    if (tid == 0) s_nlist = 0;
+    __syncthreads();
+    const int lane = tid & 31;
+    for (int i0 = 0; i0 < items; i0 += kFastThreads) {
+      const int i = i0 + tid;
+      const int r = i / cww, x0 = (i - r * cww) << 2;
+      const int y = y0 - 1 + r;
+      const bool row_ok = i < items && y >= 3 && y < ch - 3;
+      unsigned w0[3] = {0, 0, 0}, w3[3] = {0, 0, 0}, w6[3] = {0, 0, 0};
+      if (row_ok) {
+        const unsigned *p0r = reinterpret_cast<const unsigned *>(&pix[(r + 0) * smem_w + x0]);
+        const unsigned *p3r = reinterpret_cast<const unsigned *>(&pix[(r + 3) * smem_w + x0]);
+        const unsigned *p6r = reinterpret_cast<const unsigned *>(&pix[(r + 6) * smem_w + x0]);
+        w0[1] = p0r[0];
+        w6[1] = p6r[0];
+        w3[0] = p3r[-1]; w3[1] = p3r[0]; w3[2] = p3r[1];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int x = x0 + j;
+        bool pass = false;
+        if (row_ok && x >= 3 && x < cw - 3) {
+          pass = fast_quick_t(
+              [&](int dx, int dy) {
+                const int idx = j + dx + 4;   // byte index into a row's three words
+                const unsigned *row = dy == 0 ? w3 : (dy < 0 ? w0 : w6);
+                return (int)((row[idx >> 2] >> (8 * (idx & 3))) & 0xffu);
+              },
+              threshold);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (bal) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&s_nlist, __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (pass) list[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)((r << 11) | x);
+        }
+      }
+    }
+    __syncthreads();
+    const int nlist = s_nlist;
+    for (int k = tid; k < nlist; k += kFastThreads) {
+      const int e = list[k], r = e >> 11, x = e & 2047;
+      const uint8_t *px = &pix[(r + 3) * smem_w + x];
+      const int sv = fast_full_t([&](int dx, int dy) { return (int)px[dy * smem_w + dx]; }, threshold);
+      if (sv) sc[r * smem_w + x] = (uint8_t)sv;
+    }
+  } else {
+    for (int i = tid; i < (kBH + 2) * cw; i += kFastThreads) {
+      int r = i / cw, x = i - r * cw;
+      int y = y0 - 1 + r;
+      int s = 0;
+      if (x >= 3 && x < cw - 3 && y >= 3 && y < ch - 3) s = fast_score(&pix[(r + 3) * smem_w + x], smem_w, threshold);
+      sc[r * smem_w + x] = (uint8_t)s;
+    }
   }
   __syncthreads();
   // ---- NMS + ordered compaction: thread t owns positions [t*R, (t+1)*R) of the band in row-major order
   const int rows = min(kBH, ch - y0);
   const int npos = rows * cw;
-  const int R = (npos + kFastThreads - 1) / kFastThreads;
-  const int p0 = tid * R, p1 = min(p0 + R, npos);
+  // word path: runs of positions that start on a word boundary, scores read four at a time (most words are all zero), the
+  // survivors' scores parked in the pixel plane (no longer needed) so that the second pass does not repeat the test
+  const int R = words ? 4 * ((npos / 4 + kFastThreads - 1) / kFastThreads) : (npos + kFastThreads - 1) / kFastThreads;
+  const int p0 = min(tid * R, npos), p1 = min(p0 + R, npos);
   int cnt = 0;
-  for (int p = p0; p < p1; p++) {
-    int r = p / cw, x = p - r * cw;
-    int s = sc[(r + 1) * smem_w + x];
-    if (s > 0 && x > 0 && x < cw - 1) {
-      const uint8_t *c = &sc[(r + 1) * smem_w + x];
-      bool keep = s > c[-1] && s > c[1] && s > c[-smem_w - 1] && s > c[-smem_w] && s > c[-smem_w + 1] &&
-                  s > c[smem_w - 1] && s > c[smem_w] && s > c[smem_w + 1];
-      cnt += keep ? 1 : 0;
+  if (words) {
+    for (int p = p0; p < p1; p += 4) {
+      const int r = p / cw, x = p - r * cw;
+      const unsigned wv = *reinterpret_cast<const unsigned *>(&sc[(r + 1) * smem_w + x]);
+      unsigned kept = 0;
+      if (wv) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int sv = (int)((wv >> (8 * k)) & 0xffu), xx = x + k;
+          if (sv > 0 && xx > 0 && xx < cw - 1) {
+            const uint8_t *c = &sc[(r + 1) * smem_w + xx];
+            const bool keep = sv > c[-1] && sv > c[1] && sv > c[-smem_w - 1] && sv > c[-smem_w] && sv > c[-smem_w + 1] &&
+                              sv > c[smem_w - 1] && sv > c[smem_w] && sv > c[smem_w + 1];
+            if (keep) {
+              kept |= (unsigned)sv << (8 * k);
+              cnt++;
+            }
+          }
+        }
+      }
+      *reinterpret_cast<unsigned *>(&pix[r * smem_w + x]) = kept;
+    }
+  } else {
+    for (int p = p0; p < p1; p++) {
+      int r = p / cw, x = p - r * cw;
+      int s = sc[(r + 1) * smem_w + x];
+      if (s > 0 && x > 0 && x < cw - 1) {
+        const uint8_t *c = &sc[(r + 1) * smem_w + x];
+        bool keep = s > c[-1] && s > c[1] && s > c[-smem_w - 1] && s > c[-smem_w] && s > c[-smem_w + 1] &&
+                    s > c[smem_w - 1] && s > c[smem_w] && s > c[smem_w + 1];
+        cnt += keep ? 1 : 0;
+      }
     }
   }
   // block exclusive scan of cnt
@@ -141,6 +263,20 @@ __device__ __forceinline__ void fast_body(const uint8_t *__restrict__ img, int p
   }
   __syncthreads();
   int w = s_base + excl;
+  if (words) {
+    for (int p = p0; p < p1; p += 4) {
+      const int r = p / cw, x = p - r * cw;
+      unsigned kept = *reinterpret_cast<const unsigned *>(&pix[r * smem_w + x]);
+      while (kept) {
+        const int k = (__ffs((int)kept) - 1) >> 3;
+        const unsigned sv = (kept >> (8 * k)) & 0xffu;
+        if (w < kps_cap) kps[w] = (unsigned)(x + k) | ((unsigned)(y0 + r) << 12) | (sv << 24);
+        w++;
+        kept &= ~(0xffu << (8 * k));
+      }
+    }
+    return;
+  }
   for (int p = p0; p < p1; p++) {
     int r = p / cw, x = p - r * cw;
     int s = sc[(r + 1) * smem_w + x];
@@ -163,7 +299,7 @@ __global__ void __launch_bounds__(kFastThreads)
   fast_body(img, pitch, cells, max_bands, threshold, total, band_off, band_cnt, kps, kps_cap, smem_w);
 }
 // grid = (band, cell, job)
-__global__ void __launch_bounds__(kFastThreads)
+__global__ void __launch_bounds__(kFastThreads, 3)
     k_fast_b(const SlotRec *__restrict__ slots, const FrontJob *__restrict__ jobs, FrontGeom g, int smem_w) {
   const SlotRec &sl = slots[jobs[blockIdx.z].slot];
   fast_body(sl.lvl[0].p, sl.lvl[0].pitch, g.cells, g.max_bands, g.fast_threshold, sl.fast_total, sl.band_off, sl.band_cnt, sl.kps,
@@ -174,7 +310,8 @@ __global__ void __launch_bounds__(kFastThreads)
 // Grider_GRID.h:128-133: std::sort(cell corners, compare_response), keep the first num_features_grid.  One CTA per
 // cell: the cell's corners (band slices of the compact list, i.e. row-major order — the order cv::FAST emits them in)
 // are gathered into shared memory, ONE thread runs libstdc++'s introsort on them (introsort.h: the tie permutation is
-// part of the contract), and the survivors are written as full-image float coordinates to a fixed-stride table
+// part of the contract) — pruned to the partitions that can reach the first num_features_grid positions, which is a
+// selection, not a sort, with the identical result — and the survivors are written as full-image float coordinates to a fixed-stride table
 // (cell c at c * nfg).  Cells with more corners than fit in shared memory sort in a global scratch slice.
 constexpr int kSelThreads = 128;
 constexpr int kSelSmemCap = 8192;
@@ -209,7 +346,7 @@ __device__ __forceinline__ void fast_select_body(const FastCell *__restrict__ ce
   }
   __syncthreads();
   if (tid == 0) {
-    isort::sort(v, n);
+    isort::sort_prefix(v, n, nfg);   // exactly std::sort's first nfg elements (introsort.h), without sorting the rest
     cand_cnt[c] = min(n, nfg);
   }
   __syncthreads();
@@ -238,7 +375,7 @@ __global__ void __launch_bounds__(kSelThreads)
 void launch_fast_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, const FrontGeom &g, cudaStream_t s) {
   if (n_jobs <= 0 || g.n_cells <= 0) return;
   const int smem_w = (g.max_cell_w + 15) & ~15;
-  const size_t smem = (size_t)(2 * kBH + 10) * smem_w;
+  const size_t smem = (size_t)(2 * kBH + 10) * smem_w + 3 * kFastPad + (size_t)(kBH + 2) * smem_w * 2;
   static SmemOptIn optin;
   optin.ensure(k_fast_b, smem);
   PLVIWO_CARVEOUT(k_fast_b);
@@ -260,13 +397,16 @@ void launch_fast_select(const FastCell *d_cells, int n_cells, int max_bands, uns
 }
 
 // host instantiation of the same sort (tests: compared with the real std::sort and with the kernel)
-void host_sort_corners(unsigned *v, int n) { isort::sort(v, n); }
+void host_sort_corners(unsigned *v, int n, int keep) {
+  if (keep > 0) isort::sort_prefix(v, n, keep);
+  else isort::sort(v, n);
+}
 
 void launch_fast(const DevImage &img, const FastCell *d_cells, int n_cells, int max_bands, int max_cell_w, int threshold,
                  unsigned *d_total, int *d_band_off, int *d_band_cnt, unsigned *d_kps, int kps_cap, cudaStream_t s) {
   if (n_cells <= 0) return;
   int smem_w = (max_cell_w + 15) & ~15;
-  size_t smem = (size_t)(2 * kBH + 10) * smem_w;
+  size_t smem = (size_t)(2 * kBH + 10) * smem_w + 3 * kFastPad + (size_t)(kBH + 2) * smem_w * 2;
   static SmemOptIn optin;
   optin.ensure(k_fast, smem);
   dim3 grid(max_bands, n_cells);

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kGT)
   }
   __syncthreads();
 
-  int n_out = nk, detection_ran = 0, n_added = 0, overflow = 0;
+  int detection_ran = 0, n_ext = 0;
   const double min_feat_percent = 0.50;
   const int need = g.num_features - nk;
   const int need_min = min(20, (int)(min_feat_percent * g.num_features));
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kGT)
     const int nv = s_nvalid, nfg = g.nfg;
     // ---- Grider_GRID.h:133-149 on the candidate table: bounds and mask0_updated (caller mask, or inside the (2d+1)^2
     // square of a kept point whose square lies inside the image, :457-461), in (cell, rank) order
-    float2 *__restrict__ ext = g.ext_pt + (size_t)s * g.cand_cap;
+    float2 *__restrict__ ext = g.ext_in + (size_t)s * g.cand_cap;
     int next = 0;
     const int total_q = nv * nfg;
     for (int base = 0; base < total_q; base += kGT) {
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kGT)
             }
             if (!occ) {
               pass = true;
-              pr = sl.cand_ref[i];   // cornerSubPix result of exactly this corner (Grider_GRID.h:163-179)
+              pr = p;                // refined by k_group_subpix before the distance test (Grider_GRID.h:163-179)
             }
           }
         }
@@ -185,7 +185,34 @@ __global__ void __launch_bounds__(kGT)
       if (pass) ext[next + e] = pr;
       next += bs.total;
     }
-    __syncthreads();
+    n_ext = next;
+  }
+  if (tid == 0) {
+    g.wn[s] = nk;                       // points kept so far; k_group_accept appends the new ones
+    g.wmode[s] = first ? 1 : 0;
+    g.winfo[4 * s + 0] = detection_ran;
+    g.winfo[4 * s + 1] = 0;
+    g.winfo[4 * s + 2] = 0;
+    g.winfo[4 * s + 3] = n_ext;         // candidates waiting for cornerSubPix (k_group_subpix) and the distance test
+  }
+}
+
+// Second half of the top-off detection, after cornerSubPix of the surviving candidates (Grider_GRID.h:163-179).
+__global__ void __launch_bounds__(kGT)
+    k_group_accept(const __grid_constant__ GroupDev g, const TrackJob *__restrict__ jobs) {
+  __shared__ BlockScan bs;
+  const TrackJob &job = jobs[blockIdx.x];
+  const int s = job.stream, tid = threadIdx.x;
+  const int d = g.min_px_dist;
+  const int close_w = g.close_w, close_h = g.close_h, close_n = close_w * close_h;
+  const size_t o = (size_t)s * g.pts_cap;
+  float2 *__restrict__ wpts = g.wpts + o;
+  uint64_t *__restrict__ wids = g.wids + o;
+  int *__restrict__ close = g.close + (size_t)s * close_n;
+  const float2 *__restrict__ ext = g.ext_pt + (size_t)s * g.cand_cap;
+  const int nk = g.wn[s], next = g.winfo[4 * s + 3];
+  int n_added = 0, overflow = 0, n_out = nk;
+  if (next > 0) {
     // ---- minimum-distance rejection among the new points, in order (:497-512), then ids (:519-527)
     for (int e = tid; e < next; e += kGT) {
       const float2 kp = ext[e];
@@ -223,8 +250,6 @@ __global__ void __launch_bounds__(kGT)
   }
   if (tid == 0) {
     g.wn[s] = n_out;
-    g.wmode[s] = first ? 1 : 0;
-    g.winfo[4 * s + 0] = detection_ran;
     g.winfo[4 * s + 1] = n_added;
     g.winfo[4 * s + 2] = overflow;
   }
@@ -234,6 +259,11 @@ void launch_group_detect(const GroupDev &g, const TrackJob *jobs, int n_jobs, cu
   if (n_jobs <= 0) return;
   PLVIWO_CARVEOUT(k_group_detect);
   k_group_detect<<<n_jobs, kGT, 0, s>>>(g, jobs);
+}
+void launch_group_accept(const GroupDev &g, const TrackJob *jobs, int n_jobs, cudaStream_t s) {
+  if (n_jobs <= 0) return;
+  PLVIWO_CARVEOUT(k_group_accept);
+  k_group_accept<<<n_jobs, kGT, 0, s>>>(g, jobs);
 }
 
 // ============================================================================================= RANSAC gate + rows

@@ -156,92 +156,242 @@ __device__ __forceinline__ void ccl_union(int *parent, int a, int b) {
   }
 }
 
+__device__ __forceinline__ bool edge_at(const unsigned *__restrict__ edges, int words_per_row, int x, int y) {
+  return (__ldg(edges + (size_t)y * words_per_row + (x >> 5)) >> (x & 31)) & 1u;
+}
+
+// Connected components in three steps:
+//   k_ccl_tile     every 64 x 16 tile labels ITS pixels in shared memory (union-find with shared-memory atomics) and counts
+//                  pixels / bounding boxes per tile-local component: the label written out for a pixel is the raster index of
+//                  its tile-local root, the aggregates go to the root's slot of the cnt / bbox planes (other edge pixels of
+//                  the tile get cnt = 0);
+//   k_ccl_border   unions across tile borders on the global label array (only border pixels: ~8 % of the frame);
+//   k_ccl_flatten  every edge pixel looks up its global root; tile-local roots that are not global roots hand their
+//                  aggregates to the global root.
+// Only edge pixels carry a label, a pixel count and a bounding box; everything asks the bit-packed edge map first.  The
+// planes are written for the ~5-10 % of the pixels that are edges, and the hot global atomics of a large component are one
+// per TILE it crosses instead of one per few pixels.
+constexpr int kTileW = 64, kTileH = 16, kTilePx = kTileW * kTileH, kTileThreads = 256;
+
+__device__ __forceinline__ int sm_find(const int *lab, int i) {
+  int p = lab[i];
+  while (p != i) {
+    i = p;
+    p = lab[i];
+  }
+  return i;
+}
+__device__ __forceinline__ void sm_union(int *lab, int a, int b) {
+  while (true) {
+    a = sm_find(lab, a);
+    b = sm_find(lab, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }   // link the larger root under the smaller index
+    const int old = atomicMin(lab + a, b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
 template <class B>
-__global__ void k_ccl_init(const __grid_constant__ B b, int w, int h) {
-  const FldBuffers &fb = b.fld_of(blockIdx.y);
+__global__ void __launch_bounds__(kTileThreads)
+    k_ccl_tile(const __grid_constant__ B b, int w, int h) {
+  const FldBuffers &fb = b.fld_of(blockIdx.z);
   const unsigned *__restrict__ edges = fb.edges;
   const int words_per_row = fb.words_per_row;
   int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt, *__restrict__ bbox = fb.bbox /* maxy, minx, maxx planes */;
-  int *__restrict__ counters = fb.counters;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 8) counters[i] = 0;
-  if (i >= w * h) return;
-  const int y = i / w, x = i - y * w;
-  const bool e = (edges[(size_t)y * words_per_row + (x >> 5)] >> (x & 31)) & 1u;
-  label[i] = e ? i : -1;
-  cnt[i] = 0;
-  bbox[i] = 0;                 // max y
-  bbox[w * h + i] = 0x7fffffff;  // min x
-  bbox[2 * w * h + i] = -1;    // max x
-}
-
-template <class B>
-__global__ void k_ccl_merge(const __grid_constant__ B b, int w, int h) {
-  int *__restrict__ label = b.fld_of(blockIdx.y).label;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= w * h) return;
-  if (label[i] < 0) return;
-  const int y = i / w, x = i - y * w;
-  // backward half of the 8-neighbourhood: W, NW, N, NE
-  if (x > 0 && label[i - 1] >= 0) ccl_union(label, i, i - 1);
-  if (y > 0) {
-    if (x > 0 && label[i - w - 1] >= 0) ccl_union(label, i, i - w - 1);
-    if (label[i - w] >= 0) ccl_union(label, i, i - w);
-    if (x < w - 1 && label[i - w + 1] >= 0) ccl_union(label, i, i - w + 1);
+  __shared__ unsigned bits[kTileH][2];
+  __shared__ int lab[kTilePx];
+  __shared__ int a_cnt[kTilePx], a_ymax[kTilePx], a_xmin[kTilePx], a_xmax[kTilePx];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && tid < 8) fb.counters[tid] = 0;
+  if (tid < kTileH * 2) {
+    const int r = tid >> 1, k = tid & 1;
+    const int gy = y0 + r, gw = (x0 >> 5) + k;
+    unsigned v = 0;
+    if (gy < h && gw < words_per_row) v = edges[(size_t)gy * words_per_row + gw];
+    if (gy < h && (gw << 5) + 32 > w) v &= (gw << 5) < w ? (0xffffffffu >> (32 - (w - (gw << 5)))) : 0u;   // beyond the frame
+    bits[r][k] = v;
+  }
+  __syncthreads();
+  auto edge = [&](int lx, int ly) -> bool { return (bits[ly][lx >> 5] >> (lx & 31)) & 1u; };
+  // thread t owns the 4 pixels (4 (t % 16) .., t / 16)
+  const int ly = tid >> 4, lx0 = (tid & 15) << 2;
+  const unsigned nib = (bits[ly][lx0 >> 5] >> (lx0 & 31)) & 15u;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int p = ly * kTileW + lx0 + k;
+    lab[p] = ((nib >> k) & 1u) ? p : -1;
+    a_cnt[p] = 0;
+    a_ymax[p] = 0;
+    a_xmin[p] = kTileW;
+    a_xmax[p] = -1;
+  }
+  __syncthreads();
+  // backward half of the 8-neighbourhood inside the tile: W, NW, N, NE.  N is 8-adjacent to the other three (and they are
+  // merged with it when THEY are processed), so a set N needs one union; otherwise W (or, without W, NW — W's own N) and NE
+  // are independent.
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (!((nib >> k) & 1u)) continue;
+    const int lx = lx0 + k, p = ly * kTileW + lx;
+    const bool eW = lx > 0 && edge(lx - 1, ly);
+    if (ly > 0) {
+      if (edge(lx, ly - 1)) {
+        sm_union(lab, p, p - kTileW);
+        continue;
+      }
+      if (eW) sm_union(lab, p, p - 1);
+      else if (lx > 0 && edge(lx - 1, ly - 1)) sm_union(lab, p, p - kTileW - 1);
+      if (lx < kTileW - 1 && edge(lx + 1, ly - 1)) sm_union(lab, p, p - kTileW + 1);
+    } else if (eW) {
+      sm_union(lab, p, p - 1);
+    }
+  }
+  __syncthreads();
+  int root[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    root[k] = -1;
+    if ((nib >> k) & 1u) {
+      const int lx = lx0 + k;
+      const int r = sm_find(lab, ly * kTileW + lx);
+      root[k] = r;
+      atomicAdd(&a_cnt[r], 1);
+      atomicMax(&a_ymax[r], ly);
+      atomicMin(&a_xmin[r], lx);
+      atomicMax(&a_xmax[r], lx);
+    }
+  }
+  __syncthreads();
+  const int n = w * h;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (root[k] < 0) continue;
+    const int lx = lx0 + k, p = ly * kTileW + lx;
+    const int gi = (y0 + ly) * w + x0 + lx;
+    const int r = root[k];
+    label[gi] = (y0 + (r >> 6)) * w + x0 + (r & (kTileW - 1));
+    if (r == p) {
+      cnt[gi] = a_cnt[p];
+      bbox[gi] = y0 + a_ymax[p];
+      bbox[n + gi] = x0 + a_xmin[p];
+      bbox[2 * n + gi] = x0 + a_xmax[p];
+    } else {
+      cnt[gi] = 0;
+    }
   }
 }
 
-// flatten + per-component pixel count and bounding box (warp-aggregated atomics keyed by the root)
+// One thread per pixel of a tile border: rows y = 16 k (all x) first, then columns x = 64 m (all y).
+template <class B>
+__global__ void k_ccl_border(const __grid_constant__ B b, int w, int h) {
+  const FldBuffers &fb = b.fld_of(blockIdx.y);
+  const unsigned *__restrict__ edges = fb.edges;
+  const int words_per_row = fb.words_per_row;
+  int *__restrict__ label = fb.label;
+  const int nrow = (h - 1) / kTileH, ncol = (w - 1) / kTileW;   // interior boundaries
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nrow * w) {
+    const int y = (t / w + 1) * kTileH, x = t % w;
+    if (!edge_at(edges, words_per_row, x, y)) return;
+    const int i = y * w + x;
+    if (x > 0 && edge_at(edges, words_per_row, x - 1, y - 1)) ccl_union(label, i, i - w - 1);
+    if (edge_at(edges, words_per_row, x, y - 1)) ccl_union(label, i, i - w);
+    if (x < w - 1 && edge_at(edges, words_per_row, x + 1, y - 1)) ccl_union(label, i, i - w + 1);
+    return;
+  }
+  const int u = t - nrow * w;
+  if (u >= ncol * h) return;
+  const int x = (u / h + 1) * kTileW, y = u % h;
+  if (!edge_at(edges, words_per_row, x, y)) return;
+  const int i = y * w + x;
+  if (y > 0 && edge_at(edges, words_per_row, x - 1, y - 1)) ccl_union(label, i, i - w - 1);
+  if (edge_at(edges, words_per_row, x - 1, y)) ccl_union(label, i, i - 1);
+  if (y < h - 1 && edge_at(edges, words_per_row, x - 1, y + 1)) ccl_union(label, i, i + w - 1);
+}
+
+// One thread per 32-pixel word of the edge map.
 template <class B>
 __global__ void k_ccl_flatten(const __grid_constant__ B b, int w, int h) {
-  int *__restrict__ label = b.fld_of(blockIdx.y).label, *__restrict__ cnt = b.fld_of(blockIdx.y).cnt, *__restrict__ bbox = b.fld_of(blockIdx.y).bbox;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int root = -1;
-  if (i < w * h && label[i] >= 0) {
-    root = ccl_find(label, i);
+  const FldBuffers &fb = b.fld_of(blockIdx.y);
+  const int words_per_row = fb.words_per_row;
+  int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt, *__restrict__ bbox = fb.bbox;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= words_per_row * h) return;
+  unsigned e = fb.edges[t];
+  if (!e) return;
+  const int y = t / words_per_row, xb = (t - y * words_per_row) << 5;
+  const int n = w * h;
+  while (e) {
+    const int k = __ffs((int)e) - 1;
+    e &= e - 1;
+    const int x = xb + k;
+    if (x >= w) break;
+    const int i = y * w + x;
+    const int root = ccl_find(label, i);
     label[i] = root;
-  }
-  const unsigned active = __ballot_sync(0xffffffffu, root >= 0);
-  if (root < 0) return;
-  const int y = i / w, x = i - y * w;
-  const unsigned peers = __match_any_sync(active, root);
-  const int n = __popc(peers);
-  const int ymax = __reduce_max_sync(peers, y);
-  const int xmin = __reduce_min_sync(peers, x);
-  const int xmax = __reduce_max_sync(peers, x);
-  if ((threadIdx.x & 31) == __ffs(peers) - 1) {
-    atomicAdd(cnt + root, n);
-    atomicMax(bbox + root, ymax);
-    atomicMin(bbox + w * h + root, xmin);
-    atomicMax(bbox + 2 * w * h + root, xmax);
+    const int c = cnt[i];
+    if (c > 0 && root != i) {   // a tile-local root under another tile's root: its aggregates move up
+      atomicAdd(cnt + root, c);
+      atomicMax(bbox + root, bbox[i]);
+      atomicMin(bbox + n + root, bbox[n + i]);
+      atomicMax(bbox + 2 * n + root, bbox[2 * n + i]);
+    }
   }
 }
 
-// components large enough to hold a chain of length_threshold + 1 pixels, in three size classes so that the walk
-// below starts the big ones first (the walk of one component is sequential: the largest component is the critical path)
-constexpr int kClassA = 1024, kClassB = 128;   // pixels
-__host__ __device__ inline int comp_cap_a(int n) { return n / kClassA + 1; }
+// Components large enough to hold a chain of length_threshold + 1 pixels are queued for the walk in three classes:
+//   BIG    the private bit map (bounding box rounded to 32-pixel words, plus padding) does not fit a warp's slice of the
+//          walk kernel's shared-memory arena: a whole CTA gathers it and one warp walks it, these go first (they are also
+//          the long ones: a walk is sequential and the longest component is the critical path of the launch);
+//   B, C   everything else, >= 128 pixels first: one WARP per component, the warps of a CTA work side by side.
+constexpr int kClassB = 128;            // pixels
+constexpr int kPadRows = 2;             // zero rows above and below the private bit map (the walk looks 2 pixels ahead)
+constexpr int kWalkThreads = 128;
+constexpr int kWalkWarps = kWalkThreads / 32;
+constexpr int kSliceWords = 1600;       // per-warp bit map slice (6.25 KB): e.g. 128 x 224 or 640 x 68 pixels of bounding box
 __host__ __device__ inline int comp_cap_b(int n) { return n / kClassB + 1; }
+// a BIG component spans > kSliceWords words, i.e. at least ~280 pixels in a row or column direction: at most n / kClassB of them
+__host__ __device__ inline int comp_cap_big(int n) { return n / kClassB + 1; }
 
+// counters: [0] BIG components, [1] BIG cursor, [2] chain-point cursor, [3] chains, [4] segments, [5] class-B components,
+//           [6] class-C components, [7] cursor over B then C
 template <class B>
-__global__ void k_ccl_roots(const __grid_constant__ B b, int w, int h, int min_pixels) {
+__global__ void k_ccl_roots(const __grid_constant__ B b, int w, int h, int min_pixels) {   // one thread per edge-map word
   const FldBuffers &fb = b.fld_of(blockIdx.y);
-  const int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt;
+  const int words_per_row = fb.words_per_row;
+  const int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt, *__restrict__ bbox = fb.bbox;
   int *__restrict__ comp_root = fb.comp_root, *__restrict__ counters = fb.counters;
   const int max_comps = fb.max_chains;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= w * h) return;
-  if (label[i] != i) return;
-  const int c = cnt[i];
-  if (c < min_pixels) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= words_per_row * h) return;
+  unsigned e = fb.edges[t];
+  if (!e) return;
+  const int y = t / words_per_row, xb = (t - y * words_per_row) << 5;
   const int n = w * h;
-  if (c >= kClassA) {
-    comp_root[atomicAdd(counters + 0, 1)] = i;                                   // at most n / kClassA of these
-  } else if (c >= kClassB) {
-    comp_root[comp_cap_a(n) + atomicAdd(counters + 5, 1)] = i;                   // at most n / kClassB
-  } else {
-    int k = atomicAdd(counters + 6, 1);
-    if (k < max_comps) comp_root[comp_cap_a(n) + comp_cap_b(n) + k] = i;
+  while (e) {
+    const int k = __ffs((int)e) - 1;
+    e &= e - 1;
+    const int x = xb + k;
+    if (x >= w) break;
+    const int i = y * w + x;
+    if (label[i] != i) continue;
+    const int c = cnt[i];
+    if (c < min_pixels) continue;
+    const int bh = bbox[i] - y + 1;
+    const int groups = (bbox[2 * n + i] >> 5) - (bbox[n + i] >> 5) + 1;
+    const bool big = (bh + 2 * kPadRows) * (groups + 2) > kSliceWords;
+    if (big) {
+      const int q = atomicAdd(counters + 0, 1);
+      if (q < comp_cap_big(n)) comp_root[q] = i;
+    } else if (c >= kClassB) {
+      comp_root[comp_cap_big(n) + atomicAdd(counters + 5, 1)] = i;                 // at most n / kClassB
+    } else {
+      const int q = atomicAdd(counters + 6, 1);
+      if (q < max_comps) comp_root[comp_cap_big(n) + comp_cap_b(n) + q] = i;
+    }
   }
 }
 
@@ -254,7 +404,9 @@ __global__ void k_ccl_roots(const __grid_constant__ B b, int w, int h, int min_p
 // permute once the direction is known, so the direction update is not on the path to the table address.
 // The neighbour key is taken from a 5 x 5 bit window B (bit 5 (r + 2) + (c + 2) = pixel (r, c) relative to the window
 // centre): for a pixel at offset (dr, dc) from the centre, Bs = B >> (6 + 5 dr + dc) has neighbour i at bit
-// {12, 11, 10, 5, 0, 1, 2, 7}[i], and key = (Bs & 0xA7) | ((Bs >> 2) & 0x700) packs those into 11 bits.
+// {12, 11, 10, 5, 0, 1, 2, 7}[i]; the key packs those 8 bits into one byte (bits 0-2 stay, 5 -> 3, 7 -> 4, 10-12 -> 5-7),
+// so the tables are 4.5 KB (they were 33 KB with an 11-bit key, which cost the kernel its co-residency with everything
+// else that needs shared memory).
 static int choose_neighbour_host(unsigned mask, int direction) {
   const int i0 = direction < 0 ? direction + 8 : direction;      // neighbour index with difference 0
   if ((mask >> i0) & 1u) return i0;
@@ -268,7 +420,7 @@ static int choose_neighbour_host(unsigned mask, int direction) {
 static inline int nb_dr(int i) { return (i <= 2) ? 1 : ((i == 3 || i == 7) ? 0 : -1); }
 static inline int nb_dc(int i) { return (i == 0 || i == 6 || i == 7) ? 1 : ((i == 1 || i == 5) ? 0 : -1); }
 
-constexpr int kKeys = 2048;
+constexpr int kKeys = 256;
 constexpr int kLut1 = 2 * kKeys * 8;    // [first step?][neighbour key][direction + 3] -> decision
 constexpr int kLut2 = 8 * 8 * 8;        // [min(step, 7)][direction + 3][i] -> next direction + 3
 constexpr int kLutSize = kLut1 + kLut2;
@@ -282,7 +434,7 @@ void init_fld_constants() {
   cudaGetDevice(&dev);
   if (g_walk_lut_ready[dev & 63]) return;
   static uint8_t lut[kLutSize];
-  static const int key_bit[8] = {10, 9, 8, 5, 0, 1, 2, 7};   // key bit of neighbour i (see above)
+  static const int key_bit[8] = {7, 6, 5, 3, 0, 1, 2, 4};   // key bit of neighbour i (see above)
   for (int first = 0; first < 2; first++)
     for (unsigned key = 0; key < (unsigned)kKeys; key++) {
       unsigned mask = 0;
@@ -307,12 +459,6 @@ void init_fld_constants() {
   g_walk_lut_ready[dev & 63] = true;
 }
 
-// counters: [0] class-A components, [1] next component to take, [2] chain-point cursor, [3] chains, [4] segments,
-//           [5] class-B components, [6] class-C components
-constexpr int kWalkThreads = 256;
-constexpr int kWalkCtas = 148 * 2;   // components are pulled from an atomic queue, biggest class first
-constexpr int kPadRows = 2;          // zero rows above and below the private bit map (the walk looks 2 pixels ahead)
-
 // explicit shared-memory accesses by 32-bit shared address (keeps the address arithmetic out of the walk loop)
 __device__ __forceinline__ unsigned lds_u32(unsigned addr) {
   unsigned v;
@@ -333,211 +479,227 @@ __device__ __forceinline__ void sts_u32(unsigned addr, unsigned v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-// One CTA per component.  All its warps gather the component's private bit map (shared memory: row stride
-// ws = groups + 2 words with one zero word on each side, two zero rows above and below; word g + 1 of row ly + 2 is the
-// component's part of edge word (y0 + ly, g0 + g), so the gather needs no shifting).  Then warp 0 walks.  The walk is a
-// chain of dependent steps and a GPU thread retires a dependent instruction every ~4 cycles, so the step is spread
-// over the warp and software-pipelined: lane j < 25 reads pixel j of the 5 x 5 window around the CURRENT pixel (one
-// shared load, one ballot) while the decision for the current pixel is taken from the window fetched around the
-// PREVIOUS pixel (shift, 11-bit key, one table look-up).  The dependent chain of a step is
-// shift -> key -> table load -> decode, ~90 cycles; the first version (one thread, 6 loads + ~150 instructions per
-// step) needed ~600.
+struct WalkCtx {
+  const unsigned *edges;
+  int words_per_row;
+  const int *label, *cnt, *bbox;
+  int *counters;
+  int2 *chain_pts;
+  int *chain_seed, *chain_off, *chain_len;
+  int max_chains, w, n, length_threshold;
+  bool vec4;
+};
+
+// Gather of one component's private bit map by `nw` warps (this is warp `wi` of them): private word = edge word AND
+// (label == root).  Row stride ws = groups + 2 words with one zero word on each side, kPadRows zero rows above and below;
+// word g + 1 of row ly + kPadRows is the component's part of edge word (y0 + ly, g0 + g), so no shifting is needed.  A
+// warp covers 128 pixels (4 words) per round with one 16-byte label load per lane, skipped where the edge map is empty.
+__device__ __forceinline__ void walk_gather(const WalkCtx &c, unsigned *bm, int root, int y0, int g0, int groups, int bh, int ws,
+                                            int wi, int nw, int lane) {
+  const int segs = (groups + 3) >> 2;          // 4-word segments per row
+  const int items = bh * segs;
+  const unsigned gmask = 0xffu << (lane & 24);
+  for (int it0 = wi * 4; it0 < items; it0 += nw * 4) {
+    int4 lab[4];
+    unsigned nib[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int it = it0 + u;
+      nib[u] = 0;
+      lab[u] = make_int4(-2, -2, -2, -2);
+      if (it < items) {
+        const int ly = it / segs, sg = it - ly * segs;
+        const int g = 4 * sg + (lane >> 3);
+        if (g < groups) {
+          const unsigned e = __ldg(c.edges + (size_t)(y0 + ly) * c.words_per_row + g0 + g);
+          nib[u] = (e >> (4 * (lane & 7))) & 15u;
+          if (nib[u]) {
+            const int *lp = c.label + (size_t)(y0 + ly) * c.w + ((g0 + g) << 5) + 4 * (lane & 7);
+            if (c.vec4) {
+              lab[u] = *reinterpret_cast<const int4 *>(lp);
+            } else {
+              if (nib[u] & 1u) lab[u].x = lp[0];
+              if (nib[u] & 2u) lab[u].y = lp[1];
+              if (nib[u] & 4u) lab[u].z = lp[2];
+              if (nib[u] & 8u) lab[u].w = lp[3];
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int it = it0 + u;
+      unsigned bits = (lab[u].x == root ? 1u : 0u) | (lab[u].y == root ? 2u : 0u) | (lab[u].z == root ? 4u : 0u) |
+                      (lab[u].w == root ? 8u : 0u);
+      bits = (bits & nib[u]) << (4 * (lane & 7));
+      const unsigned word = __reduce_or_sync(gmask, bits);
+      if ((lane & 7) == 0 && word && it < items) {
+        const int ly = it / segs, sg = it - ly * segs;
+        bm[(ly + kPadRows) * ws + 1 + 4 * sg + (lane >> 3)] = word;
+      }
+    }
+  }
+}
+
+// The sequential part, one warp: raster-order seeds, one chain per seed.  The walk is a chain of dependent steps and a GPU
+// thread retires a dependent instruction every ~4 cycles, so the step is spread over the warp and software-pipelined:
+// lane j < 25 reads pixel j of the 5 x 5 window around the CURRENT pixel (one shared load, one ballot) while the decision
+// for the current pixel is taken from the window fetched around the PREVIOUS pixel (shift, 8-bit key, one table look-up).
+// All state is warp-uniform.
+__device__ __forceinline__ void walk_component(const WalkCtx &c, unsigned *bm, unsigned lut_addr, int root, int y0, int g0, int groups,
+                                               int bh, int ws, int lane) {
+  const int my_dr = lane < 25 ? lane / 5 - 2 : 0;   // this lane's pixel of the window (lanes >= 25 look at the centre; their
+  const int my_dc = lane < 25 ? lane % 5 - 2 : 0;   // ballot bits are dropped)
+  int npts = 0;
+  if (lane == 0) npts = atomicAdd(c.counters + 2, c.cnt[root]);   // this component's slice of the chain-point pool
+  npts = __shfl_sync(0xffffffffu, npts, 0);
+  const int xbase = (g0 << 5) - 32;                // global x of bit 0 of a private row
+  const unsigned bm_addr = (unsigned)__cvta_generic_to_shared(bm);
+  const int my_off = my_dr * ws;
+  int sy = 0, sg = 0;                              // scan position (row, word): everything before it is consumed
+  while (sy < bh) {
+    // next seed: first set bit at or after the scan position, 32 words per probe
+    const int g = sg + lane;
+    const unsigned v = g < groups ? bm[(sy + kPadRows) * ws + 1 + g] : 0u;
+    const unsigned any = __ballot_sync(0xffffffffu, v != 0);
+    if (!any) {
+      sg += 32;
+      if (sg >= groups) { sg = 0; sy++; }
+      continue;
+    }
+    const int first = __ffs(any) - 1;
+    const unsigned wv = __shfl_sync(0xffffffffu, v, first);
+    sg += first;
+    // ---- walk one chain; p = bit position in the private row (pixel local x + 32), rb = word index of the row start
+    int p = ((sg + 1) << 5) + __ffs(wv) - 1, cy = sy;
+    int rb = (cy + kPadRows) * ws;
+    const int start = npts;
+    const int seed = (y0 + cy) * c.w + xbase + p;
+    int step = 0;
+    unsigned dsel = 0, sh = 6;              // dsel: running direction + 3 (byte selector)
+    unsigned tb = lut_addr + kKeys * 8;     // first-step half of the table
+    // consume the seed, then fetch its 5 x 5 window
+    if (lane == 0) sts_u32(bm_addr + 4u * (unsigned)(rb + (p >> 5)), wv & ~(1u << (p & 31)));
+    __syncwarp();   // the other lanes' window loads below must see the cleared bit (memory ordering inside the warp)
+    unsigned Bw;
+    {
+      const int qb = p + my_dc;
+      const unsigned word = lds_u32(bm_addr + 4u * (unsigned)(rb + my_off + (qb >> 5)));
+      Bw = __ballot_sync(0xffffffffu, (word >> (qb & 31)) & 1u);
+    }
+    while (true) {
+      // Bw: window around the previous pixel (the seed itself in the first round); the current pixel sits at offset
+      // (dr, dc) of the previous move inside it and sh = 6 + 5 dr + dc.  Start fetching the current pixel's window.
+      const int qb = p + my_dc;
+      const unsigned waddr = bm_addr + 4u * (unsigned)(rb + my_off + (qb >> 5));
+      const unsigned word = lds_u32(waddr);
+      const unsigned Bs = Bw >> sh;
+      const unsigned key = (Bs & 7u) | ((Bs >> 2) & 8u) | ((Bs >> 3) & 16u) | ((Bs >> 5) & 0xE0u);
+      const uint2 ev = lds_u64(tb + key * 8u);
+      if (lane == 0) c.chain_pts[npts] = make_int2(xbase + p, y0 + cy);
+      npts++;
+      Bw = __ballot_sync(0xffffffffu, (word >> (qb & 31)) & 1u);
+      const unsigned e = __byte_perm(ev.x, ev.y, dsel);   // byte dsel of the 8 entries
+      const unsigned i = e & 15u;
+      if (i == 8u) break;
+      dsel = lds_u8(lut_addr + kLut1 + ((unsigned)min(step, 7) * 8u + dsel) * 8u + i);
+      step++;
+      tb = lut_addr;
+      const unsigned r1 = (e >> 4) & 3u, c1 = (e >> 6) & 3u;   // dr + 1, dc + 1
+      sh = 5u * r1 + c1;
+      // consume the new pixel: the lane that just fetched it (window position 6 + sh) rewrites its word without it
+      if (lane == (int)(sh + 6u)) sts_u32(waddr, word & ~(1u << (qb & 31)));
+      __syncwarp();   // orders the store before the next round's window loads of the other lanes (and the seed scan)
+      p += (int)c1 - 1;
+      cy += (int)r1 - 1;
+      rb += ((int)r1 - 1) * ws;
+    }
+    if (npts - start < c.length_threshold + 1) {
+      npts = start;  // chain too short: dropped (its pixels stay consumed)
+    } else if (lane == 0) {
+      const int k = atomicAdd(c.counters + 3, 1);
+      if (k < c.max_chains) {
+        c.chain_seed[k] = seed;
+        c.chain_off[k] = start;
+        c.chain_len[k] = npts - start;
+      }
+    }
+  }
+}
+
+// grid = (walkers, frame).  Phase 1: the CTA takes BIG components one at a time (all warps gather into the whole arena,
+// warp 0 walks).  Phase 2: every warp takes components of its own from the common queue (B then C) and works in its slice
+// of the arena; no block-wide synchronisation any more.
 template <class B>
 __global__ void __launch_bounds__(kWalkThreads)
     k_fld_walk_cc(const __grid_constant__ B b, int w, int h, int length_threshold) {
   const FldBuffers &fb = b.fld_of(blockIdx.y);
-  const unsigned *__restrict__ edges = fb.edges;
-  const int words_per_row = fb.words_per_row;
-  const int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt, *__restrict__ bbox = fb.bbox;
+  WalkCtx c;
+  c.edges = fb.edges;
+  c.words_per_row = fb.words_per_row;
+  c.label = fb.label;
+  c.cnt = fb.cnt;
+  c.bbox = fb.bbox;
+  c.counters = fb.counters;
+  c.chain_pts = fb.chain_pts;
+  c.chain_seed = fb.chain_seed;
+  c.chain_off = fb.chain_off;
+  c.chain_len = fb.chain_len;
+  c.max_chains = fb.max_chains;
+  c.w = w;
+  c.n = w * h;
+  c.length_threshold = length_threshold;
+  c.vec4 = (w & 3) == 0;
   const int *__restrict__ comp_root = fb.comp_root;
-  int *__restrict__ counters = fb.counters;
-  const int max_comps = fb.max_chains, max_chains = fb.max_chains;
-  int2 *__restrict__ chain_pts = fb.chain_pts;
-  int *__restrict__ chain_seed = fb.chain_seed, *__restrict__ chain_off = fb.chain_off, *__restrict__ chain_len = fb.chain_len;
-  extern __shared__ __align__(16) uint8_t walk_smem[];   // decision tables, then the private bit map
+  extern __shared__ __align__(16) uint8_t walk_smem[];   // decision tables, then the bit map arena
   uint8_t *lut = walk_smem;
-  unsigned *bm = reinterpret_cast<unsigned *>(walk_smem + kLutSize);
+  unsigned *arena = reinterpret_cast<unsigned *>(walk_smem + kLutSize);
   __shared__ int s_ci;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = w * h;
-  const int nA = min(counters[0], comp_cap_a(n)), nB = min(counters[5], comp_cap_b(n)), nC = min(counters[6], max_comps);
-  const int ncomp = nA + nB + nC;
-  if ((int)blockIdx.x >= ncomp) return;
+  const int n = c.n;
+  const int nBig = min(c.counters[0], comp_cap_big(n));
+  const int nB = min(c.counters[5], comp_cap_b(n)), nC = min(c.counters[6], c.max_chains);
+  const int nSmall = nB + nC;
+  // a CTA that can get neither a BIG component nor (as one of its warps) a small one has nothing to do
+  if ((int)blockIdx.x >= nBig && (int)blockIdx.x * kWalkWarps >= nSmall) return;
   for (int i = tid; i < kLutSize / 4; i += kWalkThreads)
     reinterpret_cast<unsigned *>(lut)[i] = reinterpret_cast<const unsigned *>(g_walk_lut)[i];
-  const bool vec4 = (w & 3) == 0;
-  // this lane's pixel of the 5 x 5 window (lanes >= 25 look at the centre; their ballot bits are dropped)
-  const int my_dr = lane < 25 ? lane / 5 - 2 : 0;
-  const int my_dc = lane < 25 ? lane % 5 - 2 : 0;
+  const unsigned lut_addr = (unsigned)__cvta_generic_to_shared(lut);
+  // ---- phase 1
   while (true) {
     __syncthreads();   // the previous component's walk is finished (and the table is in place)
-    if (tid == 0) s_ci = atomicAdd(counters + 1, 1);
+    if (tid == 0) s_ci = nBig > 0 ? atomicAdd(c.counters + 1, 1) : 0x7fffffff;
     __syncthreads();
     const int q = s_ci;
-    if (q >= ncomp) break;
-    const int root = comp_root[q < nA ? q : (q < nA + nB ? comp_cap_a(n) + (q - nA) : comp_cap_a(n) + comp_cap_b(n) + (q - nA - nB))];
-    const int y0 = root / w, y1 = bbox[root];
-    const int g0 = bbox[n + root] >> 5, g1 = bbox[2 * n + root] >> 5;
-    const int groups = g1 - g0 + 1, bh = y1 - y0 + 1;
-    const int ws = groups + 2;
-    for (int i = tid; i < (bh + 2 * kPadRows) * ws; i += kWalkThreads) bm[i] = 0;
+    if (q >= nBig) break;
+    const int root = comp_root[q];
+    const int y0 = root / w, y1 = c.bbox[root];
+    const int g0 = c.bbox[n + root] >> 5, g1 = c.bbox[2 * n + root] >> 5;
+    const int groups = g1 - g0 + 1, bh = y1 - y0 + 1, ws = groups + 2;
+    for (int i = tid; i < (bh + 2 * kPadRows) * ws; i += kWalkThreads) arena[i] = 0;
     __syncthreads();
-    // ---- gather: private word = edge word AND (label == root).  A warp covers 128 pixels (4 words) per round with one
-    // 16-byte label load per lane, skipped where the edge map is empty; 4 rounds in flight.
-    {
-      const int segs = (groups + 3) >> 2;          // 4-word segments per row
-      const int items = bh * segs;
-      const unsigned gmask = 0xffu << (lane & 24);
-      for (int it0 = warp * 4; it0 < items; it0 += (kWalkThreads / 32) * 4) {
-        int4 lab[4];
-        unsigned nib[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int it = it0 + u;
-          nib[u] = 0;
-          lab[u] = make_int4(-2, -2, -2, -2);
-          if (it < items) {
-            const int ly = it / segs, sg = it - ly * segs;
-            const int g = 4 * sg + (lane >> 3);
-            if (g < groups) {
-              const unsigned e = __ldg(edges + (size_t)(y0 + ly) * words_per_row + g0 + g);
-              nib[u] = (e >> (4 * (lane & 7))) & 15u;
-              if (nib[u]) {
-                const int *lp = label + (size_t)(y0 + ly) * w + ((g0 + g) << 5) + 4 * (lane & 7);
-                if (vec4) {
-                  lab[u] = *reinterpret_cast<const int4 *>(lp);
-                } else {
-                  if (nib[u] & 1u) lab[u].x = lp[0];
-                  if (nib[u] & 2u) lab[u].y = lp[1];
-                  if (nib[u] & 4u) lab[u].z = lp[2];
-                  if (nib[u] & 8u) lab[u].w = lp[3];
-                }
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int it = it0 + u;
-          unsigned bits = (lab[u].x == root ? 1u : 0u) | (lab[u].y == root ? 2u : 0u) | (lab[u].z == root ? 4u : 0u) |
-                          (lab[u].w == root ? 8u : 0u);
-          bits = (bits & nib[u]) << (4 * (lane & 7));
-          const unsigned word = __reduce_or_sync(gmask, bits);
-          if ((lane & 7) == 0 && word && it < items) {
-            const int ly = it / segs, sg = it - ly * segs;
-            bm[(ly + kPadRows) * ws + 1 + 4 * sg + (lane >> 3)] = word;
-          }
-        }
-      }
-    }
+    walk_gather(c, arena, root, y0, g0, groups, bh, ws, warp, kWalkWarps, lane);
     __syncthreads();
-    if (warp != 0) continue;   // warp 0 scans and walks; the others wait at the barrier above
-#ifdef PLVIWO_WALK_PROF
-    long long prof_t0 = clock64(), prof_scan = 0, prof_walk = 0, prof_pro = 0, prof_epi = 0;
-    int prof_chains = 0, prof_probes = 0;
-#endif
-    // ---- sequential part: raster-order seeds, one chain per seed.  All state below is warp-uniform.
-    int npts = 0;
-    if (lane == 0) npts = atomicAdd(counters + 2, cnt[root]);   // this component's slice of the chain-point pool
-    npts = __shfl_sync(0xffffffffu, npts, 0);
-    const int xbase = (g0 << 5) - 32;                // global x of bit 0 of a private row
-    const unsigned bm_addr = (unsigned)__cvta_generic_to_shared(bm), lut_addr = (unsigned)__cvta_generic_to_shared(lut);
-    const int my_off = my_dr * ws;
-    int sy = 0, sg = 0;                              // scan position (row, word): everything before it is consumed
-    while (sy < bh) {
-      // next seed: first set bit at or after the scan position, 32 words per probe
-#ifdef PLVIWO_WALK_PROF
-      long long prof_a = clock64();
-      prof_probes++;
-#endif
-      const int g = sg + lane;
-      const unsigned v = g < groups ? bm[(sy + kPadRows) * ws + 1 + g] : 0u;
-      const unsigned any = __ballot_sync(0xffffffffu, v != 0);
-      if (!any) {
-        sg += 32;
-        if (sg >= groups) { sg = 0; sy++; }
-        continue;
-      }
-      const int first = __ffs(any) - 1;
-      const unsigned wv = __shfl_sync(0xffffffffu, v, first);
-      sg += first;
-      // ---- walk one chain; p = bit position in the private row (pixel local x + 32), rb = word index of the row start
-      int p = ((sg + 1) << 5) + __ffs(wv) - 1, cy = sy;
-      int rb = (cy + kPadRows) * ws;
-      const int start = npts;
-      const int seed = (y0 + cy) * w + xbase + p;
-      int step = 0;
-      unsigned dsel = 0, sh = 6;              // dsel: running direction + 3 (byte selector)
-      unsigned tb = lut_addr + kKeys * 8;     // first-step half of the table
-#ifdef PLVIWO_WALK_PROF
-      long long prof_b = clock64();
-      prof_scan += prof_b - prof_a;
-      prof_chains++;
-#endif
-      // consume the seed (lane 0 still holds nothing of it: the scan word wv is the seed's word), then fetch its 5 x 5
-      // window.  Shared-memory operations of one warp execute in order, so the loads see the cleared bit.
-      if (lane == 0) sts_u32(bm_addr + 4u * (unsigned)(rb + (p >> 5)), wv & ~(1u << (p & 31)));
-      __syncwarp();   // the other lanes' window loads below must see the cleared bit (memory ordering inside the warp)
-      unsigned B;
-      {
-        const int qb = p + my_dc;
-        const unsigned word = lds_u32(bm_addr + 4u * (unsigned)(rb + my_off + (qb >> 5)));
-        B = __ballot_sync(0xffffffffu, (word >> (qb & 31)) & 1u);
-      }
-#ifdef PLVIWO_WALK_PROF
-      long long prof_c = clock64();
-      prof_pro += prof_c - prof_b;
-#endif
-      while (true) {
-        // B: window around the previous pixel (the seed itself in the first round); the current pixel sits at offset
-        // (dr, dc) of the previous move inside it and sh = 6 + 5 dr + dc.  Start fetching the current pixel's window.
-        const int qb = p + my_dc;
-        const unsigned waddr = bm_addr + 4u * (unsigned)(rb + my_off + (qb >> 5));
-        const unsigned word = lds_u32(waddr);
-        const unsigned Bs = B >> sh;
-        const unsigned key = (Bs & 0xA7u) | ((Bs >> 2) & 0x700u);
-        const uint2 ev = lds_u64(tb + key * 8u);
-        if (lane == 0) chain_pts[npts] = make_int2(xbase + p, y0 + cy);
-        npts++;
-        B = __ballot_sync(0xffffffffu, (word >> (qb & 31)) & 1u);
-        const unsigned e = __byte_perm(ev.x, ev.y, dsel);   // byte dsel of the 8 entries
-        const unsigned i = e & 15u;
-        if (i == 8u) break;
-        dsel = lds_u8(lut_addr + kLut1 + ((unsigned)min(step, 7) * 8u + dsel) * 8u + i);
-        step++;
-        tb = lut_addr;
-        const unsigned r1 = (e >> 4) & 3u, c1 = (e >> 6) & 3u;   // dr + 1, dc + 1
-        sh = 5u * r1 + c1;
-        // consume the new pixel: the lane that just fetched it (window position 6 + sh) rewrites its word without it
-        if (lane == (int)(sh + 6u)) sts_u32(waddr, word & ~(1u << (qb & 31)));
-        __syncwarp();   // orders the store before the next round's window loads of the other lanes (and the seed scan)
-        p += (int)c1 - 1;
-        cy += (int)r1 - 1;
-        rb += ((int)r1 - 1) * ws;
-      }
-#ifdef PLVIWO_WALK_PROF
-      long long prof_d = clock64();
-      prof_walk += prof_d - prof_c;
-#endif
-      if (npts - start < length_threshold + 1) {
-        npts = start;  // chain too short: dropped (its pixels stay consumed)
-      } else if (lane == 0) {
-        const int c = atomicAdd(counters + 3, 1);
-        if (c < max_chains) {
-          chain_seed[c] = seed;
-          chain_off[c] = start;
-          chain_len[c] = npts - start;
-        }
-      }
-#ifdef PLVIWO_WALK_PROF
-      prof_epi += clock64() - prof_d;
-#endif
-    }
-#ifdef PLVIWO_WALK_PROF
-    if (lane == 0 && cnt[root] >= 512)
-      printf("comp root %d px %d bbox %dx%d: total %lld cyc, scan %lld (probes %d), prologue %lld, loop %lld, epilogue %lld, chains %d\n", root, cnt[root], groups * 32,
-             bh, clock64() - prof_t0, prof_scan, prof_probes, prof_pro, prof_walk, prof_epi, prof_chains);
-#endif
+    if (warp == 0) walk_component(c, arena, lut_addr, root, y0, g0, groups, bh, ws, lane);
+  }
+  // ---- phase 2
+  unsigned *bm = arena + warp * kSliceWords;
+  while (true) {
+    int q = 0;
+    if (lane == 0) q = atomicAdd(c.counters + 7, 1);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q >= nSmall) break;
+    const int root = comp_root[q < nB ? comp_cap_big(n) + q : comp_cap_big(n) + comp_cap_b(n) + (q - nB)];
+    const int y0 = root / w, y1 = c.bbox[root];
+    const int g0 = c.bbox[n + root] >> 5, g1 = c.bbox[2 * n + root] >> 5;
+    const int groups = g1 - g0 + 1, bh = y1 - y0 + 1, ws = groups + 2;
+    for (int i = lane; i < (bh + 2 * kPadRows) * ws; i += 32) bm[i] = 0;
+    __syncwarp();
+    walk_gather(c, bm, root, y0, g0, groups, bh, ws, 0, 1, lane);
+    __syncwarp();
+    walk_component(c, bm, lut_addr, root, y0, g0, groups, bh, ws, lane);
+    __syncwarp();
   }
 }
 
@@ -753,7 +915,7 @@ int FldBuffers::alloc(int w, int h, int length_threshold, int out_capacity) {
   A(&label, (n + 32) * sizeof(int));   // slack: the walk gathers labels with 16-byte loads
   A(&cnt, n * sizeof(int));
   A(&bbox, 3 * n * sizeof(int));
-  A(&comp_root, (size_t)(max_chains + comp_cap_a((int)n) + comp_cap_b((int)n)) * sizeof(int));
+  A(&comp_root, (size_t)(max_chains + comp_cap_big((int)n) + comp_cap_b((int)n)) * sizeof(int));
   A(&counters, 8 * sizeof(int));
   A(&chain_pts, n * sizeof(int2));
   A(&chain_seed, (size_t)max_chains * sizeof(int));
@@ -779,28 +941,36 @@ static void launch_fld_any(const B &b, int nb_frames, int w, int h, int max_chai
                            cudaStream_t s, cudaEvent_t *ev) {
   const int n = w * h;
   const int tpb = 256, nb = (n + tpb - 1) / tpb;
-  const dim3 gpx(nb, nb_frames);
-  PLVIWO_CARVEOUT(k_ccl_init<B>);
-  k_ccl_init<B><<<gpx, tpb, 0, s>>>(b, w, h);
-  PLVIWO_CARVEOUT(k_ccl_merge<B>);
-  k_ccl_merge<B><<<gpx, tpb, 0, s>>>(b, w, h);
+  PLVIWO_CARVEOUT(k_ccl_tile<B>);
+  k_ccl_tile<B><<<dim3((w + kTileW - 1) / kTileW, (h + kTileH - 1) / kTileH, nb_frames), kTileThreads, 0, s>>>(b, w, h);
+  const int nborder = ((h - 1) / kTileH) * w + ((w - 1) / kTileW) * h;
+  if (nborder > 0) {
+    PLVIWO_CARVEOUT(k_ccl_border<B>);
+    k_ccl_border<B><<<dim3((nborder + tpb - 1) / tpb, nb_frames), tpb, 0, s>>>(b, w, h);
+  }
+  const int nwords = ((w + 31) / 32) * h;
   PLVIWO_CARVEOUT(k_ccl_flatten<B>);
-  k_ccl_flatten<B><<<gpx, tpb, 0, s>>>(b, w, h);
+  k_ccl_flatten<B><<<dim3((nwords + tpb - 1) / tpb, nb_frames), tpb, 0, s>>>(b, w, h);
   PLVIWO_CARVEOUT(k_ccl_roots<B>);
-  k_ccl_roots<B><<<gpx, tpb, 0, s>>>(b, w, h, length_threshold + 1);
+  k_ccl_roots<B><<<dim3((nwords + tpb - 1) / tpb, nb_frames), tpb, 0, s>>>(b, w, h, length_threshold + 1);
   if (ev) cudaEventRecord(ev[0], s);
   init_fld_constants();
   const int ws = ((w + 31) >> 5) + 2;
-  size_t smem = (size_t)kLutSize + (size_t)(h + 2 * kPadRows) * ws * sizeof(unsigned);
+  const size_t arena_words = std::max<size_t>((size_t)(h + 2 * kPadRows) * ws, (size_t)kWalkWarps * kSliceWords);
+  size_t smem = (size_t)kLutSize + arena_words * sizeof(unsigned);
   static SmemOptIn optin;
   optin.ensure(k_fld_walk_cc<B>, smem);
-  // Grid size per frame: the walk is bound by its longest component (a sequential chain of ~130-cycle steps), not by the
-  // number of walkers; a batch of frames shares one launch (grid.y = frame).  PLVIWO_WALK_CTAS overrides.
+  // Walkers per frame: components are pulled from atomic queues (BIG ones by whole CTAs, the rest by single warps), the
+  // launch lasts as long as its longest component; a batch of frames shares one launch (grid.y = frame).
   static const int walk_ctas_env = [] {
     const char *e = std::getenv("PLVIWO_WALK_CTAS");
     return e ? std::atoi(e) : 0;
   }();
-  const int walk_ctas = walk_ctas_env > 0 ? walk_ctas_env : (nb_frames > 8 ? 64 : (nb_frames > 1 ? 148 : kWalkCtas));
+  // A walker CTA holds 30 KB of shared memory for as long as its components last (milliseconds for the few long ones): in a
+  // launch over many frames the walkers are kept scarce (256 per launch, < 2 per SM) so that the other kernels of the
+  // pipeline — other streams, other ticks — stay resident beside them; the walk's WORK is small, its duration is the
+  // latency of the longest component either way.
+  const int walk_ctas = walk_ctas_env > 0 ? walk_ctas_env : (nb_frames > 1 ? std::max(2, std::min(74, 256 / nb_frames)) : 148);
   PLVIWO_CARVEOUT(k_fld_walk_cc<B>);
   k_fld_walk_cc<B><<<dim3(walk_ctas, nb_frames), kWalkThreads, smem, s>>>(b, w, h, length_threshold);
   if (ev) cudaEventRecord(ev[1], s);

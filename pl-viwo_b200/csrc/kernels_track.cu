@@ -10,6 +10,7 @@
 #include "fe_group_dev.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <cfloat>
 #include <cstdio>
@@ -157,6 +158,27 @@ void launch_corner_subpix_batch(const SlotRec *slots, const FrontJob *jobs, int 
   launch_corner_subpix(DevImage(), nullptr, nullptr, -1, 0);   // constant table of this device
   PLVIWO_CARVEOUT(k_corner_subpix_b);
   k_corner_subpix_b<<<dim3((n + kSpWarps - 1) / kSpWarps, n_jobs), kSpWarps * 32, 0, s>>>(slots, jobs, n, g.nfg);
+}
+
+// Stream group: cornerSubPix of the candidates the top-off detection of a frame really considers (the corners of the valid
+// cells that pass the mask test: a few dozen per frame), between the two halves of the detection.  Same body, same result
+// per corner as refining the whole candidate table ahead of time, at a tenth of the work.
+__global__ void __launch_bounds__(kSpWarps * 32)
+    k_corner_subpix_g(const __grid_constant__ GroupDev g, const TrackJob *__restrict__ jobs) {
+  const TrackJob &job = jobs[blockIdx.y];
+  const int s = job.stream;
+  const int n = g.winfo[4 * s + 3];
+  if ((int)blockIdx.x * kSpWarps >= n) return;
+  const bool first = g.wmode[s] == 1;
+  const DevImage &im = g.slots[first ? job.cur_slot : job.prev_slot].lvl[0];
+  const size_t o = (size_t)s * g.cand_cap;
+  corner_subpix_body(im.p, im.w, im.h, im.pitch, g.ext_in + o, g.ext_pt + o, n, nullptr, 0);
+}
+void launch_group_subpix(const GroupDev &g, const TrackJob *jobs, int n_jobs, cudaStream_t s) {
+  if (n_jobs <= 0 || g.cand_cap <= 0) return;
+  launch_corner_subpix(DevImage(), nullptr, nullptr, -1, 0);   // constant table of this device
+  PLVIWO_CARVEOUT(k_corner_subpix_g);
+  k_corner_subpix_g<<<dim3((g.cand_cap + kSpWarps - 1) / kSpWarps, n_jobs), kSpWarps * 32, 0, s>>>(g, jobs);
 }
 
 // ============================================================================================== undistort
@@ -745,6 +767,263 @@ __global__ void __launch_bounds__(kLk15MaxLevels * 32)
   lk15_body(a, pts0, pts1, status, p0n, p1n, n, host_flag, flag_value, done_counter, tab_cnt, tab_stride);
 }
 
+// ------------------------------------------------------------------------------ LK, 15 x 15 window, one warp per feature
+// The throughput form of k_lk15, for launches that carry thousands of features (stream groups).  k_lk15 minimises the
+// LATENCY of one feature: a CTA per feature, six warps building the levels side by side, four warps sharing the iteration
+// chain with a barrier per iteration — every warp repeats the scalar part of an iteration, and an SM holds 10 features.
+// Here ONE warp owns a feature: it builds level l (the same code, so the float normal matrix is summed in the same order),
+// then runs level l's iterations alone — lane (row, half) owns 8 (7) adjacent window pixels of one row, their I / Ix / Iy
+// values and the 2 x 9 block of the next image under them stay in registers, no barrier, no exchange through shared memory
+// — and moves on to level l - 1.  The mismatch sums are exact integers (per-lane 64-bit, warp reductions on 16-bit pieces),
+// so the split of the window over lanes cannot change a bit: results are identical to k_lk15's (tests/test_group_gpu.py
+// compares a group, which runs this kernel, with single handles, which run k_lk15).  An SM holds 32+ features.
+constexpr int kLkwWarps = 4;
+struct LkwSmem {
+  uint8_t raw[(kW15 + 3) * (kW15 + 3) + 12];
+  short ddx[(kW15 + 1) * (kW15 + 1)];
+  short ddy[(kW15 + 1) * (kW15 + 1)];
+  __align__(16) short patch[3][kW15][16];   // [I, Ix, Iy][window row][window column (15 used, column 15 = 0)]
+  uint8_t jreg[kJR * kJR + 7];
+};
+
+template <class Args>
+__device__ __forceinline__ void lk15w_body(const Args &a, const float2 *__restrict__ pts0, float2 *__restrict__ pts1,
+                                           uint8_t *__restrict__ status, float2 *__restrict__ p0n, float2 *__restrict__ p1n, int pi,
+                                           LkwSmem &sm) {
+  constexpr int win = kW15, np = win + 3, nd = win + 1;
+  constexpr int kRawLoads = (np * np + 31) / 32;   // 11
+  const int lane = threadIdx.x & 31;
+  const int r0 = (lane >> 2) * 2, c0 = (lane & 3) * 4;   // set-up: this lane's 2 x 4 block of window pixels
+  const int wy = lane >> 1, wx = (lane & 1) * 8;         // chain: this lane's row and its 8 adjacent pixels
+  const bool own = wy < win;
+  const float2 prev_in = pts0[pi];
+  const float half = (win - 1) * 0.5f;
+  const float FLT_SCALE = 1.f / (1 << 20);
+  float2 next = a.flow_is_zero ? prev_in : pts1[pi];   // OPTFLOW_USE_INITIAL_FLOW
+  bool ok = true;
+#pragma unroll 1
+  for (int level = a.max_level; level >= 0; level--) {
+    const int cols = a.w[level], rows = a.h[level];
+    const float lscale = 1.f / (float)(1 << level);
+    if (level == a.max_level) {
+      next.x = next.x * lscale;
+      next.y = next.y * lscale;
+    } else {
+      next.x = next.x * 2.f;
+      next.y = next.y * 2.f;
+    }
+    // ---- set-up of this level (k_lk15's, verbatim): raw neighbourhood, Scharr derivatives, fixed-point patches, A
+    const float px = prev_in.x * lscale - half, py = prev_in.y * lscale - half;
+    const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
+    const bool in_range = !(ipx < -win || ipx >= cols || ipy < -win || ipy >= rows);
+    if (!in_range) {
+      if (level == 0) ok = false;
+      continue;
+    }
+    float A11 = 0, A12 = 0, A22 = 0;
+    __syncwarp();   // the previous level's patches have been read by every lane
+    {
+      uint8_t *raw = sm.raw;
+      short *ddx = sm.ddx, *ddy = sm.ddy;
+      {
+        const uint8_t *I = a.p0[level];
+        const int pitchI = a.pitch0[level];
+        uint8_t v[kRawLoads];
+#pragma unroll
+        for (int j = 0; j < kRawLoads; j++) {
+          const int i = lane + 32 * j;
+          v[j] = 0;
+          if (i < np * np) {
+            const int r = i / np, c = i - r * np;
+            v[j] = I[(size_t)reflect101(ipy - 1 + r, rows) * pitchI + reflect101(ipx - 1 + c, cols)];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kRawLoads; j++)
+          if (lane + 32 * j < np * np) raw[lane + 32 * j] = v[j];
+      }
+      const float fa = px - ipx, fb = py - ipy;
+      const int iw00 = __float2int_rn((1.f - fa) * (1.f - fb) * 16384.f);
+      const int iw01 = __float2int_rn(fa * (1.f - fb) * 16384.f);
+      const int iw10 = __float2int_rn((1.f - fa) * fb * 16384.f);
+      const int iw11 = 16384 - iw00 - iw01 - iw10;
+      __syncwarp();
+      for (int i = lane; i < nd * nd; i += 32) {
+        int r = i / nd, c = i - r * nd;
+        int gx = ipx + c, gy = ipy + r;
+        int vx = 0, vy = 0;
+        if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
+          const uint8_t *q = raw + (r + 1) * np + (c + 1);
+          int tl = q[-np - 1], tc = q[-np], tr = q[-np + 1];
+          int ml = q[-1], mr = q[1];
+          int bl = q[np - 1], bc = q[np], br = q[np + 1];
+          vx = 3 * (tr + br) + 10 * mr - 3 * (tl + bl) - 10 * ml;
+          vy = 3 * (bl + br) + 10 * bc - 3 * (tl + tr) - 10 * tc;
+        }
+        ddx[i] = (short)vx;
+        ddy[i] = (short)vy;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int y = r0 + (k >> 2), x = c0 + (k & 3);
+        int ival = 0, ixval = 0, iyval = 0;
+        if (y < win && x < win) {
+          const uint8_t *q = raw + (y + 1) * np + (x + 1);
+          ival = (q[0] * iw00 + q[1] * iw01 + q[np] * iw10 + q[np + 1] * iw11 + (1 << 8)) >> 9;
+          const int di = y * nd + x;
+          ixval = (ddx[di] * iw00 + ddx[di + 1] * iw01 + ddx[di + nd] * iw10 + ddx[di + nd + 1] * iw11 + (1 << 13)) >> 14;
+          iyval = (ddy[di] * iw00 + ddy[di + 1] * iw01 + ddy[di + nd] * iw10 + ddy[di + nd + 1] * iw11 + (1 << 13)) >> 14;
+        }
+        if (y < win && x < 16) {
+          sm.patch[0][y][x] = (short)ival;
+          sm.patch[1][y][x] = (short)ixval;
+          sm.patch[2][y][x] = (short)iyval;
+        }
+        A11 += (float)(ixval * ixval);
+        A12 += (float)(ixval * iyval);
+        A22 += (float)(iyval * iyval);
+      }
+      A11 = warp_sum(A11) * FLT_SCALE;
+      A12 = warp_sum(A12) * FLT_SCALE;
+      A22 = warp_sum(A22) * FLT_SCALE;
+    }
+    __syncwarp();
+    float Dt = A11 * A22 - A12 * A12;
+    const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+    if (minEig < a.min_eig || Dt < FLT_EPSILON) {
+      if (level == 0) ok = false;
+      continue;
+    }
+    Dt = 1.f / Dt;
+    // ---- this lane's 8 window pixels: I, Ix, Iy (int16 pairs, one 16-byte load per patch)
+    int Iw[8], Ix[8], Iy[8];
+    {
+      uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0;
+      if (own) {
+        q0 = *reinterpret_cast<const uint4 *>(&sm.patch[0][wy][wx]);
+        q1 = *reinterpret_cast<const uint4 *>(&sm.patch[1][wy][wx]);
+        q2 = *reinterpret_cast<const uint4 *>(&sm.patch[2][wy][wx]);
+      }
+      const unsigned w0[4] = {q0.x, q0.y, q0.z, q0.w}, w1[4] = {q1.x, q1.y, q1.z, q1.w}, w2[4] = {q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        Iw[2 * k] = (short)(w0[k] & 0xffffu);
+        Iw[2 * k + 1] = (short)(w0[k] >> 16);
+        Ix[2 * k] = (short)(w1[k] & 0xffffu);
+        Ix[2 * k + 1] = (short)(w1[k] >> 16);
+        Iy[2 * k] = (short)(w2[k] & 0xffffu);
+        Iy[2 * k + 1] = (short)(w2[k] >> 16);
+      }
+    }
+    float2 result = next;   // nextPts[ptidx] as stored by OpenCV; only rewritten after an update step
+    next.x -= half;
+    next.y -= half;
+    float2 prevDelta = make_float2(0.f, 0.f);
+    const uint8_t *J = a.p1[level];
+    const int pitchJ = a.pitch1[level];
+    int jt[9], jb[9];   // the 2 x 9 block of the next image under this lane's pixels
+#pragma unroll
+    for (int k = 0; k < 9; k++) jt[k] = jb[k] = 0;
+    int cached_x = INT_MIN, cached_y = INT_MIN;
+    int reg_x0 = INT_MIN / 2, reg_y0 = INT_MIN / 2;   // origin of the staged region (none yet)
+    for (int j = 0; j < a.max_count; j++) {
+      const int inx = __float2int_rd(next.x), iny = __float2int_rd(next.y);
+      if (inx < -win || inx >= cols || iny < -win || iny >= rows) {
+        if (level == 0) ok = false;
+        break;
+      }
+      const float ja = next.x - inx, jbf = next.y - iny;
+      const int jw00 = __float2int_rn((1.f - ja) * (1.f - jbf) * 16384.f);
+      const int jw01 = __float2int_rn(ja * (1.f - jbf) * 16384.f);
+      const int jw10 = __float2int_rn((1.f - ja) * jbf * 16384.f);
+      const int jw11 = 16384 - jw00 - jw01 - jw10;
+      if (inx != cached_x || iny != cached_y) {   // warp-uniform
+        cached_x = inx;
+        cached_y = iny;
+        if (inx < reg_x0 || inx + kJSpan > reg_x0 + kJR || iny < reg_y0 || iny + kJSpan > reg_y0 + kJR) {
+          // (re)stage the region around the window; pixel (rx, ry) of it is J(reflect(reg_x0 + rx), reflect(reg_y0 + ry))
+          reg_x0 = inx - kJMargin;
+          reg_y0 = iny - kJMargin;
+          __syncwarp();   // every lane is done reading the old region
+          constexpr int kJLoads = (kJR * kJR + 31) / 32;   // 20, in two rounds of 10 loads in flight
+#pragma unroll 1
+          for (int q0 = 0; q0 < kJLoads; q0 += kJLoads / 2) {
+            uint8_t t[kJLoads / 2];
+#pragma unroll
+            for (int q = 0; q < kJLoads / 2; q++) {
+              const int i = lane + 32 * (q0 + q);
+              const int ry = i / kJR, rx = i - ry * kJR;
+              t[q] = 0;
+              if (i < kJR * kJR) t[q] = J[(size_t)reflect101(reg_y0 + ry, rows) * pitchJ + reflect101(reg_x0 + rx, cols)];
+            }
+#pragma unroll
+            for (int q = 0; q < kJLoads / 2; q++)
+              if (lane + 32 * (q0 + q) < kJR * kJR) sm.jreg[lane + 32 * (q0 + q)] = t[q];
+          }
+          __syncwarp();
+        }
+        if (own) {
+          const uint8_t *Jp = sm.jreg + (iny - reg_y0 + wy) * kJR + (inx - reg_x0 + wx);
+#pragma unroll
+          for (int k = 0; k < 9; k++) {
+            jt[k] = Jp[k];
+            jb[k] = Jp[kJR + k];
+          }
+        }
+      }
+      // mismatch vector: exact integer sums (the pixels a lane does not own have I = Ix = Iy = 0 and contribute 0)
+      long long s1 = 0, s2 = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int jv = (jt[k] * jw00 + jt[k + 1] * jw01 + jb[k] * jw10 + jb[k + 1] * jw11 + (1 << 8)) >> 9;
+        const int dv = own ? jv - Iw[k] : 0;
+        s1 += (long long)(dv * Ix[k]);
+        s2 += (long long)(dv * Iy[k]);
+      }
+      const long long t1 = ((long long)__reduce_add_sync(0xffffffffu, (int)(s1 >> 32)) << 32) +
+                           ((long long)__reduce_add_sync(0xffffffffu, (int)((s1 >> 16) & 0xffff)) << 16) +
+                           (long long)__reduce_add_sync(0xffffffffu, (int)(s1 & 0xffff));
+      const long long t2 = ((long long)__reduce_add_sync(0xffffffffu, (int)(s2 >> 32)) << 32) +
+                           ((long long)__reduce_add_sync(0xffffffffu, (int)((s2 >> 16) & 0xffff)) << 16) +
+                           (long long)__reduce_add_sync(0xffffffffu, (int)(s2 & 0xffff));
+      const float b1 = (float)t1 * FLT_SCALE;
+      const float b2 = (float)t2 * FLT_SCALE;
+      const float2 delta = make_float2((A12 * b2 - A22 * b1) * Dt, (A12 * b1 - A11 * b2) * Dt);
+      next.x += delta.x;
+      next.y += delta.y;
+      result = make_float2(next.x + half, next.y + half);
+      {
+        const float d2 = delta.x * delta.x + delta.y * delta.y;
+        bool stop;
+        if (d2 < a.eps_sq * 0.999999f) stop = true;
+        else if (d2 > a.eps_sq * 1.000001f) stop = false;
+        else stop = (double)delta.x * (double)delta.x + (double)delta.y * (double)delta.y <= (double)a.eps_sq;
+        if (stop) break;
+      }
+      if (j > 0 && fabsf(delta.x + prevDelta.x) <= 0.01f && fabsf(delta.y + prevDelta.y) <= 0.01f) {
+        result.x -= delta.x * 0.5f;
+        result.y -= delta.y * 0.5f;
+        break;
+      }
+      prevDelta = delta;
+    }
+    next = result;
+    if (level == 0 && ok) {
+      int fx = __float2int_rd(next.x - half), fy = __float2int_rd(next.y - half);
+      if (fx < -win || fx >= cols || fy < -win || fy >= rows) ok = false;
+    }
+  }
+  if (lane == 0) {
+    pts1[pi] = next;
+    status[pi] = ok ? 1 : 0;
+  }
+  if (a.undistort) {
+    if (lane == 0) p0n[pi] = undistort_radtan(prev_in, a.calib.K, a.calib.D);
+    if (lane == 1) p1n[pi] = undistort_radtan(next, a.calib.K, a.calib.D);
+  }
+}
+
 // ---- stream group: the points of every stream of a tracking launch in ONE launch (grid.y = job).  The arguments of a job
 // (pyramids of its previous and current slot, calibration in force) are assembled in shared memory; the per-feature work is
 // the body above, so a stream's tracks are bit-identical to those of a single handle.
@@ -799,12 +1078,35 @@ __global__ void __launch_bounds__(kLkWarps * 32)
   lk_body(sa, g.wpts + o, g.lk_pts1 + o, g.lk_status + o, g.lk_p0n + o, g.lk_p1n + o, n);
 }
 
+__global__ void __launch_bounds__(kLkwWarps * 32, 5)
+    k_lk15w_g(const __grid_constant__ GroupDev g, const TrackJob *__restrict__ jobs, const __grid_constant__ LkParams prm) {
+  __shared__ LkArgs sa;
+  __shared__ LkwSmem sm[kLkwWarps];
+  const TrackJob &job = jobs[blockIdx.y];
+  const int s = job.stream;
+  const int n = g.wn[s];
+  if (g.wmode[s] != 0 || n < 10 || (int)blockIdx.x * kLkwWarps >= n) return;   // TrackKLT.cpp:848-852
+  if (threadIdx.x == 0) group_lk_args(sa, g, job, prm);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  const int pi = blockIdx.x * kLkwWarps + warp;
+  if (pi >= n) return;
+  const size_t o = (size_t)s * g.pts_cap;
+  lk15w_body(sa, g.wpts + o, g.lk_pts1 + o, g.lk_status + o, g.lk_p0n + o, g.lk_p1n + o, pi, sm[warp]);
+}
+
 void launch_group_lk(const GroupDev &g, const TrackJob *jobs, int n_jobs, const LkParams &prm, cudaStream_t s) {
   if (n_jobs <= 0) return;
   if (prm.win == kW15 && prm.max_level + 1 <= kLk15MaxLevels) {
-    const int levels = prm.max_level + 1;
-    PLVIWO_CARVEOUT(k_lk15_g);
-    k_lk15_g<<<dim3(g.pts_cap, n_jobs), std::max(levels, kChainWarps) * 32, 0, s>>>(g, jobs, prm);
+    static const bool per_cta = std::getenv("PLVIWO_GROUP_LK_CTA") != nullptr;   // k_lk15 (CTA per feature) instead
+    if (per_cta) {
+      const int levels = prm.max_level + 1;
+      PLVIWO_CARVEOUT(k_lk15_g);
+      k_lk15_g<<<dim3(g.pts_cap, n_jobs), std::max(levels, kChainWarps) * 32, 0, s>>>(g, jobs, prm);
+      return;
+    }
+    PLVIWO_CARVEOUT(k_lk15w_g);
+    k_lk15w_g<<<dim3((g.pts_cap + kLkwWarps - 1) / kLkwWarps, n_jobs), kLkwWarps * 32, 0, s>>>(g, jobs, prm);
     return;
   }
   const int win = prm.win, np = win + 3, nd = win + 1, nw = win * win;

@@ -170,9 +170,13 @@ def test_introsort_restatement_equals_std_sort(fe):
         if trial % 5 == 2:
             resp = np.sort(resp)[::-1].copy()
         packed = (resp << 24) | np.arange(n, dtype=np.uint32)      # low bits = original index
-        got = fe.op_sort_corners(packed, 9, device=-1)
+        nfg = int(rng.integers(1, 40))
+        got, pre = fe.op_sort_corners(packed, nfg, device=-1, prefix=True)
         perm = cvops.sort_perm(resp.astype(np.float32))
         assert np.array_equal(got & 0xffffff, np.asarray(perm, np.uint32)), (trial, n, span)
+        # the pruned selection the kernel runs (isort::sort_prefix): the same first nfg elements, in the same order
+        idx = (pre[:, 0].astype(np.uint32) | (pre[:, 1].astype(np.uint32) << 12))
+        assert np.array_equal(idx, np.asarray(perm[:nfg], np.uint32)), (trial, n, span, nfg)
 
 
 def test_append_new_measurements(fe):
