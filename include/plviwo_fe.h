@@ -70,8 +70,9 @@ typedef struct FeConfig {
   float fld_distance_threshold; /* 1.414213562f                                                         */
   float canny_th1, canny_th2;   /* 50, 50 (aperture 3, L1 gradient)                                     */
   float line_min_length;        /* 40 (TrackLSD.cpp:231)                                                */
-  int32_t line_samples;         /* extension (not in the reference): LK over this many points sampled   */
-                                /* along each of last frame's segments; 0 = off                         */
+  int32_t line_samples;         /* extension (BASELINE.json configs[2], not in the reference): LK over this many   */
+                                /* points sampled evenly along every segment the line detector kept in the previous */
+                                /* frame (longer than line_min_length), previous -> current image; 0 = off          */
   int32_t lookahead;            /* frames that plviwo_fe_submit may run ahead of plviwo_fe_collect      */
   int32_t downsample;           /* UpdaterCamera::feed_measurement's pre-step (UpdaterCamera.cpp:86-95): cv::pyrDown of */
                                 /* image and mask to (width/2, height/2) before tracking; width/height above are the    */
@@ -153,6 +154,14 @@ const char *plviwo_fe_last_error(const FeHandle *h);          /* h may be NULL: 
 /* ---- per-frame ---------------------------------------------------------------------------------------- */
 /* Intrinsics are refined online by the estimator (StateHelper.cpp:166): call before feed whenever they change. */
 int plviwo_fe_set_calib(FeHandle *h, const double K[4], const double D[4]);
+/* The same with the camera model named (ov_core::CamBase subclasses, cam/CamRadtan.h / cam/CamEqui.h).  Only the radtan
+ * model is implemented: FE_CAM_EQUI is rejected with FE_BAD_ARG instead of being undistorted with the wrong formula. */
+enum FeCameraModel { FE_CAM_RADTAN = 0, FE_CAM_EQUI = 1 };
+int plviwo_fe_set_camera(FeHandle *h, int model, const double K[4], const double D[4]);
+/* TrackBase::currid (TrackBase.h:192) is one counter per tracker object, shared by all its cameras: a caller that owns
+ * several handles hands the counter from handle to handle around every feed (between frames only). */
+int plviwo_fe_get_currid(FeHandle *h, uint64_t *currid);
+int plviwo_fe_set_currid(FeHandle *h, uint64_t currid);
 int plviwo_fe_set_num_features(FeHandle *h, int num_features);
 int plviwo_fe_change_feat_id(FeHandle *h, uint64_t id_old, uint64_t id_new);
 
@@ -193,8 +202,8 @@ int plviwo_fe_get_line_points(FeHandle *h, FeLinePoint *out, int cap, int *n_out
  * points.  For callers that, like UpdaterCamera.cpp:105-110, only know the vanishing points after the point tracker was
  * fed: feed with any vp (e.g. zeros), then classify, then read the rows. */
 int plviwo_fe_classify_lines(FeHandle *h, const double vp[6]);
-/* extension: LK-tracked samples of last frame's segments: per sample (line row index in the PREVIOUS frame,
- * u0 v0 u1 v1, status) */
+/* extension: LK-tracked samples of the previous frame's detected segments, segment-major (line_samples consecutive
+ * entries per segment, in detection order): u0 v0 (previous image) u1 v1 (current image) and the KLT status */
 int plviwo_fe_get_line_samples(FeHandle *h, float *uv01 /* 4 per sample */, uint8_t *status, int cap, int *n_out);
 
 /* ---- tracker state: teacher-forced parity tests, checkpoint / resume ---------------------------------- */
@@ -257,6 +266,7 @@ int plviwo_fe_stereo_create(const FeConfig *cfg, const double K_right[4], const 
 int plviwo_fe_stereo_destroy(FeStereoHandle *h);
 const char *plviwo_fe_stereo_last_error(const FeStereoHandle *h);
 int plviwo_fe_stereo_set_calib(FeStereoHandle *h, int cam, const double K[4], const double D[4]);
+int plviwo_fe_stereo_set_camera(FeStereoHandle *h, int cam, int model, const double K[4], const double D[4]);
 int plviwo_fe_stereo_set_num_features(FeStereoHandle *h, int num_features);
 int plviwo_fe_stereo_change_feat_id(FeStereoHandle *h, uint64_t id_old, uint64_t id_new);
 /* Synchronous drop-in for feed_new_camera with two images (HOST buffers, 8UC1, same stride; masks may be NULL). */

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "cam/CamBase.h"
+#include "cam/CamRadtan.h"
 #include "feat/FeatureDatabase.h"
 #include "plviwo_fe.h"
 #include "track/TrackBase.h"
@@ -61,6 +62,14 @@ class TrackB200 : public ov_core::TrackBase {
     }
   }
 
+  // TrackBase::change_feat_id (TrackBase.cpp:267-285) is not virtual: callers that rename a feature use this wrapper, which
+  // also renames it inside the handles (the next frame would re-emit the old id otherwise)
+  void change_feat_id_b200(size_t id_old, size_t id_new) {
+    change_feat_id(id_old, id_new);
+    for (auto &kv : handles_) plviwo_fe_change_feat_id(kv.second, (uint64_t)id_old, (uint64_t)id_new);
+    if (stereo_) plviwo_fe_stereo_change_feat_id(stereo_, (uint64_t)id_old, (uint64_t)id_new);
+  }
+
   // line rows of the last frame of a camera (consumed by TrackLSDB200)
   FeHandle *handle(size_t cam_id) { return handles_.at(cam_id); }
   FeStereoHandle *stereo_handle() { return stereo_; }   // non-null once a two-image message was fed
@@ -94,26 +103,41 @@ class TrackB200 : public ov_core::TrackBase {
     return cfg;
   }
   int numaruco_of_currid() const { return (int)((currid.load() - 1) / 4); }   // TrackBase.cpp:34: currid = 4 * numaruco + 1
+  // only the radtan model is implemented: any other CamBase subclass (cam/CamEqui.h) is refused, not mis-undistorted
+  void require_radtan(size_t cam_id) const {
+    if (!std::dynamic_pointer_cast<ov_core::CamRadtan>(camera_calib.at(cam_id)))
+      throw std::invalid_argument("plviwo::TrackB200: camera " + std::to_string(cam_id) + " is not an ov_core::CamRadtan (only radtan is implemented)");
+  }
 
   void feed_monocular(const ov_core::CameraData &message, size_t msg_id) {
     const size_t cam_id = (size_t)message.sensor_ids.at(msg_id);
     const cv::Mat &img = message.images.at(msg_id);
     const cv::Mat &mask = message.masks.at(msg_id);
+    require_radtan(cam_id);
     FeHandle *h = handle_for(cam_id, img);
     // intrinsics are refined online (StateHelper.cpp:166): hand over the current values every frame
     const Eigen::MatrixXd calib = camera_calib.at(cam_id)->get_value();
     const double K[4] = {calib(0), calib(1), calib(2), calib(3)}, D[4] = {calib(4), calib(5), calib(6), calib(7)};
-    plviwo_fe_set_calib(h, K, D);
-    if (num_features != last_num_features_) {
-      plviwo_fe_set_num_features(h, num_features);
-      last_num_features_ = num_features;
+    if (plviwo_fe_set_camera(h, FE_CAM_RADTAN, K, D) != FE_OK) throw std::runtime_error(std::string("plviwo_fe_set_camera: ") + plviwo_fe_last_error(h));
+    int &last_nf = last_num_features_[cam_id];   // per handle: every camera's handle follows set_num_features
+    if (num_features != last_nf) {
+      if (plviwo_fe_set_num_features(h, num_features) != FE_OK)
+        throw std::runtime_error(std::string("plviwo_fe_set_num_features: ") + plviwo_fe_last_error(h));
+      last_nf = num_features;
     }
+    // one id counter for all cameras of the tracker (TrackBase.h:192): the handle continues from the shared counter ...
+    plviwo_fe_set_currid(h, (uint64_t)currid.load());
     // the vanishing points are only known to the caller of TrackLSD: feed with zeros, TrackLSDB200 re-classifies
     const double vp0[6] = {0, 0, 0, 0, 0, 0};
     FeFrameInfo info;
     const int rc = plviwo_fe_feed(h, message.timestamp, img.data, img.cols, img.rows, (int)img.step, mask.empty() ? nullptr : mask.data,
                                   mask.empty() ? 0 : (int)mask.step, use_lines_ ? vp0 : nullptr, &info);
     if (rc != FE_OK) throw std::runtime_error(std::string("plviwo_fe_feed: ") + plviwo_fe_last_error(h));
+    {   // ... and hands it back, so that code reading TrackBase::currid sees the ids that were given out
+      uint64_t c = 0;
+      plviwo_fe_get_currid(h, &c);
+      currid = (size_t)c;
+    }
     // rows -> FeatureDatabase::update_feature (TrackKLT.cpp:176-179)
     rows_.resize((size_t)info.n_point_rows);
     int n = 0;
@@ -162,10 +186,14 @@ class TrackB200 : public ov_core::TrackBase {
       if (plviwo_fe_stereo_create(&cfg, K[1], D[1], device_, &stereo_) != FE_OK)
         throw std::runtime_error(std::string("plviwo_fe_stereo_create: ") + plviwo_fe_stereo_last_error(nullptr));
     }
-    for (int c = 0; c < 2; c++) plviwo_fe_stereo_set_calib(stereo_, c, K[c], D[c]);
-    if (num_features != last_num_features_) {
-      plviwo_fe_stereo_set_num_features(stereo_, num_features);
-      last_num_features_ = num_features;
+    for (int c = 0; c < 2; c++) {
+      require_radtan(cam[c]);
+      plviwo_fe_stereo_set_camera(stereo_, c, FE_CAM_RADTAN, K[c], D[c]);
+    }
+    if (num_features != last_num_features_stereo_) {
+      if (plviwo_fe_stereo_set_num_features(stereo_, num_features) != FE_OK)
+        throw std::runtime_error(std::string("plviwo_fe_stereo_set_num_features: ") + plviwo_fe_stereo_last_error(stereo_));
+      last_num_features_stereo_ = num_features;
     }
     const bool has_mask = !mask[0]->empty() && !mask[1]->empty();
     const double vp0[6] = {0, 0, 0, 0, 0, 0};   // TrackLSDB200 re-classifies with the real vanishing points
@@ -201,7 +229,8 @@ class TrackB200 : public ov_core::TrackBase {
   bool use_lines_;
   FeStereoHandle *stereo_ = nullptr;
   int device_;
-  int last_num_features_ = -1;
+  std::map<size_t, int> last_num_features_;   // per camera handle (a fresh entry is 0: the first feed sets it)
+  int last_num_features_stereo_ = -1;
   std::map<size_t, FeHandle *> handles_;
   std::vector<FePointRow> rows_;
   std::vector<uint64_t> ids_;

@@ -390,6 +390,7 @@ class TrackLSD:
         self.track_feats = track_feats
         self.currid = 1                                           # TrackLSD.cpp:32
         self.lines_last = np.zeros((0, 4), f32)
+        self.lines_det_last = np.zeros((0, 4), f32)   # extension (cfg.line_samples): segments detected in the last frame
         self.ids_last: List[int] = []
         self.pol_last: List[Dict[int, float]] = []
         self.trace: Dict[str, object] = {}
@@ -423,6 +424,7 @@ class TrackLSD:
         for _ in range(len(lines)):                               # :233-236
             self.currid += 1
             ids.append(self.currid)
+        self.lines_det_new = lines.copy()
         return lines, ids
 
     # -- TrackLSD.cpp:744-792 (bbox index mix-up reproduced)
@@ -556,10 +558,26 @@ class FrontEnd:
             mask = np.zeros_like(img)
         if self.cfg.downsample:          # UpdaterCamera.cpp:86-95
             img, mask = self.klt.ops.downsample(img), self.klt.ops.downsample(mask)
+        prev_eq = self.klt.img_last
         prows = self.klt.feed_new_camera(timestamp, img, mask)
+        # extension (BASELINE.json configs[2]; NOT in the reference): LK over cfg.line_samples points sampled evenly along
+        # every segment the detector kept in the previous frame, previous -> current equalised image, with the point
+        # tracker's LK parameters (cv::calcOpticalFlowPyrLK, initial flow = the sample itself).  Rides in the point
+        # tracker's LK call, so it only exists when that call is made (>= 10 points to track).
+        self.sample_uv, self.sample_status = np.zeros((0, 4), f32), np.zeros((0,), np.uint8)
+        S = int(self.cfg.line_samples)
+        if S > 0 and self.lsd is not None and prev_eq is not None and len(self.lsd.lines_det_last) and "mask_klt" in self.klt.trace:
+            L = self.lsd.lines_det_last.astype(f32)
+            a = (np.arange(S, dtype=f32) / f32(S - 1)) if S > 1 else np.full((1,), 0.5, f32)
+            p0 = np.stack([(L[:, None, 0] + (L[:, None, 2] - L[:, None, 0]) * a[None, :]).astype(f32),
+                           (L[:, None, 1] + (L[:, None, 3] - L[:, None, 1]) * a[None, :]).astype(f32)], -1).reshape(-1, 2)
+            p1, st = self.klt.ops.lk(prev_eq, self.klt.trace["img_eq"], p0, p0.copy(), self.cfg.win_size, self.cfg.pyr_levels)
+            self.sample_uv = np.concatenate([p0, p1], 1).astype(f32)
+            self.sample_status = st
         lrows = []
         if self.lsd is not None:
             if vps is None:
                 vps = [(1e5, 263.0), (608.0, -1e5), (608.0, 263.0)]
             lrows = self.lsd.feed_new_camera(timestamp, img, mask, vps, img_eq=self.klt.trace["img_eq"])
+            self.lsd.lines_det_last = self.lsd.lines_det_new
         return prows, lrows

@@ -122,7 +122,8 @@ EXPORTS = [
     "plviwo_fe_group_submit", "plviwo_fe_group_collect", "plviwo_fe_group_play", "plviwo_fe_group_get_point_rows",
     "plviwo_fe_group_get_last_obs", "plviwo_fe_group_get_line_rows", "plviwo_fe_group_get_line_points",
     "plviwo_fe_group_get_state", "plviwo_fe_group_set_state", "plviwo_fe_group_tap", "plviwo_fe_group_enable_timing",
-    "plviwo_fe_group_get_times",
+    "plviwo_fe_group_get_times", "plviwo_fe_set_camera", "plviwo_fe_get_currid", "plviwo_fe_set_currid",
+    "plviwo_fe_stereo_set_camera",
 ]
 
 
@@ -139,6 +140,10 @@ def lib() -> C.CDLL:
         L.plviwo_fe_create.argtypes = [C.POINTER(FeConfig), C.c_int, C.POINTER(C.c_void_p)]
         L.plviwo_fe_destroy.argtypes = [C.c_void_p]
         L.plviwo_fe_set_calib.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.plviwo_fe_set_camera.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.plviwo_fe_get_currid.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.plviwo_fe_set_currid.argtypes = [C.c_void_p, C.c_uint64]
+        L.plviwo_fe_stereo_set_camera.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.plviwo_fe_set_num_features.argtypes = [C.c_void_p, C.c_int]
         L.plviwo_fe_classify_lines.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.plviwo_fe_change_feat_id.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
@@ -359,6 +364,18 @@ class FrontEnd:
 
     def set_num_features(self, n: int):
         _check(self._lib.plviwo_fe_set_num_features(self._h, n), self._h)
+
+    def set_camera(self, model: int, K: Sequence[float], D: Sequence[float]):
+        """CamBase model + calibration (0 radtan, 1 equidistant: rejected, not implemented)."""
+        _check(self._lib.plviwo_fe_set_camera(self._h, model, (C.c_double * 4)(*K), (C.c_double * 4)(*D)), self._h)
+
+    def get_currid(self) -> int:
+        v = C.c_uint64(0)
+        _check(self._lib.plviwo_fe_get_currid(self._h, C.byref(v)), self._h)
+        return int(v.value)
+
+    def set_currid(self, currid: int):
+        _check(self._lib.plviwo_fe_set_currid(self._h, currid), self._h)
 
     def classify_lines(self, vanishing_points):
         """TrackLSD::LineClassification of the last frame's line rows with these vanishing points (3 x (x, y))."""
@@ -677,7 +694,9 @@ class GroupEngine:
     name = "group"
 
     def __init__(self, fe_mod, dev, metas, workload, lookahead=None):
-        la = int(os.environ.get("PLVIWO_BENCH_GROUP_LA", "0")) or lookahead or (3 if len(metas) >= 16 else 12)
+        # ticks in flight: the chain walk of a tick's frames lasts ~3 ms (its longest component), the other kernels of a tick
+        # ~2 ms: six ticks in flight keep the device busy while walks finish (measured: 3 -> 6 ticks +5 %, 10 no more)
+        la = int(os.environ.get("PLVIWO_BENCH_GROUP_LA", "0")) or lookahead or (6 if len(metas) >= 16 else 12)
         self.lookahead = la
         self.metas = metas
         self.g = GroupFrontEnd(default_config(lookahead=la, **workload), len(metas), device=dev, calibs=[(K, D) for K, D, _ in metas])

@@ -152,6 +152,27 @@ int plviwo_fe_set_calib(FeHandle *h, const double K[4], const double D[4]) {
   if (!h || !K || !D) return FE_BAD_ARG;
   return h->ctx->set_calib(K, D);
 }
+
+int plviwo_fe_set_camera(FeHandle *h, int model, const double K[4], const double D[4]) {
+  if (!h || !K || !D) return FE_BAD_ARG;
+  if (model != FE_CAM_RADTAN) {
+    h->ctx->last_error = "set_camera: only the radtan model is implemented (an equidistant camera, cam/CamEqui.h:108-129, would be "
+                         "undistorted with the wrong formula)";
+    return FE_BAD_ARG;
+  }
+  return h->ctx->set_calib(K, D);
+}
+
+int plviwo_fe_get_currid(FeHandle *h, uint64_t *currid) {
+  if (!h || !currid) return FE_BAD_ARG;
+  *currid = h->ctx->currid();
+  return FE_OK;
+}
+
+int plviwo_fe_set_currid(FeHandle *h, uint64_t currid) {
+  if (!h) return FE_BAD_ARG;
+  return h->ctx->set_currid(currid);
+}
 int plviwo_fe_set_num_features(FeHandle *h, int n) {
   if (!h || n < 1) return FE_BAD_ARG;
   return h->ctx->set_num_features(n);
@@ -923,6 +944,15 @@ int plviwo_fe_stereo_set_calib(FeStereoHandle *h, int cam, const double K[4], co
   if (!h || !K || !D) return FE_BAD_ARG;
   return h->st->set_calib(cam, K, D);
 }
+int plviwo_fe_stereo_set_camera(FeStereoHandle *h, int cam, int model, const double K[4], const double D[4]) {
+  if (!h || !K || !D) return FE_BAD_ARG;
+  if (model != FE_CAM_RADTAN) {
+    h->st->last_error = "set_camera: only the radtan model is implemented";
+    return FE_BAD_ARG;
+  }
+  return plviwo_fe_stereo_set_calib(h, cam, K, D);
+}
+
 int plviwo_fe_stereo_set_num_features(FeStereoHandle *h, int n) {
   if (!h || n < 1) return FE_BAD_ARG;
   return h->st->set_num_features(n);

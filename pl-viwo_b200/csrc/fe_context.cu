@@ -240,7 +240,7 @@ int FeContext::init() {
   max_cells_ = std::max(cfg_.grid_x * cfg_.grid_y, 1);
   max_bands_ = (H_ + kFastBandRows - 1) / kFastBandRows;
   kps_cap_ = W_ * H_ / 4 + 1024;
-  cand_cap_ = std::max(max_cells_ * (cfg_.num_features + 1), 1024);
+  cand_cap_ = std::max(max_cells_ * (cfg_.num_features + 1), 1024);   // set_num_features() is checked against this
   if (cand_cap_ > 65536) cand_cap_ = 65536;
   FE_CUDA(cudaMalloc(&d_cells_, (size_t)max_cells_ * sizeof(FastCell)));
   for (FrameSlot &s : slots_) {
@@ -424,7 +424,44 @@ int FeContext::set_num_features(int n) {
     last_error = "set_num_features: collect the pending frames first";
     return FE_BAD_ARG;
   }
+  if (n < 1) {
+    last_error = "set_num_features: bad feature count";
+    return FE_BAD_ARG;
+  }
+  // the candidate table (cells x num_features_grid) of the new layout must fit the buffers sized at creation
+  if (cand_table_size(n) > cand_cap_) {
+    last_error = "set_num_features: the candidate table of that feature count exceeds the capacity this handle was created with";
+    return FE_BAD_ARG;
+  }
   cfg_.num_features = n;
+  return FE_OK;
+}
+
+// cells x num_features_grid of the Grider_GRID layout for a feature count (layout_cells)
+int FeContext::cand_table_size(int num_features) const {
+  const int gx = cfg_.grid_x, gy = cfg_.grid_y;
+  int ggx = gx, ggy = gy;
+  if (num_features < ggx * ggy) {
+    double ratio = (double)ggx / (double)ggy;
+    ggy = (int)std::ceil(std::sqrt(num_features / ratio));
+    ggx = (int)std::ceil(ggy * ratio);
+  }
+  const int nfg = (int)((double)num_features / (double)(ggx * ggy)) + 1;
+  const int csx = W_ / ggx, csy = H_ / ggy;
+  int ncell = 0;
+  if (csx > 0 && csy > 0)
+    for (int x = 0; x < gx; x++)
+      for (int y = 0; y < gy; y++)
+        if (x * csx + csx <= W_ && y * csy + csy <= H_) ncell++;
+  return ncell * nfg;
+}
+
+int FeContext::set_currid(uint64_t id) {
+  if (!queue_.empty()) {
+    last_error = "set_currid: collect the pending frames first";
+    return FE_BAD_ARG;
+  }
+  currid_ = id;
   return FE_OK;
 }
 
@@ -594,13 +631,15 @@ int FeContext::enqueue_frame_independent(FrameSlot &s) {
         if (rc) return rc;
         if (timing) s.line_timed = 1;
       }
+      FE_CUDA(cudaEventRecord(s.ev_lines, s.s_line));
+      s.lines_recorded = true;
     }
   }
   s.warmed = true;
   // bookkeeping (identical for both ways of issuing the work)
   const int ncell = (int)cells_.size(), ntab = ncell * cells_nb_;
   mst_.kernel_launches_total += (cfg_.histogram_method != FE_HIST_NONE ? 1 : 0) + 1 + std::max(s.pyr.n - 2, 0) +
-                                 (ncell > 0 ? 3 : 0) + 1 + (lines && !batched ? 11 : 0);
+                                 (ncell > 0 ? 3 : 0) + 1 + (lines && !batched ? 13 : 0);
   (void)ntab;
   if (ncell > 0) mst_.d2h_bytes += (size_t)ncell * sizeof(int) + (size_t)2 * ncell * cells_nfg_ * sizeof(float2);
   if (lines) mst_.d2h_bytes += 2 * sizeof(int) + 1024 * sizeof(float4);
@@ -634,10 +673,12 @@ int FeContext::flush_line_batch() {
     FE_CUDA(cudaMemcpyAsync(s.h_fld_counts, s.fld.counters + 3, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     FE_CUDA(cudaMemcpyAsync(s.h_segs, s.fld.out, 1024 * sizeof(float4), cudaMemcpyDeviceToHost, st));
     launch_signal_inc(&s.h_flags[2], s.d_seq + 2, st);
+    FE_CUDA(cudaEventRecord(s.ev_lines, st));
+    s.lines_recorded = true;
     s.line_pending = false;
   }
   FE_CUDA(cudaGetLastError());
-  mst_.kernel_launches_total += 10 + n;   // canny, 4 x components, walk, order, segments, compact + one signal per frame
+  mst_.kernel_launches_total += 12 + n;   // canny, 6 x components, walk, order, segments, compact + one signal per frame
   pending_lines_.clear();
   return FE_OK;
 }
@@ -674,8 +715,21 @@ int FeContext::track_candidates(FrameSlot &prev, FrameSlot &s) {
 
 int FeContext::submit(double t, const uint8_t *image, int stride, bool on_device, const uint8_t *mask, int mask_stride,
                       const double vp[6]) {
-  int rc = submit_impl(t, image, stride, on_device, mask, mask_stride, vp);
-  if (rc) last_error = t_err;
+  int si = -1;
+  int rc = submit_impl(t, image, stride, on_device, mask, mask_stride, vp, &si);
+  if (rc) {
+    last_error = t_err;
+    if (si >= 0 && !external_) {   // a failed submit leaves no trace: the slot is free again, nothing of it is pending
+      FrameSlot &s = slots_[si];
+      cudaStreamSynchronize(s.s_a);
+      cudaStreamSynchronize(s.s_b);
+      if (s.s_line) cudaStreamSynchronize(s.s_line);
+      cudaGetLastError();
+      pending_lines_.erase(std::remove(pending_lines_.begin(), pending_lines_.end(), si), pending_lines_.end());
+      s.line_pending = false;
+      s.busy = false;
+    }
+  }
   flush_stats(mst_);
   return rc;
 }
@@ -689,9 +743,16 @@ int FeContext::submit_impl(double t, const uint8_t *image, int stride, bool on_d
     if (!slots_[i].busy && i != last_slot_) { si = i; break; }
   if (si < 0) return err(FE_BAD_ARG, "submit: lookahead window full (collect a frame first)");
   FrameSlot &s = slots_[si];
+  if (slot_out) *slot_out = si;
   s.busy = true;
   s.timestamp = t;
   s.res.clear();
+  // the slot's previous frame: its FAST / selection / sub-pixel path (s_b) and line path read level 0 / the half image that
+  // the image path (s_a) is about to overwrite
+  if (s.warmed) {
+    FE_CUDA(cudaStreamWaitEvent(s.s_a, s.ev_fast, 0));
+    if (cfg_.use_lines && s.lines_recorded) FE_CUDA(cudaStreamWaitEvent(s.s_a, s.ev_lines, 0));
+  }
   for (int i = 0; i < 4; i++) {
     s.K[i] = cfg_.K[i];
     s.D[i] = cfg_.D[i];
@@ -1376,7 +1437,7 @@ int FeContext::perform_matching(const FrameSlot &f0, FrameSlot &f1, std::vector<
       else std::this_thread::yield();
     }
     const int S = cfg_.line_samples;
-    for (const float4 &l : lines_last_) {
+    for (const float4 &l : lines_det_last_) {   // every segment the detector kept in the previous frame (> line_min_length)
       for (int k = 0; k < S && n2 + ns < max_pts_; k++) {
         float a = S > 1 ? (float)k / (float)(S - 1) : 0.5f;
         h_pts0_[n2 + ns] = make_float2(l.x + (l.z - l.x) * a, l.y + (l.w - l.y) * a);
@@ -1645,6 +1706,7 @@ int FeContext::lsd_feed(FrameSlot &cur) {
   }
   for (size_t i = 0; i < lines_new.size(); i++) ids_new.push_back(++line_currid_);
   info->n_lines_detected = (int)lines_new.size();
+  if (cfg_.line_samples > 0) lines_det_last_ = lines_new;   // the next frame's LK samples points along these
 
   // AssignPointToLines (:744-792) against the CURRENT points of the point tracker (:127-129)
   const std::vector<Pt> &points = res.obs;        // the point tracker's pts_last / ids_last after THIS frame
@@ -1784,7 +1846,7 @@ int FeContext::set_state(const void *buf, size_t n_bytes) {
   StateHeader hd;
   std::memcpy(&hd, p, sizeof(hd));
   p += sizeof(hd);
-  if (hd.magic != 0x504c5657u || hd.w != W_ || hd.h != H_) return FE_BAD_ARG;
+  if (hd.magic != 0x504c5657u || hd.version != 1 || hd.w != W_ || hd.h != H_) return FE_BAD_ARG;
   if (hd.n_pts < 0 || hd.n_lines < 0 || hd.n_pol_entries < 0) return FE_BAD_ARG;
   {   // the blob must hold everything its header announces (a truncated or foreign buffer is rejected, not read past)
     const size_t need = sizeof(hd) + (size_t)hd.n_pts * (sizeof(Pt) + sizeof(uint64_t)) +
@@ -1794,27 +1856,39 @@ int FeContext::set_state(const void *buf, size_t n_bytes) {
     if (n_bytes < need) return FE_BAD_ARG;
   }
   auto get = [&](void *dst, size_t n) { std::memcpy(dst, p, n); p += n; };
-  currid_ = hd.currid;
-  line_currid_ = hd.line_currid;
-  pts_last_.resize(hd.n_pts);
-  ids_last_.resize(hd.n_pts);
-  get(pts_last_.data(), (size_t)hd.n_pts * sizeof(Pt));
-  get(ids_last_.data(), (size_t)hd.n_pts * sizeof(uint64_t));
-  lines_last_.resize(hd.n_lines);
-  line_ids_last_.resize(hd.n_lines);
-  get(lines_last_.data(), (size_t)hd.n_lines * sizeof(float4));
-  get(line_ids_last_.data(), (size_t)hd.n_lines * sizeof(uint64_t));
+  // parse into temporaries: the tracker state is only replaced once the whole blob has been checked
+  std::vector<Pt> t_pts(hd.n_pts);
+  std::vector<uint64_t> t_ids(hd.n_pts);
+  get(t_pts.data(), (size_t)hd.n_pts * sizeof(Pt));
+  get(t_ids.data(), (size_t)hd.n_pts * sizeof(uint64_t));
+  std::vector<float4> t_lines(hd.n_lines);
+  std::vector<uint64_t> t_lids(hd.n_lines);
+  get(t_lines.data(), (size_t)hd.n_lines * sizeof(float4));
+  get(t_lids.data(), (size_t)hd.n_lines * sizeof(uint64_t));
   std::vector<int32_t> sizes(hd.n_lines);
   get(sizes.data(), (size_t)hd.n_lines * sizeof(int32_t));
-  pol_last_.assign(hd.n_lines, {});
+  long long tot = 0;
+  for (int32_t v : sizes) {
+    if (v < 0) return FE_BAD_ARG;
+    tot += v;
+  }
+  if (tot != hd.n_pol_entries) return FE_BAD_ARG;   // the entries the lines announce are the entries the blob holds
+  std::vector<std::map<int, double>> t_pol(hd.n_lines);
   for (int i = 0; i < hd.n_lines; i++)
     for (int k = 0; k < sizes[i]; k++) {
       int32_t key;
       double val;
       get(&key, sizeof(key));
       get(&val, sizeof(val));
-      pol_last_[i][key] = val;
+      t_pol[i][key] = val;
     }
+  currid_ = hd.currid;
+  line_currid_ = hd.line_currid;
+  pts_last_.swap(t_pts);
+  ids_last_.swap(t_ids);
+  lines_last_.swap(t_lines);
+  line_ids_last_.swap(t_lids);
+  pol_last_.swap(t_pol);
   for (FrameSlot &s : slots_) {
     s.busy = false;
   }

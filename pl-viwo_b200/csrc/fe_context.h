@@ -109,6 +109,7 @@ struct FrameSlot {
   cudaGraphExec_t g_image = nullptr, g_fast = nullptr, g_lines = nullptr;
   int graph_version = -1;
   bool warmed = false;
+  bool lines_recorded = false;   // ev_lines has been recorded at least once
   cudaEvent_t ev_t[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool timed = false;
 
@@ -171,6 +172,9 @@ class FeContext {
   // results of the last collected frame (TrackBase::get_last_obs / get_last_ids are result().obs / obs_ids)
   const FrameResult &result() const { return *cur_res_; }
   int set_num_features(int n);
+  int set_currid(uint64_t id);
+  uint64_t currid() const { return currid_; }
+  int cand_table_size(int num_features) const;
   int classify_lines(const double vp[6]);
   int change_feat_id(uint64_t id_old, uint64_t id_new);
 
@@ -249,6 +253,7 @@ class FeContext {
   std::vector<uint64_t> ids_last_;
   uint64_t currid_ = 1;
   // ---- line tracker state (TrackLSD.h:248-279)
+  std::vector<float4> lines_det_last_;   // cfg.line_samples: the segments detected in the last fed frame (not part of the state blob)
   std::vector<float4> lines_last_;
   std::vector<uint64_t> line_ids_last_;
   std::vector<std::map<int, double>> pol_last_;

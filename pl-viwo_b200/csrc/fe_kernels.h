@@ -138,6 +138,9 @@ struct FldBuffers {
   int *label = nullptr;           // connected-component label per pixel (root = smallest raster index), -1 = no edge
   int *cnt = nullptr;             // pixels per component (at the root)
   int *bbox = nullptr;            // 3 planes at the root: max y, min x, max x (min y is the root's row)
+  int *lroots = nullptr;          // tile-local roots of the connected-component pass (k_ccl_tile -> k_ccl_link)
+  int *lroot_n = nullptr;
+  int lroot_cap = 0;
   int *comp_root = nullptr;       // roots of the components big enough to hold a chain
   int *counters = nullptr;        // [0] components [1] - [2] chain-point cursor [3] chains [4] segments
   int2 *chain_pts = nullptr;      // chain points, one slice per component (capacity = w * h)

@@ -75,6 +75,8 @@ int FeStereo::set_calib(int cam, const double K[4], const double D[4]) {
 
 int FeStereo::set_num_features(int n) {
   if (!queue_.empty()) return err(FE_BAD_ARG, "set_num_features: collect the pending pairs first");
+  if (n < 1 || cam_[0]->cand_table_size(n) > cam_[0]->cand_cap_)
+    return err(FE_BAD_ARG, "set_num_features: the candidate table of that feature count exceeds the capacity this rig was created with");
   cfg_.num_features = n;
   cam_[0]->cfg_.num_features = cam_[1]->cfg_.num_features = n;
   return FE_OK;

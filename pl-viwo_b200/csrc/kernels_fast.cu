@@ -43,6 +43,23 @@ __device__ __forceinline__ bool fast_quick_t(Get get, int threshold) {
   return br || dk;
 }
 
+// the corner test proper: 9 contiguous ring pixels all brighter or all darker than the centre by more than the threshold
+template <class Get>
+__device__ __forceinline__ bool fast_arc_t(Get get, int threshold) {
+  constexpr int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+  constexpr int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+  const int v = get(0, 0);
+  unsigned bright = 0, dark = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const int dk = v - get(dx[k], dy[k]);
+    bright |= (dk > threshold ? 1u : 0u) << k;
+    dark |= (dk < -threshold ? 1u : 0u) << k;
+  }
+  return has_arc9(bright) || has_arc9(dark);
+}
+
+// score of a pixel that passed fast_arc_t
 template <class Get>
 __device__ __forceinline__ int fast_full_t(Get get, int threshold) {
   // ring offsets in OpenCV's order (Appendix A4)
@@ -50,14 +67,9 @@ __device__ __forceinline__ int fast_full_t(Get get, int threshold) {
   constexpr int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
   const int v = get(0, 0);
   int d[16];
-  unsigned bright = 0, dark = 0;
 #pragma unroll
-  for (int k = 0; k < 16; k++) {
-    d[k] = v - get(dx[k], dy[k]);
-    bright |= (d[k] > threshold ? 1u : 0u) << k;
-    dark |= (d[k] < -threshold ? 1u : 0u) << k;
-  }
-  if (!has_arc9(bright) && !has_arc9(dark)) return 0;
+  for (int k = 0; k < 16; k++) d[k] = v - get(dx[k], dy[k]);
+  (void)threshold;
   // a0 = max over arcs of min(d), b0 = min over arcs of max(d): sliding window of 9 over the circular ring
   int mn2[16], mx2[16];
 #pragma unroll
@@ -84,7 +96,7 @@ __device__ __forceinline__ int fast_full_t(Get get, int threshold) {
 
 __device__ __forceinline__ int fast_score(const uint8_t *__restrict__ px, int stride, int threshold) {
   auto get = [&](int dx, int dy) { return (int)px[dy * stride + dx]; };
-  if (!fast_quick_t(get, threshold)) return 0;
+  if (!fast_quick_t(get, threshold) || !fast_arc_t(get, threshold)) return 0;
   return fast_full_t(get, threshold);
 }
 
@@ -97,7 +109,7 @@ __device__ __forceinline__ void fast_body(const uint8_t *__restrict__ img, int p
   uint8_t *pix = smem + kFastPad;                              // (kBH + 8) rows x smem_w
   uint8_t *sc = smem + 2 * kFastPad + (kBH + 8) * smem_w;      // (kBH + 2) rows x smem_w
   __shared__ int warp_tot[kFastThreads / 32];
-  __shared__ int s_base, s_nlist;
+  __shared__ int s_base, s_nlist, s_nlist2;
 
   const FastCell cell = cells[blockIdx.y];
   const int band = blockIdx.x;
@@ -143,52 +155,96 @@ __device__ __forceinline__ void fast_body(const uint8_t *__restrict__ img, int p
     const int cww = cw >> 2;
     const int items = (kBH + 2) * cww;
     for (int i = tid; i < (kBH + 2) * (smem_w >> 2); i += kFastThreads) reinterpret_cast<unsigned *>(sc)[i] = 0;
-    if (tid == 0) s_nlist = 0;
+    if (tid == 0) s_nlist = s_nlist2 = 0;
     __syncthreads();
     const int lane = tid & 31;
+    const unsigned t4 = (unsigned)min(max(threshold, 0), 255) * 0x01010101u;
     for (int i0 = 0; i0 < items; i0 += kFastThreads) {
       const int i = i0 + tid;
       const int r = i / cww, x0 = (i - r * cww) << 2;
       const int y = y0 - 1 + r;
-      const bool row_ok = i < items && y >= 3 && y < ch - 3;
-      unsigned w0[3] = {0, 0, 0}, w3[3] = {0, 0, 0}, w6[3] = {0, 0, 0};
-      if (row_ok) {
+      unsigned pass4 = 0;
+      if (i < items && y >= 3 && y < ch - 3) {
+        // the four pixels at once, one byte lane each: centre +- threshold with saturation (a pixel cannot exceed 255 or go
+        // below 0, so the saturated bound decides the same), the four ring pixels at distance 3 as whole words (N, S) or
+        // funnel shifts of the centre row (E, W), per-byte unsigned compares
         const unsigned *p0r = reinterpret_cast<const unsigned *>(&pix[(r + 0) * smem_w + x0]);
         const unsigned *p3r = reinterpret_cast<const unsigned *>(&pix[(r + 3) * smem_w + x0]);
         const unsigned *p6r = reinterpret_cast<const unsigned *>(&pix[(r + 6) * smem_w + x0]);
-        w0[1] = p0r[0];
-        w6[1] = p6r[0];
-        w3[0] = p3r[-1]; w3[1] = p3r[0]; w3[2] = p3r[1];
-      }
+        const unsigned v4 = p3r[0], pS = p0r[0], pN = p6r[0];
+        const unsigned pE = __funnelshift_r(v4, p3r[1], 24), pW = __funnelshift_r(p3r[-1], v4, 8);
+        const unsigned hi4 = __vaddus4(v4, t4), lo4 = __vsubus4(v4, t4);
+        const unsigned br = (__vcmpgtu4(pN, hi4) | __vcmpgtu4(pS, hi4)) & (__vcmpgtu4(pE, hi4) | __vcmpgtu4(pW, hi4));
+        const unsigned dk = (__vcmpltu4(pN, lo4) | __vcmpltu4(pS, lo4)) & (__vcmpltu4(pE, lo4) | __vcmpltu4(pW, lo4));
+        pass4 = br | dk;
+        // columns 0..2 and cw-3..cw-1 of the cell are never tested
+        if (x0 == 0) pass4 &= 0xff000000u;
+        if (x0 + 4 >= cw - 3) {
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int x = x0 + j;
-        bool pass = false;
-        if (row_ok && x >= 3 && x < cw - 3) {
-          pass = fast_quick_t(
-              [&](int dx, int dy) {
-                const int idx = j + dx + 4;   // byte index into a row's three words
-                const unsigned *row = dy == 0 ? w3 : (dy < 0 ? w0 : w6);
-                return (int)((row[idx >> 2] >> (8 * (idx & 3))) & 0xffu);
-              },
-              threshold);
+          for (int j = 0; j < 4; j++)
+            if (x0 + j >= cw - 3) pass4 &= ~(0xffu << (8 * j));
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-        if (bal) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&s_nlist, __popc(bal));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (pass) list[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)((r << 11) | x);
-        }
+      }
+      const int mine = __popc(pass4 & 0x01010101u);
+      int incl = mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const int tot = __shfl_sync(0xffffffffu, incl, 31);
+      if (tot) {
+        int base = 0;
+        if (lane == 31) base = atomicAdd(&s_nlist, tot);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (pass4 & (0xffu << (8 * j))) list[base++] = (unsigned short)((r << 11) | (x0 + j));
       }
     }
     __syncthreads();
+    //  2. the ring test on the survivors, one per lane; those with an arc go to a second list ...
+    unsigned short *list2 = list + (kBH + 2) * smem_w;
     const int nlist = s_nlist;
-    for (int k = tid; k < nlist; k += kFastThreads) {
-      const int e = list[k], r = e >> 11, x = e & 2047;
+    for (int k0 = 0; k0 < nlist; k0 += kFastThreads) {
+      const int k = k0 + tid;
+      bool pass = false;
+      int e = 0;
+      if (k < nlist) {
+        e = list[k];
+        const uint8_t *px = &pix[((e >> 11) + 3) * smem_w + (e & 2047)];
+        pass = fast_arc_t([&](int dx, int dy) { return (int)px[dy * smem_w + dx]; }, threshold);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, pass);
+      if (bal) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_nlist2, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pass) list2[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)e;
+      }
+    }
+    __syncthreads();
+    //  3. ... and get their score, again one per lane
+    const int nlist2 = s_nlist2;
+    for (int k = tid; k < nlist2; k += kFastThreads) {
+      const int e = list2[k], r = e >> 11, x = e & 2047;
       const uint8_t *px = &pix[(r + 3) * smem_w + x];
-      const int sv = fast_full_t([&](int dx, int dy) { return (int)px[dy * smem_w + dx]; }, threshold);
-      if (sv) sc[r * smem_w + x] = (uint8_t)sv;
+      sc[r * smem_w + x] = (uint8_t)fast_full_t([&](int dx, int dy) { return (int)px[dy * smem_w + dx]; }, threshold);
+    }
+    __syncthreads();
+    //  4. strict 3 x 3 non-maximum suppression on the scored pixels (the second list holds exactly the non-zero scores), one
+    //     per lane; the survivors' scores are parked in the pixel plane, which nobody reads any more
+    const int brows = min(kBH, ch - y0);
+    for (int i = tid; i < brows * (smem_w >> 2); i += kFastThreads) reinterpret_cast<unsigned *>(pix)[i] = 0;
+    __syncthreads();
+    for (int k = tid; k < nlist2; k += kFastThreads) {
+      const int e = list2[k], r = e >> 11, x = e & 2047;
+      if (r < 1 || r > brows) continue;
+      const uint8_t *c = &sc[r * smem_w + x];
+      const int sv = c[0];
+      if (sv > c[-1] && sv > c[1] && sv > c[-smem_w - 1] && sv > c[-smem_w] && sv > c[-smem_w + 1] && sv > c[smem_w - 1] &&
+          sv > c[smem_w] && sv > c[smem_w + 1])
+        pix[(r - 1) * smem_w + x] = (uint8_t)sv;
     }
   } else {
     for (int i = tid; i < (kBH + 2) * cw; i += kFastThreads) {
@@ -211,24 +267,8 @@ __device__ __forceinline__ void fast_body(const uint8_t *__restrict__ img, int p
   if (words) {
     for (int p = p0; p < p1; p += 4) {
       const int r = p / cw, x = p - r * cw;
-      const unsigned wv = *reinterpret_cast<const unsigned *>(&sc[(r + 1) * smem_w + x]);
-      unsigned kept = 0;
-      if (wv) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int sv = (int)((wv >> (8 * k)) & 0xffu), xx = x + k;
-          if (sv > 0 && xx > 0 && xx < cw - 1) {
-            const uint8_t *c = &sc[(r + 1) * smem_w + xx];
-            const bool keep = sv > c[-1] && sv > c[1] && sv > c[-smem_w - 1] && sv > c[-smem_w] && sv > c[-smem_w + 1] &&
-                              sv > c[smem_w - 1] && sv > c[smem_w] && sv > c[smem_w + 1];
-            if (keep) {
-              kept |= (unsigned)sv << (8 * k);
-              cnt++;
-            }
-          }
-        }
-      }
-      *reinterpret_cast<unsigned *>(&pix[r * smem_w + x]) = kept;
+      const unsigned kept = *reinterpret_cast<const unsigned *>(&pix[r * smem_w + x]);
+      cnt += __popc(__vcmpne4(kept, 0u) & 0x01010101u);
     }
   } else {
     for (int p = p0; p < p1; p++) {
@@ -299,7 +339,7 @@ __global__ void __launch_bounds__(kFastThreads)
   fast_body(img, pitch, cells, max_bands, threshold, total, band_off, band_cnt, kps, kps_cap, smem_w);
 }
 // grid = (band, cell, job)
-__global__ void __launch_bounds__(kFastThreads, 3)
+__global__ void __launch_bounds__(kFastThreads, 4)
     k_fast_b(const SlotRec *__restrict__ slots, const FrontJob *__restrict__ jobs, FrontGeom g, int smem_w) {
   const SlotRec &sl = slots[jobs[blockIdx.z].slot];
   fast_body(sl.lvl[0].p, sl.lvl[0].pitch, g.cells, g.max_bands, g.fast_threshold, sl.fast_total, sl.band_off, sl.band_cnt, sl.kps,
@@ -375,7 +415,7 @@ __global__ void __launch_bounds__(kSelThreads)
 void launch_fast_batch(const SlotRec *slots, const FrontJob *jobs, int n_jobs, const FrontGeom &g, cudaStream_t s) {
   if (n_jobs <= 0 || g.n_cells <= 0) return;
   const int smem_w = (g.max_cell_w + 15) & ~15;
-  const size_t smem = (size_t)(2 * kBH + 10) * smem_w + 3 * kFastPad + (size_t)(kBH + 2) * smem_w * 2;
+  const size_t smem = (size_t)(2 * kBH + 10) * smem_w + 3 * kFastPad + (size_t)(kBH + 2) * smem_w * 4;
   static SmemOptIn optin;
   optin.ensure(k_fast_b, smem);
   PLVIWO_CARVEOUT(k_fast_b);
@@ -406,7 +446,7 @@ void launch_fast(const DevImage &img, const FastCell *d_cells, int n_cells, int 
                  unsigned *d_total, int *d_band_off, int *d_band_cnt, unsigned *d_kps, int kps_cap, cudaStream_t s) {
   if (n_cells <= 0) return;
   int smem_w = (max_cell_w + 15) & ~15;
-  size_t smem = (size_t)(2 * kBH + 10) * smem_w + 3 * kFastPad + (size_t)(kBH + 2) * smem_w * 2;
+  size_t smem = (size_t)(2 * kBH + 10) * smem_w + 3 * kFastPad + (size_t)(kBH + 2) * smem_w * 4;
   static SmemOptIn optin;
   optin.ensure(k_fast, smem);
   dim3 grid(max_bands, n_cells);

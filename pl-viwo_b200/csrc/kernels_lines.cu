@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kTileThreads)
   __shared__ int a_cnt[kTilePx], a_ymax[kTilePx], a_xmin[kTilePx], a_xmax[kTilePx];
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && tid < 8) fb.counters[tid] = 0;
+  // (counters and the local-root count are zeroed by k_ccl_reset, ahead of this launch)
   if (tid < kTileH * 2) {
     const int r = tid >> 1, k = tid & 1;
     const int gy = y0 + r, gw = (x0 >> 5) + k;
@@ -219,10 +219,12 @@ __global__ void __launch_bounds__(kTileThreads)
   // thread t owns the 4 pixels (4 (t % 16) .., t / 16)
   const int ly = tid >> 4, lx0 = (tid & 15) << 2;
   const unsigned nib = (bits[ly][lx0 >> 5] >> (lx0 & 31)) & 15u;
+  // only edge pixels are ever looked at below (neighbours are tested on the bit map first): nothing to set up elsewhere
 #pragma unroll
   for (int k = 0; k < 4; k++) {
+    if (!((nib >> k) & 1u)) continue;
     const int p = ly * kTileW + lx0 + k;
-    lab[p] = ((nib >> k) & 1u) ? p : -1;
+    lab[p] = p;
     a_cnt[p] = 0;
     a_ymax[p] = 0;
     a_xmin[p] = kTileW;
@@ -278,8 +280,8 @@ __global__ void __launch_bounds__(kTileThreads)
       bbox[gi] = y0 + a_ymax[p];
       bbox[n + gi] = x0 + a_xmin[p];
       bbox[2 * n + gi] = x0 + a_xmax[p];
-    } else {
-      cnt[gi] = 0;
+      const int q = atomicAdd(fb.lroot_n, 1);   // tile-local roots, for k_ccl_link
+      if (q < fb.lroot_cap) fb.lroots[q] = gi;
     }
   }
 }
@@ -312,33 +314,50 @@ __global__ void k_ccl_border(const __grid_constant__ B b, int w, int h) {
   if (y < h - 1 && edge_at(edges, words_per_row, x - 1, y + 1)) ccl_union(label, i, i + w - 1);
 }
 
-// One thread per 32-pixel word of the edge map.
+template <class B>
+__global__ void k_ccl_reset(const __grid_constant__ B b) {
+  const FldBuffers &fb = b.fld_of(blockIdx.x);
+  if (threadIdx.x < 8) fb.counters[threadIdx.x] = 0;
+  if (threadIdx.x == 8) *fb.lroot_n = 0;
+}
+
+// One thread per tile-local root: find the global root once, point straight at it, hand the aggregates over.
+template <class B>
+__global__ void k_ccl_link(const __grid_constant__ B b, int w, int h) {
+  const FldBuffers &fb = b.fld_of(blockIdx.y);
+  int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt, *__restrict__ bbox = fb.bbox;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= min(*fb.lroot_n, fb.lroot_cap)) return;
+  const int i = fb.lroots[t];
+  const int root = ccl_find(label, i);
+  if (root == i) return;
+  const int n = w * h;
+  atomicExch(label + i, root);   // other threads may be walking through this node: any ancestor is a valid parent
+  atomicAdd(cnt + root, cnt[i]);
+  atomicMax(bbox + root, bbox[i]);
+  atomicMin(bbox + n + root, bbox[n + i]);
+  atomicMax(bbox + 2 * n + root, bbox[2 * n + i]);
+}
+
+// One thread per 32-pixel word of the edge map: a pixel's label is its tile-local root's label (the global root).
 template <class B>
 __global__ void k_ccl_flatten(const __grid_constant__ B b, int w, int h) {
   const FldBuffers &fb = b.fld_of(blockIdx.y);
   const int words_per_row = fb.words_per_row;
-  int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt, *__restrict__ bbox = fb.bbox;
+  int *__restrict__ label = fb.label;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= words_per_row * h) return;
   unsigned e = fb.edges[t];
   if (!e) return;
   const int y = t / words_per_row, xb = (t - y * words_per_row) << 5;
-  const int n = w * h;
   while (e) {
     const int k = __ffs((int)e) - 1;
     e &= e - 1;
     const int x = xb + k;
     if (x >= w) break;
     const int i = y * w + x;
-    const int root = ccl_find(label, i);
-    label[i] = root;
-    const int c = cnt[i];
-    if (c > 0 && root != i) {   // a tile-local root under another tile's root: its aggregates move up
-      atomicAdd(cnt + root, c);
-      atomicMax(bbox + root, bbox[i]);
-      atomicMin(bbox + n + root, bbox[n + i]);
-      atomicMax(bbox + 2 * n + root, bbox[2 * n + i]);
-    }
+    const int l = label[i];
+    if (l != i) label[i] = __ldcg(label + l);
   }
 }
 
@@ -917,6 +936,9 @@ int FldBuffers::alloc(int w, int h, int length_threshold, int out_capacity) {
   A(&bbox, 3 * n * sizeof(int));
   A(&comp_root, (size_t)(max_chains + comp_cap_big((int)n) + comp_cap_b((int)n)) * sizeof(int));
   A(&counters, 8 * sizeof(int));
+  lroot_cap = (int)(n / 4 + 1);
+  A(&lroots, (size_t)lroot_cap * sizeof(int));
+  A(&lroot_n, sizeof(int));
   A(&chain_pts, n * sizeof(int2));
   A(&chain_seed, (size_t)max_chains * sizeof(int));
   A(&chain_off, (size_t)max_chains * sizeof(int));
@@ -930,6 +952,7 @@ int FldBuffers::alloc(int w, int h, int length_threshold, int out_capacity) {
 }
 
 void FldBuffers::release() {
+  cudaFree(lroots); cudaFree(lroot_n);
   cudaFree(edges); cudaFree(label); cudaFree(cnt); cudaFree(bbox); cudaFree(comp_root); cudaFree(counters);
   cudaFree(chain_pts); cudaFree(chain_seed); cudaFree(chain_off); cudaFree(chain_len); cudaFree(order);
   cudaFree(segs); cudaFree(seg_cnt); cudaFree(out);
@@ -940,7 +963,10 @@ template <class B>
 static void launch_fld_any(const B &b, int nb_frames, int w, int h, int max_chains, int length_threshold, float distance_threshold,
                            cudaStream_t s, cudaEvent_t *ev) {
   const int n = w * h;
-  const int tpb = 256, nb = (n + tpb - 1) / tpb;
+  const int tpb = 256;
+  const int lroot_cap = n / 4 + 1;
+  PLVIWO_CARVEOUT(k_ccl_reset<B>);
+  k_ccl_reset<B><<<nb_frames, 32, 0, s>>>(b);
   PLVIWO_CARVEOUT(k_ccl_tile<B>);
   k_ccl_tile<B><<<dim3((w + kTileW - 1) / kTileW, (h + kTileH - 1) / kTileH, nb_frames), kTileThreads, 0, s>>>(b, w, h);
   const int nborder = ((h - 1) / kTileH) * w + ((w - 1) / kTileW) * h;
@@ -949,6 +975,8 @@ static void launch_fld_any(const B &b, int nb_frames, int w, int h, int max_chai
     k_ccl_border<B><<<dim3((nborder + tpb - 1) / tpb, nb_frames), tpb, 0, s>>>(b, w, h);
   }
   const int nwords = ((w + 31) / 32) * h;
+  PLVIWO_CARVEOUT(k_ccl_link<B>);
+  k_ccl_link<B><<<dim3((lroot_cap + tpb - 1) / tpb, nb_frames), tpb, 0, s>>>(b, w, h);
   PLVIWO_CARVEOUT(k_ccl_flatten<B>);
   k_ccl_flatten<B><<<dim3((nwords + tpb - 1) / tpb, nb_frames), tpb, 0, s>>>(b, w, h);
   PLVIWO_CARVEOUT(k_ccl_roots<B>);

@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(kLk15MaxLevels * 32)
 // Here ONE warp owns a feature: it builds level l (the same code, so the float normal matrix is summed in the same order),
 // then runs level l's iterations alone — lane (row, half) owns 8 (7) adjacent window pixels of one row, their I / Ix / Iy
 // values and the 2 x 9 block of the next image under them stay in registers, no barrier, no exchange through shared memory
-// — and moves on to level l - 1.  The mismatch sums are exact integers (per-lane 64-bit, warp reductions on 16-bit pieces),
+// — and moves on to level l - 1.  The mismatch sums are exact integers (per-lane 32-bit, warp reductions on 16-bit halves),
 // so the split of the window over lanes cannot change a bit: results are identical to k_lk15's (tests/test_group_gpu.py
 // compares a group, which runs this kernel, with single handles, which run k_lk15).  An SM holds 32+ features.
 constexpr int kLkwWarps = 4;
@@ -973,20 +973,18 @@ __device__ __forceinline__ void lk15w_body(const Args &a, const float2 *__restri
         }
       }
       // mismatch vector: exact integer sums (the pixels a lane does not own have I = Ix = Iy = 0 and contribute 0)
-      long long s1 = 0, s2 = 0;
+      // |jv - Iw| <= 255 * 32 and |Ix|, |Iy| <= 16 * 255 (Scharr of 8-bit pixels, bilinear weights summing to 1), so a
+      // lane's eight products stay below 2^29: 32-bit per lane, the warp total through 16-bit halves as in k_lk15
+      int s1 = 0, s2 = 0;
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const int jv = (jt[k] * jw00 + jt[k + 1] * jw01 + jb[k] * jw10 + jb[k + 1] * jw11 + (1 << 8)) >> 9;
         const int dv = own ? jv - Iw[k] : 0;
-        s1 += (long long)(dv * Ix[k]);
-        s2 += (long long)(dv * Iy[k]);
+        s1 += dv * Ix[k];
+        s2 += dv * Iy[k];
       }
-      const long long t1 = ((long long)__reduce_add_sync(0xffffffffu, (int)(s1 >> 32)) << 32) +
-                           ((long long)__reduce_add_sync(0xffffffffu, (int)((s1 >> 16) & 0xffff)) << 16) +
-                           (long long)__reduce_add_sync(0xffffffffu, (int)(s1 & 0xffff));
-      const long long t2 = ((long long)__reduce_add_sync(0xffffffffu, (int)(s2 >> 32)) << 32) +
-                           ((long long)__reduce_add_sync(0xffffffffu, (int)((s2 >> 16) & 0xffff)) << 16) +
-                           (long long)__reduce_add_sync(0xffffffffu, (int)(s2 & 0xffff));
+      const long long t1 = ((long long)__reduce_add_sync(0xffffffffu, s1 >> 16) << 16) + (long long)__reduce_add_sync(0xffffffffu, s1 & 0xffff);
+      const long long t2 = ((long long)__reduce_add_sync(0xffffffffu, s2 >> 16) << 16) + (long long)__reduce_add_sync(0xffffffffu, s2 & 0xffff);
       const float b1 = (float)t1 * FLT_SCALE;
       const float b2 = (float)t2 * FLT_SCALE;
       const float2 delta = make_float2((A12 * b2 - A22 * b1) * Dt, (A12 * b1 - A11 * b2) * Dt);

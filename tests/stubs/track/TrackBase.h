@@ -20,6 +20,7 @@ class TrackBase {
   virtual ~TrackBase() {}
   virtual void feed_new_camera(const CameraData &message) = 0;
   std::shared_ptr<FeatureDatabase> get_feature_database() { return database; }
+  void change_feat_id(size_t id_old, size_t id_new) { database->change_feat_id(id_old, id_new); }   // non-virtual (TrackBase.h)
  protected:
   std::unordered_map<size_t, std::shared_ptr<CamBase>> camera_calib;
   std::shared_ptr<FeatureDatabase> database;

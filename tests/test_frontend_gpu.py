@@ -577,3 +577,45 @@ def test_pipelined_with_masks_and_device_frames(fe, synth):
         assert np.array_equal(c0.line_rows()[0], c1.line_rows()[0]), t
     c0.close()
     c1.close()
+
+
+def test_capacity_and_boundary_guards(fe, synth):
+    """Round-1 advisor findings: set_num_features beyond the candidate-table capacity of the handle, state blobs whose line
+    sizes do not add up, the camera-model gate and the shared id counter."""
+    W, H = 640, 280
+    seq = synth.SynthSequence(seed=3, width=W, height=H, n_frames=4, hard=False)
+    kw = dict(num_features=150, fast_threshold=20, grid_x=1, grid_y=1, min_px_dist=10, pyr_levels=3, win_size=15)
+    h = fe.FrontEnd(fe.default_config(width=W, height=H, K=seq.K, D=seq.D, **kw))
+    h.feed_new_camera(seq.timestamp(0), seq.frame(0), None, seq.vanishing_points(0), update_db=False)
+    h.set_num_features(600)                       # 1 cell x 601 candidates fits the 1024 slots of this handle
+    with pytest.raises(fe.FrontEndError):
+        h.set_num_features(2000)                  # 1 x 2001 does not: refused, not an overrun
+    h.feed_new_camera(seq.timestamp(1), seq.frame(1), None, seq.vanishing_points(1), update_db=False)
+    # camera model gate
+    h.set_camera(0, seq.K, seq.D)
+    with pytest.raises(fe.FrontEndError):
+        h.set_camera(1, seq.K, seq.D)             # equidistant: not implemented, must not be silently mis-undistorted
+    # id counter hand-over (TrackBase::currid is shared by the cameras of one tracker)
+    c = h.get_currid()
+    assert c >= 2
+    h.set_currid(c + 1000)
+    h.feed_new_camera(seq.timestamp(2), seq.frame(2), None, seq.vanishing_points(2), update_db=False)
+    assert h.get_currid() >= c + 1000
+    # a blob whose per-line sizes announce more entries than the header: rejected, the tracker state is untouched
+    blob = bytearray(h.get_state())
+    before = h.get_state()
+    hdr = np.frombuffer(bytes(blob[:56]), fe._STATE_HDR, 1)[0]
+    n_pts, n_lines = int(hdr["n_pts"]), int(hdr["n_lines"])
+    if n_lines > 0:
+        off = 56 + 16 * n_pts + 24 * n_lines      # the int32 sizes array
+        sizes = np.frombuffer(bytes(blob[off:off + 4 * n_lines]), np.int32).copy()
+        sizes[0] += 5
+        blob[off:off + 4 * n_lines] = sizes.tobytes()
+        with pytest.raises(fe.FrontEndError):
+            h.set_state(bytes(blob))
+        assert h.get_state() == before
+    bad = bytearray(before)
+    bad[4:8] = np.uint32(7).tobytes()             # unknown version
+    with pytest.raises(fe.FrontEndError):
+        h.set_state(bytes(bad))
+    h.close()
