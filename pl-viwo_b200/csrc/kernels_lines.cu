@@ -582,6 +582,7 @@ __device__ __forceinline__ void walk_component(const WalkCtx &c, unsigned *bm, u
     const int g = sg + lane;
     const unsigned v = g < groups ? bm[(sy + kPadRows) * ws + 1 + g] : 0u;
     const unsigned any = __ballot_sync(0xffffffffu, v != 0);
+    __syncwarp();   // every lane's probe has been read before a lane consumes a pixel below (write after read)
     if (!any) {
       sg += 32;
       if (sg >= groups) { sg = 0; sy++; }
@@ -606,6 +607,7 @@ __device__ __forceinline__ void walk_component(const WalkCtx &c, unsigned *bm, u
       const int qb = p + my_dc;
       const unsigned word = lds_u32(bm_addr + 4u * (unsigned)(rb + my_off + (qb >> 5)));
       Bw = __ballot_sync(0xffffffffu, (word >> (qb & 31)) & 1u);
+      __syncwarp();
     }
     while (true) {
       // Bw: window around the previous pixel (the seed itself in the first round); the current pixel sits at offset
@@ -619,6 +621,7 @@ __device__ __forceinline__ void walk_component(const WalkCtx &c, unsigned *bm, u
       if (lane == 0) c.chain_pts[npts] = make_int2(xbase + p, y0 + cy);
       npts++;
       Bw = __ballot_sync(0xffffffffu, (word >> (qb & 31)) & 1u);
+      __syncwarp();   // all window loads of this round are done before a lane rewrites its word below (write after read)
       const unsigned e = __byte_perm(ev.x, ev.y, dsel);   // byte dsel of the 8 entries
       const unsigned i = e & 15u;
       if (i == 8u) break;

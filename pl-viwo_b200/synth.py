@@ -70,7 +70,7 @@ class SynthSequence:
             y = int(rng.integers(0, ch - h))
             delta = float(rng.choice([-1, 1]) * rng.uniform(18, 55))
             img[y:y + h, x:x + w] += delta
-            if rng.random() < 0.6:  # window grid
+            if rng.random() < (0.0 if self.line_heavy else 0.6):  # window grid (the line-heavy scene keeps its edges long)
                 nx, ny = int(rng.integers(2, 6)), int(rng.integers(2, 5))
                 for i in range(nx):
                     for j in range(ny):
@@ -78,7 +78,7 @@ class SynthSequence:
                         wy = y + int((j + 0.2) * h / ny)
                         ww, wh = max(3, int(0.55 * w / nx)), max(3, int(0.55 * h / ny))
                         img[wy:wy + wh, wx:wx + ww] -= delta * 1.3
-        n_strokes = 650 if self.line_heavy else 300
+        n_strokes = 150 if self.line_heavy else 300
         for _ in range(n_strokes):
             L = rng.uniform(60, 400) * self.sc
             ang = rng.uniform(0, np.pi)
@@ -91,6 +91,25 @@ class SynthSequence:
             layer = np.zeros((ch, cw), np.float32)
             cv2.line(layer, (int(x0), int(y0)), (int(x1), int(y1)), 1.0, th, cv2.LINE_AA)
             img += val * layer
+        if self.line_heavy:
+            # BASELINE.json configs[2] wants >= 300 segments longer than TrackLSD's 40 px cut: a jittered lattice of long,
+            # slightly tilted bars ("street grid / facade lines").  Crossings are >= 50 px apart in the frame at every zoom
+            # of the sequence, so each bar contributes pieces longer than the cut on both of its sides.
+            P = 80.0 * self.sc
+            for k in range(int(cw / P) + 2):
+                x = (k + rng.uniform(-0.2, 0.2)) * P
+                tilt = rng.normal(0, 0.03) * ch
+                val = float(rng.choice([-1, 1]) * rng.uniform(40, 70))
+                layer = np.zeros((ch, cw), np.float32)
+                cv2.line(layer, (int(x - tilt / 2), 0), (int(x + tilt / 2), ch - 1), 1.0, int(rng.integers(3, 6)), cv2.LINE_AA)
+                img += val * layer
+            for k in range(int(ch / P) + 2):
+                y = (k + rng.uniform(-0.2, 0.2)) * P
+                tilt = rng.normal(0, 0.03) * cw
+                val = float(rng.choice([-1, 1]) * rng.uniform(40, 70))
+                layer = np.zeros((ch, cw), np.float32)
+                cv2.line(layer, (0, int(y - tilt / 2)), (cw - 1, int(y + tilt / 2)), 1.0, int(rng.integers(3, 6)), cv2.LINE_AA)
+                img += val * layer
         self.canvas = np.clip(img, 40, 200).astype(np.float32)
 
     # ------------------------------------------------------------------ motion

@@ -8,11 +8,10 @@ mkdir -p $out
 export CUDA_DEVICE_MAX_CONNECTIONS=32
 KTESTS="tests/test_kernels_gpu.py"
 FTEST="tests/test_frontend_gpu.py::test_teacher_forced_1280x560"
-GTEST="tests/test_group_gpu.py"
-[ -f $GTEST ] || GTEST=""
+GTEST="tests/test_group_gpu.py::test_group_equals_single_handles tests/test_group_gpu.py::test_group_masks_clahe_partial_ticks_and_reset"
 for tool in memcheck racecheck; do
   lim=900
-  [ $tool = racecheck ] && lim=1200
+  [ $tool = racecheck ] && lim=1500
   log=$out/sanitizer_${tag}_${tool}.txt
   echo "== compute-sanitizer --tool $tool ($(date -u +%FT%TZ))" > $log
   timeout $lim compute-sanitizer --tool $tool --error-exitcode 86 --print-limit 20 \

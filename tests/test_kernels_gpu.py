@@ -147,3 +147,20 @@ def test_clahe_bit_exact(fe, synth, shape):
     else:
         img = rng.integers(0, 256, shape, dtype=np.uint8)
     assert np.array_equal(fe.op_clahe(img), cvops.clahe(img))
+
+
+def test_fld_restatement_against_contrib_golden(fe):
+    """The CUDA line extractor against the real cv::ximgproc::FastLineDetector output (tests/golden/make_golden_fld.py);
+    skipped only while the golden file is absent (no opencv_contrib in the authoring image)."""
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gpath = os.path.join(here, "fld_golden.npz")
+    if not os.path.exists(gpath):
+        pytest.skip("tests/golden/fld_golden.npz absent: run tests/golden/make_golden_fld.py where cv2.ximgproc exists")
+    inputs, golden = dict(np.load(os.path.join(here, "fld_inputs.npz"))), dict(np.load(gpath))
+    for name, img in inputs.items():
+        got = fe.op_fld(img)
+        want = golden[name]
+        assert got.shape == want.shape, (name, got.shape, want.shape)
+        if len(want):
+            assert np.abs(got - want).max() <= 2e-3, name

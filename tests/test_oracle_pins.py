@@ -168,3 +168,33 @@ def test_frontend_oracle_matches_golden_rows():
                 assert np.abs(uv[:, :2] - g[:, 1:3]).max() < (1e-6 if ops is cvops else 2e-2)
             assert list(fe.klt.get_last_ids()) == list(GOLD["fe_last_ids_%d" % t])
             assert [r.id for r in lrow] == list(GOLD["fe_line_ids_%d" % t])
+
+
+def _fld_golden():
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gpath, ipath = os.path.join(here, "fld_golden.npz"), os.path.join(here, "fld_inputs.npz")
+    if not os.path.exists(gpath):
+        pytest.skip("tests/golden/fld_golden.npz absent: run tests/golden/make_golden_fld.py where cv2.ximgproc exists "
+                    "(FastLineDetector parity stays unpinned until then)")
+    return dict(np.load(ipath)), dict(np.load(gpath))
+
+
+def test_fld_inputs_are_committed():
+    """The images the FastLineDetector pin is generated from travel with the repo (tests/golden/make_golden_fld.py)."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fld_inputs.npz"))
+    assert set(d.files) == {"kaist_320x192", "kaist_640x280", "lines_640x280"}
+    assert d["kaist_640x280"].shape == (280, 640) and d["kaist_320x192"].dtype == np.uint8
+
+
+def test_fld_restatement_against_contrib_golden():
+    """oracle/csrc/oracle_shim.cpp (FastLineDetector restated) against the real cv::ximgproc::FastLineDetector output:
+    same number of segments, same order, end points to 1e-3 px."""
+    from oracle import cvops
+    inputs, golden = _fld_golden()
+    for name, img in inputs.items():
+        got = cvops.fld_detect(img)
+        want = golden[name]
+        assert got.shape == want.shape, (name, got.shape, want.shape)
+        assert np.abs(got - want).max() <= 1e-3 if len(want) else True, name
