@@ -41,7 +41,7 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before the CUDA c
 
 WORKLOAD = dict(width=1280, height=560, num_features=400, fast_threshold=20, grid_x=5, grid_y=5, min_px_dist=10,
                 pyr_levels=4, win_size=15)
-N_STREAMS = 64
+N_STREAMS = int(os.environ.get("PLVIWO_BENCH_STREAMS", "64"))   # 64 = BASELINE.json configs[4]; the override is for experiments
 SEQ_FRAMES = 64          # distinct frames per stream, played forwards and backwards (ping-pong: no jump at the wrap)
 FRAMES_PER_STEP = 32
 METRIC = "front-end frames/sec @1280x560"

@@ -696,7 +696,9 @@ class GroupEngine:
     def __init__(self, fe_mod, dev, metas, workload, lookahead=None):
         # ticks in flight: the chain walk of a tick's frames lasts ~3 ms (its longest component), the other kernels of a tick
         # ~2 ms: six ticks in flight keep the device busy while walks finish (measured: 3 -> 6 ticks +5 %, 10 no more)
-        la = int(os.environ.get("PLVIWO_BENCH_GROUP_LA", "0")) or lookahead or (6 if len(metas) >= 16 else 12)
+        # (profiles/sweep_group.sh, one B200: 64 streams 3 ticks 31.7 k frames/s, 6: 33.6 k, 12: 38.3 k, 16: 38.6 k; 8 streams
+        # 12: 15.1 k, 24: 20.2 k, 48: 20.1 k)
+        la = int(os.environ.get("PLVIWO_BENCH_GROUP_LA", "0")) or lookahead or (12 if len(metas) >= 16 else 24)
         self.lookahead = la
         self.metas = metas
         self.g = GroupFrontEnd(default_config(lookahead=la, **workload), len(metas), device=dev, calibs=[(K, D) for K, D, _ in metas])

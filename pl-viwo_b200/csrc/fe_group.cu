@@ -86,10 +86,14 @@ int FeGroup::init() {
   RB_ = la_ + 2;
   {   // ticks whose state-independent work shares one set of launches: enough frames per launch to fill the device
     const char *e = std::getenv("PLVIWO_GROUP_FRONT_TICKS");
-    int b = e ? std::atoi(e) : std::max(1, 32 / std::max(S_, 1));
-    B_ = std::max(1, std::min(b, std::max(la_, 1)));
+    // measured on B200 (profiles/sweep_group.sh): launches that carry >= 128-256 frames run the image / FAST / line kernels
+    // at their best (64 streams: 1 tick per batch 33.6 k frames/s, 2: 37.8 k, 4: 38.3 k; 32 streams, 4 ticks: 36.0 k)
+    int b = e ? std::atoi(e) : std::max(1, (256 + S_ - 1) / std::max(S_, 1));
+    B_ = std::max(1, std::min(b, std::max(la_ / 3, 1)));
+    // tracking lanes: the streams are split over this many CUDA streams, each running its own detect -> LK -> gate -> lines
+    // chain; the chain is latency bound (~0.4 ms per tick whatever the number of streams), so lanes overlap
     e = std::getenv("PLVIWO_GROUP_LANES");
-    lanes_ = e ? std::atoi(e) : (S_ >= 32 ? 4 : (S_ >= 8 ? 2 : 1));
+    lanes_ = e ? std::atoi(e) : 4;
     lanes_ = std::max(1, std::min(lanes_, S_));
   }
   K_.resize(4 * (size_t)S_);
@@ -261,6 +265,11 @@ int FeGroup::init() {
   for (auto &st : s_front_) FG_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, lo));
   s_track_.resize(lanes_);
   for (auto &st : s_track_) FG_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi));
+  // the line association of tick t only needs tick t's points: it runs beside the point chain of tick t + 1
+  s_lines_.resize(lanes_);
+  for (auto &st : s_lines_) FG_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi));
+  ev_gate_.resize((size_t)RB_ * lanes_);
+  for (auto &e : ev_gate_) FG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   ev_copy_.resize(RB_);
   ev_front_.resize(RB_);
   for (auto &e : ev_copy_) FG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -283,6 +292,8 @@ FeGroup::~FeGroup() {
   if (s_copy_) cudaStreamDestroy(s_copy_);
   for (auto st : s_front_) cudaStreamDestroy(st);
   for (auto st : s_track_) cudaStreamDestroy(st);
+  for (auto st : s_lines_) cudaStreamDestroy(st);
+  for (auto e : ev_gate_) cudaEventDestroy(e);
   for (auto e : ev_copy_) cudaEventDestroy(e);
   for (auto e : ev_front_) cudaEventDestroy(e);
   for (auto e : ev_done_) cudaEventDestroy(e);
@@ -584,15 +595,25 @@ int FeGroup::launch_track(int tick) {
       launches_ += 2;
       launch_group_lk(g_, dj + j0, n, prm, st);
       step(FE_GK_LK);
+      // the gate rewrites pts_last / ids_last, which the previous tick's line association (side stream) still reads
+      if (tick > 0 && cfg_.use_lines && !tm) FG_CUDA(cudaStreamWaitEvent(st, ev_done_[(size_t)((tick - 1) % RB_) * lanes_ + l], 0));
       launch_group_gate(g_, dj + j0, n, st);
       step(FE_GK_GATE);
       launches_ += 3;
+      cudaStream_t sl = st;
       if (cfg_.use_lines) {
-        launch_group_lines(g_, dj + j0, n, st);
+        if (!tm) {   // side stream: ordered after this tick's gate and (stream order) after the previous tick's association
+          sl = s_lines_[l];
+          FG_CUDA(cudaEventRecord(ev_gate_[(size_t)ring * lanes_ + l], st));
+          FG_CUDA(cudaStreamWaitEvent(sl, ev_gate_[(size_t)ring * lanes_ + l], 0));
+        }
+        launch_group_lines(g_, dj + j0, n, sl);
         launches_++;
         step(FE_GK_LINES);
       }
       FG_CUDA(cudaGetLastError());
+      FG_CUDA(cudaEventRecord(ev_done_[(size_t)ring * lanes_ + l], sl));
+      continue;
     }
     FG_CUDA(cudaEventRecord(ev_done_[(size_t)ring * lanes_ + l], st));
   }

@@ -99,7 +99,8 @@ class FeGroup {
   int *h_ljobs_ = nullptr, *d_ljobs_ = nullptr;        // RB * B * S
   TrackJob *h_tjobs_ = nullptr, *d_tjobs_ = nullptr;   // RB * S
   cudaStream_t s_copy_ = nullptr;
-  std::vector<cudaStream_t> s_front_, s_track_;
+  std::vector<cudaStream_t> s_front_, s_track_, s_lines_;
+  std::vector<cudaEvent_t> ev_gate_;                   // per ring entry * lanes: the point chain of the tick is done
   std::vector<cudaEvent_t> ev_copy_, ev_front_;        // per front-batch buffer
   std::vector<cudaEvent_t> ev_done_;                   // per ring entry * lanes
   std::vector<cudaEvent_t> ev_lane_prev_;              // per lane: previous tick's tracking done (front may reuse its slots)

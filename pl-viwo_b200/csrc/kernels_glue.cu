@@ -327,7 +327,8 @@ __global__ void __launch_bounds__(kGT)
   __shared__ BlockScan bs;
   __shared__ float s_ms1[kRounds][14], s_ms2[kRounds][14];
   __shared__ double s_F[kRounds][27];
-  __shared__ int s_nm[kRounds], s_ok[kRounds];
+  __shared__ int s_nm[kRounds], s_ok[kRounds], s_good[kRounds][3];
+  __shared__ double s_bestF[9];
   __shared__ int s_niters, s_maxgood, s_R, s_stop, s_best;
   const TrackJob &job = jobs[blockIdx.x];
   const int s = job.stream, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -424,37 +425,36 @@ __global__ void __launch_bounds__(kGT)
         __syncthreads();
         const int R = s_R;
         if (R == 0) break;
-        if (lane == 0 && warp < R) s_nm[warp] = s_ok[warp] ? rc::run_7point(s_ms1[warp], s_ms2[warp], s_F[warp]) : 0;
-        __syncthreads();
-        for (int r = 0; r < R; r++) {
-          if (iter + r >= s_niters) {   // the adaptive count dropped below the samples solved ahead
-            if (tid == 0) s_stop = 1;
-            break;
-          }
-          if (!s_ok[r]) {
-            if (tid == 0) s_stop = 1;
-            break;
-          }
-          const int nm = s_nm[r];
-          for (int i = 0; i < nm; i++) {
-            const double *F = s_F[r] + 9 * i;
+        // warp r: the 7-point models of sample r (one lane), then their inlier counts over all points (all lanes)
+        if (warp < R) {
+          int nm = 0;
+          if (lane == 0 && s_ok[warp]) nm = rc::run_7point(s_ms1[warp], s_ms2[warp], s_F[warp]);
+          nm = __shfl_sync(0xffffffffu, nm, 0);
+          if (lane == 0) s_nm[warp] = nm;
+          __syncwarp();
+          for (int i = 0; i < nm && i < 3; i++) {
+            const double *F = s_F[warp] + 9 * i;
             int good = 0;
-            for (int k = tid; k < n; k += kGT) {
-              const uint8_t f = rc::epipolar_error(F, m1[k].x, m1[k].y, m2[k].x, m2[k].y) <= t;
-              mcur[k] = f;
-              good += f;
+            for (int k = lane; k < n; k += 32) good += rc::epipolar_error(F, m1[k].x, m1[k].y, m2[k].x, m2[k].y) <= t ? 1 : 0;
+            good = __reduce_add_sync(0xffffffffu, good);
+            if (lane == 0) s_good[warp][i] = good;
+          }
+        }
+        __syncthreads();
+        // the sequential accept rule and adaptive iteration count, in sample order (RANSACPointSetRegistrator::run)
+        if (tid == 0) {
+          for (int r = 0; r < R; r++) {
+            if (iter + r >= s_niters || !s_ok[r]) {   // the count dropped below the samples solved ahead / no sample
+              s_stop = 1;
+              break;
             }
-            good = block_sum(good, bs);
-            if (good > max(s_maxgood, 6)) {   // uniform: every thread sees the same totals
-              uint8_t *tmp = mcur;
-              mcur = mbest;
-              mbest = tmp;
-              __syncthreads();
-              if (tid == 0) {
+            for (int i = 0; i < s_nm[r] && i < 3; i++) {
+              const int good = s_good[r][i];
+              if (good > max(s_maxgood, 6)) {
                 s_maxgood = good;
+                for (int q = 0; q < 9; q++) s_bestF[q] = s_F[r][9 * i + q];
                 s_niters = rc::ransac_update_num_iters(0.999, (double)(n - good) / n, 7, s_niters);
               }
-              __syncthreads();
             }
           }
         }
@@ -463,8 +463,8 @@ __global__ void __launch_bounds__(kGT)
         if (s_stop || iter >= s_niters) break;
       }
       n_in = s_maxgood;
-      if (n_in == 0)
-        for (int i = tid; i < n; i += kGT) mbest[i] = 0;
+      if (n_in > 0)   // the mask of the accepted model
+        for (int k = tid; k < n; k += kGT) mbest[k] = rc::epipolar_error(s_bestF, m1[k].x, m1[k].y, m2[k].x, m2[k].y) <= t ? 1 : 0;
     }
   }
   __syncthreads();
