@@ -578,6 +578,12 @@ def main():
         h_seq[k].copy_(torch.from_numpy(data[k]))
     d_seq.copy_(h_seq)
     torch.cuda.synchronize()
+    # what the host link gives this process (pinned -> device), for reading the e2e number: every frame crosses it once
+    nb = min(S, 8)
+    t0 = time.perf_counter()
+    d_seq[:nb].copy_(h_seq[:nb], non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_gbps = nb * SEQ_FRAMES * H * W / (time.perf_counter() - t0) / 1e9
     d_ptrs = [[d_seq[k, t].data_ptr() for t in range(SEQ_FRAMES)] for k in range(S)]
     h_ptrs = [[h_seq[k, t].numpy() for t in range(SEQ_FRAMES)] for k in range(S)]
 
@@ -712,7 +718,9 @@ def main():
         "e2e": {"value": total_frames_e2e / (ms_e2e * 1e-3), "unit": "frames/s",
                 "h2d_bytes_per_step": res_e2e["counters"]["h2d_bytes"] / args.steps,
                 "d2h_bytes_per_step": res_e2e["counters"]["d2h_bytes"] / args.steps,
-                "api": "pinned host frames through the C ABI (%s), H2D of every frame and D2H of every row inside the timed region" % eng.name},
+                "api": "pinned host frames through the C ABI (%s), H2D of every frame and D2H of every row inside the timed region" % eng.name,
+                "h2d_link_GBps_measured": round(h2d_gbps, 1),
+                "h2d_GBps_used": round(total_frames_e2e / world / (ms_e2e * 1e-3) * H * W / 1e9, 1)},
         "gpu_launches": launches,
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
     }

@@ -378,39 +378,29 @@ __host__ __device__ inline int comp_cap_big(int n) { return n / kClassB + 1; }
 // counters: [0] BIG components, [1] BIG cursor, [2] chain-point cursor, [3] chains, [4] segments, [5] class-B components,
 //           [6] class-C components, [7] cursor over B then C
 template <class B>
-__global__ void k_ccl_roots(const __grid_constant__ B b, int w, int h, int min_pixels) {   // one thread per edge-map word
+__global__ void k_ccl_roots(const __grid_constant__ B b, int w, int h, int min_pixels) {   // one thread per tile-local root
   const FldBuffers &fb = b.fld_of(blockIdx.y);
-  const int words_per_row = fb.words_per_row;
   const int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt, *__restrict__ bbox = fb.bbox;
   int *__restrict__ comp_root = fb.comp_root, *__restrict__ counters = fb.counters;
   const int max_comps = fb.max_chains;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= words_per_row * h) return;
-  unsigned e = fb.edges[t];
-  if (!e) return;
-  const int y = t / words_per_row, xb = (t - y * words_per_row) << 5;
+  if (t >= min(*fb.lroot_n, fb.lroot_cap)) return;
+  const int i = fb.lroots[t];
+  if (label[i] != i) return;   // a global root is the tile-local root of its own tile
+  const int c = cnt[i];
+  if (c < min_pixels) return;
   const int n = w * h;
-  while (e) {
-    const int k = __ffs((int)e) - 1;
-    e &= e - 1;
-    const int x = xb + k;
-    if (x >= w) break;
-    const int i = y * w + x;
-    if (label[i] != i) continue;
-    const int c = cnt[i];
-    if (c < min_pixels) continue;
-    const int bh = bbox[i] - y + 1;
-    const int groups = (bbox[2 * n + i] >> 5) - (bbox[n + i] >> 5) + 1;
-    const bool big = (bh + 2 * kPadRows) * (groups + 2) > kSliceWords;
-    if (big) {
-      const int q = atomicAdd(counters + 0, 1);
-      if (q < comp_cap_big(n)) comp_root[q] = i;
-    } else if (c >= kClassB) {
-      comp_root[comp_cap_big(n) + atomicAdd(counters + 5, 1)] = i;                 // at most n / kClassB
-    } else {
-      const int q = atomicAdd(counters + 6, 1);
-      if (q < max_comps) comp_root[comp_cap_big(n) + comp_cap_b(n) + q] = i;
-    }
+  const int bh = bbox[i] - i / w + 1;
+  const int groups = (bbox[2 * n + i] >> 5) - (bbox[n + i] >> 5) + 1;
+  const bool big = (bh + 2 * kPadRows) * (groups + 2) > kSliceWords;
+  if (big) {
+    const int q = atomicAdd(counters + 0, 1);
+    if (q < comp_cap_big(n)) comp_root[q] = i;
+  } else if (c >= kClassB) {
+    comp_root[comp_cap_big(n) + atomicAdd(counters + 5, 1)] = i;                 // at most n / kClassB
+  } else {
+    const int q = atomicAdd(counters + 6, 1);
+    if (q < max_comps) comp_root[comp_cap_big(n) + comp_cap_b(n) + q] = i;
   }
 }
 
@@ -983,7 +973,7 @@ static void launch_fld_any(const B &b, int nb_frames, int w, int h, int max_chai
   PLVIWO_CARVEOUT(k_ccl_flatten<B>);
   k_ccl_flatten<B><<<dim3((nwords + tpb - 1) / tpb, nb_frames), tpb, 0, s>>>(b, w, h);
   PLVIWO_CARVEOUT(k_ccl_roots<B>);
-  k_ccl_roots<B><<<dim3((nwords + tpb - 1) / tpb, nb_frames), tpb, 0, s>>>(b, w, h, length_threshold + 1);
+  k_ccl_roots<B><<<dim3((lroot_cap + tpb - 1) / tpb, nb_frames), tpb, 0, s>>>(b, w, h, length_threshold + 1);
   if (ev) cudaEventRecord(ev[0], s);
   init_fld_constants();
   const int ws = ((w + 31) >> 5) + 2;

@@ -979,7 +979,7 @@ __device__ __forceinline__ void lk15w_body(const Args &a, const float2 *__restri
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const int jv = (jt[k] * jw00 + jt[k + 1] * jw01 + jb[k] * jw10 + jb[k + 1] * jw11 + (1 << 8)) >> 9;
-        const int dv = own ? jv - Iw[k] : 0;
+        const int dv = jv - Iw[k];   // lanes without pixels hold I = Ix = Iy = 0 and J = 0: dv = 0
         s1 += dv * Ix[k];
         s2 += dv * Iy[k];
       }
