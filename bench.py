@@ -742,8 +742,19 @@ def build_roofline(stage, peak, peak_src, fps_per_gpu, res):
     if isinstance(stage, dict) and "group" in stage:    # stream group: per-kernel CUDA-event times from the library
         t = stage["group"]
         ab = algorithmic_bytes(300.0)
-        bytes_of = {"hist": ab["hist"], "eq_pyr1": ab["eq_pyr1"], "pyr_rest": ab["pyr_rest"], "fast": ab["fast"], "canny": ab["canny"],
-                    "walk": ab["fld_walk"], "lk": ab["lk"]}
+        # FAST runs on the valid cells of the detection only, as the reference does (Grider_GRID.h:108-125): its algorithmic
+        # bytes are the pixels of the cells it ran on (counted by the library), not the whole frame
+        n_cells = WORKLOAD["grid_x"] * WORKLOAD["grid_y"]
+        fast_frames = t["frames_of"].get("fast", 0)
+        fast_frac = min(1.0, t.get("fast_cells", 0) / max(fast_frames * n_cells, 1)) if fast_frames else 1.0
+        out["fast_cells_per_frame"] = round(fast_frac * n_cells, 3)
+        out["whole_frame"]["algorithmic_bytes"] = ab1["frame_total"] - ab1["fast"] * (1.0 - fast_frac)
+        out["whole_frame"]["achieved_GBps"] = out["whole_frame"]["algorithmic_bytes"] * fps_per_gpu / 1e9
+        out["whole_frame"]["frac"] = out["whole_frame"]["achieved_GBps"] / peak
+        out["whole_frame"]["note"] = ("SURVEY 8(d) bytes of a frame with FAST counted on the %.2f of %d grid cells per frame it ran on "
+                                      "(the all-cells figure is %d B)" % (fast_frac * n_cells, n_cells, ab1["frame_total"]))
+        bytes_of = {"hist": ab["hist"], "eq_pyr1": ab["eq_pyr1"], "pyr_rest": ab["pyr_rest"], "fast": ab["fast"] * fast_frac,
+                    "canny": ab["canny"], "walk": ab["fld_walk"], "lk": ab["lk"]}
         ks = {}
         for k, msv in t["ms"].items():
             n, fr = t["launches"][k], t["frames_of"][k]

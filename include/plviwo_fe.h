@@ -307,7 +307,7 @@ int plviwo_fe_stereo_get_stage_times(FeStereoHandle *h, FeStageTimes *out, int r
 typedef struct FeGroupHandle FeGroupHandle;
 enum FeGroupKernel {
   FE_GK_HIST = 0, FE_GK_EQ_PYR1, FE_GK_PYR_REST, FE_GK_FAST, FE_GK_SELECT, FE_GK_SUBPIX, FE_GK_CANNY, FE_GK_CCL, FE_GK_WALK,
-  FE_GK_SEGMENTS, FE_GK_DETECT, FE_GK_LK, FE_GK_GATE, FE_GK_LINES, FE_GK_ACCEPT, FE_GK_COUNT
+  FE_GK_SEGMENTS, FE_GK_DETECT, FE_GK_LK, FE_GK_GATE, FE_GK_LINES, FE_GK_ACCEPT, FE_GK_CANDS, FE_GK_COUNT
 };
 typedef struct FeGroupTimes {
   double ms[16];             /* CUDA-event time per kernel (FeGroupKernel), summed over launches (timing enabled) */
@@ -315,6 +315,7 @@ typedef struct FeGroupTimes {
   uint64_t frames[16];       /* frames carried by those launches                                                   */
   uint64_t ticks, frames_total, kernel_launches_total;
   uint64_t h2d_bytes, d2h_bytes;   /* frames copied in; rows written back to pinned host memory                    */
+  uint64_t fast_cells;       /* grid cells FAST ran on (the valid cells of the detections, Grider_GRID.h:108-125)  */
 } FeGroupTimes;
 
 int plviwo_fe_group_create(const FeConfig *cfg, int n_streams, int device, FeGroupHandle **out);

@@ -87,13 +87,13 @@ class FeStageTimes(C.Structure):
 
 
 GROUP_KERNELS = ["hist", "eq_pyr1", "pyr_rest", "fast", "select", "subpix", "canny", "ccl", "walk", "segments", "detect", "lk", "gate",
-                 "lines", "accept"]
+                 "lines", "accept", "cands"]
 
 
 class FeGroupTimes(C.Structure):
     _fields_ = [("ms", C.c_double * 16), ("launches", C.c_uint64 * 16), ("frames", C.c_uint64 * 16), ("ticks", C.c_uint64),
                 ("frames_total", C.c_uint64), ("kernel_launches_total", C.c_uint64), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64)]
+                ("d2h_bytes", C.c_uint64), ("fast_cells", C.c_uint64)]
 
 
 POINT_ROW_DTYPE = np.dtype([("id", "<u8"), ("u", "<f4"), ("v", "<f4"), ("un", "<f4"), ("vn", "<f4")])
@@ -685,7 +685,7 @@ class GroupFrontEnd:
         return {"ms": {k: t.ms[i] for i, k in enumerate(GROUP_KERNELS)}, "launches": {k: int(t.launches[i]) for i, k in enumerate(GROUP_KERNELS)},
                 "frames_of": {k: int(t.frames[i]) for i, k in enumerate(GROUP_KERNELS)}, "ticks": int(t.ticks),
                 "frames": int(t.frames_total), "kernel_launches_total": int(t.kernel_launches_total),
-                "h2d_bytes": int(t.h2d_bytes), "d2h_bytes": int(t.d2h_bytes)}
+                "h2d_bytes": int(t.h2d_bytes), "d2h_bytes": int(t.d2h_bytes), "fast_cells": int(t.fast_cells)}
 
 
 class GroupEngine:

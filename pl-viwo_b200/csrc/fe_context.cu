@@ -678,7 +678,7 @@ int FeContext::flush_line_batch() {
     s.line_pending = false;
   }
   FE_CUDA(cudaGetLastError());
-  mst_.kernel_launches_total += 12 + n;   // canny, 6 x components, walk, order, segments, compact + one signal per frame
+  mst_.kernel_launches_total += 11 + n;   // canny, 5 x components, walk, order, segments, compact + one signal per frame
   pending_lines_.clear();
   return FE_OK;
 }
@@ -784,7 +784,8 @@ int FeContext::submit_impl(double t, const uint8_t *image, int stride, bool on_d
       src = s.h_raw;
       sstride = Win_;
     }
-    FE_CUDA(cudaMemcpy2DAsync(dst.p, dst.pitch, src, sstride, Win_, Hin_, cudaMemcpyHostToDevice, s.s_a));
+    if (sstride == Win_ && dst.pitch == Win_) FE_CUDA(cudaMemcpyAsync(dst.p, src, (size_t)Win_ * Hin_, cudaMemcpyHostToDevice, s.s_a));   // one contiguous transfer
+    else FE_CUDA(cudaMemcpy2DAsync(dst.p, dst.pitch, src, sstride, Win_, Hin_, cudaMemcpyHostToDevice, s.s_a));
     mst_.h2d_bytes += (size_t)Win_ * Hin_;
   }
   if (cfg_.downsample) {   // cv::pyrDown(img, .., Size(cols / 2.0, rows / 2.0)) (UpdaterCamera.cpp:90-91)

@@ -201,6 +201,8 @@ int FeGroup::init() {
   FG_CUDA(dev_alloc(dev_allocs_, &g_.lk_p1n, P));
   FG_CUDA(dev_alloc(dev_allocs_, &g_.lk_status, P));
   FG_CUDA(dev_alloc(dev_allocs_, &g_.close, (size_t)S_ * std::max(g_.close_w * g_.close_h, 1)));
+  FG_CUDA(dev_alloc(dev_allocs_, &g_.valid, (size_t)S_ * kValidStride));
+  FG_CUDA(dev_alloc(dev_allocs_, &g_.stats, 4));
   FG_CUDA(dev_alloc(dev_allocs_, &g_.ext_in, (size_t)S_ * g_.cand_cap));
   FG_CUDA(dev_alloc(dev_allocs_, &g_.ext_pt, (size_t)S_ * g_.cand_cap));
   {
@@ -256,7 +258,12 @@ int FeGroup::init() {
   // ---- streams and events
   int lo = 0, hi = 0;
   FG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  FG_CUDA(cudaStreamCreateWithPriority(&s_copy_, cudaStreamNonBlocking, lo));
+  {
+    int ncopy = 4;
+    if (const char *e = std::getenv("PLVIWO_GROUP_COPY_STREAMS")) ncopy = std::max(1, std::min(std::atoi(e), 8));
+    s_copy_.resize(ncopy);
+    for (auto &st : s_copy_) FG_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, lo));
+  }
   // front batches of consecutive ticks run on different streams: the tail of one batch's chain walk (a few long
   // components, milliseconds) overlaps the next batches' kernels
   int nfront = std::min(RB_, 6);
@@ -270,7 +277,7 @@ int FeGroup::init() {
   for (auto &st : s_lines_) FG_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi));
   ev_gate_.resize((size_t)RB_ * lanes_);
   for (auto &e : ev_gate_) FG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  ev_copy_.resize(RB_);
+  ev_copy_.resize((size_t)RB_ * s_copy_.size());
   ev_front_.resize(RB_);
   for (auto &e : ev_copy_) FG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto &e : ev_front_) FG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -289,7 +296,7 @@ FeGroup::~FeGroup() {
   for (void *p : host_allocs_) cudaFreeHost(p);
   for (uint8_t *p : h_raw_) if (p) cudaFreeHost(p);
   for (uint8_t *p : h_mask_) if (p) cudaFreeHost(p);
-  if (s_copy_) cudaStreamDestroy(s_copy_);
+  for (auto st : s_copy_) cudaStreamDestroy(st);
   for (auto st : s_front_) cudaStreamDestroy(st);
   for (auto st : s_track_) cudaStreamDestroy(st);
   for (auto st : s_lines_) cudaStreamDestroy(st);
@@ -351,6 +358,12 @@ FeGroupTimes FeGroup::times(bool reset) {
   t.d2h_bytes = d2h_bytes_;
   t.frames_total = frames_done_;
   t.ticks = (uint64_t)collected_;
+  {   // grid cells the detector ran on (device counter; everything collected has finished)
+    unsigned long long v = 0;
+    if (g_.stats && cudaMemcpy(&v, g_.stats, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) t.fast_cells = v - fast_cells_base_;
+    if (reset) fast_cells_base_ = v;
+    cudaGetLastError();
+  }
   if (reset) {
     times_ = FeGroupTimes{};
     launches_ = h2d_bytes_ = d2h_bytes_ = frames_done_ = 0;
@@ -406,7 +419,11 @@ int FeGroup::submit(const double *timestamps, const uint8_t *const *images, int 
         src = h_raw_[slot];
         sstride = W_;
       }
-      FG_CUDA(cudaMemcpy2DAsync(sl.raw.p, sl.raw.pitch, src, sstride, W_, H_, cudaMemcpyHostToDevice, s_copy_));
+      // a tight frame into a tight staging image is ONE contiguous transfer (a 2-D copy is issued row by row: 1280-byte
+      // rows reach less than half of the link's bandwidth)
+      cudaStream_t cs = s_copy_[copy_rr_++ % s_copy_.size()];
+      if (sstride == W_ && sl.raw.pitch == W_) FG_CUDA(cudaMemcpyAsync(sl.raw.p, src, (size_t)W_ * H_, cudaMemcpyHostToDevice, cs));
+      else FG_CUDA(cudaMemcpy2DAsync(sl.raw.p, sl.raw.pitch, src, sstride, W_, H_, cudaMemcpyHostToDevice, cs));
       h2d_bytes_ += (size_t)W_ * H_;
       fj.src = sl.raw.p;
       fj.src_pitch = sl.raw.pitch;
@@ -416,7 +433,7 @@ int FeGroup::submit(const double *timestamps, const uint8_t *const *images, int 
       int rc = ensure_mask_buffer(slot);
       if (rc) return rc;
       for (int y = 0; y < H_; y++) std::memcpy(h_mask_[slot] + (size_t)y * W_, masks[s] + (size_t)y * mask_stride, W_);
-      FG_CUDA(cudaMemcpyAsync(slots_[slot].mask, h_mask_[slot], (size_t)W_ * H_, cudaMemcpyHostToDevice, s_copy_));
+      FG_CUDA(cudaMemcpyAsync(slots_[slot].mask, h_mask_[slot], (size_t)W_ * H_, cudaMemcpyHostToDevice, s_copy_[copy_rr_++ % s_copy_.size()]));
       h2d_bytes_ += (size_t)W_ * H_;
       fj.flags |= 1;
     }
@@ -476,8 +493,11 @@ int FeGroup::launch_front(FrontBatch &b, int buf) {
   std::memcpy(hj, b.jobs.data(), nj * sizeof(FrontJob));
   if (nl) std::memcpy(hl, b.line_slots.data(), nl * sizeof(int));
   // the frames (and masks) of the batch are on their way on the copy stream
-  FG_CUDA(cudaEventRecord(ev_copy_[buf], s_copy_));
-  FG_CUDA(cudaStreamWaitEvent(st, ev_copy_[buf], 0));
+  for (size_t c = 0; c < s_copy_.size(); c++) {
+    cudaEvent_t ev = ev_copy_[(size_t)buf * s_copy_.size() + c];
+    FG_CUDA(cudaEventRecord(ev, s_copy_[c]));
+    FG_CUDA(cudaStreamWaitEvent(st, ev, 0));
+  }
   FG_CUDA(cudaMemcpyAsync(dj, hj, nj * sizeof(FrontJob), cudaMemcpyHostToDevice, st));
   if (nl) FG_CUDA(cudaMemcpyAsync(dl, hl, nl * sizeof(int), cudaMemcpyHostToDevice, st));
   const bool tm = timing_;
@@ -512,14 +532,8 @@ int FeGroup::launch_front(FrontBatch &b, int buf) {
     launches_++;
   }
   step(FE_GK_PYR_REST, nj);
-  if (fg_.n_cells > 0) {
-    launch_fast_batch(d_slots_, dj, nj, fg_, st);
-    launches_++;
-    step(FE_GK_FAST, nj);
-    launch_fast_select_batch(d_slots_, dj, nj, fg_, st);
-    launches_++;
-    step(FE_GK_SELECT, nj);
-  }
+  // FAST is NOT here: the reference runs it on the cells the detection finds short of features only (Grider_GRID.h:108-125,
+  // 1-3 of 25 cells on a tracked sequence), so it runs inside the detection of the tick (launch_track)
   if (nl > 0) {
     launch_canny_table(d_slots_, dl, nl, W_ / 2, H_ / 2, cfg_.canny_th1, st);
     launches_++;
@@ -531,7 +545,7 @@ int FeGroup::launch_front(FrontBatch &b, int buf) {
     }
     launch_fld_table(d_slots_, dl, nl, W_ / 2, H_ / 2, s0.fld.max_chains, cfg_.fld_length_threshold, cfg_.fld_distance_threshold, st,
                      tm ? ev2 : nullptr);
-    launches_ += 10;
+    launches_ += 9;
     if (tm) {
       cudaEvent_t e1 = mark();
       account(FE_GK_CCL, e0, ev2[0], nl);
@@ -588,11 +602,20 @@ int FeGroup::launch_track(int tick) {
       }
       launch_group_detect(g_, dj + j0, n, st);
       step(FE_GK_DETECT);
+      if (fg_.n_cells > 0) {
+        launch_group_fast(g_, dj + j0, n, fg_, st);
+        step(FE_GK_FAST);
+        launch_group_fast_select(g_, dj + j0, n, fg_, st);
+        step(FE_GK_SELECT);
+        launches_ += 2;
+      }
+      launch_group_cands(g_, dj + j0, n, st);
+      step(FE_GK_CANDS);
       launch_group_subpix(g_, dj + j0, n, st);
       step(FE_GK_SUBPIX);
       launch_group_accept(g_, dj + j0, n, st);
       step(FE_GK_ACCEPT);
-      launches_ += 2;
+      launches_ += 3;
       launch_group_lk(g_, dj + j0, n, prm, st);
       step(FE_GK_LK);
       // the gate rewrites pts_last / ids_last, which the previous tick's line association (side stream) still reads
@@ -911,10 +934,6 @@ int FeGroup::set_state(int s, const void *buf, size_t n_bytes) {
     launch_hist_batch(d_slots_, d_fjobs_, 1, fg_, d_slot_flags_, st);
     launch_eq_pyr1_batch(d_slots_, d_fjobs_, 1, fg_, cfg_.use_lines != 0, st);
     for (int l = 2; l < sl.n_lvl; l++) launch_pyr_level_batch(d_slots_, d_fjobs_, 1, l, sl.lvl[l].w, sl.lvl[l].h, st);
-    if (fg_.n_cells > 0) {
-      launch_fast_batch(d_slots_, d_fjobs_, 1, fg_, st);
-      launch_fast_select_batch(d_slots_, d_fjobs_, 1, fg_, st);
-    }
     FG_CUDA(cudaGetLastError());
     FG_CUDA(cudaStreamSynchronize(st));
     prev_slot_[s] = slot;

@@ -98,7 +98,8 @@ class FeGroup {
   FrontJob *h_fjobs_ = nullptr, *d_fjobs_ = nullptr;   // RB * B * S
   int *h_ljobs_ = nullptr, *d_ljobs_ = nullptr;        // RB * B * S
   TrackJob *h_tjobs_ = nullptr, *d_tjobs_ = nullptr;   // RB * S
-  cudaStream_t s_copy_ = nullptr;
+  std::vector<cudaStream_t> s_copy_;                   // frames go in round-robin over a few copy streams (a 0.7 MB copy has a fixed cost that only overlaps across streams)
+  unsigned copy_rr_ = 0;
   std::vector<cudaStream_t> s_front_, s_track_, s_lines_;
   std::vector<cudaEvent_t> ev_gate_;                   // per ring entry * lanes: the point chain of the tick is done
   std::vector<cudaEvent_t> ev_copy_, ev_front_;        // per front-batch buffer
@@ -121,7 +122,7 @@ class FeGroup {
   size_t ev_next_ = 0;
   cudaEvent_t timing_event();
   int drain_timing();
-  uint64_t launches_ = 0, h2d_bytes_ = 0, d2h_bytes_ = 0, frames_done_ = 0;
+  uint64_t launches_ = 0, h2d_bytes_ = 0, d2h_bytes_ = 0, frames_done_ = 0, fast_cells_base_ = 0;
 };
 
 }  // namespace plviwo

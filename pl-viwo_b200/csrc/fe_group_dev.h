@@ -33,6 +33,8 @@ struct GroupOutHeader {
   int32_t reserved[12];
 };
 
+constexpr int kValidStride = 260;
+
 struct GroupDev {
   // ---- geometry / parameters (FeConfig)
   int W, H;
@@ -62,6 +64,8 @@ struct GroupDev {
   float2 *lk_pts1, *lk_p0n, *lk_p1n;
   uint8_t *lk_status;
   int *close;                    // min-distance grid of the detection, stream s at s * close_w * close_h
+  int *valid;                    // valid cells of the detection, stream s at s * kValidStride: [0] count, [4 + i] cell index (or -1)
+  unsigned long long *stats;     // [0] grid cells FAST ran on (all streams, since creation)
   float2 *ext_in;                // candidates of the valid cells that passed the mask test, stream s at s * cand_cap
   float2 *ext_pt;                // ... after cornerSubPix
   // ---- line tracker state, double buffered (buffer b of stream s at (2 * s + b) * cap)
@@ -85,7 +89,13 @@ struct GroupDev {
 };
 
 // tracking launches (kernels_glue.cu, kernels_track.cu)
+// the top-off detection of a tick: k_group_detect (existing points, valid cells) -> FAST + selection on the VALID cells only
+// (Grider_GRID.h:108-151 runs cv::FAST on valid_locs only) -> k_group_cands (mask / occupancy test of the candidates)
+// -> cornerSubPix -> k_group_accept
 void launch_group_detect(const GroupDev &g, const TrackJob *jobs, int n_jobs, cudaStream_t s);
+void launch_group_fast(const GroupDev &g, const TrackJob *jobs, int n_jobs, const FrontGeom &fg, cudaStream_t s);          // kernels_fast.cu
+void launch_group_fast_select(const GroupDev &g, const TrackJob *jobs, int n_jobs, const FrontGeom &fg, cudaStream_t s);   // kernels_fast.cu
+void launch_group_cands(const GroupDev &g, const TrackJob *jobs, int n_jobs, cudaStream_t s);
 void launch_group_subpix(const GroupDev &g, const TrackJob *jobs, int n_jobs, cudaStream_t s);   // kernels_track.cu
 void launch_group_accept(const GroupDev &g, const TrackJob *jobs, int n_jobs, cudaStream_t s);
 void launch_group_lk(const GroupDev &g, const TrackJob *jobs, int n_jobs, const LkParams &prm, cudaStream_t s);

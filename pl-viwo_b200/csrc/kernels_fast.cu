@@ -10,6 +10,7 @@
 // halo that is CLAMPED TO THE CELL (rows outside the cell simply do not exist), scores go to a second shared
 // plane, and survivors are emitted with an ordered block-wide compaction.  Bands of a cell reserve their slice
 // of the compact output with one atomic; the host (or the selection kernel) walks bands in order.
+#include "fe_group_dev.h"
 #include "fe_kernels.h"
 #include "introsort.h"
 
@@ -102,7 +103,7 @@ __device__ __forceinline__ int fast_score(const uint8_t *__restrict__ px, int st
 
 constexpr int kFastPad = 16;   // bytes in front of the staged pixels: the 4-pixel path reads the word left of column 0
 
-__device__ __forceinline__ void fast_body(const uint8_t *__restrict__ img, int pitch, const FastCell *__restrict__ cells, int max_bands,
+__device__ __forceinline__ void fast_body(const int cell_idx, const uint8_t *__restrict__ img, int pitch, const FastCell *__restrict__ cells, int max_bands,
                                           int threshold, unsigned *__restrict__ total, int *__restrict__ band_off,
                                           int *__restrict__ band_cnt, unsigned *__restrict__ kps, int kps_cap, int smem_w) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -111,9 +112,9 @@ __device__ __forceinline__ void fast_body(const uint8_t *__restrict__ img, int p
   __shared__ int warp_tot[kFastThreads / 32];
   __shared__ int s_base, s_nlist, s_nlist2;
 
-  const FastCell cell = cells[blockIdx.y];
+  const FastCell cell = cells[cell_idx];
   const int band = blockIdx.x;
-  const int slot = blockIdx.y * max_bands + band;
+  const int slot = cell_idx * max_bands + band;
   const int y0 = band * kBH;
   const int cw = cell.w, ch = cell.h;
   if (y0 >= ch) {
@@ -336,13 +337,28 @@ __global__ void __launch_bounds__(kFastThreads)
     k_fast(const uint8_t *__restrict__ img, int pitch, const FastCell *__restrict__ cells, int max_bands, int threshold,
            unsigned *__restrict__ total, int *__restrict__ band_off, int *__restrict__ band_cnt,
            unsigned *__restrict__ kps, int kps_cap, int smem_w) {
-  fast_body(img, pitch, cells, max_bands, threshold, total, band_off, band_cnt, kps, kps_cap, smem_w);
+  fast_body(blockIdx.y, img, pitch, cells, max_bands, threshold, total, band_off, band_cnt, kps, kps_cap, smem_w);
 }
 // grid = (band, cell, job)
 __global__ void __launch_bounds__(kFastThreads, 4)
     k_fast_b(const SlotRec *__restrict__ slots, const FrontJob *__restrict__ jobs, FrontGeom g, int smem_w) {
   const SlotRec &sl = slots[jobs[blockIdx.z].slot];
-  fast_body(sl.lvl[0].p, sl.lvl[0].pitch, g.cells, g.max_bands, g.fast_threshold, sl.fast_total, sl.band_off, sl.band_cnt, sl.kps,
+  fast_body(blockIdx.y, sl.lvl[0].p, sl.lvl[0].pitch, g.cells, g.max_bands, g.fast_threshold, sl.fast_total, sl.band_off, sl.band_cnt,
+            sl.kps, g.kps_cap, smem_w);
+}
+// Stream group, FAST on demand: grid = (band, index into the stream's valid-cell list, job).  The reference runs cv::FAST on the
+// valid cells only (Grider_GRID.h:108-125); which cells are valid is known once k_group_detect has counted the tracked points
+// per cell, so the detector runs between the two halves of the detection, on the image the detection is about.
+__global__ void __launch_bounds__(kFastThreads, 4)
+    k_fast_g(const __grid_constant__ GroupDev gd, const TrackJob *__restrict__ jobs, FrontGeom g, int smem_w) {
+  const TrackJob &job = jobs[blockIdx.z];
+  const int s = job.stream;
+  const int *__restrict__ valid = gd.valid + (size_t)s * kValidStride;
+  if ((int)blockIdx.y >= valid[0]) return;
+  const int c = valid[4 + blockIdx.y];
+  if (c < 0) return;
+  const SlotRec &sl = gd.slots[gd.wmode[s] == 1 ? job.cur_slot : job.prev_slot];
+  fast_body(c, sl.lvl[0].p, sl.lvl[0].pitch, g.cells, g.max_bands, g.fast_threshold, sl.fast_total, sl.band_off, sl.band_cnt, sl.kps,
             g.kps_cap, smem_w);
 }
 
@@ -357,7 +373,7 @@ constexpr int kSelThreads = 128;
 constexpr int kSelSmemCap = 8192;
 constexpr int kSelMaxBands = 256;   // 4095 rows / kFastBandRows
 
-__device__ __forceinline__ void fast_select_body(const FastCell *__restrict__ cells, int max_bands,
+__device__ __forceinline__ void fast_select_body(const int c, const FastCell *__restrict__ cells, int max_bands,
                   unsigned *__restrict__ total /* [0] corners, [1] scratch cursor */,
                   const int *__restrict__ band_off, const int *__restrict__ band_cnt, const unsigned *__restrict__ kps,
                   int kps_cap, unsigned *__restrict__ scratch, int nfg, float2 *__restrict__ cand_sel,
@@ -365,7 +381,7 @@ __device__ __forceinline__ void fast_select_body(const FastCell *__restrict__ ce
   __shared__ unsigned sv[kSelSmemCap];
   __shared__ int pref[kSelMaxBands + 1];
   __shared__ int s_base;
-  const int c = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   const int tot = min((int)total[0], kps_cap);
   if (tid == 0) {
     int acc = 0;
@@ -402,13 +418,26 @@ __global__ void __launch_bounds__(kSelThreads)
                   const int *__restrict__ band_off, const int *__restrict__ band_cnt, const unsigned *__restrict__ kps,
                   int kps_cap, unsigned *__restrict__ scratch, int nfg, float2 *__restrict__ cand_sel,
                   int *__restrict__ cand_cnt) {
-  fast_select_body(cells, max_bands, total, band_off, band_cnt, kps, kps_cap, scratch, nfg, cand_sel, cand_cnt);
+  fast_select_body(blockIdx.x, cells, max_bands, total, band_off, band_cnt, kps, kps_cap, scratch, nfg, cand_sel, cand_cnt);
 }
 // grid = (cell, job)
 __global__ void __launch_bounds__(kSelThreads)
     k_fast_select_b(const SlotRec *__restrict__ slots, const FrontJob *__restrict__ jobs, FrontGeom g) {
   const SlotRec &sl = slots[jobs[blockIdx.y].slot];
-  fast_select_body(g.cells, g.max_bands, sl.fast_total, sl.band_off, sl.band_cnt, sl.kps, g.kps_cap, sl.sort_scratch, g.nfg, sl.cand,
+  fast_select_body(blockIdx.x, g.cells, g.max_bands, sl.fast_total, sl.band_off, sl.band_cnt, sl.kps, g.kps_cap, sl.sort_scratch, g.nfg,
+                   sl.cand, sl.cand_cnt);
+}
+// grid = (index into the stream's valid-cell list, job)
+__global__ void __launch_bounds__(kSelThreads)
+    k_fast_select_g(const __grid_constant__ GroupDev gd, const TrackJob *__restrict__ jobs, FrontGeom g) {
+  const TrackJob &job = jobs[blockIdx.y];
+  const int s = job.stream;
+  const int *__restrict__ valid = gd.valid + (size_t)s * kValidStride;
+  if ((int)blockIdx.x >= valid[0]) return;
+  const int c = valid[4 + blockIdx.x];
+  if (c < 0) return;
+  const SlotRec &sl = gd.slots[gd.wmode[s] == 1 ? job.cur_slot : job.prev_slot];
+  fast_select_body(c, g.cells, g.max_bands, sl.fast_total, sl.band_off, sl.band_cnt, sl.kps, g.kps_cap, sl.sort_scratch, g.nfg, sl.cand,
                    sl.cand_cnt);
 }
 
@@ -425,6 +454,21 @@ void launch_fast_select_batch(const SlotRec *slots, const FrontJob *jobs, int n_
   if (n_jobs <= 0 || g.n_cells <= 0 || g.max_bands > kSelMaxBands) return;
   PLVIWO_CARVEOUT(k_fast_select_b);
   k_fast_select_b<<<dim3(g.n_cells, n_jobs), kSelThreads, 0, s>>>(slots, jobs, g);
+}
+
+void launch_group_fast(const GroupDev &gd, const TrackJob *jobs, int n_jobs, const FrontGeom &g, cudaStream_t s) {
+  if (n_jobs <= 0 || g.n_cells <= 0) return;
+  const int smem_w = (g.max_cell_w + 15) & ~15;
+  const size_t smem = (size_t)(2 * kBH + 10) * smem_w + 3 * kFastPad + (size_t)(kBH + 2) * smem_w * 4;
+  static SmemOptIn optin;
+  optin.ensure(k_fast_g, smem);
+  PLVIWO_CARVEOUT(k_fast_g);
+  k_fast_g<<<dim3(g.max_bands, g.n_cells, n_jobs), kFastThreads, smem, s>>>(gd, jobs, g, smem_w);
+}
+void launch_group_fast_select(const GroupDev &gd, const TrackJob *jobs, int n_jobs, const FrontGeom &g, cudaStream_t s) {
+  if (n_jobs <= 0 || g.n_cells <= 0 || g.max_bands > kSelMaxBands) return;
+  PLVIWO_CARVEOUT(k_fast_select_g);
+  k_fast_select_g<<<dim3(g.n_cells, n_jobs), kSelThreads, 0, s>>>(gd, jobs, g);
 }
 
 void launch_fast_select(const FastCell *d_cells, int n_cells, int max_bands, unsigned *d_total, const int *d_band_off,

@@ -1,8 +1,9 @@
 // State-dependent steps of the front end on the device (sm_100a), one CTA per camera stream of a stream group:
 //
-//   k_group_detect   TrackKLT::perform_detection_monocular (TrackKLT.cpp:395-528) on the frame's candidate table — the
-//                    occupancy loop, the valid-cell list, the mask test of Grider_GRID.h:140-147, the minimum-distance
-//                    rejection and the id assignment
+//   k_group_detect   TrackKLT::perform_detection_monocular (TrackKLT.cpp:395-528) — the occupancy loop and the valid-cell
+//                    list; FAST + selection then run on the valid cells only (kernels_fast.cu: k_fast_g, k_fast_select_g);
+//   k_group_cands    the mask test of Grider_GRID.h:140-147 on the candidates; k_group_accept (after cornerSubPix) the
+//                    minimum-distance rejection and the id assignment
 //   k_group_gate     the tail of TrackKLT::perform_matching (:862-885: cv::findFundamentalMat(FM_RANSAC) on the undistorted
 //                    pairs, mask_klt && mask_rsc) and of feed_monocular (:143-189: reset, bounds / mask filter, the rows of
 //                    FeatureDatabase::update_feature, pts_last / ids_last)
@@ -62,8 +63,6 @@ __global__ void __launch_bounds__(kGT)
     k_group_detect(const __grid_constant__ GroupDev g, const TrackJob *__restrict__ jobs) {
   __shared__ BlockScan bs;
   __shared__ int grid_cnt[256];
-  __shared__ short valid_cell[256];
-  __shared__ int s_nvalid;
   const TrackJob &job = jobs[blockIdx.x];
   const int s = job.stream, tid = threadIdx.x;
   const int cols = g.W, rows = g.H, d = g.min_px_dist, gx = g.grid_x, gy = g.grid_y;
@@ -127,10 +126,11 @@ __global__ void __launch_bounds__(kGT)
   }
   __syncthreads();
 
-  int detection_ran = 0, n_ext = 0;
+  int detection_ran = 0;
   const double min_feat_percent = 0.50;
   const int need = g.num_features - nk;
   const int need_min = min(20, (int)(min_feat_percent * g.num_features));
+  int *__restrict__ valid = g.valid + (size_t)s * kValidStride;
   if (need >= need_min) {   // :468-471
     detection_ran = 1;
     // ---- valid cells in x-major order (:479-492)
@@ -146,55 +146,76 @@ __global__ void __launch_bounds__(kGT)
             const int sy = min((int)floor(y * ify), rows - 1), sx = min((int)floor(x * ifx), cols - 1);
             mg = mask[(size_t)sy * cols + sx];
           }
-          if (min(grid_cnt[y * gx + x], 255) < req && mg != 255) valid_cell[nv++] = (short)g.cell_of_loc[x * gy + y];
+          if (min(grid_cnt[y * gx + x], 255) < req && mg != 255) valid[4 + nv++] = g.cell_of_loc[x * gy + y];
         }
-      s_nvalid = nv;
+      valid[0] = nv;
+      atomicAdd(g.stats, (unsigned long long)nv);
     }
-    __syncthreads();
-    const int nv = s_nvalid, nfg = g.nfg;
-    // ---- Grider_GRID.h:133-149 on the candidate table: bounds and mask0_updated (caller mask, or inside the (2d+1)^2
-    // square of a kept point whose square lies inside the image, :457-461), in (cell, rank) order
-    float2 *__restrict__ ext = g.ext_in + (size_t)s * g.cand_cap;
-    int next = 0;
-    const int total_q = nv * nfg;
-    for (int base = 0; base < total_q; base += kGT) {
-      const int q = base + tid;
-      bool pass = false;
-      float2 pr = make_float2(0.f, 0.f);
-      if (q < total_q) {
-        const int v = q / nfg, k = q - v * nfg, c = valid_cell[v];
-        if (c >= 0 && k < min(sl.cand_cnt[c], nfg)) {
-          const int i = c * nfg + k;
-          const float2 p = sl.cand[i];
-          const int ix = (int)p.x, iy = (int)p.y;
-          if (!(ix < 0 || ix > cols || iy < 0 || iy > rows) && iy < rows && ix < cols) {
-            bool occ = mask != nullptr && mask[(size_t)iy * cols + ix] > 127;
-            for (int j = 0; j < nk && !occ; j++) {
-              const float2 w = wpts[j];
-              const int x = (int)w.x, y = (int)w.y;
-              occ = x - d >= 0 && x + d < cols && y - d >= 0 && y + d < rows && abs(ix - x) <= d && abs(iy - y) <= d;
-            }
-            if (!occ) {
-              pass = true;
-              pr = p;                // refined by k_group_subpix before the distance test (Grider_GRID.h:163-179)
-            }
-          }
-        }
-      }
-      const int e = block_excl(pass ? 1 : 0, bs);
-      if (pass) ext[next + e] = pr;
-      next += bs.total;
-    }
-    n_ext = next;
   }
   if (tid == 0) {
+    if (!detection_ran) valid[0] = 0;
+    // the FAST counters of the image the detection is about (k_fast_g / k_fast_select_g follow on this CUDA stream)
+    sl.fast_total[0] = 0;
+    sl.fast_total[1] = 0;
     g.wn[s] = nk;                       // points kept so far; k_group_accept appends the new ones
     g.wmode[s] = first ? 1 : 0;
     g.winfo[4 * s + 0] = detection_ran;
     g.winfo[4 * s + 1] = 0;
     g.winfo[4 * s + 2] = 0;
-    g.winfo[4 * s + 3] = n_ext;         // candidates waiting for cornerSubPix (k_group_subpix) and the distance test
+    g.winfo[4 * s + 3] = 0;             // candidates waiting for cornerSubPix: k_group_cands
   }
+}
+
+// Grider_GRID.h:133-149 on the candidate table of the valid cells (k_fast_g + k_fast_select_g have just filled it): bounds and
+// mask0_updated (caller mask, or inside the (2d+1)^2 square of a kept point whose square lies inside the image,
+// TrackKLT.cpp:457-461), in (cell, rank) order.
+__global__ void __launch_bounds__(kGT)
+    k_group_cands(const __grid_constant__ GroupDev g, const TrackJob *__restrict__ jobs) {
+  __shared__ BlockScan bs;
+  const TrackJob &job = jobs[blockIdx.x];
+  const int s = job.stream, tid = threadIdx.x;
+  if (g.winfo[4 * s + 0] == 0) return;   // no detection this frame
+  const int cols = g.W, rows = g.H, d = g.min_px_dist;
+  const bool first = g.wmode[s] == 1;
+  const int islot = first ? job.cur_slot : job.prev_slot;
+  const SlotRec &sl = g.slots[islot];
+  const uint8_t *__restrict__ mask = (g.slot_flags[islot] & 1) ? sl.mask : nullptr;
+  const float2 *__restrict__ wpts = g.wpts + (size_t)s * g.pts_cap;
+  const int *__restrict__ valid = g.valid + (size_t)s * kValidStride;
+  const int nk = g.wn[s];
+  const int nv = valid[0], nfg = g.nfg;
+  float2 *__restrict__ ext = g.ext_in + (size_t)s * g.cand_cap;
+  int next = 0;
+  const int total_q = nv * nfg;
+  for (int base = 0; base < total_q; base += kGT) {
+    const int q = base + tid;
+    bool pass = false;
+    float2 pr = make_float2(0.f, 0.f);
+    if (q < total_q) {
+      const int v = q / nfg, k = q - v * nfg, c = valid[4 + v];
+      if (c >= 0 && k < min(sl.cand_cnt[c], nfg)) {
+        const int i = c * nfg + k;
+        const float2 p = sl.cand[i];
+        const int ix = (int)p.x, iy = (int)p.y;
+        if (!(ix < 0 || ix > cols || iy < 0 || iy > rows) && iy < rows && ix < cols) {
+          bool occ = mask != nullptr && mask[(size_t)iy * cols + ix] > 127;
+          for (int j = 0; j < nk && !occ; j++) {
+            const float2 w = wpts[j];
+            const int x = (int)w.x, y = (int)w.y;
+            occ = x - d >= 0 && x + d < cols && y - d >= 0 && y + d < rows && abs(ix - x) <= d && abs(iy - y) <= d;
+          }
+          if (!occ) {
+            pass = true;
+            pr = p;                // refined by k_group_subpix before the distance test (Grider_GRID.h:163-179)
+          }
+        }
+      }
+    }
+    const int e = block_excl(pass ? 1 : 0, bs);
+    if (pass) ext[next + e] = pr;
+    next += bs.total;
+  }
+  if (tid == 0) g.winfo[4 * s + 3] = next;
 }
 
 // Second half of the top-off detection, after cornerSubPix of the surviving candidates (Grider_GRID.h:163-179).
@@ -259,6 +280,11 @@ void launch_group_detect(const GroupDev &g, const TrackJob *jobs, int n_jobs, cu
   if (n_jobs <= 0) return;
   PLVIWO_CARVEOUT(k_group_detect);
   k_group_detect<<<n_jobs, kGT, 0, s>>>(g, jobs);
+}
+void launch_group_cands(const GroupDev &g, const TrackJob *jobs, int n_jobs, cudaStream_t s) {
+  if (n_jobs <= 0) return;
+  PLVIWO_CARVEOUT(k_group_cands);
+  k_group_cands<<<n_jobs, kGT, 0, s>>>(g, jobs);
 }
 void launch_group_accept(const GroupDev &g, const TrackJob *jobs, int n_jobs, cudaStream_t s) {
   if (n_jobs <= 0) return;

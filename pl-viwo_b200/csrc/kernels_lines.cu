@@ -166,8 +166,8 @@ __device__ __forceinline__ bool edge_at(const unsigned *__restrict__ edges, int 
 //                  its tile-local root, the aggregates go to the root's slot of the cnt / bbox planes (other edge pixels of
 //                  the tile get cnt = 0);
 //   k_ccl_border   unions across tile borders on the global label array (only border pixels: ~8 % of the frame);
-//   k_ccl_flatten  every edge pixel looks up its global root; tile-local roots that are not global roots hand their
-//                  aggregates to the global root.
+//   k_ccl_link     tile-local roots that are not global roots point straight at their global root and hand it their
+//                  aggregates (a pixel reaches its global root in two loads: label[label[p]]).
 // Only edge pixels carry a label, a pixel count and a bounding box; everything asks the bit-packed edge map first.  The
 // planes are written for the ~5-10 % of the pixels that are edges, and the hot global atomics of a large component are one
 // per TILE it crosses instead of one per few pixels.
@@ -326,38 +326,17 @@ template <class B>
 __global__ void k_ccl_link(const __grid_constant__ B b, int w, int h) {
   const FldBuffers &fb = b.fld_of(blockIdx.y);
   int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt, *__restrict__ bbox = fb.bbox;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= min(*fb.lroot_n, fb.lroot_cap)) return;
-  const int i = fb.lroots[t];
-  const int root = ccl_find(label, i);
-  if (root == i) return;
+  const int nl = min(*fb.lroot_n, fb.lroot_cap);
   const int n = w * h;
-  atomicExch(label + i, root);   // other threads may be walking through this node: any ancestor is a valid parent
-  atomicAdd(cnt + root, cnt[i]);
-  atomicMax(bbox + root, bbox[i]);
-  atomicMin(bbox + n + root, bbox[n + i]);
-  atomicMax(bbox + 2 * n + root, bbox[2 * n + i]);
-}
-
-// One thread per 32-pixel word of the edge map: a pixel's label is its tile-local root's label (the global root).
-template <class B>
-__global__ void k_ccl_flatten(const __grid_constant__ B b, int w, int h) {
-  const FldBuffers &fb = b.fld_of(blockIdx.y);
-  const int words_per_row = fb.words_per_row;
-  int *__restrict__ label = fb.label;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= words_per_row * h) return;
-  unsigned e = fb.edges[t];
-  if (!e) return;
-  const int y = t / words_per_row, xb = (t - y * words_per_row) << 5;
-  while (e) {
-    const int k = __ffs((int)e) - 1;
-    e &= e - 1;
-    const int x = xb + k;
-    if (x >= w) break;
-    const int i = y * w + x;
-    const int l = label[i];
-    if (l != i) label[i] = __ldcg(label + l);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nl; t += gridDim.x * blockDim.x) {
+    const int i = fb.lroots[t];
+    const int root = ccl_find(label, i);
+    if (root == i) continue;
+    atomicExch(label + i, root);   // other threads may be walking through this node: any ancestor is a valid parent
+    atomicAdd(cnt + root, cnt[i]);
+    atomicMax(bbox + root, bbox[i]);
+    atomicMin(bbox + n + root, bbox[n + i]);
+    atomicMax(bbox + 2 * n + root, bbox[2 * n + i]);
   }
 }
 
@@ -383,24 +362,25 @@ __global__ void k_ccl_roots(const __grid_constant__ B b, int w, int h, int min_p
   const int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt, *__restrict__ bbox = fb.bbox;
   int *__restrict__ comp_root = fb.comp_root, *__restrict__ counters = fb.counters;
   const int max_comps = fb.max_chains;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= min(*fb.lroot_n, fb.lroot_cap)) return;
-  const int i = fb.lroots[t];
-  if (label[i] != i) return;   // a global root is the tile-local root of its own tile
-  const int c = cnt[i];
-  if (c < min_pixels) return;
+  const int nl = min(*fb.lroot_n, fb.lroot_cap);
   const int n = w * h;
-  const int bh = bbox[i] - i / w + 1;
-  const int groups = (bbox[2 * n + i] >> 5) - (bbox[n + i] >> 5) + 1;
-  const bool big = (bh + 2 * kPadRows) * (groups + 2) > kSliceWords;
-  if (big) {
-    const int q = atomicAdd(counters + 0, 1);
-    if (q < comp_cap_big(n)) comp_root[q] = i;
-  } else if (c >= kClassB) {
-    comp_root[comp_cap_big(n) + atomicAdd(counters + 5, 1)] = i;                 // at most n / kClassB
-  } else {
-    const int q = atomicAdd(counters + 6, 1);
-    if (q < max_comps) comp_root[comp_cap_big(n) + comp_cap_b(n) + q] = i;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nl; t += gridDim.x * blockDim.x) {
+    const int i = fb.lroots[t];
+    if (label[i] != i) continue;   // a global root is the tile-local root of its own tile
+    const int c = cnt[i];
+    if (c < min_pixels) continue;
+    const int bh = bbox[i] - i / w + 1;
+    const int groups = (bbox[2 * n + i] >> 5) - (bbox[n + i] >> 5) + 1;
+    const bool big = (bh + 2 * kPadRows) * (groups + 2) > kSliceWords;
+    if (big) {
+      const int q = atomicAdd(counters + 0, 1);
+      if (q < comp_cap_big(n)) comp_root[q] = i;
+    } else if (c >= kClassB) {
+      comp_root[comp_cap_big(n) + atomicAdd(counters + 5, 1)] = i;                 // at most n / kClassB
+    } else {
+      const int q = atomicAdd(counters + 6, 1);
+      if (q < max_comps) comp_root[comp_cap_big(n) + comp_cap_b(n) + q] = i;
+    }
   }
 }
 
@@ -539,8 +519,16 @@ __device__ __forceinline__ void walk_gather(const WalkCtx &c, unsigned *bm, int 
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int it = it0 + u;
-      unsigned bits = (lab[u].x == root ? 1u : 0u) | (lab[u].y == root ? 2u : 0u) | (lab[u].z == root ? 4u : 0u) |
-                      (lab[u].w == root ? 8u : 0u);
+      // a pixel's label is its tile-local root (k_ccl_tile); the label of a tile-local root is the global root (k_ccl_link)
+      const int l4[4] = {lab[u].x, lab[u].y, lab[u].z, lab[u].w};
+      unsigned bits = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (!((nib[u] >> k) & 1u)) continue;
+        int l = l4[k];
+        if (l != root) l = __ldg(c.label + l);
+        bits |= (l == root ? 1u : 0u) << k;
+      }
       bits = (bits & nib[u]) << (4 * (lane & 7));
       const unsigned word = __reduce_or_sync(gmask, bits);
       if ((lane & 7) == 0 && word && it < items) {
@@ -967,13 +955,14 @@ static void launch_fld_any(const B &b, int nb_frames, int w, int h, int max_chai
     PLVIWO_CARVEOUT(k_ccl_border<B>);
     k_ccl_border<B><<<dim3((nborder + tpb - 1) / tpb, nb_frames), tpb, 0, s>>>(b, w, h);
   }
-  const int nwords = ((w + 31) / 32) * h;
+  // tile-local roots are a few thousand per frame (capacity n / 4): a fixed small grid strides over the list.  There is no
+  // flatten pass: a pixel's label is its tile-local root and that root's label is the global root, which is all the walk's
+  // gather needs (two loads for the pixels of the components that are walked instead of a pass over every edge pixel)
+  const int root_ctas = std::max(1, std::min((lroot_cap + tpb - 1) / tpb, 12));
   PLVIWO_CARVEOUT(k_ccl_link<B>);
-  k_ccl_link<B><<<dim3((lroot_cap + tpb - 1) / tpb, nb_frames), tpb, 0, s>>>(b, w, h);
-  PLVIWO_CARVEOUT(k_ccl_flatten<B>);
-  k_ccl_flatten<B><<<dim3((nwords + tpb - 1) / tpb, nb_frames), tpb, 0, s>>>(b, w, h);
+  k_ccl_link<B><<<dim3(root_ctas, nb_frames), tpb, 0, s>>>(b, w, h);
   PLVIWO_CARVEOUT(k_ccl_roots<B>);
-  k_ccl_roots<B><<<dim3((lroot_cap + tpb - 1) / tpb, nb_frames), tpb, 0, s>>>(b, w, h, length_threshold + 1);
+  k_ccl_roots<B><<<dim3(root_ctas, nb_frames), tpb, 0, s>>>(b, w, h, length_threshold + 1);
   if (ev) cudaEventRecord(ev[0], s);
   init_fld_constants();
   const int ws = ((w + 31) >> 5) + 2;

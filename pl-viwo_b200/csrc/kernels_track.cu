@@ -778,12 +778,18 @@ __global__ void __launch_bounds__(kLk15MaxLevels * 32)
 // so the split of the window over lanes cannot change a bit: results are identical to k_lk15's (tests/test_group_gpu.py
 // compares a group, which runs this kernel, with single handles, which run k_lk15).  An SM holds 32+ features.
 constexpr int kLkwWarps = 4;
+// Staged rows of the previous image (18 x 18 pixels) and of the region of the next image (25 x 25) are kept with a row
+// stride that is a multiple of 4 bytes and their first word aligned like the image's: a neighbourhood that lies inside the
+// image is staged with 32-bit loads (4 + 6 per lane instead of 11 + 20 single bytes with reflected indices); the bytes
+// that end up in shared memory are the same either way.
+constexpr int kRawStride = 24;   // >= 18 + 3
+constexpr int kJStride = 28;     // >= 25 + 3
 struct LkwSmem {
-  uint8_t raw[(kW15 + 3) * (kW15 + 3) + 12];
-  short ddx[(kW15 + 1) * (kW15 + 1)];
-  short ddy[(kW15 + 1) * (kW15 + 1)];
+  __align__(16) uint8_t raw[(kW15 + 3) * kRawStride + 8];
+  __align__(16) short ddx[(kW15 + 1) * (kW15 + 1)];
+  __align__(16) short ddy[(kW15 + 1) * (kW15 + 1)];
   __align__(16) short patch[3][kW15][16];   // [I, Ix, Iy][window row][window column (15 used, column 15 = 0)]
-  uint8_t jreg[kJR * kJR + 7];
+  __align__(16) uint8_t jreg[kJR * kJStride + 4];
 };
 
 template <class Args>
@@ -823,24 +829,52 @@ __device__ __forceinline__ void lk15w_body(const Args &a, const float2 *__restri
     float A11 = 0, A12 = 0, A22 = 0;
     __syncwarp();   // the previous level's patches have been read by every lane
     {
-      uint8_t *raw = sm.raw;
+      const uint8_t *raw = sm.raw;
       short *ddx = sm.ddx, *ddy = sm.ddy;
+      bool interior = false;
+      int roff_b = 0;
       {
         const uint8_t *I = a.p0[level];
         const int pitchI = a.pitch0[level];
-        uint8_t v[kRawLoads];
+        const int rx0 = ipx - 1, ry0 = ipy - 1;
+        if (rx0 >= 0 && ry0 >= 0 && rx0 + np <= cols && ry0 + np <= rows && ((((size_t)I) | (size_t)pitchI) & 3) == 0) {
+          // inside the image: 18 rows x 6 aligned words (the staged row starts at the word that holds column rx0)
+          const int roff = rx0 & 3;
+          const uint8_t *base = I + (size_t)ry0 * pitchI + (rx0 - roff);
+          constexpr int kWords = np * (kRawStride / 4);   // 108
+          unsigned v[(kWords + 31) / 32];
 #pragma unroll
-        for (int j = 0; j < kRawLoads; j++) {
-          const int i = lane + 32 * j;
-          v[j] = 0;
-          if (i < np * np) {
-            const int r = i / np, c = i - r * np;
-            v[j] = I[(size_t)reflect101(ipy - 1 + r, rows) * pitchI + reflect101(ipx - 1 + c, cols)];
+          for (int j = 0; j < (kWords + 31) / 32; j++) {
+            const int i = lane + 32 * j;
+            v[j] = 0;
+            if (i < kWords) {
+              const int r = i / (kRawStride / 4), c = i - r * (kRawStride / 4);
+              v[j] = __ldg(reinterpret_cast<const unsigned *>(base + (size_t)r * pitchI) + c);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < (kWords + 31) / 32; j++)
+            if (lane + 32 * j < kWords) reinterpret_cast<unsigned *>(sm.raw)[lane + 32 * j] = v[j];
+          raw = sm.raw + roff;
+          interior = true;
+          roff_b = 8 * roff;
+        } else {
+          uint8_t v[kRawLoads];
+#pragma unroll
+          for (int j = 0; j < kRawLoads; j++) {
+            const int i = lane + 32 * j;
+            v[j] = 0;
+            if (i < np * np) {
+              const int r = i / np, c = i - r * np;
+              v[j] = I[(size_t)reflect101(ry0 + r, rows) * pitchI + reflect101(rx0 + c, cols)];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < kRawLoads; j++) {
+            const int i = lane + 32 * j;
+            if (i < np * np) sm.raw[(i / np) * kRawStride + (i % np)] = v[j];
           }
         }
-#pragma unroll
-        for (int j = 0; j < kRawLoads; j++)
-          if (lane + 32 * j < np * np) raw[lane + 32 * j] = v[j];
       }
       const float fa = px - ipx, fb = py - ipy;
       const int iw00 = __float2int_rn((1.f - fa) * (1.f - fb) * 16384.f);
@@ -848,15 +882,46 @@ __device__ __forceinline__ void lk15w_body(const Args &a, const float2 *__restri
       const int iw10 = __float2int_rn((1.f - fa) * fb * 16384.f);
       const int iw11 = 16384 - iw00 - iw01 - iw10;
       __syncwarp();
+      if (interior) {
+        // Scharr derivatives of the 16 x 16 positions, all inside the image: this lane's row r and 8 adjacent columns from
+        // three staged rows of 10 pixels, each taken as four aligned words and shifted into place
+        const int r = lane >> 1, cb = (lane & 1) * 8;
+        unsigned X[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const uint4 wv = *reinterpret_cast<const uint4 *>(sm.raw + (r + k) * kRawStride + cb);
+          X[k][0] = __funnelshift_r(wv.x, wv.y, roff_b);
+          X[k][1] = __funnelshift_r(wv.y, wv.z, roff_b);
+          X[k][2] = __funnelshift_r(wv.z, wv.w, roff_b);
+        }
+        int S[10], Dv[10];   // column smoothing 3 t + 10 m + 3 b and column difference b - t
+#pragma unroll
+        for (int c = 0; c < 10; c++) {
+          const int t = (X[0][c >> 2] >> (8 * (c & 3))) & 0xff, m = (X[1][c >> 2] >> (8 * (c & 3))) & 0xff,
+                    bb = (X[2][c >> 2] >> (8 * (c & 3))) & 0xff;
+          S[c] = 3 * (t + bb) + 10 * m;
+          Dv[c] = bb - t;
+        }
+        unsigned px[4], py[4];
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+          const int vx0 = S[c + 2] - S[c], vx1 = S[c + 3] - S[c + 1];
+          const int vy0 = 3 * (Dv[c] + Dv[c + 2]) + 10 * Dv[c + 1], vy1 = 3 * (Dv[c + 1] + Dv[c + 3]) + 10 * Dv[c + 2];
+          px[c >> 1] = ((unsigned)vx0 & 0xffffu) | ((unsigned)vx1 << 16);
+          py[c >> 1] = ((unsigned)vy0 & 0xffffu) | ((unsigned)vy1 << 16);
+        }
+        *reinterpret_cast<uint4 *>(&ddx[r * nd + cb]) = make_uint4(px[0], px[1], px[2], px[3]);
+        *reinterpret_cast<uint4 *>(&ddy[r * nd + cb]) = make_uint4(py[0], py[1], py[2], py[3]);
+      } else
       for (int i = lane; i < nd * nd; i += 32) {
         int r = i / nd, c = i - r * nd;
         int gx = ipx + c, gy = ipy + r;
         int vx = 0, vy = 0;
         if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
-          const uint8_t *q = raw + (r + 1) * np + (c + 1);
-          int tl = q[-np - 1], tc = q[-np], tr = q[-np + 1];
+          const uint8_t *q = raw + (r + 1) * kRawStride + (c + 1);
+          int tl = q[-kRawStride - 1], tc = q[-kRawStride], tr = q[-kRawStride + 1];
           int ml = q[-1], mr = q[1];
-          int bl = q[np - 1], bc = q[np], br = q[np + 1];
+          int bl = q[kRawStride - 1], bc = q[kRawStride], br = q[kRawStride + 1];
           vx = 3 * (tr + br) + 10 * mr - 3 * (tl + bl) - 10 * ml;
           vy = 3 * (bl + br) + 10 * bc - 3 * (tl + tr) - 10 * tc;
         }
@@ -869,8 +934,8 @@ __device__ __forceinline__ void lk15w_body(const Args &a, const float2 *__restri
         const int y = r0 + (k >> 2), x = c0 + (k & 3);
         int ival = 0, ixval = 0, iyval = 0;
         if (y < win && x < win) {
-          const uint8_t *q = raw + (y + 1) * np + (x + 1);
-          ival = (q[0] * iw00 + q[1] * iw01 + q[np] * iw10 + q[np + 1] * iw11 + (1 << 8)) >> 9;
+          const uint8_t *q = raw + (y + 1) * kRawStride + (x + 1);
+          ival = (q[0] * iw00 + q[1] * iw01 + q[kRawStride] * iw10 + q[kRawStride + 1] * iw11 + (1 << 8)) >> 9;
           const int di = y * nd + x;
           ixval = (ddx[di] * iw00 + ddx[di + 1] * iw01 + ddx[di + nd] * iw10 + ddx[di + nd + 1] * iw11 + (1 << 13)) >> 14;
           iyval = (ddy[di] * iw00 + ddy[di + 1] * iw01 + ddy[di + nd] * iw10 + ddy[di + nd + 1] * iw11 + (1 << 13)) >> 14;
@@ -927,6 +992,7 @@ __device__ __forceinline__ void lk15w_body(const Args &a, const float2 *__restri
     for (int k = 0; k < 9; k++) jt[k] = jb[k] = 0;
     int cached_x = INT_MIN, cached_y = INT_MIN;
     int reg_x0 = INT_MIN / 2, reg_y0 = INT_MIN / 2;   // origin of the staged region (none yet)
+    int joff = 0;                                     // byte offset of the region's first column inside its staged rows
     for (int j = 0; j < a.max_count; j++) {
       const int inx = __float2int_rd(next.x), iny = __float2int_rd(next.y);
       if (inx < -win || inx >= cols || iny < -win || iny >= rows) {
@@ -946,29 +1012,52 @@ __device__ __forceinline__ void lk15w_body(const Args &a, const float2 *__restri
           reg_x0 = inx - kJMargin;
           reg_y0 = iny - kJMargin;
           __syncwarp();   // every lane is done reading the old region
-          constexpr int kJLoads = (kJR * kJR + 31) / 32;   // 20, in two rounds of 10 loads in flight
-#pragma unroll 1
-          for (int q0 = 0; q0 < kJLoads; q0 += kJLoads / 2) {
-            uint8_t t[kJLoads / 2];
+          if (reg_x0 >= 0 && reg_y0 >= 0 && reg_x0 + kJR <= cols && reg_y0 + kJR <= rows && ((((size_t)J) | (size_t)pitchJ) & 3) == 0) {
+            // inside the image: 25 rows x 7 aligned words
+            joff = reg_x0 & 3;
+            const uint8_t *base = J + (size_t)reg_y0 * pitchJ + (reg_x0 - joff);
+            constexpr int kWords = kJR * (kJStride / 4);   // 175
+            unsigned t[(kWords + 31) / 32];
 #pragma unroll
-            for (int q = 0; q < kJLoads / 2; q++) {
-              const int i = lane + 32 * (q0 + q);
-              const int ry = i / kJR, rx = i - ry * kJR;
+            for (int q = 0; q < (kWords + 31) / 32; q++) {
+              const int i = lane + 32 * q;
               t[q] = 0;
-              if (i < kJR * kJR) t[q] = J[(size_t)reflect101(reg_y0 + ry, rows) * pitchJ + reflect101(reg_x0 + rx, cols)];
+              if (i < kWords) {
+                const int ry = i / (kJStride / 4), cw = i - ry * (kJStride / 4);
+                t[q] = __ldg(reinterpret_cast<const unsigned *>(base + (size_t)ry * pitchJ) + cw);
+              }
             }
 #pragma unroll
-            for (int q = 0; q < kJLoads / 2; q++)
-              if (lane + 32 * (q0 + q) < kJR * kJR) sm.jreg[lane + 32 * (q0 + q)] = t[q];
+            for (int q = 0; q < (kWords + 31) / 32; q++)
+              if (lane + 32 * q < kWords) reinterpret_cast<unsigned *>(sm.jreg)[lane + 32 * q] = t[q];
+          } else {
+            joff = 0;
+            constexpr int kJLoads = (kJR * kJR + 31) / 32;   // 20, in two rounds of 10 loads in flight
+#pragma unroll 1
+            for (int q0 = 0; q0 < kJLoads; q0 += kJLoads / 2) {
+              uint8_t t[kJLoads / 2];
+#pragma unroll
+              for (int q = 0; q < kJLoads / 2; q++) {
+                const int i = lane + 32 * (q0 + q);
+                const int ry = i / kJR, rx = i - ry * kJR;
+                t[q] = 0;
+                if (i < kJR * kJR) t[q] = J[(size_t)reflect101(reg_y0 + ry, rows) * pitchJ + reflect101(reg_x0 + rx, cols)];
+              }
+#pragma unroll
+              for (int q = 0; q < kJLoads / 2; q++) {
+                const int i = lane + 32 * (q0 + q);
+                if (i < kJR * kJR) sm.jreg[(i / kJR) * kJStride + (i % kJR)] = t[q];
+              }
+            }
           }
           __syncwarp();
         }
         if (own) {
-          const uint8_t *Jp = sm.jreg + (iny - reg_y0 + wy) * kJR + (inx - reg_x0 + wx);
+          const uint8_t *Jp = sm.jreg + (iny - reg_y0 + wy) * kJStride + (inx - reg_x0 + joff + wx);
 #pragma unroll
           for (int k = 0; k < 9; k++) {
             jt[k] = Jp[k];
-            jb[k] = Jp[kJR + k];
+            jb[k] = Jp[kJStride + k];
           }
         }
       }

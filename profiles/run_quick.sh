@@ -1,0 +1,11 @@
+# quick check of a change on one B200 (under gpurun): group + kernel tests, then short bench runs (no CPU baseline, no extras)
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_group_gpu.py tests/test_kernels_gpu.py -x -q -m gpu > gpurun_out/q_pytest.txt 2>&1; tail -3 gpurun_out/q_pytest.txt
+run() { tag=$1; shift; env "$@" timeout 300 python bench.py --steps 8 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/q_$tag.json 2> gpurun_out/q_$tag.err; python -c "
+import json
+try:
+    d=json.loads(open('gpurun_out/q_$tag.json').read()); print('$tag', round(d['value']), round(d['e2e']['value']), {k: round(v['avg_ms']*1000) for k,v in d['roofline'].get('per_kernel',{}).items()}, d['roofline'].get('fast_cells_per_frame'))
+except Exception as e: print('$tag', 'ERR', e)"; }
+run s64 PLVIWO_BENCH_STREAMS=64
+run s64_l8 PLVIWO_BENCH_STREAMS=64 PLVIWO_GROUP_LANES=8
+run s8 PLVIWO_BENCH_STREAMS=8

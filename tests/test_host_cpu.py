@@ -266,7 +266,7 @@ def test_ctypes_structs_match_the_c_header(fe, tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     structs = {"FeConfig": fe.FeConfig, "FePointRow": fe.FePointRow, "FeLineRow": fe.FeLineRow, "FeLinePoint": fe.FeLinePoint,
                "FeFrameInfo": fe.FeFrameInfo, "FeStageTimes": fe.FeStageTimes, "FePlayStats": fe.FePlayStats,
-               "FeStereoInfo": fe.FeStereoInfo}
+               "FeStereoInfo": fe.FeStereoInfo, "FeGroupTimes": fe.FeGroupTimes}
     lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "plviwo_fe.h"', "int main(void) {"]
     for name, cls in structs.items():
         lines.append('  printf("%s size %%zu\\n", sizeof(%s));' % (name, name))
