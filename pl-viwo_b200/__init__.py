@@ -698,7 +698,9 @@ class GroupEngine:
         # ~2 ms: six ticks in flight keep the device busy while walks finish (measured: 3 -> 6 ticks +5 %, 10 no more)
         # (profiles/sweep_group.sh, one B200: 64 streams 3 ticks 31.7 k frames/s, 6: 33.6 k, 12: 38.3 k, 16: 38.6 k; 8 streams
         # 12: 15.1 k, 24: 20.2 k, 48: 20.1 k)
-        la = int(os.environ.get("PLVIWO_BENCH_GROUP_LA", "0")) or lookahead or (12 if len(metas) >= 16 else 24)
+        # after FAST moved on demand and the line association came off the point chain (round 2, second half): 64 streams, 12 / 24 /
+        # 36 ticks in flight: 47.8 k / 49.3 k / 49.7 k frames/s
+        la = int(os.environ.get("PLVIWO_BENCH_GROUP_LA", "0")) or lookahead or 24
         self.lookahead = la
         self.metas = metas
         self.g = GroupFrontEnd(default_config(lookahead=la, **workload), len(metas), device=dev, calibs=[(K, D) for K, D, _ in metas])
@@ -713,7 +715,9 @@ class GroupEngine:
                 p = ptrs[k][t]
                 tab[i * S + k] = int(p) if on_device else p.ctypes.data
         ts = [1.0 + 0.1 * (first + i) for i in range(n_frames)]
-        st = self.g.play(ts, tab, pitch, on_device, vanishing_points=[m[2] for m in self.metas])
+        # PLVIWO_BENCH_NO_LINES=1 (experiments only): the line tracker is not fed, the point path runs alone
+        vps = None if os.environ.get("PLVIWO_BENCH_NO_LINES") else [m[2] for m in self.metas]
+        st = self.g.play(ts, tab, pitch, on_device, vanishing_points=vps)
         return int(sum(x.frames for x in st))
 
     def counters(self, reset=False):

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -187,9 +188,11 @@ int FeGroup::init() {
 
   // ---- tracker state and work arrays
   const size_t P = (size_t)S_ * g_.pts_cap;
-  FG_CUDA(dev_alloc(dev_allocs_, &g_.pts, P));
-  FG_CUDA(dev_alloc(dev_allocs_, &g_.ids, P));
-  FG_CUDA(dev_alloc(dev_allocs_, &g_.n_pts, S_));
+  FG_CUDA(dev_alloc(dev_allocs_, &g_.pts, P * RB_));   // ring of state records, one per output record (fe_group_dev.h)
+  FG_CUDA(dev_alloc(dev_allocs_, &g_.ids, P * RB_));
+  FG_CUDA(dev_alloc(dev_allocs_, &g_.n_pts, (size_t)S_ * RB_));
+  prev_rec_.resize(S_);
+  for (int s = 0; s < S_; s++) prev_rec_[s] = s;       // record (ring 0, stream s): zero points
   FG_CUDA(dev_alloc(dev_allocs_, &g_.currid, S_));
   FG_CUDA(dev_alloc(dev_allocs_, &g_.wpts, P));
   FG_CUDA(dev_alloc(dev_allocs_, &g_.wids, P));
@@ -279,6 +282,18 @@ int FeGroup::init() {
   for (auto &e : ev_gate_) FG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   ev_copy_.resize((size_t)RB_ * s_copy_.size());
   ev_front_.resize(RB_);
+  trace_ = std::getenv("PLVIWO_GROUP_TRACE") != nullptr;
+  if (trace_) {
+    ev_tr0_.resize(RB_);
+    ev_tr1_.resize(RB_);
+    tr_valid_.assign(RB_, 0);
+    for (auto &e : ev_tr0_) FG_CUDA(cudaEventCreate(&e));
+    for (auto &e : ev_tr1_) FG_CUDA(cudaEventCreate(&e));
+    ev_trs_.resize((size_t)RB_ * 4);
+    for (auto &e : ev_trs_) FG_CUDA(cudaEventCreate(&e));
+  }
+  ev_pyr_.resize(RB_);
+  for (auto &e : ev_pyr_) FG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto &e : ev_copy_) FG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto &e : ev_front_) FG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   ev_done_.resize((size_t)RB_ * lanes_);
@@ -290,6 +305,16 @@ int FeGroup::init() {
 FeGroup::~FeGroup() {
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
+  if (trace_ && tr_n_ > 0)
+    std::fprintf(stderr, "[plviwo group trace] %ld front batches (%d ticks each): device latency %.3f ms, interval between batches %.3f ms\n",
+                 tr_n_, B_, tr_lat_ms_ / tr_n_, tr_np_ ? tr_period_ms_ / tr_np_ : 0.0);
+  if (trace_ && tr_n_ > 0)
+    std::fprintf(stderr, "[plviwo group trace] stages of a front batch, ms: equalise + pyramid %.3f, Canny + tiles %.3f, components %.3f, walk %.3f, "
+                 "segments %.3f\n", tr_stage_ms_[0] / tr_n_, tr_stage_ms_[1] / tr_n_, tr_stage_ms_[2] / tr_n_, tr_stage_ms_[3] / tr_n_,
+                 tr_stage_ms_[4] / tr_n_);
+  for (auto e : ev_tr0_) cudaEventDestroy(e);
+  for (auto e : ev_tr1_) cudaEventDestroy(e);
+  for (auto e : ev_trs_) cudaEventDestroy(e);
   for (SlotRec &sl : slots_)
     if (cfg_.use_lines) sl.fld.release();
   for (void *p : dev_allocs_) cudaFree(p);
@@ -303,6 +328,7 @@ FeGroup::~FeGroup() {
   for (auto e : ev_gate_) cudaEventDestroy(e);
   for (auto e : ev_copy_) cudaEventDestroy(e);
   for (auto e : ev_front_) cudaEventDestroy(e);
+  for (auto e : ev_pyr_) cudaEventDestroy(e);
   for (auto e : ev_done_) cudaEventDestroy(e);
   for (auto e : ev_pool_) cudaEventDestroy(e);
 }
@@ -447,6 +473,8 @@ int FeGroup::submit(const double *timestamps, const uint8_t *const *images, int 
     j.prev_slot = prev_slot_[s];
     j.flags = lines ? 1 : 0;
     j.out = ring * S_ + s;
+    j.prev_rec = prev_rec_[s];
+    prev_rec_[s] = j.out;
     j.timestamp = timestamps[s];
     for (int i = 0; i < 4; i++) {
       j.K[i] = K_[4 * s + i];
@@ -500,6 +528,21 @@ int FeGroup::launch_front(FrontBatch &b, int buf) {
   }
   FG_CUDA(cudaMemcpyAsync(dj, hj, nj * sizeof(FrontJob), cudaMemcpyHostToDevice, st));
   if (nl) FG_CUDA(cudaMemcpyAsync(dl, hl, nl * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (trace_) {
+    if (tr_valid_[buf]) {   // the buffer's previous batch has been collected: read its events before they are re-recorded
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ev_tr0_[buf], ev_tr1_[buf]) == cudaSuccess) { tr_lat_ms_ += ms; tr_n_++; }
+      cudaEvent_t *es = &ev_trs_[(size_t)buf * 4];
+      cudaEvent_t seq[6] = {ev_tr0_[buf], es[0], es[1], es[2], es[3], ev_tr1_[buf]};
+      for (int k = 0; k < 5; k++)
+        if (cudaEventElapsedTime(&ms, seq[k], seq[k + 1]) == cudaSuccess) tr_stage_ms_[k] += ms;
+      const int nxt = (buf + 1) % RB_;
+      if (tr_valid_[nxt] && cudaEventElapsedTime(&ms, ev_tr0_[buf], ev_tr0_[nxt]) == cudaSuccess && ms > 0) { tr_period_ms_ += ms; tr_np_++; }
+      cudaGetLastError();
+    }
+    tr_valid_[buf] = 1;
+    cudaEventRecord(ev_tr0_[buf], st);
+  }
   const bool tm = timing_;
   cudaEvent_t e0 = nullptr;
   auto mark = [&]() -> cudaEvent_t {
@@ -532,20 +575,27 @@ int FeGroup::launch_front(FrontBatch &b, int buf) {
     launches_++;
   }
   step(FE_GK_PYR_REST, nj);
+  // the point chains of the batch's ticks need nothing else (launch_track); only the line association waits for the rest
+  FG_CUDA(cudaEventRecord(ev_pyr_[buf], st));
+  if (trace_) for (int k = 0; k < 4; k++) cudaEventRecord(ev_trs_[(size_t)buf * 4 + k], st);   // (re-recorded below where the stage exists)
   // FAST is NOT here: the reference runs it on the cells the detection finds short of features only (Grider_GRID.h:108-125,
   // 1-3 of 25 cells on a tracked sequence), so it runs inside the detection of the tick (launch_track)
   if (nl > 0) {
-    launch_canny_table(d_slots_, dl, nl, W_ / 2, H_ / 2, cfg_.canny_th1, st);
-    launches_++;
+    launch_canny_table(d_slots_, dl, nl, W_ / 2, H_ / 2, cfg_.canny_th1, st);   // + tile-local component labels (fused)
+    launches_ += 2;
     step(FE_GK_CANNY, nl);
     cudaEvent_t ev2[2] = {nullptr, nullptr};
     if (tm) {
       ev2[0] = timing_event();
       ev2[1] = timing_event();
+    } else if (trace_) {
+      cudaEventRecord(ev_trs_[(size_t)buf * 4 + 1], st);
+      ev2[0] = ev_trs_[(size_t)buf * 4 + 2];
+      ev2[1] = ev_trs_[(size_t)buf * 4 + 3];
     }
     launch_fld_table(d_slots_, dl, nl, W_ / 2, H_ / 2, s0.fld.max_chains, cfg_.fld_length_threshold, cfg_.fld_distance_threshold, st,
-                     tm ? ev2 : nullptr);
-    launches_ += 9;
+                     (tm || trace_) ? ev2 : nullptr);
+    launches_ += 7;
     if (tm) {
       cudaEvent_t e1 = mark();
       account(FE_GK_CCL, e0, ev2[0], nl);
@@ -556,6 +606,7 @@ int FeGroup::launch_front(FrontBatch &b, int buf) {
   }
   FG_CUDA(cudaGetLastError());
   FG_CUDA(cudaEventRecord(ev_front_[buf], st));
+  if (trace_) cudaEventRecord(ev_tr1_[buf], st);
   return FE_OK;
 }
 
@@ -586,7 +637,7 @@ int FeGroup::launch_track(int tick) {
     cudaStream_t st = timing_ ? s_front_[0] : s_track_[l];
     const int n = j1 - j0;
     if (n > 0) {
-      FG_CUDA(cudaStreamWaitEvent(st, ev_front_[tr.batch], 0));
+      FG_CUDA(cudaStreamWaitEvent(st, ev_pyr_[tr.batch], 0));
       FG_CUDA(cudaMemcpyAsync(dj + j0, hj + j0, (size_t)n * sizeof(TrackJob), cudaMemcpyHostToDevice, st));
       cudaEvent_t e0 = nullptr;
       auto step = [&](int k) {
@@ -618,8 +669,7 @@ int FeGroup::launch_track(int tick) {
       launches_ += 3;
       launch_group_lk(g_, dj + j0, n, prm, st);
       step(FE_GK_LK);
-      // the gate rewrites pts_last / ids_last, which the previous tick's line association (side stream) still reads
-      if (tick > 0 && cfg_.use_lines && !tm) FG_CUDA(cudaStreamWaitEvent(st, ev_done_[(size_t)((tick - 1) % RB_) * lanes_ + l], 0));
+      // (the gate writes this tick's state record; the previous tick's line association reads ITS record: no ordering needed)
       launch_group_gate(g_, dj + j0, n, st);
       step(FE_GK_GATE);
       launches_ += 3;
@@ -629,6 +679,7 @@ int FeGroup::launch_track(int tick) {
           sl = s_lines_[l];
           FG_CUDA(cudaEventRecord(ev_gate_[(size_t)ring * lanes_ + l], st));
           FG_CUDA(cudaStreamWaitEvent(sl, ev_gate_[(size_t)ring * lanes_ + l], 0));
+          FG_CUDA(cudaStreamWaitEvent(sl, ev_front_[tr.batch], 0));   // the frame's segments (chain walk + fit of the batch)
         }
         launch_group_lines(g_, dj + j0, n, sl);
         launches_++;
@@ -766,7 +817,8 @@ int FeGroup::get_state(int s, void *buf, size_t cap, size_t *n_bytes) {
   hd.w = W_;
   hd.h = H_;
   int n_pts = 0, lb = 0, n_lines = 0;
-  FG_CUDA(cudaMemcpy(&n_pts, g_.n_pts + s, sizeof(int), cudaMemcpyDeviceToHost));
+  const size_t rec = (size_t)prev_rec_[s];   // the stream's current state record
+  FG_CUDA(cudaMemcpy(&n_pts, g_.n_pts + rec, sizeof(int), cudaMemcpyDeviceToHost));
   FG_CUDA(cudaMemcpy(&hd.currid, g_.currid + s, sizeof(uint64_t), cudaMemcpyDeviceToHost));
   hd.line_currid = 1;
   std::vector<float4> lines;
@@ -808,9 +860,9 @@ int FeGroup::get_state(int s, void *buf, size_t cap, size_t *n_bytes) {
   uint8_t *p = static_cast<uint8_t *>(buf);
   auto put = [&](const void *src, size_t n) { std::memcpy(p, src, n); p += n; };
   put(&hd, sizeof(hd));
-  FG_CUDA(cudaMemcpy(p, g_.pts + (size_t)s * g_.pts_cap, n_pts * sizeof(float2), cudaMemcpyDeviceToHost));
+  FG_CUDA(cudaMemcpy(p, g_.pts + rec * g_.pts_cap, n_pts * sizeof(float2), cudaMemcpyDeviceToHost));
   p += n_pts * sizeof(float2);
-  FG_CUDA(cudaMemcpy(p, g_.ids + (size_t)s * g_.pts_cap, n_pts * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  FG_CUDA(cudaMemcpy(p, g_.ids + rec * g_.pts_cap, n_pts * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   p += n_pts * sizeof(uint64_t);
   put(lines.data(), lines.size() * sizeof(float4));
   put(lids.data(), lids.size() * sizeof(uint64_t));
@@ -896,9 +948,10 @@ int FeGroup::set_state(int s, const void *buf, size_t n_bytes) {
   // ---- apply
   FG_CUDA(cudaDeviceSynchronize());
   const int n = hd.n_pts;
-  FG_CUDA(cudaMemcpy(g_.pts + (size_t)s * g_.pts_cap, p_pts, n * sizeof(float2), cudaMemcpyHostToDevice));
-  FG_CUDA(cudaMemcpy(g_.ids + (size_t)s * g_.pts_cap, p_ids, n * sizeof(uint64_t), cudaMemcpyHostToDevice));
-  FG_CUDA(cudaMemcpy(g_.n_pts + s, &n, sizeof(int), cudaMemcpyHostToDevice));
+  const size_t rec = (size_t)prev_rec_[s];   // nothing is in flight: the stream's current state record is rewritten in place
+  FG_CUDA(cudaMemcpy(g_.pts + rec * g_.pts_cap, p_pts, n * sizeof(float2), cudaMemcpyHostToDevice));
+  FG_CUDA(cudaMemcpy(g_.ids + rec * g_.pts_cap, p_ids, n * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  FG_CUDA(cudaMemcpy(g_.n_pts + rec, &n, sizeof(int), cudaMemcpyHostToDevice));
   FG_CUDA(cudaMemcpy(g_.currid + s, &hd.currid, sizeof(uint64_t), cudaMemcpyHostToDevice));
   if (cfg_.use_lines) {
     const int lb = 0;

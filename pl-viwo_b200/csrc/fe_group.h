@@ -100,9 +100,19 @@ class FeGroup {
   TrackJob *h_tjobs_ = nullptr, *d_tjobs_ = nullptr;   // RB * S
   std::vector<cudaStream_t> s_copy_;                   // frames go in round-robin over a few copy streams (a 0.7 MB copy has a fixed cost that only overlaps across streams)
   unsigned copy_rr_ = 0;
+  // PLVIWO_GROUP_TRACE=1: device-side latency of every front batch (first kernel .. segments) and the interval between
+  // consecutive batches, printed when the group is destroyed (diagnostics; two timed events per batch)
+  bool trace_ = false;
+  std::vector<cudaEvent_t> ev_tr0_, ev_tr1_, ev_trs_;   // ev_trs_: 4 per batch (after the pyramid, Canny + tiles, components, walk)
+  double tr_stage_ms_[5] = {0, 0, 0, 0, 0};
+  std::vector<char> tr_valid_;
+  int tr_prev_ = -1;
+  double tr_lat_ms_ = 0, tr_period_ms_ = 0, tr_lane_ms_ = 0;
+  long tr_n_ = 0, tr_np_ = 0;
+  std::vector<int> prev_rec_;                          // per stream: the state record that holds its pts_last (fe_group_dev.h)
   std::vector<cudaStream_t> s_front_, s_track_, s_lines_;
   std::vector<cudaEvent_t> ev_gate_;                   // per ring entry * lanes: the point chain of the tick is done
-  std::vector<cudaEvent_t> ev_copy_, ev_front_;        // per front-batch buffer
+  std::vector<cudaEvent_t> ev_copy_, ev_front_, ev_pyr_;   // per front-batch buffer (ev_pyr_: the batch's pyramids are built)
   std::vector<cudaEvent_t> ev_done_;                   // per ring entry * lanes
   std::vector<cudaEvent_t> ev_lane_prev_;              // per lane: previous tick's tracking done (front may reuse its slots)
   // ---- bookkeeping (caller's thread)

@@ -16,8 +16,8 @@ struct TrackJob {
   int stream;
   int cur_slot, prev_slot;   // indices into the SlotRec table; prev_slot < 0: no previous image (first frame of the stream)
   int flags;                 // bit 0: run the line tracker (vanishing points given)
-  int out;                   // index of the frame's output record
-  int pad;
+  int out;                   // index of the frame's output record = of the state record the frame WRITES (pts_last after it)
+  int prev_rec;              // state record holding the stream's pts_last / ids_last BEFORE this frame
   double timestamp;
   double K[4], D[4];         // calibration in force when the frame was submitted
   double vp[6];
@@ -50,11 +50,14 @@ struct GroupDev {
   // ---- slot table
   const SlotRec *slots;
   const int *slot_flags;
-  // ---- point tracker state, stream s at s * pts_cap
+  // ---- point tracker state.  pts_last / ids_last live in a RING of records (one per output record: tick ring x stream), record
+  // r at r * pts_cap: the frame of a tick reads its stream's previous record and writes its own, so the line association of a
+  // tick — which reads the points of ITS tick and may run much later than the point chain, after the batch's chain walk —
+  // never holds up the next tick's point chain.
   float2 *pts;
   uint64_t *ids;
-  int *n_pts;
-  uint64_t *currid;
+  int *n_pts;                    // per record
+  uint64_t *currid;              // per stream
   // ---- work arrays of the frame being tracked
   float2 *wpts;                  // pts_old after the top-off detection (LK input)
   uint64_t *wids;

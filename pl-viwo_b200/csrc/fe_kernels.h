@@ -220,7 +220,9 @@ struct FldTable {
   __device__ const DevImage &half_of(int k) const { return slots[idx[k]].half; }
   __device__ const FldBuffers &fld_of(int k) const { return slots[idx[k]].fld; }
 };
-// Line paths of n_jobs frames; line_slots: device array of slot indices.  ev as launch_fld.
+// Line paths of n_jobs frames; line_slots: device array of slot indices.  ev as launch_fld.  launch_canny_table also labels
+// the connected components of every 64 x 16 tile (fused into the Canny kernel); launch_fld_table continues from there and
+// must follow it on the same stream.
 void launch_canny_table(const SlotRec *slots, const int *line_slots, int n_jobs, int w, int h, float th_low, cudaStream_t s);
 void launch_fld_table(const SlotRec *slots, const int *line_slots, int n_jobs, int w, int h, int max_chains, int length_threshold,
                       float distance_threshold, cudaStream_t s, cudaEvent_t *ev = nullptr);

@@ -67,15 +67,15 @@ __global__ void __launch_bounds__(kGT)
   const int s = job.stream, tid = threadIdx.x;
   const int cols = g.W, rows = g.H, d = g.min_px_dist, gx = g.grid_x, gy = g.grid_y;
   const int close_w = g.close_w, close_h = g.close_h, close_n = close_w * close_h;
-  const int n0 = g.n_pts[s];
+  const int n0 = g.n_pts[job.prev_rec];
   // TrackKLT.cpp:110-123 — nothing tracked last time (or no previous image): detect on the CURRENT image only
   const bool first = n0 == 0 || job.prev_slot < 0;
   const int islot = first ? job.cur_slot : job.prev_slot;
   const SlotRec &sl = g.slots[islot];
   const uint8_t *__restrict__ mask = (g.slot_flags[islot] & 1) ? sl.mask : nullptr;
   const size_t o = (size_t)s * g.pts_cap;
-  const float2 *__restrict__ pts = g.pts + o;
-  const uint64_t *__restrict__ ids = g.ids + o;
+  const float2 *__restrict__ pts = g.pts + (size_t)job.prev_rec * g.pts_cap;
+  const uint64_t *__restrict__ ids = g.ids + (size_t)job.prev_rec * g.pts_cap;
   float2 *__restrict__ wpts = g.wpts + o;
   uint64_t *__restrict__ wids = g.wids + o;
   int *__restrict__ close = g.close + (size_t)s * close_n;
@@ -187,33 +187,47 @@ __global__ void __launch_bounds__(kGT)
   float2 *__restrict__ ext = g.ext_in + (size_t)s * g.cand_cap;
   int next = 0;
   const int total_q = nv * nfg;
-  for (int base = 0; base < total_q; base += kGT) {
-    const int q = base + tid;
-    bool pass = false;
-    float2 pr = make_float2(0.f, 0.f);
-    if (q < total_q) {
+  // one WARP per candidate for the occupancy test (its lanes share the kept points), then the ordered compaction
+  constexpr int kChunk = 2048;
+  __shared__ uint8_t s_pass[kChunk];
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int base = 0; base < total_q; base += kChunk) {
+    const int nq = min(kChunk, total_q - base);
+    for (int ql = warp; ql < nq; ql += kGT / 32) {
+      const int q = base + ql;
       const int v = q / nfg, k = q - v * nfg, c = valid[4 + v];
+      bool pass = false;
       if (c >= 0 && k < min(sl.cand_cnt[c], nfg)) {
-        const int i = c * nfg + k;
-        const float2 p = sl.cand[i];
+        const float2 p = sl.cand[c * nfg + k];
         const int ix = (int)p.x, iy = (int)p.y;
         if (!(ix < 0 || ix > cols || iy < 0 || iy > rows) && iy < rows && ix < cols) {
           bool occ = mask != nullptr && mask[(size_t)iy * cols + ix] > 127;
-          for (int j = 0; j < nk && !occ; j++) {
-            const float2 w = wpts[j];
-            const int x = (int)w.x, y = (int)w.y;
-            occ = x - d >= 0 && x + d < cols && y - d >= 0 && y + d < rows && abs(ix - x) <= d && abs(iy - y) <= d;
-          }
           if (!occ) {
-            pass = true;
-            pr = p;                // refined by k_group_subpix before the distance test (Grider_GRID.h:163-179)
+            for (int j = lane; j < nk; j += 32) {
+              const float2 w = wpts[j];
+              const int x = (int)w.x, y = (int)w.y;
+              occ = occ || (x - d >= 0 && x + d < cols && y - d >= 0 && y + d < rows && abs(ix - x) <= d && abs(iy - y) <= d);
+            }
+            occ = __any_sync(0xffffffffu, occ);
           }
+          pass = !occ;
         }
       }
+      if (lane == 0) s_pass[ql] = pass ? 1 : 0;
     }
-    const int e = block_excl(pass ? 1 : 0, bs);
-    if (pass) ext[next + e] = pr;
-    next += bs.total;
+    __syncthreads();
+    for (int b0 = 0; b0 < nq; b0 += kGT) {
+      const int ql = b0 + tid;
+      const bool pass = ql < nq && s_pass[ql];
+      const int e = block_excl(pass ? 1 : 0, bs);
+      if (pass) {
+        const int q = base + ql;
+        const int v = q / nfg, k = q - v * nfg;
+        ext[next + e] = sl.cand[valid[4 + v] * nfg + k];   // refined by k_group_subpix before the distance test (Grider_GRID.h:163-179)
+      }
+      next += bs.total;
+    }
+    __syncthreads();
   }
   if (tid == 0) g.winfo[4 * s + 3] = next;
 }
@@ -360,8 +374,8 @@ __global__ void __launch_bounds__(kGT)
   const int s = job.stream, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = g.wn[s], mode = g.wmode[s];
   const size_t o = (size_t)s * g.pts_cap;
-  float2 *__restrict__ pts = g.pts + o;
-  uint64_t *__restrict__ ids = g.ids + o;
+  float2 *__restrict__ pts = g.pts + (size_t)job.out * g.pts_cap;      // this frame's state record
+  uint64_t *__restrict__ ids = g.ids + (size_t)job.out * g.pts_cap;
   const float2 *__restrict__ wpts = g.wpts + o;
   const uint64_t *__restrict__ wids = g.wids + o;
   uint8_t *const rec = g.out + (size_t)job.out * g.out_stride;
@@ -390,7 +404,7 @@ __global__ void __launch_bounds__(kGT)
       obs_uv[i] = wpts[i];
     }
     if (tid == 0) {
-      g.n_pts[s] = n;
+      g.n_pts[job.out] = n;
       hdr->info.first_frame = 1;
       hdr->info.n_last_obs = n;
       hdr->n_obs = n;
@@ -399,7 +413,7 @@ __global__ void __launch_bounds__(kGT)
   }
   if (n < 10) {   // n == 0: mask_out stays empty => reset (:143-152); 1..9: every point fails (:848-852)
     if (tid == 0) {
-      g.n_pts[s] = 0;
+      g.n_pts[job.out] = 0;
       if (n == 0) hdr->info.reset = 1;
     }
     return;
@@ -528,7 +542,7 @@ __global__ void __launch_bounds__(kGT)
   }
   n_klt = block_sum(n_klt, bs);
   if (tid == 0) {
-    g.n_pts[s] = n_good;
+    g.n_pts[job.out] = n_good;
     hdr->info.n_lk_in = n;
     hdr->info.n_klt_ok = n_klt;
     hdr->info.n_ransac_ok = n_in;
@@ -633,10 +647,9 @@ __global__ void __launch_bounds__(kGT)
   int *__restrict__ loff = g.loff + (size_t)s * (LC + 1);
   float2 *__restrict__ lpos = g.lpos + (size_t)s * PC;
   int *__restrict__ lmatch = g.lmatch + (size_t)s * LC;
-  const size_t o = (size_t)s * g.pts_cap;
-  const float2 *__restrict__ pts = g.pts + o;      // the point tracker's pts_last / ids_last after THIS frame (:127-129)
-  const uint64_t *__restrict__ pids = g.ids + o;
-  const int npt = g.n_pts[s];
+  const float2 *__restrict__ pts = g.pts + (size_t)job.out * g.pts_cap;      // the point tracker's pts_last / ids_last after THIS frame (:127-129)
+  const uint64_t *__restrict__ pids = g.ids + (size_t)job.out * g.pts_cap;
+  const int npt = g.n_pts[job.out];
   if (tid == 0) s_over = 0;
 
   // ---- perform_detection_monocular (:218-236): x2, FilterShortLines(40), a fresh id for EVERY detected line

@@ -28,102 +28,6 @@
 
 namespace plviwo {
 
-// ------------------------------------------------------------------------------------------------ Canny
-constexpr int kCnW = 64, kCnH = 16, kCnThreads = 256;
-
-template <class B>
-__global__ void __launch_bounds__(kCnThreads)
-    k_canny(const __grid_constant__ B b, int low) {
-  const uint8_t *__restrict__ img = b.half_of(blockIdx.z).p;
-  const int w = b.half_of(blockIdx.z).w, h = b.half_of(blockIdx.z).h, pitch = b.half_of(blockIdx.z).pitch;
-  unsigned *__restrict__ edges = b.fld_of(blockIdx.z).edges;
-  const int words_per_row = b.fld_of(blockIdx.z).words_per_row;
-  __shared__ uint8_t pix[kCnH + 4][kCnW + 4];
-  __shared__ short sdx[kCnH + 2][kCnW + 2];
-  __shared__ short sdy[kCnH + 2][kCnW + 2];
-  __shared__ unsigned short mag[kCnH + 2][kCnW + 2];
-  const int tx0 = blockIdx.x * kCnW, ty0 = blockIdx.y * kCnH;
-  const int tid = threadIdx.x;
-  // pixels with a halo of 2, BORDER_REPLICATE
-  for (int i = tid; i < (kCnH + 4) * (kCnW + 4); i += kCnThreads) {
-    int r = i / (kCnW + 4), c = i - r * (kCnW + 4);
-    int gx = min(max(tx0 - 2 + c, 0), w - 1), gy = min(max(ty0 - 2 + r, 0), h - 1);
-    pix[r][c] = img[(size_t)gy * pitch + gx];
-  }
-  __syncthreads();
-  // Sobel + L1 magnitude with a halo of 1; zero outside the image
-  for (int i = tid; i < (kCnH + 2) * (kCnW + 2); i += kCnThreads) {
-    int r = i / (kCnW + 2), c = i - r * (kCnW + 2);
-    int gx = tx0 - 1 + c, gy = ty0 - 1 + r;
-    int dx = 0, dy = 0, m = 0;
-    if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
-      const uint8_t *p = &pix[r + 1][c + 1];
-      const int s = kCnW + 4;
-      dx = (p[-s + 1] + 2 * p[1] + p[s + 1]) - (p[-s - 1] + 2 * p[-1] + p[s - 1]);
-      dy = (p[s - 1] + 2 * p[s] + p[s + 1]) - (p[-s - 1] + 2 * p[-s] + p[-s + 1]);
-      m = abs(dx) + abs(dy);
-    }
-    sdx[r][c] = (short)dx;
-    sdy[r][c] = (short)dy;
-    mag[r][c] = (unsigned short)m;
-  }
-  __syncthreads();
-  // non-maximum suppression; warp wv handles rows 2wv, 2wv+1; 32 pixels per ballot
-  const int wv = tid >> 5, lane = tid & 31;
-#pragma unroll
-  for (int q = 0; q < 4; q++) {
-    int r = 2 * wv + (q >> 1), c = (q & 1) * 32 + lane;
-    int gx = tx0 + c, gy = ty0 + r;
-    bool edge = false;
-    if (gx < w && gy < h) {
-      int m = mag[r + 1][c + 1];
-      if (m > low) {
-        int dx = sdx[r + 1][c + 1], dy = sdy[r + 1][c + 1];
-        int x = abs(dx), y = abs(dy) << 15;
-        int tg22x = x * 13573;
-        if (y < tg22x) {
-          edge = m > mag[r + 1][c] && m >= mag[r + 1][c + 2];
-        } else {
-          int tg67x = tg22x + (x << 16);
-          if (y > tg67x) {
-            edge = m > mag[r][c + 1] && m >= mag[r + 2][c + 1];
-          } else {
-            int s = (dx ^ dy) < 0 ? -1 : 1;
-            edge = m > mag[r][c + 1 - s] && m > mag[r + 2][c + 1 + s];
-          }
-        }
-      }
-      // FastLineDetector clears the two corner blocks of the edge map before walking
-      if (gy < 6 && gx < 6) edge = false;
-      if (gy >= h - 5 && gx >= w - 5) edge = false;
-    }
-    unsigned bits = __ballot_sync(0xffffffffu, edge);
-    if (lane == 0 && gy < h && (tx0 + (q & 1) * 32) < w) edges[(size_t)gy * words_per_row + ((tx0 + (q & 1) * 32) >> 5)] = bits;
-  }
-}
-
-template <class B>
-static void launch_canny_any(const B &b, int n, int w, int h, float th_low, cudaStream_t s) {
-  dim3 grid((w + kCnW - 1) / kCnW, (h + kCnH - 1) / kCnH, n);
-  PLVIWO_CARVEOUT(k_canny<B>);
-  k_canny<B><<<grid, kCnThreads, 0, s>>>(b, (int)floorf(th_low));
-}
-void launch_canny_batch(const FldBatch &b, float th_low, float th_high, cudaStream_t s) {
-  (void)th_high;  // low == high is enforced at create time (no hysteresis pass is implemented)
-  launch_canny_any(b, b.n, b.half[0].w, b.half[0].h, th_low, s);
-}
-void launch_canny_table(const SlotRec *slots, const int *line_slots, int n_jobs, int w, int h, float th_low, cudaStream_t s) {
-  if (n_jobs <= 0) return;
-  launch_canny_any(FldTable{slots, line_slots}, n_jobs, w, h, th_low, s);
-}
-void launch_canny(const DevImage &half, float th_low, float th_high, FldBuffers &fb, cudaStream_t s) {
-  FldBatch b;
-  b.n = 1;
-  b.half[0] = half;
-  b.f[0] = fb;
-  launch_canny_batch(b, th_low, th_high, s);
-}
-
 __global__ void k_unpack_edges(const unsigned *__restrict__ edges, int words_per_row, int w, int h,
                                uint8_t *__restrict__ out) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -193,32 +97,23 @@ __device__ __forceinline__ void sm_union(int *lab, int a, int b) {
   }
 }
 
-template <class B>
-__global__ void __launch_bounds__(kTileThreads)
-    k_ccl_tile(const __grid_constant__ B b, int w, int h) {
-  const FldBuffers &fb = b.fld_of(blockIdx.z);
-  const unsigned *__restrict__ edges = fb.edges;
-  const int words_per_row = fb.words_per_row;
+struct CclTileSmem {
+  unsigned bits[kTileH][2];
+  int lab[kTilePx];
+  int a_cnt[kTilePx], a_ymax[kTilePx], a_xmin[kTilePx], a_xmax[kTilePx];
+};
+
+// Labels one 64 x 16 tile whose edge bits are in sm.bits (block-wide call, kTileThreads threads, bits visible to all).
+__device__ __forceinline__ void ccl_tile_body(const FldBuffers &fb, CclTileSmem &sm, int x0, int y0, int w, int h) {
   int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt, *__restrict__ bbox = fb.bbox /* maxy, minx, maxx planes */;
-  __shared__ unsigned bits[kTileH][2];
-  __shared__ int lab[kTilePx];
-  __shared__ int a_cnt[kTilePx], a_ymax[kTilePx], a_xmin[kTilePx], a_xmax[kTilePx];
+  auto &bits = sm.bits;
+  int *lab = sm.lab, *a_cnt = sm.a_cnt, *a_ymax = sm.a_ymax, *a_xmin = sm.a_xmin, *a_xmax = sm.a_xmax;
   const int tid = threadIdx.x;
-  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
-  // (counters and the local-root count are zeroed by k_ccl_reset, ahead of this launch)
-  if (tid < kTileH * 2) {
-    const int r = tid >> 1, k = tid & 1;
-    const int gy = y0 + r, gw = (x0 >> 5) + k;
-    unsigned v = 0;
-    if (gy < h && gw < words_per_row) v = edges[(size_t)gy * words_per_row + gw];
-    if (gy < h && (gw << 5) + 32 > w) v &= (gw << 5) < w ? (0xffffffffu >> (32 - (w - (gw << 5)))) : 0u;   // beyond the frame
-    bits[r][k] = v;
-  }
-  __syncthreads();
   auto edge = [&](int lx, int ly) -> bool { return (bits[ly][lx >> 5] >> (lx & 31)) & 1u; };
   // thread t owns the 4 pixels (4 (t % 16) .., t / 16)
   const int ly = tid >> 4, lx0 = (tid & 15) << 2;
   const unsigned nib = (bits[ly][lx0 >> 5] >> (lx0 & 31)) & 15u;
+  if (!__syncthreads_or((int)nib)) return;   // no edge pixel in this tile
   // only edge pixels are ever looked at below (neighbours are tested on the bit map first): nothing to set up elsewhere
 #pragma unroll
   for (int k = 0; k < 4; k++) {
@@ -286,6 +181,161 @@ __global__ void __launch_bounds__(kTileThreads)
   }
 }
 
+template <class B>
+__global__ void __launch_bounds__(kTileThreads)
+    k_ccl_tile(const __grid_constant__ B b, int w, int h) {
+  const FldBuffers &fb = b.fld_of(blockIdx.z);
+  const unsigned *__restrict__ edges = fb.edges;
+  const int words_per_row = fb.words_per_row;
+  __shared__ CclTileSmem sm;
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  // (counters and the local-root count are zeroed by k_ccl_reset, ahead of this launch)
+  if (tid < kTileH * 2) {
+    const int r = tid >> 1, k = tid & 1;
+    const int gy = y0 + r, gw = (x0 >> 5) + k;
+    unsigned v = 0;
+    if (gy < h && gw < words_per_row) v = edges[(size_t)gy * words_per_row + gw];
+    if (gy < h && (gw << 5) + 32 > w) v &= (gw << 5) < w ? (0xffffffffu >> (32 - (w - (gw << 5)))) : 0u;   // beyond the frame
+    sm.bits[r][k] = v;
+  }
+  __syncthreads();
+  ccl_tile_body(fb, sm, x0, y0, w, h);
+}
+
+template <class B>
+__global__ void k_ccl_reset(const __grid_constant__ B b) {
+  const FldBuffers &fb = b.fld_of(blockIdx.x);
+  if (threadIdx.x < 8) fb.counters[threadIdx.x] = 0;
+  if (threadIdx.x == 8) *fb.lroot_n = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ Canny
+constexpr int kCnW = 64, kCnH = 16, kCnThreads = 256;
+
+// kFuse: the CTA goes on to label its tile (the Canny tile IS the connected-component tile: same 64 x 16 pixels, same 256
+// threads), so the edge bits never make the trip through global memory before the first labelling step and the frame's
+// tiles are launched once instead of twice.  k_ccl_reset must have run before the launch.
+static_assert(kCnW == kTileW && kCnH == kTileH && kCnThreads == kTileThreads, "Canny tile = connected-component tile");
+struct CannySmem {
+  uint8_t pix[kCnH + 4][kCnW + 4];
+  short sdx[kCnH + 2][kCnW + 2];
+  short sdy[kCnH + 2][kCnW + 2];
+  unsigned short mag[kCnH + 2][kCnW + 2];
+};
+template <class B, bool kFuse>
+__global__ void __launch_bounds__(kCnThreads)
+    k_canny(const __grid_constant__ B b, int low) {
+  const uint8_t *__restrict__ img = b.half_of(blockIdx.z).p;
+  const int w = b.half_of(blockIdx.z).w, h = b.half_of(blockIdx.z).h, pitch = b.half_of(blockIdx.z).pitch;
+  unsigned *__restrict__ edges = b.fld_of(blockIdx.z).edges;
+  const int words_per_row = b.fld_of(blockIdx.z).words_per_row;
+  // the labelling pass reuses the gradient planes' shared memory (they are dead once the edge bits exist)
+  __shared__ __align__(16) uint8_t smem_raw[kFuse ? (sizeof(CclTileSmem) > sizeof(CannySmem) ? sizeof(CclTileSmem) : sizeof(CannySmem))
+                                                  : sizeof(CannySmem)];
+  __shared__ unsigned s_bits[kCnH][2];
+  CannySmem &cs = *reinterpret_cast<CannySmem *>(smem_raw);
+  auto &pix = cs.pix;
+  auto &sdx = cs.sdx;
+  auto &sdy = cs.sdy;
+  auto &mag = cs.mag;
+  const int tx0 = blockIdx.x * kCnW, ty0 = blockIdx.y * kCnH;
+  const int tid = threadIdx.x;
+  // pixels with a halo of 2, BORDER_REPLICATE
+  for (int i = tid; i < (kCnH + 4) * (kCnW + 4); i += kCnThreads) {
+    int r = i / (kCnW + 4), c = i - r * (kCnW + 4);
+    int gx = min(max(tx0 - 2 + c, 0), w - 1), gy = min(max(ty0 - 2 + r, 0), h - 1);
+    pix[r][c] = img[(size_t)gy * pitch + gx];
+  }
+  __syncthreads();
+  // Sobel + L1 magnitude with a halo of 1; zero outside the image
+  for (int i = tid; i < (kCnH + 2) * (kCnW + 2); i += kCnThreads) {
+    int r = i / (kCnW + 2), c = i - r * (kCnW + 2);
+    int gx = tx0 - 1 + c, gy = ty0 - 1 + r;
+    int dx = 0, dy = 0, m = 0;
+    if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+      const uint8_t *p = &pix[r + 1][c + 1];
+      const int s = kCnW + 4;
+      dx = (p[-s + 1] + 2 * p[1] + p[s + 1]) - (p[-s - 1] + 2 * p[-1] + p[s - 1]);
+      dy = (p[s - 1] + 2 * p[s] + p[s + 1]) - (p[-s - 1] + 2 * p[-s] + p[-s + 1]);
+      m = abs(dx) + abs(dy);
+    }
+    sdx[r][c] = (short)dx;
+    sdy[r][c] = (short)dy;
+    mag[r][c] = (unsigned short)m;
+  }
+  __syncthreads();
+  // non-maximum suppression; warp wv handles rows 2wv, 2wv+1; 32 pixels per ballot
+  const int wv = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    int r = 2 * wv + (q >> 1), c = (q & 1) * 32 + lane;
+    int gx = tx0 + c, gy = ty0 + r;
+    bool edge = false;
+    if (gx < w && gy < h) {
+      int m = mag[r + 1][c + 1];
+      if (m > low) {
+        int dx = sdx[r + 1][c + 1], dy = sdy[r + 1][c + 1];
+        int x = abs(dx), y = abs(dy) << 15;
+        int tg22x = x * 13573;
+        if (y < tg22x) {
+          edge = m > mag[r + 1][c] && m >= mag[r + 1][c + 2];
+        } else {
+          int tg67x = tg22x + (x << 16);
+          if (y > tg67x) {
+            edge = m > mag[r][c + 1] && m >= mag[r + 2][c + 1];
+          } else {
+            int s = (dx ^ dy) < 0 ? -1 : 1;
+            edge = m > mag[r][c + 1 - s] && m > mag[r + 2][c + 1 + s];
+          }
+        }
+      }
+      // FastLineDetector clears the two corner blocks of the edge map before walking
+      if (gy < 6 && gx < 6) edge = false;
+      if (gy >= h - 5 && gx >= w - 5) edge = false;
+    }
+    unsigned bits = __ballot_sync(0xffffffffu, edge);
+    if (lane == 0 && gy < h && (tx0 + (q & 1) * 32) < w) edges[(size_t)gy * words_per_row + ((tx0 + (q & 1) * 32) >> 5)] = bits;
+    if (kFuse && lane == 0) s_bits[r][q & 1] = bits;   // pixels beyond the frame are not edges: the same bits k_ccl_tile would read
+  }
+  if (kFuse) {
+    __syncthreads();   // every warp is done with the gradient planes; the tile's bits are complete
+    CclTileSmem &ts = *reinterpret_cast<CclTileSmem *>(smem_raw);
+    if (tid < kCnH * 2) ts.bits[tid >> 1][tid & 1] = s_bits[tid >> 1][tid & 1];
+    __syncthreads();
+    ccl_tile_body(b.fld_of(blockIdx.z), ts, tx0, ty0, w, h);
+  }
+}
+
+template <class B>
+static void launch_canny_any(const B &b, int n, int w, int h, float th_low, cudaStream_t s, bool fuse_labels = false) {
+  dim3 grid((w + kCnW - 1) / kCnW, (h + kCnH - 1) / kCnH, n);
+  if (fuse_labels) {   // Canny + the tile-local labelling of the connected components; launch_fld_any(..., tiles_done = true) follows
+    PLVIWO_CARVEOUT(k_ccl_reset<B>);
+    k_ccl_reset<B><<<n, 32, 0, s>>>(b);
+    PLVIWO_CARVEOUT((k_canny<B, true>));
+    k_canny<B, true><<<grid, kCnThreads, 0, s>>>(b, (int)floorf(th_low));
+    return;
+  }
+  PLVIWO_CARVEOUT((k_canny<B, false>));
+  k_canny<B, false><<<grid, kCnThreads, 0, s>>>(b, (int)floorf(th_low));
+}
+void launch_canny_batch(const FldBatch &b, float th_low, float th_high, cudaStream_t s) {
+  (void)th_high;  // low == high is enforced at create time (no hysteresis pass is implemented)
+  launch_canny_any(b, b.n, b.half[0].w, b.half[0].h, th_low, s);
+}
+void launch_canny_table(const SlotRec *slots, const int *line_slots, int n_jobs, int w, int h, float th_low, cudaStream_t s) {
+  if (n_jobs <= 0) return;
+  launch_canny_any(FldTable{slots, line_slots}, n_jobs, w, h, th_low, s, true);
+}
+void launch_canny(const DevImage &half, float th_low, float th_high, FldBuffers &fb, cudaStream_t s) {
+  FldBatch b;
+  b.n = 1;
+  b.half[0] = half;
+  b.f[0] = fb;
+  launch_canny_batch(b, th_low, th_high, s);
+}
+
 // One thread per pixel of a tile border: rows y = 16 k (all x) first, then columns x = 64 m (all y).
 template <class B>
 __global__ void k_ccl_border(const __grid_constant__ B b, int w, int h) {
@@ -312,13 +362,6 @@ __global__ void k_ccl_border(const __grid_constant__ B b, int w, int h) {
   if (y > 0 && edge_at(edges, words_per_row, x - 1, y - 1)) ccl_union(label, i, i - w - 1);
   if (edge_at(edges, words_per_row, x - 1, y)) ccl_union(label, i, i - 1);
   if (y < h - 1 && edge_at(edges, words_per_row, x - 1, y + 1)) ccl_union(label, i, i + w - 1);
-}
-
-template <class B>
-__global__ void k_ccl_reset(const __grid_constant__ B b) {
-  const FldBuffers &fb = b.fld_of(blockIdx.x);
-  if (threadIdx.x < 8) fb.counters[threadIdx.x] = 0;
-  if (threadIdx.x == 8) *fb.lroot_n = 0;
 }
 
 // One thread per tile-local root: find the global root once, point straight at it, hand the aggregates over.
@@ -942,14 +985,16 @@ void FldBuffers::release() {
 
 template <class B>
 static void launch_fld_any(const B &b, int nb_frames, int w, int h, int max_chains, int length_threshold, float distance_threshold,
-                           cudaStream_t s, cudaEvent_t *ev) {
+                           cudaStream_t s, cudaEvent_t *ev, bool tiles_done = false) {
   const int n = w * h;
   const int tpb = 256;
   const int lroot_cap = n / 4 + 1;
-  PLVIWO_CARVEOUT(k_ccl_reset<B>);
-  k_ccl_reset<B><<<nb_frames, 32, 0, s>>>(b);
-  PLVIWO_CARVEOUT(k_ccl_tile<B>);
-  k_ccl_tile<B><<<dim3((w + kTileW - 1) / kTileW, (h + kTileH - 1) / kTileH, nb_frames), kTileThreads, 0, s>>>(b, w, h);
+  if (!tiles_done) {   // (the stream group's Canny launch has labelled the tiles already: launch_canny_table)
+    PLVIWO_CARVEOUT(k_ccl_reset<B>);
+    k_ccl_reset<B><<<nb_frames, 32, 0, s>>>(b);
+    PLVIWO_CARVEOUT(k_ccl_tile<B>);
+    k_ccl_tile<B><<<dim3((w + kTileW - 1) / kTileW, (h + kTileH - 1) / kTileH, nb_frames), kTileThreads, 0, s>>>(b, w, h);
+  }
   const int nborder = ((h - 1) / kTileH) * w + ((w - 1) / kTileW) * h;
   if (nborder > 0) {
     PLVIWO_CARVEOUT(k_ccl_border<B>);
@@ -997,7 +1042,7 @@ void launch_fld_batch(const FldBatch &b, int length_threshold, float distance_th
 void launch_fld_table(const SlotRec *slots, const int *line_slots, int n_jobs, int w, int h, int max_chains, int length_threshold,
                       float distance_threshold, cudaStream_t s, cudaEvent_t *ev) {
   if (n_jobs <= 0) return;
-  launch_fld_any(FldTable{slots, line_slots}, n_jobs, w, h, max_chains, length_threshold, distance_threshold, s, ev);
+  launch_fld_any(FldTable{slots, line_slots}, n_jobs, w, h, max_chains, length_threshold, distance_threshold, s, ev, true);
 }
 
 void launch_fld(const DevImage &half, int length_threshold, float distance_threshold, FldBuffers &fb, cudaStream_t s,

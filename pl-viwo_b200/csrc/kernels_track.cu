@@ -784,12 +784,17 @@ constexpr int kLkwWarps = 4;
 // that end up in shared memory are the same either way.
 constexpr int kRawStride = 24;   // >= 18 + 3
 constexpr int kJStride = 28;     // >= 25 + 3
+// One buffer per warp, used three ways in turn (each hand-over is separated by a __syncwarp): the staged rows of the previous
+// image + the Scharr planes (set-up), the fixed-point patches I / Ix / Iy (written once every lane has read what it needs of
+// the former, read back row-wise into registers), the staged region of the next image (iterations).  1.5 KB per feature
+// instead of 3.6 KB: a CTA of four features needs 6 KB of shared memory, so the kernel's residency does not depend on what
+// the long-lived kernels of the pipeline (the chain walkers) leave free.
+constexpr int kLkwDdxOff = ((kW15 + 3) * kRawStride + 8 + 15) & ~15;                  // 448
+constexpr int kLkwDdyOff = kLkwDdxOff + (kW15 + 1) * (kW15 + 1) * 2;                   // 960
+constexpr int kLkwBytes = kLkwDdyOff + (kW15 + 1) * (kW15 + 1) * 2;                    // 1472
+static_assert(3 * kW15 * 16 * 2 <= kLkwBytes && kJR * kJStride + 4 <= kLkwBytes, "patches and the J region fit the buffer");
 struct LkwSmem {
-  __align__(16) uint8_t raw[(kW15 + 3) * kRawStride + 8];
-  __align__(16) short ddx[(kW15 + 1) * (kW15 + 1)];
-  __align__(16) short ddy[(kW15 + 1) * (kW15 + 1)];
-  __align__(16) short patch[3][kW15][16];   // [I, Ix, Iy][window row][window column (15 used, column 15 = 0)]
-  __align__(16) uint8_t jreg[kJR * kJStride + 4];
+  __align__(16) uint8_t buf[kLkwBytes];
 };
 
 template <class Args>
@@ -829,8 +834,9 @@ __device__ __forceinline__ void lk15w_body(const Args &a, const float2 *__restri
     float A11 = 0, A12 = 0, A22 = 0;
     __syncwarp();   // the previous level's patches have been read by every lane
     {
-      const uint8_t *raw = sm.raw;
-      short *ddx = sm.ddx, *ddy = sm.ddy;
+      uint8_t *const raw_s = sm.buf;
+      const uint8_t *raw = raw_s;
+      short *ddx = reinterpret_cast<short *>(sm.buf + kLkwDdxOff), *ddy = reinterpret_cast<short *>(sm.buf + kLkwDdyOff);
       bool interior = false;
       int roff_b = 0;
       {
@@ -854,8 +860,8 @@ __device__ __forceinline__ void lk15w_body(const Args &a, const float2 *__restri
           }
 #pragma unroll
           for (int j = 0; j < (kWords + 31) / 32; j++)
-            if (lane + 32 * j < kWords) reinterpret_cast<unsigned *>(sm.raw)[lane + 32 * j] = v[j];
-          raw = sm.raw + roff;
+            if (lane + 32 * j < kWords) reinterpret_cast<unsigned *>(raw_s)[lane + 32 * j] = v[j];
+          raw = raw_s + roff;
           interior = true;
           roff_b = 8 * roff;
         } else {
@@ -872,7 +878,7 @@ __device__ __forceinline__ void lk15w_body(const Args &a, const float2 *__restri
 #pragma unroll
           for (int j = 0; j < kRawLoads; j++) {
             const int i = lane + 32 * j;
-            if (i < np * np) sm.raw[(i / np) * kRawStride + (i % np)] = v[j];
+            if (i < np * np) raw_s[(i / np) * kRawStride + (i % np)] = v[j];
           }
         }
       }
@@ -889,10 +895,11 @@ __device__ __forceinline__ void lk15w_body(const Args &a, const float2 *__restri
         unsigned X[3][3];
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-          const uint4 wv = *reinterpret_cast<const uint4 *>(sm.raw + (r + k) * kRawStride + cb);
-          X[k][0] = __funnelshift_r(wv.x, wv.y, roff_b);
-          X[k][1] = __funnelshift_r(wv.y, wv.z, roff_b);
-          X[k][2] = __funnelshift_r(wv.z, wv.w, roff_b);
+          const uint2 *rp = reinterpret_cast<const uint2 *>(raw_s + (r + k) * kRawStride + cb);   // 8-byte aligned (stride 24)
+          const uint2 wa = rp[0], wb = rp[1];
+          X[k][0] = __funnelshift_r(wa.x, wa.y, roff_b);
+          X[k][1] = __funnelshift_r(wa.y, wb.x, roff_b);
+          X[k][2] = __funnelshift_r(wb.x, wb.y, roff_b);
         }
         int S[10], Dv[10];   // column smoothing 3 t + 10 m + 3 b and column difference b - t
 #pragma unroll
@@ -929,6 +936,7 @@ __device__ __forceinline__ void lk15w_body(const Args &a, const float2 *__restri
         ddy[i] = (short)vy;
       }
       __syncwarp();
+      short pv[3][8];   // this lane's 2 x 4 block of I, Ix, Iy: stored once every lane is done with the rows and planes
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const int y = r0 + (k >> 2), x = c0 + (k & 3);
@@ -940,14 +948,27 @@ __device__ __forceinline__ void lk15w_body(const Args &a, const float2 *__restri
           ixval = (ddx[di] * iw00 + ddx[di + 1] * iw01 + ddx[di + nd] * iw10 + ddx[di + nd + 1] * iw11 + (1 << 13)) >> 14;
           iyval = (ddy[di] * iw00 + ddy[di + 1] * iw01 + ddy[di + nd] * iw10 + ddy[di + nd + 1] * iw11 + (1 << 13)) >> 14;
         }
-        if (y < win && x < 16) {
-          sm.patch[0][y][x] = (short)ival;
-          sm.patch[1][y][x] = (short)ixval;
-          sm.patch[2][y][x] = (short)iyval;
-        }
+        pv[0][k] = (short)ival;
+        pv[1][k] = (short)ixval;
+        pv[2][k] = (short)iyval;
         A11 += (float)(ixval * ixval);
         A12 += (float)(ixval * iyval);
         A22 += (float)(iyval * iyval);
+      }
+      __syncwarp();   // the patches take the place of the rows and planes they were computed from
+      {
+        short(*patch)[kW15][16] = reinterpret_cast<short(*)[kW15][16]>(sm.buf);
+#pragma unroll
+        for (int pl = 0; pl < 3; pl++)
+#pragma unroll
+          for (int rr = 0; rr < 2; rr++) {
+            const int y = r0 + rr;
+            if (y < win) {
+              const unsigned lo = ((unsigned)(unsigned short)pv[pl][4 * rr]) | ((unsigned)(unsigned short)pv[pl][4 * rr + 1] << 16);
+              const unsigned hi = ((unsigned)(unsigned short)pv[pl][4 * rr + 2]) | ((unsigned)(unsigned short)pv[pl][4 * rr + 3] << 16);
+              *reinterpret_cast<uint2 *>(&patch[pl][y][c0]) = make_uint2(lo, hi);
+            }
+          }
       }
       A11 = warp_sum(A11) * FLT_SCALE;
       A12 = warp_sum(A12) * FLT_SCALE;
@@ -966,9 +987,10 @@ __device__ __forceinline__ void lk15w_body(const Args &a, const float2 *__restri
     {
       uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0;
       if (own) {
-        q0 = *reinterpret_cast<const uint4 *>(&sm.patch[0][wy][wx]);
-        q1 = *reinterpret_cast<const uint4 *>(&sm.patch[1][wy][wx]);
-        q2 = *reinterpret_cast<const uint4 *>(&sm.patch[2][wy][wx]);
+        const short(*patch)[kW15][16] = reinterpret_cast<const short(*)[kW15][16]>(sm.buf);
+        q0 = *reinterpret_cast<const uint4 *>(&patch[0][wy][wx]);
+        q1 = *reinterpret_cast<const uint4 *>(&patch[1][wy][wx]);
+        q2 = *reinterpret_cast<const uint4 *>(&patch[2][wy][wx]);
       }
       const unsigned w0[4] = {q0.x, q0.y, q0.z, q0.w}, w1[4] = {q1.x, q1.y, q1.z, q1.w}, w2[4] = {q2.x, q2.y, q2.z, q2.w};
 #pragma unroll
@@ -1029,7 +1051,7 @@ __device__ __forceinline__ void lk15w_body(const Args &a, const float2 *__restri
             }
 #pragma unroll
             for (int q = 0; q < (kWords + 31) / 32; q++)
-              if (lane + 32 * q < kWords) reinterpret_cast<unsigned *>(sm.jreg)[lane + 32 * q] = t[q];
+              if (lane + 32 * q < kWords) reinterpret_cast<unsigned *>(sm.buf)[lane + 32 * q] = t[q];
           } else {
             joff = 0;
             constexpr int kJLoads = (kJR * kJR + 31) / 32;   // 20, in two rounds of 10 loads in flight
@@ -1046,14 +1068,14 @@ __device__ __forceinline__ void lk15w_body(const Args &a, const float2 *__restri
 #pragma unroll
               for (int q = 0; q < kJLoads / 2; q++) {
                 const int i = lane + 32 * (q0 + q);
-                if (i < kJR * kJR) sm.jreg[(i / kJR) * kJStride + (i % kJR)] = t[q];
+                if (i < kJR * kJR) sm.buf[(i / kJR) * kJStride + (i % kJR)] = t[q];
               }
             }
           }
           __syncwarp();
         }
         if (own) {
-          const uint8_t *Jp = sm.jreg + (iny - reg_y0 + wy) * kJStride + (inx - reg_x0 + joff + wx);
+          const uint8_t *Jp = sm.buf + (iny - reg_y0 + wy) * kJStride + (inx - reg_x0 + joff + wx);
 #pragma unroll
           for (int k = 0; k < 9; k++) {
             jt[k] = Jp[k];
@@ -1165,7 +1187,8 @@ __global__ void __launch_bounds__(kLkWarps * 32)
   lk_body(sa, g.wpts + o, g.lk_pts1 + o, g.lk_status + o, g.lk_p0n + o, g.lk_p1n + o, n);
 }
 
-__global__ void __launch_bounds__(kLkwWarps * 32, 5)
+template <int kMinCtas>   // resident CTAs per SM the register allocation aims at (5: 94 registers, no spills; 6: 80, a few spilled words in the set-up)
+__global__ void __launch_bounds__(kLkwWarps * 32, kMinCtas)
     k_lk15w_g(const __grid_constant__ GroupDev g, const TrackJob *__restrict__ jobs, const __grid_constant__ LkParams prm) {
   __shared__ LkArgs sa;
   __shared__ LkwSmem sm[kLkwWarps];
@@ -1192,8 +1215,15 @@ void launch_group_lk(const GroupDev &g, const TrackJob *jobs, int n_jobs, const 
       k_lk15_g<<<dim3(g.pts_cap, n_jobs), std::max(levels, kChainWarps) * 32, 0, s>>>(g, jobs, prm);
       return;
     }
-    PLVIWO_CARVEOUT(k_lk15w_g);
-    k_lk15w_g<<<dim3((g.pts_cap + kLkwWarps - 1) / kLkwWarps, n_jobs), kLkwWarps * 32, 0, s>>>(g, jobs, prm);
+    static const int occ = [] { const char *e = std::getenv("PLVIWO_LK_OCC"); return e ? std::atoi(e) : 5; }();
+    const dim3 grid((g.pts_cap + kLkwWarps - 1) / kLkwWarps, n_jobs);
+    if (occ >= 6) {
+      PLVIWO_CARVEOUT(k_lk15w_g<6>);
+      k_lk15w_g<6><<<grid, kLkwWarps * 32, 0, s>>>(g, jobs, prm);
+    } else {
+      PLVIWO_CARVEOUT(k_lk15w_g<5>);
+      k_lk15w_g<5><<<grid, kLkwWarps * 32, 0, s>>>(g, jobs, prm);
+    }
     return;
   }
   const int win = prm.win, np = win + 3, nd = win + 1, nw = win * win;
