@@ -99,26 +99,57 @@ __device__ __forceinline__ void sm_union(int *lab, int a, int b) {
 
 struct CclTileSmem {
   unsigned bits[kTileH][2];
+  int pref[kTileH * 2 + 1];      // exclusive prefix of the words' population counts
   int lab[kTilePx];
   int a_cnt[kTilePx], a_ymax[kTilePx], a_xmin[kTilePx], a_xmax[kTilePx];
 };
 
 // Labels one 64 x 16 tile whose edge bits are in sm.bits (block-wide call, kTileThreads threads, bits visible to all).
+// The work is per EDGE pixel and edge pixels are a fraction of the tile, so they are enumerated densely: thread t takes the
+// t-th, (t + 256)-th ... set bit of the tile's 32 words (prefix of the population counts, then the n-th set bit of the word) —
+// every lane of a warp has a pixel in hand in every step instead of one lane in four.  The result does not depend on the
+// order the pixels are processed in (roots are minima, aggregates are sums / minima / maxima).
 __device__ __forceinline__ void ccl_tile_body(const FldBuffers &fb, CclTileSmem &sm, int x0, int y0, int w, int h) {
   int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt, *__restrict__ bbox = fb.bbox /* maxy, minx, maxx planes */;
   auto &bits = sm.bits;
   int *lab = sm.lab, *a_cnt = sm.a_cnt, *a_ymax = sm.a_ymax, *a_xmin = sm.a_xmin, *a_xmax = sm.a_xmax;
   const int tid = threadIdx.x;
-  auto edge = [&](int lx, int ly) -> bool { return (bits[ly][lx >> 5] >> (lx & 31)) & 1u; };
-  // thread t owns the 4 pixels (4 (t % 16) .., t / 16)
-  const int ly = tid >> 4, lx0 = (tid & 15) << 2;
-  const unsigned nib = (bits[ly][lx0 >> 5] >> (lx0 & 31)) & 15u;
-  if (!__syncthreads_or((int)nib)) return;   // no edge pixel in this tile
-  // only edge pixels are ever looked at below (neighbours are tested on the bit map first): nothing to set up elsewhere
+  const unsigned *flat = &bits[0][0];   // word f = row f / 2, half f % 2: pixel index = 32 f + bit
+  if (tid < 32) {
+    const int c = __popc(flat[tid]);
+    int incl = c;
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    if (!((nib >> k) & 1u)) continue;
-    const int p = ly * kTileW + lx0 + k;
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (tid >= d) incl += t;
+    }
+    sm.pref[tid] = incl - c;
+    if (tid == 31) sm.pref[32] = incl;
+  }
+  __syncthreads();
+  const int total = sm.pref[32];
+  if (total == 0) return;   // no edge pixel in this tile
+  auto edge = [&](int lx, int ly) -> bool { return (bits[ly][lx >> 5] >> (lx & 31)) & 1u; };
+  constexpr int kMaxPer = kTilePx / kTileThreads;   // 4
+  int px[kMaxPer];
+#pragma unroll
+  for (int k = 0; k < kMaxPer; k++) {
+    const int e = tid + k * kTileThreads;
+    px[k] = -1;
+    if (e < total) {
+      int f = 0;   // largest f with pref[f] <= e
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1)
+        if (sm.pref[f + step] <= e) f += step;
+      unsigned m = flat[f];
+      for (int r = e - sm.pref[f]; r > 0; r--) m &= m - 1;   // drop the r lowest set bits
+      px[k] = 32 * f + __ffs((int)m) - 1;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxPer; k++) {
+    const int p = px[k];
+    if (p < 0) continue;
     lab[p] = p;
     a_cnt[p] = 0;
     a_ymax[p] = 0;
@@ -130,9 +161,10 @@ __device__ __forceinline__ void ccl_tile_body(const FldBuffers &fb, CclTileSmem 
   // merged with it when THEY are processed), so a set N needs one union; otherwise W (or, without W, NW — W's own N) and NE
   // are independent.
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    if (!((nib >> k) & 1u)) continue;
-    const int lx = lx0 + k, p = ly * kTileW + lx;
+  for (int k = 0; k < kMaxPer; k++) {
+    const int p = px[k];
+    if (p < 0) continue;
+    const int ly = p >> 6, lx = p & (kTileW - 1);
     const bool eW = lx > 0 && edge(lx - 1, ly);
     if (ly > 0) {
       if (edge(lx, ly - 1)) {
@@ -147,26 +179,27 @@ __device__ __forceinline__ void ccl_tile_body(const FldBuffers &fb, CclTileSmem 
     }
   }
   __syncthreads();
-  int root[4];
+  int root[kMaxPer];
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
+  for (int k = 0; k < kMaxPer; k++) {
     root[k] = -1;
-    if ((nib >> k) & 1u) {
-      const int lx = lx0 + k;
-      const int r = sm_find(lab, ly * kTileW + lx);
-      root[k] = r;
-      atomicAdd(&a_cnt[r], 1);
-      atomicMax(&a_ymax[r], ly);
-      atomicMin(&a_xmin[r], lx);
-      atomicMax(&a_xmax[r], lx);
-    }
+    const int p = px[k];
+    if (p < 0) continue;
+    const int ly = p >> 6, lx = p & (kTileW - 1);
+    const int r = sm_find(lab, p);
+    root[k] = r;
+    atomicAdd(&a_cnt[r], 1);
+    atomicMax(&a_ymax[r], ly);
+    atomicMin(&a_xmin[r], lx);
+    atomicMax(&a_xmax[r], lx);
   }
   __syncthreads();
   const int n = w * h;
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
+  for (int k = 0; k < kMaxPer; k++) {
     if (root[k] < 0) continue;
-    const int lx = lx0 + k, p = ly * kTileW + lx;
+    const int p = px[k];
+    const int ly = p >> 6, lx = p & (kTileW - 1);
     const int gi = (y0 + ly) * w + x0 + lx;
     const int r = root[k];
     label[gi] = (y0 + (r >> 6)) * w + x0 + (r & (kTileW - 1));

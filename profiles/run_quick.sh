@@ -7,5 +7,4 @@ try:
     d=json.loads(open('gpurun_out/q_$tag.json').read()); print('$tag', round(d['value']), round(d['e2e']['value']), {k: round(v['avg_ms']*1000) for k,v in d['roofline'].get('per_kernel',{}).items()}, d['roofline'].get('fast_cells_per_frame'))
 except Exception as e: print('$tag', 'ERR', e)"; }
 run s64 PLVIWO_BENCH_STREAMS=64
-run s64_l8 PLVIWO_BENCH_STREAMS=64 PLVIWO_GROUP_LANES=8
 run s8 PLVIWO_BENCH_STREAMS=8
