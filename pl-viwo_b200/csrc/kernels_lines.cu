@@ -239,8 +239,8 @@ __global__ void __launch_bounds__(kTileThreads)
 template <class B>
 __global__ void k_ccl_reset(const __grid_constant__ B b) {
   const FldBuffers &fb = b.fld_of(blockIdx.x);
-  if (threadIdx.x < 8) fb.counters[threadIdx.x] = 0;
-  if (threadIdx.x == 8) *fb.lroot_n = 0;
+  if (threadIdx.x < 12) fb.counters[threadIdx.x] = 0;
+  if (threadIdx.x == 12) *fb.lroot_n = 0;
 }
 
 // ------------------------------------------------------------------------------------------------ Canny
@@ -420,18 +420,23 @@ __global__ void k_ccl_link(const __grid_constant__ B b, int w, int h) {
 //   BIG    the private bit map (bounding box rounded to 32-pixel words, plus padding) does not fit a warp's slice of the
 //          walk kernel's shared-memory arena: a whole CTA gathers it and one warp walks it, these go first (they are also
 //          the long ones: a walk is sequential and the longest component is the critical path of the launch);
-//   B, C   everything else, >= 128 pixels first: one WARP per component, the warps of a CTA work side by side.
-constexpr int kClassB = 128;            // pixels
+//   W      fits a slice but not class T: one WARP per component, the warps of a CTA work side by side;
+//   T      the bounding box is at most 62 x 44 pixels — nine components in ten, a third of the walked pixels: one THREAD per
+//          component (k_fld_walk_thread), the bit map is one 64-bit word per row.  A warp instruction costs an issue slot
+//          whether one lane or 32 have a pixel in hand: here 32 components advance per instruction instead of one.
 constexpr int kPadRows = 2;             // zero rows above and below the private bit map (the walk looks 2 pixels ahead)
 constexpr int kWalkThreads = 128;
 constexpr int kWalkWarps = kWalkThreads / 32;
 constexpr int kSliceWords = 1600;       // per-warp bit map slice (6.25 KB): e.g. 128 x 224 or 640 x 68 pixels of bounding box
-__host__ __device__ inline int comp_cap_b(int n) { return n / kClassB + 1; }
-// a BIG component spans > kSliceWords words, i.e. at least ~280 pixels in a row or column direction: at most n / kClassB of them
-__host__ __device__ inline int comp_cap_big(int n) { return n / kClassB + 1; }
+constexpr int kTMaxW = 62, kTMaxH = 44; // class T bounding box
+constexpr int kTRows = kTMaxH + 2;      // rows of a thread's bit map (one zero row above and below)
+constexpr int kTLanes = 64;             // threads per CTA of the thread-walk kernel
+// a BIG component spans > kSliceWords words, i.e. at least ~280 pixels in a row or column direction: at most n / 128 of them
+__host__ __device__ inline int comp_cap_big(int n) { return n / 128 + 1; }
+// comp_root: [0, comp_cap_big) BIG, then max_chains entries of class W, then max_chains entries of class T
 
-// counters: [0] BIG components, [1] BIG cursor, [2] chain-point cursor, [3] chains, [4] segments, [5] class-B components,
-//           [6] class-C components, [7] cursor over B then C
+// counters: [0] BIG components, [1] BIG cursor, [2] chain-point cursor, [3] chains, [4] segments, [5] class-W components,
+//           [6] class-T components, [7] class-W cursor, [8] class-T cursor
 template <class B>
 __global__ void k_ccl_roots(const __grid_constant__ B b, int w, int h, int min_pixels) {   // one thread per tile-local root
   const FldBuffers &fb = b.fld_of(blockIdx.y);
@@ -447,15 +452,16 @@ __global__ void k_ccl_roots(const __grid_constant__ B b, int w, int h, int min_p
     if (c < min_pixels) continue;
     const int bh = bbox[i] - i / w + 1;
     const int groups = (bbox[2 * n + i] >> 5) - (bbox[n + i] >> 5) + 1;
-    const bool big = (bh + 2 * kPadRows) * (groups + 2) > kSliceWords;
-    if (big) {
+    const int bw = bbox[2 * n + i] - bbox[n + i] + 1;
+    if (bw <= kTMaxW && bh <= kTMaxH) {
+      const int q = atomicAdd(counters + 6, 1);
+      if (q < max_comps) comp_root[comp_cap_big(n) + max_comps + q] = i;
+    } else if ((bh + 2 * kPadRows) * (groups + 2) > kSliceWords) {
       const int q = atomicAdd(counters + 0, 1);
       if (q < comp_cap_big(n)) comp_root[q] = i;
-    } else if (c >= kClassB) {
-      comp_root[comp_cap_big(n) + atomicAdd(counters + 5, 1)] = i;                 // at most n / kClassB
     } else {
-      const int q = atomicAdd(counters + 6, 1);
-      if (q < max_comps) comp_root[comp_cap_big(n) + comp_cap_b(n) + q] = i;
+      const int q = atomicAdd(counters + 5, 1);
+      if (q < max_comps) comp_root[comp_cap_big(n) + q] = i;
     }
   }
 }
@@ -735,8 +741,7 @@ __global__ void __launch_bounds__(kWalkThreads)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = c.n;
   const int nBig = min(c.counters[0], comp_cap_big(n));
-  const int nB = min(c.counters[5], comp_cap_b(n)), nC = min(c.counters[6], c.max_chains);
-  const int nSmall = nB + nC;
+  const int nSmall = min(c.counters[5], c.max_chains);   // class W
   // a CTA that can get neither a BIG component nor (as one of its warps) a small one has nothing to do
   if ((int)blockIdx.x >= nBig && (int)blockIdx.x * kWalkWarps >= nSmall) return;
   for (int i = tid; i < kLutSize / 4; i += kWalkThreads)
@@ -766,7 +771,7 @@ __global__ void __launch_bounds__(kWalkThreads)
     if (lane == 0) q = atomicAdd(c.counters + 7, 1);
     q = __shfl_sync(0xffffffffu, q, 0);
     if (q >= nSmall) break;
-    const int root = comp_root[q < nB ? comp_cap_big(n) + q : comp_cap_big(n) + comp_cap_b(n) + (q - nB)];
+    const int root = comp_root[comp_cap_big(n) + q];
     const int y0 = root / w, y1 = c.bbox[root];
     const int g0 = c.bbox[n + root] >> 5, g1 = c.bbox[2 * n + root] >> 5;
     const int groups = g1 - g0 + 1, bh = y1 - y0 + 1, ws = groups + 2;
@@ -776,6 +781,117 @@ __global__ void __launch_bounds__(kWalkThreads)
     __syncwarp();
     walk_component(c, bm, lut_addr, root, y0, g0, groups, bh, ws, lane);
     __syncwarp();
+  }
+}
+
+// Class T: one thread per component.  The component's bit map is one 64-bit word per row (bit b of row r = pixel
+// (xmin - 1 + b, y0 - 1 + r): a zero column on either side, a zero row above and below), rows of the CTA's threads interleaved in
+// shared memory.  The step is getPointChain through the same two tables as the warp walk — 3 x 3 neighbourhood -> key ->
+// decision, (step, direction, neighbour) -> direction — on three row words, so the chains are the same; seeds are the lowest set
+// bit of the first non-empty row (raster order).  No ballots, no warp synchronisation: a lane's walk touches only its own words.
+template <class B>
+__global__ void __launch_bounds__(kTLanes)
+    k_fld_walk_thread(const __grid_constant__ B b, int w, int h, int length_threshold) {
+  const FldBuffers &fb = b.fld_of(blockIdx.y);
+  const unsigned *__restrict__ edges = fb.edges;
+  const int words_per_row = fb.words_per_row;
+  const int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt, *__restrict__ bbox = fb.bbox;
+  int *__restrict__ counters = fb.counters;
+  int2 *__restrict__ chain_pts = fb.chain_pts;
+  const int max_chains = fb.max_chains;
+  const int n = w * h;
+  __shared__ __align__(16) uint8_t lut[kLutSize];
+  __shared__ unsigned long long bm[kTRows * kTLanes];
+  const int tid = threadIdx.x;
+  const int nT = min(counters[6], max_chains);
+  if ((int)blockIdx.x * kTLanes >= nT) return;   // more walkers than components
+  for (int i = tid; i < kLutSize / 4; i += kTLanes) reinterpret_cast<unsigned *>(lut)[i] = reinterpret_cast<const unsigned *>(g_walk_lut)[i];
+  __syncthreads();
+  const int *__restrict__ queue = fb.comp_root + comp_cap_big(n) + max_chains;
+  unsigned long long *row = bm + tid;   // row r of this thread: row[r * kTLanes]
+  while (true) {
+    const int q = atomicAdd(counters + 8, 1);
+    if (q >= nT) break;
+    const int root = queue[q];
+    const int y0 = root / w, y1 = bbox[root], xmin = bbox[n + root], xmax = bbox[2 * n + root];
+    const int bh = y1 - y0 + 1, bw = xmax - xmin + 1;
+    // ---- gather: the component's pixels of every row of the bounding box (edge bits whose label leads to this root)
+    row[0] = 0ull;
+    row[(bh + 1) * kTLanes] = 0ull;
+    const int w0 = xmin >> 5, sh = xmin & 31;
+    const unsigned long long wmask = (bw >= 64 ? ~0ull : ((1ull << bw) - 1ull));
+    for (int r = 0; r < bh; r++) {
+      const unsigned *er = edges + (size_t)(y0 + r) * words_per_row;
+      const unsigned e0 = er[w0], e1 = w0 + 1 < words_per_row ? er[w0 + 1] : 0u, e2 = w0 + 2 < words_per_row ? er[w0 + 2] : 0u;
+      unsigned long long v = ((unsigned long long)e0 | ((unsigned long long)e1 << 32)) >> sh;
+      if (sh) v |= (unsigned long long)e2 << (64 - sh);
+      v &= wmask;
+      unsigned long long mine = 0ull;
+      const int base = (y0 + r) * w + xmin;
+      while (v) {
+        const int bpos = __ffsll((long long)v) - 1;
+        v &= v - 1;
+        int l = label[base + bpos];
+        if (l != root) l = label[l];   // tile-local root -> global root
+        if (l == root) mine |= 1ull << bpos;
+      }
+      row[(r + 1) * kTLanes] = mine << 1;
+    }
+    // ---- walk
+    int npts = atomicAdd(counters + 2, cnt[root]);   // this component's slice of the chain-point pool
+    const int xorg = xmin - 1, yorg = y0 - 1;
+    int sy = 1;
+    bool in_chain = false;
+    int cy = 0, cx = 0, start = 0, seed = 0, step = 0;
+    unsigned dsel = 0;
+    const uint8_t *tb = lut;
+    while (true) {
+      if (!in_chain) {
+        if (sy > bh) break;
+        const unsigned long long R = row[sy * kTLanes];
+        if (R == 0ull) {
+          sy++;
+          continue;
+        }
+        cx = __ffsll((long long)R) - 1;
+        cy = sy;
+        row[sy * kTLanes] = R & ~(1ull << cx);   // the seed is consumed
+        start = npts;
+        seed = (yorg + cy) * w + xorg + cx;
+        step = 0;
+        dsel = 0;
+        tb = lut + kKeys * 8;   // first-step half of the table
+        in_chain = true;
+      }
+      chain_pts[npts++] = make_int2(xorg + cx, yorg + cy);
+      const unsigned long long Ra = row[(cy - 1) * kTLanes], Rc = row[cy * kTLanes], Rb = row[(cy + 1) * kTLanes];
+      const unsigned t3 = (unsigned)(Ra >> (cx - 1)) & 7u, c3 = (unsigned)(Rc >> (cx - 1)) & 7u, b3 = (unsigned)(Rb >> (cx - 1)) & 7u;
+      const unsigned key = t3 | ((c3 & 1u) << 3) | ((c3 >> 2) << 4) | (b3 << 5);
+      const unsigned e = tb[key * 8u + dsel];
+      const unsigned i = e & 15u;
+      if (i == 8u) {   // the chain ends here
+        if (npts - start < length_threshold + 1) {
+          npts = start;   // too short: dropped (its pixels stay consumed)
+        } else {
+          const int k = atomicAdd(counters + 3, 1);
+          if (k < max_chains) {
+            fb.chain_seed[k] = seed;
+            fb.chain_off[k] = start;
+            fb.chain_len[k] = npts - start;
+          }
+        }
+        in_chain = false;
+        continue;
+      }
+      dsel = lut[kLut1 + ((unsigned)min(step, 7) * 8u + dsel) * 8u + i];
+      step++;
+      tb = lut;
+      const int dr = (int)((e >> 4) & 3u) - 1, dc = (int)((e >> 6) & 3u) - 1;
+      cy += dr;
+      cx += dc;
+      const unsigned long long Rn = dr < 0 ? Ra : (dr > 0 ? Rb : Rc);
+      row[cy * kTLanes] = Rn & ~(1ull << cx);   // the new pixel is consumed
+    }
   }
 }
 
@@ -991,8 +1107,8 @@ int FldBuffers::alloc(int w, int h, int length_threshold, int out_capacity) {
   A(&label, (n + 32) * sizeof(int));   // slack: the walk gathers labels with 16-byte loads
   A(&cnt, n * sizeof(int));
   A(&bbox, 3 * n * sizeof(int));
-  A(&comp_root, (size_t)(max_chains + comp_cap_big((int)n) + comp_cap_b((int)n)) * sizeof(int));
-  A(&counters, 8 * sizeof(int));
+  A(&comp_root, (size_t)(2 * max_chains + comp_cap_big((int)n)) * sizeof(int));
+  A(&counters, 12 * sizeof(int));
   lroot_cap = (int)(n / 4 + 1);
   A(&lroots, (size_t)lroot_cap * sizeof(int));
   A(&lroot_n, sizeof(int));
@@ -1004,7 +1120,7 @@ int FldBuffers::alloc(int w, int h, int length_threshold, int out_capacity) {
   A(&segs, (n / kSegsPerChainDiv + 2) * sizeof(float4));
   A(&seg_cnt, (size_t)2 * max_chains * sizeof(int));
   A(&out, (size_t)out_cap * sizeof(float4));
-  if (ok) ok = cudaMemset(counters, 0, 8 * sizeof(int)) == cudaSuccess;
+  if (ok) ok = cudaMemset(counters, 0, 12 * sizeof(int)) == cudaSuccess;
   return ok ? 0 : 1;
 }
 
@@ -1059,6 +1175,10 @@ static void launch_fld_any(const B &b, int nb_frames, int w, int h, int max_chai
   // pipeline — other streams, other ticks — stay resident beside them; the walk's WORK is small, its duration is the
   // latency of the longest component either way.
   const int walk_ctas = walk_ctas_env > 0 ? walk_ctas_env : (nb_frames > 1 ? std::max(2, std::min(74, 256 / nb_frames)) : 148);
+  // class T first: a short launch (its longest component has a few hundred pixels), one thread per component
+  const int walk_t = nb_frames > 1 ? 4 : 32;   // CTAs of kTLanes threads per frame (about 250 class-T components per frame)
+  PLVIWO_CARVEOUT(k_fld_walk_thread<B>);
+  k_fld_walk_thread<B><<<dim3(walk_t, nb_frames), kTLanes, 0, s>>>(b, w, h, length_threshold);
   PLVIWO_CARVEOUT(k_fld_walk_cc<B>);
   k_fld_walk_cc<B><<<dim3(walk_ctas, nb_frames), kWalkThreads, smem, s>>>(b, w, h, length_threshold);
   if (ev) cudaEventRecord(ev[1], s);
