@@ -678,7 +678,7 @@ int FeContext::flush_line_batch() {
     s.line_pending = false;
   }
   FE_CUDA(cudaGetLastError());
-  mst_.kernel_launches_total += 12 + n;   // canny, 5 x components, 2 x walk, order, segments, compact + one signal per frame
+  mst_.kernel_launches_total += 11 + n + (n >= 16 ? 1 : 0);   // canny, 5 x components, walk (+ thread walk for a large batch), order, segments, compact + one signal per frame
   pending_lines_.clear();
   return FE_OK;
 }

@@ -595,7 +595,7 @@ int FeGroup::launch_front(FrontBatch &b, int buf) {
     }
     launch_fld_table(d_slots_, dl, nl, W_ / 2, H_ / 2, s0.fld.max_chains, cfg_.fld_length_threshold, cfg_.fld_distance_threshold, st,
                      (tm || trace_) ? ev2 : nullptr);
-    launches_ += 8;
+    launches_ += 7 + (nl >= 16 ? 1 : 0);
     if (tm) {
       cudaEvent_t e1 = mark();
       account(FE_GK_CCL, e0, ev2[0], nl);

@@ -438,7 +438,7 @@ __host__ __device__ inline int comp_cap_big(int n) { return n / 128 + 1; }
 // counters: [0] BIG components, [1] BIG cursor, [2] chain-point cursor, [3] chains, [4] segments, [5] class-W components,
 //           [6] class-T components, [7] class-W cursor, [8] class-T cursor
 template <class B>
-__global__ void k_ccl_roots(const __grid_constant__ B b, int w, int h, int min_pixels) {   // one thread per tile-local root
+__global__ void k_ccl_roots(const __grid_constant__ B b, int w, int h, int min_pixels, int thread_class) {   // strides over the tile-local roots
   const FldBuffers &fb = b.fld_of(blockIdx.y);
   const int *__restrict__ label = fb.label, *__restrict__ cnt = fb.cnt, *__restrict__ bbox = fb.bbox;
   int *__restrict__ comp_root = fb.comp_root, *__restrict__ counters = fb.counters;
@@ -453,7 +453,7 @@ __global__ void k_ccl_roots(const __grid_constant__ B b, int w, int h, int min_p
     const int bh = bbox[i] - i / w + 1;
     const int groups = (bbox[2 * n + i] >> 5) - (bbox[n + i] >> 5) + 1;
     const int bw = bbox[2 * n + i] - bbox[n + i] + 1;
-    if (bw <= kTMaxW && bh <= kTMaxH) {
+    if (thread_class && bw <= kTMaxW && bh <= kTMaxH) {
       const int q = atomicAdd(counters + 6, 1);
       if (q < max_comps) comp_root[comp_cap_big(n) + max_comps + q] = i;
     } else if ((bh + 2 * kPadRows) * (groups + 2) > kSliceWords) {
@@ -710,12 +710,72 @@ __device__ __forceinline__ void walk_component(const WalkCtx &c, unsigned *bm, u
   }
 }
 
+// The same walk by ONE lane of the warp (the others wait at the __syncwarp that follows): no ballots, no warp synchronisation
+// inside the step, about half the instructions per step of the cooperative form (a warp instruction costs an issue slot whether
+// one lane or 25 take part), at a similar latency per step — the step is a chain of dependent shared-memory accesses either
+// way.  The 3 x 3 neighbourhood comes from two adjacent words of each of the three rows (funnel shift), the tables are the
+// cooperative walk's, so are the seeds (raster order) and the consumption order: identical chains.
+__device__ __forceinline__ void walk_component_single(const WalkCtx &c, unsigned *bm, const uint8_t *lut, int root, int y0, int g0,
+                                                      int groups, int bh, int ws) {
+  int npts = atomicAdd(c.counters + 2, c.cnt[root]);   // this component's slice of the chain-point pool
+  const int xbase = (g0 << 5) - 32;                    // global x of bit 0 of a private row
+  int sy = 0, sg = 0;                                  // scan position (row, word): everything before it is consumed
+  while (sy < bh) {
+    const int rbs = (sy + kPadRows) * ws;
+    unsigned wv = 0;
+    while (sg < groups && (wv = bm[rbs + 1 + sg]) == 0u) sg++;
+    if (sg >= groups) {
+      sg = 0;
+      sy++;
+      continue;
+    }
+    int p = ((sg + 1) << 5) + __ffs((int)wv) - 1, cy = sy;
+    int rb = rbs;
+    const int start = npts;
+    const int seed = (y0 + cy) * c.w + xbase + p;
+    int step = 0;
+    unsigned dsel = 0;
+    const uint8_t *tb = lut + kKeys * 8;     // first-step half of the table
+    bm[rb + (p >> 5)] = wv & ~(1u << (p & 31));   // the seed is consumed
+    while (true) {
+      c.chain_pts[npts++] = make_int2(xbase + p, y0 + cy);
+      const int q = p - 1, wi = q >> 5, sh = q & 31;
+      const unsigned *r0 = bm + rb + wi;
+      const unsigned t3 = __funnelshift_r(r0[-ws], r0[-ws + 1], sh) & 7u;
+      const unsigned c3 = __funnelshift_r(r0[0], r0[1], sh) & 7u;
+      const unsigned b3 = __funnelshift_r(r0[ws], r0[ws + 1], sh) & 7u;
+      const unsigned key = t3 | ((c3 & 1u) << 3) | ((c3 >> 2) << 4) | (b3 << 5);
+      const unsigned e = tb[key * 8u + dsel];
+      const unsigned i = e & 15u;
+      if (i == 8u) break;
+      dsel = lut[kLut1 + ((unsigned)min(step, 7) * 8u + dsel) * 8u + i];
+      step++;
+      tb = lut;
+      const int dr = (int)((e >> 4) & 3u) - 1, dc = (int)((e >> 6) & 3u) - 1;
+      p += dc;
+      cy += dr;
+      rb += dr * ws;
+      bm[rb + (p >> 5)] &= ~(1u << (p & 31));   // the new pixel is consumed
+    }
+    if (npts - start < c.length_threshold + 1) {
+      npts = start;  // chain too short: dropped (its pixels stay consumed)
+    } else {
+      const int k = atomicAdd(c.counters + 3, 1);
+      if (k < c.max_chains) {
+        c.chain_seed[k] = seed;
+        c.chain_off[k] = start;
+        c.chain_len[k] = npts - start;
+      }
+    }
+  }
+}
+
 // grid = (walkers, frame).  Phase 1: the CTA takes BIG components one at a time (all warps gather into the whole arena,
 // warp 0 walks).  Phase 2: every warp takes components of its own from the common queue (B then C) and works in its slice
 // of the arena; no block-wide synchronisation any more.
 template <class B>
 __global__ void __launch_bounds__(kWalkThreads)
-    k_fld_walk_cc(const __grid_constant__ B b, int w, int h, int length_threshold) {
+    k_fld_walk_cc(const __grid_constant__ B b, int w, int h, int length_threshold, int coop) {
   const FldBuffers &fb = b.fld_of(blockIdx.y);
   WalkCtx c;
   c.edges = fb.edges;
@@ -762,7 +822,10 @@ __global__ void __launch_bounds__(kWalkThreads)
     __syncthreads();
     walk_gather(c, arena, root, y0, g0, groups, bh, ws, warp, kWalkWarps, lane);
     __syncthreads();
-    if (warp == 0) walk_component(c, arena, lut_addr, root, y0, g0, groups, bh, ws, lane);
+    if (warp == 0) {
+      if (coop) walk_component(c, arena, lut_addr, root, y0, g0, groups, bh, ws, lane);
+      else if (lane == 0) walk_component_single(c, arena, lut, root, y0, g0, groups, bh, ws);
+    }
   }
   // ---- phase 2
   unsigned *bm = arena + warp * kSliceWords;
@@ -779,7 +842,8 @@ __global__ void __launch_bounds__(kWalkThreads)
     __syncwarp();
     walk_gather(c, bm, root, y0, g0, groups, bh, ws, 0, 1, lane);
     __syncwarp();
-    walk_component(c, bm, lut_addr, root, y0, g0, groups, bh, ws, lane);
+    if (coop) walk_component(c, bm, lut_addr, root, y0, g0, groups, bh, ws, lane);
+    else if (lane == 0) walk_component_single(c, bm, lut, root, y0, g0, groups, bh, ws);
     __syncwarp();
   }
 }
@@ -1156,7 +1220,12 @@ static void launch_fld_any(const B &b, int nb_frames, int w, int h, int max_chai
   PLVIWO_CARVEOUT(k_ccl_link<B>);
   k_ccl_link<B><<<dim3(root_ctas, nb_frames), tpb, 0, s>>>(b, w, h);
   PLVIWO_CARVEOUT(k_ccl_roots<B>);
-  k_ccl_roots<B><<<dim3(root_ctas, nb_frames), tpb, 0, s>>>(b, w, h, length_threshold + 1);
+  // class T (one thread per small component, a launch of its own ahead of the warp walk) pays when launches carry many frames
+  // (a stream group: 32-256 per launch); one frame, or the few frames a single handle batches, are about latency — there
+  // everything that is not BIG goes to the warps of the one walk launch (measured: one pipelined stream 12.7 k frames/s
+  // without the extra launch, 11.6 k with it)
+  const int thread_class = nb_frames >= 16 ? 1 : 0;
+  k_ccl_roots<B><<<dim3(root_ctas, nb_frames), tpb, 0, s>>>(b, w, h, length_threshold + 1, thread_class);
   if (ev) cudaEventRecord(ev[0], s);
   init_fld_constants();
   const int ws = ((w + 31) >> 5) + 2;
@@ -1176,11 +1245,17 @@ static void launch_fld_any(const B &b, int nb_frames, int w, int h, int max_chai
   // latency of the longest component either way.
   const int walk_ctas = walk_ctas_env > 0 ? walk_ctas_env : (nb_frames > 1 ? std::max(2, std::min(74, 256 / nb_frames)) : 148);
   // class T first: a short launch (its longest component has a few hundred pixels), one thread per component
-  const int walk_t = nb_frames > 1 ? 4 : 32;   // CTAs of kTLanes threads per frame (about 250 class-T components per frame)
-  PLVIWO_CARVEOUT(k_fld_walk_thread<B>);
-  k_fld_walk_thread<B><<<dim3(walk_t, nb_frames), kTLanes, 0, s>>>(b, w, h, length_threshold);
+  const int walk_t = 4;   // CTAs of kTLanes threads per frame (about 250 class-T components per frame)
+  if (thread_class) {
+    PLVIWO_CARVEOUT(k_fld_walk_thread<B>);
+    k_fld_walk_thread<B><<<dim3(walk_t, nb_frames), kTLanes, 0, s>>>(b, w, h, length_threshold);
+  }
   PLVIWO_CARVEOUT(k_fld_walk_cc<B>);
-  k_fld_walk_cc<B><<<dim3(walk_ctas, nb_frames), kWalkThreads, smem, s>>>(b, w, h, length_threshold);
+  // PLVIWO_WALK_SINGLE=1: the single-lane step instead of the warp-cooperative one (25 lanes fetch the 5 x 5 window).  Same
+  // chains, same throughput in the 64-stream pipeline (55.3 k vs 55.4 k frames/s) and the same launch duration: the step is a
+  // chain of dependent shared-memory accesses either way.  The cooperative form is the one compute-sanitizer has seen.
+  static const int coop = [] { const char *e = std::getenv("PLVIWO_WALK_SINGLE"); return (e && std::atoi(e)) ? 0 : 1; }();
+  k_fld_walk_cc<B><<<dim3(walk_ctas, nb_frames), kWalkThreads, smem, s>>>(b, w, h, length_threshold, coop);
   if (ev) cudaEventRecord(ev[1], s);
   PLVIWO_CARVEOUT(k_fld_order<B>);
   k_fld_order<B><<<dim3((max_chains + 127) / 128, nb_frames), 128, 0, s>>>(b);
