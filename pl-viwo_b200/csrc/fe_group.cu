@@ -5,6 +5,7 @@
 #include "fe_group.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -312,6 +313,9 @@ FeGroup::~FeGroup() {
     std::fprintf(stderr, "[plviwo group trace] stages of a front batch, ms: equalise + pyramid %.3f, Canny + tiles %.3f, components %.3f, walk %.3f, "
                  "segments %.3f\n", tr_stage_ms_[0] / tr_n_, tr_stage_ms_[1] / tr_n_, tr_stage_ms_[2] / tr_n_, tr_stage_ms_[3] / tr_n_,
                  tr_stage_ms_[4] / tr_n_);
+  if (trace_ && tr_host_ticks_ > 0)
+    std::fprintf(stderr, "[plviwo group trace] host per tick, us: submit %.1f (of which issuing frame copies %.1f), waiting in collect %.1f\n",
+                 tr_host_submit_us_ / tr_host_ticks_, tr_host_copy_us_ / tr_host_ticks_, tr_host_wait_us_ / tr_host_ticks_);
   for (auto e : ev_tr0_) cudaEventDestroy(e);
   for (auto e : ev_tr1_) cudaEventDestroy(e);
   for (auto e : ev_trs_) cudaEventDestroy(e);
@@ -401,6 +405,8 @@ FeGroupTimes FeGroup::times(bool reset) {
 int FeGroup::submit(const double *timestamps, const uint8_t *const *images, int stride, bool on_device, const uint8_t *const *masks,
                     int mask_stride, const double *vps) {
   FG_CUDA(cudaSetDevice(device_));
+  const auto t_sub0 = std::chrono::steady_clock::now();
+  double copy_us = 0;
   if (!timestamps || !images || stride < W_) return err(FE_BAD_ARG, "submit: bad arguments");
   if (submitted_ - collected_ > la_) return err(FE_BAD_ARG, "submit: lookahead window full (collect a tick first)");
   const long long tick = submitted_;
@@ -447,10 +453,12 @@ int FeGroup::submit(const double *timestamps, const uint8_t *const *images, int 
       }
       // a tight frame into a tight staging image is ONE contiguous transfer (a 2-D copy is issued row by row: 1280-byte
       // rows reach less than half of the link's bandwidth)
+      const auto t_c0 = std::chrono::steady_clock::now();
       cudaStream_t cs = s_copy_[copy_rr_++ % s_copy_.size()];
       if (sstride == W_ && sl.raw.pitch == W_) FG_CUDA(cudaMemcpyAsync(sl.raw.p, src, (size_t)W_ * H_, cudaMemcpyHostToDevice, cs));
       else FG_CUDA(cudaMemcpy2DAsync(sl.raw.p, sl.raw.pitch, src, sstride, W_, H_, cudaMemcpyHostToDevice, cs));
       h2d_bytes_ += (size_t)W_ * H_;
+      if (trace_) copy_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_c0).count();
       fj.src = sl.raw.p;
       fj.src_pitch = sl.raw.pitch;
     }
@@ -490,8 +498,14 @@ int FeGroup::submit(const double *timestamps, const uint8_t *const *images, int 
     if (tr.cur_slot[s] < 0) std::memset(h_out_ + (size_t)(ring * S_ + s) * g_.out_stride, 0, sizeof(GroupOutHeader));
   b.ticks.push_back((int)tick);
   submitted_++;
-  if ((int)b.ticks.size() >= B_) return flush_front();
-  return FE_OK;
+  int rc_flush = FE_OK;
+  if ((int)b.ticks.size() >= B_) rc_flush = flush_front();
+  if (trace_) {
+    tr_host_copy_us_ += copy_us;
+    tr_host_submit_us_ += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_sub0).count();
+    tr_host_ticks_++;
+  }
+  return rc_flush;
 }
 
 int FeGroup::flush_front() {
@@ -705,7 +719,9 @@ int FeGroup::collect(FeFrameInfo *infos) {
     int rc = flush_front();
     if (rc) return rc;
   }
+  const auto t_w0 = std::chrono::steady_clock::now();
   for (int l = 0; l < lanes_; l++) FG_CUDA(cudaEventSynchronize(ev_done_[(size_t)ring * lanes_ + l]));
+  if (trace_) tr_host_wait_us_ += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_w0).count();
   collected_++;
   last_collected_ = tick;
   int status = FE_OK;

@@ -105,6 +105,8 @@ class FeGroup {
   bool trace_ = false;
   std::vector<cudaEvent_t> ev_tr0_, ev_tr1_, ev_trs_;   // ev_trs_: 4 per batch (after the pyramid, Canny + tiles, components, walk)
   double tr_stage_ms_[5] = {0, 0, 0, 0, 0};
+  double tr_host_copy_us_ = 0, tr_host_submit_us_ = 0, tr_host_wait_us_ = 0;   // host time: issuing the frame copies, the whole of submit, waiting in collect
+  long tr_host_ticks_ = 0;
   std::vector<char> tr_valid_;
   int tr_prev_ = -1;
   double tr_lat_ms_ = 0, tr_period_ms_ = 0, tr_lane_ms_ = 0;
