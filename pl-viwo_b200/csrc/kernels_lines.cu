@@ -1224,7 +1224,9 @@ static void launch_fld_any(const B &b, int nb_frames, int w, int h, int max_chai
   // (a stream group: 32-256 per launch); one frame, or the few frames a single handle batches, are about latency — there
   // everything that is not BIG goes to the warps of the one walk launch (measured: one pipelined stream 12.7 k frames/s
   // without the extra launch, 11.6 k with it)
-  const int thread_class = nb_frames >= 16 ? 1 : 0;
+  // PLVIWO_WALK_THREAD_MIN = frames per launch from which class T is used (read at every launch: the tests switch it)
+  const char *tmin_env = std::getenv("PLVIWO_WALK_THREAD_MIN");
+  const int thread_class = nb_frames >= (tmin_env ? std::max(1, std::atoi(tmin_env)) : 16) ? 1 : 0;
   k_ccl_roots<B><<<dim3(root_ctas, nb_frames), tpb, 0, s>>>(b, w, h, length_threshold + 1, thread_class);
   if (ev) cudaEventRecord(ev[0], s);
   init_fld_constants();

@@ -133,9 +133,15 @@ def test_group_masks_clahe_partial_ticks_and_reset(fe, synth):
     g.close()
 
 
-def test_group_teacher_forced_against_oracle(fe, synth):
+@pytest.mark.parametrize("thread_walk", [False, True])
+def test_group_teacher_forced_against_oracle(fe, synth, thread_walk, monkeypatch):
     """Every frame of every stream on the oracle's state (plviwo_fe_group_set_state): ids and row order bit-exact, UVs
-    within 0.05 px, status flags >= 99.5 %, line ids / point-on-line sets identical."""
+    within 0.05 px, status flags >= 99.5 %, line ids / point-on-line sets identical.  thread_walk: the chain walk's
+    thread-per-component class, which a group otherwise uses from 16 frames per launch on (the 64-stream bench)."""
+    if thread_walk:
+        monkeypatch.setenv("PLVIWO_WALK_THREAD_MIN", "1")
+    else:
+        monkeypatch.delenv("PLVIWO_WALK_THREAD_MIN", raising=False)
     W, H, n_frames, S = 1280, 560, 12, 2
     seqs = [synth.SynthSequence(seed=1030 + s, width=W, height=H, n_frames=n_frames) for s in range(S)]
     oracles = [ofe.FrontEnd(ofe.FeConfig(K=q.K, D=q.D, **CFG2)) for q in seqs]

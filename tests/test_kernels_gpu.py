@@ -106,10 +106,16 @@ def test_canny_bit_exact(fe, synth):
         assert np.array_equal(got, ref), "%s: %d pixels differ" % (name, int((got != ref).sum()))
 
 
-def test_fld_vs_restatement(fe, synth):
+@pytest.mark.parametrize("thread_walk", [False, True])
+def test_fld_vs_restatement(fe, synth, thread_walk, monkeypatch):
     """The line extractor has no executable reference (opencv_contrib absent): compared with the oracle's C++
     restatement.  Transcendental rounding (atan2/cos/sin) differs between device and host libm, so endpoints are
-    compared to 1e-3 px and segment counts must be equal."""
+    compared to 1e-3 px and segment counts must be equal.  thread_walk: the components whose bounding box fits 62 x 44 pixels
+    are walked by one thread each (k_fld_walk_thread; by default only launches that carry >= 16 frames do that)."""
+    if thread_walk:
+        monkeypatch.setenv("PLVIWO_WALK_THREAD_MIN", "1")
+    else:
+        monkeypatch.delenv("PLVIWO_WALK_THREAD_MIN", raising=False)
     for lh in (False, True):
         seq = synth.SynthSequence(seed=31, n_frames=4, line_heavy=lh)
         small = cvops.half_res(cvops.equalize_hist(seq.frame(1)))
