@@ -131,16 +131,20 @@ enum FeStage {
   FE_STAGE_LINE_FRAMES = FE_STAGE_COUNT /* launches[] only: frames carried by the timed line-path launches (a launch of the
                                            line path carries a batch of frames; ms[] / launches[] of CANNY..FLD_SEG is per launch) */
 };
+/* indices of FeStageTimes.host_ms: wall time of the host-side steps of a single handle */
+enum FeHostStage {
+  FE_HOST_SUBMIT = 0, FE_HOST_DETECTION, FE_HOST_MATCHING, FE_HOST_RANSAC, FE_HOST_LINES, FE_HOST_COLLECT, FE_HOST_LINE_WAIT,
+  FE_HOST_CAND_WAIT /* candidate table */, FE_HOST_SPECULATE /* speculative LK launch */, FE_HOST_ASSEMBLE /* result assembly */,
+  FE_HOST_LINE_ASSIGN /* AssignPointToLines */, FE_HOST_SPEC_LAUNCH, FE_HOST_LK_LAUNCH, FE_HOST_LK_WAIT, FE_HOST_LINE_MATCH,
+  FE_HOST_LINE_ROWS, FE_HOST_COUNT
+};
 typedef struct FeStageTimes {
   double ms[16];
   uint64_t launches[16];
   uint64_t frames;
   uint64_t kernel_launches_total;
   uint64_t h2d_bytes, d2h_bytes;   /* bytes moved by the handle's own cudaMemcpyAsync calls */
-  double host_ms[16];              /* host wall time: [0] submit, [1] detection, [2] matching, [3] ransac, [4] lines,
-                                      [5] collect, [6] line wait, [7] candidate-table wait, [8] speculative LK launch,
-                                      [9] result assembly, [10] AssignPointToLines, [11] speculative launch, [12] LK launch,
-                                      [13] LK wait, [14] LineMatch, [15] line rows */
+  double host_ms[16];              /* host wall time per FeHostStage */
 } FeStageTimes;
 
 /* ---- lifetime ----------------------------------------------------------------------------------------- */

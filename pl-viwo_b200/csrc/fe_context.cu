@@ -736,7 +736,7 @@ int FeContext::submit(double t, const uint8_t *image, int stride, bool on_device
 
 int FeContext::submit_impl(double t, const uint8_t *image, int stride, bool on_device, const uint8_t *mask, int mask_stride,
                            const double vp[6], int *slot_out) {
-  HostTimer ht(&mst_.host_ms[0]);
+  HostTimer ht(&mst_.host_ms[FE_HOST_SUBMIT]);
   FE_CUDA(cudaSetDevice(device_));
   int si = -1;
   for (int i = 0; i < (int)slots_.size(); i++)
@@ -964,7 +964,7 @@ int FeContext::collect(FeFrameInfo *info) {
 }
 
 int FeContext::collect_impl(FeFrameInfo *info) {
-  HostTimer ht(&mst_.host_ms[5]);
+  HostTimer ht(&mst_.host_ms[FE_HOST_COLLECT]);
   FE_CUDA(cudaSetDevice(device_));
   if (queue_.empty()) return err(FE_BAD_ARG, "collect: nothing submitted");
   const int si = queue_.front();
@@ -1168,7 +1168,7 @@ int FeContext::klt_feed(FrameSlot &cur) {
 // of the speculative arrays by index; a point without a speculative result (no next frame was queued yet, or the layout
 // changed) goes through an ordinary launch.  Results are bit-identical either way.
 int FeContext::speculate(FrameSlot &prev, const float2 *lk_pts, const uint8_t *lk_status, int n) {
-  HostTimer hs(&kst_.host_ms[8]);
+  HostTimer hs(&kst_.host_ms[FE_HOST_SPECULATE]);
   spec_of_lk_.assign((size_t)n, -1);
   if (!use_spec_ || cfg_.line_samples > 0) return FE_OK;
   int nxt = -1;
@@ -1192,7 +1192,7 @@ int FeContext::speculate(FrameSlot &prev, const float2 *lk_pts, const uint8_t *l
   spec_n_ = k;
   spec_timed_ = false;
   if (k > 0) {
-    HostTimer h11(&kst_.host_ms[11]);
+    HostTimer h11(&kst_.host_ms[FE_HOST_SPEC_LAUNCH]);
     FE_CUDA(cudaStreamWaitEvent(s_pt_, fn.ev_pyr, 0));
     spec_timed_ = fn.timed;
     if (spec_timed_) cudaEventRecord(ev_pt_[2], s_pt_);
@@ -1308,7 +1308,7 @@ int FeContext::grid_candidates(FrameSlot &slot, const std::vector<uint8_t> &mask
     FE_CUDA(cudaEventRecord(slot.ev_fast, slot.s_b));
   }
   {
-    HostTimer hw(&kst_.host_ms[7]);
+    HostTimer hw(&kst_.host_ms[FE_HOST_CAND_WAIT]);
     int rc = wait_predetection(slot);
     if (rc) return rc;
   }
@@ -1363,7 +1363,7 @@ int FeContext::grid_candidates(FrameSlot &slot, const std::vector<uint8_t> &mask
 int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, std::vector<uint64_t> &ids0, std::vector<int> &src,
                                  FrameResult &res) {
   src.resize(pts0.size(), -1);   // per point: index into the speculative LK arrays, -1 none, -(2 + i) = candidate i
-  HostTimer ht(&kst_.host_ms[1]);
+  HostTimer ht(&kst_.host_ms[FE_HOST_DETECTION]);
   FeFrameInfo *info = &res.info;
   const int d = cfg_.min_px_dist;
   OccGrids g;
@@ -1395,7 +1395,7 @@ int FeContext::perform_detection(const FrameSlot &img, std::vector<Pt> &pts0, st
 
 int FeContext::perform_matching(const FrameSlot &f0, FrameSlot &f1, std::vector<Pt> &pts0, const std::vector<int> &src, bool spec,
                                 std::vector<Pt> &pts1, std::vector<uint8_t> &mask_out, bool &mask_empty, FrameResult &res) {
-  HostTimer ht(&kst_.host_ms[2]);
+  HostTimer ht(&kst_.host_ms[FE_HOST_MATCHING]);
   FeFrameInfo *info = &res.info;
   std::vector<float> &tap_lk_ = res.tap_lk, &sample_uv = res.sample_uv;
   std::vector<uint8_t> &sample_status = res.sample_status;
@@ -1466,7 +1466,7 @@ int FeContext::perform_matching(const FrameSlot &f0, FrameSlot &f1, std::vector<
     kst_.h2d_bytes += (size_t)nt * 2 * sizeof(float2);
     kst_.d2h_bytes += (size_t)nt * (3 * sizeof(float2) + 1);
     if (timing) cudaEventRecord(ev_pt_[4], s_pt_);
-    HostTimer tl(&kst_.host_ms[12]);
+    HostTimer tl(&kst_.host_ms[FE_HOST_LK_LAUNCH]);
     // the LK kernel publishes the completion sequence number itself (its last feature writes the pinned flag)
     const bool self_signal = launch_lk(f0.pyr, f1.pyr, h_pts0_, h_pts1_, h_status_, h_p0n_, h_p1n_, nt, prm, s_pt_, h_flag_lk_,
                                        ++seq_lk_, d_lk_done_);
@@ -1476,7 +1476,7 @@ int FeContext::perform_matching(const FrameSlot &f0, FrameSlot &f1, std::vector<
     FE_CUDA(cudaGetLastError());
   }
   {
-    HostTimer tw(&kst_.host_ms[13]);
+    HostTimer tw(&kst_.host_ms[FE_HOST_LK_WAIT]);
     if (spec_n_ > 0 && wait_flag(&h_flag_lk_[1], seq_sp_, s_pt_, &t_err)) return FE_CUDA_ERROR;
     if (need_b && wait_flag(&f1.h_flags[3], f1.seq_sc, f1.s_b, &t_err)) return FE_CUDA_ERROR;
     if (nt > 0 && wait_flag(h_flag_lk_, seq_lk_, s_pt_, &t_err)) return FE_CUDA_ERROR;
@@ -1491,7 +1491,7 @@ int FeContext::perform_matching(const FrameSlot &f0, FrameSlot &f1, std::vector<
     acc_time(kst_, FE_STAGE_LK, ev_pt_[2], ev_pt_[3]);
   }
   // assemble the per-point results in the reference's order
-  HostTimer *ha = new HostTimer(&kst_.host_ms[9]);
+  HostTimer *ha = new HostTimer(&kst_.host_ms[FE_HOST_ASSEMBLE]);
   if (spec)
     for (int i = 0; i < n; i++) {
       const int k = src[i];
@@ -1532,7 +1532,7 @@ int FeContext::perform_matching(const FrameSlot &f0, FrameSlot &f1, std::vector<
   int mask_valid = 0;
   int n_in;
   {
-    HostTimer hr(&kst_.host_ms[3]);
+    HostTimer hr(&kst_.host_ms[FE_HOST_RANSAC]);
     n_in = ransac_fundamental(reinterpret_cast<const float *>(a_p0n_.data()), reinterpret_cast<const float *>(a_p1n_.data()), n,
                               2.0 / max_focal, 0.999, mask_rsc.data(), &mask_valid);
   }
@@ -1675,7 +1675,7 @@ void line_match_host(const std::vector<std::map<int, double>> &pol_last, const s
 }
 
 int FeContext::lsd_feed(FrameSlot &cur) {
-  HostTimer ht(&lst_.host_ms[4]);
+  HostTimer ht(&lst_.host_ms[FE_HOST_LINES]);
   FrameResult &res = cur.res;
   FeFrameInfo *info = &res.info;
   std::vector<FeLineRow> &line_rows = res.line_rows;
@@ -1683,7 +1683,7 @@ int FeContext::lsd_feed(FrameSlot &cur) {
   std::vector<float> &tap_fld_ = res.tap_fld;
   const bool taps = this->taps.load(std::memory_order_relaxed);
   {
-    HostTimer hw(&lst_.host_ms[6]);
+    HostTimer hw(&lst_.host_ms[FE_HOST_LINE_WAIT]);
     int rc = wait_flag(&cur.h_flags[2], cur.seq_lines, cur.s_line, &t_err);
     if (rc) return rc;
   }
@@ -1716,7 +1716,7 @@ int FeContext::lsd_feed(FrameSlot &cur) {
   std::vector<std::vector<Pt>> positions;
   std::vector<float4> filt_lines;
   std::vector<uint64_t> filt_ids;
-  HostTimer *t_assign = new HostTimer(&lst_.host_ms[10]);
+  HostTimer *t_assign = new HostTimer(&lst_.host_ms[FE_HOST_LINE_ASSIGN]);
   assign_points_to_lines_host(lines_new, ids_new, points, pids, pol_new, positions, filt_lines, filt_ids, sc_px_, sc_py_, sc_pass_);
   delete t_assign;
   if (lines_last_.empty()) {  // first frame / lost (:95-115): no database rows
@@ -1728,10 +1728,10 @@ int FeContext::lsd_feed(FrameSlot &cur) {
   // LineMatch (:368-407)
   std::map<int, int> matches;
   {
-    HostTimer tm(&lst_.host_ms[14]);
+    HostTimer tm(&lst_.host_ms[FE_HOST_LINE_MATCH]);
     line_match_host(pol_last_, pol_new, filt_lines, lines_last_, matches, sc_inv_, sc_shared_, sc_touched_);
   }
-  HostTimer t_rows(&lst_.host_ms[15]);
+  HostTimer t_rows(&lst_.host_ms[FE_HOST_LINE_ROWS]);
   info->n_line_matches = (int)matches.size();
   std::vector<uint64_t> good_ids(filt_lines.size());
   for (size_t i = 0; i < filt_lines.size(); i++) {  // :146-158
