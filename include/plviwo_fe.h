@@ -326,6 +326,9 @@ int plviwo_fe_group_create(const FeConfig *cfg, int n_streams, int device, FeGro
 int plviwo_fe_group_destroy(FeGroupHandle *g);
 const char *plviwo_fe_group_last_error(const FeGroupHandle *g);
 int plviwo_fe_group_set_calib(FeGroupHandle *g, int stream, const double K[4], const double D[4]);
+/* as plviwo_fe_set_camera (CamBase::camera_k_OPENCV / camera_d_OPENCV + the model of the CamBase subclass, cam/CamBase.h:47-60):
+ * FE_CAM_EQUI is refused with FE_BAD_ARG */
+int plviwo_fe_group_set_camera(FeGroupHandle *g, int stream, int model, const double K[4], const double D[4]);
 /* One tick: images[s] = frame of stream s (host or device pointer, NULL: no frame for that stream), timestamps[s] its
  * time; masks = NULL or per-stream host pointers (NULL entries allowed); vps = NULL (line tracker not fed) or 6 doubles per
  * stream.  Device frames are read in place and must stay valid until the tick is collected. */

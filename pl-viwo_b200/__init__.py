@@ -118,7 +118,7 @@ EXPORTS = [
     "plviwo_fe_stereo_set_state", "plviwo_fe_stereo_get_stage_times", "plviwo_fe_stereo_get_line_rows",
     "plviwo_fe_stereo_get_line_points", "plviwo_fe_stereo_classify_lines", "plviwo_op_line_match",
     "plviwo_op_assign_points",
-    "plviwo_fe_group_create", "plviwo_fe_group_destroy", "plviwo_fe_group_last_error", "plviwo_fe_group_set_calib",
+    "plviwo_fe_group_create", "plviwo_fe_group_destroy", "plviwo_fe_group_last_error", "plviwo_fe_group_set_calib", "plviwo_fe_group_set_camera",
     "plviwo_fe_group_submit", "plviwo_fe_group_collect", "plviwo_fe_group_play", "plviwo_fe_group_get_point_rows",
     "plviwo_fe_group_get_last_obs", "plviwo_fe_group_get_line_rows", "plviwo_fe_group_get_line_points",
     "plviwo_fe_group_get_state", "plviwo_fe_group_set_state", "plviwo_fe_group_tap", "plviwo_fe_group_enable_timing",
@@ -207,6 +207,7 @@ def lib() -> C.CDLL:
         L.plviwo_fe_group_create.argtypes = [C.POINTER(FeConfig), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.plviwo_fe_group_destroy.argtypes = [C.c_void_p]
         L.plviwo_fe_group_set_calib.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.plviwo_fe_group_set_camera.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.plviwo_fe_group_submit.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                              C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_double)]
         L.plviwo_fe_group_collect.argtypes = [C.c_void_p, C.POINTER(FeFrameInfo)]
@@ -581,6 +582,10 @@ class GroupFrontEnd:
 
     def set_calib(self, stream: int, K, D):
         self._check(self._lib.plviwo_fe_group_set_calib(self._h, stream, (C.c_double * 4)(*K), (C.c_double * 4)(*D)))
+
+    def set_camera(self, stream: int, model: int, K, D):
+        """Calibration with the camera model stated (0 radtan, 1 equidistant: refused, cam/CamEqui.h is not implemented)."""
+        self._check(self._lib.plviwo_fe_group_set_camera(self._h, stream, model, (C.c_double * 4)(*K), (C.c_double * 4)(*D)))
 
     def submit(self, timestamps, images, stride: int = 0, on_device: bool = False, vanishing_points=None, masks=None):
         """images: per stream a 2-D uint8 array / device pointer (on_device) / None (no frame for that stream in this tick);

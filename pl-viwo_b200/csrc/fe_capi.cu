@@ -807,6 +807,15 @@ int plviwo_fe_group_set_calib(FeGroupHandle *g, int stream, const double K[4], c
   return g->grp->set_calib(stream, K, D);
 }
 
+int plviwo_fe_group_set_camera(FeGroupHandle *g, int stream, int model, const double K[4], const double D[4]) {
+  if (!g) return FE_BAD_ARG;
+  if (model != FE_CAM_RADTAN) {   // as plviwo_fe_set_camera: an equidistant camera is refused, not undistorted with the radtan formula
+    g->grp->last_error = "set_camera: only the radtan model is implemented (cam/CamEqui.h:108-129 is not)";
+    return FE_BAD_ARG;
+  }
+  return g->grp->set_calib(stream, K, D);
+}
+
 int plviwo_fe_group_submit(FeGroupHandle *g, const double *timestamps, const uint8_t *const *images, int stride, int on_device,
                            const uint8_t *const *masks, int mask_stride, const double *vps) {
   API_BEGIN

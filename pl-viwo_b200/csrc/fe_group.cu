@@ -382,6 +382,7 @@ int FeGroup::drain_timing() {
 }
 
 FeGroupTimes FeGroup::times(bool reset) {
+  cudaSetDevice(device_);   // the counter below lives on the group's device (a process may hold groups on several)
   FeGroupTimes t = times_;
   t.kernel_launches_total = launches_;
   t.h2d_bytes = h2d_bytes_;
