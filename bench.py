@@ -57,7 +57,10 @@ def bench_config(world: int) -> dict:
     return {"workload": WORKLOAD_NAME, "streams": N_STREAMS, "gpus": world, "frames_per_step": FRAMES_PER_STEP,
             "frames_per_step_note": "a step = %d frames of every stream" % FRAMES_PER_STEP,
             "stream_to_gpu": "stream s -> rank s mod N, seed 1000 + s", "sequence_frames": SEQ_FRAMES,
-            "sequence_order": "ping-pong", **{k: v for k, v in WORKLOAD.items()}}
+            "sequence_order": "ping-pong",
+            "cache": "inputs larger than L2: %d streams x %d distinct frames x 0.72 MB (2.9 GB per job) are cycled, every frame is read "
+                     "from HBM (GPU arm) / DRAM (reference arm); no L2 flush between steps" % (N_STREAMS, SEQ_FRAMES),
+            **{k: v for k, v in WORKLOAD.items()}}
 
 
 def frame_index(i: int, n: int = SEQ_FRAMES) -> int:
