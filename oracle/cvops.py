@@ -117,6 +117,17 @@ def undistort(pts: np.ndarray, K, D) -> np.ndarray:
     return cv2.undistortPoints(p, Km, Dm).reshape(-1, 2).astype(np.float32)
 
 
+def undistort_equi(pts: np.ndarray, K, D) -> np.ndarray:
+    """CamEqui::undistort_f -> cv::fisheye::undistortPoints(1 point, K, D4) — cam/CamEqui.h:108-129 (one call per point).
+    Not on the product path yet (the library refuses FE_CAM_EQUI): the oracle side of the next camera model."""
+    Km = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]], np.float64)
+    Dm = np.array(D, np.float64)
+    p = np.ascontiguousarray(pts, np.float32).reshape(-1, 1, 2)
+    if len(p) == 0:
+        return p.reshape(-1, 2)
+    return cv2.fisheye.undistortPoints(p, Km, Dm).reshape(-1, 2).astype(np.float32)
+
+
 def find_fundamental_mask(p0n: np.ndarray, p1n: np.ndarray, thr: float):
     """cv::findFundamentalMat(p0, p1, FM_RANSAC, thr, 0.999, mask) — TrackKLT.cpp:873.  Returns the uint8 mask, or an
     empty array when OpenCV returns no model."""

@@ -345,6 +345,39 @@ def lk(img0, img1, pts0, pts1_init, win: int, max_level: int, max_count: int = 3
 
 
 # ---------------------------------------------------------------------------------------------- A6
+def undistort_equi(pts, K, D):
+    """cv::fisheye::undistortPoints (OpenCV 4.x fisheye.cpp), identity R / P, default criteria (10 iterations, eps 1e-8):
+    theta_d = |(x - c) / f| clipped to [-pi/2, pi/2]; Newton on theta (1 + k1 theta^2 + k2 theta^4 + k3 theta^6 + k4 theta^8) =
+    theta_d; the point is pw tan(theta) / theta_d, or (-1e6, -1e6) when the iteration did not converge or theta changed sign.
+    Bit-exact against cv2 4.13 (tests/test_oracle_pins.py)."""
+    p = np.asarray(pts, f32).reshape(-1, 2).astype(np.float64)
+    pwx = (p[:, 0] - K[2]) / K[0]
+    pwy = (p[:, 1] - K[3]) / K[1]
+    theta_d = np.minimum(np.maximum(-np.pi / 2.0, np.sqrt(pwx * pwx + pwy * pwy)), np.pi / 2.0)
+    out = np.zeros_like(p)
+    for i in range(len(p)):
+        td = float(theta_d[i])
+        converged, theta, scale = False, td, 0.0
+        if abs(td) > 1e-8:
+            for _ in range(10):
+                t2 = theta * theta
+                t4 = t2 * t2
+                t6 = t4 * t2
+                t8 = t6 * t2
+                k0, k1, k2, k3 = D[0] * t2, D[1] * t4, D[2] * t6, D[3] * t8
+                fix = (theta * (1 + k0 + k1 + k2 + k3) - td) / (1 + 3 * k0 + 5 * k1 + 7 * k2 + 9 * k3)
+                theta = theta - fix
+                if abs(fix) < 1e-8:
+                    converged = True
+                    break
+            scale = np.tan(theta) / td
+        else:
+            converged = True
+        flipped = (td < 0 and theta > 0) or (td > 0 and theta < 0)
+        out[i] = (pwx[i] * scale, pwy[i] * scale) if (converged and not flipped) else (-1000000.0, -1000000.0)
+    return out.astype(f32)
+
+
 def undistort(pts, K, D):
     """cv::undistortPoints, radtan 4 coefficients: 5 fixed-point iterations in double."""
     p = np.asarray(pts, f32).reshape(-1, 2).astype(np.float64)

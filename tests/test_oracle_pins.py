@@ -109,6 +109,18 @@ def test_lk_close_and_status_equal():
     assert np.abs(g_p[ok] - r_p[ok]).max() < 5e-3
 
 
+def test_undistort_equidistant_restatement_exact():
+    """The next camera model (cam/CamEqui.h:108-129, cv::fisheye::undistortPoints): the NumPy restatement against cv2 on an
+    EuRoC-like calibration, points over the whole image and beyond its border.  (The library refuses FE_CAM_EQUI so far.)"""
+    Ke, De = [458.654, 457.296, 367.215, 248.375], [-0.0348, 0.0123, -0.0071, 0.0021]
+    rng = np.random.default_rng(5)
+    pts = np.stack([rng.uniform(-20, 772, 3000), rng.uniform(-20, 500, 3000)], 1).astype(np.float32)
+    pts[0] = (Ke[2], Ke[3])          # the principal point: theta_d = 0
+    assert np.array_equal(npops.undistort_equi(pts, Ke, De), cvops.undistort_equi(pts, Ke, De))
+    strong = [0.35, -0.6, 0.9, -0.4]  # a strongly distorting lens
+    assert np.array_equal(npops.undistort_equi(pts, Ke, strong), cvops.undistort_equi(pts, Ke, strong))
+
+
 def test_undistort_exact():
     K, D = tuple(GOLD["K"]), tuple(GOLD["D"])
     assert np.array_equal(npops.undistort(GOLD["subpix_out"], K, D), GOLD["und_p0"])
